@@ -1,0 +1,229 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of ``oracle/liboracle.so``, the CPU restatement of the reference's
+(leanEthereum/leanMultisig) hot-path algorithms.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package; the product (``leanmultisig_b200``) never does.
+
+Parity pin status is recorded in ``oracle/oracle.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+P = 0x7F000001
+u32p = C.POINTER(C.c_uint32)
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc only)."""
+    if force or not os.path.exists(_SO):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.lm_or_kb_mul.restype = C.c_uint32
+        _lib.lm_or_kb_from_u32.restype = C.c_uint32
+        _lib.lm_or_kb_to_u32.restype = C.c_uint32
+        _lib.lm_or_kb_inv.restype = C.c_uint32
+        _lib.lm_or_kb_two_adic_generator.restype = C.c_uint32
+        _lib.lm_or_merkle_verify.restype = C.c_int
+        _lib.lm_or_poseidon1_init()
+    return _lib
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u32p)
+
+
+def _u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+# ---------------------------------------------------------------- field helpers
+def to_monty(x) -> np.ndarray:
+    """canonical integers -> Montgomery-form u32 (x * 2^32 mod p)."""
+    x = np.asarray(x, dtype=np.uint64) % P
+    return ((x << np.uint64(32)) % np.uint64(P)).astype(np.uint32)
+
+
+_RINV = pow(1 << 32, -1, P)
+
+
+def from_monty(x) -> np.ndarray:
+    x = np.asarray(x, dtype=np.uint64)
+    return ((x * np.uint64(_RINV)) % np.uint64(P)).astype(np.uint32)
+
+
+def random_field(rng: np.random.Generator, shape) -> np.ndarray:
+    """Uniform Montgomery-form residues in [0, p) (the reference samples the Monty value directly,
+    monty_31.rs:139-149)."""
+    return rng.integers(0, P, size=shape, dtype=np.uint32)
+
+
+def kb_mul(a: int, b: int) -> int:
+    return lib().lm_or_kb_mul(C.c_uint32(a), C.c_uint32(b))
+
+
+def kb_inv(a: int) -> int:
+    return lib().lm_or_kb_inv(C.c_uint32(a))
+
+
+def two_adic_generator(bits: int) -> int:
+    return lib().lm_or_kb_two_adic_generator(C.c_uint32(bits))
+
+
+def ef_mul(a, b) -> np.ndarray:
+    a, b = _u32(a), _u32(b)
+    out = np.empty(5, dtype=np.uint32)
+    lib().lm_or_ef_mul(_p(a), _p(b), _p(out))
+    return out
+
+
+def ef_inv(a) -> np.ndarray:
+    a = _u32(a)
+    out = np.empty(5, dtype=np.uint32)
+    lib().lm_or_ef_inv(_p(a), _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- Poseidon1
+def poseidon1_permute(states, dense: bool = False) -> np.ndarray:
+    s = _u32(states).copy().reshape(-1, 16)
+    lib().lm_or_poseidon1_permute_batch(_p(s), C.c_uint64(s.shape[0]), C.c_int(1 if dense else 0))
+    return s.reshape(np.shape(states))
+
+
+def poseidon1_compress(states) -> np.ndarray:
+    s = _u32(states).copy().reshape(-1, 16)
+    lib().lm_or_poseidon1_compress_batch(_p(s), C.c_uint64(s.shape[0]))
+    return s.reshape(np.shape(states))
+
+
+# ---------------------------------------------------------------- Merkle
+def hash_slice(data) -> np.ndarray:
+    d = _u32(data)
+    out = np.empty(8, dtype=np.uint32)
+    lib().lm_or_hash_slice(_p(d), C.c_uint64(d.size), _p(out))
+    return out
+
+
+def zero_suffix_state(n_zero_chunks: int) -> np.ndarray:
+    out = np.empty(16, dtype=np.uint32)
+    lib().lm_or_zero_suffix_state(C.c_uint32(n_zero_chunks), _p(out))
+    return out
+
+
+def first_digest_layer(mat, full_width: int, effective_width: int) -> np.ndarray:
+    m = _u32(mat)
+    h, w = m.shape
+    out = np.empty((h, 8), dtype=np.uint32)
+    lib().lm_or_first_digest_layer(_p(m), C.c_uint64(h), C.c_uint32(w), C.c_uint32(full_width),
+                                   C.c_uint32(effective_width), _p(out))
+    return out
+
+
+def merkle_tree(mat, full_width: int, effective_width: int) -> np.ndarray:
+    """All digest layers back to back: (2h-1) x 8; root = last row."""
+    m = _u32(mat)
+    h, w = m.shape
+    out = np.empty((2 * h - 1, 8), dtype=np.uint32)
+    lib().lm_or_merkle_tree(_p(m), C.c_uint64(h), C.c_uint32(w), C.c_uint32(full_width),
+                            C.c_uint32(effective_width), _p(out))
+    return out
+
+
+def merkle_open(mat, full_width: int, layers, index: int):
+    m, l = _u32(mat), _u32(layers)
+    h, w = m.shape
+    log_h = h.bit_length() - 1
+    row = np.empty(full_width, dtype=np.uint32)
+    path = np.empty((log_h, 8), dtype=np.uint32)
+    lib().lm_or_merkle_open(_p(m), C.c_uint64(h), C.c_uint32(w), C.c_uint32(full_width), _p(l),
+                            C.c_uint64(index), _p(row), _p(path))
+    return row, path
+
+
+def merkle_verify(root, log_h: int, index: int, row, path) -> bool:
+    root, row, path = _u32(root), _u32(row), _u32(path)
+    return bool(lib().lm_or_merkle_verify(_p(root), C.c_uint32(log_h), C.c_uint64(index), _p(row),
+                                          C.c_uint32(row.size), _p(path)))
+
+
+# ---------------------------------------------------------------- RS encode
+def prepare_evals(evals, n_vars: int, dim: int, folding: int, log_inv_rate: int, dft_n_cols: int) -> np.ndarray:
+    e = _u32(evals)
+    h = 1 << (n_vars + log_inv_rate - folding)
+    out = np.empty((h, dft_n_cols * dim), dtype=np.uint32)
+    lib().lm_or_prepare_evals(_p(e), C.c_uint32(n_vars), C.c_uint32(dim), C.c_uint32(folding),
+                              C.c_uint32(log_inv_rate), C.c_uint32(dft_n_cols), _p(out))
+    return out
+
+
+def dft_batch_by_evals(mat) -> np.ndarray:
+    m = _u32(mat).copy()
+    h, w = m.shape
+    lib().lm_or_dft_batch_by_evals(_p(m), C.c_uint64(h), C.c_uint64(w))
+    return m
+
+
+def reorder_and_dft(evals, n_vars: int, dim: int, folding: int, log_inv_rate: int, dft_n_cols: int) -> np.ndarray:
+    e = _u32(evals)
+    h = 1 << (n_vars + log_inv_rate - folding)
+    out = np.empty((h, dft_n_cols * dim), dtype=np.uint32)
+    lib().lm_or_reorder_and_dft(_p(e), C.c_uint32(n_vars), C.c_uint32(dim), C.c_uint32(folding),
+                                C.c_uint32(log_inv_rate), C.c_uint32(dft_n_cols), _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- multilinear
+def eq_table(point, scalar=None) -> np.ndarray:
+    pt = _u32(point).reshape(-1, 5)
+    k = pt.shape[0]
+    sc = _u32(scalar) if scalar is not None else np.array([to_monty(1), 0, 0, 0, 0], dtype=np.uint32)
+    out = np.empty((1 << k, 5), dtype=np.uint32)
+    lib().lm_or_eq_table(_p(pt), C.c_uint32(k), _p(sc), _p(out))
+    return out
+
+
+def expand_from_univariate(y, n: int) -> np.ndarray:
+    y = _u32(y)
+    out = np.empty((n, 5), dtype=np.uint32)
+    lib().lm_or_expand_from_univariate(_p(y), C.c_uint32(n), _p(out))
+    return out
+
+
+def mle_eval(evals, point) -> np.ndarray:
+    e = _u32(evals)
+    pt = _u32(point).reshape(-1, 5)
+    n = pt.shape[0]
+    dim = 5 if (e.ndim == 2 and e.shape[1] == 5) else 1
+    assert e.size == (1 << n) * dim
+    out = np.empty(5, dtype=np.uint32)
+    lib().lm_or_mle_eval(_p(e), C.c_uint32(n), C.c_uint32(dim), _p(pt), _p(out))
+    return out
+
+
+def fold_msb(evals, r) -> np.ndarray:
+    e, r = _u32(evals), _u32(r)
+    dim = 5 if (e.ndim == 2 and e.shape[1] == 5) else 1
+    n = e.size // dim
+    out = np.empty((n // 2, 5), dtype=np.uint32)
+    lib().lm_or_fold_msb(_p(e), C.c_uint64(n), C.c_uint32(dim), _p(r), _p(out))
+    return out

@@ -1,0 +1,71 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY (see kb.h).
+ *
+ * Reed-Solomon encode of the stacked multilinear witness: block gather followed
+ * by the radix-2 "DFT on evaluations".
+ *   reference: crates/whir/src/utils.rs:69-150  reorder_and_dft, prepare_evals_for_fft_unpacked
+ *              crates/whir/src/dft.rs:52-62     roots_of_unity_table
+ *              crates/whir/src/dft.rs:79-144    dft_batch_by_evals (layer order: half-block 1,2,4,...,h/2)
+ *              crates/whir/src/dft.rs:546-568   butterflies (a,b) -> (a + t(b-a), a - t(b-a))
+ *              crates/whir/src/dft.rs:147-155   EF matrix = 5x wider base matrix
+ * The reference groups layers (L1-sized initial chunk, then 3 per pass) purely for
+ * cache reasons; the arithmetic is the plain layer-by-layer network below.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "kb.h"
+#include "oracle.h"
+
+/* utils.rs:128-150.  evals: 2^n_vars elements of `dim` u32 each (dim = 1 base, 5 extension).
+ * out: (2^(n_vars + log_inv_rate - folding)) rows x dft_n_cols elements. */
+void lm_or_prepare_evals(const uint32_t *evals, uint32_t n_vars, uint32_t dim, uint32_t folding_factor,
+                         uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t *out) {
+  uint64_t full_len = ((uint64_t)1 << n_vars) << log_inv_rate;
+  uint64_t block_size = full_len >> folding_factor;
+  uint32_t log_block = n_vars + log_inv_rate - folding_factor;
+  uint64_t out_len = block_size * dft_n_cols;
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = 0; i < out_len; i++) {
+    uint64_t block_index = i % dft_n_cols;
+    uint64_t offset_in_block = i / dft_n_cols;
+    uint64_t src = ((block_index << log_block) + offset_in_block) >> log_inv_rate;
+    for (uint32_t d = 0; d < dim; d++) out[i * dim + d] = evals[src * dim + d];
+  }
+}
+
+/* dft.rs:79-144 on an h x w base-field matrix, in place. */
+void lm_or_dft_batch_by_evals(uint32_t *mat, uint64_t h, uint64_t w) {
+  if (h < 2) return;
+  unsigned log_h = 0;
+  while (((uint64_t)1 << log_h) < h) log_h++;
+  /* nth_roots = 1, g, g^2, ..., g^(h/2-1);  layer with half-block m uses stride h/(2m) */
+  kb_t g = kb_two_adic_generator(log_h);
+  kb_t *roots = (kb_t *)malloc((h / 2) * sizeof(kb_t));
+  roots[0] = KB_ONE;
+  for (uint64_t i = 1; i < h / 2; i++) roots[i] = kb_mul(roots[i - 1], g);
+  for (uint64_t m = 1; m < h; m <<= 1) {
+    uint64_t stride = h / (2 * m);
+#pragma omp parallel for schedule(static)
+    for (uint64_t pair = 0; pair < h / 2; pair++) {
+      uint64_t blk = pair / m, i = pair % m;
+      uint32_t *lo = mat + (blk * 2 * m + i) * w;
+      uint32_t *hi = lo + m * w;
+      kb_t t = roots[i * stride];
+      for (uint64_t c = 0; c < w; c++) {
+        kb_t a = lo[c], b = hi[c];
+        kb_t x = kb_mul(kb_sub(b, a), t);
+        lo[c] = kb_add(a, x);
+        hi[c] = kb_sub(a, x);
+      }
+    }
+  }
+  free(roots);
+}
+
+/* utils.rs:69-95: gather + DFT.  Output matrix has 2^(n_vars+log_inv_rate-folding) rows
+ * and dft_n_cols * dim base columns. */
+void lm_or_reorder_and_dft(const uint32_t *evals, uint32_t n_vars, uint32_t dim, uint32_t folding_factor,
+                           uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t *out) {
+  lm_or_prepare_evals(evals, n_vars, dim, folding_factor, log_inv_rate, dft_n_cols, out);
+  uint64_t h = (uint64_t)1 << (n_vars + log_inv_rate - folding_factor);
+  lm_or_dft_batch_by_evals(out, h, (uint64_t)dft_n_cols * dim);
+}
