@@ -1,0 +1,114 @@
+/* leanmultisig_b200 — C ABI of the B200-native proving hot path for leanEthereum/leanMultisig.
+ *
+ * Every entry point replaces one call site of the reference's Rust prover (the reference has no FFI of its own;
+ * INTEGRATION.md shows the Rust `extern "C"` block and the three-line patch per call site).  Conventions:
+ *   - field element  F  = u32 in Montgomery form, canonical in [0, p), p = 2^31 - 2^24 + 1
+ *                        (crates/backend/koala-bear/src/monty_31/monty_31.rs:32-42)
+ *   - extension      EF = 5 consecutive F, coefficient of X^0 first, F[X]/(X^5 + X^2 - 1)
+ *                        (crates/backend/koala-bear/src/quintic_extension/extension.rs:26-36)
+ *   - digest            = 8 F (crates/backend/symetric/src/merkle.rs:11)
+ *   - multilinear index = variable x_0 is the most-significant bit (crates/backend/poly/src/evals.rs:219)
+ *   - every function returns LM_OK (0) or a negative status and never unwinds; lm_last_error() gives the text.
+ *     The reference panics on violated preconditions; the Rust shim turns a non-zero status into a panic.
+ *   - host pointers are borrowed for the duration of the call only; results either go to caller-allocated
+ *     buffers or stay on the device behind an opaque handle with an explicit *_free.
+ *   - calls on one lm_ctx are serialised by the caller (the prover drives them from the thread that owns the
+ *     Fiat-Shamir transcript, crates/backend/fiat-shamir/src/traits.rs:15-44); each call is synchronous with
+ *     respect to its host-visible outputs.  lm_dev_* calls only enqueue on the context's stream.
+ */
+#ifndef LEANMULTISIG_B200_H
+#define LEANMULTISIG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_OK 0
+#define LM_ERR_INVALID (-1)   /* violated precondition (the reference would panic) */
+#define LM_ERR_CUDA (-2)      /* CUDA runtime failure, see lm_last_error() */
+#define LM_ERR_NO_DEVICE (-3) /* no CUDA device: there is no CPU fallback */
+#define LM_ERR_OOM (-4)
+
+#define LM_DIGEST_ELEMS 8
+
+typedef struct lm_ctx lm_ctx;   /* one per GPU: stream, twiddle table, scratch arena */
+typedef struct lm_tree lm_tree; /* committed matrix + all Merkle layers (+ the polynomial), device resident */
+
+const char* lm_last_error(void);
+int lm_device_count(void);
+
+/* Replaces setup_prover / precompute_dft_twiddles (src/lib.rs:13-16, crates/whir/src/utils.rs:200-202) and the
+ * OnceLock Poseidon constants (poseidon1_koalabear_16.rs:575): selects `device`, creates a stream and uploads
+ * the twiddle table for transforms of up to 2^max_log_domain rows (<= 24). */
+int lm_init(int device, uint32_t max_log_domain, lm_ctx** out_ctx);
+int lm_destroy(lm_ctx* ctx);
+/* Run subsequent work on an existing CUDA stream (cudaStream_t passed as void*); NULL restores the own stream. */
+int lm_set_stream(lm_ctx* ctx, void* cuda_stream);
+int lm_sync(lm_ctx* ctx);
+/* Pin / unpin a caller-owned host buffer so that commits read it at full PCIe rate (cudaHostRegister). */
+int lm_host_register(void* ptr, size_t bytes);
+int lm_host_unregister(void* ptr);
+
+/* ---- WHIR commit: crates/whir/src/commit.rs:64-85 (reorder_and_dft + MerkleData::build) -------------------
+ * evals: 2^n_vars elements of elem_dim words (1 = base field, 5 = extension), entries >= actual_len are zero
+ * (only the first actual_len are read).  Builds the Reed-Solomon codeword matrix of
+ * 2^(n_vars + log_inv_rate - folding_factor) rows x 2^folding_factor columns (columns that are entirely zero
+ * are not stored, commit.rs:70-74), hashes every row with the Poseidon1 sponge and builds the Merkle tree.
+ * out_root receives the root; the handle owns codeword, digest layers and a device copy of the live evals. */
+int lm_commit(lm_ctx* ctx, const uint32_t* evals, uint32_t n_vars, uint32_t elem_dim, uint64_t actual_len,
+              uint32_t folding_factor, uint32_t log_inv_rate, lm_tree** out_tree, uint32_t out_root[8]);
+/* Same, evals already resident on this context's device (e.g. the output of an on-device fold). */
+int lm_commit_dev(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_t elem_dim, uint64_t actual_len,
+                  uint32_t folding_factor, uint32_t log_inv_rate, int retain_evals, lm_tree** out_tree,
+                  uint32_t out_root[8]);
+/* MerkleData::open (crates/whir/src/commit.rs:34-45 -> crates/whir/src/merkle.rs:205-211): for each index the
+ * full row zero-extended to full width (n x full_width words) and the sibling path, leaf level first
+ * (n x log2(height) x 8 words). */
+int lm_open(lm_tree* tree, const uint64_t* indices, uint32_t n, uint32_t* out_rows, uint32_t* out_paths);
+/* height (rows), full row width in words, stored row width in words, elem_dim */
+int lm_tree_shape(const lm_tree* tree, uint64_t* height, uint32_t* full_width, uint32_t* stored_width,
+                  uint32_t* elem_dim);
+/* Out-of-domain sample: polynomial.evaluate(point) on the committed polynomial (commit.rs:89-92,
+ * crates/backend/poly/src/evals.rs:142).  point: n_vars x 5 words; out: 5 words. */
+int lm_tree_eval(lm_tree* tree, const uint32_t* point, uint32_t out[5]);
+/* Copy device-resident pieces back (parity tests, debugging): codeword matrix height x stored_width and the
+ * digest layers (2*height - 1) x 8, leaf layer first. */
+int lm_tree_read_codeword(lm_tree* tree, uint32_t* out);
+int lm_tree_read_layers(lm_tree* tree, uint32_t* out);
+int lm_tree_free(lm_tree* tree);
+
+/* MleRef::evaluate on a host polynomial (crates/backend/poly/src/evals.rs:142-347): evals has 2^n_vars
+ * elements of elem_dim words of which the first live_len may be non-zero. */
+int lm_mle_eval(lm_ctx* ctx, const uint32_t* evals, uint32_t n_vars, uint32_t elem_dim, uint64_t live_len,
+                const uint32_t* point, uint32_t out[5]);
+
+/* ---- device-pointer layer (inputs already in HBM; used by the kernel-only benchmark and by lm_* above) -----
+ * All pointers are device pointers on ctx's device; work is enqueued on ctx's stream, no synchronisation. */
+int lm_dev_alloc(lm_ctx* ctx, size_t bytes, void** out);
+int lm_dev_free(lm_ctx* ctx, void* ptr);
+int lm_dev_upload(lm_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);   /* synchronous */
+int lm_dev_download(lm_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* synchronous */
+/* Poseidon1KoalaBear16::permute / compress_in_place on n 16-word states (poseidon1_koalabear_16.rs:873,1020) */
+int lm_dev_poseidon1(lm_ctx* ctx, uint32_t* d_states, uint64_t n, int compress);
+/* reorder_and_dft (crates/whir/src/utils.rs:69): d_out = 2^(n_vars+log_inv_rate-folding) x (dft_n_cols*dim) */
+int lm_dev_reorder_and_dft(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_t elem_dim,
+                           uint32_t folding_factor, uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out);
+/* EvalsDft::dft_batch_by_evals (crates/whir/src/dft.rs:79), in place on a height x width matrix */
+int lm_dev_dft(lm_ctx* ctx, uint32_t* d_mat, uint64_t height, uint64_t width);
+/* build_merkle_tree_koalabear (crates/whir/src/merkle.rs:59-88): d_layers = (2*height - 1) x 8 words */
+int lm_dev_merkle_tree(lm_ctx* ctx, const uint32_t* d_mat, uint64_t height, uint32_t stored_width,
+                       uint32_t full_width, uint32_t effective_width, uint32_t* d_layers);
+/* eval_multilinear (evals.rs:142) with device-resident evals and point; d_out: 5 words */
+int lm_dev_mle_eval(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_t elem_dim, uint64_t live_len,
+                    const uint32_t* d_point, uint32_t* d_out);
+/* fold_multilinear (crates/backend/poly/src/utils.rs:161-186): d_out = n_in/2 EF */
+int lm_dev_fold_msb(lm_ctx* ctx, const uint32_t* d_in, uint64_t n_in, uint32_t elem_dim, const uint32_t r[5],
+                    uint32_t* d_out);
+/* eval_eq_scaled (crates/backend/poly/src/eq_mle.rs:20-26): d_out = 2^k EF; point is a HOST pointer (k x 5) */
+int lm_dev_eq_table(lm_ctx* ctx, const uint32_t* point, uint32_t k, const uint32_t scalar[5], uint32_t* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

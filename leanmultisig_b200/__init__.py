@@ -1,0 +1,11 @@
+"""leanmultisig_b200 — B200-native proving hot path for leanEthereum/leanMultisig.
+
+The product is the CUDA library behind ``include/leanmultisig_b200.h`` (``csrc/``).  This package is the thin
+Python host side used by the tests and the benchmark: it mirrors the reference's call sites
+(``WhirConfig::commit``, ``MerkleData::open``, ``MleRef::evaluate`` ...) one to one on top of the C ABI and
+holds no arithmetic of its own.
+"""
+from ._lib import LIB_PATH, LmError, build, declared_symbols, lib  # noqa: F401
+from .whir import Context, DeviceBuffer, Tree  # noqa: F401
+
+__all__ = ["Context", "DeviceBuffer", "Tree", "LmError", "build", "lib", "declared_symbols", "LIB_PATH"]

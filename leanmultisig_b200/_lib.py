@@ -1,0 +1,93 @@
+"""ctypes loader for the C-ABI shared library (include/leanmultisig_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc (csrc/Makefile), and if that is
+impossible, or no CUDA device is visible when a context is created, the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libleanmultisig_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "leanmultisig_b200.h")
+
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+
+class LmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"leanmultisig_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into lib/libleanmultisig_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j4"] + (["-B"] if force else [])
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def declared_symbols() -> list[str]:
+    """Every function the public header declares (used by the CPU-side export test)."""
+    txt = open(HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lm_[a-z0-9_]+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing and could not be built; the CUDA extension is required")
+        L = C.CDLL(LIB_PATH)
+        L.lm_last_error.restype = C.c_char_p
+        vp, sz, u32, u64, i = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
+        sig = {
+            "lm_device_count": [],
+            "lm_init": [i, u32, C.POINTER(vp)],
+            "lm_destroy": [vp],
+            "lm_set_stream": [vp, vp],
+            "lm_sync": [vp],
+            "lm_host_register": [vp, sz],
+            "lm_host_unregister": [vp],
+            "lm_commit": [vp, vp, u32, u32, u64, u32, u32, C.POINTER(vp), u32p],
+            "lm_commit_dev": [vp, vp, u32, u32, u64, u32, u32, i, C.POINTER(vp), u32p],
+            "lm_open": [vp, u64p, u32, u32p, u32p],
+            "lm_tree_shape": [vp, u64p, u32p, u32p, u32p],
+            "lm_tree_eval": [vp, u32p, u32p],
+            "lm_tree_read_codeword": [vp, u32p],
+            "lm_tree_read_layers": [vp, u32p],
+            "lm_tree_free": [vp],
+            "lm_mle_eval": [vp, vp, u32, u32, u64, u32p, u32p],
+            "lm_dev_alloc": [vp, sz, C.POINTER(vp)],
+            "lm_dev_free": [vp, vp],
+            "lm_dev_upload": [vp, vp, vp, sz],
+            "lm_dev_download": [vp, vp, vp, sz],
+            "lm_dev_poseidon1": [vp, vp, u64, i],
+            "lm_dev_reorder_and_dft": [vp, vp, u32, u32, u32, u32, u32, vp],
+            "lm_dev_dft": [vp, vp, u64, u64],
+            "lm_dev_merkle_tree": [vp, vp, u64, u32, u32, u32, vp],
+            "lm_dev_mle_eval": [vp, vp, u32, u32, u64, vp, vp],
+            "lm_dev_fold_msb": [vp, vp, u64, u32, u32p, vp],
+            "lm_dev_eq_table": [vp, u32p, u32, u32p, vp],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise LmError(rc, lib().lm_last_error().decode())

@@ -1,0 +1,453 @@
+// extern "C" boundary of libleanmultisig_b200.so — see include/leanmultisig_b200.h for the contract and the
+// reference call site each entry point replaces.  Host-side logic only: shape derivation that mirrors
+// WhirConfig::commit (crates/whir/src/commit.rs:64-85), device memory ownership, stream plumbing.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/leanmultisig_b200.h"
+#include "merkle.h"
+#include "ntt.h"
+#include "poly.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  if (e == cudaErrorMemoryAllocation) return fail(LM_ERR_OOM, "%s: %s", what, cudaGetErrorString(e));
+  return fail(LM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+}  // namespace
+
+struct lm_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  uint32_t* d_tw = nullptr;
+  unsigned tw_log_n = 0;
+  uint32_t* d_scratch = nullptr;  // grows on demand (MLE evaluation tables)
+  size_t scratch_words = 0;
+  uint32_t* d_small = nullptr;  // 64 words: points / results of host-facing calls
+  uint32_t* d_point = nullptr;  // up to 64 x 5 words
+
+  int ensure_scratch(size_t words) {
+    if (words <= scratch_words) return LM_OK;
+    if (d_scratch) cudaFree(d_scratch);
+    d_scratch = nullptr;
+    scratch_words = 0;
+    CU(cudaMalloc(&d_scratch, words * sizeof(uint32_t)));
+    scratch_words = words;
+    return LM_OK;
+  }
+};
+
+struct lm_tree {
+  lm_ctx* ctx = nullptr;
+  uint32_t n_vars = 0, elem_dim = 1;
+  uint64_t actual_len = 0;  // in elements
+  uint64_t height = 0;
+  uint32_t full_width = 0, stored_width = 0, effective_width = 0;  // in words
+  uint32_t* d_evals = nullptr;     // live prefix of the polynomial (actual_len * elem_dim words) or null
+  bool owns_evals = false;
+  uint32_t* d_codeword = nullptr;  // height x stored_width
+  uint32_t* d_layers = nullptr;    // (2 height - 1) x 8
+};
+
+extern "C" {
+
+const char* lm_last_error(void) { return g_err; }
+
+int lm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int lm_init(int device, uint32_t max_log_domain, lm_ctx** out_ctx) {
+  if (!out_ctx) return fail(LM_ERR_INVALID, "lm_init: out_ctx is null");
+  *out_ctx = nullptr;
+  if (max_log_domain > 24) return fail(LM_ERR_INVALID, "lm_init: KoalaBear two-adicity is 24, got %u", max_log_domain);
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    return fail(LM_ERR_NO_DEVICE, "lm_init: no CUDA device visible; this library has no CPU path");
+  if (device < 0 || device >= n) return fail(LM_ERR_INVALID, "lm_init: device %d out of range (%d visible)", device, n);
+  CU(cudaSetDevice(device));
+  lm_ctx* c = new (std::nothrow) lm_ctx();
+  if (!c) return fail(LM_ERR_OOM, "lm_init: host allocation failed");
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  c->tw_log_n = max_log_domain;
+  if (max_log_domain > 0) {
+    CU(cudaMalloc(&c->d_tw, sizeof(uint32_t) << (max_log_domain - 1)));
+    CU(lm::ntt_fill_twiddles(c->stream, c->d_tw, max_log_domain));
+  }
+  CU(cudaMalloc(&c->d_small, 64 * sizeof(uint32_t)));
+  CU(cudaMalloc(&c->d_point, 64 * 5 * sizeof(uint32_t)));
+  CU(cudaStreamSynchronize(c->stream));
+  *out_ctx = c;
+  return LM_OK;
+}
+
+int lm_destroy(lm_ctx* c) {
+  if (!c) return LM_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->d_tw) cudaFree(c->d_tw);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->d_small) cudaFree(c->d_small);
+  if (c->d_point) cudaFree(c->d_point);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return LM_OK;
+}
+
+int lm_set_stream(lm_ctx* c, void* s) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_set_stream: ctx is null");
+  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+  return LM_OK;
+}
+
+int lm_sync(lm_ctx* c) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_sync: ctx is null");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_host_register(void* ptr, size_t bytes) {
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return LM_OK;
+}
+int lm_host_unregister(void* ptr) {
+  CU(cudaHostUnregister(ptr));
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ device layer
+int lm_dev_alloc(lm_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) return fail(LM_ERR_INVALID, "lm_dev_alloc: null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(out, bytes ? bytes : 1));
+  return LM_OK;
+}
+int lm_dev_free(lm_ctx* c, void* p) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_free: ctx is null");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaFree(p));
+  return LM_OK;
+}
+int lm_dev_upload(lm_ctx* c, void* d, const void* h, size_t bytes) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_upload: ctx is null");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+int lm_dev_download(lm_ctx* c, void* h, const void* d, size_t bytes) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_download: ctx is null");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_dev_poseidon1(lm_ctx* c, uint32_t* d_states, uint64_t n, int compress) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_poseidon1: ctx is null");
+  CU(cudaSetDevice(c->device));
+  CU(lm::poseidon1_states(c->stream, d_states, n, compress));
+  return LM_OK;
+}
+
+int lm_dev_reorder_and_dft(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint32_t folding,
+                           uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft: ctx is null");
+  if (dim != 1 && dim != 5) return fail(LM_ERR_INVALID, "elem_dim must be 1 or 5, got %u", dim);
+  if (folding > n_vars) return fail(LM_ERR_INVALID, "folding_factor %u > n_vars %u", folding, n_vars);
+  if (dft_n_cols > (1u << folding)) return fail(LM_ERR_INVALID, "dft_n_cols %u > 2^folding", dft_n_cols);
+  if (n_vars + log_inv_rate - folding > c->tw_log_n)
+    return fail(LM_ERR_INVALID, "domain 2^%u exceeds the twiddle table 2^%u given to lm_init",
+                n_vars + log_inv_rate - folding, c->tw_log_n);
+  CU(cudaSetDevice(c->device));
+  CU(lm::ntt_reorder_and_dft(c->stream, d_evals, n_vars, dim, folding, log_inv_rate, dft_n_cols, d_out, c->d_tw,
+                             c->tw_log_n));
+  return LM_OK;
+}
+
+int lm_dev_dft(lm_ctx* c, uint32_t* d_mat, uint64_t h, uint64_t w) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_dft: ctx is null");
+  if (h == 0 || (h & (h - 1))) return fail(LM_ERR_INVALID, "lm_dev_dft: height %llu is not a power of two", (unsigned long long)h);
+  if (h > ((uint64_t)1 << c->tw_log_n)) return fail(LM_ERR_INVALID, "lm_dev_dft: height exceeds the twiddle table");
+  CU(cudaSetDevice(c->device));
+  CU(lm::ntt_dft_batch_by_evals(c->stream, d_mat, h, w, 0, c->d_tw, c->tw_log_n));
+  return LM_OK;
+}
+
+int lm_dev_merkle_tree(lm_ctx* c, const uint32_t* d_mat, uint64_t h, uint32_t stored_w, uint32_t full_w,
+                       uint32_t eff_w, uint32_t* d_layers) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_merkle_tree: ctx is null");
+  if (h == 0 || (h & (h - 1))) return fail(LM_ERR_INVALID, "merkle: height %llu is not a power of two", (unsigned long long)h);
+  if (full_w % 8 || full_w < 16 || eff_w > full_w || stored_w > full_w)
+    return fail(LM_ERR_INVALID, "merkle: widths full=%u stored=%u effective=%u", full_w, stored_w, eff_w);
+  CU(cudaSetDevice(c->device));
+  CU(lm::merkle_leaf_digests(c->stream, d_mat, h, stored_w, full_w, eff_w, d_layers));
+  CU(lm::merkle_tree_from_digests(c->stream, d_layers, h));
+  return LM_OK;
+}
+
+int lm_dev_mle_eval(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint64_t live_len,
+                    const uint32_t* d_point, uint32_t* d_out) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_mle_eval: ctx is null");
+  if (dim != 1 && dim != 5) return fail(LM_ERR_INVALID, "elem_dim must be 1 or 5, got %u", dim);
+  if (n_vars > 34) return fail(LM_ERR_INVALID, "n_vars %u too large", n_vars);
+  CU(cudaSetDevice(c->device));
+  int rc = c->ensure_scratch(lm::mle_eval_scratch_words(n_vars));
+  if (rc != LM_OK) return rc;
+  CU(lm::mle_eval(c->stream, d_evals, n_vars, dim, live_len, d_point, c->d_scratch, d_out));
+  return LM_OK;
+}
+
+int lm_dev_fold_msb(lm_ctx* c, const uint32_t* d_in, uint64_t n_in, uint32_t dim, const uint32_t r[5], uint32_t* d_out) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_fold_msb: ctx is null");
+  if (n_in < 2 || (n_in & (n_in - 1))) return fail(LM_ERR_INVALID, "fold: length must be a power of two >= 2");
+  CU(cudaSetDevice(c->device));
+  CU(lm::fold_msb(c->stream, d_in, n_in, dim, r, d_out));
+  return LM_OK;
+}
+
+int lm_dev_eq_table(lm_ctx* c, const uint32_t* point, uint32_t k, const uint32_t scalar[5], uint32_t* d_out) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_eq_table: ctx is null");
+  if (k > 64) return fail(LM_ERR_INVALID, "eq table: k = %u too large", k);
+  CU(cudaSetDevice(c->device));
+  if (k) CU(cudaMemcpyAsync(c->d_point, point, (size_t)k * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(lm::eq_table(c->stream, c->d_point, (int)k, scalar, d_out));
+  CU(cudaStreamSynchronize(c->stream));  // c->d_point is reused by the next call
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ commit / open
+static int commit_impl(lm_ctx* c, const uint32_t* evals, bool evals_on_device, uint32_t n_vars, uint32_t dim,
+                       uint64_t actual_len, uint32_t folding, uint32_t log_inv_rate, bool retain_evals,
+                       lm_tree** out_tree, uint32_t out_root[8]) {
+  if (!c || !out_tree || !out_root) return fail(LM_ERR_INVALID, "lm_commit: null argument");
+  *out_tree = nullptr;
+  if (dim != 1 && dim != 5) return fail(LM_ERR_INVALID, "lm_commit: elem_dim must be 1 or 5, got %u", dim);
+  if (n_vars > 32) return fail(LM_ERR_INVALID, "lm_commit: n_vars %u too large", n_vars);
+  if (folding > n_vars) return fail(LM_ERR_INVALID, "lm_commit: folding_factor %u > n_vars %u", folding, n_vars);
+  if (folding < 1) return fail(LM_ERR_INVALID, "lm_commit: folding_factor must be >= 1 (leaf width >= 16 words)");
+  const uint64_t evals_len = (uint64_t)1 << n_vars;
+  if (actual_len > evals_len) return fail(LM_ERR_INVALID, "lm_commit: actual_len exceeds 2^n_vars");
+  const uint32_t log_h = n_vars + log_inv_rate - folding;
+  if (log_h > c->tw_log_n)
+    return fail(LM_ERR_INVALID, "lm_commit: domain 2^%u exceeds the twiddle table 2^%u given to lm_init", log_h, c->tw_log_n);
+  // commit.rs:68-74: number of column blocks that hold data
+  const uint64_t n_blocks = (uint64_t)1 << folding;
+  const uint64_t block_len = evals_len / n_blocks;
+  uint64_t eff_cols = (actual_len + block_len - 1) / block_len;
+  // stored width: whole columns, rounded up so that rows stay 16-byte aligned (any width >= eff_cols gives the
+  // same root and openings, merkle.rs:205-211,251-288)
+  uint64_t dft_cols = eff_cols;
+  while ((dft_cols * dim) % 4 != 0 && dft_cols < n_blocks) dft_cols++;
+  if (dft_cols == 0) dft_cols = (dim == 1) ? 4 : 4;
+  if (dft_cols > n_blocks) dft_cols = n_blocks;
+  const uint32_t full_w = (uint32_t)(n_blocks * dim);
+  if (full_w % 8 != 0 || full_w < 16)
+    return fail(LM_ERR_INVALID, "lm_commit: full leaf width %u must be a multiple of 8 and >= 16", full_w);
+
+  CU(cudaSetDevice(c->device));
+  lm_tree* t = new (std::nothrow) lm_tree();
+  if (!t) return fail(LM_ERR_OOM, "lm_commit: host allocation failed");
+  t->ctx = c;
+  t->n_vars = n_vars;
+  t->elem_dim = dim;
+  t->actual_len = actual_len;
+  t->height = (uint64_t)1 << log_h;
+  t->full_width = full_w;
+  t->stored_width = (uint32_t)(dft_cols * dim);
+  t->effective_width = (uint32_t)(eff_cols * dim);
+  auto cleanup = [&](int rc) {
+    lm_tree_free(t);
+    return rc;
+  };
+#define CUT(call)                                                      \
+  do {                                                                 \
+    cudaError_t e__ = (call);                                          \
+    if (e__ != cudaSuccess) return cleanup(cuda_fail(e__, #call));     \
+  } while (0)
+
+  // the gather reads whole columns: dft_cols * block_len elements (zero beyond actual_len)
+  // ... and lm_tree_eval reads the live prefix in rows of min(2^n_vars, 1024) elements
+  uint64_t need_len = dft_cols * block_len;
+  const uint64_t eval_row = evals_len < 1024 ? evals_len : 1024;
+  const uint64_t eval_len = (actual_len + eval_row - 1) / eval_row * eval_row;
+  if (eval_len > need_len) need_len = eval_len;
+  const uint64_t need_words = need_len * dim, live_words = actual_len * dim;
+  const uint32_t* d_src = nullptr;
+  if (evals_on_device && !retain_evals) {
+    d_src = evals;  // caller guarantees 2^n_vars elements are addressable
+  } else {
+    CUT(cudaMalloc(&t->d_evals, (need_words ? need_words : 1) * sizeof(uint32_t)));
+    t->owns_evals = true;
+    if (live_words)
+      CUT(cudaMemcpyAsync(t->d_evals, evals, live_words * sizeof(uint32_t),
+                          evals_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (need_words > live_words)
+      CUT(cudaMemsetAsync(t->d_evals + live_words, 0, (need_words - live_words) * sizeof(uint32_t), c->stream));
+    d_src = t->d_evals;
+  }
+  CUT(cudaMalloc(&t->d_codeword, t->height * t->stored_width * sizeof(uint32_t)));
+  CUT(cudaMalloc(&t->d_layers, (2 * t->height - 1) * 8 * sizeof(uint32_t)));
+  CUT(lm::ntt_reorder_and_dft(c->stream, d_src, n_vars, dim, folding, log_inv_rate, (uint32_t)dft_cols, t->d_codeword,
+                              c->d_tw, c->tw_log_n));
+  CUT(lm::merkle_leaf_digests(c->stream, t->d_codeword, t->height, t->stored_width, t->full_width, t->effective_width,
+                              t->d_layers));
+  CUT(lm::merkle_tree_from_digests(c->stream, t->d_layers, t->height));
+  CUT(cudaMemcpyAsync(out_root, t->d_layers + (2 * t->height - 2) * 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                      c->stream));
+  CUT(cudaStreamSynchronize(c->stream));
+#undef CUT
+  *out_tree = t;
+  return LM_OK;
+}
+
+int lm_commit(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, uint64_t actual_len, uint32_t folding,
+              uint32_t log_inv_rate, lm_tree** out_tree, uint32_t out_root[8]) {
+  if (!evals && actual_len) return fail(LM_ERR_INVALID, "lm_commit: evals is null");
+  return commit_impl(c, evals, false, n_vars, dim, actual_len, folding, log_inv_rate, true, out_tree, out_root);
+}
+
+int lm_commit_dev(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint64_t actual_len,
+                  uint32_t folding, uint32_t log_inv_rate, int retain_evals, lm_tree** out_tree, uint32_t out_root[8]) {
+  if (!d_evals) return fail(LM_ERR_INVALID, "lm_commit_dev: d_evals is null");
+  return commit_impl(c, d_evals, true, n_vars, dim, actual_len, folding, log_inv_rate, retain_evals != 0, out_tree,
+                     out_root);
+}
+
+int lm_tree_shape(const lm_tree* t, uint64_t* height, uint32_t* full_w, uint32_t* stored_w, uint32_t* dim) {
+  if (!t) return fail(LM_ERR_INVALID, "lm_tree_shape: tree is null");
+  if (height) *height = t->height;
+  if (full_w) *full_w = t->full_width;
+  if (stored_w) *stored_w = t->stored_width;
+  if (dim) *dim = t->elem_dim;
+  return LM_OK;
+}
+
+int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows, uint32_t* out_paths) {
+  if (!t || (n && (!indices || !out_rows || !out_paths))) return fail(LM_ERR_INVALID, "lm_open: null argument");
+  lm_ctx* c = t->ctx;
+  CU(cudaSetDevice(c->device));
+  uint32_t log_h = 0;
+  while (((uint64_t)1 << log_h) < t->height) log_h++;
+  for (uint32_t q = 0; q < n; q++)
+    if (indices[q] >= t->height) return fail(LM_ERR_INVALID, "lm_open: index %llu >= height %llu",
+                                             (unsigned long long)indices[q], (unsigned long long)t->height);
+  const size_t rows_words = (size_t)n * t->full_width, paths_words = (size_t)n * log_h * 8;
+  if (n == 0) return LM_OK;
+  uint64_t* d_idx = nullptr;
+  uint32_t* d_buf = nullptr;
+  CU(cudaMalloc(&d_idx, n * sizeof(uint64_t)));
+  cudaError_t e = cudaMalloc(&d_buf, (rows_words + paths_words + 1) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, indices, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess)
+    e = lm::merkle_open_gather(c->stream, t->d_codeword, t->d_layers, t->height, t->stored_width, t->full_width, d_idx,
+                               n, d_buf, d_buf + rows_words);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out_rows, d_buf, rows_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && paths_words)
+    e = cudaMemcpyAsync(out_paths, d_buf + rows_words, paths_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_idx);
+  if (d_buf) cudaFree(d_buf);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_open");
+  return LM_OK;
+}
+
+int lm_tree_eval(lm_tree* t, const uint32_t* point, uint32_t out[5]) {
+  if (!t || !point || !out) return fail(LM_ERR_INVALID, "lm_tree_eval: null argument");
+  if (!t->d_evals) return fail(LM_ERR_INVALID, "lm_tree_eval: the polynomial was not retained by this commit");
+  lm_ctx* c = t->ctx;
+  CU(cudaSetDevice(c->device));
+  if (t->n_vars > 64) return fail(LM_ERR_INVALID, "lm_tree_eval: n_vars too large");
+  if (t->n_vars)
+    CU(cudaMemcpyAsync(c->d_point, point, (size_t)t->n_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  int rc = lm_dev_mle_eval(c, t->d_evals, t->n_vars, t->elem_dim, t->actual_len, c->d_point, c->d_small);
+  if (rc != LM_OK) return rc;
+  CU(cudaMemcpyAsync(out, c->d_small, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_tree_read_codeword(lm_tree* t, uint32_t* out) {
+  if (!t || !out) return fail(LM_ERR_INVALID, "lm_tree_read_codeword: null argument");
+  return lm_dev_download(t->ctx, out, t->d_codeword, t->height * t->stored_width * sizeof(uint32_t));
+}
+int lm_tree_read_layers(lm_tree* t, uint32_t* out) {
+  if (!t || !out) return fail(LM_ERR_INVALID, "lm_tree_read_layers: null argument");
+  return lm_dev_download(t->ctx, out, t->d_layers, (2 * t->height - 1) * 8 * sizeof(uint32_t));
+}
+
+int lm_tree_free(lm_tree* t) {
+  if (!t) return LM_OK;
+  if (t->ctx) {
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+  }
+  if (t->d_evals && t->owns_evals) cudaFree(t->d_evals);
+  if (t->d_codeword) cudaFree(t->d_codeword);
+  if (t->d_layers) cudaFree(t->d_layers);
+  delete t;
+  return LM_OK;
+}
+
+int lm_mle_eval(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, uint64_t live_len, const uint32_t* point,
+                uint32_t out[5]) {
+  if (!c || !evals || !point || !out) return fail(LM_ERR_INVALID, "lm_mle_eval: null argument");
+  if (dim != 1 && dim != 5) return fail(LM_ERR_INVALID, "elem_dim must be 1 or 5, got %u", dim);
+  if (n_vars > 34) return fail(LM_ERR_INVALID, "lm_mle_eval: n_vars too large");
+  const uint64_t len = (uint64_t)1 << n_vars;
+  if (live_len > len) return fail(LM_ERR_INVALID, "lm_mle_eval: live_len exceeds 2^n_vars");
+  CU(cudaSetDevice(c->device));
+  uint32_t* d_evals = nullptr;
+  // rows are read in 2^10-element chunks: round the live prefix up and zero the tail
+  const uint64_t chunk = n_vars < 10 ? len : 1024;
+  uint64_t padded = (live_len + chunk - 1) / chunk * chunk;
+  if (padded == 0) padded = chunk;
+  CU(cudaMalloc(&d_evals, padded * dim * sizeof(uint32_t)));
+  cudaError_t e = cudaMemcpyAsync(d_evals, evals, live_len * dim * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess && padded > live_len)
+    e = cudaMemsetAsync(d_evals + live_len * dim, 0, (padded - live_len) * dim * sizeof(uint32_t), c->stream);
+  if (e == cudaSuccess && n_vars)
+    e = cudaMemcpyAsync(c->d_point, point, (size_t)n_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  int rc = LM_OK;
+  if (e != cudaSuccess) rc = cuda_fail(e, "lm_mle_eval upload");
+  if (rc == LM_OK) rc = lm_dev_mle_eval(c, d_evals, n_vars, dim, live_len, c->d_point, c->d_small);
+  if (rc == LM_OK) {
+    e = cudaMemcpyAsync(out, c->d_small, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "lm_mle_eval download");
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_evals);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// KoalaBear (p = 2^31 - 2^24 + 1) arithmetic for sm_100a, Montgomery form (x * 2^32 mod p) in u32.
+//
+// Replaces, on the device, the reference's scalar + AVX/NEON field code:
+//   crates/backend/koala-bear/src/monty_31/utils.rs:65-127   (monty_add / monty_sub / monty_reduce)
+//   crates/backend/koala-bear/src/monty_31/monty_31.rs:677-685 (Mul)
+//   crates/backend/koala-bear/src/quintic_extension/extension.rs:531-548 (quintic_mul)
+// Values crossing any kernel boundary are canonical in [0, p), exactly what the reference stores
+// (monty_31.rs:32-42), so results are bit-identical whatever instruction sequence produced them.
+//
+// Instruction notes (sm_100a): a Montgomery product is IMAD.WIDE.U32 (a*b), IMAD (m = lo * -p^-1),
+// IMAD.WIDE.U32 (m*p + t) and the high word is the result in [0, 2p); canonicalisation is IADD + IMNMX.U32.
+#pragma once
+#include <cstdint>
+
+#ifndef __CUDACC__
+#ifndef __host__
+#define __host__
+#endif
+#ifndef __device__
+#define __device__
+#endif
+#ifndef __forceinline__
+#define __forceinline__ inline
+#endif
+#endif
+
+#define LM_HD __host__ __device__ __forceinline__
+
+namespace lm {
+
+constexpr uint32_t KB_P = 0x7f000001u;
+constexpr uint32_t KB_NEG_MU = 0x7effffffu;  // -p^-1 mod 2^32
+constexpr uint32_t KB_R1 = 0x01fffffeu;      // 2^32 mod p  (Montgomery form of 1)
+constexpr uint32_t KB_R2 = 0x17f7efe4u;      // 2^64 mod p  (checked in kb_selfcheck)
+
+LM_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// x in [0, 2p) -> [0, p)
+LM_HD uint32_t kb_canon(uint32_t x) { return umin32(x, x - KB_P); }
+LM_HD uint32_t kb_add(uint32_t a, uint32_t b) { return kb_canon(a + b); }
+LM_HD uint32_t kb_sub(uint32_t a, uint32_t b) {
+  uint32_t d = a - b;
+  return umin32(d, d + KB_P);
+}
+LM_HD uint32_t kb_neg(uint32_t a) { return a ? KB_P - a : 0u; }
+
+// ---- 32x32 -> 64 multiply-add, pinned to IMAD.WIDE.U32 on the device ------------------------------------
+// Measured on B200 (tools/microbench/int_pipes.cu, profiles/r01_int_pipes.txt): IMAD and IMAD.WIDE issue at
+// 64 lanes/clk/SM, IMAD.HI at 32, IADD3/IMNMX at 128 on the other pipe.  ptxas rewrites a Montgomery reduction
+// whose modulus it can see into IMAD.HI (half rate), and multiplications by small literals into shift/IMAD.HI
+// chains, so the modulus and the MDS coefficients are read from constant memory, which it cannot fold.
+#ifdef __CUDACC__
+struct KbOpaque {
+  uint32_t p;
+  uint32_t mds[16];
+};
+static __constant__ KbOpaque c_kb = {KB_P, {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1}};
+#endif
+#ifdef __CUDA_ARCH__
+#define LM_KB_P_OPAQUE (c_kb.p)
+#else
+#define LM_KB_P_OPAQUE KB_P
+#endif
+
+LM_HD uint64_t mul_wide(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  uint64_t d;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+  return d;
+#else
+  return (uint64_t)a * b;
+#endif
+}
+LM_HD uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+#ifdef __CUDA_ARCH__
+  uint64_t d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+#else
+  return (uint64_t)a * b + c;
+#endif
+}
+
+// Montgomery reduction without the final conditional subtraction:
+// returns (t + m p) / 2^32  <  t / 2^32 + p.   Requires t < 2^64 - 2^32 p.
+LM_HD uint32_t kb_redc_lazy(uint64_t t) {
+  uint32_t m = (uint32_t)t * KB_NEG_MU;
+  uint64_t t2 = mad_wide(m, LM_KB_P_OPAQUE, t);
+  return (uint32_t)(t2 >> 32);
+}
+// a * b * 2^-32 mod p, result in [0, 2p) provided a * b < 2^32 p (e.g. a < 2p, b < p or both < 1.43p).
+LM_HD uint32_t kb_mul_lazy(uint32_t a, uint32_t b) { return kb_redc_lazy(mul_wide(a, b)); }
+// canonical product
+LM_HD uint32_t kb_mul(uint32_t a, uint32_t b) { return kb_canon(kb_mul_lazy(a, b)); }
+
+// value-preserving (mod p) shrink of a 64-bit accumulator to < 2^57:  hi * (2^32 mod p) + lo
+LM_HD uint64_t kb_fold(uint64_t acc) { return mad_wide((uint32_t)(acc >> 32), KB_R1, (uint64_t)(uint32_t)acc); }
+
+// Accumulator for sum_j a_j * c_j with a_j < p + 2^25, c_j < p.  Every product is < 2^62, so three of them
+// fit on top of a folded (< 2^57) accumulator; `mac<K>()` folds when the compile-time term index says so.
+struct KbDot {
+  uint64_t acc;
+  LM_HD explicit KbDot(uint64_t init = 0) : acc(init) {}
+  template <int TERM_INDEX>
+  LM_HD void mac(uint32_t a, uint32_t c) {
+    if (TERM_INDEX > 0 && TERM_INDEX % 3 == 0) acc = kb_fold(acc);
+    acc = mad_wide(a, c, acc);
+  }
+  // sum * 2^-32 mod p in [0, p + 2^25)
+  LM_HD uint32_t finish_lazy() const { return kb_redc_lazy(kb_fold(acc)); }
+  LM_HD uint32_t finish() const { return kb_canon(finish_lazy()); }
+};
+
+// ---- quintic extension EF = F[X]/(X^5 + X^2 - 1), AoS [c0..c4] -------------------------------------------
+struct Ef {
+  uint32_t c[5];
+};
+LM_HD Ef ef_zero() { return Ef{{0, 0, 0, 0, 0}}; }
+LM_HD Ef ef_from_base(uint32_t a) { return Ef{{a, 0, 0, 0, 0}}; }
+LM_HD Ef ef_add(const Ef& a, const Ef& b) {
+  Ef r;
+#pragma unroll
+  for (int i = 0; i < 5; i++) r.c[i] = kb_add(a.c[i], b.c[i]);
+  return r;
+}
+LM_HD Ef ef_sub(const Ef& a, const Ef& b) {
+  Ef r;
+#pragma unroll
+  for (int i = 0; i < 5; i++) r.c[i] = kb_sub(a.c[i], b.c[i]);
+  return r;
+}
+LM_HD Ef ef_mul_base(const Ef& a, uint32_t b) {
+  Ef r;
+#pragma unroll
+  for (int i = 0; i < 5; i++) r.c[i] = kb_mul(a.c[i], b);
+  return r;
+}
+LM_HD Ef ef_add_base(Ef a, uint32_t b) {
+  a.c[0] = kb_add(a.c[0], b);
+  return a;
+}
+// Product mod X^5 = 1 - X^2.  Each output coefficient is one delayed-reduction dot product of length 5
+// against pre-combined b terms — the same regrouping as the reference's quintic_mul (extension.rs:531-548),
+// with negated terms expressed as (p - x) so all accumulations are unsigned.
+LM_HD Ef ef_mul(const Ef& a, const Ef& b) {
+  const uint32_t b0 = b.c[0], b1 = b.c[1], b2 = b.c[2], b3 = b.c[3], b4 = b.c[4];
+  const uint32_t b0m3 = kb_sub(b0, b3), b1m4 = kb_sub(b1, b4), b4m2 = kb_sub(b4, b2);
+  const uint32_t b3m14 = kb_sub(b3, b1m4);
+  const uint32_t rows[5][5] = {{b0, b4, b3, b2, b1m4},
+                               {b1, b0, b4, b3, b2},
+                               {b2, b1m4, b0m3, b4m2, b3m14},
+                               {b3, b2, b1m4, b0m3, b4m2},
+                               {b4, b3, b2, b1m4, b0m3}};
+  Ef r;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    KbDot d;
+    d.mac<0>(a.c[0], rows[i][0]);
+    d.mac<1>(a.c[1], rows[i][1]);
+    d.mac<2>(a.c[2], rows[i][2]);
+    d.mac<3>(a.c[3], rows[i][3]);
+    d.mac<4>(a.c[4], rows[i][4]);
+    r.c[i] = d.finish();
+  }
+  return r;
+}
+LM_HD Ef ef_sqr(const Ef& a) { return ef_mul(a, a); }
+
+}  // namespace lm

@@ -1,0 +1,232 @@
+// Poseidon1 Merkle commitment over a row-major KoalaBear matrix (sm_100a).
+//
+// Device replacement for
+//   crates/whir/src/merkle.rs:59-88,215-288      build_merkle_tree_koalabear, first_digest_layer(_with_initial_state)
+//   crates/backend/symetric/src/sponge.rs:28-108 precompute_zero_suffix_state, hash_rtl_iter, absorb_rtl_chunks
+//   crates/backend/symetric/src/merkle.rs:21-35,50-90  MerkleTree::from_first_layer, compress_layer
+//
+// Kernels
+//   leaf_sponge_kernel   one thread per matrix row; the row is hashed right to left, rate 8 / width 16, as if
+//                        zero-extended to `full_w`; a run of >= 2 all-zero trailing rate chunks is replaced by the
+//                        pre-computed sponge state of those zeros (passed by value).  INT32-ALU bound: ~5k integer
+//                        instructions per compression against 32 B of row data.
+//   tree_levels_kernel   one CTA folds 2*T consecutive digests of a layer through up to log2(2T) levels, writing
+//                        every intermediate layer (all layers are retained for openings).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "merkle.h"
+#include "poseidon1.cuh"
+
+namespace lm {
+
+__constant__ P1Tables c_p1 =
+#include "poseidon1_tables.inc"
+    ;
+static const P1Tables h_p1 =
+#include "poseidon1_tables.inc"
+    ;
+
+struct State16 {
+  uint32_t v[16];
+};
+
+// Element `pos` of the virtual row: stored value if pos < lim else 0.
+// Fast path: whole 8-chunk below lim and 16-byte aligned -> two 128-bit loads.
+__device__ __forceinline__ void load_chunk8(const uint32_t* __restrict__ row, int64_t first, uint32_t lim, bool vec_ok,
+                                            uint32_t out[8]) {
+  if (vec_ok && first >= 0 && (uint64_t)first + 8 <= lim) {
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(row + first));
+    const uint4 hi = __ldg(reinterpret_cast<const uint4*>(row + first) + 1);
+    out[0] = lo.x, out[1] = lo.y, out[2] = lo.z, out[3] = lo.w;
+    out[4] = hi.x, out[5] = hi.y, out[6] = hi.z, out[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int64_t pos = first + k;
+      out[k] = (pos >= 0 && (uint64_t)pos < lim) ? __ldg(row + pos) : 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t lim, uint32_t virt_w,
+                   int from_state, State16 init, uint32_t* __restrict__ digests) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h) return;
+  const uint32_t* row = mat + r * stored_w;
+  const bool vec_ok = (stored_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mat) & 15) == 0);
+  uint32_t s[16];
+  int64_t chunk = (int64_t)(virt_w / 8) - 1;  // index of the right-most rate chunk not yet absorbed
+  if (from_state) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = init.v[i];
+  } else {
+    // first compression takes the right-most 16 elements
+    load_chunk8(row, 8 * (chunk - 1), lim, vec_ok, s);
+    load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
+    chunk -= 2;
+    p1_compress<8>(s, c_p1);
+  }
+  for (; chunk >= 0; chunk--) {
+    load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
+    p1_compress<8>(s, c_p1);
+  }
+  uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
+  out[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  out[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// layer0: n0 digests (n0 = 2 * T * gridDim.x at full size). CTA b owns digests [b*2T, (b+1)*2T) and writes
+// its part of each of the next `levels` layers.  layer_out[l] points at the start of layer (l+1).
+template <int T>
+__global__ void __launch_bounds__(T)
+tree_levels_kernel(const uint32_t* __restrict__ layer0, uint64_t n0, int levels, uint32_t* __restrict__ next_base) {
+  __shared__ uint32_t sm[2][T][8 + 1];  // +1: avoid 8-way bank conflicts on the strided reads
+  const int t = threadIdx.x;
+  uint64_t n_prev = n0;
+  uint32_t* out_layer = next_base;
+  uint64_t cta_span = 2 * (uint64_t)T;  // digests of the current layer owned by this CTA
+  int buf = 0;
+  for (int l = 0; l < levels; l++) {
+    const uint64_t span_next = cta_span / 2;
+    const uint64_t base_next = (uint64_t)blockIdx.x * span_next;
+    if ((uint64_t)t < span_next && base_next + t < n_prev / 2) {
+      uint32_t s[16];
+      if (l == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(layer0 + 16 * (base_next + t));
+        uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+        s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
+        s[8] = c.x, s[9] = c.y, s[10] = c.z, s[11] = c.w, s[12] = d.x, s[13] = d.y, s[14] = d.z, s[15] = d.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          s[k] = sm[buf ^ 1][2 * t][k];
+          s[8 + k] = sm[buf ^ 1][2 * t + 1][k];
+        }
+      }
+      p1_compress<8>(s, c_p1);
+      uint4* dst = reinterpret_cast<uint4*>(out_layer + 8 * (base_next + t));
+      dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
+      dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
+#pragma unroll
+      for (int k = 0; k < 8; k++) sm[buf][t][k] = s[k];
+    }
+    __syncthreads();
+    buf ^= 1;
+    out_layer += 8 * (n_prev / 2);
+    n_prev /= 2;
+    cta_span = span_next;
+  }
+}
+
+static State16 zero_suffix_state_host(uint32_t n_zero_chunks) {
+  // sponge.rs:28-48 evaluated with the same arithmetic header on the host (a 16-word constant per commit shape)
+  State16 st;
+  for (int i = 0; i < 16; i++) st.v[i] = 0;
+  p1_compress<16>(st.v, h_p1);
+  for (uint32_t k = 0; k + 2 < n_zero_chunks; k++) {
+    for (int i = 8; i < 16; i++) st.v[i] = 0;
+    p1_compress<16>(st.v, h_p1);
+  }
+  return st;
+}
+
+cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
+                                uint32_t full_w, uint32_t eff_w, uint32_t* d_digests) {
+  if (h == 0) return cudaSuccess;
+  if (full_w % 8 != 0 || full_w < 16 || eff_w > full_w || stored_w > full_w) return cudaErrorInvalidValue;
+  const uint32_t n_zero_chunks = (full_w - eff_w) / 8;
+  State16 init{};
+  uint32_t lim, virt_w;
+  int from_state = 0;
+  if (n_zero_chunks >= 2) {
+    init = zero_suffix_state_host(n_zero_chunks);
+    from_state = 1;
+    lim = eff_w < stored_w ? eff_w : stored_w;
+    virt_w = (eff_w + 7) / 8 * 8;
+  } else {
+    lim = stored_w;
+    virt_w = full_w;
+  }
+  const int T = 128;
+  const uint64_t blocks = (h + T - 1) / T;
+  leaf_sponge_kernel<<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests);
+  return cudaGetLastError();
+}
+
+cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, uint64_t h) {
+  // layers back to back: h, h/2, ..., 1 digests
+  constexpr int T = 128;
+  uint32_t* cur = d_layers;
+  uint64_t n = h;
+  while (n > 1) {
+    int levels = 0;
+    uint64_t m = n;
+    while (m > 1 && levels < 8) m >>= 1, levels++;  // 2T = 256 digests per CTA -> up to 8 levels
+    const uint64_t blocks = (n + 2 * T - 1) / (2 * T);
+    uint32_t* next = cur + 8 * n;
+    tree_levels_kernel<T><<<(unsigned)blocks, T, 0, stream>>>(cur, n, levels, next);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    for (int l = 0; l < levels; l++) {
+      cur += 8 * n;
+      n >>= 1;
+    }
+  }
+  return cudaSuccess;
+}
+
+// Openings (crates/whir/src/merkle.rs:205-211 + crates/backend/symetric/src/merkle.rs:43-47): one CTA per query
+// packs the zero-extended row and the sibling of every level into contiguous buffers (one D2H copy each).
+__global__ void open_gather_kernel(const uint32_t* __restrict__ mat, const uint32_t* __restrict__ layers, uint64_t h,
+                                   uint32_t log_h, uint32_t stored_w, uint32_t full_w,
+                                   const uint64_t* __restrict__ indices, uint32_t* __restrict__ rows,
+                                   uint32_t* __restrict__ paths) {
+  const uint32_t q = blockIdx.x;
+  const uint64_t idx = indices[q];
+  for (uint32_t c = threadIdx.x; c < full_w; c += blockDim.x)
+    rows[(uint64_t)q * full_w + c] = c < stored_w ? mat[idx * stored_w + c] : 0u;
+  for (uint32_t k = threadIdx.x; k < log_h * 8; k += blockDim.x) {
+    const uint32_t l = k >> 3;
+    // layer l starts at digest offset 2h - 2h/2^l
+    const uint64_t off = 2 * h - ((2 * h) >> l);
+    paths[(uint64_t)q * log_h * 8 + k] = layers[8 * (off + ((idx >> l) ^ 1)) + (k & 7)];
+  }
+}
+
+cudaError_t merkle_open_gather(cudaStream_t stream, const uint32_t* d_mat, const uint32_t* d_layers, uint64_t h,
+                               uint32_t stored_w, uint32_t full_w, const uint64_t* d_indices, uint32_t n,
+                               uint32_t* d_rows, uint32_t* d_paths) {
+  if (n == 0) return cudaSuccess;
+  uint32_t log_h = 0;
+  while (((uint64_t)1 << log_h) < h) log_h++;
+  open_gather_kernel<<<n, 128, 0, stream>>>(d_mat, d_layers, h, log_h, stored_w, full_w, d_indices, d_rows, d_paths);
+  return cudaGetLastError();
+}
+
+// Batched permutation / compression of explicit states (parity tests, PoW grinding building block).
+__global__ void __launch_bounds__(128) permute_states_kernel(uint32_t* states, uint64_t n, int compress) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[16];
+  uint4* p = reinterpret_cast<uint4*>(states + 16 * i);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint4 v = p[k];
+    s[4 * k] = v.x, s[4 * k + 1] = v.y, s[4 * k + 2] = v.z, s[4 * k + 3] = v.w;
+  }
+  if (compress)
+    p1_compress<16>(s, c_p1);
+  else
+    p1_permute<16>(s, c_p1);
+#pragma unroll
+  for (int k = 0; k < 4; k++) p[k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+}
+
+cudaError_t poseidon1_states(cudaStream_t stream, uint32_t* d_states, uint64_t n, int compress) {
+  if (n == 0) return cudaSuccess;
+  permute_states_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_states, n, compress);
+  return cudaGetLastError();
+}
+
+}  // namespace lm

@@ -1,0 +1,18 @@
+// Internal (C++) launch interface of merkle.cu; the public C ABI is include/leanmultisig_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace lm {
+// digests[r] = sponge(row r zero-extended to full_w); rows are stored_w wide, entries >= eff_w are zero.
+cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
+                                uint32_t full_w, uint32_t eff_w, uint32_t* d_digests);
+// d_layers holds (2h - 1) digests: layer 0 (h leaf digests, already filled) then h/2, ..., 1.
+cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, uint64_t h);
+// rows (n x full_w, zero-extended) and sibling paths (n x log2(h) x 8, leaf level first) of n leaf indices
+cudaError_t merkle_open_gather(cudaStream_t stream, const uint32_t* d_mat, const uint32_t* d_layers, uint64_t h,
+                               uint32_t stored_w, uint32_t full_w, const uint64_t* d_indices, uint32_t n,
+                               uint32_t* d_rows, uint32_t* d_paths);
+// n explicit 16-word states: permutation (compress = 0) or permutation + feed-forward (compress = 1)
+cudaError_t poseidon1_states(cudaStream_t stream, uint32_t* d_states, uint64_t n, int compress);
+}  // namespace lm

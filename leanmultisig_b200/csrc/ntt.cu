@@ -1,0 +1,256 @@
+// Reed-Solomon encode of the stacked witness on sm_100a: block gather + radix-2 "DFT on evaluations".
+//
+// Device replacement for
+//   crates/whir/src/utils.rs:69-150   reorder_and_dft / prepare_evals_for_fft_unpacked
+//   crates/whir/src/dft.rs:52-62      roots_of_unity_table
+//   crates/whir/src/dft.rs:79-155     dft_batch_by_evals / dft_algebra_batch_by_evals
+//   crates/whir/src/dft.rs:546-568    butterflies (a, b) -> (a + t (b - a), a - t (b - a))
+//
+// Layout.  The matrix is row-major h x w u32 (an EF matrix is the same memory with w = 5 * n_cols, dft.rs:147-155).
+// The transform is independent per column; layer l (half-block m = 2^l) pairs rows (i, i + m) with twiddle
+// w_h^((i mod m) * h / 2m).  A pass kernel keeps a tile of 2^L rows x 8 columns (32 B per row = one DRAM sector)
+// in shared memory and runs L consecutive layers on it, radix-8 in registers between barriers, so a 2^22-row
+// transform is two passes over HBM (11 + 11 layers) instead of the CPU's eight.  Rows of a tile are 2^l0 apart
+// (l0 = first layer of the pass); the first pass can gather straight from the evaluation vector, where column j
+// is the contiguous slice evals[j << (n - k) ..] with every value repeated 2^r times, so the first r layers
+// (identities on repeated data) are skipped.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "kb.cuh"
+#include "ntt.h"
+
+namespace lm {
+
+// ------------------------------------------------------------------------------------------------ twiddles
+// tw[e] = g^e for e < 2^(log_n - 1), g = primitive 2^log_n-th root (koala_bear.rs:46-54), Montgomery form.
+static const uint32_t TWO_ADIC_GEN_CANON[25] = {
+    0x1,        0x7f000000, 0x7e010002, 0x6832fe4a, 0x8dbd69c,  0xa28f031,  0x5c4a5b99, 0x29b75a80, 0x17668b8a,
+    0x27ad539b, 0x334d48c7, 0x7744959c, 0x768fc6fa, 0x303964b2, 0x3e687d4d, 0x45a60e61, 0x6e2f4d7a, 0x163bd499,
+    0x6c4a8a45, 0x143ef899, 0x514ddcad, 0x484ef19b, 0x205d63c3, 0x68e7dd49, 0x6ac49f88,
+};
+
+uint32_t two_adic_generator_monty(unsigned bits) { return kb_mul(TWO_ADIC_GEN_CANON[bits], KB_R2); }
+
+__global__ void twiddle_kernel(uint32_t* tw, uint64_t n_half, uint32_t g) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_half) return;
+  uint32_t r = KB_R1, b = g;
+  for (uint64_t k = e; k; k >>= 1) {
+    if (k & 1) r = kb_mul(r, b);
+    b = kb_mul(b, b);
+  }
+  tw[e] = r;
+}
+
+cudaError_t ntt_fill_twiddles(cudaStream_t stream, uint32_t* d_tw, unsigned log_n) {
+  if (log_n == 0) return cudaSuccess;
+  const uint64_t n_half = (uint64_t)1 << (log_n - 1);
+  const uint32_t g = two_adic_generator_monty(log_n);
+  twiddle_kernel<<<(unsigned)((n_half + 255) / 256), 256, 0, stream>>>(d_tw, n_half, g);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ gather
+// out[i][j*dim + d] = evals[(((j << log_block) + i) >> r) * dim + d]      (utils.rs:128-150)
+__global__ void gather_kernel(const uint32_t* __restrict__ evals, uint32_t* __restrict__ out, uint64_t h, uint32_t n_cols,
+                              uint32_t dim, uint32_t log_block, uint32_t r) {
+  const uint64_t w = (uint64_t)n_cols * dim;
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= h * w) return;
+  const uint64_t i = idx / w, c = idx % w;
+  const uint64_t j = c / dim, d = c % dim;
+  out[idx] = __ldg(evals + ((((j << log_block) + i) >> r) * dim + d));
+}
+
+// ------------------------------------------------------------------------------------------------ butterflies
+__device__ __forceinline__ void bfly(uint32_t& a, uint32_t& b, uint32_t t) {
+  const uint32_t x = kb_mul(kb_sub(b, a), t);
+  b = kb_sub(a, x);
+  a = kb_add(a, x);
+}
+__device__ __forceinline__ void bfly4(uint4& a, uint4& b, uint32_t t) {
+  bfly(a.x, b.x, t);
+  bfly(a.y, b.y, t);
+  bfly(a.z, b.z, t);
+  bfly(a.w, b.w, t);
+}
+
+constexpr int TILE_COLS = 8;       // u32 columns per tile = 32 B per row
+constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory
+
+// One group of G layers (local layers lp .. lp+G-1) on the shared tile, radix 2^G in registers.
+// Work item = (u, half): rows j0 + q * 2^lp (q < 2^G) of 16-byte half `half`.
+template <int G>
+__device__ __forceinline__ void tile_group(uint4* tile, int L, int lp, int l0, uint64_t row_lo, int log_h,
+                                           const uint32_t* __restrict__ tw, int tw_shift) {
+  constexpr int Q = 1 << G;
+  const int n_items = 1 << (L - G + 1);
+  for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+    // consecutive threads -> consecutive 16-byte slots whenever the row stride allows it
+    const int half = item & 1;
+    const int u = item >> 1;
+    const int j0 = ((u >> lp) << (lp + G)) | (u & ((1 << lp) - 1));
+    uint4 v[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = tile[(j0 + (q << lp)) * 2 + half];
+#pragma unroll
+    for (int s = 0; s < G; s++) {
+      const int l = l0 + lp + s;  // global layer
+      // twiddle exponent of the low row: ((row mod 2^l) << (log_h - l - 1)), row = row_lo + j * 2^l0
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        if (q & (1 << s)) continue;
+        const uint64_t jm = (uint64_t)(j0 & ((1 << lp) - 1)) + ((uint64_t)(q & ((1 << s) - 1)) << lp);
+        const uint64_t row_mod = row_lo + (jm << l0);
+        const uint64_t e = row_mod << (log_h - l - 1);
+        const uint32_t t = __ldg(tw + (e << tw_shift));
+        bfly4(v[q], v[q | (1 << s)], t);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) tile[(j0 + (q << lp)) * 2 + half] = v[q];
+  }
+}
+
+// Pass over layers [l0 + skip, l0 + L) of an h x w matrix; one CTA per (column tile, row group).
+// src == nullptr: in place on `mat`.  src != nullptr (only with l0 == 0): gather from the evaluation vector
+// (dim = 1): element (row, col) = src[(col << log_block) + (row >> r)].
+__global__ void __launch_bounds__(512)
+ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
+                int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift) {
+  extern __shared__ uint4 tile[];  // [2^L][2]
+  const uint32_t n_col_tiles = (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
+  const uint64_t col0 = (uint64_t)(blockIdx.x % n_col_tiles) * TILE_COLS;  // column tile varies fastest: CTAs that
+  const uint64_t grp = blockIdx.x / n_col_tiles;                           // run together cover whole rows
+  // rows of this tile: row(j) = ((grp >> l0) << (l0 + L)) + (grp & (2^l0 - 1)) + j * 2^l0
+  const uint64_t row_lo = grp & (((uint64_t)1 << l0) - 1);
+  const uint64_t row_base = ((grp >> l0) << (l0 + L)) + row_lo;
+  const int n_rows = 1 << L;
+  const bool two_halves = col0 + 8 <= w;  // w % 4 == 0 guaranteed by the launcher
+
+  if (src == nullptr) {
+    for (int item = threadIdx.x; item < 2 * n_rows; item += blockDim.x) {
+      const int j = item >> 1, half = item & 1;
+      if (half == 1 && !two_halves) {
+        tile[item] = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      const uint64_t row = row_base + ((uint64_t)j << l0);
+      tile[item] = *reinterpret_cast<const uint4*>(mat + row * w + col0 + 4 * half);
+    }
+  } else {
+    // column c of the tile is contiguous in src: consecutive threads read consecutive rows of one column
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
+    const int n_cols_here = two_halves ? 8 : 4;
+    for (int item = threadIdx.x; item < n_cols_here * n_rows; item += blockDim.x) {
+      const int c = item >> L, j = item & (n_rows - 1);
+      const uint64_t row = row_base + j;
+      t32[j * 8 + c] = __ldg(src + (((col0 + c) << log_block) + row) / ((uint64_t)1 << r));
+    }
+    if (!two_halves)
+      for (int j = threadIdx.x; j < n_rows; j += blockDim.x) tile[2 * j + 1] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+
+  int lp = skip;
+  while (lp < L) {
+    const int rem = L - lp;
+    const int g = rem <= 4 ? (rem == 4 ? 2 : rem) : 3;  // 3,3,...,then 3 / 2+2 / 2 / 1
+    if (g == 3)
+      tile_group<3>(tile, L, lp, l0, row_lo, log_h, tw, tw_shift);
+    else if (g == 2)
+      tile_group<2>(tile, L, lp, l0, row_lo, log_h, tw, tw_shift);
+    else
+      tile_group<1>(tile, L, lp, l0, row_lo, log_h, tw, tw_shift);
+    lp += g;
+    __syncthreads();
+  }
+
+  for (int item = threadIdx.x; item < 2 * n_rows; item += blockDim.x) {
+    const int j = item >> 1, half = item & 1;
+    if (half == 1 && !two_halves) continue;
+    const uint64_t row = row_base + ((uint64_t)j << l0);
+    *reinterpret_cast<uint4*>(mat + row * w + col0 + 4 * half) = tile[item];
+  }
+}
+
+// Generic single-layer kernel for widths that are not a multiple of 4 (not on the benchmark path).
+__global__ void ntt_layer_kernel(uint32_t* __restrict__ mat, uint64_t h, uint64_t w, int l, int log_h,
+                                 const uint32_t* __restrict__ tw, int tw_shift) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (h / 2) * w) return;
+  const uint64_t pair = idx / w, c = idx % w;
+  const uint64_t m = (uint64_t)1 << l;
+  const uint64_t blk = pair >> l, i = pair & (m - 1);
+  uint32_t* lo = mat + (blk * 2 * m + i) * w + c;
+  uint32_t* hi = lo + m * w;
+  const uint32_t t = __ldg(tw + ((i << (log_h - l - 1)) << tw_shift));
+  uint32_t a = *lo, b = *hi;
+  bfly(a, b, t);
+  *lo = a;
+  *hi = b;
+}
+
+static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32_t* d_src, uint32_t log_block,
+                              uint32_t r, uint64_t h, uint64_t w, int skip, const uint32_t* d_tw, unsigned tw_log_n) {
+  int log_h = 0;
+  while (((uint64_t)1 << log_h) < h) log_h++;
+  if (((uint64_t)1 << log_h) != h || (unsigned)log_h > tw_log_n) return cudaErrorInvalidValue;
+  const int tw_shift = (int)tw_log_n - log_h;  // w_h^e = w_N^(e << tw_shift)
+  if (log_h == 0) return cudaSuccess;
+
+  if (w % 4 != 0) {
+    if (d_src != nullptr) return cudaErrorInvalidValue;
+    for (int l = skip; l < log_h; l++) {
+      const uint64_t n = (h / 2) * w;
+      ntt_layer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_mat, h, w, l, log_h, d_tw, tw_shift);
+    }
+    return cudaGetLastError();
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG) * 32);
+    attr_set = true;
+  }
+  // split log_h layers into ceil(log_h / 11) passes of nearly equal depth
+  const int n_pass = (log_h + MAX_TILE_LOG - 1) / MAX_TILE_LOG;
+  int l0 = 0, skip_left = skip;
+  for (int p = 0; p < n_pass; p++) {
+    const int L = (log_h - l0 + (n_pass - p) - 1) / (n_pass - p);
+    const int sk = skip_left < L ? skip_left : L;
+    skip_left -= sk;
+    const uint64_t n_cta = ((w + TILE_COLS - 1) / TILE_COLS) * (h >> L);
+    const size_t smem = ((size_t)1 << L) * 32;
+    ntt_pass_kernel<<<(unsigned)n_cta, 512, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
+                                                            log_block, r, d_tw, tw_shift);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    l0 += L;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t ntt_dft_batch_by_evals(cudaStream_t stream, uint32_t* d_mat, uint64_t h, uint64_t w, int skip_layers,
+                                   const uint32_t* d_tw, unsigned tw_log_n) {
+  return run_layers(stream, d_mat, nullptr, 0, 0, h, w, skip_layers, d_tw, tw_log_n);
+}
+
+cudaError_t ntt_reorder_and_dft(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim,
+                                uint32_t folding_factor, uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out,
+                                const uint32_t* d_tw, unsigned tw_log_n) {
+  if (folding_factor > n_vars + log_inv_rate) return cudaErrorInvalidValue;
+  const uint32_t log_block = n_vars + log_inv_rate - folding_factor;
+  const uint64_t h = (uint64_t)1 << log_block;
+  const uint64_t w = (uint64_t)dft_n_cols * dim;
+  if (dft_n_cols == 0) return cudaSuccess;
+  const int skip = (int)(log_inv_rate < log_block ? log_inv_rate : log_block);
+  if (dim == 1 && w % 4 == 0) return run_layers(stream, d_out, d_evals, log_block, log_inv_rate, h, w, skip, d_tw, tw_log_n);
+  const uint64_t n = h * w;
+  gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_evals, d_out, h, dft_n_cols, dim, log_block, log_inv_rate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return run_layers(stream, d_out, nullptr, 0, 0, h, w, skip, d_tw, tw_log_n);
+}
+
+}  // namespace lm

@@ -1,0 +1,17 @@
+// Internal (C++) launch interface of ntt.cu; the public C ABI is include/leanmultisig_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace lm {
+uint32_t two_adic_generator_monty(unsigned bits);
+// d_tw[e] = g^e, e < 2^(log_n - 1), g = primitive 2^log_n-th root of unity (Montgomery form)
+cudaError_t ntt_fill_twiddles(cudaStream_t stream, uint32_t* d_tw, unsigned log_n);
+// in-place evals-DFT of an h x w row-major matrix, skipping the first `skip_layers` layers
+cudaError_t ntt_dft_batch_by_evals(cudaStream_t stream, uint32_t* d_mat, uint64_t h, uint64_t w, int skip_layers,
+                                   const uint32_t* d_tw, unsigned tw_log_n);
+// gather + DFT: d_out is (2^(n_vars + log_inv_rate - folding)) x (dft_n_cols * dim)
+cudaError_t ntt_reorder_and_dft(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim,
+                                uint32_t folding_factor, uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out,
+                                const uint32_t* d_tw, unsigned tw_log_n);
+}  // namespace lm

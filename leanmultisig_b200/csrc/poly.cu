@@ -1,0 +1,216 @@
+// Multilinear-extension kernels on sm_100a: eq tables, MLE evaluation, MSB-first folding.
+//
+// Device replacement for
+//   crates/backend/poly/src/eq_mle.rs:16-26,85-150    eval_eq / compute_eval_eq (scaled eq table)
+//   crates/backend/poly/src/evals.rs:142-347           eval_multilinear_generic (sqrt-split evaluation)
+//   crates/backend/poly/src/utils.rs:161-186           fold_multilinear (MSB-first)
+// MLE index convention: variable x_0 is the most-significant bit of the evaluation index (evals.rs:219).
+//
+// mle_eval: index = (hi | lo) with |lo| = LO_VARS = 10 bits.  Thread t of a CTA owns lo = t and walks a
+// contiguous range of hi, so global reads are fully coalesced 4 KiB rows (base field) and the per-row factor
+// eq_hi[hi] is a warp-uniform broadcast.  Each term is 5 IMAD.WIDE into 64-bit accumulators with delayed
+// reduction; the kernel is HBM-bound (4 B per element read once).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "kb.cuh"
+#include "poly.h"
+
+namespace lm {
+
+constexpr int LO_VARS = 10;
+constexpr int EVAL_THREADS = 1 << LO_VARS;
+
+// out[b] = scalar * prod_i (b_i ? z_i : 1 - z_i), b big-endian over k variables; one thread per entry.
+__global__ void eq_table_kernel(const uint32_t* __restrict__ point, int k, Ef scalar, uint32_t* __restrict__ out) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ((uint64_t)1 << k)) return;
+  Ef acc = scalar;
+  for (int i = 0; i < k; i++) {
+    Ef z;
+#pragma unroll
+    for (int c = 0; c < 5; c++) z.c[c] = __ldg(point + 5 * i + c);
+    if (!((b >> (k - 1 - i)) & 1)) {
+      // 1 - z
+#pragma unroll
+      for (int c = 0; c < 5; c++) z.c[c] = kb_neg(z.c[c]);
+      z.c[0] = kb_add(z.c[0], KB_R1);
+    }
+    acc = ef_mul(acc, z);
+  }
+#pragma unroll
+  for (int c = 0; c < 5; c++) out[5 * b + c] = acc.c[c];
+}
+
+cudaError_t eq_table(cudaStream_t stream, const uint32_t* d_point, int k, const uint32_t scalar[5], uint32_t* d_out) {
+  Ef s;
+  for (int c = 0; c < 5; c++) s.c[c] = scalar[c];
+  const uint64_t n = (uint64_t)1 << k;
+  eq_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_point, k, s, d_out);
+  return cudaGetLastError();
+}
+
+__device__ __forceinline__ Ef warp_reduce_ef(Ef v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Ef o;
+#pragma unroll
+    for (int c = 0; c < 5; c++) o.c[c] = __shfl_down_sync(0xffffffffu, v.c[c], off);
+    v = ef_add(v, o);
+  }
+  return v;
+}
+
+// partial[blockIdx.x] = sum over this CTA's hi range of eq_hi[hi] * sum_lo eq_lo[lo] * f[hi, lo]
+// n_lo = 2^lo_vars <= 1024 entries per row; rows >= live_rows are all-zero and skipped by the launcher.
+template <int DIM>
+__global__ void __launch_bounds__(EVAL_THREADS)
+mle_eval_kernel(const uint32_t* __restrict__ evals, int lo_vars, uint64_t live_rows, uint64_t rows_per_cta,
+                const uint32_t* __restrict__ eq_hi, const uint32_t* __restrict__ eq_lo, uint32_t* __restrict__ partial) {
+  __shared__ Ef red[EVAL_THREADS / 32];
+  const int t = threadIdx.x;
+  const uint64_t n_lo = (uint64_t)1 << lo_vars;
+  const uint64_t row0 = (uint64_t)blockIdx.x * rows_per_cta;
+  uint64_t row1 = row0 + rows_per_cta;
+  if (row1 > live_rows) row1 = live_rows;
+  Ef acc = ef_zero();
+  if ((uint64_t)t < n_lo) {
+    uint64_t a[5] = {0, 0, 0, 0, 0};
+    int terms = 0;
+    for (uint64_t row = row0; row < row1; row++) {
+      Ef e;
+#pragma unroll
+      for (int c = 0; c < 5; c++) e.c[c] = __ldg(eq_hi + 5 * row + c);
+      if (DIM == 1) {
+        const uint32_t f = __ldg(evals + row * n_lo + t);
+        if (terms == 3) {
+#pragma unroll
+          for (int c = 0; c < 5; c++) a[c] = kb_fold(a[c]);
+          terms = 0;
+        }
+#pragma unroll
+        for (int c = 0; c < 5; c++) a[c] = mad_wide(f, e.c[c], a[c]);
+        terms++;
+      } else {
+        Ef f;
+#pragma unroll
+        for (int c = 0; c < 5; c++) f.c[c] = __ldg(evals + (row * n_lo + t) * 5 + c);
+        acc = ef_add(acc, ef_mul(f, e));
+      }
+    }
+    if (DIM == 1) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) acc.c[c] = kb_canon(kb_redc_lazy(kb_fold(a[c])));
+    }
+    Ef l;
+#pragma unroll
+    for (int c = 0; c < 5; c++) l.c[c] = __ldg(eq_lo + 5 * t + c);
+    acc = ef_mul(acc, l);
+  }
+  acc = warp_reduce_ef(acc);
+  if ((t & 31) == 0) red[t >> 5] = acc;
+  __syncthreads();
+  if (t < 32) {
+    Ef v = (t < EVAL_THREADS / 32) ? red[t] : ef_zero();
+    v = warp_reduce_ef(v);
+    if (t == 0) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) partial[5 * blockIdx.x + c] = v.c[c];
+    }
+  }
+}
+
+__global__ void sum_partials_kernel(const uint32_t* __restrict__ partial, int n, uint32_t* __restrict__ out) {
+  // single CTA of 256 threads
+  __shared__ Ef red[8];
+  Ef acc = ef_zero();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    Ef v;
+#pragma unroll
+    for (int c = 0; c < 5; c++) v.c[c] = partial[5 * i + c];
+    acc = ef_add(acc, v);
+  }
+  acc = warp_reduce_ef(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Ef v = (threadIdx.x < 8) ? red[threadIdx.x] : ef_zero();
+    v = warp_reduce_ef(v);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) out[c] = v.c[c];
+    }
+  }
+}
+
+size_t mle_eval_scratch_words(uint32_t n_vars) {
+  const int lo_vars = n_vars < (uint32_t)LO_VARS ? (int)n_vars : LO_VARS;
+  const uint64_t n_hi = (uint64_t)1 << (n_vars - lo_vars);
+  return (size_t)(5 * n_hi + 5 * ((uint64_t)1 << lo_vars) + 5 * 4096 + 8);
+}
+
+cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint64_t live_len,
+                     const uint32_t* d_point, uint32_t* d_scratch, uint32_t* d_out) {
+  if (dim != 1 && dim != 5) return cudaErrorInvalidValue;
+  const int lo_vars = n_vars < (uint32_t)LO_VARS ? (int)n_vars : LO_VARS;
+  const int hi_vars = (int)n_vars - lo_vars;
+  const uint64_t n_hi = (uint64_t)1 << hi_vars, n_lo = (uint64_t)1 << lo_vars;
+  uint32_t* d_eq_hi = d_scratch;
+  uint32_t* d_eq_lo = d_eq_hi + 5 * n_hi;
+  uint32_t* d_partial = d_eq_lo + 5 * n_lo;
+  const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
+  cudaError_t e;
+  if ((e = eq_table(stream, d_point, hi_vars, one, d_eq_hi)) != cudaSuccess) return e;
+  if ((e = eq_table(stream, d_point + 5 * hi_vars, lo_vars, one, d_eq_lo)) != cudaSuccess) return e;
+  uint64_t live_rows = (live_len + n_lo - 1) / n_lo;
+  if (live_rows > n_hi) live_rows = n_hi;
+  // enough CTAs to fill the machine, at most 4096 partial sums
+  uint64_t n_cta = live_rows < 4096 ? live_rows : 4096;
+  if (n_cta == 0) n_cta = 1;
+  const uint64_t rows_per_cta = (live_rows + n_cta - 1) / n_cta;
+  n_cta = rows_per_cta ? (live_rows + rows_per_cta - 1) / rows_per_cta : 1;
+  if (n_cta == 0) n_cta = 1;
+  if (dim == 1)
+    mle_eval_kernel<1><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_evals, lo_vars, live_rows, rows_per_cta, d_eq_hi,
+                                                                     d_eq_lo, d_partial);
+  else
+    mle_eval_kernel<5><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_evals, lo_vars, live_rows, rows_per_cta, d_eq_hi,
+                                                                     d_eq_lo, d_partial);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  sum_partials_kernel<<<1, 256, 0, stream>>>(d_partial, (int)n_cta, d_out);
+  return cudaGetLastError();
+}
+
+// out[i] = in[i] + r * (in[i + half] - in[i]),  i < half;   EF output
+template <int DIM>
+__global__ void fold_msb_kernel(const uint32_t* __restrict__ in, uint64_t half, Ef r, uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half) return;
+  Ef o;
+  if (DIM == 1) {
+    const uint32_t a = __ldg(in + i), b = __ldg(in + i + half);
+    o = ef_add_base(ef_mul_base(r, kb_sub(b, a)), a);
+  } else {
+    Ef a, b;
+#pragma unroll
+    for (int c = 0; c < 5; c++) a.c[c] = __ldg(in + 5 * i + c), b.c[c] = __ldg(in + 5 * (i + half) + c);
+    o = ef_add(a, ef_mul(r, ef_sub(b, a)));
+  }
+#pragma unroll
+  for (int c = 0; c < 5; c++) out[5 * i + c] = o.c[c];
+}
+
+cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, uint32_t dim, const uint32_t r[5],
+                     uint32_t* d_out) {
+  if ((dim != 1 && dim != 5) || n_in < 2) return cudaErrorInvalidValue;
+  Ef rr;
+  for (int c = 0; c < 5; c++) rr.c[c] = r[c];
+  const uint64_t half = n_in / 2;
+  const unsigned blocks = (unsigned)((half + 255) / 256);
+  if (dim == 1)
+    fold_msb_kernel<1><<<blocks, 256, 0, stream>>>(d_in, half, rr, d_out);
+  else
+    fold_msb_kernel<5><<<blocks, 256, 0, stream>>>(d_in, half, rr, d_out);
+  return cudaGetLastError();
+}
+
+}  // namespace lm

@@ -1,0 +1,18 @@
+// Internal (C++) launch interface of poly.cu; the public C ABI is include/leanmultisig_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace lm {
+// d_out[b] = scalar * eq(point, b), b < 2^k big-endian; point is k x 5 words on the device
+cudaError_t eq_table(cudaStream_t stream, const uint32_t* d_point, int k, const uint32_t scalar[5], uint32_t* d_out);
+// scratch (in u32 words) mle_eval needs for an n_vars-variate polynomial
+size_t mle_eval_scratch_words(uint32_t n_vars);
+// d_out[0..5) = MLE(evals)(point); evals[live_len..) are zero and never read
+cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint64_t live_len,
+                     const uint32_t* d_point, uint32_t* d_scratch, uint32_t* d_out);
+// d_out (n_in / 2 EF) = MSB-first fold of d_in (n_in elements of `dim` words) with challenge r
+cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, uint32_t dim, const uint32_t r[5],
+                     uint32_t* d_out);
+}  // namespace lm

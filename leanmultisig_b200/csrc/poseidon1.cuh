@@ -1,0 +1,177 @@
+// Poseidon1-KoalaBear width-16 permutation / 2-to-1 compression for sm_100a, one state per thread.
+//
+// Computes exactly what the reference's Poseidon1KoalaBear16::permute / compress_in_place compute
+//   crates/backend/koala-bear/src/poseidon1_koalabear_16.rs:873-912 (permute_generic)
+//   .../poseidon1_koalabear_16.rs:934-1016 (permute_simd), :1020-1030 (compress_in_place)
+// but is organised for a GPU integer pipe instead of 16-lane AVX-512:
+//
+//  * Full rounds.  State lanes are held as v * R^e (R = 2^32) with a per-round exponent e that is allowed
+//    to drift: S-box = two lazy Montgomery products (v^3 R^(3e-2)); the circulant MDS has entries <= 101, so
+//    it is 16 IMAD.WIDE per output lane on the un-reduced S-box outputs (sum < 2^41) started from the next
+//    round's constant, followed by ONE Montgomery reduction (2 instructions) that leaves v' R^(3e-3) in
+//    [0, p + 2^9).  Every step is homogeneous, so pre-scaling the round constants by the right power of R
+//    (tools/gen_poseidon1_consts.py) makes the drift free; it is undone once at the end (FIX).
+//  * Partial rounds.  Only lane 0 is non-linear, so lanes 1..15 are never updated round by round.  With
+//    z_k = (lane0 at round k)^3 the whole partial section is   s0_{r+1} = FR0[r] z_r + D_r + sum_{k<r} GTRI[r][k] z_k,
+//    D = G x' (one 21x16 matrix-vector product on the state entering the section) and the lanes leaving the
+//    section are  MI x' + V z + const.  All of it is long dot products with delayed reduction (KbDot):
+//    ~1.1k IMAD.WIDE and ~60 reductions instead of 300 reduced rank-1 updates.
+//
+// Inputs/outputs are canonical Montgomery-form residues in [0, p).
+#pragma once
+#include "kb.cuh"
+
+namespace lm {
+
+struct P1Tables {
+  uint32_t RC0[16];
+  uint32_t RC_INIT[4][16];
+  uint32_t G[21][16];
+  uint32_t G_CONST[21];
+  uint32_t FR0[20];
+  uint32_t GTRI[20][20];
+  uint32_t MI[15][16];
+  uint32_t V[15][20];
+  uint32_t LANE_CONST[15];
+  uint32_t RC_TERM[3][16];
+  uint32_t FIX;
+};
+
+// v^3 * R^-2 for a lane a < 1.43 p; result < 1.75 p
+LM_HD uint32_t p1_sbox_lazy(uint32_t a) { return kb_mul_lazy(kb_mul_lazy(a, a), a); }
+
+// out[i] = redc(init[i] + sum_j C[(i - j) mod 16] * a3[j]),  C = first column of the circulant MDS.
+// N_OUT < 16 computes only the first N_OUT lanes (the digest half of a compression).
+template <int N_OUT>
+LM_HD void p1_mds_redc(const uint32_t a3[16], const uint32_t* init, uint32_t out[16]) {
+#ifdef __CUDA_ARCH__
+  const uint32_t* C = c_kb.mds;  // opaque to ptxas: stays IMAD.WIDE instead of shift / IMAD.HI chains
+#else
+  constexpr uint32_t C[16] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
+#endif
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) {
+    uint64_t acc = init ? (uint64_t)init[i] : 0ull;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const int k = (16 + i - j) & 15;
+      if (k == 0 || k == 9 || k == 13 || k == 15)
+        acc += a3[j];  // coefficient 1: two IADD3 on the otherwise idle ALU pipe
+      else
+        acc = mad_wide(a3[j], C[k], acc);
+    }
+    out[i] = kb_redc_lazy(acc);
+  }
+}
+
+// dot(x[0..16), row) on top of `init`
+LM_HD KbDot p1_dot16(const uint32_t x[16], const uint32_t* row, uint64_t init) {
+  KbDot d(init);
+  d.mac<0>(x[0], row[0]);
+  d.mac<1>(x[1], row[1]);
+  d.mac<2>(x[2], row[2]);
+  d.mac<3>(x[3], row[3]);
+  d.mac<4>(x[4], row[4]);
+  d.mac<5>(x[5], row[5]);
+  d.mac<6>(x[6], row[6]);
+  d.mac<7>(x[7], row[7]);
+  d.mac<8>(x[8], row[8]);
+  d.mac<9>(x[9], row[9]);
+  d.mac<10>(x[10], row[10]);
+  d.mac<11>(x[11], row[11]);
+  d.mac<12>(x[12], row[12]);
+  d.mac<13>(x[13], row[13]);
+  d.mac<14>(x[14], row[14]);
+  d.mac<15>(x[15], row[15]);
+  return d;
+}
+
+// Permutation; N_OUT = 16 for the full permutation, 8 when only the digest half is needed.
+// s: canonical in, canonical out (lanes >= N_OUT are left unspecified).
+template <int N_OUT, class Tab>
+LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
+  uint32_t a[16], x[16];
+
+  // ---- 4 initial full rounds
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = kb_add(s[i], T.RC0[i]);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
+    p1_mds_redc<16>(a, T.RC_INIT[r], x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = x[i];
+  }
+  // x = x' (state entering the partial section, first_rc already added), held at R^-39, lanes < p + 2^9
+
+  // ---- partial section
+  uint32_t d[20];  // D_r, canonical-ish (< p + 2^25), held at R^1
+#pragma unroll
+  for (int r = 0; r < 20; r++) d[r] = p1_dot16(x, T.G[r + 1], T.G_CONST[r + 1]).finish_lazy();
+  uint32_t s0 = p1_dot16(x, T.G[0], 0).finish_lazy();
+
+  // lanes 1..15 leaving the section: start their accumulators with MI x' + const now, then x is dead
+  uint32_t lane_lin[15];
+#pragma unroll
+  for (int i = 0; i < 15; i++) lane_lin[i] = p1_dot16(x, T.MI[i], T.LANE_CONST[i]).finish_lazy();
+
+  uint32_t z[20];
+#pragma unroll
+  for (int r = 0; r < 20; r++) {
+    z[r] = kb_canon(p1_sbox_lazy(s0));
+    // s0_{r+1} = D_r + FR0[r] z_r + sum_{k<r} GTRI[r][k] z_k ;  D_r enters as D_r * 2^32 == D_r * R
+    uint64_t acc = mul_wide(d[r], KB_R1);
+    acc = mad_wide(z[r], T.FR0[r], acc);
+    int terms = 2;
+#pragma unroll
+    for (int k = 0; k < r; k++) {
+      if (terms % 3 == 0) acc = kb_fold(acc);
+      acc = mad_wide(z[k], T.GTRI[r][k], acc);
+      terms++;
+    }
+    s0 = kb_redc_lazy(kb_fold(acc));
+  }
+
+  a[0] = s0;
+#pragma unroll
+  for (int i = 0; i < 15; i++) {
+    uint64_t acc = mul_wide(lane_lin[i], KB_R1);
+    int terms = 1;
+#pragma unroll
+    for (int k = 0; k < 20; k++) {
+      if (terms % 3 == 0) acc = kb_fold(acc);
+      acc = mad_wide(z[k], T.V[i][k], acc);
+      terms++;
+    }
+    a[i + 1] = kb_redc_lazy(kb_fold(acc));
+  }
+
+  // ---- 4 terminal full rounds (first round constant already inside a[])
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
+    p1_mds_redc<16>(a, T.RC_TERM[r], x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = x[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
+  p1_mds_redc<N_OUT>(a, nullptr, x);
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) s[i] = kb_mul(x[i], T.FIX);
+}
+
+// compress_in_place: state <- permute(state) + state, only the first N_OUT lanes are produced.
+template <int N_OUT, class Tab>
+LM_HD void p1_compress(uint32_t s[16], const Tab& T) {
+  uint32_t in[N_OUT];
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) in[i] = s[i];
+  p1_permute<N_OUT>(s, T);
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) s[i] = kb_add(s[i], in[i]);
+}
+
+}  // namespace lm

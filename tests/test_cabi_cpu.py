@@ -1,0 +1,81 @@
+"""CPU tier: the C-ABI library loads, exports every declared symbol, and fails loudly without a GPU."""
+import ctypes as C
+import subprocess
+import sys
+import os
+
+import numpy as np
+import pytest
+
+import leanmultisig_b200 as L
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = L.lib()
+    names = L.declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_no_cpu_fallback():
+    lib = L.lib()
+    if lib.lm_device_count() > 0:
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = lib.lm_init(0, 20, C.byref(h))
+    assert rc == -3 and b"no CPU path" in lib.lm_last_error()
+    with pytest.raises(L.LmError):
+        L.Context(0, 20)
+
+
+def test_product_does_not_import_oracle():
+    # the product package must never reach into oracle/
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "leanmultisig_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in txt and "liboracle" not in txt and '"oracle/' not in txt, f
+
+
+def test_generated_poseidon_tables_are_current():
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_poseidon1_consts.py"), "--check"]) == 0
+
+
+@pytest.fixture(scope="module")
+def hostcheck():
+    """The kernel's arithmetic headers compiled for the host (tests/hostcheck): same code the GPU runs."""
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
+    so = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
+    deps = [src] + [os.path.join(ROOT, "leanmultisig_b200", "csrc", f) for f in ("kb.cuh", "poseidon1.cuh", "poseidon1_tables.inc")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    for f in ("hc_kb_mul", "hc_kb_add", "hc_kb_sub", "hc_r2"):
+        getattr(lib, f).restype = C.c_uint32
+    return lib
+
+
+def test_kernel_arithmetic_on_host_matches_oracle(hostcheck, rng):
+    x = O.random_field(rng, (512, 16))
+    x[0] = O.P - 1
+    x[1] = 0
+    y = x.copy()
+    hostcheck.hc_poseidon1_permute(y.ctypes.data_as(O.u32p), C.c_uint64(len(y)))
+    assert np.array_equal(y, O.poseidon1_permute(x, dense=True))
+    y = x.copy()
+    hostcheck.hc_poseidon1_compress8(y.ctypes.data_as(O.u32p), C.c_uint64(len(y)))
+    assert np.array_equal(y[:, :8], O.poseidon1_compress(x)[:, :8])
+    a, b = O.random_field(rng, (300, 5)), O.random_field(rng, (300, 5))
+    out = np.empty_like(a)
+    hostcheck.hc_ef_mul(a.ctypes.data_as(O.u32p), b.ctypes.data_as(O.u32p), out.ctypes.data_as(O.u32p), C.c_uint64(300))
+    for i in range(300):
+        assert np.array_equal(out[i], O.ef_mul(a[i], b[i]))
+    for u, v in [(0, 0), (O.P - 1, O.P - 1), (1, O.P - 1), (12345, 678910)]:
+        assert hostcheck.hc_kb_mul(u, v) == O.kb_mul(u, v)
+        assert hostcheck.hc_kb_add(u, v) == (u + v) % O.P
+        assert hostcheck.hc_kb_sub(u, v) == (u - v) % O.P
+    assert hostcheck.hc_r2() == pow(2, 64, O.P)
