@@ -99,6 +99,12 @@ int lm_dev_dft(lm_ctx* ctx, uint32_t* d_mat, uint64_t height, uint64_t width);
 /* build_merkle_tree_koalabear (crates/whir/src/merkle.rs:59-88): d_layers = (2*height - 1) x 8 words */
 int lm_dev_merkle_tree(lm_ctx* ctx, const uint32_t* d_mat, uint64_t height, uint32_t stored_width,
                        uint32_t full_width, uint32_t effective_width, uint32_t* d_layers);
+/* the two halves of lm_dev_merkle_tree, separately launchable (per-kernel timing): first_digest_layer
+ * (crates/whir/src/merkle.rs:215-288) into d_layers[0 .. height), then MerkleTree::from_first_layer
+ * (crates/backend/symetric/src/merkle.rs:21-35) over the already filled leaf layer */
+int lm_dev_merkle_leaves(lm_ctx* ctx, const uint32_t* d_mat, uint64_t height, uint32_t stored_width,
+                         uint32_t full_width, uint32_t effective_width, uint32_t* d_layers);
+int lm_dev_merkle_levels(lm_ctx* ctx, uint32_t* d_layers, uint64_t height);
 /* eval_multilinear (evals.rs:142) with device-resident evals and point; d_out: 5 words */
 int lm_dev_mle_eval(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_t elem_dim, uint64_t live_len,
                     const uint32_t* d_point, uint32_t* d_out);

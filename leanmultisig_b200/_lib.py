@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
             "lm_dev_reorder_and_dft": [vp, vp, u32, u32, u32, u32, u32, vp],
             "lm_dev_dft": [vp, vp, u64, u64],
             "lm_dev_merkle_tree": [vp, vp, u64, u32, u32, u32, vp],
+            "lm_dev_merkle_leaves": [vp, vp, u64, u32, u32, u32, vp],
+            "lm_dev_merkle_levels": [vp, vp, u64],
             "lm_dev_mle_eval": [vp, vp, u32, u32, u64, vp, vp],
             "lm_dev_fold_msb": [vp, vp, u64, u32, u32p, vp],
             "lm_dev_eq_table": [vp, u32p, u32, u32p, vp],

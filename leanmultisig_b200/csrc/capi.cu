@@ -213,6 +213,24 @@ int lm_dev_merkle_tree(lm_ctx* c, const uint32_t* d_mat, uint64_t h, uint32_t st
   return LM_OK;
 }
 
+int lm_dev_merkle_leaves(lm_ctx* c, const uint32_t* d_mat, uint64_t h, uint32_t stored_w, uint32_t full_w,
+                         uint32_t eff_w, uint32_t* d_layers) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_merkle_leaves: ctx is null");
+  if (full_w % 8 || full_w < 16 || eff_w > full_w || stored_w > full_w)
+    return fail(LM_ERR_INVALID, "merkle: widths full=%u stored=%u effective=%u", full_w, stored_w, eff_w);
+  CU(cudaSetDevice(c->device));
+  CU(lm::merkle_leaf_digests(c->stream, d_mat, h, stored_w, full_w, eff_w, d_layers));
+  return LM_OK;
+}
+
+int lm_dev_merkle_levels(lm_ctx* c, uint32_t* d_layers, uint64_t h) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_merkle_levels: ctx is null");
+  if (h == 0 || (h & (h - 1))) return fail(LM_ERR_INVALID, "merkle: height %llu is not a power of two", (unsigned long long)h);
+  CU(cudaSetDevice(c->device));
+  CU(lm::merkle_tree_from_digests(c->stream, d_layers, h));
+  return LM_OK;
+}
+
 int lm_dev_mle_eval(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint64_t live_len,
                     const uint32_t* d_point, uint32_t* d_out) {
   if (!c) return fail(LM_ERR_INVALID, "lm_dev_mle_eval: ctx is null");

@@ -10,8 +10,9 @@ n_vars = int(sys.argv[1]) if len(sys.argv) > 1 else 28
 k, r = 7, 1
 live = 1 << (n_vars - 1)
 ctx = L.Context(0, 24)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
 ctx.set_stream(stream.cuda_stream)
+torch.cuda.set_stream(stream)
 P = 0x7F000001
 g = torch.Generator(device="cuda").manual_seed(0)
 ev = (torch.randint(0, P, (live,), dtype=torch.int64, device="cuda", generator=g)).to(torch.int32)
