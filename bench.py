@@ -223,12 +223,14 @@ def run_b200(args):
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
+        launches0 = l.lm_kernel_launches()
         # ---- kernel-level timed region: K steps, L2 flushed between steps (flush excluded via events per step)
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
         for k in range(args.steps):
             step_dev(evs[k])
             flush.zero_()
         barrier()
+        launches = l.lm_kernel_launches() - launches0
         t_ntt = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
         t_leaf = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
         t_lvl = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
@@ -282,7 +284,7 @@ def run_b200(args):
                              "unit": "GB/s"},
             "e2e": {"value": world * elems_per_commit / (t_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": t_e2e,
                     "h2d_bytes_per_step": live * 4, "d2h_bytes_per_step": 32},
-            "gpu_launches": args.steps * 6,
+            "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
         line["roofline_commit"]["frac"] = line["roofline_commit"]["achieved"] / peak

@@ -37,6 +37,8 @@ typedef struct lm_tree lm_tree; /* committed matrix + all Merkle layers (+ the p
 
 const char* lm_last_error(void);
 int lm_device_count(void);
+/* number of CUDA kernels this library has launched so far in this process */
+uint64_t lm_kernel_launches(void);
 
 /* Replaces setup_prover / precompute_dft_twiddles (src/lib.rs:13-16, crates/whir/src/utils.rs:200-202) and the
  * OnceLock Poseidon constants (poseidon1_koalabear_16.rs:575): selects `device`, creates a stream and uploads

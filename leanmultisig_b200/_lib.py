@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
             raise RuntimeError(f"{LIB_PATH} is missing and could not be built; the CUDA extension is required")
         L = C.CDLL(LIB_PATH)
         L.lm_last_error.restype = C.c_char_p
+        L.lm_kernel_launches.restype = C.c_uint64
+        L.lm_kernel_launches.argtypes = []
         vp, sz, u32, u64, i = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
         sig = {
             "lm_device_count": [],

@@ -12,6 +12,11 @@
 #include "merkle.h"
 #include "ntt.h"
 #include "poly.h"
+#include "launch_count.h"
+
+namespace lm {
+std::atomic<uint64_t> g_kernel_launches{0};
+}
 
 namespace {
 
@@ -73,6 +78,8 @@ struct lm_tree {
 extern "C" {
 
 const char* lm_last_error(void) { return g_err; }
+
+uint64_t lm_kernel_launches(void) { return lm::g_kernel_launches.load(); }
 
 int lm_device_count(void) {
   int n = 0;

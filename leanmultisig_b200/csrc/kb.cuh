@@ -53,13 +53,16 @@ LM_HD uint32_t kb_neg(uint32_t a) { return a ? KB_P - a : 0u; }
 struct KbOpaque {
   uint32_t p;
   uint32_t mds[16];
+  double mds_d[16];
 };
-static __constant__ KbOpaque c_kb = {KB_P, {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1}};
+static __constant__ KbOpaque c_kb = {KB_P,
+                                     {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1},
+                                     {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1}};
 #endif
 #ifdef __CUDA_ARCH__
 #define LM_KB_P_OPAQUE (c_kb.p)
 #else
-#define LM_KB_P_OPAQUE KB_P
+#define LM_KB_P_OPAQUE (c_kb.p)
 #endif
 
 LM_HD uint64_t mul_wide(uint32_t a, uint32_t b) {

@@ -14,6 +14,7 @@
 //                        every intermediate layer (all layers are retained for openings).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "launch_count.h"
 #include "merkle.h"
 #include "poseidon1.cuh"
 
@@ -25,6 +26,10 @@ __constant__ P1Tables c_p1 =
 static const P1Tables h_p1 =
 #include "poseidon1_tables.inc"
     ;
+
+#ifndef LEAF_MIN_BLOCKS
+#define LEAF_MIN_BLOCKS 3
+#endif
 
 struct State16 {
   uint32_t v[16];
@@ -48,7 +53,7 @@ __device__ __forceinline__ void load_chunk8(const uint32_t* __restrict__ row, in
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, LEAF_MIN_BLOCKS)
 leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t lim, uint32_t virt_w,
                    int from_state, State16 init, uint32_t* __restrict__ digests) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,24 +61,43 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
   const uint32_t* row = mat + r * stored_w;
   const bool vec_ok = (stored_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mat) & 15) == 0);
   uint32_t s[16];
-  int64_t chunk = (int64_t)(virt_w / 8) - 1;  // index of the right-most rate chunk not yet absorbed
+  // One compression call site (the unrolled permutation is ~100 KiB of code): the sponge absorbs rate chunks
+  // n-1, n-2, ..., 0 into lanes 8..15; without a precomputed state the first compression also takes chunk n-2
+  // as lanes 0..7, so the chunk sequence is n-1, n-3, n-4, ...
+  const int64_t n_chunks = virt_w / 8;
+  int64_t chunk = n_chunks - 1, n_comp = n_chunks;
   if (from_state) {
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = init.v[i];
   } else {
-    // first compression takes the right-most 16 elements
-    load_chunk8(row, 8 * (chunk - 1), lim, vec_ok, s);
-    load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
-    chunk -= 2;
-    p1_compress<8>(s, c_p1);
+    load_chunk8(row, 8 * (n_chunks - 2), lim, vec_ok, s);
+    n_comp = n_chunks - 1;
   }
-  for (; chunk >= 0; chunk--) {
+  for (int64_t it = 0; it < n_comp; it++) {
     load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
     p1_compress<8>(s, c_p1);
+    chunk -= (it == 0 && !from_state) ? 2 : 1;
   }
   uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
   out[0] = make_uint4(s[0], s[1], s[2], s[3]);
   out[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// One level: next[i] = C(prev[2i] || prev[2i+1])[0..8), one thread per parent.  Used while a level still fills
+// the machine; the short tail of the tree goes through tree_levels_kernel below.
+__global__ void __launch_bounds__(128)
+tree_level_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* __restrict__ next) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_next) return;
+  uint32_t s[16];
+  const uint4* src = reinterpret_cast<const uint4*>(prev + 16 * i);
+  const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+  s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
+  s[8] = c.x, s[9] = c.y, s[10] = c.z, s[11] = c.w, s[12] = d.x, s[13] = d.y, s[14] = d.z, s[15] = d.w;
+  p1_compress<8>(s, c_p1);
+  uint4* dst = reinterpret_cast<uint4*>(next + 8 * i);
+  dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
 // layer0: n0 digests (n0 = 2 * T * gridDim.x at full size). CTA b owns digests [b*2T, (b+1)*2T) and writes
@@ -150,7 +174,7 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
   }
   const int T = 128;
   const uint64_t blocks = (h + T - 1) / T;
-  leaf_sponge_kernel<<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests);
+  leaf_sponge_kernel<<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests); count_launch();
   return cudaGetLastError();
 }
 
@@ -159,13 +183,22 @@ cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, ui
   constexpr int T = 128;
   uint32_t* cur = d_layers;
   uint64_t n = h;
+  // wide levels: one launch per level, every thread busy
+  while (n / 2 >= 8192) {
+    uint32_t* next = cur + 8 * n;
+    tree_level_kernel<<<(unsigned)((n / 2 + 127) / 128), 128, 0, stream>>>(cur, n / 2, next); count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    cur = next;
+    n >>= 1;
+  }
   while (n > 1) {
     int levels = 0;
     uint64_t m = n;
     while (m > 1 && levels < 8) m >>= 1, levels++;  // 2T = 256 digests per CTA -> up to 8 levels
     const uint64_t blocks = (n + 2 * T - 1) / (2 * T);
     uint32_t* next = cur + 8 * n;
-    tree_levels_kernel<T><<<(unsigned)blocks, T, 0, stream>>>(cur, n, levels, next);
+    tree_levels_kernel<T><<<(unsigned)blocks, T, 0, stream>>>(cur, n, levels, next); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     for (int l = 0; l < levels; l++) {
@@ -200,7 +233,7 @@ cudaError_t merkle_open_gather(cudaStream_t stream, const uint32_t* d_mat, const
   if (n == 0) return cudaSuccess;
   uint32_t log_h = 0;
   while (((uint64_t)1 << log_h) < h) log_h++;
-  open_gather_kernel<<<n, 128, 0, stream>>>(d_mat, d_layers, h, log_h, stored_w, full_w, d_indices, d_rows, d_paths);
+  open_gather_kernel<<<n, 128, 0, stream>>>(d_mat, d_layers, h, log_h, stored_w, full_w, d_indices, d_rows, d_paths); count_launch();
   return cudaGetLastError();
 }
 
@@ -225,7 +258,7 @@ __global__ void __launch_bounds__(128) permute_states_kernel(uint32_t* states, u
 
 cudaError_t poseidon1_states(cudaStream_t stream, uint32_t* d_states, uint64_t n, int compress) {
   if (n == 0) return cudaSuccess;
-  permute_states_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_states, n, compress);
+  permute_states_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_states, n, compress); count_launch();
   return cudaGetLastError();
 }
 

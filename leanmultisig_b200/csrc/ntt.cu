@@ -16,6 +16,7 @@
 // (identities on repeated data) are skipped.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "launch_count.h"
 #include "kb.cuh"
 #include "ntt.h"
 
@@ -46,7 +47,7 @@ cudaError_t ntt_fill_twiddles(cudaStream_t stream, uint32_t* d_tw, unsigned log_
   if (log_n == 0) return cudaSuccess;
   const uint64_t n_half = (uint64_t)1 << (log_n - 1);
   const uint32_t g = two_adic_generator_monty(log_n);
-  twiddle_kernel<<<(unsigned)((n_half + 255) / 256), 256, 0, stream>>>(d_tw, n_half, g);
+  twiddle_kernel<<<(unsigned)((n_half + 255) / 256), 256, 0, stream>>>(d_tw, n_half, g); count_launch();
   return cudaGetLastError();
 }
 
@@ -78,37 +79,38 @@ __device__ __forceinline__ void bfly4(uint4& a, uint4& b, uint32_t t) {
 constexpr int TILE_COLS = 8;       // u32 columns per tile = 32 B per row
 constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory
 
+// 16-byte slot of (row j, half) inside the shared tile.  The XOR folds row bits 3..4 into the slot index so that the
+// 8 threads of an LDS.128 phase hit 8 distinct slots both for consecutive rows and for rows 8/16 apart (the
+// first register group of a pass); the un-swizzled layout was 2- to 4-way bank conflicted there (ncu: 50 %).
+__device__ __forceinline__ int tile_slot(int j, int half) { return ((j << 1) | half) ^ (((j >> 3) & 3) << 1); }
+
 // One group of G layers (local layers lp .. lp+G-1) on the shared tile, radix 2^G in registers.
 // Work item = (u, half): rows j0 + q * 2^lp (q < 2^G) of 16-byte half `half`.
+// tw_s: per-CTA twiddles, tw_s[(1 << ll) + i] = twiddle of local layer ll for (row index mod 2^ll) == i.
 template <int G>
-__device__ __forceinline__ void tile_group(uint4* tile, int L, int lp, int l0, uint64_t row_lo, int log_h,
-                                           const uint32_t* __restrict__ tw, int tw_shift) {
+__device__ __forceinline__ void tile_group(uint4* tile, const uint32_t* tw_s, int L, int lp) {
   constexpr int Q = 1 << G;
   const int n_items = 1 << (L - G + 1);
   for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
-    // consecutive threads -> consecutive 16-byte slots whenever the row stride allows it
     const int half = item & 1;
     const int u = item >> 1;
-    const int j0 = ((u >> lp) << (lp + G)) | (u & ((1 << lp) - 1));
+    const int j_lo = u & ((1 << lp) - 1);
+    const int j0 = ((u >> lp) << (lp + G)) | j_lo;
     uint4 v[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) v[q] = tile[(j0 + (q << lp)) * 2 + half];
+    for (int q = 0; q < Q; q++) v[q] = tile[tile_slot(j0 + (q << lp), half)];
 #pragma unroll
     for (int s = 0; s < G; s++) {
-      const int l = l0 + lp + s;  // global layer
-      // twiddle exponent of the low row: ((row mod 2^l) << (log_h - l - 1)), row = row_lo + j * 2^l0
+      const uint32_t* tw_l = tw_s + (1 << (lp + s));
 #pragma unroll
       for (int q = 0; q < Q; q++) {
         if (q & (1 << s)) continue;
-        const uint64_t jm = (uint64_t)(j0 & ((1 << lp) - 1)) + ((uint64_t)(q & ((1 << s) - 1)) << lp);
-        const uint64_t row_mod = row_lo + (jm << l0);
-        const uint64_t e = row_mod << (log_h - l - 1);
-        const uint32_t t = __ldg(tw + (e << tw_shift));
+        const uint32_t t = tw_l[j_lo + ((q & ((1 << s) - 1)) << lp)];
         bfly4(v[q], v[q | (1 << s)], t);
       }
     }
 #pragma unroll
-    for (int q = 0; q < Q; q++) tile[(j0 + (q << lp)) * 2 + half] = v[q];
+    for (int q = 0; q < Q; q++) tile[tile_slot(j0 + (q << lp), half)] = v[q];
   }
 }
 
@@ -118,7 +120,8 @@ __device__ __forceinline__ void tile_group(uint4* tile, int L, int lp, int l0, u
 __global__ void __launch_bounds__(512)
 ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
                 int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift) {
-  extern __shared__ uint4 tile[];  // [2^L][2]
+  extern __shared__ uint4 tile[];  // [2^L][2] slots, then 2^L twiddle words
+  uint32_t* tw_s = reinterpret_cast<uint32_t*>(tile + ((size_t)2 << L));
   const uint32_t n_col_tiles = (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
   const uint64_t col0 = (uint64_t)(blockIdx.x % n_col_tiles) * TILE_COLS;  // column tile varies fastest: CTAs that
   const uint64_t grp = blockIdx.x / n_col_tiles;                           // run together cover whole rows
@@ -128,27 +131,35 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
   const int n_rows = 1 << L;
   const bool two_halves = col0 + 8 <= w;  // w % 4 == 0 guaranteed by the launcher
 
+  // twiddles of this CTA: layer l = l0 + ll pairs rows whose index mod 2^l is row_lo + (i << l0), i < 2^ll,
+  // with w_h^((row mod 2^l) << (log_h - l - 1))
+  for (int k = threadIdx.x + 1; k < n_rows; k += blockDim.x) {
+    const int ll = 31 - __clz(k);
+    const uint64_t i = (uint64_t)k - ((uint64_t)1 << ll);
+    const uint64_t e = (row_lo + (i << l0)) << (log_h - (l0 + ll) - 1);
+    tw_s[k] = __ldg(tw + (e << tw_shift));
+  }
+
   if (src == nullptr) {
     for (int item = threadIdx.x; item < 2 * n_rows; item += blockDim.x) {
       const int j = item >> 1, half = item & 1;
-      if (half == 1 && !two_halves) {
-        tile[item] = make_uint4(0, 0, 0, 0);
-        continue;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (half == 0 || two_halves) {
+        const uint64_t row = row_base + ((uint64_t)j << l0);
+        v = *reinterpret_cast<const uint4*>(mat + row * w + col0 + 4 * half);
       }
-      const uint64_t row = row_base + ((uint64_t)j << l0);
-      tile[item] = *reinterpret_cast<const uint4*>(mat + row * w + col0 + 4 * half);
+      tile[tile_slot(j, half)] = v;
     }
   } else {
     // column c of the tile is contiguous in src: consecutive threads read consecutive rows of one column
     uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
     const int n_cols_here = two_halves ? 8 : 4;
-    for (int item = threadIdx.x; item < n_cols_here * n_rows; item += blockDim.x) {
+    for (int item = threadIdx.x; item < 8 * n_rows; item += blockDim.x) {
       const int c = item >> L, j = item & (n_rows - 1);
       const uint64_t row = row_base + j;
-      t32[j * 8 + c] = __ldg(src + (((col0 + c) << log_block) + row) / ((uint64_t)1 << r));
+      const uint32_t v = c < n_cols_here ? __ldg(src + ((((col0 + c) << log_block) + row) >> r)) : 0u;
+      t32[tile_slot(j, c >> 2) * 4 + (c & 3)] = v;
     }
-    if (!two_halves)
-      for (int j = threadIdx.x; j < n_rows; j += blockDim.x) tile[2 * j + 1] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
 
@@ -157,11 +168,11 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
     const int rem = L - lp;
     const int g = rem <= 4 ? (rem == 4 ? 2 : rem) : 3;  // 3,3,...,then 3 / 2+2 / 2 / 1
     if (g == 3)
-      tile_group<3>(tile, L, lp, l0, row_lo, log_h, tw, tw_shift);
+      tile_group<3>(tile, tw_s, L, lp);
     else if (g == 2)
-      tile_group<2>(tile, L, lp, l0, row_lo, log_h, tw, tw_shift);
+      tile_group<2>(tile, tw_s, L, lp);
     else
-      tile_group<1>(tile, L, lp, l0, row_lo, log_h, tw, tw_shift);
+      tile_group<1>(tile, tw_s, L, lp);
     lp += g;
     __syncthreads();
   }
@@ -170,7 +181,7 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
     const int j = item >> 1, half = item & 1;
     if (half == 1 && !two_halves) continue;
     const uint64_t row = row_base + ((uint64_t)j << l0);
-    *reinterpret_cast<uint4*>(mat + row * w + col0 + 4 * half) = tile[item];
+    *reinterpret_cast<uint4*>(mat + row * w + col0 + 4 * half) = tile[tile_slot(j, half)];
   }
 }
 
@@ -203,14 +214,14 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     if (d_src != nullptr) return cudaErrorInvalidValue;
     for (int l = skip; l < log_h; l++) {
       const uint64_t n = (h / 2) * w;
-      ntt_layer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_mat, h, w, l, log_h, d_tw, tw_shift);
+      ntt_layer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_mat, h, w, l, log_h, d_tw, tw_shift); count_launch();
     }
     return cudaGetLastError();
   }
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG) * 32);
+    cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG) * 36);
     attr_set = true;
   }
   // split log_h layers into ceil(log_h / 11) passes of nearly equal depth
@@ -221,9 +232,9 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     const int sk = skip_left < L ? skip_left : L;
     skip_left -= sk;
     const uint64_t n_cta = ((w + TILE_COLS - 1) / TILE_COLS) * (h >> L);
-    const size_t smem = ((size_t)1 << L) * 32;
+    const size_t smem = ((size_t)1 << L) * 36;  // tile + per-CTA twiddles
     ntt_pass_kernel<<<(unsigned)n_cta, 512, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
-                                                            log_block, r, d_tw, tw_shift);
+                                                            log_block, r, d_tw, tw_shift); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     l0 += L;
@@ -247,7 +258,7 @@ cudaError_t ntt_reorder_and_dft(cudaStream_t stream, const uint32_t* d_evals, ui
   const int skip = (int)(log_inv_rate < log_block ? log_inv_rate : log_block);
   if (dim == 1 && w % 4 == 0) return run_layers(stream, d_out, d_evals, log_block, log_inv_rate, h, w, skip, d_tw, tw_log_n);
   const uint64_t n = h * w;
-  gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_evals, d_out, h, dft_n_cols, dim, log_block, log_inv_rate);
+  gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_evals, d_out, h, dft_n_cols, dim, log_block, log_inv_rate); count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return run_layers(stream, d_out, nullptr, 0, 0, h, w, skip, d_tw, tw_log_n);

@@ -12,6 +12,7 @@
 // reduction; the kernel is HBM-bound (4 B per element read once).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "launch_count.h"
 #include "kb.cuh"
 #include "poly.h"
 
@@ -45,7 +46,7 @@ cudaError_t eq_table(cudaStream_t stream, const uint32_t* d_point, int k, const 
   Ef s;
   for (int c = 0; c < 5; c++) s.c[c] = scalar[c];
   const uint64_t n = (uint64_t)1 << k;
-  eq_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_point, k, s, d_out);
+  eq_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_point, k, s, d_out); count_launch();
   return cudaGetLastError();
 }
 
@@ -174,9 +175,9 @@ cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_va
                                                                      d_eq_lo, d_partial);
   else
     mle_eval_kernel<5><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_evals, lo_vars, live_rows, rows_per_cta, d_eq_hi,
-                                                                     d_eq_lo, d_partial);
+                                                                     d_eq_lo, d_partial); count_launch();
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  sum_partials_kernel<<<1, 256, 0, stream>>>(d_partial, (int)n_cta, d_out);
+  sum_partials_kernel<<<1, 256, 0, stream>>>(d_partial, (int)n_cta, d_out); count_launch();
   return cudaGetLastError();
 }
 
@@ -209,7 +210,7 @@ cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, u
   if (dim == 1)
     fold_msb_kernel<1><<<blocks, 256, 0, stream>>>(d_in, half, rr, d_out);
   else
-    fold_msb_kernel<5><<<blocks, 256, 0, stream>>>(d_in, half, rr, d_out);
+    fold_msb_kernel<5><<<blocks, 256, 0, stream>>>(d_in, half, rr, d_out); count_launch();
   return cudaGetLastError();
 }
 

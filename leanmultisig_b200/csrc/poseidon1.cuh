@@ -35,6 +35,8 @@ struct P1Tables {
   uint32_t LANE_CONST[15];
   uint32_t RC_TERM[3][16];
   uint32_t FIX;
+  double RC_INIT_D[4][16];  // RC_INIT / RC_TERM again as doubles (exact integers < p)
+  double RC_TERM_D[3][16];
 };
 
 // v^3 * R^-2 for a lane a < 1.43 p; result < 1.75 p
@@ -42,26 +44,41 @@ LM_HD uint32_t p1_sbox_lazy(uint32_t a) { return kb_mul_lazy(kb_mul_lazy(a, a), 
 
 // out[i] = redc(init[i] + sum_j C[(i - j) mod 16] * a3[j]),  C = first column of the circulant MDS.
 // N_OUT < 16 computes only the first N_OUT lanes (the digest half of a compression).
+//
+// Device version: the sum (< 2^41) is accumulated EXACTLY on the FP64 pipe.  Measured on B200
+// (profiles/r01_int_pipes2.txt): IMAD.WIDE issues once per 4 cycles per SM sub-partition (6 with a 64-bit
+// addend), DFMA once per ~2, and the two pipes overlap, so 16 DFMA per lane replace 12 IMAD.WIDE + adds.
+// u32 -> f64 is the 2^52 trick (one DADD), f64 -> (lo, hi) another DADD; every intermediate is an integer
+// below 2^53, so the result is bit-identical to the integer evaluation on the host path.
 template <int N_OUT>
-LM_HD void p1_mds_redc(const uint32_t a3[16], const uint32_t* init, uint32_t out[16]) {
+LM_HD void p1_mds_redc(const uint32_t a3[16], const uint32_t* init, const double* init_d, uint32_t out[16]) {
 #ifdef __CUDA_ARCH__
-  const uint32_t* C = c_kb.mds;  // opaque to ptxas: stays IMAD.WIDE instead of shift / IMAD.HI chains
+  (void)init;
+  constexpr double TWO52 = 4503599627370496.0;
+  double d[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) d[j] = __hiloint2double(0x43300000, (int)a3[j]) - TWO52;
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) {
+    double y = init_d ? init_d[i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) y = fma(c_kb.mds_d[(16 + i - j) & 15], d[j], y);
+    y += TWO52;
+    const uint32_t lo = (uint32_t)__double2loint(y);
+    const uint32_t hi = (uint32_t)__double2hiint(y) - 0x43300000u;
+    out[i] = kb_redc_lazy(((uint64_t)hi << 32) | lo);
+  }
 #else
+  (void)init_d;
   constexpr uint32_t C[16] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
-#endif
 #pragma unroll
   for (int i = 0; i < N_OUT; i++) {
     uint64_t acc = init ? (uint64_t)init[i] : 0ull;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const int k = (16 + i - j) & 15;
-      if (k == 0 || k == 9 || k == 13 || k == 15)
-        acc += a3[j];  // coefficient 1: two IADD3 on the otherwise idle ALU pipe
-      else
-        acc = mad_wide(a3[j], C[k], acc);
-    }
+    for (int j = 0; j < 16; j++) acc += (uint64_t)C[(16 + i - j) & 15] * a3[j];
     out[i] = kb_redc_lazy(acc);
   }
+#endif
 }
 
 // dot(x[0..16), row) on top of `init`
@@ -92,14 +109,20 @@ template <int N_OUT, class Tab>
 LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
   uint32_t a[16], x[16];
 
-  // ---- 4 initial full rounds
+  // ---- 4 initial full rounds.  Kept as a real loop on the device (constants indexed by the round): the fully
+  // unrolled permutation is ~140 KiB of SASS and was starved by instruction fetch (ncu: 19 % of warp cycles in
+  // stall_no_instruction, I-cache hit rate 68 %).
 #pragma unroll
   for (int i = 0; i < 16; i++) a[i] = kb_add(s[i], T.RC0[i]);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int r = 0; r < 4; r++) {
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
-    p1_mds_redc<16>(a, T.RC_INIT[r], x);
+    p1_mds_redc<16>(a, T.RC_INIT[r], T.RC_INIT_D[r], x);
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = x[i];
   }
@@ -147,18 +170,23 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
     a[i + 1] = kb_redc_lazy(kb_fold(acc));
   }
 
-  // ---- 4 terminal full rounds (first round constant already inside a[])
+  // ---- 4 terminal full rounds (first round constant already inside a[]); three looped, the last one only
+  // produces the lanes that are kept
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int r = 0; r < 3; r++) {
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
-    p1_mds_redc<16>(a, T.RC_TERM[r], x);
+    p1_mds_redc<16>(a, T.RC_TERM[r], T.RC_TERM_D[r], x);
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = x[i];
   }
 #pragma unroll
   for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
-  p1_mds_redc<N_OUT>(a, nullptr, x);
+  p1_mds_redc<N_OUT>(a, nullptr, nullptr, x);
 #pragma unroll
   for (int i = 0; i < N_OUT; i++) s[i] = kb_mul(x[i], T.FIX);
 }

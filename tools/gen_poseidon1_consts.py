@@ -256,6 +256,15 @@ def emit(t) -> str:
     arr1("LANE_CONST[15]", t["LANE_CONST"])
     arr2("RC_TERM[3][16]", t["RC_TERM"])
     out.append("  /* FIX */ 0x%08xu," % t["FIX"])
+
+    def darr2(name, rows):
+        out.append("  /* %s (same integers as doubles, for the FP64-pipe MDS) */ {" % name)
+        for row in rows:
+            out.append("  {" + ", ".join("%d.0" % (v % P) for v in row) + "},")
+        out.append("  },")
+
+    darr2("RC_INIT_D[4][16]", t["RC_INIT"])
+    darr2("RC_TERM_D[3][16]", t["RC_TERM"])
     out.append("}")
     return "\n".join(out) + "\n"
 
