@@ -85,6 +85,44 @@ int lm_tree_free(lm_tree* tree);
 int lm_mle_eval(lm_ctx* ctx, const uint32_t* evals, uint32_t n_vars, uint32_t elem_dim, uint64_t live_len,
                 const uint32_t* point, uint32_t out[5]);
 
+/* ---- WHIR open: product sumcheck session -----------------------------------------------------------------
+ * Replaces SumcheckSingle (crates/whir/src/open.rs:323-446) and the bodies it calls; the Fiat-Shamir transcript
+ * stays with the caller, so the reference's run_product_sumcheck / sumcheck_prove_many_rounds loops
+ * (crates/backend/sumcheck/src/product_computation.rs:37-125, prove.rs:86-151) become, per round:
+ *   lm_sc_round / lm_sc_fold_round -> (c0, c2);  c1 = sum - 2 c0 - c2;  transcript absorbs (c0, c1, c2), grinds,
+ *   samples r;  after the last round lm_sc_fold(r).
+ * The session holds the polynomial table p (base field until first folded, then EF) and the weight table w (EF),
+ * both of 2^n_vars entries, MSB-first folding (crates/backend/poly/src/utils.rs:161-186). */
+typedef struct lm_sumcheck lm_sumcheck;
+/* p = the polynomial committed in `tree` (borrowed from the tree, which must outlive the session); w = 0 */
+int lm_sc_new_from_tree(lm_tree* tree, lm_sumcheck** out);
+/* p = host polynomial (2^n_vars entries of elem_dim words, first live_len possibly non-zero); w = 0 */
+int lm_sc_new(lm_ctx* ctx, const uint32_t* evals, uint32_t n_vars, uint32_t elem_dim, uint64_t live_len,
+              lm_sumcheck** out);
+/* combine_statement terms (open.rs:518-584): w[(selector << m) + x] += scalar * eq(point, x)   (point: m x 5)
+ * resp. scalar * next_mle(point, x) (crates/backend/poly/src/next_mle.rs:35).  Also add_new_equality
+ * (open.rs:337-358) with selector 0 and m = n_vars. */
+int lm_sc_add_eq(lm_sumcheck* sc, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]);
+int lm_sc_add_next(lm_sumcheck* sc, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]);
+/* add_new_base_equality (open.rs:360-382): w[x] += sum_q scalars[q] * eq(points[q], x); points: n_q x n_vars
+ * base-field words, scalars: n_q x 5 */
+int lm_sc_add_base_eq(lm_sumcheck* sc, const uint32_t* points, uint32_t n_q, const uint32_t* scalars);
+/* round polynomial h(X) = c0 + c1 X + c2 X^2 of the current tables (product_computation.rs:127-170) */
+int lm_sc_round(lm_sumcheck* sc, uint32_t c0[5], uint32_t c2[5]);
+/* fold both tables with challenge r (n_vars decreases by one) */
+int lm_sc_fold(lm_sumcheck* sc, const uint32_t r[5]);
+/* fold with r and compute the next round polynomial in the same pass (product_computation.rs:242-304) */
+int lm_sc_fold_round(lm_sumcheck* sc, const uint32_t r[5], uint32_t c0[5], uint32_t c2[5]);
+int lm_sc_num_vars(const lm_sumcheck* sc, uint32_t* n_vars, uint32_t* poly_dim);
+/* copy the current tables to the host: poly 2^n_vars x poly_dim words, weights 2^n_vars x 5 (NULL to skip) */
+int lm_sc_read(lm_sumcheck* sc, uint32_t* out_poly, uint32_t* out_weights);
+/* OOD sample on the current (folded) polynomial (open.rs:96-99); point: n_vars x 5 */
+int lm_sc_eval_poly(lm_sumcheck* sc, const uint32_t* point, uint32_t out[5]);
+/* commit the current (folded) polynomial: reorder_and_dft + MerkleData::build of a WHIR round (open.rs:81-91) */
+int lm_sc_commit_poly(lm_sumcheck* sc, uint32_t folding_factor, uint32_t log_inv_rate, lm_tree** out_tree,
+                      uint32_t out_root[8]);
+int lm_sc_free(lm_sumcheck* sc);
+
 /* ---- device-pointer layer (inputs already in HBM; used by the kernel-only benchmark and by lm_* above) -----
  * All pointers are device pointers on ctx's device; work is enqueued on ctx's stream, no synchronisation. */
 int lm_dev_alloc(lm_ctx* ctx, size_t bytes, void** out);

@@ -70,6 +70,19 @@ def lib() -> C.CDLL:
             "lm_tree_read_layers": [vp, u32p],
             "lm_tree_free": [vp],
             "lm_mle_eval": [vp, vp, u32, u32, u64, u32p, u32p],
+            "lm_sc_new_from_tree": [vp, C.POINTER(vp)],
+            "lm_sc_new": [vp, vp, u32, u32, u64, C.POINTER(vp)],
+            "lm_sc_add_eq": [vp, u64, u32p, u32, u32p],
+            "lm_sc_add_next": [vp, u64, u32p, u32, u32p],
+            "lm_sc_add_base_eq": [vp, u32p, u32, u32p],
+            "lm_sc_round": [vp, u32p, u32p],
+            "lm_sc_fold": [vp, u32p],
+            "lm_sc_fold_round": [vp, u32p, u32p, u32p],
+            "lm_sc_num_vars": [vp, u32p, u32p],
+            "lm_sc_read": [vp, u32p, u32p],
+            "lm_sc_eval_poly": [vp, u32p, u32p],
+            "lm_sc_commit_poly": [vp, u32, u32, C.POINTER(vp), u32p],
+            "lm_sc_free": [vp],
             "lm_dev_alloc": [vp, sz, C.POINTER(vp)],
             "lm_dev_free": [vp, vp],
             "lm_dev_upload": [vp, vp, vp, sz],

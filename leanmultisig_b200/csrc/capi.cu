@@ -12,6 +12,7 @@
 #include "merkle.h"
 #include "ntt.h"
 #include "poly.h"
+#include "sumcheck.h"
 #include "launch_count.h"
 
 namespace lm {
@@ -73,6 +74,29 @@ struct lm_tree {
   bool owns_evals = false;
   uint32_t* d_codeword = nullptr;  // height x stored_width
   uint32_t* d_layers = nullptr;    // (2 height - 1) x 8
+};
+
+// Product-sumcheck session of WHIR open (reference: SumcheckSingle, crates/whir/src/open.rs:323-446).
+struct lm_sumcheck {
+  lm_ctx* ctx = nullptr;
+  uint32_t n_vars = 0;       // current number of variables of both tables
+  uint32_t p_dim = 1;        // 1 while the polynomial is still the (borrowed) base-field witness
+  uint64_t p_live = 0;       // entries of p that may be non-zero
+  const uint32_t* d_p = nullptr;  // current polynomial table
+  uint32_t* d_p_owned = nullptr;  // EF table owned by the session (after the first fold) or an uploaded copy
+  uint32_t* d_w = nullptr;        // weights, 2^n_vars EF, folded in place
+  uint32_t* d_out10 = nullptr;    // (c0, c2) of the last round
+  uint32_t* d_scratch = nullptr;
+  size_t scratch_words = 0;
+  int ensure_scratch(size_t words) {
+    if (words <= scratch_words) return LM_OK;
+    if (d_scratch) cudaFree(d_scratch);
+    d_scratch = nullptr;
+    scratch_words = 0;
+    CU(cudaMalloc(&d_scratch, words * sizeof(uint32_t)));
+    scratch_words = words;
+    return LM_OK;
+  }
 };
 
 extern "C" {
@@ -254,7 +278,7 @@ int lm_dev_fold_msb(lm_ctx* c, const uint32_t* d_in, uint64_t n_in, uint32_t dim
   if (!c) return fail(LM_ERR_INVALID, "lm_dev_fold_msb: ctx is null");
   if (n_in < 2 || (n_in & (n_in - 1))) return fail(LM_ERR_INVALID, "fold: length must be a power of two >= 2");
   CU(cudaSetDevice(c->device));
-  CU(lm::fold_msb(c->stream, d_in, n_in, dim, r, d_out));
+  CU(lm::fold_msb(c->stream, d_in, n_in, dim, n_in, r, d_out));
   return LM_OK;
 }
 
@@ -441,6 +465,252 @@ int lm_tree_free(lm_tree* t) {
   if (t->d_layers) cudaFree(t->d_layers);
   delete t;
   return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ WHIR open session
+int lm_sc_free(lm_sumcheck* s) {
+  if (!s) return LM_OK;
+  if (s->ctx) {
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+  }
+  if (s->d_p_owned) cudaFree(s->d_p_owned);
+  if (s->d_w) cudaFree(s->d_w);
+  if (s->d_out10) cudaFree(s->d_out10);
+  if (s->d_scratch) cudaFree(s->d_scratch);
+  delete s;
+  return LM_OK;
+}
+
+static int sc_new_common(lm_ctx* c, uint32_t n_vars, lm_sumcheck** out) {
+  if (!c || !out) return fail(LM_ERR_INVALID, "lm_sc_new: null argument");
+  *out = nullptr;
+  if (n_vars < 1 || n_vars > 32) return fail(LM_ERR_INVALID, "lm_sc_new: n_vars %u out of range", n_vars);
+  CU(cudaSetDevice(c->device));
+  lm_sumcheck* s = new (std::nothrow) lm_sumcheck();
+  if (!s) return fail(LM_ERR_OOM, "lm_sc_new: host allocation failed");
+  s->ctx = c;
+  s->n_vars = n_vars;
+  const size_t w_bytes = ((size_t)5 << n_vars) * sizeof(uint32_t);
+  cudaError_t e = cudaMalloc(&s->d_w, w_bytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_w, 0, w_bytes, c->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_out10, 16 * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    lm_sc_free(s);
+    return cuda_fail(e, "lm_sc_new");
+  }
+  int rc = s->ensure_scratch(lm::prod_round_scratch_words());
+  if (rc != LM_OK) {
+    lm_sc_free(s);
+    return rc;
+  }
+  *out = s;
+  return LM_OK;
+}
+
+int lm_sc_new_from_tree(lm_tree* t, lm_sumcheck** out) {
+  if (!t) return fail(LM_ERR_INVALID, "lm_sc_new_from_tree: tree is null");
+  if (!t->d_evals) return fail(LM_ERR_INVALID, "lm_sc_new_from_tree: the polynomial was not retained by this commit");
+  int rc = sc_new_common(t->ctx, t->n_vars, out);
+  if (rc != LM_OK) return rc;
+  (*out)->d_p = t->d_evals;
+  (*out)->p_dim = t->elem_dim;
+  (*out)->p_live = t->actual_len;
+  return LM_OK;
+}
+
+int lm_sc_new(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, uint64_t live_len, lm_sumcheck** out) {
+  if (!evals && live_len) return fail(LM_ERR_INVALID, "lm_sc_new: evals is null");
+  if (dim != 1 && dim != 5) return fail(LM_ERR_INVALID, "lm_sc_new: elem_dim must be 1 or 5");
+  if (n_vars > 32 || live_len > ((uint64_t)1 << n_vars)) return fail(LM_ERR_INVALID, "lm_sc_new: live_len exceeds 2^n_vars");
+  int rc = sc_new_common(c, n_vars, out);
+  if (rc != LM_OK) return rc;
+  lm_sumcheck* s = *out;
+  cudaError_t e = cudaMalloc(&s->d_p_owned, (live_len ? live_len : 1) * dim * sizeof(uint32_t));
+  if (e == cudaSuccess && live_len)
+    e = cudaMemcpyAsync(s->d_p_owned, evals, live_len * dim * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    lm_sc_free(s);
+    *out = nullptr;
+    return cuda_fail(e, "lm_sc_new upload");
+  }
+  s->d_p = s->d_p_owned;
+  s->p_dim = dim;
+  s->p_live = live_len;
+  return LM_OK;
+}
+
+static int sc_upload_point(lm_sumcheck* s, const uint32_t* point, uint32_t words) {
+  lm_ctx* c = s->ctx;
+  if (words > 64 * 5) return fail(LM_ERR_INVALID, "point too long");
+  if (words) CU(cudaMemcpyAsync(c->d_point, point, words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  return LM_OK;
+}
+
+int lm_sc_add_eq(lm_sumcheck* s, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]) {
+  if (!s || !scalar || (m && !point)) return fail(LM_ERR_INVALID, "lm_sc_add_eq: null argument");
+  if (m > s->n_vars || (selector >> (s->n_vars - m)) != 0)
+    return fail(LM_ERR_INVALID, "lm_sc_add_eq: selector %llu does not fit %u - %u variables", (unsigned long long)selector,
+                s->n_vars, m);
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  int rc = s->ensure_scratch(lm::weights_add_eq_scratch_words(m) + lm::prod_round_scratch_words());
+  if (rc != LM_OK) return rc;
+  if ((rc = sc_upload_point(s, point, 5 * m)) != LM_OK) return rc;
+  CU(lm::weights_add_eq(c->stream, s->d_w, selector, c->d_point, m, scalar, s->d_scratch));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_sc_add_next(lm_sumcheck* s, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]) {
+  if (!s || !scalar || !point) return fail(LM_ERR_INVALID, "lm_sc_add_next: null argument");
+  if (m < 1 || m > s->n_vars || (selector >> (s->n_vars - m)) != 0)
+    return fail(LM_ERR_INVALID, "lm_sc_add_next: bad selector / point length");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  int rc = sc_upload_point(s, point, 5 * m);
+  if (rc != LM_OK) return rc;
+  CU(lm::weights_add_next(c->stream, s->d_w, selector, c->d_point, m, scalar));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_sc_add_base_eq(lm_sumcheck* s, const uint32_t* points, uint32_t n_q, const uint32_t* scalars) {
+  if (!s || (n_q && (!points || !scalars))) return fail(LM_ERR_INVALID, "lm_sc_add_base_eq: null argument");
+  if (n_q == 0) return LM_OK;
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  const uint32_t m = s->n_vars;
+  const size_t tab_words = lm::weights_add_base_eq_scratch_words(m, n_q);
+  int rc = s->ensure_scratch(tab_words + (size_t)n_q * (m + 5) + lm::prod_round_scratch_words());
+  if (rc != LM_OK) return rc;
+  uint32_t* d_pts = s->d_scratch + tab_words;
+  uint32_t* d_sc = d_pts + (size_t)n_q * m;
+  CU(cudaMemcpyAsync(d_pts, points, (size_t)n_q * m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_sc, scalars, (size_t)n_q * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(lm::weights_add_base_eq(c->stream, s->d_w, m, d_pts, n_q, d_sc, s->d_scratch));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+static int sc_fetch_round(lm_sumcheck* s, uint32_t c0[5], uint32_t c2[5]) {
+  uint32_t h[10];
+  CU(cudaMemcpyAsync(h, s->d_out10, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->stream));
+  CU(cudaStreamSynchronize(s->ctx->stream));
+  memcpy(c0, h, 5 * sizeof(uint32_t));
+  memcpy(c2, h + 5, 5 * sizeof(uint32_t));
+  return LM_OK;
+}
+
+int lm_sc_round(lm_sumcheck* s, uint32_t c0[5], uint32_t c2[5]) {
+  if (!s || !c0 || !c2) return fail(LM_ERR_INVALID, "lm_sc_round: null argument");
+  if (s->n_vars < 1) return fail(LM_ERR_INVALID, "lm_sc_round: no variables left");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(lm::prod_round(c->stream, s->d_p, s->p_dim, s->p_live, s->d_w, (uint64_t)1 << s->n_vars, s->d_scratch, s->d_out10));
+  return sc_fetch_round(s, c0, c2);
+}
+
+// make room for the EF polynomial table the first time a base-field polynomial is folded
+static int sc_prepare_fold_target(lm_sumcheck* s, uint32_t** p_out) {
+  const uint64_t half = (uint64_t)1 << (s->n_vars - 1);
+  if (s->p_dim == 5 && s->d_p == s->d_p_owned) {
+    *p_out = s->d_p_owned;  // EF table owned by us: in place
+    return LM_OK;
+  }
+  uint32_t* fresh = nullptr;
+  CU(cudaMalloc(&fresh, half * 5 * sizeof(uint32_t)));
+  *p_out = fresh;
+  return LM_OK;
+}
+static void sc_commit_fold(lm_sumcheck* s, uint32_t* p_out) {
+  if (p_out != s->d_p_owned) {
+    if (s->d_p_owned) {
+      cudaStreamSynchronize(s->ctx->stream);
+      cudaFree(s->d_p_owned);
+    }
+    s->d_p_owned = p_out;
+  }
+  s->d_p = s->d_p_owned;
+  s->p_dim = 5;
+  s->n_vars -= 1;
+  s->p_live = (uint64_t)1 << s->n_vars;
+}
+
+int lm_sc_fold(lm_sumcheck* s, const uint32_t r[5]) {
+  if (!s || !r) return fail(LM_ERR_INVALID, "lm_sc_fold: null argument");
+  if (s->n_vars < 1) return fail(LM_ERR_INVALID, "lm_sc_fold: no variables left");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  uint32_t* p_out = nullptr;
+  int rc = sc_prepare_fold_target(s, &p_out);
+  if (rc != LM_OK) return rc;
+  const uint64_t n = (uint64_t)1 << s->n_vars;
+  CU(lm::fold_msb(c->stream, s->d_p, n, s->p_dim, s->p_live, r, p_out));
+  CU(lm::fold_msb(c->stream, s->d_w, n, 5, n, r, s->d_w));
+  sc_commit_fold(s, p_out);
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_sc_fold_round(lm_sumcheck* s, const uint32_t r[5], uint32_t c0[5], uint32_t c2[5]) {
+  if (!s || !r || !c0 || !c2) return fail(LM_ERR_INVALID, "lm_sc_fold_round: null argument");
+  if (s->n_vars < 2) return fail(LM_ERR_INVALID, "lm_sc_fold_round: needs at least two variables");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  uint32_t* p_out = nullptr;
+  int rc = sc_prepare_fold_target(s, &p_out);
+  if (rc != LM_OK) return rc;
+  const uint64_t n = (uint64_t)1 << s->n_vars;
+  CU(lm::prod_fold_round(c->stream, s->d_p, s->p_dim, s->p_live, s->d_w, n, r, p_out, s->d_w, s->d_scratch, s->d_out10));
+  sc_commit_fold(s, p_out);
+  return sc_fetch_round(s, c0, c2);
+}
+
+int lm_sc_num_vars(const lm_sumcheck* s, uint32_t* n_vars, uint32_t* poly_dim) {
+  if (!s) return fail(LM_ERR_INVALID, "lm_sc_num_vars: null argument");
+  if (n_vars) *n_vars = s->n_vars;
+  if (poly_dim) *poly_dim = s->p_dim;
+  return LM_OK;
+}
+
+int lm_sc_read(lm_sumcheck* s, uint32_t* out_poly, uint32_t* out_weights) {
+  if (!s) return fail(LM_ERR_INVALID, "lm_sc_read: null argument");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  const uint64_t n = (uint64_t)1 << s->n_vars;
+  if (out_poly) {
+    memset(out_poly, 0, n * s->p_dim * sizeof(uint32_t));
+    CU(cudaMemcpyAsync(out_poly, s->d_p, s->p_live * s->p_dim * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (out_weights) CU(cudaMemcpyAsync(out_weights, s->d_w, n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_sc_eval_poly(lm_sumcheck* s, const uint32_t* point, uint32_t out[5]) {
+  if (!s || !point || !out) return fail(LM_ERR_INVALID, "lm_sc_eval_poly: null argument");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  int rc = sc_upload_point(s, point, 5 * s->n_vars);
+  if (rc != LM_OK) return rc;
+  // mle_eval reads whole rows of min(2^n, 1024) entries: only valid when the table is fully materialised
+  const uint64_t n = (uint64_t)1 << s->n_vars;
+  const uint64_t row = n < 1024 ? n : 1024;
+  if (s->p_live % row != 0 && s->p_live != n)
+    return fail(LM_ERR_INVALID, "lm_sc_eval_poly: live prefix must be a multiple of %llu", (unsigned long long)row);
+  rc = lm_dev_mle_eval(c, s->d_p, s->n_vars, s->p_dim, s->p_live, c->d_point, c->d_small);
+  if (rc != LM_OK) return rc;
+  CU(cudaMemcpyAsync(out, c->d_small, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_sc_commit_poly(lm_sumcheck* s, uint32_t folding_factor, uint32_t log_inv_rate, lm_tree** out_tree, uint32_t out_root[8]) {
+  if (!s) return fail(LM_ERR_INVALID, "lm_sc_commit_poly: null argument");
+  return commit_impl(s->ctx, s->d_p, true, s->n_vars, s->p_dim, s->p_live, folding_factor, log_inv_rate, false, out_tree,
+                     out_root);
 }
 
 int lm_mle_eval(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, uint64_t live_len, const uint32_t* point,

@@ -62,7 +62,7 @@ static __constant__ KbOpaque c_kb = {KB_P,
 #ifdef __CUDA_ARCH__
 #define LM_KB_P_OPAQUE (c_kb.p)
 #else
-#define LM_KB_P_OPAQUE (c_kb.p)
+#define LM_KB_P_OPAQUE KB_P
 #endif
 
 LM_HD uint64_t mul_wide(uint32_t a, uint32_t b) {

@@ -183,34 +183,40 @@ cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_va
 
 // out[i] = in[i] + r * (in[i + half] - in[i]),  i < half;   EF output
 template <int DIM>
-__global__ void fold_msb_kernel(const uint32_t* __restrict__ in, uint64_t half, Ef r, uint32_t* __restrict__ out) {
+__global__ void fold_msb_kernel(const uint32_t* in, uint64_t half, uint64_t live, Ef r, uint32_t* out) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half) return;
   Ef o;
   if (DIM == 1) {
-    const uint32_t a = __ldg(in + i), b = __ldg(in + i + half);
+    const uint32_t a = i < live ? __ldg(in + i) : 0u, b = i + half < live ? __ldg(in + i + half) : 0u;
     o = ef_add_base(ef_mul_base(r, kb_sub(b, a)), a);
   } else {
-    Ef a, b;
+    Ef a = ef_zero(), b = ef_zero();
+    if (i < live) {
 #pragma unroll
-    for (int c = 0; c < 5; c++) a.c[c] = __ldg(in + 5 * i + c), b.c[c] = __ldg(in + 5 * (i + half) + c);
+      for (int c = 0; c < 5; c++) a.c[c] = in[5 * i + c];
+    }
+    if (i + half < live) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) b.c[c] = in[5 * (i + half) + c];
+    }
     o = ef_add(a, ef_mul(r, ef_sub(b, a)));
   }
 #pragma unroll
   for (int c = 0; c < 5; c++) out[5 * i + c] = o.c[c];
 }
 
-cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, uint32_t dim, const uint32_t r[5],
-                     uint32_t* d_out) {
+cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, uint32_t dim, uint64_t live,
+                     const uint32_t r[5], uint32_t* d_out) {
   if ((dim != 1 && dim != 5) || n_in < 2) return cudaErrorInvalidValue;
   Ef rr;
   for (int c = 0; c < 5; c++) rr.c[c] = r[c];
   const uint64_t half = n_in / 2;
   const unsigned blocks = (unsigned)((half + 255) / 256);
   if (dim == 1)
-    fold_msb_kernel<1><<<blocks, 256, 0, stream>>>(d_in, half, rr, d_out);
+    fold_msb_kernel<1><<<blocks, 256, 0, stream>>>(d_in, half, live, rr, d_out);
   else
-    fold_msb_kernel<5><<<blocks, 256, 0, stream>>>(d_in, half, rr, d_out); count_launch();
+    fold_msb_kernel<5><<<blocks, 256, 0, stream>>>(d_in, half, live, rr, d_out); count_launch();
   return cudaGetLastError();
 }
 

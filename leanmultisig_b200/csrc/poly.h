@@ -13,6 +13,7 @@ size_t mle_eval_scratch_words(uint32_t n_vars);
 cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint64_t live_len,
                      const uint32_t* d_point, uint32_t* d_scratch, uint32_t* d_out);
 // d_out (n_in / 2 EF) = MSB-first fold of d_in (n_in elements of `dim` words) with challenge r
-cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, uint32_t dim, const uint32_t r[5],
-                     uint32_t* d_out);
+// (entries >= live are zero and not read; EF tables may be folded in place, d_out == d_in)
+cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, uint32_t dim, uint64_t live,
+                     const uint32_t r[5], uint32_t* d_out);
 }  // namespace lm

@@ -1,0 +1,393 @@
+// WHIR-open kernels on sm_100a: statement weights, product-sumcheck rounds, STIR equality updates.
+//
+// Device replacement for
+//   crates/whir/src/open.rs:518-584                        combine_statement (eq / next weights with selectors)
+//   crates/backend/poly/src/next_mle.rs:35-58              matrix_next_mle_folded
+//   crates/whir/src/open.rs:337-382                        add_new_equality / add_new_base_equality
+//   crates/backend/poly/src/eq_mle.rs:372-430              compute_eval_eq_base_packed_batched
+//   crates/backend/sumcheck/src/product_computation.rs:127-170   round polynomial (c0, c2)
+//   crates/backend/sumcheck/src/product_computation.rs:242-304   fold with the previous challenge + next round
+// Tables are AoS EF (5 words) exactly like the reference's Vec<EF>; the polynomial may still be base field in
+// the first round.  MSB-first folding: t'[i] = t[i] + r (t[i + n/2] - t[i]).
+//
+// All kernels stream their tables once (HBM bound: 24 B per index in round 0, 40 B afterwards) with delayed
+// modular reduction in 64-bit accumulators; sums are reduced warp -> CTA -> one partial per CTA -> final kernel.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "launch_count.h"
+#include "kb.cuh"
+#include "poly.h"
+#include "sumcheck.h"
+
+namespace lm {
+
+constexpr int SPLIT_LO = 10;  // eq(point, x) = hi[x >> 10] * lo[x & 1023]
+
+__device__ __forceinline__ Ef ld_ef(const uint32_t* p) {
+  Ef v;
+#pragma unroll
+  for (int c = 0; c < 5; c++) v.c[c] = __ldg(p + c);
+  return v;
+}
+__device__ __forceinline__ Ef ld_ef_rw(const uint32_t* p) {
+  Ef v;
+#pragma unroll
+  for (int c = 0; c < 5; c++) v.c[c] = p[c];
+  return v;
+}
+__device__ __forceinline__ void st_ef(uint32_t* p, const Ef& v) {
+#pragma unroll
+  for (int c = 0; c < 5; c++) p[c] = v.c[c];
+}
+
+// ---------------------------------------------------------------------------------------------- weights
+// w[base + x] += hi[x >> lo_vars] * lo[x & mask]
+__global__ void weights_add_split_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t n, int lo_vars,
+                                         const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo) {
+  const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const Ef h = ld_ef(hi + 5 * (x >> lo_vars));
+  const Ef l = ld_ef(lo + 5 * (x & (((uint64_t)1 << lo_vars) - 1)));
+  uint32_t* dst = w + 5 * (base + x);
+  st_ef(dst, ef_add(ld_ef_rw(dst), ef_mul(h, l)));
+}
+
+cudaError_t weights_add_eq(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_point, uint32_t m,
+                           const uint32_t scalar[5], uint32_t* d_scratch) {
+  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  const int hi_vars = (int)m - lo_vars;
+  uint32_t* d_hi = d_scratch;
+  uint32_t* d_lo = d_hi + 5 * ((uint64_t)1 << hi_vars);
+  const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
+  cudaError_t e;
+  if ((e = eq_table(stream, d_point, hi_vars, scalar, d_hi)) != cudaSuccess) return e;
+  if ((e = eq_table(stream, d_point + 5 * hi_vars, lo_vars, one, d_lo)) != cudaSuccess) return e;
+  const uint64_t n = (uint64_t)1 << m;
+  weights_add_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_w, selector << m, n, lo_vars, d_hi, d_lo);
+  count_launch();
+  return cudaGetLastError();
+}
+size_t weights_add_eq_scratch_words(uint32_t m) {
+  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  return 5 * (((size_t)1 << (m - lo_vars)) + ((size_t)1 << lo_vars)) + 8;
+}
+
+// next_mle.rs:35-58, term k: w[base + (b << (k+1)) + (1 << k)] += scalar * (1 - oc[n-k-1]) * prod_{j >= n-k} oc[j]
+//                                                               * eq(oc[0 .. n-k-1), b)
+__global__ void weights_add_next_kernel(uint32_t* __restrict__ w, uint64_t base, const uint32_t* __restrict__ oc, int n,
+                                        int k, Ef scalar) {
+  const int pre = n - k - 1;
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ((uint64_t)1 << pre)) return;
+  Ef acc = scalar;
+  {
+    Ef z = ld_ef(oc + 5 * pre);
+#pragma unroll
+    for (int c = 0; c < 5; c++) z.c[c] = kb_neg(z.c[c]);
+    z.c[0] = kb_add(z.c[0], KB_R1);
+    acc = ef_mul(acc, z);
+  }
+  for (int j = n - k; j < n; j++) acc = ef_mul(acc, ld_ef(oc + 5 * j));
+  for (int i = 0; i < pre; i++) {
+    Ef z = ld_ef(oc + 5 * i);
+    if (!((b >> (pre - 1 - i)) & 1)) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) z.c[c] = kb_neg(z.c[c]);
+      z.c[0] = kb_add(z.c[0], KB_R1);
+    }
+    acc = ef_mul(acc, z);
+  }
+  uint32_t* dst = w + 5 * (base + (b << (k + 1)) + ((uint64_t)1 << k));
+  st_ef(dst, ef_add(ld_ef_rw(dst), acc));
+}
+__global__ void weights_add_next_last_kernel(uint32_t* __restrict__ w, uint64_t idx, const uint32_t* __restrict__ oc, int n,
+                                             Ef scalar) {
+  Ef acc = scalar;
+  for (int j = 0; j < n; j++) acc = ef_mul(acc, ld_ef(oc + 5 * j));
+  uint32_t* dst = w + 5 * idx;
+  st_ef(dst, ef_add(ld_ef_rw(dst), acc));
+}
+
+cudaError_t weights_add_next(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_point, uint32_t m,
+                             const uint32_t scalar[5]) {
+  Ef s;
+  for (int c = 0; c < 5; c++) s.c[c] = scalar[c];
+  const uint64_t base = selector << m;
+  for (int k = 0; k < (int)m; k++) {
+    const uint64_t n = (uint64_t)1 << (m - k - 1);
+    weights_add_next_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_w, base, d_point, (int)m, k, s);
+    count_launch();
+  }
+  weights_add_next_last_kernel<<<1, 1, 0, stream>>>(d_w, base + (((uint64_t)1 << m) - 1), d_point, (int)m, s);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---- batched base-field equality (STIR queries): w[x] += sum_q s_q eq(pt_q, x), pt_q in F^m
+// tables: a[q][xh] = s_q * eq(pt_q[0..hi), xh)  (EF),  l[q][xl] = eq(pt_q[hi..m), xl)  (F)
+__global__ void base_eq_tables_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, int m,
+                                      int hi_vars, int n_q, uint32_t* __restrict__ a, uint32_t* __restrict__ l) {
+  const int lo_vars = m - hi_vars;
+  const uint64_t n_hi = (uint64_t)1 << hi_vars, n_lo = (uint64_t)1 << lo_vars;
+  const uint64_t per_q = n_hi + n_lo;
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_q * n_q) return;
+  const int q = (int)(idx / per_q);
+  const uint64_t e = idx % per_q;
+  const uint32_t* pt = pts + (uint64_t)q * m;
+  if (e < n_hi) {
+    uint32_t acc = KB_R1;
+    for (int i = 0; i < hi_vars; i++) {
+      const uint32_t z = __ldg(pt + i);
+      acc = kb_mul(acc, ((e >> (hi_vars - 1 - i)) & 1) ? z : kb_sub(KB_R1, z));
+    }
+    const Ef s = ld_ef(scalars + 5 * q);
+    st_ef(a + 5 * ((uint64_t)q * n_hi + e), ef_mul_base(s, acc));
+  } else {
+    const uint64_t x = e - n_hi;
+    uint32_t acc = KB_R1;
+    for (int i = 0; i < lo_vars; i++) {
+      const uint32_t z = __ldg(pt + hi_vars + i);
+      acc = kb_mul(acc, ((x >> (lo_vars - 1 - i)) & 1) ? z : kb_sub(KB_R1, z));
+    }
+    l[(uint64_t)q * n_lo + x] = acc;
+  }
+}
+__global__ void weights_add_base_eq_kernel(uint32_t* __restrict__ w, uint64_t n, int lo_vars, int n_q,
+                                           const uint32_t* __restrict__ a, const uint32_t* __restrict__ l) {
+  const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const uint64_t n_lo = (uint64_t)1 << lo_vars, n_hi = n >> lo_vars;
+  const uint64_t xh = x >> lo_vars, xl = x & (n_lo - 1);
+  uint64_t acc[5] = {0, 0, 0, 0, 0};
+  int terms = 0;
+  for (int q = 0; q < n_q; q++) {
+    const uint32_t f = __ldg(l + (uint64_t)q * n_lo + xl);
+    const Ef e = ld_ef(a + 5 * ((uint64_t)q * n_hi + xh));
+    if (terms == 3) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) acc[c] = kb_fold(acc[c]);
+      terms = 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 5; c++) acc[c] = mad_wide(f, e.c[c], acc[c]);
+    terms++;
+  }
+  uint32_t* dst = w + 5 * x;
+  Ef cur = ld_ef_rw(dst);
+#pragma unroll
+  for (int c = 0; c < 5; c++) cur.c[c] = kb_add(cur.c[c], kb_canon(kb_redc_lazy(kb_fold(acc[c]))));
+  st_ef(dst, cur);
+}
+
+size_t weights_add_base_eq_scratch_words(uint32_t m, uint32_t n_q) {
+  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  const int hi_vars = (int)m - lo_vars;
+  return (size_t)n_q * (5 * ((size_t)1 << hi_vars) + ((size_t)1 << lo_vars) + m + 5) + 16;
+}
+
+cudaError_t weights_add_base_eq(cudaStream_t stream, uint32_t* d_w, uint32_t m, const uint32_t* d_points, uint32_t n_q,
+                                const uint32_t* d_scalars, uint32_t* d_scratch) {
+  if (n_q == 0) return cudaSuccess;
+  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  const int hi_vars = (int)m - lo_vars;
+  uint32_t* d_a = d_scratch;
+  uint32_t* d_l = d_a + 5 * (size_t)n_q * ((size_t)1 << hi_vars);
+  const uint64_t n_tab = (uint64_t)n_q * (((uint64_t)1 << hi_vars) + ((uint64_t)1 << lo_vars));
+  base_eq_tables_kernel<<<(unsigned)((n_tab + 127) / 128), 128, 0, stream>>>(d_points, d_scalars, (int)m, hi_vars, (int)n_q,
+                                                                              d_a, d_l);
+  count_launch();
+  const uint64_t n = (uint64_t)1 << m;
+  weights_add_base_eq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_w, n, lo_vars, (int)n_q, d_a, d_l);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- sumcheck rounds
+struct Acc10 {
+  uint64_t a[10];  // c0[0..5), c2[0..5)
+  int terms;
+};
+
+__device__ __forceinline__ void acc_init(Acc10& s) {
+#pragma unroll
+  for (int c = 0; c < 10; c++) s.a[c] = 0;
+  s.terms = 0;
+}
+__device__ __forceinline__ void acc_maybe_fold(Acc10& s) {
+  if (s.terms == 3) {
+#pragma unroll
+    for (int c = 0; c < 10; c++) s.a[c] = kb_fold(s.a[c]);
+    s.terms = 0;
+  }
+}
+// block reduction of (c0, c2) and write of one partial (10 words) per CTA
+__device__ __forceinline__ void block_reduce_pair(Ef c0, Ef c2, uint32_t* __restrict__ partial) {
+  __shared__ Ef red0[32], red2[32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Ef o0, o2;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      o0.c[c] = __shfl_down_sync(0xffffffffu, c0.c[c], off);
+      o2.c[c] = __shfl_down_sync(0xffffffffu, c2.c[c], off);
+    }
+    c0 = ef_add(c0, o0);
+    c2 = ef_add(c2, o2);
+  }
+  const int t = threadIdx.x;
+  if ((t & 31) == 0) red0[t >> 5] = c0, red2[t >> 5] = c2;
+  __syncthreads();
+  if (t < 32) {
+    const int nw = blockDim.x >> 5;
+    c0 = t < nw ? red0[t] : ef_zero();
+    c2 = t < nw ? red2[t] : ef_zero();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      Ef o0, o2;
+#pragma unroll
+      for (int c = 0; c < 5; c++) {
+        o0.c[c] = __shfl_down_sync(0xffffffffu, c0.c[c], off);
+        o2.c[c] = __shfl_down_sync(0xffffffffu, c2.c[c], off);
+      }
+      c0 = ef_add(c0, o0);
+      c2 = ef_add(c2, o2);
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) partial[10 * blockIdx.x + c] = c0.c[c], partial[10 * blockIdx.x + 5 + c] = c2.c[c];
+    }
+  }
+}
+
+// c0 = sum_{i < half} w[i] p[i];  c2 = sum (w[i+half] - w[i]) (p[i+half] - p[i]);  p entries >= live are zero.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+prod_round_kernel(const uint32_t* __restrict__ p, uint64_t live, const uint32_t* __restrict__ w, uint64_t half,
+                  uint32_t* __restrict__ partial) {
+  Ef c0 = ef_zero(), c2 = ef_zero();
+  Acc10 s;
+  acc_init(s);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (uint64_t)gridDim.x * blockDim.x) {
+    const Ef w0 = ld_ef(w + 5 * i), w1 = ld_ef(w + 5 * (i + half));
+    const Ef dw = ef_sub(w1, w0);
+    if (DIM == 1) {
+      const uint32_t p0 = i < live ? __ldg(p + i) : 0u;
+      const uint32_t p1 = i + half < live ? __ldg(p + i + half) : 0u;
+      const uint32_t dp = kb_sub(p1, p0);
+      acc_maybe_fold(s);
+#pragma unroll
+      for (int c = 0; c < 5; c++) {
+        s.a[c] = mad_wide(p0, w0.c[c], s.a[c]);
+        s.a[5 + c] = mad_wide(dp, dw.c[c], s.a[5 + c]);
+      }
+      s.terms++;
+    } else {
+      const Ef p0 = i < live ? ld_ef(p + 5 * i) : ef_zero();
+      const Ef p1 = i + half < live ? ld_ef(p + 5 * (i + half)) : ef_zero();
+      c0 = ef_add(c0, ef_mul(w0, p0));
+      c2 = ef_add(c2, ef_mul(dw, ef_sub(p1, p0)));
+    }
+  }
+  if (DIM == 1) {
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      c0.c[c] = kb_canon(kb_redc_lazy(kb_fold(s.a[c])));
+      c2.c[c] = kb_canon(kb_redc_lazy(kb_fold(s.a[5 + c])));
+    }
+  }
+  block_reduce_pair(c0, c2, partial);
+}
+
+// Fold both tables with r (old length n = 4 * quarter) into p_out / w_out (EF, length 2 * quarter) and compute the
+// next round's (c0, c2) on the folded tables in the same pass (product_computation.rs:242-304).
+template <int DIM>
+__global__ void __launch_bounds__(256)
+prod_fold_round_kernel(const uint32_t* p, uint64_t live, const uint32_t* w, uint64_t quarter, Ef r, uint32_t* p_out,
+                       uint32_t* w_out, uint32_t* __restrict__ partial) {
+  Ef c0 = ef_zero(), c2 = ef_zero();
+  const uint64_t half = 2 * quarter;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < quarter; i += (uint64_t)gridDim.x * blockDim.x) {
+    Ef x0, x1;
+    if (DIM == 1) {
+      const uint32_t a0 = i < live ? __ldg(p + i) : 0u, a1 = i + quarter < live ? __ldg(p + i + quarter) : 0u;
+      const uint32_t b0 = i + half < live ? __ldg(p + i + half) : 0u;
+      const uint32_t b1 = i + half + quarter < live ? __ldg(p + i + half + quarter) : 0u;
+      x0 = ef_add_base(ef_mul_base(r, kb_sub(b0, a0)), a0);
+      x1 = ef_add_base(ef_mul_base(r, kb_sub(b1, a1)), a1);
+    } else {
+      const Ef a0 = i < live ? ld_ef_rw(p + 5 * i) : ef_zero();
+      const Ef a1 = i + quarter < live ? ld_ef_rw(p + 5 * (i + quarter)) : ef_zero();
+      const Ef b0 = i + half < live ? ld_ef_rw(p + 5 * (i + half)) : ef_zero();
+      const Ef b1 = i + half + quarter < live ? ld_ef_rw(p + 5 * (i + half + quarter)) : ef_zero();
+      x0 = ef_add(a0, ef_mul(r, ef_sub(b0, a0)));
+      x1 = ef_add(a1, ef_mul(r, ef_sub(b1, a1)));
+    }
+    const Ef u0 = ld_ef_rw(w + 5 * i), u1 = ld_ef_rw(w + 5 * (i + quarter));
+    const Ef v0 = ld_ef_rw(w + 5 * (i + half)), v1 = ld_ef_rw(w + 5 * (i + half + quarter));
+    const Ef y0 = ef_add(u0, ef_mul(r, ef_sub(v0, u0)));
+    const Ef y1 = ef_add(u1, ef_mul(r, ef_sub(v1, u1)));
+    st_ef(p_out + 5 * i, x0);
+    st_ef(p_out + 5 * (i + quarter), x1);
+    st_ef(w_out + 5 * i, y0);
+    st_ef(w_out + 5 * (i + quarter), y1);
+    c0 = ef_add(c0, ef_mul(y0, x0));
+    c2 = ef_add(c2, ef_mul(ef_sub(y1, y0), ef_sub(x1, x0)));
+  }
+  block_reduce_pair(c0, c2, partial);
+}
+
+// out[0..5) = sum_k partial[10k + 0..5),  out[5..10) = sum_k partial[10k + 5..10)
+__global__ void sum_pair_partials_kernel(const uint32_t* __restrict__ partial, int n, uint32_t* __restrict__ out) {
+  Ef c0 = ef_zero(), c2 = ef_zero();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    c0 = ef_add(c0, ld_ef_rw(partial + 10 * i));
+    c2 = ef_add(c2, ld_ef_rw(partial + 10 * i + 5));
+  }
+  // reuse the CTA reduction; the single CTA writes partial slot 0 of `out`
+  block_reduce_pair(c0, c2, out);
+}
+
+static unsigned round_grid(uint64_t work) {
+  uint64_t blocks = (work + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;  // persistent-style grid: 8 CTAs of 256 threads per SM
+  if (blocks == 0) blocks = 1;
+  return (unsigned)blocks;
+}
+
+size_t prod_round_scratch_words() { return 10 * (148 * 8) + 16; }
+
+cudaError_t prod_round(cudaStream_t stream, const uint32_t* d_p, uint32_t dim, uint64_t live, const uint32_t* d_w, uint64_t n,
+                       uint32_t* d_scratch, uint32_t* d_out10) {
+  if (n < 2 || (dim != 1 && dim != 5)) return cudaErrorInvalidValue;
+  const uint64_t half = n / 2;
+  const unsigned grid = round_grid(half);
+  if (dim == 1)
+    prod_round_kernel<1><<<grid, 256, 0, stream>>>(d_p, live, d_w, half, d_scratch);
+  else
+    prod_round_kernel<5><<<grid, 256, 0, stream>>>(d_p, live, d_w, half, d_scratch);
+  count_launch();
+  sum_pair_partials_kernel<<<1, 256, 0, stream>>>(d_scratch, (int)grid, d_out10);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t prod_fold_round(cudaStream_t stream, const uint32_t* d_p, uint32_t dim, uint64_t live, const uint32_t* d_w,
+                            uint64_t n, const uint32_t r[5], uint32_t* d_p_out, uint32_t* d_w_out, uint32_t* d_scratch,
+                            uint32_t* d_out10) {
+  if (n < 4 || (dim != 1 && dim != 5)) return cudaErrorInvalidValue;
+  Ef rr;
+  for (int c = 0; c < 5; c++) rr.c[c] = r[c];
+  const uint64_t quarter = n / 4;
+  const unsigned grid = round_grid(quarter);
+  if (dim == 1)
+    prod_fold_round_kernel<1><<<grid, 256, 0, stream>>>(d_p, live, d_w, quarter, rr, d_p_out, d_w_out, d_scratch);
+  else
+    prod_fold_round_kernel<5><<<grid, 256, 0, stream>>>(d_p, live, d_w, quarter, rr, d_p_out, d_w_out, d_scratch);
+  count_launch();
+  sum_pair_partials_kernel<<<1, 256, 0, stream>>>(d_scratch, (int)grid, d_out10);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace lm

@@ -93,6 +93,76 @@ class Tree:
             self.handle = None
 
 
+class ProductSumcheck:
+    """WHIR-open sumcheck session (reference: SumcheckSingle, crates/whir/src/open.rs:323-446).
+
+    Holds the polynomial table and the weight table on the device; the caller owns the transcript and drives
+    one call per round, exactly like run_product_sumcheck / sumcheck_prove_many_rounds do on the CPU."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.handle = ctx, handle
+
+    @property
+    def n_vars(self) -> int:
+        n, d = C.c_uint32(), C.c_uint32()
+        check(lib().lm_sc_num_vars(self.handle, C.byref(n), C.byref(d)))
+        return n.value
+
+    @property
+    def poly_dim(self) -> int:
+        n, d = C.c_uint32(), C.c_uint32()
+        check(lib().lm_sc_num_vars(self.handle, C.byref(n), C.byref(d)))
+        return d.value
+
+    def add_eq(self, selector: int, point, scalar):
+        pt = _u32(point).reshape(-1, 5)
+        check(lib().lm_sc_add_eq(self.handle, selector, _p(pt), pt.shape[0], _p(_u32(scalar))))
+
+    def add_next(self, selector: int, point, scalar):
+        pt = _u32(point).reshape(-1, 5)
+        check(lib().lm_sc_add_next(self.handle, selector, _p(pt), pt.shape[0], _p(_u32(scalar))))
+
+    def add_base_eq(self, points, scalars):
+        pts, sc = _u32(points), _u32(scalars).reshape(-1, 5)
+        check(lib().lm_sc_add_base_eq(self.handle, _p(pts), pts.shape[0], _p(sc)))
+
+    def round(self):
+        c0, c2 = np.empty(5, dtype=np.uint32), np.empty(5, dtype=np.uint32)
+        check(lib().lm_sc_round(self.handle, _p(c0), _p(c2)))
+        return c0, c2
+
+    def fold(self, r):
+        check(lib().lm_sc_fold(self.handle, _p(_u32(r))))
+
+    def fold_round(self, r):
+        c0, c2 = np.empty(5, dtype=np.uint32), np.empty(5, dtype=np.uint32)
+        check(lib().lm_sc_fold_round(self.handle, _p(_u32(r)), _p(c0), _p(c2)))
+        return c0, c2
+
+    def read(self):
+        n, d = self.n_vars, self.poly_dim
+        poly = np.empty((1 << n, d) if d == 5 else (1 << n,), dtype=np.uint32)
+        w = np.empty((1 << n, 5), dtype=np.uint32)
+        check(lib().lm_sc_read(self.handle, _p(poly), _p(w)))
+        return poly, w
+
+    def eval_poly(self, point) -> np.ndarray:
+        out = np.empty(5, dtype=np.uint32)
+        check(lib().lm_sc_eval_poly(self.handle, _p(_u32(point).reshape(-1, 5)), _p(out)))
+        return out
+
+    def commit_poly(self, folding_factor: int, log_inv_rate: int) -> Tree:
+        root = np.empty(8, dtype=np.uint32)
+        t = C.c_void_p()
+        check(lib().lm_sc_commit_poly(self.handle, folding_factor, log_inv_rate, C.byref(t), _p(root)))
+        return Tree(self.ctx, t, root)
+
+    def free(self):
+        if self.handle:
+            check(lib().lm_sc_free(self.handle))
+            self.handle = None
+
+
 class Context:
     """One GPU: stream + twiddle table (reference: setup_prover / precompute_dft_twiddles)."""
 
@@ -150,6 +220,19 @@ class Context:
         live = (e.size // dim) if live_len is None else live_len
         check(lib().lm_mle_eval(self.handle, e.ctypes.data_as(C.c_void_p), n, dim, live, _p(pt), _p(out)))
         return out
+
+    def sumcheck_from_tree(self, tree: Tree) -> ProductSumcheck:
+        h = C.c_void_p()
+        check(lib().lm_sc_new_from_tree(tree.handle, C.byref(h)))
+        return ProductSumcheck(self, h)
+
+    def sumcheck(self, evals, n_vars: int, live_len: int | None = None) -> ProductSumcheck:
+        e = _u32(evals)
+        dim = 5 if (e.ndim == 2 and e.shape[1] == 5) else 1
+        live = (e.size // dim) if live_len is None else live_len
+        h = C.c_void_p()
+        check(lib().lm_sc_new(self.handle, e.ctypes.data_as(C.c_void_p), n_vars, dim, live, C.byref(h)))
+        return ProductSumcheck(self, h)
 
     # ---- device-buffer API ------------------------------------------------------------------------------
     def poseidon1(self, states, compress: bool = False) -> np.ndarray:

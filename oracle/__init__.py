@@ -227,3 +227,50 @@ def fold_msb(evals, r) -> np.ndarray:
     out = np.empty((n // 2, 5), dtype=np.uint32)
     lib().lm_or_fold_msb(_p(e), C.c_uint64(n), C.c_uint32(dim), _p(r), _p(out))
     return out
+
+
+# ---------------------------------------------------------------- WHIR open: weights + product sumcheck
+def weights_add_eq(weights, selector: int, point, scalar) -> None:
+    """in place: weights[(selector << m) + x] += scalar * eq(point, x)"""
+    pt, sc = _u32(point).reshape(-1, 5), _u32(scalar)
+    lib().lm_or_weights_add_eq(_p(weights), C.c_uint64(selector), _p(pt), C.c_uint32(pt.shape[0]), _p(sc))
+
+
+def next_mle_folded(point) -> np.ndarray:
+    pt = _u32(point).reshape(-1, 5)
+    out = np.empty((1 << pt.shape[0], 5), dtype=np.uint32)
+    lib().lm_or_next_mle_folded(_p(pt), C.c_uint32(pt.shape[0]), _p(out))
+    return out
+
+
+def weights_add_next(weights, selector: int, point, scalar) -> None:
+    pt, sc = _u32(point).reshape(-1, 5), _u32(scalar)
+    lib().lm_or_weights_add_next(_p(weights), C.c_uint64(selector), _p(pt), C.c_uint32(pt.shape[0]), _p(sc))
+
+
+def weights_add_base_eq(weights, points, scalars) -> None:
+    pts, sc = _u32(points), _u32(scalars).reshape(-1, 5)
+    lib().lm_or_weights_add_base_eq(_p(weights), C.c_uint32(pts.shape[1]), _p(pts), C.c_uint32(pts.shape[0]), _p(sc))
+
+
+def prod_round(p, w):
+    p, w = _u32(p), _u32(w)
+    dim = 5 if (p.ndim == 2 and p.shape[1] == 5) else 1
+    n = w.shape[0]
+    c0, c2 = np.empty(5, dtype=np.uint32), np.empty(5, dtype=np.uint32)
+    lib().lm_or_prod_round(_p(p), C.c_uint32(dim), _p(w), C.c_uint64(n), _p(c0), _p(c2))
+    return c0, c2
+
+
+def evals_to_coeffs(data) -> np.ndarray:
+    d = _u32(data).copy().reshape(-1, 5)
+    lib().lm_or_evals_to_coeffs(_p(d), C.c_uint64(d.shape[0]))
+    return d
+
+
+def ef_add(a, b) -> np.ndarray:
+    return ((_u32(a).astype(np.uint64) + _u32(b)) % P).astype(np.uint32)
+
+
+def ef_sub(a, b) -> np.ndarray:
+    return ((_u32(a).astype(np.uint64) + P - _u32(b)) % P).astype(np.uint32)

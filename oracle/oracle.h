@@ -62,6 +62,17 @@ uint32_t lm_or_kb_to_u32(uint32_t a);
 uint32_t lm_or_kb_inv(uint32_t a);
 uint32_t lm_or_kb_two_adic_generator(uint32_t bits);
 
+/* sumcheck.c */
+void lm_or_weights_add_eq(uint32_t *weights, uint64_t selector, const uint32_t *point, uint32_t m,
+                          const uint32_t scalar[5]);
+void lm_or_next_mle_folded(const uint32_t *oc, uint32_t n, uint32_t *res);
+void lm_or_weights_add_next(uint32_t *weights, uint64_t selector, const uint32_t *point, uint32_t m,
+                            const uint32_t scalar[5]);
+void lm_or_weights_add_base_eq(uint32_t *weights, uint32_t m, const uint32_t *points, uint32_t n_q,
+                               const uint32_t *scalars);
+void lm_or_prod_round(const uint32_t *p, uint32_t dim, const uint32_t *w, uint64_t n, uint32_t c0[5], uint32_t c2[5]);
+void lm_or_evals_to_coeffs(uint32_t *data, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif
