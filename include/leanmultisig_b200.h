@@ -123,6 +123,29 @@ int lm_sc_commit_poly(lm_sumcheck* sc, uint32_t folding_factor, uint32_t log_inv
                       uint32_t out_root[8]);
 int lm_sc_free(lm_sumcheck* sc);
 
+/* ---- AIR ("SuperSpartan") sumcheck session --------------------------------------------------------------
+ * Replaces AirSumcheckSession (crates/sub_protocols/src/air_sumcheck.rs:45-292), the implementor of
+ * trait OuterSumcheckSession (air_sumcheck.rs:34-42) that prove_batched_air_sumcheck (air_sumcheck.rs:636-681)
+ * drives.  A Rust struct implementing the trait forwards compute_bare_round_poly -> lm_air_round (+ the p(1) /
+ * Lagrange step it already does on a handful of values), process_challenge -> lm_air_fold,
+ * final_column_evals -> lm_air_final.  table_id: 0 = execution table (crates/lean_vm/src/tables/execution/air.rs).
+ * cols: n_cols host pointers to base-field columns of 2^log_rows entries in natural row order (the shifted
+ * columns are derived on the device).  eq_factor: log_rows x 5; the LAST entry belongs to the variable bound
+ * first.  alpha_powers: n_alpha x 5 (ExtraDataForBuses::alpha_powers), logup_alphas_eq: n_la x 5, bus_beta: 5. */
+typedef struct lm_air lm_air;
+int lm_air_new(lm_ctx* ctx, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
+               const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
+               const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5], lm_air** out);
+int lm_air_info(const lm_air* air, uint32_t* n_vars, uint32_t* degree, uint32_t* n_cols_total);
+/* out_evals: degree x 5 words = sum_j eq(j) C(row pair j at z) for z = 0, 2, 3, .., degree over the WHOLE
+ * hypercube (no separate padding term), before the missing_mul_factor scaling (air_sumcheck.rs:242-249) */
+int lm_air_round(lm_air* air, uint32_t* out_evals);
+/* bind the least-significant remaining variable to r (fold_multilinear_at_bit, crates/backend/poly/src/utils.rs:117) */
+int lm_air_fold(lm_air* air, const uint32_t r[5]);
+/* after the last fold: the (n_cols + n_shift) column evaluations, 5 words each (air_sumcheck.rs:289-291) */
+int lm_air_final(lm_air* air, uint32_t* out);
+int lm_air_free(lm_air* air);
+
 /* ---- device-pointer layer (inputs already in HBM; used by the kernel-only benchmark and by lm_* above) -----
  * All pointers are device pointers on ctx's device; work is enqueued on ctx's stream, no synchronisation. */
 int lm_dev_alloc(lm_ctx* ctx, size_t bytes, void** out);

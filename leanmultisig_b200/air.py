@@ -1,0 +1,140 @@
+"""Host-side mirror of the AIR sumcheck session on top of the C ABI.
+
+Reference names kept: trait OuterSumcheckSession (crates/sub_protocols/src/air_sumcheck.rs:34-42),
+AirSumcheckSession::new (:67-126), compute_bare_round_poly (:225-266), process_challenge (:268-287),
+final_column_evals (:289-291), prove_batched_air_sumcheck (:636-681), expand_bare_to_full
+(crates/backend/fiat-shamir/src/utils.rs:30-41).  The device computes the round sums and the folds; the few
+field operations per round that the reference performs on the host are done here on Python ints.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import field as F
+from ._lib import check, lib, u32p
+
+EXECUTION_TABLE = 0
+
+
+def _u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _p(a):
+    return a.ctypes.data_as(u32p)
+
+
+class AirSumcheckSession:
+    def __init__(self, ctx, table_id: int, columns, eq_factor, sum_, alpha_powers, logup_alphas_eq_poly, bus_beta):
+        cols = [_u32(c) for c in columns]
+        n = cols[0].size
+        self._initial_n_vars = n.bit_length() - 1
+        assert all(c.size == n for c in cols) and n == 1 << self._initial_n_vars
+        eq = _u32(eq_factor).reshape(-1, 5)
+        assert eq.shape[0] == self._initial_n_vars
+        ap, la, beta = _u32(alpha_powers).reshape(-1, 5), _u32(logup_alphas_eq_poly).reshape(-1, 5), _u32(bus_beta)
+        ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        h = C.c_void_p()
+        check(lib().lm_air_new(ctx.handle, table_id, ptrs, len(cols), self._initial_n_vars, _p(eq), _p(ap), ap.shape[0],
+                               _p(la), la.shape[0], _p(beta), C.byref(h)))
+        self.handle = h
+        nv, deg, tot = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().lm_air_info(h, C.byref(nv), C.byref(deg), C.byref(tot)))
+        self._degree, self._n_cols_total = deg.value, tot.value
+        self.eq_factor = [F.from_monty(e) for e in eq]  # the last element is removed at each round
+        self._sum = F.from_monty(sum_)
+        self.missing_mul_factor = F.ONE
+        self.rounds_done = 0
+
+    # ---- trait OuterSumcheckSession ------------------------------------------------------------------------
+    def initial_n_vars(self) -> int:
+        return self._initial_n_vars
+
+    def sum(self) -> np.ndarray:
+        return F.to_monty(self._sum)
+
+    def bare_degree(self) -> int:
+        return self._degree
+
+    def eq_alpha(self) -> np.ndarray:
+        return F.to_monty(self.eq_factor[-1])
+
+    def compute_bare_round_poly(self) -> np.ndarray:
+        """coefficients (degree + 1) x 5 of the bare round polynomial"""
+        raw = np.empty((self._degree, 5), dtype=np.uint32)
+        check(lib().lm_air_round(self.handle, _p(raw)))
+        p_evals = [F.mul(F.from_monty(v), self.missing_mul_factor) for v in raw]
+        alpha = self.eq_factor[-1]
+        # p(1) from the running sum: sum = (1 - alpha) p(0) + alpha p(1)
+        p_at_1 = F.mul(F.sub(self._sum, F.mul(F.sub(F.ONE, alpha), p_evals[0])), F.inv(alpha))
+        p_evals.insert(1, p_at_1)
+        coeffs = F.lagrange_interpolation_at_integers(p_evals)
+        return np.stack([F.to_monty(c) for c in coeffs])
+
+    def process_challenge(self, challenge, bare_poly) -> None:
+        r = F.from_monty(challenge)
+        alpha = self.eq_factor[-1]
+        eq_eval = F.add(F.mul(F.sub(F.ONE, alpha), F.sub(F.ONE, r)), F.mul(alpha, r))
+        coeffs = [F.from_monty(c) for c in _u32(bare_poly).reshape(-1, 5)]
+        self._sum = F.mul(F.poly_eval(coeffs, r), eq_eval)
+        self.missing_mul_factor = F.mul(self.missing_mul_factor, eq_eval)
+        check(lib().lm_air_fold(self.handle, _p(_u32(challenge))))
+        self.rounds_done += 1
+        self.eq_factor.pop()
+
+    def final_column_evals(self) -> np.ndarray:
+        out = np.empty((self._n_cols_total, 5), dtype=np.uint32)
+        check(lib().lm_air_final(self.handle, _p(out)))
+        return out
+
+    def free(self):
+        if self.handle:
+            check(lib().lm_air_free(self.handle))
+            self.handle = None
+
+
+def expand_bare_to_full(bare_coeffs, alpha) -> list:
+    """full(X) = ((1 - alpha) + (2 alpha - 1) X) * bare(X)   (fiat-shamir/src/utils.rs:30-41)"""
+    a = F.from_monty(alpha)
+    c0, c1 = F.sub(F.ONE, a), F.sub(F.add(a, a), F.ONE)
+    bare = [F.from_monty(c) for c in _u32(bare_coeffs).reshape(-1, 5)]
+    full = [F.ZERO] * (len(bare) + 1)
+    for i, b in enumerate(bare):
+        full[i] = F.add(full[i], F.mul(c0, b))
+        full[i + 1] = F.add(full[i + 1], F.mul(c1, b))
+    return full
+
+
+def prove_batched_air_sumcheck(sessions, eta, absorb_and_sample):
+    """Back-loaded batching of several sessions (air_sumcheck.rs:636-681).  `absorb_and_sample(coeffs)` stands for
+    prover_state.add_sumcheck_polynomial + sample and returns the challenge (5 Montgomery words)."""
+    n_rounds = max(s.initial_n_vars() for s in sessions)
+    max_full_degree = max(s.bare_degree() + 1 for s in sessions)
+    eta_c = F.from_monty(eta)
+    eta_powers = [F.power(eta_c, i) for i in range(len(sessions))]
+    k = [F.ONE] * len(sessions)
+    challenges = []
+    for rnd in range(n_rounds):
+        combined = [F.ZERO] * (max_full_degree + 1)
+        bare_polys = [None] * len(sessions)
+        for idx, s in enumerate(sessions):
+            join_round = n_rounds - s.initial_n_vars()
+            w = F.mul(eta_powers[idx], k[idx])
+            if rnd < join_round:
+                combined[1] = F.add(combined[1], F.mul(w, F.from_monty(s.sum())))
+            else:
+                bare = s.compute_bare_round_poly()
+                for i, c in enumerate(expand_bare_to_full(bare, s.eq_alpha())):
+                    combined[i] = F.add(combined[i], F.mul(w, c))
+                bare_polys[idx] = bare
+        ch = _u32(absorb_and_sample(np.stack([F.to_monty(c) for c in combined])))
+        challenges.append(ch)
+        for idx, s in enumerate(sessions):
+            join_round = n_rounds - s.initial_n_vars()
+            if rnd < join_round:
+                k[idx] = F.mul(k[idx], F.from_monty(ch))
+            elif bare_polys[idx] is not None:
+                s.process_challenge(ch, bare_polys[idx])
+    return challenges

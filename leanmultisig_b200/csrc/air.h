@@ -1,0 +1,18 @@
+// Internal (C++) launch interface of air.cu; the public C ABI is include/leanmultisig_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace lm {
+cudaError_t air_shift_column(cudaStream_t stream, const uint32_t* d_col, uint64_t n, uint32_t* d_out);
+size_t air_round_scratch_words(uint32_t log_n);
+// d_out[5 x 5] = evaluations at z = 0, 2, 3, 4, 5 of the execution-table round polynomial over 22 SoA columns of
+// 2^log_n rows (dim words per entry); d_eq_point: log_n - 1 EF entries on the device; the rest are host arrays.
+cudaError_t air_exec_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t dim, uint32_t log_n, const uint32_t* d_eq_point,
+                           const uint32_t* alpha_powers, const uint32_t* la, uint32_t n_la, const uint32_t beta[5],
+                           uint32_t* d_scratch, uint32_t* d_out);
+// fold the least-significant variable of n_cols SoA columns (n rows -> n/2 EF rows); d_out must not alias d_in
+cudaError_t air_fold_lsb(cudaStream_t stream, const uint32_t* d_in, uint32_t dim, uint64_t n, uint32_t n_cols, const uint32_t r[5],
+                         uint32_t* d_out);
+}  // namespace lm

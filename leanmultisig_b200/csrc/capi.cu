@@ -13,6 +13,7 @@
 #include "ntt.h"
 #include "poly.h"
 #include "sumcheck.h"
+#include "air.h"
 #include "launch_count.h"
 
 namespace lm {
@@ -97,6 +98,22 @@ struct lm_sumcheck {
     scratch_words = words;
     return LM_OK;
   }
+};
+
+// AIR sumcheck session (reference: AirSumcheckSession, crates/sub_protocols/src/air_sumcheck.rs:45-292)
+struct lm_air {
+  lm_ctx* ctx = nullptr;
+  uint32_t table_id = 0, n_cols = 0, n_shift = 0, degree = 0;
+  uint32_t log_n = 0;       // current number of variables
+  uint32_t dim = 1;         // 1 until the first fold
+  uint32_t* d_cols = nullptr;   // current SoA columns
+  uint32_t* d_spare = nullptr;  // ping-pong target of the next fold
+  size_t cols_words = 0, spare_words = 0;
+  uint32_t* d_eq = nullptr;     // eq_factor, initial log_n x 5
+  uint32_t* d_scratch = nullptr;
+  uint32_t* d_out = nullptr;
+  std::vector<uint32_t> alpha, la;
+  uint32_t beta[5] = {0, 0, 0, 0, 0};
 };
 
 extern "C" {
@@ -711,6 +728,127 @@ int lm_sc_commit_poly(lm_sumcheck* s, uint32_t folding_factor, uint32_t log_inv_
   if (!s) return fail(LM_ERR_INVALID, "lm_sc_commit_poly: null argument");
   return commit_impl(s->ctx, s->d_p, true, s->n_vars, s->p_dim, s->p_live, folding_factor, log_inv_rate, false, out_tree,
                      out_root);
+}
+
+// ------------------------------------------------------------------------------------------ AIR sumcheck session
+int lm_air_free(lm_air* a) {
+  if (!a) return LM_OK;
+  if (a->ctx) {
+    cudaSetDevice(a->ctx->device);
+    cudaStreamSynchronize(a->ctx->stream);
+  }
+  if (a->d_cols) cudaFree(a->d_cols);
+  if (a->d_spare) cudaFree(a->d_spare);
+  if (a->d_eq) cudaFree(a->d_eq);
+  if (a->d_scratch) cudaFree(a->d_scratch);
+  if (a->d_out) cudaFree(a->d_out);
+  delete a;
+  return LM_OK;
+}
+
+int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
+               const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* logup_alphas_eq,
+               uint32_t n_la, const uint32_t bus_beta[5], lm_air** out) {
+  if (!c || !cols || !eq_factor || !alpha_powers || !logup_alphas_eq || !bus_beta || !out)
+    return fail(LM_ERR_INVALID, "lm_air_new: null argument");
+  *out = nullptr;
+  if (table_id != 0) return fail(LM_ERR_INVALID, "lm_air_new: only the execution table (id 0) is implemented");
+  if (n_cols != 20) return fail(LM_ERR_INVALID, "lm_air_new: the execution table has 20 columns, got %u", n_cols);
+  if (n_alpha < 13) return fail(LM_ERR_INVALID, "lm_air_new: need >= 13 alpha powers, got %u", n_alpha);
+  if (n_la < 5) return fail(LM_ERR_INVALID, "lm_air_new: need >= 5 logup alphas, got %u", n_la);
+  if (log_rows < 1 || log_rows > 30) return fail(LM_ERR_INVALID, "lm_air_new: log_rows %u out of range", log_rows);
+  CU(cudaSetDevice(c->device));
+  lm_air* a = new (std::nothrow) lm_air();
+  if (!a) return fail(LM_ERR_OOM, "lm_air_new: host allocation failed");
+  a->ctx = c;
+  a->table_id = table_id;
+  a->n_cols = 20;
+  a->n_shift = 2;
+  a->degree = 5;
+  a->log_n = log_rows;
+  a->alpha.assign(alpha_powers, alpha_powers + 5 * (size_t)n_alpha);
+  a->la.assign(logup_alphas_eq, logup_alphas_eq + 5 * (size_t)n_la);
+  memcpy(a->beta, bus_beta, sizeof(a->beta));
+  const uint64_t n = (uint64_t)1 << log_rows;
+  const uint32_t all = a->n_cols + a->n_shift;
+  a->cols_words = (size_t)all * n;
+  cudaError_t e = cudaMalloc(&a->d_cols, a->cols_words * sizeof(uint32_t));
+  for (uint32_t k = 0; e == cudaSuccess && k < a->n_cols; k++) {
+    if (!cols[k]) {
+      lm_air_free(a);
+      return fail(LM_ERR_INVALID, "lm_air_new: column %u is null", k);
+    }
+    e = cudaMemcpyAsync(a->d_cols + (size_t)k * n, cols[k], n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  }
+  // shifted copies of the first n_shift columns (compute_shifted_columns, air_sumcheck.rs:683-694)
+  for (uint32_t k = 0; e == cudaSuccess && k < a->n_shift; k++)
+    e = lm::air_shift_column(c->stream, a->d_cols + (size_t)k * n, n, a->d_cols + (size_t)(a->n_cols + k) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_eq, (size_t)log_rows * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(a->d_eq, eq_factor, (size_t)log_rows * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_scratch, lm::air_round_scratch_words(log_rows) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_out, 64 * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    lm_air_free(a);
+    return cuda_fail(e, "lm_air_new");
+  }
+  *out = a;
+  return LM_OK;
+}
+
+int lm_air_info(const lm_air* a, uint32_t* n_vars, uint32_t* degree, uint32_t* n_cols_total) {
+  if (!a) return fail(LM_ERR_INVALID, "lm_air_info: null argument");
+  if (n_vars) *n_vars = a->log_n;
+  if (degree) *degree = a->degree;
+  if (n_cols_total) *n_cols_total = a->n_cols + a->n_shift;
+  return LM_OK;
+}
+
+int lm_air_round(lm_air* a, uint32_t* out_evals) {
+  if (!a || !out_evals) return fail(LM_ERR_INVALID, "lm_air_round: null argument");
+  if (a->log_n < 1) return fail(LM_ERR_INVALID, "lm_air_round: no variables left");
+  lm_ctx* c = a->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(lm::air_exec_round(c->stream, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(), a->la.data(),
+                        (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch, a->d_out));
+  CU(cudaMemcpyAsync(out_evals, a->d_out, (size_t)a->degree * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_air_fold(lm_air* a, const uint32_t r[5]) {
+  if (!a || !r) return fail(LM_ERR_INVALID, "lm_air_fold: null argument");
+  if (a->log_n < 1) return fail(LM_ERR_INVALID, "lm_air_fold: no variables left");
+  lm_ctx* c = a->ctx;
+  CU(cudaSetDevice(c->device));
+  const uint64_t n = (uint64_t)1 << a->log_n;
+  const uint32_t all = a->n_cols + a->n_shift;
+  const size_t need = (size_t)all * (n / 2) * 5;
+  if (a->spare_words < need) {
+    if (a->d_spare) cudaFree(a->d_spare);
+    a->d_spare = nullptr;
+    a->spare_words = 0;
+    CU(cudaMalloc(&a->d_spare, need * sizeof(uint32_t)));
+    a->spare_words = need;
+  }
+  CU(lm::air_fold_lsb(c->stream, a->d_cols, a->dim, n, all, r, a->d_spare));
+  std::swap(a->d_cols, a->d_spare);
+  std::swap(a->cols_words, a->spare_words);
+  a->dim = 5;
+  a->log_n -= 1;
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_air_final(lm_air* a, uint32_t* out) {
+  if (!a || !out) return fail(LM_ERR_INVALID, "lm_air_final: null argument");
+  if (a->log_n != 0 || a->dim != 5) return fail(LM_ERR_INVALID, "lm_air_final: %u variables are still unbound", a->log_n);
+  lm_ctx* c = a->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(out, a->d_cols, (size_t)(a->n_cols + a->n_shift) * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
 }
 
 int lm_mle_eval(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, uint64_t live_len, const uint32_t* point,

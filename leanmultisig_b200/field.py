@@ -1,0 +1,94 @@
+"""Host-side KoalaBear / quintic-extension arithmetic on Python ints.
+
+Only for the handful of per-round values the reference also computes on the host (p(1), Lagrange
+interpolation, eq factors of a challenge): crates/backend/poly/src/dense_poly.rs:33,
+crates/sub_protocols/src/air_sumcheck.rs:250-275.  Boundary values are Montgomery-form u32 exactly like the
+reference's memory; internally canonical residues are used.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+P = 0x7F000001
+_R = (1 << 32) % P
+_RINV = pow(_R, -1, P)
+
+
+def from_monty(v) -> tuple:
+    return tuple(int(x) * _RINV % P for x in np.asarray(v, dtype=np.uint64).reshape(-1))
+
+
+def to_monty(e) -> np.ndarray:
+    return np.array([x % P * _R % P for x in e], dtype=np.uint32)
+
+
+ZERO = (0, 0, 0, 0, 0)
+ONE = (1, 0, 0, 0, 0)
+
+
+def add(a, b):
+    return tuple((x + y) % P for x, y in zip(a, b))
+
+
+def sub(a, b):
+    return tuple((x - y) % P for x, y in zip(a, b))
+
+
+def neg(a):
+    return tuple((-x) % P for x in a)
+
+
+def scal(a, k: int):
+    return tuple(x * k % P for x in a)
+
+
+def mul(a, b):
+    """product in F[X]/(X^5 + X^2 - 1)  (quintic_extension/extension.rs:26)"""
+    d = [0] * 9
+    for i, x in enumerate(a):
+        if x:
+            for j, y in enumerate(b):
+                d[i + j] += x * y
+    return ((d[0] + d[5] - d[8]) % P, (d[1] + d[6]) % P, (d[2] - d[5] + d[7] + d[8]) % P, (d[3] - d[6] + d[8]) % P,
+            (d[4] - d[7]) % P)
+
+
+def power(a, e: int):
+    r = ONE
+    while e:
+        if e & 1:
+            r = mul(r, a)
+        a = mul(a, a)
+        e >>= 1
+    return r
+
+
+def inv(a):
+    return power(a, P ** 5 - 2)
+
+
+def poly_eval(coeffs, x):
+    acc = ZERO
+    for c in reversed(coeffs):
+        acc = add(mul(acc, x), c)
+    return acc
+
+
+def lagrange_interpolation_at_integers(values):
+    """coefficients of the unique polynomial of degree < len(values) with p(i) = values[i], i = 0..len-1
+    (DensePolynomial::lagrange_interpolation, crates/backend/poly/src/dense_poly.rs:33)."""
+    n = len(values)
+    coeffs = [ZERO] * n
+    for i, v in enumerate(values):
+        # numerator polynomial prod_{j != i} (X - j), base-field coefficients
+        num = [1]
+        denom = 1
+        for j in range(n):
+            if j == i:
+                continue
+            num = [(a - j * b) % P for a, b in zip([0] + num, num + [0])]
+            denom = denom * (i - j) % P
+        dinv = pow(denom, -1, P)
+        for k in range(n):
+            coeffs[k] = add(coeffs[k], scal(v, num[k] * dinv % P))
+    return coeffs

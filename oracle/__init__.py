@@ -274,3 +274,42 @@ def ef_add(a, b) -> np.ndarray:
 
 def ef_sub(a, b) -> np.ndarray:
     return ((_u32(a).astype(np.uint64) + P - _u32(b)) % P).astype(np.uint32)
+
+
+# ---------------------------------------------------------------- AIR sumcheck (execution table)
+EXEC_N_COLS, EXEC_N_SHIFT, EXEC_N_CONSTRAINTS, EXEC_DEGREE = 20, 2, 13, 5
+
+
+def air_exec_eval(point, alpha_powers, la, beta) -> np.ndarray:
+    pt, ap, la, beta = _u32(point).reshape(22, 5), _u32(alpha_powers).reshape(-1, 5), _u32(la).reshape(-1, 5), _u32(beta)
+    out = np.empty(5, dtype=np.uint32)
+    lib().lm_or_air_exec_eval(_p(pt), _p(ap), _p(la), C.c_uint32(la.shape[0]), _p(beta), _p(out))
+    return out
+
+
+def shift_column(col) -> np.ndarray:
+    c = _u32(col)
+    out = np.empty_like(c)
+    lib().lm_or_shift_column(_p(c), C.c_uint64(c.size), _p(out))
+    return out
+
+
+def air_exec_round(cols, eq_point, alpha_powers, la, beta) -> np.ndarray:
+    """cols: (22, n) base or (22, n, 5) extension; returns evaluations at z = 0, 2, 3, 4, 5 (5 x 5)."""
+    c = _u32(cols)
+    dim = 5 if c.ndim == 3 else 1
+    n = c.shape[1]
+    eqp, ap, la, beta = _u32(eq_point).reshape(-1, 5), _u32(alpha_powers).reshape(-1, 5), _u32(la).reshape(-1, 5), _u32(beta)
+    out = np.empty((5, 5), dtype=np.uint32)
+    lib().lm_or_air_exec_round(_p(c), C.c_uint64(n), C.c_uint32(dim), _p(eqp), _p(ap), _p(la), C.c_uint32(la.shape[0]),
+                               _p(beta), _p(out))
+    return out
+
+
+def fold_lsb(col, r) -> np.ndarray:
+    c, r = _u32(col), _u32(r)
+    dim = 5 if (c.ndim == 2 and c.shape[1] == 5) else 1
+    n = c.size // dim
+    out = np.empty((n // 2, 5), dtype=np.uint32)
+    lib().lm_or_fold_lsb(_p(c), C.c_uint64(n), C.c_uint32(dim), _p(r), _p(out))
+    return out

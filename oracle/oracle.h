@@ -73,6 +73,15 @@ void lm_or_weights_add_base_eq(uint32_t *weights, uint32_t m, const uint32_t *po
 void lm_or_prod_round(const uint32_t *p, uint32_t dim, const uint32_t *w, uint64_t n, uint32_t c0[5], uint32_t c2[5]);
 void lm_or_evals_to_coeffs(uint32_t *data, uint64_t n);
 
+/* air.c */
+void lm_or_air_exec_eval(const uint32_t *point, const uint32_t *alpha_powers, const uint32_t *la, uint32_t n_la,
+                         const uint32_t beta[5], uint32_t out[5]);
+void lm_or_shift_column(const uint32_t *col, uint64_t n, uint32_t *out);
+void lm_or_air_exec_round(const uint32_t *cols, uint64_t n, uint32_t dim, const uint32_t *eq_point,
+                          const uint32_t *alpha_powers, const uint32_t *la, uint32_t n_la, const uint32_t beta[5],
+                          uint32_t *out);
+void lm_or_fold_lsb(const uint32_t *in, uint64_t n_in, uint32_t dim, const uint32_t r[5], uint32_t *out);
+
 #ifdef __cplusplus
 }
 #endif
