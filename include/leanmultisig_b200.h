@@ -146,6 +146,32 @@ int lm_air_fold(lm_air* air, const uint32_t r[5]);
 int lm_air_final(lm_air* air, uint32_t* out);
 int lm_air_free(lm_air* air);
 
+/* ---- Logup: fingerprints + quotient GKR -----------------------------------------------------------------
+ * lm_finger_print replaces finger_print(_packed) (crates/utils/src/multilinear.rs:76-98): out[r] = c - sum_i
+ * alphas[i] * data[r][i] for n_rows rows of n_data base-field words (row-major); alphas: n_data x 5; out: n_rows x 5.
+ *
+ * lm_gkr_* replaces prove_gkr_quotient (crates/sub_protocols/src/quotient_gkr/mod.rs:31-141) with the transcript
+ * left to the caller.  nums (base field) / dens (EF) are the ACTIVE prefix in NATURAL order (the reference's
+ * chunk-bit-reversed packing of logup.rs:88-199 is a CPU SIMD layout and is not used); the rest of the next
+ * power of two is (0, 1).  lm_gkr_new runs the whole up pass (sum_quotients_2_by_2, layers.rs:124-189) and keeps
+ * every layer.  Per layer, top to bottom (mod.rs:73-141, sumcheck_utils.rs:282-359):
+ *   lm_gkr_layer_begin(K, claim_point[K x 5], alpha);  K times { lm_gkr_round -> (c0_raw, c2_raw);  host:
+ *   build_bare_from_coeffs (sumcheck_utils.rs:491-503), transcript, r;  lm_gkr_fold(r) };  lm_gkr_layer_end ->
+ *   inner evals [nl, nr, dl, dr].  Rounds bind the least-significant variable first; eq_alpha of a round is the
+ *   last remaining coordinate of the claim point.  Sums run over the whole hypercube (no separate padding term). */
+typedef struct lm_gkr lm_gkr;
+int lm_finger_print(lm_ctx* ctx, const uint32_t* data, uint64_t n_rows, uint32_t n_data, const uint32_t* alphas,
+                    const uint32_t c[5], uint32_t* out);
+int lm_gkr_new(lm_ctx* ctx, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, lm_gkr** out);
+int lm_gkr_num_vars(const lm_gkr* gkr, uint32_t* n_vars);
+/* the 2^5 numerators and denominators of the top layer, 32 x 5 words each (mod.rs:64-66) */
+int lm_gkr_top(lm_gkr* gkr, uint32_t* top_nums, uint32_t* top_dens);
+int lm_gkr_layer_begin(lm_gkr* gkr, uint32_t claim_vars, const uint32_t* claim_point, const uint32_t alpha[5]);
+int lm_gkr_round(lm_gkr* gkr, uint32_t c0[5], uint32_t c2[5]);
+int lm_gkr_fold(lm_gkr* gkr, const uint32_t r[5]);
+int lm_gkr_layer_end(lm_gkr* gkr, uint32_t* inner_evals /* 4 x 5 */);
+int lm_gkr_free(lm_gkr* gkr);
+
 /* ---- device-pointer layer (inputs already in HBM; used by the kernel-only benchmark and by lm_* above) -----
  * All pointers are device pointers on ctx's device; work is enqueued on ctx's stream, no synchronisation. */
 int lm_dev_alloc(lm_ctx* ctx, size_t bytes, void** out);

@@ -7,6 +7,7 @@ holds no arithmetic of its own.
 """
 from ._lib import LIB_PATH, LmError, build, declared_symbols, lib  # noqa: F401
 from .air import AirSumcheckSession, prove_batched_air_sumcheck  # noqa: F401
+from .logup import GkrQuotientProver, finger_print  # noqa: F401
 from .whir import Context, DeviceBuffer, ProductSumcheck, Tree  # noqa: F401
 
 __all__ = ["Context", "DeviceBuffer", "ProductSumcheck", "Tree", "LmError", "build", "lib", "declared_symbols", "LIB_PATH"]

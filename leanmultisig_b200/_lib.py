@@ -89,6 +89,15 @@ def lib() -> C.CDLL:
             "lm_air_fold": [vp, u32p],
             "lm_air_final": [vp, u32p],
             "lm_air_free": [vp],
+            "lm_finger_print": [vp, u32p, u64, u32, u32p, u32p, u32p],
+            "lm_gkr_new": [vp, u32p, u32p, u64, C.POINTER(vp)],
+            "lm_gkr_num_vars": [vp, u32p],
+            "lm_gkr_top": [vp, u32p, u32p],
+            "lm_gkr_layer_begin": [vp, u32, u32p, u32p],
+            "lm_gkr_round": [vp, u32p, u32p],
+            "lm_gkr_fold": [vp, u32p],
+            "lm_gkr_layer_end": [vp, u32p],
+            "lm_gkr_free": [vp],
             "lm_dev_alloc": [vp, sz, C.POINTER(vp)],
             "lm_dev_free": [vp, vp],
             "lm_dev_upload": [vp, vp, vp, sz],

@@ -14,6 +14,7 @@
 #include "poly.h"
 #include "sumcheck.h"
 #include "air.h"
+#include "gkr.h"
 #include "launch_count.h"
 
 namespace lm {
@@ -115,6 +116,24 @@ struct lm_air {
   std::vector<uint32_t> alpha, la;
   uint32_t beta[5] = {0, 0, 0, 0, 0};
 };
+
+// Quotient-GKR session (reference: prove_gkr_quotient, crates/sub_protocols/src/quotient_gkr/mod.rs:31-141)
+struct lm_gkr {
+  lm_ctx* ctx = nullptr;
+  uint32_t n_vars = 0;  // of layer 0
+  // layer l has n_vars - l variables; layer 0 numerators are base field
+  std::vector<uint32_t*> nums, dens;
+  uint32_t* d_w[2] = {nullptr, nullptr};  // ping-pong working tables of the current layer sumcheck
+  uint32_t* d_eq = nullptr;               // claim point of the current layer (<= 64 x 5)
+  uint32_t* d_scratch = nullptr;
+  uint32_t* d_out10 = nullptr;
+  // current layer sumcheck
+  int cur_layer = -1;
+  uint32_t cur_vars = 0;  // variables still unbound in the working columns
+  int cur_src = 0, cur_buf = 0;
+  uint32_t alpha[5] = {0, 0, 0, 0, 0};
+};
+static const uint32_t LM_GKR_TOP_VARS = 5;  // N_VARS_TO_SEND_GKR_COEFFS (crates/sub_protocols/src/lib.rs:14)
 
 extern "C" {
 
@@ -848,6 +867,170 @@ int lm_air_final(lm_air* a, uint32_t* out) {
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(out, a->d_cols, (size_t)(a->n_cols + a->n_shift) * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Logup / quotient GKR
+int lm_gkr_free(lm_gkr* g) {
+  if (!g) return LM_OK;
+  if (g->ctx) {
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+  }
+  for (auto p : g->nums) cudaFree(p);
+  for (auto p : g->dens) cudaFree(p);
+  for (int k = 0; k < 2; k++)
+    if (g->d_w[k]) cudaFree(g->d_w[k]);
+  if (g->d_eq) cudaFree(g->d_eq);
+  if (g->d_scratch) cudaFree(g->d_scratch);
+  if (g->d_out10) cudaFree(g->d_out10);
+  delete g;
+  return LM_OK;
+}
+
+int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, lm_gkr** out) {
+  if (!c || !nums || !dens || !out) return fail(LM_ERR_INVALID, "lm_gkr_new: null argument");
+  *out = nullptr;
+  if (active_len < 2) return fail(LM_ERR_INVALID, "lm_gkr_new: need at least two fractions");
+  uint32_t n_vars = 0;
+  while (((uint64_t)1 << n_vars) < active_len) n_vars++;
+  if (n_vars <= LM_GKR_TOP_VARS) return fail(LM_ERR_INVALID, "lm_gkr_new: needs more than 2^%u fractions", LM_GKR_TOP_VARS);
+  if (n_vars > 31) return fail(LM_ERR_INVALID, "lm_gkr_new: too many fractions");
+  CU(cudaSetDevice(c->device));
+  lm_gkr* g = new (std::nothrow) lm_gkr();
+  if (!g) return fail(LM_ERR_OOM, "lm_gkr_new: host allocation failed");
+  g->ctx = c;
+  g->n_vars = n_vars;
+  const uint64_t n = (uint64_t)1 << n_vars;
+  cudaError_t e = cudaSuccess;
+  uint32_t *d_n = nullptr, *d_d = nullptr;
+  e = cudaMalloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) g->nums.push_back(d_n), e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) g->dens.push_back(d_d);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = lm::gkr_pad(c->stream, d_n, 1, d_d, active_len, n);
+  // up pass (mod.rs:52-62): halve until 2^5 fractions remain
+  for (uint32_t l = 1; e == cudaSuccess && l <= n_vars - LM_GKR_TOP_VARS; l++) {
+    const uint64_t m = n >> l;
+    uint32_t *nn = nullptr, *dd = nullptr;
+    e = cudaMalloc(&nn, m * 5 * sizeof(uint32_t));
+    if (e == cudaSuccess) g->nums.push_back(nn), e = cudaMalloc(&dd, m * 5 * sizeof(uint32_t));
+    if (e == cudaSuccess) g->dens.push_back(dd);
+    if (e == cudaSuccess) e = lm::gkr_layer_up(c->stream, g->nums[l - 1], l == 1 ? 1 : 5, g->dens[l - 1], m * 2, nn, dd);
+  }
+  // working tables: the first fold of the largest layer produces 2^(n_vars - 2) rows of 20 words
+  const size_t w_words = ((size_t)1 << (n_vars - 2)) * 20;
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_w[0], w_words * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_w[1], (w_words / 2 ? w_words / 2 : 20) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_eq, 64 * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_scratch, lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_out10, 16 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    lm_gkr_free(g);
+    return cuda_fail(e, "lm_gkr_new");
+  }
+  *out = g;
+  return LM_OK;
+}
+
+int lm_gkr_num_vars(const lm_gkr* g, uint32_t* n_vars) {
+  if (!g || !n_vars) return fail(LM_ERR_INVALID, "lm_gkr_num_vars: null argument");
+  *n_vars = g->n_vars;
+  return LM_OK;
+}
+
+int lm_gkr_top(lm_gkr* g, uint32_t* top_nums, uint32_t* top_dens) {
+  if (!g || !top_nums || !top_dens) return fail(LM_ERR_INVALID, "lm_gkr_top: null argument");
+  lm_ctx* c = g->ctx;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = ((size_t)1 << LM_GKR_TOP_VARS) * 5 * sizeof(uint32_t);
+  CU(cudaMemcpyAsync(top_nums, g->nums.back(), bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(top_dens, g->dens.back(), bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_gkr_layer_begin(lm_gkr* g, uint32_t claim_vars, const uint32_t* point, const uint32_t alpha[5]) {
+  if (!g || !point || !alpha) return fail(LM_ERR_INVALID, "lm_gkr_layer_begin: null argument");
+  if (claim_vars < LM_GKR_TOP_VARS || claim_vars >= g->n_vars)
+    return fail(LM_ERR_INVALID, "lm_gkr_layer_begin: claim over %u variables, expected %u..%u", claim_vars, LM_GKR_TOP_VARS,
+                g->n_vars - 1);
+  lm_ctx* c = g->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(g->d_eq, point, (size_t)claim_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  g->cur_layer = (int)(g->n_vars - (claim_vars + 1));  // the layer below the claim has claim_vars + 1 variables
+  g->cur_vars = claim_vars;                            // its even/odd halves have claim_vars variables
+  g->cur_src = 0;
+  g->cur_buf = 0;
+  memcpy(g->alpha, alpha, sizeof(g->alpha));
+  return LM_OK;
+}
+
+int lm_gkr_round(lm_gkr* g, uint32_t c0[5], uint32_t c2[5]) {
+  if (!g || !c0 || !c2) return fail(LM_ERR_INVALID, "lm_gkr_round: null argument");
+  if (g->cur_layer < 0 || g->cur_vars < 1) return fail(LM_ERR_INVALID, "lm_gkr_round: no layer sumcheck in progress");
+  lm_ctx* c = g->ctx;
+  CU(cudaSetDevice(c->device));
+  const uint32_t* a = g->cur_src == 0 ? g->nums[g->cur_layer] : g->d_w[g->cur_buf];
+  const uint32_t* b = g->cur_src == 0 ? g->dens[g->cur_layer] : nullptr;
+  CU(lm::gkr_round(c->stream, g->cur_src, g->cur_layer == 0 ? 1 : 5, a, b, g->cur_vars, g->d_eq, g->alpha, g->d_scratch,
+                   g->d_out10));
+  uint32_t h[10];
+  CU(cudaMemcpyAsync(h, g->d_out10, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(c0, h, 5 * sizeof(uint32_t));
+  memcpy(c2, h + 5, 5 * sizeof(uint32_t));
+  return LM_OK;
+}
+
+int lm_gkr_fold(lm_gkr* g, const uint32_t r[5]) {
+  if (!g || !r) return fail(LM_ERR_INVALID, "lm_gkr_fold: null argument");
+  if (g->cur_layer < 0 || g->cur_vars < 1) return fail(LM_ERR_INVALID, "lm_gkr_fold: no layer sumcheck in progress");
+  lm_ctx* c = g->ctx;
+  CU(cudaSetDevice(c->device));
+  const uint32_t* a = g->cur_src == 0 ? g->nums[g->cur_layer] : g->d_w[g->cur_buf];
+  const uint32_t* b = g->cur_src == 0 ? g->dens[g->cur_layer] : nullptr;
+  const int dst = g->cur_src == 0 ? 0 : (g->cur_buf ^ 1);
+  CU(lm::gkr_fold(c->stream, g->cur_src, g->cur_layer == 0 ? 1 : 5, a, b, g->cur_vars, r, g->d_w[dst]));
+  g->cur_src = 1;
+  g->cur_buf = dst;
+  g->cur_vars -= 1;
+  return LM_OK;
+}
+
+int lm_gkr_layer_end(lm_gkr* g, uint32_t* inner_evals) {
+  if (!g || !inner_evals) return fail(LM_ERR_INVALID, "lm_gkr_layer_end: null argument");
+  if (g->cur_layer < 0 || g->cur_vars != 0 || g->cur_src != 1)
+    return fail(LM_ERR_INVALID, "lm_gkr_layer_end: %u variables are still unbound", g->cur_vars);
+  lm_ctx* c = g->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(inner_evals, g->d_w[g->cur_buf], 20 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  g->cur_layer = -1;
+  return LM_OK;
+}
+
+int lm_finger_print(lm_ctx* c, const uint32_t* data, uint64_t n_rows, uint32_t n_data, const uint32_t* alphas,
+                    const uint32_t cc[5], uint32_t* out) {
+  if (!c || !data || !alphas || !cc || !out) return fail(LM_ERR_INVALID, "lm_finger_print: null argument");
+  if (n_rows == 0) return LM_OK;
+  CU(cudaSetDevice(c->device));
+  uint32_t *d_data = nullptr, *d_al = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_data, n_rows * n_data * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_al, (size_t)n_data * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, n_rows * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_data, data, n_rows * n_data * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_al, alphas, (size_t)n_data * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = lm::finger_print(c->stream, d_data, n_rows, n_data, d_al, cc, d_out);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n_rows * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream);
+  if (d_data) cudaFree(d_data);
+  if (d_al) cudaFree(d_al);
+  if (d_out) cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_finger_print");
   return LM_OK;
 }
 

@@ -1,0 +1,18 @@
+// Internal (C++) launch interface of gkr.cu; the public C ABI is include/leanmultisig_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace lm {
+cudaError_t finger_print(cudaStream_t stream, const uint32_t* d_data, uint64_t n_rows, uint32_t n_data,
+                         const uint32_t* d_alphas, const uint32_t c[5], uint32_t* d_out);
+cudaError_t gkr_pad(cudaStream_t stream, uint32_t* d_nums, uint32_t num_dim, uint32_t* d_dens, uint64_t active, uint64_t n);
+cudaError_t gkr_layer_up(cudaStream_t stream, const uint32_t* d_nums, uint32_t num_dim, const uint32_t* d_dens, uint64_t n,
+                         uint32_t* d_out_nums, uint32_t* d_out_dens);
+size_t gkr_round_scratch_words(uint32_t n_vars);
+cudaError_t gkr_round(cudaStream_t stream, int src, uint32_t num_dim, const uint32_t* a, const uint32_t* b, uint32_t n_vars,
+                      const uint32_t* d_eq_point, const uint32_t alpha[5], uint32_t* d_scratch, uint32_t* d_out10);
+cudaError_t gkr_fold(cudaStream_t stream, int src, uint32_t num_dim, const uint32_t* a, const uint32_t* b, uint32_t n_vars,
+                     const uint32_t r[5], uint32_t* d_out);
+}  // namespace lm

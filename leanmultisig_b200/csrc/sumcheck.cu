@@ -16,29 +16,13 @@
 #include <cstdint>
 #include "launch_count.h"
 #include "kb.cuh"
+#include "reduce.cuh"
 #include "poly.h"
 #include "sumcheck.h"
 
 namespace lm {
 
 constexpr int SPLIT_LO = 10;  // eq(point, x) = hi[x >> 10] * lo[x & 1023]
-
-__device__ __forceinline__ Ef ld_ef(const uint32_t* p) {
-  Ef v;
-#pragma unroll
-  for (int c = 0; c < 5; c++) v.c[c] = __ldg(p + c);
-  return v;
-}
-__device__ __forceinline__ Ef ld_ef_rw(const uint32_t* p) {
-  Ef v;
-#pragma unroll
-  for (int c = 0; c < 5; c++) v.c[c] = p[c];
-  return v;
-}
-__device__ __forceinline__ void st_ef(uint32_t* p, const Ef& v) {
-#pragma unroll
-  for (int c = 0; c < 5; c++) p[c] = v.c[c];
-}
 
 // ---------------------------------------------------------------------------------------------- weights
 // w[base + x] += hi[x >> lo_vars] * lo[x & mask]
@@ -221,45 +205,6 @@ __device__ __forceinline__ void acc_maybe_fold(Acc10& s) {
     s.terms = 0;
   }
 }
-// block reduction of (c0, c2) and write of one partial (10 words) per CTA
-__device__ __forceinline__ void block_reduce_pair(Ef c0, Ef c2, uint32_t* __restrict__ partial) {
-  __shared__ Ef red0[32], red2[32];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    Ef o0, o2;
-#pragma unroll
-    for (int c = 0; c < 5; c++) {
-      o0.c[c] = __shfl_down_sync(0xffffffffu, c0.c[c], off);
-      o2.c[c] = __shfl_down_sync(0xffffffffu, c2.c[c], off);
-    }
-    c0 = ef_add(c0, o0);
-    c2 = ef_add(c2, o2);
-  }
-  const int t = threadIdx.x;
-  if ((t & 31) == 0) red0[t >> 5] = c0, red2[t >> 5] = c2;
-  __syncthreads();
-  if (t < 32) {
-    const int nw = blockDim.x >> 5;
-    c0 = t < nw ? red0[t] : ef_zero();
-    c2 = t < nw ? red2[t] : ef_zero();
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      Ef o0, o2;
-#pragma unroll
-      for (int c = 0; c < 5; c++) {
-        o0.c[c] = __shfl_down_sync(0xffffffffu, c0.c[c], off);
-        o2.c[c] = __shfl_down_sync(0xffffffffu, c2.c[c], off);
-      }
-      c0 = ef_add(c0, o0);
-      c2 = ef_add(c2, o2);
-    }
-    if (t == 0) {
-#pragma unroll
-      for (int c = 0; c < 5; c++) partial[10 * blockIdx.x + c] = c0.c[c], partial[10 * blockIdx.x + 5 + c] = c2.c[c];
-    }
-  }
-}
-
 // c0 = sum_{i < half} w[i] p[i];  c2 = sum (w[i+half] - w[i]) (p[i+half] - p[i]);  p entries >= live are zero.
 template <int DIM>
 __global__ void __launch_bounds__(256)
@@ -335,17 +280,6 @@ prod_fold_round_kernel(const uint32_t* p, uint64_t live, const uint32_t* w, uint
     c2 = ef_add(c2, ef_mul(ef_sub(y1, y0), ef_sub(x1, x0)));
   }
   block_reduce_pair(c0, c2, partial);
-}
-
-// out[0..5) = sum_k partial[10k + 0..5),  out[5..10) = sum_k partial[10k + 5..10)
-__global__ void sum_pair_partials_kernel(const uint32_t* __restrict__ partial, int n, uint32_t* __restrict__ out) {
-  Ef c0 = ef_zero(), c2 = ef_zero();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    c0 = ef_add(c0, ld_ef_rw(partial + 10 * i));
-    c2 = ef_add(c2, ld_ef_rw(partial + 10 * i + 5));
-  }
-  // reuse the CTA reduction; the single CTA writes partial slot 0 of `out`
-  block_reduce_pair(c0, c2, out);
 }
 
 static unsigned round_grid(uint64_t work) {

@@ -313,3 +313,36 @@ def fold_lsb(col, r) -> np.ndarray:
     out = np.empty((n // 2, 5), dtype=np.uint32)
     lib().lm_or_fold_lsb(_p(c), C.c_uint64(n), C.c_uint32(dim), _p(r), _p(out))
     return out
+
+
+# ---------------------------------------------------------------- Logup / quotient GKR
+def gkr_layer_up(nums, dens):
+    n_, d_ = _u32(nums), _u32(dens).reshape(-1, 5)
+    num_dim = 5 if (n_.ndim == 2 and n_.shape[1] == 5) else 1
+    n = d_.shape[0]
+    on, od = np.empty((n // 2, 5), dtype=np.uint32), np.empty((n // 2, 5), dtype=np.uint32)
+    lib().lm_or_gkr_layer_up(_p(n_), C.c_uint32(num_dim), _p(d_), C.c_uint64(n), _p(on), _p(od))
+    return on, od
+
+
+def gkr_round(nl, nr, dl, dr, eq_point, alpha):
+    nl, nr, dl, dr = (_u32(x).reshape(-1, 5) for x in (nl, nr, dl, dr))
+    eqp, alpha = _u32(eq_point).reshape(-1, 5), _u32(alpha)
+    c0, c2 = np.empty(5, dtype=np.uint32), np.empty(5, dtype=np.uint32)
+    lib().lm_or_gkr_round(_p(nl), _p(nr), _p(dl), _p(dr), C.c_uint64(nl.shape[0]), _p(eqp), _p(alpha), _p(c0), _p(c2))
+    return c0, c2
+
+
+def finger_print(data, alphas, c) -> np.ndarray:
+    d, al, c = _u32(data), _u32(alphas).reshape(-1, 5), _u32(c)
+    out = np.empty((d.shape[0], 5), dtype=np.uint32)
+    lib().lm_or_finger_print(_p(d), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1]), _p(al), _p(c), _p(out))
+    return out
+
+
+def embed(base) -> np.ndarray:
+    """base-field vector -> EF vector"""
+    b = _u32(base).reshape(-1)
+    out = np.zeros((b.size, 5), dtype=np.uint32)
+    out[:, 0] = b
+    return out

@@ -82,6 +82,14 @@ void lm_or_air_exec_round(const uint32_t *cols, uint64_t n, uint32_t dim, const 
                           uint32_t *out);
 void lm_or_fold_lsb(const uint32_t *in, uint64_t n_in, uint32_t dim, const uint32_t r[5], uint32_t *out);
 
+/* gkr.c */
+void lm_or_gkr_layer_up(const uint32_t *nums, uint32_t num_dim, const uint32_t *dens, uint64_t n, uint32_t *out_nums,
+                        uint32_t *out_dens);
+void lm_or_gkr_round(const uint32_t *nl, const uint32_t *nr, const uint32_t *dl, const uint32_t *dr, uint64_t n,
+                     const uint32_t *eq_point, const uint32_t alpha[5], uint32_t c0[5], uint32_t c2[5]);
+void lm_or_finger_print(const uint32_t *data, uint64_t n_rows, uint32_t n_data, const uint32_t *alphas,
+                        const uint32_t c[5], uint32_t *out);
+
 #ifdef __cplusplus
 }
 #endif
