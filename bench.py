@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-rows", type=int, default=22, help="log2 of codeword rows (BASELINE config: 22)")
     ap.add_argument("--cpu-sample-log-rows", type=int, default=0, help="0 = pick from the core count")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
+                    help="N > 1: one commit row-sharded over the GPUs (strong scaling) or one commit per GPU (weak)")
     return ap.parse_args()
 
 
@@ -171,6 +173,9 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if world > 1 and args.multi == "sharded":
+        return run_b200_sharded(args, rank, local_rank, world)
 
     wl = workload(args.log_rows)
     n_vars, live, rows = wl["n_vars"], wl["live"], wl["rows"]
@@ -302,8 +307,111 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_sharded(args, rank, local_rank, world):
+    """N > 1: ONE commit of the BASELINE shape, row-sharded over the ranks (leanmultisig_b200/sharded.py):
+    local sub-transform, one all-to-all inside the NTT, last log2(N) layers, per-rank Merkle subtrees, all-gather
+    of the N^2 subtree roots, replicated top.  Strong scaling: the total work is fixed."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import leanmultisig_b200 as L
+    from leanmultisig_b200._lib import lib
+    from leanmultisig_b200.sharded import CudaBackend, ShardedCommit
+
+    wl = workload(args.log_rows)
+    n_vars, live = wl["n_vars"], wl["live"]
+    elems_per_commit = 1 << n_vars
+    l = lib()
+    ctx = L.Context(local_rank, 24)
+    backend = CudaBackend(ctx)
+    stream = backend.stream
+    sc = ShardedCommit(backend, dist, n_vars, FOLDING, LOG_INV_RATE, live_cols=64)
+    shard_len = live // world
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    shard = torch.randint(0, P, (shard_len,), dtype=torch.int64, device="cuda", generator=gen).to(torch.int32)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    host = torch.empty(shard_len, dtype=torch.int32).pin_memory()
+    host.copy_(shard.cpu())
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        root = sc.commit(shard)
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = l.lm_kernel_launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        evs[k][0].record(stream)
+        root = sc.commit(shard)
+        evs[k][1].record(stream)
+        flush.zero_()
+    barrier()
+    launches = l.lm_kernel_launches() - launches0
+    t_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    # e2e: pinned host shard -> device -> commit -> root on the host
+    for _ in range(min(args.warmup, 3)):
+        sc.commit(host.cuda(non_blocking=True))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        root = sc.commit(host.cuda(non_blocking=True))
+    barrier()
+    t_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    tt = torch.tensor([t_step, t_e2e], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_step, t_e2e = tt.tolist()
+    roots = [None] * world
+    dist.all_gather_object(roots, [int(x) for x in np.asarray(root).reshape(-1)])
+    if rank == 0:
+        assert all(r == roots[0] for r in roots), "ranks disagree on the Merkle root"
+        peak, peak_src = peaks()
+        rows = wl["rows"]
+        commit_bytes = live * 4 + rows * 64 * 4 + (2 * rows - 1) * 32
+        ach = commit_bytes / (t_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": elems_per_commit / (t_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"WHIR commit 2^{args.log_rows}x64 KoalaBear, rate 1/2 (evals-DFT + Poseidon1 Merkle)",
+                       "n_vars": n_vars, "folding_factor": FOLDING, "log_inv_rate": LOG_INV_RATE, "live_cols": 64,
+                       "full_cols": 128, "elements_per_commit": elems_per_commit,
+                       "l2": "256 MiB flush write between timed steps",
+                       "parallelism": f"one commit row-sharded over {world} GPUs: all-to-all inside the NTT, "
+                                      f"all-gather of {world * world} subtree roots"},
+            "roofline": {"bound": "hbm", "kernel": "whole sharded commit (aggregate over ranks)", "achieved": ach,
+                         "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world), "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": commit_bytes},
+            "e2e": {"value": elems_per_commit / (t_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": t_e2e,
+                    "h2d_bytes_per_step": live * 4, "d2h_bytes_per_step": 32 * world},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    # Libraries (NCCL's version banner, torchrun notices) may print to fd 1; the contract is ONE JSON line on stdout,
+    # so everything else is sent to stderr and the line is written to the saved descriptor.
+    global print
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    import builtins
+
+    def print(*a, **k):  # noqa: A001
+        k.pop("flush", None)
+        builtins.print(*a, file=real_stdout, flush=True, **k)
+
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -185,6 +185,10 @@ int lm_dev_reorder_and_dft(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars
                            uint32_t folding_factor, uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out);
 /* EvalsDft::dft_batch_by_evals (crates/whir/src/dft.rs:79), in place on a height x width matrix */
 int lm_dev_dft(lm_ctx* ctx, uint32_t* d_mat, uint64_t height, uint64_t width);
+/* the last layers [l_first, log_h) of dft_batch_by_evals on the rows one rank holds after the all-to-all of a
+ * row-sharded commit: local row (m, j'), m < n_blocks, j' < run, is global row m * block + offset + j' */
+int lm_dev_dft_layers_mapped(lm_ctx* ctx, uint32_t* d_mat, uint64_t width, uint32_t log_h, uint32_t l_first,
+                             uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset);
 /* build_merkle_tree_koalabear (crates/whir/src/merkle.rs:59-88): d_layers = (2*height - 1) x 8 words */
 int lm_dev_merkle_tree(lm_ctx* ctx, const uint32_t* d_mat, uint64_t height, uint32_t stored_width,
                        uint32_t full_width, uint32_t effective_width, uint32_t* d_layers);

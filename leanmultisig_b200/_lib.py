@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
             "lm_dev_poseidon1": [vp, vp, u64, i],
             "lm_dev_reorder_and_dft": [vp, vp, u32, u32, u32, u32, u32, vp],
             "lm_dev_dft": [vp, vp, u64, u64],
+            "lm_dev_dft_layers_mapped": [vp, vp, u64, u32, u32, u64, u64, u64, u64],
             "lm_dev_merkle_tree": [vp, vp, u64, u32, u32, u32, vp],
             "lm_dev_merkle_leaves": [vp, vp, u64, u32, u32, u32, vp],
             "lm_dev_merkle_levels": [vp, vp, u64],

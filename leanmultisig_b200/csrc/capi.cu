@@ -268,6 +268,16 @@ int lm_dev_dft(lm_ctx* c, uint32_t* d_mat, uint64_t h, uint64_t w) {
   return LM_OK;
 }
 
+int lm_dev_dft_layers_mapped(lm_ctx* c, uint32_t* d_mat, uint64_t w, uint32_t log_h, uint32_t l_first, uint64_t n_blocks,
+                             uint64_t run, uint64_t block, uint64_t offset) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped: ctx is null");
+  if (w % 4) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped: width %llu is not a multiple of 4", (unsigned long long)w);
+  if (log_h > c->tw_log_n) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped: domain exceeds the twiddle table");
+  CU(cudaSetDevice(c->device));
+  CU(lm::ntt_layers_mapped(c->stream, d_mat, w, log_h, l_first, n_blocks, run, block, offset, c->d_tw, c->tw_log_n));
+  return LM_OK;
+}
+
 int lm_dev_merkle_tree(lm_ctx* c, const uint32_t* d_mat, uint64_t h, uint32_t stored_w, uint32_t full_w,
                        uint32_t eff_w, uint32_t* d_layers) {
   if (!c) return fail(LM_ERR_INVALID, "lm_dev_merkle_tree: ctx is null");

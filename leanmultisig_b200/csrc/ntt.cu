@@ -202,6 +202,45 @@ __global__ void ntt_layer_kernel(uint32_t* __restrict__ mat, uint64_t h, uint64_
   *hi = b;
 }
 
+// Layers [l_first, log_h) on a locally held subset of rows (row-sharded multi-GPU commit):
+// local row (m, j') <-> global row m * block + offset + j'; the partner of a row differs only in m.
+__global__ void ntt_layer_mapped_kernel(uint32_t* __restrict__ mat, uint64_t w4, int log_h, int l, uint64_t n_blocks,
+                                        uint64_t run, uint64_t block, uint64_t offset, const uint32_t* __restrict__ tw,
+                                        int tw_shift) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = (n_blocks / 2) * run * w4;
+  if (idx >= total) return;
+  const uint64_t c4 = idx % w4, pr = idx / w4;
+  const uint64_t pair = pr / run, jp = pr % run;
+  const uint64_t m_stride = ((uint64_t)1 << l) / block;
+  const uint64_t m_lo = (pair / m_stride) * 2 * m_stride + pair % m_stride;
+  const uint64_t m_hi = m_lo + m_stride;
+  const uint64_t grow = m_lo * block + offset + jp;
+  const uint64_t e = (grow & (((uint64_t)1 << l) - 1)) << (log_h - l - 1);
+  const uint32_t t = __ldg(tw + (e << tw_shift));
+  uint4* lo = reinterpret_cast<uint4*>(mat + (m_lo * run + jp) * (w4 * 4)) + c4;
+  uint4* hi = reinterpret_cast<uint4*>(mat + (m_hi * run + jp) * (w4 * 4)) + c4;
+  uint4 a = *lo, b = *hi;
+  bfly4(a, b, t);
+  *lo = a;
+  *hi = b;
+}
+
+cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, unsigned log_h, unsigned l_first,
+                              uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, const uint32_t* d_tw,
+                              unsigned tw_log_n) {
+  if (w % 4 != 0 || log_h > tw_log_n || l_first > log_h || n_blocks < 2 || (((uint64_t)1 << l_first) < block))
+    return cudaErrorInvalidValue;
+  const int tw_shift = (int)tw_log_n - (int)log_h;
+  const uint64_t total = (n_blocks / 2) * run * (w / 4);
+  for (unsigned l = l_first; l < log_h; l++) {
+    ntt_layer_mapped_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l, n_blocks, run,
+                                                                                block, offset, d_tw, tw_shift);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
 static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32_t* d_src, uint32_t log_block,
                               uint32_t r, uint64_t h, uint64_t w, int skip, const uint32_t* d_tw, unsigned tw_log_n) {
   int log_h = 0;

@@ -1,0 +1,190 @@
+"""Row-sharded WHIR commit across the GPUs of one node.
+
+One process per GPU (`torch.distributed`, NCCL over NVLink; gloo in the CPU tests).  The stacked polynomial has
+index (column c | position s); rank q holds, for every column, the slice of s whose top g = log2(world) bits equal q.
+
+  1. local      T_q = reorder_and_dft of the shard (a polynomial of n_vars - g variables, same folding and rate):
+                the first log2(h / G) butterfly layers of the global transform act independently on G row blocks
+                and block q is exactly rank q's shard.
+  2. all-to-all rank q sends rows [q' run, (q'+1) run) of T_q to rank q' (run = h / G^2): (G-1)/G of its block.
+  3. combine    the last g layers pair rows that differ only in the block index m, now all local
+                (lm_dev_dft_layers_mapped).  Rank q' ends up with G runs of `run` consecutive codeword rows.
+  4. Merkle     leaf sponge + subtree per run (local), all-gather of the G^2 subtree roots (32 B each), the top
+                2g levels are replicated.
+The compute steps go through a backend object so that the CPU test tier can run the same orchestration with the
+oracle over gloo; the product backend is the CUDA library (`CudaBackend`), there is no CPU product path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_of(evals: np.ndarray, n_vars: int, folding: int, rank: int, world: int) -> np.ndarray:
+    """The part of the (host) polynomial rank `rank` owns, laid out as a polynomial of n_vars - g variables."""
+    g = world.bit_length() - 1
+    assert world == 1 << g and n_vars - folding >= 2 * g
+    cols = 1 << folding
+    chunk = 1 << (n_vars - folding)
+    sub = chunk >> g
+    return np.ascontiguousarray(evals.reshape(cols, chunk)[:, rank * sub:(rank + 1) * sub]).reshape(-1)
+
+
+class ShardGeometry:
+    def __init__(self, n_vars: int, folding: int, log_inv_rate: int, world: int):
+        self.world = world
+        self.g = world.bit_length() - 1
+        assert world == 1 << self.g, "world size must be a power of two"
+        self.n_vars, self.folding, self.log_inv_rate = n_vars, folding, log_inv_rate
+        self.log_h = n_vars + log_inv_rate - folding
+        self.h = 1 << self.log_h
+        self.block = self.h >> self.g          # rows of one rank's local transform
+        self.run = self.block >> self.g        # consecutive codeword rows per (rank, block) pair
+        assert self.run >= 2, "domain too small for this many ranks"
+        self.log_run = self.run.bit_length() - 1
+
+    def owner(self, row: int) -> int:
+        return (row // self.run) % self.world
+
+    def local_row(self, row: int) -> int:
+        """index of a global codeword row inside its owner's local matrix ((m, j') order)"""
+        m, rest = divmod(row, self.block)
+        return m * self.run + rest % self.run
+
+    def subtree_index(self, rank: int, m: int) -> int:
+        """position of rank's m-th subtree root in the global layer of G^2 roots"""
+        return m * self.world + rank
+
+
+class ShardedCommit:
+    """Collective: every rank calls commit() with its shard; all ranks return the same root."""
+
+    def __init__(self, backend, dist, n_vars: int, folding: int, log_inv_rate: int, live_cols: int | None = None):
+        self.b, self.dist = backend, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.geo = ShardGeometry(n_vars, folding, log_inv_rate, self.world)
+        self.cols = (1 << folding) if live_cols is None else live_cols
+        self.full_cols = 1 << folding
+
+    def commit(self, shard):
+        geo, b = self.geo, self.b
+        w = self.cols
+        # 1. local transform of the shard
+        t_local = b.reorder_and_dft(shard, geo.n_vars - geo.g, geo.folding, geo.log_inv_rate, w)  # block x w
+        # 2. exchange: equal splits of `run` rows, received in block order m = source rank
+        mat = b.empty_like(t_local)
+        if self.world > 1:
+            b.all_to_all(self.dist, mat, t_local)
+        else:
+            mat = t_local
+        # 3. last g layers on the local rows
+        if geo.g:
+            b.dft_layers_mapped(mat, w, geo.log_h, geo.log_h - geo.g, self.world, geo.run, geo.block, self.rank * geo.run)
+        self.codeword = mat
+        # 4. one subtree per run, then the replicated top
+        self.subtrees = [b.merkle_tree(b.rows(mat, m * geo.run, geo.run), self.full_cols, w) for m in range(self.world)]
+        my_roots = b.stack_roots(self.subtrees)                      # world x 8
+        all_roots = b.all_gather_roots(self.dist, my_roots)          # [rank][m] -> world x world x 8
+        top_layer0 = b.permute_roots(all_roots)                      # index m * world + rank
+        self.top = b.merkle_levels(top_layer0)                       # (2 G^2 - 1) x 8
+        self.root = b.to_host(self.top)[-1]
+        return self.root
+
+    def open_local(self, row: int):
+        """Opening of a codeword row this rank owns: (row zero-extended, sibling path leaf level first)."""
+        geo, b = self.geo, self.b
+        assert geo.owner(row) == self.rank
+        m, rest = divmod(row, geo.block)
+        jp = rest % geo.run
+        sub = b.to_host(self.subtrees[m])
+        path = []
+        off, n, idx = 0, geo.run, jp
+        for _ in range(geo.log_run):
+            path.append(sub[off + (idx ^ 1)])
+            off += n
+            n >>= 1
+            idx >>= 1
+        top = b.to_host(self.top)
+        off, n, idx = 0, self.world * self.world, geo.subtree_index(self.rank, m)
+        while n > 1:
+            path.append(top[off + (idx ^ 1)])
+            off += n
+            n >>= 1
+            idx >>= 1
+        data = b.to_host(b.rows(self.codeword, m * geo.run + jp, 1)).reshape(-1)
+        full = np.zeros(self.full_cols, dtype=np.uint32)
+        full[: data.size] = data
+        return full, np.stack(path)
+
+
+class CudaBackend:
+    """Compute steps on one GPU through the C ABI; tensors are torch CUDA int32 (device memory + NCCL plumbing)."""
+
+    def __init__(self, ctx):
+        import torch
+
+        from ._lib import check, lib
+
+        self.torch, self.ctx, self.lib, self.check = torch, ctx, lib(), check
+        # one stream for torch ops, NCCL and the library's kernels
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        ctx.set_stream(self.stream.cuda_stream)
+
+    def to_device(self, a: np.ndarray):
+        return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+    def to_host(self, t) -> np.ndarray:
+        return t.cpu().numpy().view(np.uint32)
+
+    def empty_like(self, t):
+        return self.torch.empty_like(t)
+
+    def rows(self, t, start: int, count: int):
+        return t[start:start + count]
+
+    def reorder_and_dft(self, shard, n_vars, folding, log_inv_rate, cols):
+        h = 1 << (n_vars + log_inv_rate - folding)
+        out = self.torch.empty((h, cols), dtype=self.torch.int32, device=shard.device)
+        self.check(self.lib.lm_dev_reorder_and_dft(self.ctx.handle, shard.data_ptr(), n_vars, 1, folding, log_inv_rate, cols,
+                                                   out.data_ptr()))
+        return out
+
+    def all_to_all(self, dist, out, inp):
+        self.ctx.sync()
+        dist.all_to_all_single(out, inp)
+        self.torch.cuda.synchronize()
+
+    def dft_layers_mapped(self, mat, w, log_h, l_first, n_blocks, run, block, offset):
+        self.check(self.lib.lm_dev_dft_layers_mapped(self.ctx.handle, mat.data_ptr(), w, log_h, l_first, n_blocks, run, block, offset))
+
+    def merkle_tree(self, rows, full_cols, eff_cols):
+        h, w = rows.shape
+        layers = self.torch.empty((2 * h - 1, 8), dtype=self.torch.int32, device=rows.device)
+        self.check(self.lib.lm_dev_merkle_tree(self.ctx.handle, rows.data_ptr(), h, w, full_cols, eff_cols, layers.data_ptr()))
+        return layers
+
+    def stack_roots(self, subtrees):
+        return self.torch.stack([s[-1] for s in subtrees])
+
+    def all_gather_roots(self, dist, my_roots):
+        self.ctx.sync()
+        world = dist.get_world_size()
+        out = self.torch.empty((world,) + tuple(my_roots.shape), dtype=my_roots.dtype, device=my_roots.device)
+        if world > 1:
+            dist.all_gather_into_tensor(out, my_roots.contiguous())
+        else:
+            out[0] = my_roots
+        return out
+
+    def permute_roots(self, all_roots):
+        # all_roots[rank][m] -> layer index m * world + rank
+        return all_roots.permute(1, 0, 2).contiguous().reshape(-1, 8)
+
+    def merkle_levels(self, layer0):
+        n = layer0.shape[0]
+        layers = self.torch.empty((2 * n - 1, 8), dtype=self.torch.int32, device=layer0.device)
+        layers[:n] = layer0
+        if n > 1:
+            self.check(self.lib.lm_dev_merkle_levels(self.ctx.handle, layers.data_ptr(), n))
+        self.ctx.sync()
+        return layers

@@ -192,6 +192,13 @@ def reorder_and_dft(evals, n_vars: int, dim: int, folding: int, log_inv_rate: in
     return out
 
 
+def dft_layers_mapped(mat, log_h: int, l_first: int, n_blocks: int, run: int, block: int, offset: int) -> np.ndarray:
+    m = _u32(mat).copy()
+    lib().lm_or_dft_layers_mapped(_p(m), C.c_uint64(m.shape[1]), C.c_uint32(log_h), C.c_uint32(l_first),
+                                  C.c_uint64(n_blocks), C.c_uint64(run), C.c_uint64(block), C.c_uint64(offset))
+    return m
+
+
 # ---------------------------------------------------------------- multilinear
 def eq_table(point, scalar=None) -> np.ndarray:
     pt = _u32(point).reshape(-1, 5)

@@ -69,3 +69,33 @@ void lm_or_reorder_and_dft(const uint32_t *evals, uint32_t n_vars, uint32_t dim,
   uint64_t h = (uint64_t)1 << (n_vars + log_inv_rate - folding_factor);
   lm_or_dft_batch_by_evals(out, h, (uint64_t)dft_n_cols * dim);
 }
+
+/* Layers [l_first, log_h) of the evals-DFT network applied to a SUBSET of rows held locally, for the row-sharded
+ * multi-GPU commit: local row (m, j') with m < n_blocks, j' < run  <->  global row
+ * m * block + offset + j'.  Only layers whose partner row is also local may be requested, i.e.
+ * 2^l_first >= block (partner = other m, same j').  Same butterfly and twiddles as dft.rs:79-144,546-568. */
+void lm_or_dft_layers_mapped(uint32_t *mat, uint64_t w, uint32_t log_h, uint32_t l_first, uint64_t n_blocks,
+                             uint64_t run, uint64_t block, uint64_t offset) {
+  uint64_t h = (uint64_t)1 << log_h;
+  kb_t g = kb_two_adic_generator(log_h);
+  for (uint32_t l = l_first; l < log_h; l++) {
+    uint64_t m_stride = ((uint64_t)1 << l) / block; /* partner block distance */
+#pragma omp parallel for schedule(static)
+    for (uint64_t idx = 0; idx < n_blocks / 2 * run; idx++) {
+      uint64_t pair = idx / run, jp = idx % run;
+      uint64_t m_lo = (pair / m_stride) * 2 * m_stride + pair % m_stride;
+      uint64_t m_hi = m_lo + m_stride;
+      uint64_t grow = m_lo * block + offset + jp; /* global row of the low element */
+      uint64_t e = (grow & (((uint64_t)1 << l) - 1)) << (log_h - l - 1);
+      kb_t t = kb_pow(g, e);
+      uint32_t *lo = mat + (m_lo * run + jp) * w, *hi = mat + (m_hi * run + jp) * w;
+      for (uint64_t c = 0; c < w; c++) {
+        kb_t a = lo[c], b = hi[c];
+        kb_t x = kb_mul(kb_sub(b, a), t);
+        lo[c] = kb_add(a, x);
+        hi[c] = kb_sub(a, x);
+      }
+    }
+    (void)h;
+  }
+}

@@ -49,6 +49,9 @@ void lm_or_dft_batch_by_evals(uint32_t *mat, uint64_t h, uint64_t w);
 void lm_or_reorder_and_dft(const uint32_t *evals, uint32_t n_vars, uint32_t dim, uint32_t folding_factor,
                            uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t *out);
 
+void lm_or_dft_layers_mapped(uint32_t *mat, uint64_t w, uint32_t log_h, uint32_t l_first, uint64_t n_blocks,
+                             uint64_t run, uint64_t block, uint64_t offset);
+
 /* poly.c */
 void lm_or_eq_table(const uint32_t *point, uint32_t k, const uint32_t scalar[5], uint32_t *out);
 void lm_or_expand_from_univariate(const uint32_t y[5], uint32_t n, uint32_t *out);
