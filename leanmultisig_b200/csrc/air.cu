@@ -131,22 +131,35 @@ __device__ __forceinline__ Ef ld_val<Ef>(const uint32_t* col, uint64_t row) {
 }
 
 // partial[blockIdx.x][z] = sum over this CTA's j of eq(j) * C(col(2j) + z (col(2j+1) - col(2j))), z = 0,2,3,4,5
+// EF rounds keep the 22 per-column differences in shared memory (one 4-byte-interleaved slot per thread, so the
+// accesses are conflict free): holding point and difference in registers at once is 220 words and spilled 1.4 KiB
+// per thread in the first version of this kernel.
+constexpr int AIR_THREADS = 128;
 template <class T, int DIM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(AIR_THREADS)
 air_exec_round_kernel(const uint32_t* __restrict__ cols, uint64_t n, uint64_t half, const uint32_t* __restrict__ eq_hi,
                       const uint32_t* __restrict__ eq_lo, int lo_vars, AirExtra X, uint32_t* __restrict__ partial) {
-  __shared__ Ef red[EXEC_DEG][4];
+  __shared__ Ef red[EXEC_DEG][AIR_THREADS / 32];
+  extern __shared__ uint32_t diff_s[];  // DIM == 5: [22 * 5][AIR_THREADS]
   Ef acc[EXEC_DEG];
 #pragma unroll
   for (int z = 0; z < EXEC_DEG; z++) acc[z] = ef_zero();
-  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += (uint64_t)gridDim.x * blockDim.x) {
-    T pt[EXEC_ALL], diff[EXEC_ALL];
+  const int tid = threadIdx.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + tid; j < half; j += (uint64_t)gridDim.x * blockDim.x) {
+    T pt[EXEC_ALL];
+    T diff_r[DIM == 1 ? EXEC_ALL : 1];
 #pragma unroll
     for (int c = 0; c < EXEC_ALL; c++) {
       const uint32_t* col = cols + (uint64_t)c * n * DIM;
       const T lo = ld_val<T>(col, 2 * j), hi = ld_val<T>(col, 2 * j + 1);
       pt[c] = lo;
-      diff[c] = hi - lo;
+      const T d = hi - lo;
+      if constexpr (DIM == 1) {
+        diff_r[c] = d;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 5; k++) diff_s[(c * 5 + k) * AIR_THREADS + tid] = d.c[k];
+      }
     }
     Ef eh, el;
 #pragma unroll
@@ -155,16 +168,29 @@ air_exec_round_kernel(const uint32_t* __restrict__ cols, uint64_t n, uint64_t ha
       el.c[c] = __ldg(eq_lo + 5 * (j & (((uint64_t)1 << lo_vars) - 1)) + c);
     }
     const Ef eq = ef_mul(eh, el);
-#pragma unroll
+#pragma unroll 1
     for (int zi = 0; zi < EXEC_DEG; zi++) {
-      if (zi == 1) {
+      if (zi >= 1) {
+        const int steps = zi == 1 ? 2 : 1;  // z: 0 -> 2 -> 3 -> 4 -> 5
+        for (int s2 = 0; s2 < steps; s2++) {
 #pragma unroll
-        for (int c = 0; c < EXEC_ALL; c++) pt[c] = pt[c] + diff[c] + diff[c];  // z: 0 -> 2
-      } else if (zi > 1) {
+          for (int c = 0; c < EXEC_ALL; c++) {
+            if constexpr (DIM == 1) {
+              pt[c] = pt[c] + diff_r[c];
+            } else {
+              Ef d;
 #pragma unroll
-        for (int c = 0; c < EXEC_ALL; c++) pt[c] = pt[c] + diff[c];
+              for (int k = 0; k < 5; k++) d.c[k] = diff_s[(c * 5 + k) * AIR_THREADS + tid];
+              pt[c] = pt[c] + d;
+            }
+          }
+        }
       }
-      acc[zi] = ef_add(acc[zi], ef_mul(exec_air_eval<T>(pt, X), eq));
+      const Ef v = ef_mul(exec_air_eval<T>(pt, X), eq);
+      // acc[zi] += v with a register-indexed accumulator (zi is a runtime loop counter)
+#pragma unroll
+      for (int z = 0; z < EXEC_DEG; z++)
+        if (z == zi) acc[z] = ef_add(acc[z], v);
     }
   }
   // warp then CTA reduction
@@ -269,12 +295,19 @@ cudaError_t air_exec_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t
   cudaError_t e;
   if ((e = eq_table(stream, d_eq_point, hi_vars, one, d_hi)) != cudaSuccess) return e;
   if ((e = eq_table(stream, d_eq_point + 5 * hi_vars, lo_vars, one, d_lo)) != cudaSuccess) return e;
-  uint64_t blocks = (half + 127) / 128;
+  uint64_t blocks = (half + AIR_THREADS - 1) / AIR_THREADS;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (dim == 1)
-    air_exec_round_kernel<Fb, 1><<<(unsigned)blocks, 128, 0, stream>>>(d_cols, n, half, d_hi, d_lo, lo_vars, X, d_part);
-  else
-    air_exec_round_kernel<Ef, 5><<<(unsigned)blocks, 128, 0, stream>>>(d_cols, n, half, d_hi, d_lo, lo_vars, X, d_part);
+  if (dim == 1) {
+    air_exec_round_kernel<Fb, 1><<<(unsigned)blocks, AIR_THREADS, 0, stream>>>(d_cols, n, half, d_hi, d_lo, lo_vars, X, d_part);
+  } else {
+    const size_t smem = (size_t)EXEC_ALL * 5 * AIR_THREADS * sizeof(uint32_t);  // 55 KiB
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(air_exec_round_kernel<Ef, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    air_exec_round_kernel<Ef, 5><<<(unsigned)blocks, AIR_THREADS, smem, stream>>>(d_cols, n, half, d_hi, d_lo, lo_vars, X, d_part);
+  }
   count_launch();
   air_sum_partials_kernel<<<1, 32, 0, stream>>>(d_part, (int)blocks, EXEC_DEG, d_out);
   count_launch();

@@ -44,10 +44,48 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 }  // namespace
 
+// Size-keyed cache of device allocations: a commit needs three GiB-scale buffers and cudaMalloc / cudaFree of that
+// size cost milliseconds each (the reference resets a bump arena per proof for the same reason,
+// crates/backend/zk-alloc/src/lib.rs:102-115).
+struct DevicePool {
+  std::vector<std::pair<size_t, void*>> free_list;
+  cudaError_t get(size_t bytes, void** out) {
+    for (size_t i = 0; i < free_list.size(); i++)
+      if (free_list[i].first == bytes) {
+        *out = free_list[i].second;
+        free_list.erase(free_list.begin() + i);
+        return cudaSuccess;
+      }
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) {  // drop the cache and retry once
+      cudaGetLastError();
+      release_all();
+      e = cudaMalloc(out, bytes ? bytes : 1);
+    }
+    return e;
+  }
+  void put(size_t bytes, void* p) {
+    if (!p) return;
+    if (free_list.size() >= 12) {
+      cudaFree(free_list.front().second);
+      free_list.erase(free_list.begin());
+    }
+    free_list.emplace_back(bytes, p);
+  }
+  void release_all() {
+    for (auto& e : free_list) cudaFree(e.second);
+    free_list.clear();
+  }
+};
+
 struct lm_ctx {
+  DevicePool pool;
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host-to-device copies that overlap with compute on `stream`
+  cudaEvent_t ev_copy[8] = {};         // copy of column group g finished
+  cudaEvent_t ev_start = nullptr;
   uint32_t* d_tw = nullptr;
   unsigned tw_log_n = 0;
   uint32_t* d_scratch = nullptr;  // grows on demand (MLE evaluation tables)
@@ -76,6 +114,7 @@ struct lm_tree {
   bool owns_evals = false;
   uint32_t* d_codeword = nullptr;  // height x stored_width
   uint32_t* d_layers = nullptr;    // (2 height - 1) x 8
+  size_t evals_bytes = 0, codeword_bytes = 0, layers_bytes = 0;
 };
 
 // Product-sumcheck session of WHIR open (reference: SumcheckSingle, crates/whir/src/open.rs:323-446).
@@ -161,6 +200,9 @@ int lm_init(int device, uint32_t max_log_domain, lm_ctx** out_ctx) {
   c->device = device;
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev_copy) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   c->tw_log_n = max_log_domain;
   if (max_log_domain > 0) {
     CU(cudaMalloc(&c->d_tw, sizeof(uint32_t) << (max_log_domain - 1)));
@@ -177,11 +219,16 @@ int lm_destroy(lm_ctx* c) {
   if (!c) return LM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  c->pool.release_all();
   if (c->d_tw) cudaFree(c->d_tw);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_small) cudaFree(c->d_small);
   if (c->d_point) cudaFree(c->d_point);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto ev : c->ev_copy)
+    if (ev) cudaEventDestroy(ev);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
   delete c;
   return LM_OK;
 }
@@ -399,21 +446,55 @@ static int commit_impl(lm_ctx* c, const uint32_t* evals, bool evals_on_device, u
   if (evals_on_device && !retain_evals) {
     d_src = evals;  // caller guarantees 2^n_vars elements are addressable
   } else {
-    CUT(cudaMalloc(&t->d_evals, (need_words ? need_words : 1) * sizeof(uint32_t)));
+    t->evals_bytes = (need_words ? need_words : 1) * sizeof(uint32_t);
+    CUT(c->pool.get(t->evals_bytes, reinterpret_cast<void**>(&t->d_evals)));
     t->owns_evals = true;
-    if (live_words)
-      CUT(cudaMemcpyAsync(t->d_evals, evals, live_words * sizeof(uint32_t),
-                          evals_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-    if (need_words > live_words)
-      CUT(cudaMemsetAsync(t->d_evals + live_words, 0, (need_words - live_words) * sizeof(uint32_t), c->stream));
     d_src = t->d_evals;
   }
-  CUT(cudaMalloc(&t->d_codeword, t->height * t->stored_width * sizeof(uint32_t)));
-  CUT(cudaMalloc(&t->d_layers, (2 * t->height - 1) * 8 * sizeof(uint32_t)));
-  CUT(lm::ntt_reorder_and_dft(c->stream, d_src, n_vars, dim, folding, log_inv_rate, (uint32_t)dft_cols, t->d_codeword,
-                              c->d_tw, c->tw_log_n));
-  CUT(lm::merkle_leaf_digests(c->stream, t->d_codeword, t->height, t->stored_width, t->full_width, t->effective_width,
-                              t->d_layers));
+  t->codeword_bytes = t->height * t->stored_width * sizeof(uint32_t);
+  t->layers_bytes = (2 * t->height - 1) * 8 * sizeof(uint32_t);
+  CUT(c->pool.get(t->codeword_bytes, reinterpret_cast<void**>(&t->d_codeword)));
+  CUT(c->pool.get(t->layers_bytes, reinterpret_cast<void**>(&t->d_layers)));
+  // Host input with whole live columns: pipeline  copy(group g) -> transform(group g) -> sponge step(s) of group g
+  // over column groups taken right to left (the sponge absorbs the row right to left), so that PCIe, the NTT and
+  // the hash overlap.  Everything else takes the plain path.
+  const uint32_t stored_w = t->stored_width, eff_w = t->effective_width;
+  const bool pipelined = !evals_on_device && dim == 1 && stored_w == eff_w && eff_w % 8 == 0 && eff_w >= 16 &&
+                         actual_len == eff_cols * block_len && lm::merkle_leaf_chunked_ok(stored_w, full_w, eff_w);
+  if (!pipelined) {
+    if (!evals_on_device || retain_evals) {
+      if (live_words)
+        CUT(cudaMemcpyAsync(t->d_evals, evals, live_words * sizeof(uint32_t),
+                            evals_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+      if (need_words > live_words)
+        CUT(cudaMemsetAsync(t->d_evals + live_words, 0, (need_words - live_words) * sizeof(uint32_t), c->stream));
+    }
+    CUT(lm::ntt_reorder_and_dft(c->stream, d_src, n_vars, dim, folding, log_inv_rate, (uint32_t)dft_cols, t->d_codeword,
+                                c->d_tw, c->tw_log_n));
+    CUT(lm::merkle_leaf_digests(c->stream, t->d_codeword, t->height, t->stored_width, t->full_width, t->effective_width,
+                                t->d_layers));
+  } else {
+    const uint32_t n_groups = eff_w / 8 < 8 ? eff_w / 8 : 8;       // at most 8 column groups in flight
+    const uint32_t cols_per_group = (eff_w / 8 + n_groups - 1) / n_groups * 8;
+    if (need_words > live_words)
+      CUT(cudaMemsetAsync(t->d_evals + live_words, 0, (need_words - live_words) * sizeof(uint32_t), c->stream));
+    CUT(cudaEventRecord(c->ev_start, c->stream));
+    CUT(cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
+    uint32_t g = 0;
+    for (int64_t col_end = eff_w; col_end > 0; col_end -= cols_per_group, g++) {
+      const uint32_t col_begin = col_end > (int64_t)cols_per_group ? (uint32_t)(col_end - cols_per_group) : 0u;
+      const uint32_t count = (uint32_t)col_end - col_begin;
+      CUT(cudaMemcpyAsync(t->d_evals + (size_t)col_begin * block_len, evals + (size_t)col_begin * block_len,
+                          (size_t)count * block_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+      CUT(cudaEventRecord(c->ev_copy[g % 8], c->copy_stream));
+      CUT(cudaStreamWaitEvent(c->stream, c->ev_copy[g % 8], 0));
+      CUT(lm::ntt_reorder_and_dft_cols(c->stream, t->d_evals, n_vars, folding, log_inv_rate, (uint32_t)dft_cols, col_begin,
+                                       count, t->d_codeword, c->d_tw, c->tw_log_n));
+      for (int64_t chunk = (int64_t)(col_begin + count) / 8 - 1; chunk >= (int64_t)col_begin / 8; chunk--)
+        CUT(lm::merkle_leaf_absorb_chunk(c->stream, t->d_codeword, t->height, stored_w, full_w, eff_w, (uint32_t)chunk,
+                                         t->d_layers));
+    }
+  }
   CUT(lm::merkle_tree_from_digests(c->stream, t->d_layers, t->height));
   CUT(cudaMemcpyAsync(out_root, t->d_layers + (2 * t->height - 2) * 8, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                       c->stream));
@@ -506,9 +587,15 @@ int lm_tree_free(lm_tree* t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
   }
-  if (t->d_evals && t->owns_evals) cudaFree(t->d_evals);
-  if (t->d_codeword) cudaFree(t->d_codeword);
-  if (t->d_layers) cudaFree(t->d_layers);
+  if (t->ctx) {
+    if (t->d_evals && t->owns_evals) t->ctx->pool.put(t->evals_bytes, t->d_evals);
+    t->ctx->pool.put(t->codeword_bytes, t->d_codeword);
+    t->ctx->pool.put(t->layers_bytes, t->d_layers);
+  } else {
+    if (t->d_evals && t->owns_evals) cudaFree(t->d_evals);
+    if (t->d_codeword) cudaFree(t->d_codeword);
+    if (t->d_layers) cudaFree(t->d_layers);
+  }
   delete t;
   return LM_OK;
 }

@@ -83,6 +83,31 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
   out[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
+// One sponge step for every row: state (lanes 0..7, kept in the digest buffer between steps) absorbs rate chunk
+// `chunk` of the row.  Lets the commit hash columns as soon as they are transformed, right to left, while the
+// host-to-device copy of the columns further left is still in flight.
+__global__ void __launch_bounds__(128, LEAF_MIN_BLOCKS)
+leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t chunk, int first, State16 init,
+                   uint32_t* __restrict__ digests) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h) return;
+  uint32_t s[16];
+  uint4* dg = reinterpret_cast<uint4*>(digests + 8 * r);
+  if (first) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = init.v[i];
+  } else {
+    const uint4 a = dg[0], b = dg[1];
+    s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(mat + r * stored_w + 8 * chunk);
+  const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+  s[8] = lo.x, s[9] = lo.y, s[10] = lo.z, s[11] = lo.w, s[12] = hi.x, s[13] = hi.y, s[14] = hi.z, s[15] = hi.w;
+  p1_compress<8>(s, c_p1);
+  dg[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  dg[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
 // One level: next[i] = C(prev[2i] || prev[2i+1])[0..8), one thread per parent.  Used while a level still fills
 // the machine; the short tail of the tree goes through tree_levels_kernel below.
 __global__ void __launch_bounds__(128)
@@ -175,6 +200,22 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
   const int T = 128;
   const uint64_t blocks = (h + T - 1) / T;
   leaf_sponge_kernel<<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests); count_launch();
+  return cudaGetLastError();
+}
+
+// true when the leaf sponge can be run one rate chunk at a time starting from the zero-suffix state
+bool merkle_leaf_chunked_ok(uint32_t stored_w, uint32_t full_w, uint32_t eff_w) {
+  return full_w % 8 == 0 && eff_w % 8 == 0 && stored_w % 8 == 0 && eff_w <= stored_w && eff_w > 0 && (full_w - eff_w) / 8 >= 2;
+}
+// absorb chunk `chunk` (chunks must be fed from eff_w / 8 - 1 down to 0); the first call seeds the state
+cudaError_t merkle_leaf_absorb_chunk(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
+                                     uint32_t full_w, uint32_t eff_w, uint32_t chunk, uint32_t* d_digests) {
+  if (!merkle_leaf_chunked_ok(stored_w, full_w, eff_w) || chunk >= eff_w / 8) return cudaErrorInvalidValue;
+  const int first = chunk == eff_w / 8 - 1;
+  State16 init{};
+  if (first) init = zero_suffix_state_host((full_w - eff_w) / 8);
+  leaf_absorb_kernel<<<(unsigned)((h + 127) / 128), 128, 0, stream>>>(d_mat, h, stored_w, chunk, first, init, d_digests);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -76,6 +76,12 @@ __device__ __forceinline__ void bfly4(uint4& a, uint4& b, uint32_t t) {
   bfly(a.w, b.w, t);
 }
 
+#ifndef NTT_THREADS
+#define NTT_THREADS 512
+#endif
+#ifndef NTT_MIN_BLOCKS
+#define NTT_MIN_BLOCKS 2
+#endif
 constexpr int TILE_COLS = 8;       // u32 columns per tile = 32 B per row
 constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory
 
@@ -117,13 +123,13 @@ __device__ __forceinline__ void tile_group(uint4* tile, const uint32_t* tw_s, in
 // Pass over layers [l0 + skip, l0 + L) of an h x w matrix; one CTA per (column tile, row group).
 // src == nullptr: in place on `mat`.  src != nullptr (only with l0 == 0): gather from the evaluation vector
 // (dim = 1): element (row, col) = src[(col << log_block) + (row >> r)].
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
 ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
-                int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift) {
+                int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift,
+                uint32_t tile0, uint32_t n_col_tiles) {
   extern __shared__ uint4 tile[];  // [2^L][2] slots, then 2^L twiddle words
   uint32_t* tw_s = reinterpret_cast<uint32_t*>(tile + ((size_t)2 << L));
-  const uint32_t n_col_tiles = (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
-  const uint64_t col0 = (uint64_t)(blockIdx.x % n_col_tiles) * TILE_COLS;  // column tile varies fastest: CTAs that
+  const uint64_t col0 = (uint64_t)(tile0 + blockIdx.x % n_col_tiles) * TILE_COLS;  // column tile varies fastest: CTAs that
   const uint64_t grp = blockIdx.x / n_col_tiles;                           // run together cover whole rows
   // rows of this tile: row(j) = ((grp >> l0) << (l0 + L)) + (grp & (2^l0 - 1)) + j * 2^l0
   const uint64_t row_lo = grp & (((uint64_t)1 << l0) - 1);
@@ -241,8 +247,10 @@ cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, 
   return cudaGetLastError();
 }
 
+// col_tile0 / n_tiles: restrict the pass kernels to a range of 8-column tiles (n_tiles == 0: all of them)
 static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32_t* d_src, uint32_t log_block,
-                              uint32_t r, uint64_t h, uint64_t w, int skip, const uint32_t* d_tw, unsigned tw_log_n) {
+                              uint32_t r, uint64_t h, uint64_t w, int skip, const uint32_t* d_tw, unsigned tw_log_n,
+                              uint32_t col_tile0 = 0, uint32_t n_tiles = 0) {
   int log_h = 0;
   while (((uint64_t)1 << log_h) < h) log_h++;
   if (((uint64_t)1 << log_h) != h || (unsigned)log_h > tw_log_n) return cudaErrorInvalidValue;
@@ -270,15 +278,30 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     const int L = (log_h - l0 + (n_pass - p) - 1) / (n_pass - p);
     const int sk = skip_left < L ? skip_left : L;
     skip_left -= sk;
-    const uint64_t n_cta = ((w + TILE_COLS - 1) / TILE_COLS) * (h >> L);
+    const uint32_t tiles = n_tiles ? n_tiles : (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
+    const uint64_t n_cta = (uint64_t)tiles * (h >> L);
     const size_t smem = ((size_t)1 << L) * 36;  // tile + per-CTA twiddles
-    ntt_pass_kernel<<<(unsigned)n_cta, 512, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
-                                                            log_block, r, d_tw, tw_shift); count_launch();
+    ntt_pass_kernel<<<(unsigned)n_cta, NTT_THREADS, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
+                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     l0 += L;
   }
   return cudaSuccess;
+}
+
+// gather + DFT of columns [col_begin, col_begin + col_count) only (both multiples of 8; dim = 1, width % 4 == 0):
+// used to overlap the host-to-device copy of later columns with the transform of earlier ones
+cudaError_t ntt_reorder_and_dft_cols(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding_factor,
+                                     uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t col_begin, uint32_t col_count,
+                                     uint32_t* d_out, const uint32_t* d_tw, unsigned tw_log_n) {
+  if (col_begin % 8 || col_count % 8 || col_count == 0 || col_begin + col_count > dft_n_cols || dft_n_cols % 4)
+    return cudaErrorInvalidValue;
+  const uint32_t log_block = n_vars + log_inv_rate - folding_factor;
+  const uint64_t h = (uint64_t)1 << log_block;
+  const int skip = (int)(log_inv_rate < log_block ? log_inv_rate : log_block);
+  return run_layers(stream, d_out, d_evals, log_block, log_inv_rate, h, dft_n_cols, skip, d_tw, tw_log_n, col_begin / 8,
+                    col_count / 8);
 }
 
 cudaError_t ntt_dft_batch_by_evals(cudaStream_t stream, uint32_t* d_mat, uint64_t h, uint64_t w, int skip_layers,

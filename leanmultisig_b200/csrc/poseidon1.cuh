@@ -42,27 +42,71 @@ struct P1Tables {
 // v^3 * R^-2 for a lane a < 1.43 p; result < 1.75 p
 LM_HD uint32_t p1_sbox_lazy(uint32_t a) { return kb_mul_lazy(kb_mul_lazy(a, a), a); }
 
-// out[i] = redc(init[i] + sum_j C[(i - j) mod 16] * a3[j]),  C = first column of the circulant MDS.
-// N_OUT < 16 computes only the first N_OUT lanes (the digest half of a compression).
+// out[i] = redc(init[i] + 4 * sum_j C[(i - j) mod 16] * a3[j]),  C = first column of the circulant MDS.
+// N_OUT < 16 computes only the first N_OUT lanes (the digest half of a compression).  The factor 4 is the
+// un-normalised even/odd splitting below; it is part of the scale drift the generated constants account for.
 //
-// Device version: the sum (< 2^41) is accumulated EXACTLY on the FP64 pipe.  Measured on B200
+// Device version: the sum is accumulated EXACTLY on the FP64 pipe.  Measured on B200
 // (profiles/r01_int_pipes2.txt): IMAD.WIDE issues once per 4 cycles per SM sub-partition (6 with a 64-bit
-// addend), DFMA once per ~2, and the two pipes overlap, so 16 DFMA per lane replace 12 IMAD.WIDE + adds.
-// u32 -> f64 is the 2^52 trick (one DADD), f64 -> (lo, hi) another DADD; every intermediate is an integer
-// below 2^53, so the result is bit-identical to the integer evaluation on the host path.
+// addend), DFMA once per ~2.  u32 -> f64 is the 2^52 trick (one DADD), f64 -> (lo, hi) another DADD; every
+// intermediate is an integer of magnitude below 2^53, so the result is bit-identical to the integer evaluation
+// of the host path.  The circulant product y(X) = c(X) x(X) mod X^16 - 1 is split by the CRT
+//   X^16 - 1 = (X^8 - 1)(X^8 + 1),  X^8 - 1 = (X^4 - 1)(X^4 + 1):
+// u = x_lo + x_hi, v = x_lo - x_hi; 2 y_lo = P + N, 2 y_hi = P - N with P = cu (*) u cyclic, N = cv (*) v negacyclic,
+// once more on P, and the halvings dropped: 96 DFMA + 48 DADD instead of 256 DFMA.
 template <int N_OUT>
 LM_HD void p1_mds_redc(const uint32_t a3[16], const uint32_t* init, const double* init_d, uint32_t out[16]) {
 #ifdef __CUDA_ARCH__
   (void)init;
   constexpr double TWO52 = 4503599627370496.0;
-  double d[16];
+  // c = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1}
+  // level 1: cu[k] = c[k] + c[k+8], cv[k] = 2 (c[k] - c[k+8])  (doubled: P below carries a factor 2)
+  constexpr double CV[8] = {-200, 4, 22, 10, 112, 2, -72, 124};
+  // level 2 on cu = {102, 4, 15, 39, 78, 3, 66, 64}: cuu[k] = cu[k] + cu[k+4], cuv[k] = cu[k] - cu[k+4]
+  constexpr double CUU[4] = {180, 7, 81, 103};
+  constexpr double CUV[4] = {24, 1, -51, -25};
+  double x[16];
 #pragma unroll
-  for (int j = 0; j < 16; j++) d[j] = __hiloint2double(0x43300000, (int)a3[j]) - TWO52;
+  for (int j = 0; j < 16; j++) x[j] = __hiloint2double(0x43300000, (int)a3[j]) - TWO52;
+  double u[8], v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) u[k] = x[k] + x[k + 8], v[k] = x[k] - x[k + 8];
+  // N = cv (*) v negacyclic of length 8
+  double n[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int k = (i - j) & 7;
+      acc = fma(j <= i ? CV[k] : -CV[k], v[j], acc);
+    }
+    n[i] = acc;
+  }
+  // 2 P = (cuu (*) uu cyclic4) +- (cuv (*) uv negacyclic4)
+  double uu[4], uv[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) uu[k] = u[k] + u[k + 4], uv[k] = u[k] - u[k + 4];
+  double pp[4], pn[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int k = (i - j) & 3;
+      a = fma(CUU[k], uu[j], a);
+      b = fma(j <= i ? CUV[k] : -CUV[k], uv[j], b);
+    }
+    pp[i] = a;
+    pn[i] = b;
+  }
+  double p2[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) p2[i] = pp[i] + pn[i], p2[i + 4] = pp[i] - pn[i];
 #pragma unroll
   for (int i = 0; i < N_OUT; i++) {
-    double y = init_d ? init_d[i] : 0.0;
-#pragma unroll
-    for (int j = 0; j < 16; j++) y = fma(c_kb.mds_d[(16 + i - j) & 15], d[j], y);
+    double y = i < 8 ? p2[i] + n[i] : p2[i - 8] - n[i - 8];  // 4 * (C x)_i, a non-negative integer < 2^43
+    if (init_d) y += init_d[i];
     y += TWO52;
     const uint32_t lo = (uint32_t)__double2loint(y);
     const uint32_t hi = (uint32_t)__double2hiint(y) - 0x43300000u;
@@ -73,10 +117,10 @@ LM_HD void p1_mds_redc(const uint32_t a3[16], const uint32_t* init, const double
   constexpr uint32_t C[16] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
 #pragma unroll
   for (int i = 0; i < N_OUT; i++) {
-    uint64_t acc = init ? (uint64_t)init[i] : 0ull;
+    uint64_t acc = 0;
 #pragma unroll
     for (int j = 0; j < 16; j++) acc += (uint64_t)C[(16 + i - j) & 15] * a3[j];
-    out[i] = kb_redc_lazy(acc);
+    out[i] = kb_redc_lazy(4 * acc + (init ? (uint64_t)init[i] : 0ull));
   }
 #endif
 }

@@ -63,8 +63,34 @@ def power(a, e: int):
     return r
 
 
+# X^(p i) for i = 1..4 (crates/backend/koala-bear/src/quintic_extension/mod.rs:19-48), canonical residues;
+# checked against exponentiation in tests/test_air_sumcheck.py::test_host_field_matches_oracle
+_FROBENIUS = (
+    (1576402667, 1173144480, 1567662457, 1206866823, 2428146),
+    (1680345488, 1381986, 615237464, 1380104858, 295431824),
+    (441230756, 323126830, 704986542, 1445620072, 503505220),
+    (1364444097, 1144738982, 2008416047, 143367062, 1027410849),
+)
+
+
+def frobenius(a):
+    """a -> a^p: sum_i a_i (X^p)^i, a linear map with the matrix above"""
+    out = [a[0], 0, 0, 0, 0]
+    for i in range(1, 5):
+        if a[i]:
+            for k in range(5):
+                out[k] += a[i] * _FROBENIUS[i - 1][k]
+    return tuple(x % P for x in out)
+
+
 def inv(a):
-    return power(a, P ** 5 - 2)
+    """a^-1 = (a^p a^(p^2) a^(p^3) a^(p^4)) / Norm(a)   (quintic_extension/extension.rs:585-613)"""
+    f1 = frobenius(a)
+    f12 = frobenius(mul(a, f1))          # a^(p + p^2)
+    conj = mul(f12, frobenius(frobenius(f12)))  # a^(p + p^2 + p^3 + p^4)
+    norm = mul(a, conj)
+    assert norm[1:] == (0, 0, 0, 0) and norm[0], "inverse of zero"
+    return scal(conj, pow(norm[0], -1, P))
 
 
 def poly_eval(coeffs, x):

@@ -141,16 +141,25 @@ def rpow(x, e):
     return (x % P) * pow(R, e, P) % P
 
 
-# Exponent drift of the cheap full-round reduction (see poseidon1.cuh): a lane held as
-# v * R^e comes out of S-box + small-integer MDS + one Montgomery reduction as v' * R^(3e-3).
-E_FULL = [1, 0, -3, -12, -39]
+# Scale drift of the cheap full-round arithmetic (see poseidon1.cuh).  A lane is held as v * s for a known field
+# element s: the Montgomery cube maps s -> s^3 R^-2, the MDS is evaluated without the two halvings of its
+# even/odd (Karatsuba) splitting, s -> 4 s, and the single Montgomery reduction gives s -> s R^-1.  Every step is
+# homogeneous, so constants are simply pre-multiplied by the scale in force where they are added.
+MDS_GAIN = 4
+RINV = pow(R, -1, P)
+
+
+def full_round_scales(s):
+    """(scale at which the next round constant is added inside the MDS accumulator, scale after the reduction)"""
+    acc_scale = pow(s, 3, P) * RINV * RINV * MDS_GAIN % P
+    return acc_scale, acc_scale * RINV % P
 
 
 def restructure(c):
     """Tables for the CUDA kernel's formulation.
 
     Partial rounds are rewritten so that lanes 1..15 are never materialised per round:
-      x'      = state after the 4 initial full rounds + first_rc            (held at R^-39)
+      x'      = state after the 4 initial full rounds + first_rc            (held at scale s4)
       s0_0    = (m_i x')_0
       z_k     = s0_k^3                                                      (k = 0..19)
       s0_{r+1}= fr[r][0] z_r + D_r + sum_{k<r} g[r][k] z_k
@@ -161,32 +170,41 @@ def restructure(c):
     """
     rc, m_i, fr, v, sc = c["rc"], c["m_i"], c["first_row"], c["v"], c["scalar_rc"]
     sc = sc + [0]  # no constant after the last partial round
-    e4 = E_FULL[4]
     t = {}
-    t["RC0"] = [rpow(x, 1) for x in rc[0]]
+    t["RC0"] = [x * R % P for x in rc[0]]
     # constants folded into the MDS accumulators of initial rounds 0..2 (for rounds 1..3), then first_rc
-    t["RC_INIT"] = [[rpow(x, E_FULL[r] + 1) for x in rc[r]] for r in (1, 2, 3)]
-    t["RC_INIT"].append([rpow(x, e4 + 1) for x in c["first_rc"]])
+    s = R
+    t["RC_INIT"] = []
+    for r in range(4):
+        acc_scale, s = full_round_scales(s)
+        nxt = rc[r + 1] if r < 3 else c["first_rc"]
+        t["RC_INIT"].append([x * acc_scale % P for x in nxt])
+    s4 = s
+    lin = R * R % P * pow(s4, -1, P) % P  # constant factor that brings (held x') * const * R^-1 to Montgomery scale R
     # s0_0 and D_r as linear forms in x'
     g_rows = [m_i[0][:]]
     for r in range(RP):
         g_rows.append([sum(fr[r][i] * m_i[i][j] for i in range(1, W)) % P for j in range(W)])
-    t["G"] = [[rpow(x, 2 - e4) for x in row] for row in g_rows]           # 21 x 16
+    t["G"] = [[x * lin % P for x in row] for row in g_rows]           # 21 x 16
     gtri = [[sum(fr[r][i] * v[k][i - 1] for i in range(1, W)) % P for k in range(r)] for r in range(RP)]
     # constant part of s0_{r+1}: fr0_r sc_r + sum_{k<r} g[r][k] sc_k   (held at R^2 inside the accumulator)
     t["G_CONST"] = [0] + [rpow(fr[r][0] * sc[r] + sum(gtri[r][k] * sc[k] for k in range(r)), 2) for r in range(RP)]
     t["FR0"] = [rpow(fr[r][0], 1) for r in range(RP)]
     t["GTRI"] = [[rpow(x, 1) for x in row] + [0] * (RP - len(row)) for row in gtri]
     # final lanes 1..15: (m_i x')_i + sum_k v[k][i-1] (z_k + sc_k) + rc_terminal0[i]
-    t["MI"] = [[rpow(x, 2 - e4) for x in m_i[i]] for i in range(1, W)]      # 15 x 16
+    t["MI"] = [[x * lin % P for x in m_i[i]] for i in range(1, W)]      # 15 x 16
     t["V"] = [[rpow(v[k][i - 1], 1) for k in range(RP)] for i in range(1, W)]  # 15 x 20 (lane-major)
     rct = rc[RF_HALF + RP:]
     t["LANE_CONST"] = [rpow(sum(v[k][i - 1] * sc[k] for k in range(RP)) + rct[0][i], 2) for i in range(1, W)]
     # lane 0 after the last partial round also needs the first terminal round constant
     t["G_CONST"][RP] = (t["G_CONST"][RP] + rpow(rct[0][0], 2)) % P
-    t["RC_TERM"] = [[rpow(x, E_FULL[r] + 1) for x in rct[r]] for r in (1, 2, 3)]
-    t["FIX"] = rpow(1, 1 - e4)  # multiply (Montgomery) by this to bring R^-39 back to R^1... held*FIX*R^-1
-    t["FIX"] = rpow(1, 2 - e4)
+    s = R
+    t["RC_TERM"] = []
+    for r in range(4):
+        acc_scale, s = full_round_scales(s)
+        if r < 3:
+            t["RC_TERM"].append([x * acc_scale % P for x in rct[r + 1]])
+    t["FIX"] = R * R % P * pow(s, -1, P) % P  # held * FIX * R^-1 = v * R
     return t
 
 
@@ -200,7 +218,7 @@ def permute_restructured(state_monty, t):
         return redc(redc(a * a) * a)
 
     def mds_redc(a3, init):
-        return [redc(init[i] + sum(MDS_COL[(i - j) % W] * a3[j] for j in range(W))) for i in range(W)]
+        return [redc(init[i] + MDS_GAIN * sum(MDS_COL[(i - j) % W] * a3[j] for j in range(W))) for i in range(W)]
 
     zeros = [0] * W
     s = [(x + k) % P for x, k in zip(state_monty, t["RC0"])]
