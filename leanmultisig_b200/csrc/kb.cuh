@@ -99,14 +99,14 @@ LM_HD uint32_t kb_mul(uint32_t a, uint32_t b) { return kb_canon(kb_mul_lazy(a, b
 // value-preserving (mod p) shrink of a 64-bit accumulator to < 2^57:  hi * (2^32 mod p) + lo
 LM_HD uint64_t kb_fold(uint64_t acc) { return mad_wide((uint32_t)(acc >> 32), KB_R1, (uint64_t)(uint32_t)acc); }
 
-// Accumulator for sum_j a_j * c_j with a_j < p + 2^25, c_j < p.  Every product is < 2^62, so three of them
+// Accumulator for sum_j a_j * c_j with a_j < p + 2^9, c_j < p.  Every product is < 0.2462 * 2^64, so four of them
 // fit on top of a folded (< 2^57) accumulator; `mac<K>()` folds when the compile-time term index says so.
 struct KbDot {
   uint64_t acc;
   LM_HD explicit KbDot(uint64_t init = 0) : acc(init) {}
   template <int TERM_INDEX>
   LM_HD void mac(uint32_t a, uint32_t c) {
-    if (TERM_INDEX > 0 && TERM_INDEX % 3 == 0) acc = kb_fold(acc);
+    if (TERM_INDEX > 0 && TERM_INDEX % 4 == 0) acc = kb_fold(acc);
     acc = mad_wide(a, c, acc);
   }
   // sum * 2^-32 mod p in [0, p + 2^25)

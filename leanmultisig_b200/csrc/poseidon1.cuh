@@ -190,10 +190,10 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
     // s0_{r+1} = D_r + FR0[r] z_r + sum_{k<r} GTRI[r][k] z_k ;  D_r enters as D_r * 2^32 == D_r * R
     uint64_t acc = mul_wide(d[r], KB_R1);
     acc = mad_wide(z[r], T.FR0[r], acc);
-    int terms = 2;
+    int terms = 1;  // products on top of the (small) D_r term
 #pragma unroll
     for (int k = 0; k < r; k++) {
-      if (terms % 3 == 0) acc = kb_fold(acc);
+      if (terms % 4 == 0) acc = kb_fold(acc);
       acc = mad_wide(z[k], T.GTRI[r][k], acc);
       terms++;
     }
@@ -204,10 +204,10 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
 #pragma unroll
   for (int i = 0; i < 15; i++) {
     uint64_t acc = mul_wide(lane_lin[i], KB_R1);
-    int terms = 1;
+    int terms = 0;  // canonical z (< p) times constants (< p): four products per fold
 #pragma unroll
     for (int k = 0; k < 20; k++) {
-      if (terms % 3 == 0) acc = kb_fold(acc);
+      if (terms > 0 && terms % 4 == 0) acc = kb_fold(acc);
       acc = mad_wide(z[k], T.V[i][k], acc);
       terms++;
     }
