@@ -207,6 +207,17 @@ int lm_dev_fold_msb(lm_ctx* ctx, const uint32_t* d_in, uint64_t n_in, uint32_t e
 /* eval_eq_scaled (crates/backend/poly/src/eq_mle.rs:20-26): d_out = 2^k EF; point is a HOST pointer (k x 5) */
 int lm_dev_eq_table(lm_ctx* ctx, const uint32_t* point, uint32_t k, const uint32_t scalar[5], uint32_t* d_out);
 
+/* ---- Fiat-Shamir support ---------------------------------------------------------------------------------
+ * The transcript (Challenger / ProverState, crates/backend/fiat-shamir/src/{challenger,prover}.rs) stays on the
+ * reference side of the boundary; these two calls are the parts of it that are worth offloading or sharing. */
+/* ProverState::pow_grinding's search (fiat-shamir/src/prover.rs:135-167): `state` = the challenger's 16-word state
+ * (host), result = the SMALLEST canonical witness w such that lane 8 of permute(state[0..8] | w | 0^7), as a
+ * canonical integer, has `bits` low zero bits.  The caller observes the witness exactly as the reference does. */
+int lm_pow_grind(lm_ctx* ctx, const uint32_t state[16], uint32_t bits, uint64_t* witness);
+/* Poseidon1KoalaBear16::permute_mut on ONE state on the host (poseidon1_koalabear_16.rs:873): the duplex sponge
+ * of challenger.rs:32-36 is sequential, one permutation per observation, so it is not a device job. */
+int lm_host_poseidon1_permute(uint32_t state[16]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -291,6 +291,20 @@ int lm_dev_poseidon1(lm_ctx* c, uint32_t* d_states, uint64_t n, int compress) {
   return LM_OK;
 }
 
+int lm_pow_grind(lm_ctx* c, const uint32_t* state, uint32_t bits, uint64_t* witness) {
+  if (!c || !state || !witness) return fail(LM_ERR_INVALID, "lm_pow_grind: null argument");
+  if (bits > 30) return fail(LM_ERR_INVALID, "lm_pow_grind: bits %u > 30", bits);
+  CU(cudaSetDevice(c->device));
+  CU(lm::pow_grind(c->stream, state, bits, 0, reinterpret_cast<unsigned long long*>(c->d_small), witness));
+  return LM_OK;
+}
+
+int lm_host_poseidon1_permute(uint32_t* state) {
+  if (!state) return fail(LM_ERR_INVALID, "lm_host_poseidon1_permute: null state");
+  lm::poseidon1_permute_host(state);
+  return LM_OK;
+}
+
 int lm_dev_reorder_and_dft(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint32_t folding,
                            uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out) {
   if (!c) return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft: ctx is null");

@@ -303,4 +303,56 @@ cudaError_t poseidon1_states(cudaStream_t stream, uint32_t* d_states, uint64_t n
   return cudaGetLastError();
 }
 
+// Fiat-Shamir proof-of-work search (reference: ProverState::pow_grinding, fiat-shamir/src/prover.rs:135-167):
+// witness w (canonical, < p) is accepted when lane 8 of permute(capacity | w | 0^7), read as a canonical integer,
+// has its low `bits` bits clear.  One candidate per thread; the smallest hit of the batch wins (atomicMin), so the
+// search is deterministic where the reference's rayon find_any is not.
+__global__ void __launch_bounds__(128) pow_grind_kernel(State16 base, uint64_t start, uint64_t n, uint32_t mask,
+                                                        unsigned long long* best) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t w = start + i;
+  uint32_t s[16];
+#pragma unroll
+  for (int k = 0; k < 8; k++) s[k] = base.v[k];
+  s[8] = kb_mul((uint32_t)w, KB_R2);
+#pragma unroll
+  for (int k = 9; k < 16; k++) s[k] = 0;
+  p1_permute<9>(s, c_p1);
+  const uint32_t canon = kb_canon(kb_redc_lazy((uint64_t)s[8]));
+  if ((canon & mask) == 0) atomicMin(best, (unsigned long long)w);
+}
+
+cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bits, uint64_t start,
+                      unsigned long long* d_best, uint64_t* witness) {
+  if (bits >= 31) return cudaErrorInvalidValue;
+  State16 base;
+  for (int i = 0; i < 16; i++) base.v[i] = state[i];
+  const uint32_t mask = (1u << bits) - 1u;
+  // expected 2^bits candidates: one launch of 4 * 2^bits (at least 2^16) finds a witness with probability 1 - e^-4
+  uint64_t batch = (uint64_t)4 << bits;
+  if (batch < (1u << 16)) batch = 1u << 16;
+  if (batch > (1u << 24)) batch = 1u << 24;
+  const unsigned long long none = ~0ull;
+  for (uint64_t at = start; at < KB_P; at += batch) {
+    const uint64_t n = at + batch <= KB_P ? batch : KB_P - at;
+    cudaError_t e = cudaMemcpyAsync(d_best, &none, sizeof(none), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    pow_grind_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(base, at, n, mask, d_best); count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    unsigned long long got = none;
+    if ((e = cudaMemcpyAsync(&got, d_best, sizeof(got), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    if (got != none) {
+      *witness = got;
+      return cudaSuccess;
+    }
+  }
+  return cudaErrorNotReady;  // no witness below p (probability ~ e^(-p / 2^bits))
+}
+
+// The transcript sponge itself (challenger.rs:8-76) is one permutation per 8 absorbed words, strictly sequential:
+// it stays on the host, evaluated with the same arithmetic header as the device code.
+void poseidon1_permute_host(uint32_t state[16]) { p1_permute<16>(state, h_p1); }
+
 }  // namespace lm

@@ -19,4 +19,9 @@ cudaError_t merkle_open_gather(cudaStream_t stream, const uint32_t* d_mat, const
                                uint32_t* d_rows, uint32_t* d_paths);
 // n explicit 16-word states: permutation (compress = 0) or permutation + feed-forward (compress = 1)
 cudaError_t poseidon1_states(cudaStream_t stream, uint32_t* d_states, uint64_t n, int compress);
+// smallest w >= start whose PoW check passes for the challenger state `state` (host, 16 words); d_best: device u64
+cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bits, uint64_t start,
+                      unsigned long long* d_best, uint64_t* witness);
+// one Poseidon1 permutation on the host (Fiat-Shamir transcript sponge)
+void poseidon1_permute_host(uint32_t state[16]);
 }  // namespace lm

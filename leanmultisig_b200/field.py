@@ -118,3 +118,46 @@ def lagrange_interpolation_at_integers(values):
         for k in range(n):
             coeffs[k] = add(coeffs[k], scal(v, num[k] * dinv % P))
     return coeffs
+
+
+def two_adic_generator(bits: int) -> int:
+    """canonical generator of the 2^bits-th roots of unity: successive squares of the order-2^24 generator
+    (crates/backend/koala-bear/src/koala_bear.rs, TWO_ADIC_GENERATORS)"""
+    assert 0 <= bits <= 24
+    return pow(0x6AC49F88, 1 << (24 - bits), P)
+
+
+# ---- numpy batches of canonical EF values (arrays [..., 5] of uint64) ----------------------------------------
+def np_from_monty(words) -> np.ndarray:
+    return (np.asarray(words, dtype=np.uint64) * np.uint64(_RINV)) % np.uint64(P)
+
+
+def np_to_monty(canon) -> np.ndarray:
+    return ((np.asarray(canon, dtype=np.uint64) * np.uint64(_R)) % np.uint64(P)).astype(np.uint32)
+
+
+def np_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """elementwise product of EF arrays (broadcasting over the leading axes)"""
+    p = np.uint64(P)
+    d = [None] * 9
+    for i in range(5):
+        for j in range(5):
+            t = (a[..., i] * b[..., j]) % p
+            d[i + j] = t if d[i + j] is None else d[i + j] + t
+    pp = np.uint64(2 * P)
+    out = np.stack([d[0] + d[5] + (pp - d[8] % p), d[1] + d[6], d[2] + d[7] + d[8] + (pp - d[5] % p),
+                    d[3] + d[8] + (pp - d[6] % p), d[4] + (pp - d[7] % p)], axis=-1)
+    return out % p
+
+
+def np_mle_eval_rows(rows: np.ndarray, point) -> np.ndarray:
+    """rows: [n, 2^k, 5] canonical; point: k canonical EF tuples, first coordinate = most significant index bit
+    (MleRef::evaluate on each row, crates/backend/poly/src/evals.rs:142)"""
+    p = np.uint64(P)
+    cur = rows
+    for x in point:
+        h = cur.shape[1] // 2
+        lo, hi = cur[:, :h], cur[:, h:]
+        xv = np.array(x, dtype=np.uint64).reshape(1, 1, 5)
+        cur = (lo + np_mul(hi + (p - lo), xv)) % p
+    return cur[:, 0]

@@ -292,3 +292,210 @@ class Context:
         out = d_out.download((1 << k, 5))
         d_out.free()
         return out
+
+
+# ======================================================================================================
+# WhirConfig::commit / WhirConfig::prove on the device sessions above
+# ======================================================================================================
+class SparseStatement:
+    """crates/whir/src/lib.rs:31-95.  point: m x 5 words over the low (inner) variables; values: [(selector, 5 words)]:
+    the claim is  poly(selector bits | point) = value  (or, with is_next, the next_mle-shifted claim)."""
+
+    def __init__(self, total_num_variables: int, point, values, is_next: bool = False):
+        self.total_num_variables = total_num_variables
+        self.point = _u32(point).reshape(-1, 5)
+        self.values = [(int(s), _u32(v).reshape(5)) for s, v in values]
+        self.is_next = is_next
+        assert self.point.shape[0] <= total_num_variables
+
+    @staticmethod
+    def dense(point, value) -> "SparseStatement":
+        pt = _u32(point).reshape(-1, 5)
+        return SparseStatement(pt.shape[0], pt, [(0, value)])
+
+
+class Witness:
+    """crates/whir/src/commit.rs:49-57: prover data + the out-of-domain samples taken at commit time"""
+
+    def __init__(self, tree: Tree, ood_points, ood_answers):
+        self.tree, self.ood_points, self.ood_answers = tree, ood_points, ood_answers
+
+    def free(self):
+        self.tree.free()
+
+
+def _expand_from_univariate(y, n: int):
+    """MultilinearPoint::expand_from_univariate (crates/backend/poly/src/point.rs): y, y^2, y^4, ... (canonical)"""
+    from . import field as F
+
+    out, cur = [], y
+    for _ in range(n):
+        out.append(cur)
+        cur = F.mul(cur, cur)
+    return out
+
+
+def _points_to_monty(pts) -> np.ndarray:
+    from . import field as F
+
+    return np.stack([F.to_monty(x) for x in pts]) if len(pts) else np.zeros((0, 5), dtype=np.uint32)
+
+
+def _sample_ood(prover_state, n_samples: int, n_vars: int, evaluate):
+    """sample_ood_points (crates/whir/src/utils.rs:30-57)"""
+    from . import field as F
+
+    pts, answers = [], []
+    if n_samples:
+        pts = [F.from_monty(x) for x in prover_state.sample_vec(n_samples)]
+        answers = [_u32(evaluate(_points_to_monty(_expand_from_univariate(y, n_vars)))) for y in pts]
+        prover_state.add_extension_scalars(np.concatenate(answers))
+    return pts, answers
+
+
+def evals_to_coeffs(evals: np.ndarray) -> np.ndarray:
+    """crates/backend/poly/src/evals.rs:44-56 on the (at most 2^max_num_variables_to_send_coeffs) final values"""
+    from . import field as F
+
+    d = F.np_from_monty(_u32(evals).reshape(-1, 5))
+    n = d.shape[0]
+    p = np.uint64(F.P)
+    half = 1
+    while half < n:
+        v = d.reshape(n // (2 * half), 2, half, 5)
+        v[:, 1] = (v[:, 1] + (p - v[:, 0])) % p
+        half *= 2
+    log_n = n.bit_length() - 1
+    rev = [int(format(i, f"0{log_n}b")[::-1], 2) if log_n else 0 for i in range(n)]
+    return F.np_to_monty(d[rev])
+
+
+class WhirProver:
+    """`WhirConfig::commit` (commit.rs:64-99) and `WhirConfig::prove` (open.rs:37-248) with every table on the GPU.
+
+    cfg: a whir_config.WhirConfig (or the reference's, through a binding exposing the same fields);
+    prover_state: anything with the FSProver surface of fiat_shamir.ProverState."""
+
+    def __init__(self, ctx: Context, cfg):
+        self.ctx, self.cfg = ctx, cfg
+
+    def commit(self, prover_state, polynomial, actual_len: int | None = None) -> Witness:
+        cfg = self.cfg
+        tree = self.ctx.commit(polynomial, cfg.num_variables, cfg.first_folding, cfg.starting_log_inv_rate, actual_len)
+        prover_state.add_base_scalars(tree.root)
+        pts, answers = _sample_ood(prover_state, cfg.commitment_ood_samples, cfg.num_variables, tree.evaluate)
+        return Witness(tree, pts, answers)
+
+    # -- sumcheck_prove_many_rounds with the product-sumcheck kernels (sumcheck/src/prove.rs:86-151) ------
+    @staticmethod
+    def _rounds(sc: ProductSumcheck, prover_state, n_rounds: int, pow_bits: int, total):
+        from . import field as F
+
+        chals, pending = [], None
+        for _ in range(n_rounds):
+            c0, c2 = sc.round() if pending is None else sc.fold_round(pending)
+            c0c, c2c = F.from_monty(c0), F.from_monty(c2)
+            c1c = F.sub(F.sub(total, F.add(c0c, c0c)), c2c)
+            prover_state.add_sumcheck_polynomial(np.stack([c0, F.to_monty(c1c), c2]))
+            prover_state.pow_grinding(pow_bits)
+            pending = prover_state.sample()
+            r = F.from_monty(pending)
+            total = F.add(c0c, F.mul(r, F.add(c1c, F.mul(r, c2c))))
+            chals.append(r)
+        if pending is not None:
+            sc.fold(pending)
+        return chals, total
+
+    def prove(self, prover_state, statements, witness: Witness):
+        from . import field as F
+        from .whir_config import two_adic_generator
+
+        cfg, ps = self.cfg, prover_state
+        nv = cfg.num_variables
+        for s in statements:
+            assert s.total_num_variables == nv
+        # combine_statement (open.rs:518-584): OOD constraints first, then the caller's
+        stm = [SparseStatement.dense(_points_to_monty(_expand_from_univariate(y, nv)), a)
+               for y, a in zip(witness.ood_points, witness.ood_answers)] + list(statements)
+        ps.duplex()
+        gamma = F.from_monty(ps.sample())
+        sc = self.ctx.sumcheck_from_tree(witness.tree)
+        total, gp = F.ZERO, F.ONE
+        for smt in stm:
+            for sel, val in smt.values:
+                (sc.add_next if smt.is_next else sc.add_eq)(sel, smt.point, F.to_monty(gp))
+                total = F.add(total, F.mul(F.from_monty(val), gp))
+                gp = F.mul(gp, gamma)
+        randomness, total = self._rounds(sc, ps, cfg.first_folding, cfg.starting_folding_pow_bits, total)
+
+        trees = []
+        tree = witness.tree
+        domain_size = cfg.starting_domain_size()
+        gen = two_adic_generator(domain_size.bit_length() - 1 - cfg.first_folding)
+        for round_index in range(cfg.n_rounds + 1):
+            num_variables = nv - cfg.total_folding(round_index)
+            ff = cfg.folding_at(round_index)
+            log_folded = (domain_size >> ff).bit_length() - 1
+            if round_index == cfg.n_rounds:  # final_round (open.rs:251-321)
+                poly, _ = sc.read()
+                ps.add_extension_scalars(evals_to_coeffs(poly).reshape(-1))
+                ps.pow_grinding(cfg.final_query_pow_bits)
+                idx = ps.sample_in_range(log_folded, cfg.final_queries)
+                rows, paths = tree.open(idx)
+                ps.hint_merkle_paths([(rows[q], paths[q], i) for q, i in enumerate(idx)])
+                if cfg.final_sumcheck_rounds:
+                    r, total = self._rounds(sc, ps, cfg.final_sumcheck_rounds, 0, total)
+                    randomness += r
+                break
+            rp = cfg.round_parameters[round_index]
+            ff_next = cfg.folding_at(round_index + 1)
+            new_domain_size = domain_size >> cfg.rs_reduction_factor(round_index)
+            log_inv_rate = (new_domain_size >> num_variables).bit_length() - 1
+            new_tree = sc.commit_poly(ff_next, log_inv_rate)
+            trees.append(new_tree)
+            ps.add_base_scalars(new_tree.root)
+            ood_points, ood_answers = _sample_ood(ps, rp.ood_samples, num_variables, sc.eval_poly)
+            ps.pow_grinding(rp.query_pow_bits)
+            idx = ps.sample_in_range(log_folded, rp.num_queries)
+            rows, paths = tree.open(idx)
+            ps.hint_merkle_paths([(rows[q], paths[q], i) for q, i in enumerate(idx)])
+            # STIR answers: each opened leaf folded at this round's challenges (open.rs:161-190)
+            dim = tree.elem_dim
+            leaves = F.np_from_monty(rows)
+            if dim == 5:
+                leaves = leaves.reshape(len(idx), 1 << ff, 5)
+            else:
+                z = np.zeros((len(idx), 1 << ff, 5), dtype=np.uint64)
+                z[:, :, 0] = leaves
+                leaves = z
+            stir_evals = F.np_mle_eval_rows(leaves, randomness[len(randomness) - ff:])
+            # in-domain points gen^i expanded to (x, x^2, x^4, ...), base field
+            g = gen * F._RINV % F.P
+            stir_pts = np.empty((len(idx), num_variables), dtype=np.uint32)
+            for q, i in enumerate(idx):
+                y = pow(g, i, F.P)
+                for k in range(num_variables):
+                    stir_pts[q, k] = y * F._R % F.P
+                    y = y * y % F.P
+            ps.duplex()
+            comb = F.from_monty(ps.sample())
+            powers = [F.ONE]
+            for _ in range(len(ood_points) + len(idx)):
+                powers.append(F.mul(powers[-1], comb))
+            for k, (y, ans) in enumerate(zip(ood_points, ood_answers)):
+                sc.add_eq(0, _points_to_monty(_expand_from_univariate(y, num_variables)), F.to_monty(powers[k]))
+                total = F.add(total, F.mul(powers[k], F.from_monty(ans)))
+            stir_rand = powers[len(ood_points):len(ood_points) + len(idx)]
+            if len(idx):
+                sc.add_base_eq(stir_pts, _points_to_monty(stir_rand))
+            for rnd, ev in zip(stir_rand, stir_evals):
+                total = F.add(total, F.mul(rnd, tuple(int(x) for x in ev)))
+            r, total = self._rounds(sc, ps, ff_next, rp.folding_pow_bits, total)
+            randomness += r
+            domain_size = new_domain_size
+            gen = two_adic_generator(new_domain_size.bit_length() - 1 - ff_next)
+            tree = new_tree
+        sc.free()
+        for t in trees:
+            t.free()
+        return randomness
