@@ -128,11 +128,18 @@ int lm_sc_free(lm_sumcheck* sc);
  * trait OuterSumcheckSession (air_sumcheck.rs:34-42) that prove_batched_air_sumcheck (air_sumcheck.rs:636-681)
  * drives.  A Rust struct implementing the trait forwards compute_bare_round_poly -> lm_air_round (+ the p(1) /
  * Lagrange step it already does on a handful of values), process_challenge -> lm_air_fold,
- * final_column_evals -> lm_air_final.  table_id: 0 = execution table (crates/lean_vm/src/tables/execution/air.rs).
+ * final_column_evals -> lm_air_final.  table_id: 0 = execution table (crates/lean_vm/src/tables/execution/air.rs:42-130,
+ * 20 columns), 1 = extension_op (tables/extension_op/air.rs:44-163, 29 columns), 2 = poseidon16
+ * (tables/poseidon_16/mod.rs:294-548, 109 columns); table_id | LM_AIR_NO_BUS selects the BUS = false instantiation of
+ * tables 1 and 2 (no bus constraint: logup_alphas_eq may be NULL with n_la = 0, bus_beta is ignored).
  * cols: n_cols host pointers to base-field columns of 2^log_rows entries in natural row order (the shifted
  * columns are derived on the device).  eq_factor: log_rows x 5; the LAST entry belongs to the variable bound
  * first.  alpha_powers: n_alpha x 5 (ExtraDataForBuses::alpha_powers), logup_alphas_eq: n_la x 5, bus_beta: 5. */
 typedef struct lm_air lm_air;
+#define LM_AIR_EXECUTION 0u
+#define LM_AIR_EXTENSION_OP 1u
+#define LM_AIR_POSEIDON16 2u
+#define LM_AIR_NO_BUS 0x100u
 int lm_air_new(lm_ctx* ctx, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
                const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
                const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5], lm_air** out);
@@ -145,6 +152,10 @@ int lm_air_fold(lm_air* air, const uint32_t r[5]);
 /* after the last fold: the (n_cols + n_shift) column evaluations, 5 words each (air_sumcheck.rs:289-291) */
 int lm_air_final(lm_air* air, uint32_t* out);
 int lm_air_free(lm_air* air);
+/* fill_trace_poseidon_16 (crates/lean_vm/src/tables/poseidon_16/trace_gen.rs:10-165): cols = the 109 host columns of
+ * the poseidon16 table, n_rows entries each; reads flag_permute (column 8) and the 16 inputs (columns 9..24), writes
+ * columns 25..108 (two post-full-round states, 20 partial-round S-box outputs, one more state, the 16 outputs). */
+int lm_poseidon16_fill_trace(lm_ctx* ctx, uint32_t* const* cols, uint64_t n_rows);
 
 /* ---- Logup: fingerprints + quotient GKR -----------------------------------------------------------------
  * lm_finger_print replaces finger_print(_packed) (crates/utils/src/multilinear.rs:76-98): out[r] = c - sum_i
@@ -204,6 +215,8 @@ int lm_dev_mle_eval(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint3
 /* fold_multilinear (crates/backend/poly/src/utils.rs:161-186): d_out = n_in/2 EF */
 int lm_dev_fold_msb(lm_ctx* ctx, const uint32_t* d_in, uint64_t n_in, uint32_t elem_dim, const uint32_t r[5],
                     uint32_t* d_out);
+/* fill_trace_poseidon_16 on a device-resident column-major table (109 x n_rows words) */
+int lm_dev_poseidon16_fill_trace(lm_ctx* ctx, uint32_t* d_cols, uint64_t n_rows);
 /* eval_eq_scaled (crates/backend/poly/src/eq_mle.rs:20-26): d_out = 2^k EF; point is a HOST pointer (k x 5) */
 int lm_dev_eq_table(lm_ctx* ctx, const uint32_t* point, uint32_t k, const uint32_t scalar[5], uint32_t* d_out);
 

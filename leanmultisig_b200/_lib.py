@@ -113,6 +113,8 @@ def lib() -> C.CDLL:
             "lm_dev_fold_msb": [vp, vp, u64, u32, u32p, vp],
             "lm_dev_eq_table": [vp, u32p, u32, u32p, vp],
             "lm_pow_grind": [vp, u32p, u32, u64p],
+            "lm_poseidon16_fill_trace": [vp, C.POINTER(vp), u64],
+            "lm_dev_poseidon16_fill_trace": [vp, vp, u64],
             "lm_host_poseidon1_permute": [u32p],
         }
         for name, args in sig.items():

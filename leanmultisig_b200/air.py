@@ -138,3 +138,14 @@ def prove_batched_air_sumcheck(sessions, eta, absorb_and_sample):
             elif bare_polys[idx] is not None:
                 s.process_challenge(ch, bare_polys[idx])
     return challenges
+
+
+def fill_trace_poseidon_16(ctx, trace) -> None:
+    """fill_trace_poseidon_16 (crates/lean_vm/src/tables/poseidon_16/trace_gen.rs:10-43): `trace` is the list of the 109
+    base-field columns (numpy uint32, equal length); columns 25.. are overwritten in place from flag_permute and the inputs."""
+    assert len(trace) == 109
+    n = trace[0].size
+    for c in trace:
+        assert c.dtype == np.uint32 and c.size == n and c.flags["C_CONTIGUOUS"] and c.flags["WRITEABLE"]
+    ptrs = (C.c_void_p * 109)(*[c.ctypes.data for c in trace])
+    check(lib().lm_poseidon16_fill_trace(ctx.handle, ptrs, n))

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "air.h"
+#include "air_values.cuh"
 #include "kb.cuh"
 #include "launch_count.h"
 #include "poly.h"
@@ -26,54 +27,6 @@
 namespace lm {
 
 constexpr int EXEC_COLS = 20, EXEC_SHIFT = 2, EXEC_ALL = 22, EXEC_DEG = 5;
-constexpr int AIR_LO = 10;
-
-struct AirExtra {
-  Ef alpha[16];  // alpha powers, first 13 used
-  Ef la[8];      // logup_alphas_eq_poly (first 4 + last are used by the bus column)
-  Ef la_last;
-  Ef beta;
-};
-
-// ---- value types the constraint code is generic over ------------------------------------------------------
-struct Fb {
-  uint32_t v;
-};
-__device__ __forceinline__ Fb operator+(Fb a, Fb b) { return Fb{kb_add(a.v, b.v)}; }
-__device__ __forceinline__ Fb operator-(Fb a, Fb b) { return Fb{kb_sub(a.v, b.v)}; }
-__device__ __forceinline__ Fb operator*(Fb a, Fb b) { return Fb{kb_mul(a.v, b.v)}; }
-__device__ __forceinline__ Fb operator-(Fb a) { return Fb{kb_neg(a.v)}; }
-__device__ __forceinline__ Ef operator+(const Ef& a, const Ef& b) { return ef_add(a, b); }
-__device__ __forceinline__ Ef operator-(const Ef& a, const Ef& b) { return ef_sub(a, b); }
-__device__ __forceinline__ Ef operator*(const Ef& a, const Ef& b) { return ef_mul(a, b); }
-__device__ __forceinline__ Ef operator-(const Ef& a) {
-  Ef r;
-#pragma unroll
-  for (int i = 0; i < 5; i++) r.c[i] = kb_neg(a.c[i]);
-  return r;
-}
-// constants and scalings
-__device__ __forceinline__ Fb add_one(Fb a) { return Fb{kb_add(a.v, KB_R1)}; }
-__device__ __forceinline__ Fb sub_one(Fb a) { return Fb{kb_sub(a.v, KB_R1)}; }
-__device__ __forceinline__ Ef add_one(Ef a) { return ef_add_base(a, KB_R1); }
-__device__ __forceinline__ Ef sub_one(Ef a) {
-  a.c[0] = kb_sub(a.c[0], KB_R1);
-  return a;
-}
-__device__ __forceinline__ Fb dbl(Fb a) { return a + a; }
-__device__ __forceinline__ Ef dbl(const Ef& a) { return ef_add(a, a); }
-__device__ __forceinline__ uint32_t kb_halve(uint32_t a) { return (a & 1) ? (a >> 1) + ((KB_P + 1) >> 1) : (a >> 1); }
-__device__ __forceinline__ Fb halve(Fb a) { return Fb{kb_halve(a.v)}; }
-__device__ __forceinline__ Ef halve(Ef a) {
-#pragma unroll
-  for (int i = 0; i < 5; i++) a.c[i] = kb_halve(a.c[i]);
-  return a;
-}
-// EF scalar times value
-__device__ __forceinline__ Ef scale(const Ef& s, Fb x) { return ef_mul_base(s, x.v); }
-__device__ __forceinline__ Ef scale(const Ef& s, const Ef& x) { return ef_mul(s, x); }
-__device__ __forceinline__ Ef add_val(const Ef& e, Fb x) { return ef_add_base(e, x.v); }
-__device__ __forceinline__ Ef add_val(const Ef& e, const Ef& x) { return ef_add(e, x); }
 
 // sum_k alpha^k * constraint_k(point), point = 20 flat + 2 shift values (execution/air.rs:56-130)
 template <class T>
@@ -267,7 +220,8 @@ cudaError_t air_shift_column(cudaStream_t stream, const uint32_t* d_col, uint64_
 size_t air_round_scratch_words(uint32_t log_n) {
   const uint32_t lv = log_n ? log_n - 1 : 0;
   const int lo = lv < (uint32_t)AIR_LO ? (int)lv : AIR_LO;
-  return 5 * (((size_t)1 << (lv - lo)) + ((size_t)1 << lo)) + (size_t)(148 * 8) * EXEC_DEG * 5 + 64;
+  // partial sums: 148 * 8 CTAs x 5 values (execution table) or 148 * 4 CTAs x 10 values (air_generic.cu)
+  return 5 * (((size_t)1 << (lv - lo)) + ((size_t)1 << lo)) + (size_t)(148 * 8) * 10 * 5 + 64;
 }
 
 cudaError_t air_exec_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t dim, uint32_t log_n, const uint32_t* d_eq_point,

@@ -15,4 +15,12 @@ cudaError_t air_exec_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t
 // fold the least-significant variable of n_cols SoA columns (n rows -> n/2 EF rows); d_out must not alias d_in
 cudaError_t air_fold_lsb(cudaStream_t stream, const uint32_t* d_in, uint32_t dim, uint64_t n, uint32_t n_cols, const uint32_t r[5],
                          uint32_t* d_out);
+// ---- air_generic.cu: extension_op (table 1) and poseidon16 (table 2); table | 0x100 = BUS = false instantiation ----
+bool air_table_shape(uint32_t table, uint32_t* n_cols, uint32_t* n_shift, uint32_t* degree, uint32_t* max_constraints);
+// d_out[degree x 5] = evaluations at z = 0, 2, .., degree over (n_cols + n_shift) SoA columns of 2^log_n rows
+cudaError_t air_generic_round(cudaStream_t stream, uint32_t table, const uint32_t* d_cols, uint32_t dim, uint32_t log_n,
+                              const uint32_t* d_eq_point, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* la,
+                              uint32_t n_la, const uint32_t beta[5], uint32_t* d_scratch, uint32_t* d_out);
+// columns 25..109 of the poseidon16 table from its flag_permute and input columns (column-major, n rows each)
+cudaError_t poseidon16_fill_trace(cudaStream_t stream, uint32_t* d_cols, uint64_t n);
 }  // namespace lm

@@ -879,22 +879,28 @@ int lm_air_free(lm_air* a) {
 int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
                const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* logup_alphas_eq,
                uint32_t n_la, const uint32_t bus_beta[5], lm_air** out) {
-  if (!c || !cols || !eq_factor || !alpha_powers || !logup_alphas_eq || !bus_beta || !out)
+  if (!c || !cols || !eq_factor || !alpha_powers || !bus_beta || !out || (!logup_alphas_eq && n_la))
     return fail(LM_ERR_INVALID, "lm_air_new: null argument");
   *out = nullptr;
-  if (table_id != 0) return fail(LM_ERR_INVALID, "lm_air_new: only the execution table (id 0) is implemented");
-  if (n_cols != 20) return fail(LM_ERR_INVALID, "lm_air_new: the execution table has 20 columns, got %u", n_cols);
-  if (n_alpha < 13) return fail(LM_ERR_INVALID, "lm_air_new: need >= 13 alpha powers, got %u", n_alpha);
-  if (n_la < 5) return fail(LM_ERR_INVALID, "lm_air_new: need >= 5 logup alphas, got %u", n_la);
+  uint32_t t_cols, t_shift, t_deg, t_maxc;
+  if (!lm::air_table_shape(table_id, &t_cols, &t_shift, &t_deg, &t_maxc) || (table_id & ~0x1ffu) ||
+      ((table_id & 0x100u) && (table_id & 0xffu) == 0))
+    return fail(LM_ERR_INVALID, "lm_air_new: unknown table id 0x%x (0 execution, 1 extension_op, 2 poseidon16, | 0x100 no bus)",
+                table_id);
+  const bool bus = !(table_id & 0x100u);
+  if (n_cols != t_cols) return fail(LM_ERR_INVALID, "lm_air_new: table %u has %u columns, got %u", table_id & 0xffu, t_cols, n_cols);
+  if (n_alpha < t_maxc - (bus ? 0 : 1))
+    return fail(LM_ERR_INVALID, "lm_air_new: need >= %u alpha powers, got %u", t_maxc - (bus ? 0 : 1), n_alpha);
+  if (bus && n_la < 5) return fail(LM_ERR_INVALID, "lm_air_new: need >= 5 logup alphas, got %u", n_la);
   if (log_rows < 1 || log_rows > 30) return fail(LM_ERR_INVALID, "lm_air_new: log_rows %u out of range", log_rows);
   CU(cudaSetDevice(c->device));
   lm_air* a = new (std::nothrow) lm_air();
   if (!a) return fail(LM_ERR_OOM, "lm_air_new: host allocation failed");
   a->ctx = c;
   a->table_id = table_id;
-  a->n_cols = 20;
-  a->n_shift = 2;
-  a->degree = 5;
+  a->n_cols = t_cols;
+  a->n_shift = t_shift;
+  a->degree = t_deg;
   a->log_n = log_rows;
   a->alpha.assign(alpha_powers, alpha_powers + 5 * (size_t)n_alpha);
   a->la.assign(logup_alphas_eq, logup_alphas_eq + 5 * (size_t)n_la);
@@ -927,6 +933,34 @@ int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32
   return LM_OK;
 }
 
+int lm_dev_poseidon16_fill_trace(lm_ctx* c, uint32_t* d_cols, uint64_t n_rows) {
+  if (!c || !d_cols) return fail(LM_ERR_INVALID, "lm_dev_poseidon16_fill_trace: null argument");
+  CU(cudaSetDevice(c->device));
+  CU(lm::poseidon16_fill_trace(c->stream, d_cols, n_rows));
+  return LM_OK;
+}
+
+int lm_poseidon16_fill_trace(lm_ctx* c, uint32_t* const* cols, uint64_t n_rows) {
+  if (!c || !cols) return fail(LM_ERR_INVALID, "lm_poseidon16_fill_trace: null argument");
+  for (int k = 0; k < 109; k++)
+    if (!cols[k]) return fail(LM_ERR_INVALID, "lm_poseidon16_fill_trace: column %d is null", k);
+  if (n_rows == 0) return LM_OK;
+  CU(cudaSetDevice(c->device));
+  uint32_t* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)109 * n_rows * sizeof(uint32_t)));
+  cudaError_t e = cudaSuccess;
+  // inputs: flag_permute (column 8) and the 16 input lanes (columns 9..24)
+  for (int k = 8; e == cudaSuccess && k < 25; k++)
+    e = cudaMemcpyAsync(d + (size_t)k * n_rows, cols[k], n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = lm::poseidon16_fill_trace(c->stream, d, n_rows);
+  for (int k = 25; e == cudaSuccess && k < 109; k++)
+    e = cudaMemcpyAsync(cols[k], d + (size_t)k * n_rows, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_poseidon16_fill_trace");
+  return LM_OK;
+}
+
 int lm_air_info(const lm_air* a, uint32_t* n_vars, uint32_t* degree, uint32_t* n_cols_total) {
   if (!a) return fail(LM_ERR_INVALID, "lm_air_info: null argument");
   if (n_vars) *n_vars = a->log_n;
@@ -940,8 +974,13 @@ int lm_air_round(lm_air* a, uint32_t* out_evals) {
   if (a->log_n < 1) return fail(LM_ERR_INVALID, "lm_air_round: no variables left");
   lm_ctx* c = a->ctx;
   CU(cudaSetDevice(c->device));
-  CU(lm::air_exec_round(c->stream, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(), a->la.data(),
-                        (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch, a->d_out));
+  if (a->table_id == 0)
+    CU(lm::air_exec_round(c->stream, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(), a->la.data(),
+                          (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch, a->d_out));
+  else
+    CU(lm::air_generic_round(c->stream, a->table_id, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(),
+                             (uint32_t)(a->alpha.size() / 5), a->la.data(), (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch,
+                             a->d_out));
   CU(cudaMemcpyAsync(out_evals, a->d_out, (size_t)a->degree * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return LM_OK;

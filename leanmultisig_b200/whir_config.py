@@ -167,6 +167,7 @@ class WhirConfig:
         return self.num_variables - self.total_folding(self.n_rounds)
 
     def final_round_config(self):
+        assert self.round_parameters, "no WHIR round (config.rs:422)"
         last = self.round_parameters[-1]
         rs_red = self.rs_reduction_factor(self.n_rounds - 1)
         ff = self.folding_at(self.n_rounds)

@@ -313,6 +313,46 @@ def air_exec_round(cols, eq_point, alpha_powers, la, beta) -> np.ndarray:
     return out
 
 
+AIR_EXEC, AIR_EXT_OP, AIR_POSEIDON16, AIR_NO_BUS = 0, 1, 2, 0x100
+
+
+def air_shape(table: int):
+    """(n_cols, n_shift, degree) of a table's AIR"""
+    out = (C.c_uint32 * 3)()
+    assert lib().lm_or_air_shape(C.c_uint32(table), out) == 0
+    return int(out[0]), int(out[1]), int(out[2])
+
+
+def air_eval(table: int, point, alpha_powers, la, beta) -> np.ndarray:
+    nc, ns, _ = air_shape(table)
+    pt, ap, la, beta = _u32(point).reshape(nc + ns, 5), _u32(alpha_powers).reshape(-1, 5), _u32(la).reshape(-1, 5), _u32(beta)
+    out = np.empty(5, dtype=np.uint32)
+    lib().lm_or_air_eval(C.c_uint32(table), _p(pt), _p(ap), _p(la), C.c_uint32(la.shape[0]), _p(beta), _p(out))
+    return out
+
+
+def air_round(table: int, cols, eq_point, alpha_powers, la, beta) -> np.ndarray:
+    """cols: (n_cols + n_shift, n) base or (.., n, 5) extension; returns evaluations at z = 0, 2, .., degree"""
+    nc, ns, deg = air_shape(table)
+    c = _u32(cols)
+    assert c.shape[0] == nc + ns
+    dim = 5 if c.ndim == 3 else 1
+    n = c.shape[1]
+    eqp, ap, la, beta = _u32(eq_point).reshape(-1, 5), _u32(alpha_powers).reshape(-1, 5), _u32(la).reshape(-1, 5), _u32(beta)
+    out = np.empty((deg, 5), dtype=np.uint32)
+    lib().lm_or_air_round(C.c_uint32(table), _p(c), C.c_uint64(n), C.c_uint32(dim), _p(eqp), _p(ap), _p(la),
+                          C.c_uint32(la.shape[0]), _p(beta), _p(out))
+    return out
+
+
+def poseidon16_fill_trace(cols) -> np.ndarray:
+    """cols: (109, n) base field with the 9 control columns and the 16 inputs set; returns the completed trace"""
+    c = _u32(cols).copy()
+    assert c.shape[0] == 109
+    lib().lm_or_poseidon16_fill_trace(_p(c), C.c_uint64(c.shape[1]))
+    return c
+
+
 def fold_lsb(col, r) -> np.ndarray:
     c, r = _u32(col), _u32(r)
     dim = 5 if (c.ndim == 2 and c.shape[1] == 5) else 1

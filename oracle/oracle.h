@@ -77,6 +77,12 @@ void lm_or_prod_round(const uint32_t *p, uint32_t dim, const uint32_t *w, uint64
 void lm_or_evals_to_coeffs(uint32_t *data, uint64_t n);
 
 /* air.c */
+int lm_or_air_shape(uint32_t table, uint32_t out[3]); /* n_cols, n_shift, degree */
+void lm_or_air_eval(uint32_t table, const uint32_t *point, const uint32_t *alpha_powers, const uint32_t *la, uint32_t n_la,
+                    const uint32_t beta[5], uint32_t out[5]);
+void lm_or_air_round(uint32_t table, const uint32_t *cols, uint64_t n, uint32_t dim, const uint32_t *eq_point,
+                     const uint32_t *alpha_powers, const uint32_t *la, uint32_t n_la, const uint32_t beta[5], uint32_t *out);
+void lm_or_poseidon16_fill_trace(uint32_t *cols, uint64_t n);
 void lm_or_air_exec_eval(const uint32_t *point, const uint32_t *alpha_powers, const uint32_t *la, uint32_t n_la,
                          const uint32_t beta[5], uint32_t out[5]);
 void lm_or_shift_column(const uint32_t *col, uint64_t n, uint32_t *out);

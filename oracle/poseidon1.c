@@ -19,26 +19,17 @@
 #include "kb.h"
 #include "oracle.h"
 
-#define W 16
-#define RF_HALF 4
-#define RP 20
-#define NR (2 * RF_HALF + RP)
+#include "poseidon1_consts.h"
+#define W P1_W
+#define RF_HALF P1_RF_HALF
+#define RP P1_RP
+#define NR P1_NR
 
 static const uint32_t RC_CANON[NR * W] = {
 #include "poseidon1_rc.inc"
 };
 static const uint32_t MDS_COL[W] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
 
-typedef struct {
-  kb_t rc[NR][W];            /* Montgomery form */
-  kb_t mds[W][W];            /* mds[i][j] = col[(i - j) mod 16] */
-  kb_t first_rc[W];          /* sparse form: vector added before m_i */
-  kb_t m_i[W][W];            /* dense transition matrix */
-  kb_t first_row[RP][W];     /* [mds00, w_hat[0..15)] */
-  kb_t v[RP][W];             /* rank-1 column update, v[r][15] = 0 */
-  kb_t scalar_rc[RP - 1];    /* added to lane 0 after the S-box of rounds 0..RP-2 */
-  int ready;
-} p1_consts_t;
 static p1_consts_t C;
 
 static void mat_mul(kb_t out[W][W], const kb_t a[W][W], const kb_t b[W][W]) {
@@ -209,6 +200,12 @@ void lm_or_poseidon1_compress(uint32_t s[16]) {
 }
 
 void lm_or_poseidon1_init(void) { p1_init(); }
+
+/* constants in application order, for the Poseidon16 AIR / trace generator (air.c) */
+const p1_consts_t *lm_or_p1_consts(void) {
+  p1_init();
+  return &C;
+}
 
 /* Batched entry points for the Python harness: n states, 16 u32 each. */
 void lm_or_poseidon1_permute_batch(uint32_t *states, uint64_t n, int dense) {

@@ -454,6 +454,7 @@ class WhirConfig:
         return self.num_variables - self.total_folding(self.n_rounds)
 
     def final_round_config(self):
+        assert self.round_parameters, "no WHIR round (config.rs:422)"
         last = self.round_parameters[-1]
         rs_red = self.rs_reduction_factor(self.n_rounds - 1)
         ff = self.folding_at(self.n_rounds)
@@ -812,3 +813,14 @@ def verify(cfg: WhirConfig, vs: VerifierState, commitment, statements):
     if claimed != mul(value, final_value):
         raise ProofError("InvalidProof: final sumcheck")
     return point
+
+
+def sumcheck_verify(vs: VerifierState, n_vars: int, degree: int, expected_sum, eq_alphas=None):
+    """crates/backend/sumcheck/src/verify.rs:5-30 -> (challenges, final target)"""
+    target, chals = expected_sum, []
+    for rnd in range(n_vars):
+        coeffs = vs.next_sumcheck_polynomial(degree + 1, target, None if eq_alphas is None else eq_alphas[rnd])
+        r = fm(vs.sample())
+        chals.append(r)
+        target = peval(coeffs, r)
+    return chals, target

@@ -287,15 +287,50 @@ def emit(t) -> str:
     return "\n".join(out) + "\n"
 
 
+def emit_sparse(c) -> str:
+    """Plain sparse-form tables (Montgomery form) for the Poseidon16 AIR and trace generator (air_tables.cuh):
+    the column values of the lean_vm Poseidon table are DEFINED through this formulation
+    (crates/lean_vm/src/tables/poseidon_16/{mod.rs:384-420, trace_gen.rs:46-95})."""
+    out = ["// GENERATED by tools/gen_poseidon1_consts.py — do not edit.",
+           "// Poseidon1-KoalaBear-16 sparse-form constants, Montgomery form (x * 2^32 mod p)."]
+    m = lambda row: [x * R % P for x in row]
+    rc = c["rc"]
+    out.append("{")
+    out.append("  /* RC_FULL[8][16]: initial rounds 0..3, final rounds 0..3 */ {")
+    for r in list(range(RF_HALF)) + list(range(RF_HALF + RP, 2 * RF_HALF + RP)):
+        out.append("  {\n" + cfmt(m(rc[r])) + "\n  },")
+    out.append("  },")
+    out.append("  /* FIRST_RC[16] */ {\n%s\n  }," % cfmt(m(c["first_rc"])))
+    out.append("  /* M_I[16][16] */ {")
+    for row in c["m_i"]:
+        out.append("  {\n" + cfmt(m(row)) + "\n  },")
+    out.append("  },")
+    out.append("  /* FIRST_ROW[20][16] */ {")
+    for row in c["first_row"]:
+        out.append("  {\n" + cfmt(m(row)) + "\n  },")
+    out.append("  },")
+    out.append("  /* V[20][16] (entry 15 unused) */ {")
+    for row in c["v"]:
+        out.append("  {\n" + cfmt(m(row + [0])) + "\n  },")
+    out.append("  },")
+    out.append("  /* SCALAR_RC[20] (entry 19 unused) */ {\n%s\n  }," % cfmt(m(c["scalar_rc"] + [0])))
+    out.append("}")
+    return "\n".join(out) + "\n"
+
+
 def main():
     c = derive()
     t = restructure(c)
-    path = os.path.join(CSRC, "poseidon1_tables.inc")
-    txt = emit(t)
+    ok = True
+    for name, txt in (("poseidon1_tables.inc", emit(t)), ("poseidon1_sparse_tables.inc", emit_sparse(c))):
+        path = os.path.join(CSRC, name)
+        if "--check" in sys.argv:
+            ok = ok and os.path.exists(path) and open(path).read() == txt
+        else:
+            open(path, "w").write(txt)
+            print("wrote", path)
     if "--check" in sys.argv:
-        sys.exit(0 if os.path.exists(path) and open(path).read() == txt else 1)
-    open(path, "w").write(txt)
-    print("wrote", path)
+        sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
