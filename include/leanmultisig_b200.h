@@ -183,6 +183,45 @@ int lm_gkr_fold(lm_gkr* gkr, const uint32_t r[5]);
 int lm_gkr_layer_end(lm_gkr* gkr, uint32_t* inner_evals /* 4 x 5 */);
 int lm_gkr_free(lm_gkr* gkr);
 
+/* ---- Logup table assembly ----------------------------------------------------------------------------------
+ * Replaces the table build of prove_generic_logup (crates/sub_protocols/src/logup.rs:52-211): numerators (base field)
+ * and denominators (EF) of every section, written back to back in NATURAL row order into device buffers that
+ * lm_logup_finish hands to the quotient-GKR session without a copy.  The caller (which knows Table::bus() /
+ * Table::lookups(), crates/lean_vm/src/tables/table_trait.rs:19-56) lists the sections in the reference's order:
+ *   memory, bytecode (+ padding up to the tallest table), then per table (tallest first): [execution only: bytecode
+ *   lookup], bus, one section per looked-up value column.
+ * Section rows:  numerator = 1 | +num_col[r] | -num_col[r] | 0;
+ *                denominator = c + den_sign * (alphas.last * domainsep + sum_i alphas[i] * data_i[r])   (den_sign = +-1)
+ *                              or 1 when den_sign = 0 (padding)                 (finger_print_packed, multilinear.rs:87-98)
+ * Host columns are uploaded once per (pointer, len) and stay cached for lm_logup_col_eval, which serves the column
+ * evaluations that follow the GKR (logup.rs:224-305). */
+typedef struct lm_logup lm_logup;
+#define LM_LOGUP_NUM_ONE 0u
+#define LM_LOGUP_NUM_COL 1u
+#define LM_LOGUP_NUM_NEG_COL 2u
+#define LM_LOGUP_NUM_ZERO 3u
+#define LM_LOGUP_DATA_COL 0u   /* col[offset + r * stride] + value */
+#define LM_LOGUP_DATA_ROW 1u   /* the row index r */
+#define LM_LOGUP_DATA_CONST 2u /* value */
+typedef struct {
+  const uint32_t* col; /* host array (Montgomery words) of `len` entries, or NULL */
+  uint64_t len, offset, stride;
+  uint32_t kind;
+  uint32_t value; /* canonical integer constant */
+} lm_logup_data;
+int lm_logup_new(lm_ctx* ctx, uint64_t total_active_len, const uint32_t c[5], const uint32_t* alphas_eq_poly,
+                 uint32_t n_alphas, lm_logup** out);
+int lm_logup_section(lm_logup* logup, uint64_t n_rows, uint32_t num_mode, const uint32_t* num_col, int32_t den_sign,
+                     uint32_t domainsep, const lm_logup_data* data, uint32_t n_data);
+/* MleRef::evaluate of a (cached or new) host column of `len` <= 2^n_vars entries; point: n_vars x 5 */
+int lm_logup_col_eval(lm_logup* logup, const uint32_t* col, uint64_t len, uint32_t n_vars, const uint32_t* point,
+                      uint32_t out[5]);
+/* copy what has been filled so far back to the host (parity tests); either pointer may be NULL */
+int lm_logup_read(lm_logup* logup, uint32_t* out_nums, uint32_t* out_dens);
+/* all total_active_len rows filled: pad to the next power of two with (0, 1) and run the GKR up pass */
+int lm_logup_finish(lm_logup* logup, lm_gkr** out);
+int lm_logup_free(lm_logup* logup);
+
 /* ---- device-pointer layer (inputs already in HBM; used by the kernel-only benchmark and by lm_* above) -----
  * All pointers are device pointers on ctx's device; work is enqueued on ctx's stream, no synchronisation. */
 int lm_dev_alloc(lm_ctx* ctx, size_t bytes, void** out);

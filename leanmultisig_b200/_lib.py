@@ -113,6 +113,12 @@ def lib() -> C.CDLL:
             "lm_dev_fold_msb": [vp, vp, u64, u32, u32p, vp],
             "lm_dev_eq_table": [vp, u32p, u32, u32p, vp],
             "lm_pow_grind": [vp, u32p, u32, u64p],
+            "lm_logup_new": [vp, u64, u32p, u32p, u32, C.POINTER(vp)],
+            "lm_logup_section": [vp, u64, u32, vp, C.c_int32, u32, vp, u32],
+            "lm_logup_col_eval": [vp, vp, u64, u32, u32p, u32p],
+            "lm_logup_read": [vp, vp, vp],
+            "lm_logup_finish": [vp, C.POINTER(vp)],
+            "lm_logup_free": [vp],
             "lm_poseidon16_fill_trace": [vp, C.POINTER(vp), u64],
             "lm_dev_poseidon16_fill_trace": [vp, vp, u64],
             "lm_host_poseidon1_permute": [u32p],

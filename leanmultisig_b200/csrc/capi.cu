@@ -5,7 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/leanmultisig_b200.h"
@@ -1038,28 +1040,19 @@ int lm_gkr_free(lm_gkr* g) {
   return LM_OK;
 }
 
-int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, lm_gkr** out) {
-  if (!c || !nums || !dens || !out) return fail(LM_ERR_INVALID, "lm_gkr_new: null argument");
-  *out = nullptr;
-  if (active_len < 2) return fail(LM_ERR_INVALID, "lm_gkr_new: need at least two fractions");
-  uint32_t n_vars = 0;
-  while (((uint64_t)1 << n_vars) < active_len) n_vars++;
-  if (n_vars <= LM_GKR_TOP_VARS) return fail(LM_ERR_INVALID, "lm_gkr_new: needs more than 2^%u fractions", LM_GKR_TOP_VARS);
-  if (n_vars > 31) return fail(LM_ERR_INVALID, "lm_gkr_new: too many fractions");
-  CU(cudaSetDevice(c->device));
+// takes ownership of d_n (2^n_vars words) and d_d (2^n_vars x 5 words), both already filled on [0, active_len)
+static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t active_len, uint32_t n_vars, lm_gkr** out) {
   lm_gkr* g = new (std::nothrow) lm_gkr();
-  if (!g) return fail(LM_ERR_OOM, "lm_gkr_new: host allocation failed");
+  if (!g) {
+    cudaFree(d_n), cudaFree(d_d);
+    return fail(LM_ERR_OOM, "lm_gkr: host allocation failed");
+  }
   g->ctx = c;
   g->n_vars = n_vars;
+  g->nums.push_back(d_n);
+  g->dens.push_back(d_d);
   const uint64_t n = (uint64_t)1 << n_vars;
-  cudaError_t e = cudaSuccess;
-  uint32_t *d_n = nullptr, *d_d = nullptr;
-  e = cudaMalloc(&d_n, n * sizeof(uint32_t));
-  if (e == cudaSuccess) g->nums.push_back(d_n), e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
-  if (e == cudaSuccess) g->dens.push_back(d_d);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = lm::gkr_pad(c->stream, d_n, 1, d_d, active_len, n);
+  cudaError_t e = lm::gkr_pad(c->stream, d_n, 1, d_d, active_len, n);
   // up pass (mod.rs:52-62): halve until 2^5 fractions remain
   for (uint32_t l = 1; e == cudaSuccess && l <= n_vars - LM_GKR_TOP_VARS; l++) {
     const uint64_t m = n >> l;
@@ -1082,6 +1075,196 @@ int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t a
     return cuda_fail(e, "lm_gkr_new");
   }
   *out = g;
+  return LM_OK;
+}
+
+static int gkr_vars_for(uint64_t active_len, uint32_t* n_vars_out, const char* who) {
+  if (active_len < 2) return fail(LM_ERR_INVALID, "%s: need at least two fractions", who);
+  uint32_t n_vars = 0;
+  while (((uint64_t)1 << n_vars) < active_len) n_vars++;
+  if (n_vars <= LM_GKR_TOP_VARS) return fail(LM_ERR_INVALID, "%s: needs more than 2^%u fractions", who, LM_GKR_TOP_VARS);
+  if (n_vars > 31) return fail(LM_ERR_INVALID, "%s: too many fractions", who);
+  *n_vars_out = n_vars;
+  return LM_OK;
+}
+
+int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, lm_gkr** out) {
+  if (!c || !nums || !dens || !out) return fail(LM_ERR_INVALID, "lm_gkr_new: null argument");
+  *out = nullptr;
+  uint32_t n_vars = 0;
+  if (int rc = gkr_vars_for(active_len, &n_vars, "lm_gkr_new")) return rc;
+  CU(cudaSetDevice(c->device));
+  const uint64_t n = (uint64_t)1 << n_vars;
+  uint32_t *d_n = nullptr, *d_d = nullptr;
+  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d_n), cudaFree(d_d);
+    return cuda_fail(e, "lm_gkr_new");
+  }
+  return gkr_from_device(c, d_n, d_d, active_len, n_vars, out);
+}
+
+// evaluation of a device-resident base/extension polynomial at a host point, result to the host
+static int mle_eval_on_device(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint64_t live_len,
+                              const uint32_t* point, uint32_t out[5]) {
+  if (n_vars > 64) return fail(LM_ERR_INVALID, "mle_eval: n_vars too large");
+  if (n_vars) CU(cudaMemcpyAsync(c->d_point, point, (size_t)n_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  int rc = lm_dev_mle_eval(c, d_evals, n_vars, dim, live_len, c->d_point, c->d_small);
+  if (rc != LM_OK) return rc;
+  CU(cudaMemcpyAsync(out, c->d_small, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+// ---- Logup table builder (prove_generic_logup's table assembly, logup.rs:52-211) ---------------------------------
+struct lm_logup {
+  lm_ctx* ctx = nullptr;
+  uint64_t total = 0, offset = 0;
+  uint32_t n_vars = 0;
+  uint32_t *d_nums = nullptr, *d_dens = nullptr;
+  lm::Ef c;
+  std::vector<uint32_t> alphas;  // n x 5
+  std::map<std::pair<const void*, uint64_t>, uint32_t*> cache;  // host array -> device copy
+
+  int device_copy(const uint32_t* host, uint64_t len, uint32_t** out) {
+    auto key = std::make_pair((const void*)host, len);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return LM_OK;
+    }
+    uint32_t* d = nullptr;
+    const uint64_t padded = (len + 1023) / 1024 * 1024 + 1024;  // lm_dev_mle_eval reads whole 2^10-element chunks
+    CU(cudaMalloc(&d, padded * sizeof(uint32_t)));
+    cache[key] = d;
+    CU(cudaMemcpyAsync(d, host, len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d + len, 0, (padded - len) * sizeof(uint32_t), ctx->stream));
+    *out = d;
+    return LM_OK;
+  }
+};
+
+static uint32_t to_monty_u32(uint64_t canonical) { return (uint32_t)(((canonical % lm::KB_P) << 32) % lm::KB_P); }
+
+int lm_logup_new(lm_ctx* c, uint64_t total_active_len, const uint32_t cc[5], const uint32_t* alphas_eq_poly, uint32_t n_alphas,
+                 lm_logup** out) {
+  if (!c || !cc || !alphas_eq_poly || !out) return fail(LM_ERR_INVALID, "lm_logup_new: null argument");
+  *out = nullptr;
+  if (n_alphas < 2) return fail(LM_ERR_INVALID, "lm_logup_new: need at least 2 alphas");
+  uint32_t n_vars = 0;
+  if (int rc = gkr_vars_for(total_active_len, &n_vars, "lm_logup_new")) return rc;
+  CU(cudaSetDevice(c->device));
+  lm_logup* L = new (std::nothrow) lm_logup();
+  if (!L) return fail(LM_ERR_OOM, "lm_logup_new: host allocation failed");
+  L->ctx = c;
+  L->total = total_active_len;
+  L->n_vars = n_vars;
+  for (int k = 0; k < 5; k++) L->c.c[k] = cc[k];
+  L->alphas.assign(alphas_eq_poly, alphas_eq_poly + 5 * (size_t)n_alphas);
+  const uint64_t n = (uint64_t)1 << n_vars;
+  cudaError_t e = cudaMalloc(&L->d_nums, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&L->d_dens, n * 5 * sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    lm_logup_free(L);
+    return cuda_fail(e, "lm_logup_new");
+  }
+  *out = L;
+  return LM_OK;
+}
+
+int lm_logup_section(lm_logup* L, uint64_t n_rows, uint32_t num_mode, const uint32_t* num_col, int32_t den_sign,
+                     uint32_t domainsep, const lm_logup_data* data, uint32_t n_data) {
+  if (!L || (n_data && !data)) return fail(LM_ERR_INVALID, "lm_logup_section: null argument");
+  if (L->offset + n_rows > L->total)
+    return fail(LM_ERR_INVALID, "lm_logup_section: %llu + %llu rows exceed total_active_len %llu", (unsigned long long)L->offset,
+                (unsigned long long)n_rows, (unsigned long long)L->total);
+  if (num_mode > 3) return fail(LM_ERR_INVALID, "lm_logup_section: numerator mode %u", num_mode);
+  if ((num_mode == 1 || num_mode == 2) && !num_col) return fail(LM_ERR_INVALID, "lm_logup_section: numerator column is null");
+  const size_t n_al = L->alphas.size() / 5;
+  if (n_data >= n_al || n_data > (uint32_t)lm::LOGUP_MAX_DATA)
+    return fail(LM_ERR_INVALID, "lm_logup_section: %u data columns need more than %zu alphas (max %d)", n_data, n_al, lm::LOGUP_MAX_DATA);
+  lm_ctx* c = L->ctx;
+  CU(cudaSetDevice(c->device));
+  lm::LogupSection S{};
+  S.n_rows = n_rows;
+  S.num_mode = (int)num_mode;
+  S.den_sign = den_sign > 0 ? 1 : (den_sign < 0 ? -1 : 0);
+  S.n_data = (int)n_data;
+  S.c = L->c;
+  if (num_col) {
+    uint32_t* d = nullptr;
+    if (int rc = L->device_copy(num_col, n_rows, &d)) return rc;
+    S.num_col = d;
+  }
+  // contrib = alphas.last * domainsep  (logup.rs:57-60)
+  const uint32_t ds = to_monty_u32(domainsep);
+  for (int k = 0; k < 5; k++) S.contrib.c[k] = lm::kb_mul(L->alphas[5 * (n_al - 1) + k], ds);
+  for (uint32_t i = 0; i < n_data; i++) {
+    for (int k = 0; k < 5; k++) S.alphas[i].c[k] = L->alphas[5 * i + k];
+    lm::LogupData& d = S.data[i];
+    d.kind = data[i].kind;
+    d.add = to_monty_u32(data[i].value);
+    d.offset = data[i].offset;
+    d.stride = data[i].stride ? data[i].stride : 1;
+    d.col = nullptr;
+    if (d.kind == lm::LOGUP_DATA_COL) {
+      if (!data[i].col) return fail(LM_ERR_INVALID, "lm_logup_section: data column %u is null", i);
+      if (n_rows && d.offset + (n_rows - 1) * d.stride >= data[i].len)
+        return fail(LM_ERR_INVALID, "lm_logup_section: data column %u is too short", i);
+      uint32_t* dd = nullptr;
+      if (int rc = L->device_copy(data[i].col, data[i].len, &dd)) return rc;
+      d.col = dd;
+    } else if (d.kind > 2) {
+      return fail(LM_ERR_INVALID, "lm_logup_section: data kind %u", d.kind);
+    }
+  }
+  CU(lm::logup_fill_section(c->stream, S, L->d_nums + L->offset, L->d_dens + 5 * L->offset));
+  L->offset += n_rows;
+  return LM_OK;
+}
+
+int lm_logup_col_eval(lm_logup* L, const uint32_t* col, uint64_t len, uint32_t n_vars, const uint32_t* point, uint32_t out[5]) {
+  if (!L || !col || !point || !out) return fail(LM_ERR_INVALID, "lm_logup_col_eval: null argument");
+  if (n_vars > 40 || len > ((uint64_t)1 << n_vars)) return fail(LM_ERR_INVALID, "lm_logup_col_eval: column longer than 2^n_vars");
+  lm_ctx* c = L->ctx;
+  CU(cudaSetDevice(c->device));
+  uint32_t* d = nullptr;
+  if (int rc = L->device_copy(col, len, &d)) return rc;
+  return mle_eval_on_device(c, d, n_vars, 1, len, point, out);
+}
+
+int lm_logup_read(lm_logup* L, uint32_t* out_nums, uint32_t* out_dens) {
+  if (!L) return fail(LM_ERR_INVALID, "lm_logup_read: null argument");
+  lm_ctx* c = L->ctx;
+  CU(cudaSetDevice(c->device));
+  if (out_nums) CU(cudaMemcpyAsync(out_nums, L->d_nums, L->offset * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (out_dens) CU(cudaMemcpyAsync(out_dens, L->d_dens, L->offset * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
+int lm_logup_finish(lm_logup* L, lm_gkr** out) {
+  if (!L || !out) return fail(LM_ERR_INVALID, "lm_logup_finish: null argument");
+  *out = nullptr;
+  if (L->offset != L->total)
+    return fail(LM_ERR_INVALID, "lm_logup_finish: %llu of %llu rows filled", (unsigned long long)L->offset, (unsigned long long)L->total);
+  if (!L->d_nums) return fail(LM_ERR_INVALID, "lm_logup_finish: already finished");
+  CU(cudaSetDevice(L->ctx->device));
+  uint32_t *d_n = L->d_nums, *d_d = L->d_dens;
+  L->d_nums = L->d_dens = nullptr;  // ownership moves to the GKR session
+  return gkr_from_device(L->ctx, d_n, d_d, L->total, L->n_vars, out);
+}
+
+int lm_logup_free(lm_logup* L) {
+  if (!L) return LM_OK;
+  if (L->ctx) cudaSetDevice(L->ctx->device);
+  if (L->d_nums) cudaFree(L->d_nums);
+  if (L->d_dens) cudaFree(L->d_dens);
+  for (auto& kv : L->cache) cudaFree(kv.second);
+  delete L;
   return LM_OK;
 }
 

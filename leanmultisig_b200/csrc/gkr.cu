@@ -58,6 +58,65 @@ cudaError_t finger_print(cudaStream_t stream, const uint32_t* d_data, uint64_t n
   return cudaGetLastError();
 }
 
+// ---- Logup table build (prove_generic_logup, crates/sub_protocols/src/logup.rs:52-211) --------------------------
+// One section = n_rows consecutive (numerator, denominator) pairs in NATURAL row order:
+//   numerator   = 1 | +col[r] | -col[r] | 0
+//   denominator = c + sign * (contrib + sum_i alphas[i] * data_i[r])      (finger_print_packed, multilinear.rs:87-98)
+//                 or the constant 1 for padding
+// data_i[r] = col[offset + r * stride] (+ add) | r | constant.  Everything a section needs travels in the kernel
+// parameter (constant bank); rows are independent and the writes are coalesced (4 B + 20 B per row).
+__global__ void logup_fill_kernel(const __grid_constant__ LogupSection S, uint32_t* __restrict__ nums, uint32_t* __restrict__ dens) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= S.n_rows) return;
+  uint32_t num;
+  switch (S.num_mode) {
+    case LOGUP_NUM_ONE: num = KB_R1; break;
+    case LOGUP_NUM_COL: num = __ldg(S.num_col + r); break;
+    case LOGUP_NUM_NEG_COL: num = kb_neg(__ldg(S.num_col + r)); break;
+    default: num = 0; break;
+  }
+  nums[r] = num;
+  Ef o;
+  if (S.den_sign == 0) {
+    o = ef_from_base(KB_R1);
+  } else {
+    uint64_t acc[5] = {0, 0, 0, 0, 0};
+    int terms = 0;
+    for (int i = 0; i < S.n_data; i++) {
+      const LogupData& d = S.data[i];
+      uint32_t f;
+      if (d.kind == LOGUP_DATA_COL)
+        f = kb_add(__ldg(d.col + d.offset + r * d.stride), d.add);
+      else if (d.kind == LOGUP_DATA_ROW)
+        f = kb_mul((uint32_t)r, KB_R2);  // Montgomery form of the row index (< 2^31 rows per section)
+      else
+        f = d.add;
+      if (terms == 3) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) acc[k] = kb_fold(acc[k]);
+        terms = 0;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; k++) acc[k] = mad_wide(f, S.alphas[i].c[k], acc[k]);
+      terms++;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const uint32_t fp = kb_add(S.contrib.c[k], kb_canon(kb_redc_lazy(kb_fold(acc[k]))));
+      o.c[k] = S.den_sign > 0 ? kb_add(S.c.c[k], fp) : kb_sub(S.c.c[k], fp);
+    }
+  }
+  st_ef(dens + 5 * r, o);
+}
+
+cudaError_t logup_fill_section(cudaStream_t stream, const LogupSection& S, uint32_t* d_nums, uint32_t* d_dens) {
+  if (S.n_rows == 0) return cudaSuccess;
+  if (S.n_data > LOGUP_MAX_DATA || S.n_rows > ((uint64_t)1 << 31)) return cudaErrorInvalidValue;
+  logup_fill_kernel<<<(unsigned)((S.n_rows + 255) / 256), 256, 0, stream>>>(S, d_nums, d_dens);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // nums[i] = 0, dens[i] = 1 for i in [active, n)
 __global__ void gkr_pad_kernel(uint32_t* nums, int num_dim, uint32_t* dens, uint64_t active, uint64_t n) {
   const uint64_t i = active + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -66,7 +66,32 @@ class GkrQuotientProver:
         check(lib().lm_gkr_top(self.handle, _p(tn), _p(td)))
         return tn, td
 
-    def prove(self, add_scalars, add_sumcheck_poly, sample):
+    @classmethod
+    def from_handle(cls, handle):
+        self = cls.__new__(cls)
+        self.handle = handle
+        nv = C.c_uint32()
+        check(lib().lm_gkr_num_vars(handle, C.byref(nv)))
+        self.n_vars = nv.value
+        return self
+
+    def prove_with_state(self, prover_state):
+        """prove_gkr_quotient driven by an FSProver (mod.rs:31-78): alpha of every layer is sampled after a duplex"""
+        def sample_alpha():
+            prover_state.duplex()
+            return prover_state.sample()
+
+        self._sample_alpha = sample_alpha
+        try:
+            return self.prove(lambda v: prover_state.add_extension_scalars(_u32(v).reshape(-1)),
+                              prover_state.add_sumcheck_polynomial, prover_state.sample,
+                              sample_point=lambda n: prover_state.sample_vec(n))
+        finally:
+            self._sample_alpha = None
+
+    _sample_alpha = None
+
+    def prove(self, add_scalars, add_sumcheck_poly, sample, sample_point=None):
         """returns (quotient, point, claim_num, claim_den) as Montgomery-form arrays"""
         tn, td = self.top()
         add_scalars(tn)
@@ -75,7 +100,10 @@ class GkrQuotientProver:
         quotient = F.ZERO
         for a, b in zip(top_n, top_d):
             quotient = F.add(quotient, F.mul(a, F.inv(b)))
-        point = [F.from_monty(sample()) for _ in range(N_VARS_TO_SEND_GKR_COEFFS)]
+        if sample_point is not None:
+            point = [F.from_monty(x) for x in sample_point(N_VARS_TO_SEND_GKR_COEFFS)]
+        else:
+            point = [F.from_monty(sample()) for _ in range(N_VARS_TO_SEND_GKR_COEFFS)]
         claim_num, claim_den = _mle_eval_small(top_n, point), _mle_eval_small(top_d, point)
         for k in range(N_VARS_TO_SEND_GKR_COEFFS, self.n_vars):
             point, claim_num, claim_den = self._prove_layer(k, point, claim_num, claim_den, add_scalars, add_sumcheck_poly,
@@ -84,7 +112,7 @@ class GkrQuotientProver:
                 F.to_monty(claim_den))
 
     def _prove_layer(self, k, point, claim_num, claim_den, add_scalars, add_sumcheck_poly, sample):
-        alpha_m = _u32(sample())
+        alpha_m = _u32(self._sample_alpha() if self._sample_alpha else sample())
         alpha = F.from_monty(alpha_m)
         s = F.add(claim_num, F.mul(alpha, claim_den))
         mmf = F.ONE
@@ -119,3 +147,166 @@ class GkrQuotientProver:
         if self.handle:
             check(lib().lm_gkr_free(self.handle))
             self.handle = None
+
+
+# ======================================================================================================
+# prove_generic_logup (crates/sub_protocols/src/logup.rs:27-320)
+# ======================================================================================================
+class _Data(C.Structure):
+    _fields_ = [("col", C.c_void_p), ("len", C.c_uint64), ("offset", C.c_uint64), ("stride", C.c_uint64),
+                ("kind", C.c_uint32), ("value", C.c_uint32)]
+
+
+NUM_ONE, NUM_COL, NUM_NEG_COL, NUM_ZERO = 0, 1, 2, 3
+DATA_COL, DATA_ROW, DATA_CONST = 0, 1, 2
+
+
+class LogupBuilder:
+    """lm_logup_*: numerators / denominators of all sections, assembled on the device in natural row order."""
+
+    def __init__(self, ctx, total_active_len: int, c, alphas_eq_poly):
+        al = _u32(alphas_eq_poly).reshape(-1, 5)
+        h = C.c_void_p()
+        check(lib().lm_logup_new(ctx.handle, total_active_len, _p(_u32(c)), _p(al), al.shape[0], C.byref(h)))
+        self.handle, self._keep = h, []
+
+    def section(self, n_rows: int, num_mode: int, num_col, den_sign: int, domainsep: int, data) -> None:
+        """data: list of ("col", array, offset, stride, add) | ("row",) | ("const", value)"""
+        arr = (_Data * max(len(data), 1))()
+        for i, d in enumerate(data):
+            if d[0] == "col":
+                a = d[1]
+                assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+                self._keep.append(a)
+                arr[i] = _Data(a.ctypes.data, a.size, d[2], d[3], DATA_COL, d[4])
+            elif d[0] == "row":
+                arr[i] = _Data(None, 0, 0, 1, DATA_ROW, 0)
+            else:
+                arr[i] = _Data(None, 0, 0, 1, DATA_CONST, d[1])
+        ncol = None
+        if num_col is not None:
+            assert num_col.dtype == np.uint32 and num_col.flags["C_CONTIGUOUS"]
+            self._keep.append(num_col)
+            ncol = num_col.ctypes.data
+        check(lib().lm_logup_section(self.handle, n_rows, num_mode, ncol, den_sign, domainsep, C.byref(arr), len(data)))
+
+    def col_eval(self, col, n_vars: int, point) -> np.ndarray:
+        assert col.dtype == np.uint32 and col.flags["C_CONTIGUOUS"]
+        out = np.empty(5, dtype=np.uint32)
+        pt = _u32(point).reshape(-1, 5)
+        assert pt.shape[0] == n_vars
+        check(lib().lm_logup_col_eval(self.handle, col.ctypes.data, col.size, n_vars, _p(pt), _p(out)))
+        return out
+
+    def read(self, n_rows: int):
+        nums, dens = np.empty(n_rows, dtype=np.uint32), np.empty((n_rows, 5), dtype=np.uint32)
+        check(lib().lm_logup_read(self.handle, nums.ctypes.data, dens.ctypes.data))
+        return nums, dens
+
+    def finish(self) -> GkrQuotientProver:
+        h = C.c_void_p()
+        check(lib().lm_logup_finish(self.handle, C.byref(h)))
+        return GkrQuotientProver.from_handle(h)
+
+    def free(self):
+        if self.handle:
+            check(lib().lm_logup_free(self.handle))
+            self.handle = None
+
+
+def build_logup_table(ctx, c, alphas_eq_poly, memory, memory_acc, bytecode_multilinear, bytecode_acc, traces) -> LogupBuilder:
+    """The section list of logup.rs:96-211.  traces: {tables.Table: tables.TableTrace}"""
+    from . import tables as T
+
+    log_memory = memory.size.bit_length() - 1
+    assert memory.size == 1 << log_memory and memory_acc.size == memory.size
+    stride = 1 << (T.N_INSTRUCTION_COLUMNS - 1).bit_length()
+    log_bytecode = (bytecode_multilinear.size // stride).bit_length() - 1
+    assert bytecode_acc.size == 1 << log_bytecode
+    tables_sorted = T.sort_tables_by_height({t: tr.log_n_rows for t, tr in traces.items()})
+    assert memory.size >= 1 << tables_sorted[0][1]
+    total = T.compute_total_active_len(log_memory, log_bytecode, tables_sorted)
+    b = LogupBuilder(ctx, total, c, alphas_eq_poly)
+    max_table_height = 1 << tables_sorted[0][1]
+    # memory
+    b.section(memory.size, NUM_NEG_COL, memory_acc, -1, T.LOGUP_MEMORY_DOMAINSEP, [("col", memory, 0, 1, 0), ("row",)])
+    # bytecode (+ padding up to the tallest table)
+    data = [("col", bytecode_multilinear, k, stride, 0) for k in range(T.N_INSTRUCTION_COLUMNS)] + [("row",)]
+    b.section(1 << log_bytecode, NUM_NEG_COL, bytecode_acc, -1, T.LOGUP_BYTECODE_DOMAINSEP, data)
+    if (1 << log_bytecode) < max_table_height:
+        b.section(max_table_height - (1 << log_bytecode), NUM_ZERO, None, 0, 0, [])
+    for table, log_n_rows in tables_sorted:
+        cols = traces[table].columns
+        n = 1 << log_n_rows
+        if table.is_execution:
+            data = [("col", cols[T.N_RUNTIME_COLUMNS + k], 0, 1, 0) for k in range(T.N_INSTRUCTION_COLUMNS)]
+            data.append(("col", cols[T.COL_PC], 0, 1, 0))
+            b.section(n, NUM_ONE, None, -1, T.LOGUP_BYTECODE_DOMAINSEP, data)
+        bus = table.bus
+        b.section(n, NUM_NEG_COL if bus.pull else NUM_COL, cols[bus.selector], +1, T.LOGUP_PRECOMPILE_DOMAINSEP,
+                  [("col", cols[k], 0, 1, 0) for k in bus.data])
+        for lk in table.lookups:
+            for i, vcol in enumerate(lk.values):
+                b.section(n, NUM_ONE, None, -1, T.LOGUP_MEMORY_DOMAINSEP,
+                          [("col", cols[vcol], 0, 1, 0), ("col", cols[lk.index], 0, 1, i)])
+    return b
+
+
+def prove_generic_logup(ctx, prover_state, c, alphas_eq_poly, memory, memory_acc, bytecode_multilinear, bytecode_acc, traces):
+    """logup.rs:27-320 -> dict mirroring GenericLogupStatements (Montgomery arrays)"""
+    from . import tables as T
+
+    al = _u32(alphas_eq_poly).reshape(-1, 5)
+    b = build_logup_table(ctx, c, al, memory, memory_acc, bytecode_multilinear, bytecode_acc, traces)
+    gkr = b.finish()
+    total_gkr_n_vars = gkr.n_vars
+    quotient, point, _, _ = gkr.prove_with_state(prover_state)
+    gkr.free()
+    assert not quotient.any(), "logup sum is not zero"
+    log_memory = memory.size.bit_length() - 1
+    stride = 1 << (T.N_INSTRUCTION_COLUMNS - 1).bit_length()
+    log_bytecode = (bytecode_multilinear.size // stride).bit_length() - 1
+
+    def from_end(k):
+        return point[point.shape[0] - k:]
+
+    def add(v):
+        prover_state.add_extension_scalars(v)
+        return v
+
+    out = dict(gkr_point=point, total_gkr_n_vars=total_gkr_n_vars)
+    out["memory_and_acc_point"] = from_end(log_memory)
+    out["value_memory_acc"] = add(b.col_eval(memory_acc, log_memory, from_end(log_memory)))
+    out["value_memory"] = add(b.col_eval(memory, log_memory, from_end(log_memory)))
+    out["bytecode_and_acc_point"] = from_end(log_bytecode)
+    out["value_bytecode_acc"] = add(b.col_eval(bytecode_acc, log_bytecode, from_end(log_bytecode)))
+    out["bus_numerators_values"], out["bus_denominators_values"], out["columns_values"] = {}, {}, {}
+    c_c = F.from_monty(c)
+    al_c = [F.from_monty(a) for a in al]
+    for table, log_n_rows in T.sort_tables_by_height({t: tr.log_n_rows for t, tr in traces.items()}):
+        cols = traces[table].columns
+        inner = from_end(log_n_rows)
+        values = {}
+        if table.is_execution:
+            values[T.COL_PC] = add(b.col_eval(cols[T.COL_PC], log_n_rows, inner))
+            instr = [b.col_eval(cols[T.N_RUNTIME_COLUMNS + k], log_n_rows, inner) for k in range(T.N_INSTRUCTION_COLUMNS)]
+            prover_state.add_extension_scalars(np.concatenate(instr))
+            for k, v in enumerate(instr):
+                values[T.N_RUNTIME_COLUMNS + k] = v
+        bus = table.bus
+        sel = F.from_monty(b.col_eval(cols[bus.selector], log_n_rows, inner))
+        if bus.pull:
+            sel = F.neg(sel)
+        out["bus_numerators_values"][table] = add(F.to_monty(sel))
+        data_evals = [F.from_monty(b.col_eval(cols[k], log_n_rows, inner)) for k in bus.data]
+        fp = F.scal(al_c[-1], T.LOGUP_PRECOMPILE_DOMAINSEP)
+        for a, d in zip(al_c, data_evals):
+            fp = F.add(fp, F.mul(a, d))
+        out["bus_denominators_values"][table] = add(F.to_monty(F.add(c_c, fp)))
+        for lk in table.lookups:
+            values[lk.index] = add(b.col_eval(cols[lk.index], log_n_rows, inner))
+            for vcol in lk.values:
+                values[vcol] = add(b.col_eval(cols[vcol], log_n_rows, inner))
+        out["columns_values"][table] = values
+    b.free()
+    return out
