@@ -27,8 +27,16 @@ static const P1Tables h_p1 =
 #include "poseidon1_tables.inc"
     ;
 
+// CTA shape of the permutation-bound kernels (profiles/r01_leaf_barrier_sweep.txt): two 256-thread CTAs per SM,
+// warps kept together by barriers inside the permutation.
 #ifndef LEAF_MIN_BLOCKS
-#define LEAF_MIN_BLOCKS 3
+#define LEAF_MIN_BLOCKS 2
+#endif
+#ifndef LEAF_THREADS
+#define LEAF_THREADS 256
+#endif
+#ifndef LEAF_SYNC
+#define LEAF_SYNC 1
 #endif
 
 struct State16 {
@@ -53,11 +61,12 @@ __device__ __forceinline__ void load_chunk8(const uint32_t* __restrict__ row, in
   }
 }
 
-__global__ void __launch_bounds__(128, LEAF_MIN_BLOCKS)
+__global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
 leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t lim, uint32_t virt_w,
                    int from_state, State16 init, uint32_t* __restrict__ digests) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= h) return;
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < h;
+  if (!live) r = h - 1;  // every thread runs the sponge (CTA-wide barriers inside the permutation); no store
   const uint32_t* row = mat + r * stored_w;
   const bool vec_ok = (stored_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mat) & 15) == 0);
   uint32_t s[16];
@@ -75,9 +84,10 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
   }
   for (int64_t it = 0; it < n_comp; it++) {
     load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
-    p1_compress<8>(s, c_p1);
+    p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
     chunk -= (it == 0 && !from_state) ? 2 : 1;
   }
+  if (!live) return;
   uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
   out[0] = make_uint4(s[0], s[1], s[2], s[3]);
   out[1] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -86,11 +96,12 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
 // One sponge step for every row: state (lanes 0..7, kept in the digest buffer between steps) absorbs rate chunk
 // `chunk` of the row.  Lets the commit hash columns as soon as they are transformed, right to left, while the
 // host-to-device copy of the columns further left is still in flight.
-__global__ void __launch_bounds__(128, LEAF_MIN_BLOCKS)
+__global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
 leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t chunk, int first, State16 init,
                    uint32_t* __restrict__ digests) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= h) return;
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < h;
+  if (!live) r = h - 1;
   uint32_t s[16];
   uint4* dg = reinterpret_cast<uint4*>(digests + 8 * r);
   if (first) {
@@ -103,7 +114,8 @@ leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
   const uint4* src = reinterpret_cast<const uint4*>(mat + r * stored_w + 8 * chunk);
   const uint4 lo = __ldg(src), hi = __ldg(src + 1);
   s[8] = lo.x, s[9] = lo.y, s[10] = lo.z, s[11] = lo.w, s[12] = hi.x, s[13] = hi.y, s[14] = hi.z, s[15] = hi.w;
-  p1_compress<8>(s, c_p1);
+  p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
+  if (!live) return;
   dg[0] = make_uint4(s[0], s[1], s[2], s[3]);
   dg[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
@@ -197,7 +209,7 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
     lim = stored_w;
     virt_w = full_w;
   }
-  const int T = 128;
+  const int T = LEAF_THREADS;
   const uint64_t blocks = (h + T - 1) / T;
   leaf_sponge_kernel<<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests); count_launch();
   return cudaGetLastError();
@@ -214,7 +226,8 @@ cudaError_t merkle_leaf_absorb_chunk(cudaStream_t stream, const uint32_t* d_mat,
   const int first = chunk == eff_w / 8 - 1;
   State16 init{};
   if (first) init = zero_suffix_state_host((full_w - eff_w) / 8);
-  leaf_absorb_kernel<<<(unsigned)((h + 127) / 128), 128, 0, stream>>>(d_mat, h, stored_w, chunk, first, init, d_digests);
+  leaf_absorb_kernel<<<(unsigned)((h + LEAF_THREADS - 1) / LEAF_THREADS), LEAF_THREADS, 0, stream>>>(d_mat, h, stored_w, chunk, first,
+                                                                                                       init, d_digests);
   count_launch();
   return cudaGetLastError();
 }

@@ -149,7 +149,17 @@ LM_HD KbDot p1_dot16(const uint32_t x[16], const uint32_t* row, uint64_t init) {
 
 // Permutation; N_OUT = 16 for the full permutation, 8 when only the digest half is needed.
 // s: canonical in, canonical out (lanes >= N_OUT are left unspecified).
-template <int N_OUT, class Tab>
+// SYNC: the device code places a CTA-wide barrier after every full round and a few times inside the partial
+// section.  The warps of a CTA then walk the ~100 KiB instruction stream together and share its fetches; with two
+// 256-thread CTAs per SM (<= 128 registers) this measured 8 % faster than three free-running 128-thread CTAs
+// (profiles/r01_leaf_barrier_sweep.txt).  Only for kernels in which every thread of the CTA runs the permutation
+// the same number of times.
+#if defined(__CUDA_ARCH__)
+#define LM_P1_BARRIER() do { if (SYNC) __syncthreads(); } while (0)
+#else
+#define LM_P1_BARRIER() do { } while (0)
+#endif
+template <int N_OUT, class Tab, bool SYNC = false>
 LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
   uint32_t a[16], x[16];
 
@@ -169,6 +179,7 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
     p1_mds_redc<16>(a, T.RC_INIT[r], T.RC_INIT_D[r], x);
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = x[i];
+    LM_P1_BARRIER();
   }
   // x = x' (state entering the partial section, first_rc already added), held at R^-39, lanes < p + 2^9
 
@@ -177,11 +188,13 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
 #pragma unroll
   for (int r = 0; r < 20; r++) d[r] = p1_dot16(x, T.G[r + 1], T.G_CONST[r + 1]).finish_lazy();
   uint32_t s0 = p1_dot16(x, T.G[0], 0).finish_lazy();
+  LM_P1_BARRIER();
 
   // lanes 1..15 leaving the section: start their accumulators with MI x' + const now, then x is dead
   uint32_t lane_lin[15];
 #pragma unroll
   for (int i = 0; i < 15; i++) lane_lin[i] = p1_dot16(x, T.MI[i], T.LANE_CONST[i]).finish_lazy();
+  LM_P1_BARRIER();
 
   uint32_t z[20];
 #pragma unroll
@@ -198,6 +211,7 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
       terms++;
     }
     s0 = kb_redc_lazy(kb_fold(acc));
+    if (r % 4 == 3) LM_P1_BARRIER();
   }
 
   a[0] = s0;
@@ -212,6 +226,7 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
       terms++;
     }
     a[i + 1] = kb_redc_lazy(kb_fold(acc));
+    if (i % 5 == 4) LM_P1_BARRIER();
   }
 
   // ---- 4 terminal full rounds (first round constant already inside a[]); three looped, the last one only
@@ -227,6 +242,7 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
     p1_mds_redc<16>(a, T.RC_TERM[r], T.RC_TERM_D[r], x);
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = x[i];
+    LM_P1_BARRIER();
   }
 #pragma unroll
   for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
@@ -236,12 +252,12 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
 }
 
 // compress_in_place: state <- permute(state) + state, only the first N_OUT lanes are produced.
-template <int N_OUT, class Tab>
+template <int N_OUT, class Tab, bool SYNC = false>
 LM_HD void p1_compress(uint32_t s[16], const Tab& T) {
   uint32_t in[N_OUT];
 #pragma unroll
   for (int i = 0; i < N_OUT; i++) in[i] = s[i];
-  p1_permute<N_OUT>(s, T);
+  p1_permute<N_OUT, Tab, SYNC>(s, T);
 #pragma unroll
   for (int i = 0; i < N_OUT; i++) s[i] = kb_add(s[i], in[i]);
 }
