@@ -143,6 +143,21 @@ typedef struct lm_air lm_air;
 int lm_air_new(lm_ctx* ctx, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
                const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
                const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5], lm_air** out);
+/* One row-range shard of a table split over several GPUs (leanmultisig_b200/sharded.py): cols hold the
+ * 2^log_rows rows of this shard, eq_factor the log_rows entries of the variables inside the shard, eq_scale the eq value
+ * of the shard's row-index prefix (multiplied into every weight, so the per-rank round sums only need adding up),
+ * halo_next_row[k] = first row of column k (k < n_shift) in the NEXT shard, the one-row halo of
+ * compute_shifted_columns (air_sumcheck.rs:683-694); NULL for the last shard (the last row repeats). */
+int lm_air_new_shard(lm_ctx* ctx, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
+                     const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
+                     const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5],
+                     const uint32_t* halo_next_row, const uint32_t eq_scale[5], lm_air** out);
+/* Session over already folded columns: cols_ef = (n_cols + n_shift) columns of 2^log_rows EF entries (5 words each,
+ * column after column).  Used for the last log2(G) rounds of a sharded sumcheck, after the all-gather of the per-shard
+ * column values. */
+int lm_air_new_folded(lm_ctx* ctx, uint32_t table_id, const uint32_t* cols_ef, uint32_t n_cols_total, uint32_t log_rows,
+                      const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
+                      const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5], lm_air** out);
 int lm_air_info(const lm_air* air, uint32_t* n_vars, uint32_t* degree, uint32_t* n_cols_total);
 /* out_evals: degree x 5 words = sum_j eq(j) C(row pair j at z) for z = 0, 2, 3, .., degree over the WHOLE
  * hypercube (no separate padding term), before the missing_mul_factor scaling (air_sumcheck.rs:242-249) */

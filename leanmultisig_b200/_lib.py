@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
             "lm_sc_commit_poly": [vp, u32, u32, C.POINTER(vp), u32p],
             "lm_sc_free": [vp],
             "lm_air_new": [vp, u32, C.POINTER(vp), u32, u32, u32p, u32p, u32, u32p, u32, u32p, C.POINTER(vp)],
+            "lm_air_new_shard": [vp, u32, C.POINTER(vp), u32, u32, u32p, u32p, u32, u32p, u32, u32p, u32p, u32p, C.POINTER(vp)],
+            "lm_air_new_folded": [vp, u32, u32p, u32, u32, u32p, u32p, u32, u32p, u32, u32p, C.POINTER(vp)],
             "lm_air_info": [vp, u32p, u32p, u32p],
             "lm_air_round": [vp, u32p],
             "lm_air_fold": [vp, u32p],

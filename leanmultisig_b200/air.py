@@ -26,23 +26,19 @@ def _p(a):
     return a.ctypes.data_as(u32p)
 
 
-class AirSumcheckSession:
-    def __init__(self, ctx, table_id: int, columns, eq_factor, sum_, alpha_powers, logup_alphas_eq_poly, bus_beta):
-        cols = [_u32(c) for c in columns]
-        n = cols[0].size
-        self._initial_n_vars = n.bit_length() - 1
-        assert all(c.size == n for c in cols) and n == 1 << self._initial_n_vars
+# (n_cols, n_shift, bare degree) per table_id & 0xff: execution/air.rs:42-55, extension_op/air.rs:44-57, poseidon_16/mod.rs:294-314
+AIR_SHAPES = {0: (20, 2, 5), 1: (29, 13, 6), 2: (109, 0, 10)}
+
+
+class OuterSumcheckHost:
+    """The host half of trait OuterSumcheckSession shared by the single-GPU and the sharded session: running sum,
+    missing_mul_factor, p(1) and the Lagrange step (air_sumcheck.rs:225-287).  Subclasses provide `_raw_round()`
+    (degree x 5 round sums over the whole hypercube) and `_fold(challenge)`."""
+
+    def _init_host(self, eq_factor, sum_, initial_n_vars: int, degree: int):
         eq = _u32(eq_factor).reshape(-1, 5)
-        assert eq.shape[0] == self._initial_n_vars
-        ap, la, beta = _u32(alpha_powers).reshape(-1, 5), _u32(logup_alphas_eq_poly).reshape(-1, 5), _u32(bus_beta)
-        ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
-        h = C.c_void_p()
-        check(lib().lm_air_new(ctx.handle, table_id, ptrs, len(cols), self._initial_n_vars, _p(eq), _p(ap), ap.shape[0],
-                               _p(la), la.shape[0], _p(beta), C.byref(h)))
-        self.handle = h
-        nv, deg, tot = C.c_uint32(), C.c_uint32(), C.c_uint32()
-        check(lib().lm_air_info(h, C.byref(nv), C.byref(deg), C.byref(tot)))
-        self._degree, self._n_cols_total = deg.value, tot.value
+        assert eq.shape[0] == initial_n_vars
+        self._initial_n_vars, self._degree = initial_n_vars, degree
         self.eq_factor = [F.from_monty(e) for e in eq]  # the last element is removed at each round
         self._sum = F.from_monty(sum_)
         self.missing_mul_factor = F.ONE
@@ -63,8 +59,7 @@ class AirSumcheckSession:
 
     def compute_bare_round_poly(self) -> np.ndarray:
         """coefficients (degree + 1) x 5 of the bare round polynomial"""
-        raw = np.empty((self._degree, 5), dtype=np.uint32)
-        check(lib().lm_air_round(self.handle, _p(raw)))
+        raw = self._raw_round()
         p_evals = [F.mul(F.from_monty(v), self.missing_mul_factor) for v in raw]
         alpha = self.eq_factor[-1]
         # p(1) from the running sum: sum = (1 - alpha) p(0) + alpha p(1)
@@ -80,9 +75,57 @@ class AirSumcheckSession:
         coeffs = [F.from_monty(c) for c in _u32(bare_poly).reshape(-1, 5)]
         self._sum = F.mul(F.poly_eval(coeffs, r), eq_eval)
         self.missing_mul_factor = F.mul(self.missing_mul_factor, eq_eval)
-        check(lib().lm_air_fold(self.handle, _p(_u32(challenge))))
+        self._fold(_u32(challenge))
         self.rounds_done += 1
         self.eq_factor.pop()
+
+
+class AirSumcheckSession(OuterSumcheckHost):
+    def __init__(self, ctx, table_id: int, columns, eq_factor, sum_, alpha_powers, logup_alphas_eq_poly, bus_beta, *,
+                 halo_next_row=None, eq_scale=None, folded_columns=None):
+        """columns: the table's base-field columns (natural row order).  Keyword forms used by the sharded session
+        (leanmultisig_b200/sharded.py): `halo_next_row` / `eq_scale` make this the session of ONE row-range shard
+        (lm_air_new_shard), `folded_columns` ((n_cols + n_shift) x rows x 5) starts from already folded EF columns
+        (lm_air_new_folded)."""
+        eq = _u32(eq_factor).reshape(-1, 5)
+        ap, la, beta = _u32(alpha_powers).reshape(-1, 5), _u32(logup_alphas_eq_poly).reshape(-1, 5), _u32(bus_beta)
+        h = C.c_void_p()
+        if folded_columns is not None:
+            fc = _u32(folded_columns)
+            assert fc.ndim == 3 and fc.shape[2] == 5
+            n = fc.shape[1]
+            n_vars = n.bit_length() - 1
+            assert n == 1 << n_vars and eq.shape[0] == n_vars
+            check(lib().lm_air_new_folded(ctx.handle, table_id, _p(fc), fc.shape[0], n_vars, _p(eq), _p(ap), ap.shape[0],
+                                          _p(la), la.shape[0], _p(beta), C.byref(h)))
+        else:
+            cols = [_u32(c) for c in columns]
+            n = cols[0].size
+            n_vars = n.bit_length() - 1
+            assert all(c.size == n for c in cols) and n == 1 << n_vars and eq.shape[0] == n_vars
+            ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+            if halo_next_row is None and eq_scale is None:
+                check(lib().lm_air_new(ctx.handle, table_id, ptrs, len(cols), n_vars, _p(eq), _p(ap), ap.shape[0],
+                                       _p(la), la.shape[0], _p(beta), C.byref(h)))
+            else:
+                halo = None if halo_next_row is None else _u32(halo_next_row)
+                scale = F.to_monty(F.ONE) if eq_scale is None else _u32(eq_scale)
+                check(lib().lm_air_new_shard(ctx.handle, table_id, ptrs, len(cols), n_vars, _p(eq), _p(ap), ap.shape[0],
+                                             _p(la), la.shape[0], _p(beta), None if halo is None else _p(halo), _p(scale),
+                                             C.byref(h)))
+        self.handle = h
+        nv, deg, tot = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().lm_air_info(h, C.byref(nv), C.byref(deg), C.byref(tot)))
+        self._n_cols_total = tot.value
+        self._init_host(eq, sum_, n_vars, deg.value)
+
+    def _raw_round(self) -> np.ndarray:
+        raw = np.empty((self._degree, 5), dtype=np.uint32)
+        check(lib().lm_air_round(self.handle, _p(raw)))
+        return raw
+
+    def _fold(self, challenge) -> None:
+        check(lib().lm_air_fold(self.handle, _p(challenge)))
 
     def final_column_evals(self) -> np.ndarray:
         out = np.empty((self._n_cols_total, 5), dtype=np.uint32)

@@ -226,7 +226,7 @@ size_t air_round_scratch_words(uint32_t log_n) {
 
 cudaError_t air_exec_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t dim, uint32_t log_n, const uint32_t* d_eq_point,
                            const uint32_t* alpha_powers, const uint32_t* la, uint32_t n_la, const uint32_t beta[5],
-                           uint32_t* d_scratch, uint32_t* d_out) {
+                           uint32_t* d_scratch, uint32_t* d_out, const uint32_t* eq_scale) {
   if (log_n < 1 || (dim != 1 && dim != 5) || n_la < 5 || n_la > 64) return cudaErrorInvalidValue;
   AirExtra X;
   for (int k = 0; k < 13; k++)
@@ -247,7 +247,7 @@ cudaError_t air_exec_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t
   uint32_t* d_part = d_lo + 5 * ((size_t)1 << lo_vars);
   const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
   cudaError_t e;
-  if ((e = eq_table(stream, d_eq_point, hi_vars, one, d_hi)) != cudaSuccess) return e;
+  if ((e = eq_table(stream, d_eq_point, hi_vars, eq_scale ? eq_scale : one, d_hi)) != cudaSuccess) return e;
   if ((e = eq_table(stream, d_eq_point + 5 * hi_vars, lo_vars, one, d_lo)) != cudaSuccess) return e;
   uint64_t blocks = (half + AIR_THREADS - 1) / AIR_THREADS;
   if (blocks > 148 * 8) blocks = 148 * 8;

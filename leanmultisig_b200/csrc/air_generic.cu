@@ -431,7 +431,8 @@ static cudaError_t launch_round(cudaStream_t stream, const uint32_t* d_cols, uin
 
 cudaError_t air_generic_round(cudaStream_t stream, uint32_t table, const uint32_t* d_cols, uint32_t dim, uint32_t log_n,
                               const uint32_t* d_eq_point, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* la,
-                              uint32_t n_la, const uint32_t beta[5], uint32_t* d_scratch, uint32_t* d_out) {
+                              uint32_t n_la, const uint32_t beta[5], uint32_t* d_scratch, uint32_t* d_out,
+                              const uint32_t* eq_scale) {
   uint32_t nc, ns, deg, maxc;
   if (!air_table_shape(table, &nc, &ns, &deg, &maxc) || (table & 0xffu) == 0) return cudaErrorInvalidValue;
   const int bus = (table & 0x100u) ? 0 : 1;
@@ -455,7 +456,7 @@ cudaError_t air_generic_round(cudaStream_t stream, uint32_t table, const uint32_
   uint32_t* d_part = d_lo + 5 * ((size_t)1 << lo_vars);
   const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
   cudaError_t e;
-  if ((e = eq_table(stream, d_eq_point, hi_vars, one, d_hi)) != cudaSuccess) return e;
+  if ((e = eq_table(stream, d_eq_point, hi_vars, eq_scale ? eq_scale : one, d_hi)) != cudaSuccess) return e;
   if ((e = eq_table(stream, d_eq_point + 5 * hi_vars, lo_vars, one, d_lo)) != cudaSuccess) return e;
   if ((table & 0xffu) == 1) return launch_round<ExtOpAir>(stream, d_cols, dim, n, half, d_hi, d_lo, lo_vars, X, d_part, d_out);
   return launch_round<Poseidon16Air>(stream, d_cols, dim, n, half, d_hi, d_lo, lo_vars, X, d_part, d_out);

@@ -156,6 +156,7 @@ struct lm_air {
   uint32_t* d_out = nullptr;
   std::vector<uint32_t> alpha, la;
   uint32_t beta[5] = {0, 0, 0, 0, 0};
+  uint32_t eq_scale[5] = {lm::KB_R1, 0, 0, 0, 0};  // constant factor of every eq weight (shard prefix), default 1
 };
 
 // Quotient-GKR session (reference: prove_gkr_quotient, crates/sub_protocols/src/quotient_gkr/mod.rs:31-141)
@@ -878,10 +879,13 @@ int lm_air_free(lm_air* a) {
   return LM_OK;
 }
 
-int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
-               const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* logup_alphas_eq,
-               uint32_t n_la, const uint32_t bus_beta[5], lm_air** out) {
-  if (!c || !cols || !eq_factor || !alpha_powers || !bus_beta || !out || (!logup_alphas_eq && n_la))
+// cols: base-field host columns (the shifted ones are derived, their last row taken from halo_next_row when the
+// session covers a row range that is not the last one), or cols_ef: all n_cols + n_shift columns already in EF.
+static int air_new_impl(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, const uint32_t* cols_ef, uint32_t n_cols,
+                        uint32_t log_rows, const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
+                        const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5],
+                        const uint32_t* halo_next_row, const uint32_t* eq_scale, lm_air** out) {
+  if (!c || (!cols && !cols_ef) || !eq_factor || !alpha_powers || !bus_beta || !out || (!logup_alphas_eq && n_la))
     return fail(LM_ERR_INVALID, "lm_air_new: null argument");
   *out = nullptr;
   uint32_t t_cols, t_shift, t_deg, t_maxc;
@@ -907,20 +911,31 @@ int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32
   a->alpha.assign(alpha_powers, alpha_powers + 5 * (size_t)n_alpha);
   a->la.assign(logup_alphas_eq, logup_alphas_eq + 5 * (size_t)n_la);
   memcpy(a->beta, bus_beta, sizeof(a->beta));
+  if (eq_scale) memcpy(a->eq_scale, eq_scale, sizeof(a->eq_scale));
   const uint64_t n = (uint64_t)1 << log_rows;
   const uint32_t all = a->n_cols + a->n_shift;
-  a->cols_words = (size_t)all * n;
+  a->dim = cols_ef ? 5 : 1;
+  a->cols_words = (size_t)all * n * a->dim;
   cudaError_t e = cudaMalloc(&a->d_cols, a->cols_words * sizeof(uint32_t));
-  for (uint32_t k = 0; e == cudaSuccess && k < a->n_cols; k++) {
-    if (!cols[k]) {
-      lm_air_free(a);
-      return fail(LM_ERR_INVALID, "lm_air_new: column %u is null", k);
+  if (cols_ef) {
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(a->d_cols, cols_ef, a->cols_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  } else {
+    for (uint32_t k = 0; e == cudaSuccess && k < a->n_cols; k++) {
+      if (!cols[k]) {
+        lm_air_free(a);
+        return fail(LM_ERR_INVALID, "lm_air_new: column %u is null", k);
+      }
+      e = cudaMemcpyAsync(a->d_cols + (size_t)k * n, cols[k], n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
     }
-    e = cudaMemcpyAsync(a->d_cols + (size_t)k * n, cols[k], n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    // shifted copies of the first n_shift columns (compute_shifted_columns, air_sumcheck.rs:683-694)
+    for (uint32_t k = 0; e == cudaSuccess && k < a->n_shift; k++) {
+      e = lm::air_shift_column(c->stream, a->d_cols + (size_t)k * n, n, a->d_cols + (size_t)(a->n_cols + k) * n);
+      if (e == cudaSuccess && halo_next_row)
+        e = cudaMemcpyAsync(a->d_cols + (size_t)(a->n_cols + k) * n + (n - 1), halo_next_row + k, sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, c->stream);
+    }
   }
-  // shifted copies of the first n_shift columns (compute_shifted_columns, air_sumcheck.rs:683-694)
-  for (uint32_t k = 0; e == cudaSuccess && k < a->n_shift; k++)
-    e = lm::air_shift_column(c->stream, a->d_cols + (size_t)k * n, n, a->d_cols + (size_t)(a->n_cols + k) * n);
   if (e == cudaSuccess) e = cudaMalloc(&a->d_eq, (size_t)log_rows * 5 * sizeof(uint32_t));
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(a->d_eq, eq_factor, (size_t)log_rows * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
@@ -933,6 +948,37 @@ int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32
   }
   *out = a;
   return LM_OK;
+}
+
+int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
+               const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* logup_alphas_eq,
+               uint32_t n_la, const uint32_t bus_beta[5], lm_air** out) {
+  if (!cols) return fail(LM_ERR_INVALID, "lm_air_new: null argument");
+  return air_new_impl(c, table_id, cols, nullptr, n_cols, log_rows, eq_factor, alpha_powers, n_alpha, logup_alphas_eq, n_la,
+                      bus_beta, nullptr, nullptr, out);
+}
+
+int lm_air_new_shard(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
+                     const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
+                     const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5],
+                     const uint32_t* halo_next_row, const uint32_t eq_scale[5], lm_air** out) {
+  if (!cols) return fail(LM_ERR_INVALID, "lm_air_new_shard: null argument");
+  return air_new_impl(c, table_id, cols, nullptr, n_cols, log_rows, eq_factor, alpha_powers, n_alpha, logup_alphas_eq, n_la,
+                      bus_beta, halo_next_row, eq_scale, out);
+}
+
+int lm_air_new_folded(lm_ctx* c, uint32_t table_id, const uint32_t* cols_ef, uint32_t n_cols_total, uint32_t log_rows,
+                      const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
+                      const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5], lm_air** out) {
+  if (!cols_ef) return fail(LM_ERR_INVALID, "lm_air_new_folded: null argument");
+  uint32_t t_cols, t_shift, t_deg, t_maxc;
+  if (!lm::air_table_shape(table_id, &t_cols, &t_shift, &t_deg, &t_maxc))
+    return fail(LM_ERR_INVALID, "lm_air_new_folded: unknown table id 0x%x", table_id);
+  if (n_cols_total != t_cols + t_shift)
+    return fail(LM_ERR_INVALID, "lm_air_new_folded: table %u has %u columns incl. shifted ones, got %u", table_id & 0xffu,
+                t_cols + t_shift, n_cols_total);
+  return air_new_impl(c, table_id, nullptr, cols_ef, t_cols, log_rows, eq_factor, alpha_powers, n_alpha, logup_alphas_eq,
+                      n_la, bus_beta, nullptr, nullptr, out);
 }
 
 int lm_dev_poseidon16_fill_trace(lm_ctx* c, uint32_t* d_cols, uint64_t n_rows) {
@@ -978,11 +1024,11 @@ int lm_air_round(lm_air* a, uint32_t* out_evals) {
   CU(cudaSetDevice(c->device));
   if (a->table_id == 0)
     CU(lm::air_exec_round(c->stream, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(), a->la.data(),
-                          (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch, a->d_out));
+                          (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch, a->d_out, a->eq_scale));
   else
     CU(lm::air_generic_round(c->stream, a->table_id, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(),
                              (uint32_t)(a->alpha.size() / 5), a->la.data(), (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch,
-                             a->d_out));
+                             a->d_out, a->eq_scale));
   CU(cudaMemcpyAsync(out_evals, a->d_out, (size_t)a->degree * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return LM_OK;

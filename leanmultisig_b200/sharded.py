@@ -1,4 +1,4 @@
-"""Row-sharded WHIR commit across the GPUs of one node.
+"""Row-sharded WHIR commit and row-sharded AIR sumcheck across the GPUs of one node.
 
 One process per GPU (`torch.distributed`, NCCL over NVLink; gloo in the CPU tests).  The stacked polynomial has
 index (column c | position s); rank q holds, for every column, the slice of s whose top g = log2(world) bits equal q.
@@ -11,12 +11,26 @@ index (column c | position s); rank q holds, for every column, the slice of s wh
                 (lm_dev_dft_layers_mapped).  Rank q' ends up with G runs of `run` consecutive codeword rows.
   4. Merkle     leaf sponge + subtree per run (local), all-gather of the G^2 subtree roots (32 B each), the top
                 2g levels are replicated.
+
+AIR sumcheck (`ShardedAirSumcheckSession`): rank q holds rows [q 2^(n-g), (q+1) 2^(n-g)) of every column of a table.  The
+session folds the least-significant row bit first (air_sumcheck.rs:144-151), so the first n - g rounds touch only local
+rows: every rank computes the round sums of its shard with the eq weight of its row prefix already multiplied in
+(lm_air_new_shard), ONE all-reduce of degree x 5 field words per round adds them up, and the fold is local.  The shifted
+("next row") columns need the first row of the next shard once, at setup (compute_shifted_columns, :683-694).  After
+n - g rounds every rank is left with one EF value per column: an all-gather of (n_cols + n_shift) x 5 words builds the
+2^g-row table on which the last g rounds run replicated (lm_air_new_folded).
+
 The compute steps go through a backend object so that the CPU test tier can run the same orchestration with the
 oracle over gloo; the product backend is the CUDA library (`CudaBackend`), there is no CPU product path.
 """
 from __future__ import annotations
 
 import numpy as np
+
+from . import field as F
+from .air import AIR_SHAPES, OuterSumcheckHost
+
+P = 0x7F000001
 
 
 def shard_of(evals: np.ndarray, n_vars: int, folding: int, rank: int, world: int) -> np.ndarray:
@@ -116,6 +130,73 @@ class ShardedCommit:
         return full, np.stack(path)
 
 
+class ShardedAirSumcheckSession(OuterSumcheckHost):
+    """trait OuterSumcheckSession (air_sumcheck.rs:34-42) over one row-range shard per rank.  Collective: every rank
+    constructs it with its rows and then makes the same calls with the same challenges (the transcript is replicated);
+    `prove_batched_air_sumcheck` drives it unchanged."""
+
+    def __init__(self, backend, dist, table_id: int, shard_columns, eq_factor, sum_, alpha_powers, logup_alphas_eq_poly,
+                 bus_beta):
+        self.b, self.dist = backend, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        g = self.world.bit_length() - 1
+        assert self.world == 1 << g, "world size must be a power of two"
+        n_cols, n_shift, degree = AIR_SHAPES[table_id & 0xFF]
+        cols = [np.ascontiguousarray(c, dtype=np.uint32) for c in shard_columns]
+        assert len(cols) == n_cols
+        local_rows = cols[0].size
+        self.local_vars = local_rows.bit_length() - 1
+        assert local_rows == 1 << self.local_vars and self.local_vars >= 1, "a shard needs at least two rows"
+        self.g = g
+        eq = np.ascontiguousarray(eq_factor, dtype=np.uint32).reshape(-1, 5)
+        assert eq.shape[0] == self.local_vars + g
+        self._args = (table_id, np.ascontiguousarray(alpha_powers, dtype=np.uint32).reshape(-1, 5),
+                      np.ascontiguousarray(logup_alphas_eq_poly, dtype=np.uint32).reshape(-1, 5),
+                      np.ascontiguousarray(bus_beta, dtype=np.uint32))
+        self._eq_top = eq[:g]
+        # one-row halo: first row of the shifted columns' sources on the next rank
+        halo = None
+        if n_shift and self.world > 1:
+            first = np.array([c[0] for c in cols[:n_shift]], dtype=np.uint32)
+            everyone = backend.all_gather_words(dist, first)
+            if self.rank + 1 < self.world:
+                halo = everyone[self.rank + 1]
+        # eq value of this rank's row prefix: the top g variables are the bits of the rank, most significant first
+        scale = F.ONE
+        for k in range(g):
+            e = F.from_monty(eq[k])
+            scale = F.mul(scale, e if (self.rank >> (g - 1 - k)) & 1 else F.sub(F.ONE, e))
+        self.local = backend.air_session(table_id, cols, eq[g:], *self._args[1:], halo_next_row=halo, eq_scale=F.to_monty(scale))
+        self.tail = None
+        self._init_host(eq, sum_, self.local_vars + g, degree)
+
+    def _raw_round(self) -> np.ndarray:
+        if self.rounds_done < self.local_vars:
+            raw = self.local._raw_round()
+            return self.b.all_reduce_field(self.dist, raw) if self.world > 1 else raw
+        return self.tail._raw_round()
+
+    def _fold(self, challenge) -> None:
+        if self.rounds_done < self.local_vars:
+            self.local._fold(challenge)
+            if self.rounds_done + 1 == self.local_vars and self.g:
+                mine = self.local.final_column_evals()                         # (n_cols + n_shift) x 5
+                table = self.b.all_gather_words(self.dist, mine)               # world x (n_cols + n_shift) x 5
+                folded = np.ascontiguousarray(table.transpose(1, 0, 2))        # column x row (= rank) x 5
+                self.tail = self.b.air_session(self._args[0], None, self._eq_top, *self._args[1:], folded_columns=folded)
+        else:
+            self.tail._fold(challenge)
+
+    def final_column_evals(self) -> np.ndarray:
+        return (self.tail if self.g else self.local).final_column_evals()
+
+    def free(self):
+        for s in (self.local, self.tail):
+            if s is not None:
+                s.free()
+        self.local = self.tail = None
+
+
 class CudaBackend:
     """Compute steps on one GPU through the C ABI; tensors are torch CUDA int32 (device memory + NCCL plumbing)."""
 
@@ -188,3 +269,23 @@ class CudaBackend:
             self.check(self.lib.lm_dev_merkle_levels(self.ctx.handle, layers.data_ptr(), n))
         self.ctx.sync()
         return layers
+
+    # ---- AIR sumcheck -----------------------------------------------------------------------------------------
+    def air_session(self, table_id, columns, eq_factor, alpha_powers, la, beta, **kw):
+        from .air import AirSumcheckSession
+
+        zero = np.zeros(5, dtype=np.uint32)  # the running sum lives in the sharded session, not in the per-rank ones
+        return AirSumcheckSession(self.ctx, table_id, columns, eq_factor, zero, alpha_powers, la, beta, **kw)
+
+    def all_reduce_field(self, dist, words: np.ndarray) -> np.ndarray:
+        """sum mod p over the ranks of an array of Montgomery residues (one NCCL all-reduce on widened words)"""
+        t = self.torch.from_numpy(np.ascontiguousarray(words).astype(np.int64)).cuda()
+        dist.all_reduce(t)
+        return (t.cpu().numpy() % P).astype(np.uint32).reshape(words.shape)
+
+    def all_gather_words(self, dist, words: np.ndarray) -> np.ndarray:
+        world = dist.get_world_size()
+        t = self.torch.from_numpy(np.ascontiguousarray(words).view(np.int32)).cuda()
+        out = self.torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy().view(np.uint32)

@@ -11,6 +11,7 @@ import pytest
 import oracle as O
 from oracle import whir as W
 from leanmultisig_b200 import field as F
+P = 0x7F000001
 
 ONE_M = int(O.to_monty(1))
 
@@ -325,3 +326,45 @@ def test_gpu_prove_poseidon_16_end_to_end(ctx, rng, log_n_rows):
     padded_v = [W.fm(v) for v in col_evals_v] + [W.ZERO] * ((1 << log_cols) - n_cols)
     stm_v = W.SparseStatement.dense(betas_v + natural_v, W.mle_eval_small(padded_v, betas_v))
     W.verify(cfg_o, vs, pc, [stm_v])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("table,L,G", [(0, 6, 2), (1, 5, 4), (2, 4, 2)])
+def test_gpu_air_shard_sessions_add_up_to_the_whole_table(ctx, rng, table, L, G):
+    """lm_air_new_shard / lm_air_new_folded on ONE device: G row-range shard sessions (halo row + prefix eq scale), their round
+    sums added mod p, equal the oracle's rounds over the whole table; the gathered column values continue in a folded
+    session (what leanmultisig_b200/sharded.py does across ranks)."""
+    import leanmultisig_b200 as lm
+
+    n_cols, n_shift, deg = O.air_shape(table)
+    g = G.bit_length() - 1
+    base = O.random_field(rng, (n_cols, 1 << L))
+    cols = with_shifts(table, base)
+    eq_factor = O.random_field(rng, (L, 5))
+    ap, la, beta = extras(rng)
+    challenges = O.random_field(rng, (L, 5))
+    raws, finals = oracle_rounds(table, cols, eq_factor, ap, la, beta, challenges)
+    per = (1 << L) // G
+    zero = np.zeros(5, dtype=np.uint32)
+    shards = []
+    for q in range(G):
+        scale = F.ONE
+        for k in range(g):
+            e = F.from_monty(eq_factor[k])
+            scale = F.mul(scale, e if (q >> (g - 1 - k)) & 1 else F.sub(F.ONE, e))
+        halo = base[:n_shift, (q + 1) * per] if q + 1 < G and n_shift else None
+        shards.append(lm.AirSumcheckSession(ctx, table, [base[c, q * per:(q + 1) * per] for c in range(n_cols)], eq_factor[g:],
+                                            zero, ap, la, beta, halo_next_row=halo, eq_scale=F.to_monty(scale)))
+    for r in range(L - g):
+        total = sum(s._raw_round().astype(np.int64) for s in shards) % P
+        assert np.array_equal(total.astype(np.uint32), raws[r]), f"round {r}"
+        for s in shards:
+            s._fold(challenges[r])
+    table_g = np.stack([s.final_column_evals() for s in shards]).transpose(1, 0, 2)
+    tail = lm.AirSumcheckSession(ctx, table, None, eq_factor[:g], zero, ap, la, beta, folded_columns=table_g)
+    for r in range(L - g, L):
+        assert np.array_equal(tail._raw_round(), raws[r]), f"round {r}"
+        tail._fold(challenges[r])
+    assert np.array_equal(tail.final_column_evals(), finals)
+    for s in shards + [tail]:
+        s.free()
