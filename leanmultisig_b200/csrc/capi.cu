@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -491,25 +492,29 @@ static int commit_impl(lm_ctx* c, const uint32_t* evals, bool evals_on_device, u
     CUT(lm::merkle_leaf_digests(c->stream, t->d_codeword, t->height, t->stored_width, t->full_width, t->effective_width,
                                 t->d_layers));
   } else {
-    const uint32_t n_groups = eff_w / 8 < 8 ? eff_w / 8 : 8;       // at most 8 column groups in flight
-    const uint32_t cols_per_group = (eff_w / 8 + n_groups - 1) / n_groups * 8;
+    // Column groups of 1, 1, 2, 4, 8, .. rate chunks (8 columns each): the first copy is short, every later copy is
+    // hidden behind the transform + hash of the groups before it, and the wide groups absorb several chunks per launch.
+    static const bool even_groups = getenv("LM_COMMIT_EVEN_GROUPS") != nullptr;  // A/B switch: 8 equal groups
     if (need_words > live_words)
       CUT(cudaMemsetAsync(t->d_evals + live_words, 0, (need_words - live_words) * sizeof(uint32_t), c->stream));
     CUT(cudaEventRecord(c->ev_start, c->stream));
     CUT(cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
-    uint32_t g = 0;
-    for (int64_t col_end = eff_w; col_end > 0; col_end -= cols_per_group, g++) {
-      const uint32_t col_begin = col_end > (int64_t)cols_per_group ? (uint32_t)(col_end - cols_per_group) : 0u;
-      const uint32_t count = (uint32_t)col_end - col_begin;
+    const uint32_t n_chunks = eff_w / 8;
+    uint32_t g = 0, next = 1;
+    for (uint32_t chunk_end = n_chunks; chunk_end > 0; g++) {
+      uint32_t take = even_groups ? (n_chunks + 7) / 8 : next;
+      if (take > chunk_end) take = chunk_end;
+      if (g >= 1 && !even_groups) next *= 2;
+      const uint32_t col_begin = (chunk_end - take) * 8, count = take * 8;
       CUT(cudaMemcpyAsync(t->d_evals + (size_t)col_begin * block_len, evals + (size_t)col_begin * block_len,
                           (size_t)count * block_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
       CUT(cudaEventRecord(c->ev_copy[g % 8], c->copy_stream));
       CUT(cudaStreamWaitEvent(c->stream, c->ev_copy[g % 8], 0));
       CUT(lm::ntt_reorder_and_dft_cols(c->stream, t->d_evals, n_vars, folding, log_inv_rate, (uint32_t)dft_cols, col_begin,
                                        count, t->d_codeword, c->d_tw, c->tw_log_n));
-      for (int64_t chunk = (int64_t)(col_begin + count) / 8 - 1; chunk >= (int64_t)col_begin / 8; chunk--)
-        CUT(lm::merkle_leaf_absorb_chunk(c->stream, t->d_codeword, t->height, stored_w, full_w, eff_w, (uint32_t)chunk,
-                                         t->d_layers));
+      CUT(lm::merkle_leaf_absorb_chunks(c->stream, t->d_codeword, t->height, stored_w, full_w, eff_w, chunk_end - 1, take,
+                                        t->d_layers));
+      chunk_end -= take;
     }
   }
   CUT(lm::merkle_tree_from_digests(c->stream, t->d_layers, t->height));

@@ -7,8 +7,8 @@
 // Values crossing any kernel boundary are canonical in [0, p), exactly what the reference stores
 // (monty_31.rs:32-42), so results are bit-identical whatever instruction sequence produced them.
 //
-// Instruction notes (sm_100a): a Montgomery product is IMAD.WIDE.U32 (a*b), IMAD (m = lo * -p^-1),
-// IMAD.WIDE.U32 (m*p + t) and the high word is the result in [0, 2p); canonicalisation is IADD + IMNMX.U32.
+// Instruction notes (sm_100a): a Montgomery product is IMAD.WIDE.U32 (a*b), two SHF + IADD3 (m = lo * p^-1),
+// IMAD.WIDE.U32 (m*p), IADD3 (hi - hi + p) with the result in (0, 2p]; canonicalisation is one VIADDMNMX.U32.
 #pragma once
 #include <cstdint>
 
@@ -54,10 +54,12 @@ struct KbOpaque {
   uint32_t p;
   uint32_t mds[16];
   double mds_d[16];
+  uint32_t s24, s31;  // shift amounts of p^-1 = 2^31 + 2^24 + 1, opaque so that ptxas keeps the shifts (see kb_redc_lazy)
 };
 static __constant__ KbOpaque c_kb = {KB_P,
                                      {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1},
-                                     {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1}};
+                                     {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1},
+                                     24, 31};
 #endif
 #ifdef __CUDA_ARCH__
 #define LM_KB_P_OPAQUE (c_kb.p)
@@ -84,12 +86,28 @@ LM_HD uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
 #endif
 }
 
-// Montgomery reduction without the final conditional subtraction:
-// returns (t + m p) / 2^32  <  t / 2^32 + p.   Requires t < 2^64 - 2^32 p.
+// Montgomery reduction without the final conditional subtraction: returns a value congruent to t / 2^32 in
+// (t / 2^32, t / 2^32 + p].  Requires t < 2^64 - 2^32 p.
+// Device form (monty_reduce of the reference, utils.rs:107-127, with the borrow replaced by + p): m = lo(t) p^-1 mod 2^32
+// and p^-1 = 2^31 + 2^24 + 1, so m is two shifts and a 3-input add on the ALU pipe instead of an IMAD on the
+// multiplier pipe every kernel here is bound by; u = m p has the same low word as t, hence (t - u) / 2^32 =
+// hi(t) - hi(u) with no carry chain.  The shift amounts come from constant memory: with literals ptxas folds the
+// shifts back into IMAD lo, 0x81000001.  Per reduction: 4 multiplier-pipe cycles instead of 6 (IMAD 2 + IMAD.WIDE 4).
 LM_HD uint32_t kb_redc_lazy(uint64_t t) {
+#if defined(__CUDA_ARCH__) && !defined(LM_REDC_OLD)
+  const uint32_t lo = (uint32_t)t;
+#ifdef LM_REDC_SHIFTS
+  const uint32_t m = lo + (lo << c_kb.s24) + (lo << c_kb.s31);
+#else
+  const uint32_t m = lo * 0x81000001u;
+#endif
+  const uint64_t u = mul_wide(m, c_kb.p);
+  return (uint32_t)(t >> 32) - (uint32_t)(u >> 32) + c_kb.p;
+#else
   uint32_t m = (uint32_t)t * KB_NEG_MU;
   uint64_t t2 = mad_wide(m, LM_KB_P_OPAQUE, t);
   return (uint32_t)(t2 >> 32);
+#endif
 }
 // a * b * 2^-32 mod p, result in [0, 2p) provided a * b < 2^32 p (e.g. a < 2p, b < p or both < 1.43p).
 LM_HD uint32_t kb_mul_lazy(uint32_t a, uint32_t b) { return kb_redc_lazy(mul_wide(a, b)); }

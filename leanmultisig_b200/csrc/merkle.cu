@@ -14,6 +14,7 @@
 //                        every intermediate layer (all layers are retained for openings).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include "launch_count.h"
 #include "merkle.h"
 #include "poseidon1.cuh"
@@ -38,6 +39,9 @@ static const P1Tables h_p1 =
 #ifndef LEAF_SYNC
 #define LEAF_SYNC 1
 #endif
+#ifndef LEAF_DEFAULT_GRID
+#define LEAF_DEFAULT_GRID 0
+#endif
 
 struct State16 {
   uint32_t v[16];
@@ -61,80 +65,95 @@ __device__ __forceinline__ void load_chunk8(const uint32_t* __restrict__ row, in
   }
 }
 
+// Grid-stride over blocks of LEAF_THREADS rows: the launcher may start one CTA per block or a persistent grid (a multiple
+// of the SM count) whose CTAs keep the ~100 KiB permutation hot in the instruction cache.
 __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
 leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t lim, uint32_t virt_w,
                    int from_state, State16 init, uint32_t* __restrict__ digests) {
-  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = r < h;
-  if (!live) r = h - 1;  // every thread runs the sponge (CTA-wide barriers inside the permutation); no store
-  const uint32_t* row = mat + r * stored_w;
   const bool vec_ok = (stored_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mat) & 15) == 0);
-  uint32_t s[16];
-  // One compression call site (the unrolled permutation is ~100 KiB of code): the sponge absorbs rate chunks
-  // n-1, n-2, ..., 0 into lanes 8..15; without a precomputed state the first compression also takes chunk n-2
-  // as lanes 0..7, so the chunk sequence is n-1, n-3, n-4, ...
   const int64_t n_chunks = virt_w / 8;
-  int64_t chunk = n_chunks - 1, n_comp = n_chunks;
-  if (from_state) {
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < h; base += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = base + threadIdx.x;
+    const bool live = r < h;
+    if (!live) r = h - 1;  // every thread runs the sponge (CTA-wide barriers inside the permutation); no store
+    const uint32_t* row = mat + r * stored_w;
+    uint32_t s[16];
+    // One compression call site (the unrolled permutation is ~100 KiB of code): the sponge absorbs rate chunks
+    // n-1, n-2, ..., 0 into lanes 8..15; without a precomputed state the first compression also takes chunk n-2
+    // as lanes 0..7, so the chunk sequence is n-1, n-3, n-4, ...
+    int64_t chunk = n_chunks - 1, n_comp = n_chunks;
+    if (from_state) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = init.v[i];
-  } else {
-    load_chunk8(row, 8 * (n_chunks - 2), lim, vec_ok, s);
-    n_comp = n_chunks - 1;
+      for (int i = 0; i < 16; i++) s[i] = init.v[i];
+    } else {
+      load_chunk8(row, 8 * (n_chunks - 2), lim, vec_ok, s);
+      n_comp = n_chunks - 1;
+    }
+    for (int64_t it = 0; it < n_comp; it++) {
+      load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
+      p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
+      chunk -= (it == 0 && !from_state) ? 2 : 1;
+    }
+    if (live) {
+      uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
+      out[0] = make_uint4(s[0], s[1], s[2], s[3]);
+      out[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
   }
-  for (int64_t it = 0; it < n_comp; it++) {
-    load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
-    p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
-    chunk -= (it == 0 && !from_state) ? 2 : 1;
-  }
-  if (!live) return;
-  uint4* out = reinterpret_cast<uint4*>(digests + 8 * r);
-  out[0] = make_uint4(s[0], s[1], s[2], s[3]);
-  out[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
-// One sponge step for every row: state (lanes 0..7, kept in the digest buffer between steps) absorbs rate chunk
-// `chunk` of the row.  Lets the commit hash columns as soon as they are transformed, right to left, while the
-// host-to-device copy of the columns further left is still in flight.
+// `count` sponge steps for every row: state (lanes 0..7, kept in the digest buffer between launches) absorbs rate chunks
+// chunk_hi, chunk_hi - 1, ..., chunk_hi - count + 1 of the row.  Lets the commit hash columns as soon as they are
+// transformed, right to left, while the host-to-device copy of the columns further left is still in flight.
 __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
-leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t chunk, int first, State16 init,
-                   uint32_t* __restrict__ digests) {
-  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = r < h;
-  if (!live) r = h - 1;
-  uint32_t s[16];
-  uint4* dg = reinterpret_cast<uint4*>(digests + 8 * r);
-  if (first) {
+leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t chunk_hi, uint32_t count, int first,
+                   State16 init, uint32_t* __restrict__ digests) {
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < h; base += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = base + threadIdx.x;
+    const bool live = r < h;
+    if (!live) r = h - 1;
+    uint32_t s[16];
+    uint4* dg = reinterpret_cast<uint4*>(digests + 8 * r);
+    if (first) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = init.v[i];
-  } else {
-    const uint4 a = dg[0], b = dg[1];
-    s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
+      for (int i = 0; i < 8; i++) s[i] = init.v[i];
+    } else {
+      const uint4 a = dg[0], b = dg[1];
+      s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(mat + r * stored_w + 8 * chunk_hi);
+    for (uint32_t k = 0; k < count; k++, src -= 2) {
+      const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+      s[8] = lo.x, s[9] = lo.y, s[10] = lo.z, s[11] = lo.w, s[12] = hi.x, s[13] = hi.y, s[14] = hi.z, s[15] = hi.w;
+      p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
+    }
+    if (live) {
+      dg[0] = make_uint4(s[0], s[1], s[2], s[3]);
+      dg[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
   }
-  const uint4* src = reinterpret_cast<const uint4*>(mat + r * stored_w + 8 * chunk);
-  const uint4 lo = __ldg(src), hi = __ldg(src + 1);
-  s[8] = lo.x, s[9] = lo.y, s[10] = lo.z, s[11] = lo.w, s[12] = hi.x, s[13] = hi.y, s[14] = hi.z, s[15] = hi.w;
-  p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
-  if (!live) return;
-  dg[0] = make_uint4(s[0], s[1], s[2], s[3]);
-  dg[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
 // One level: next[i] = C(prev[2i] || prev[2i+1])[0..8), one thread per parent.  Used while a level still fills
 // the machine; the short tail of the tree goes through tree_levels_kernel below.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
 tree_level_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* __restrict__ next) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_next) return;
-  uint32_t s[16];
-  const uint4* src = reinterpret_cast<const uint4*>(prev + 16 * i);
-  const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
-  s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
-  s[8] = c.x, s[9] = c.y, s[10] = c.z, s[11] = c.w, s[12] = d.x, s[13] = d.y, s[14] = d.z, s[15] = d.w;
-  p1_compress<8>(s, c_p1);
-  uint4* dst = reinterpret_cast<uint4*>(next + 8 * i);
-  dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
-  dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n_next; base += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t i = base + threadIdx.x;
+    const bool live = i < n_next;
+    if (!live) i = n_next - 1;  // CTA-wide barriers inside the permutation: every thread runs it
+    uint32_t s[16];
+    const uint4* src = reinterpret_cast<const uint4*>(prev + 16 * i);
+    const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+    s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
+    s[8] = c.x, s[9] = c.y, s[10] = c.z, s[11] = c.w, s[12] = d.x, s[13] = d.y, s[14] = d.z, s[15] = d.w;
+    p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
+    if (live) {
+      uint4* dst = reinterpret_cast<uint4*>(next + 8 * i);
+      dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
+      dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+  }
 }
 
 // layer0: n0 digests (n0 = 2 * T * gridDim.x at full size). CTA b owns digests [b*2T, (b+1)*2T) and writes
@@ -192,6 +211,16 @@ static State16 zero_suffix_state_host(uint32_t n_zero_chunks) {
   return st;
 }
 
+// CTAs of a leaf kernel over h rows: one per LEAF_THREADS rows, capped at LM_LEAF_GRID (environment, 0 = no cap) CTAs
+static uint64_t leaf_grid(uint64_t h) {
+  static const long cap = [] {
+    const char* e = getenv("LM_LEAF_GRID");
+    return e ? atol(e) : (long)LEAF_DEFAULT_GRID;
+  }();
+  const uint64_t blocks = (h + LEAF_THREADS - 1) / LEAF_THREADS;
+  return cap > 0 && blocks > (uint64_t)cap ? (uint64_t)cap : blocks;
+}
+
 cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
                                 uint32_t full_w, uint32_t eff_w, uint32_t* d_digests) {
   if (h == 0) return cudaSuccess;
@@ -210,7 +239,7 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
     virt_w = full_w;
   }
   const int T = LEAF_THREADS;
-  const uint64_t blocks = (h + T - 1) / T;
+  const uint64_t blocks = leaf_grid(h);
   leaf_sponge_kernel<<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests); count_launch();
   return cudaGetLastError();
 }
@@ -219,15 +248,18 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
 bool merkle_leaf_chunked_ok(uint32_t stored_w, uint32_t full_w, uint32_t eff_w) {
   return full_w % 8 == 0 && eff_w % 8 == 0 && stored_w % 8 == 0 && eff_w <= stored_w && eff_w > 0 && (full_w - eff_w) / 8 >= 2;
 }
-// absorb chunk `chunk` (chunks must be fed from eff_w / 8 - 1 down to 0); the first call seeds the state
-cudaError_t merkle_leaf_absorb_chunk(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
-                                     uint32_t full_w, uint32_t eff_w, uint32_t chunk, uint32_t* d_digests) {
-  if (!merkle_leaf_chunked_ok(stored_w, full_w, eff_w) || chunk >= eff_w / 8) return cudaErrorInvalidValue;
-  const int first = chunk == eff_w / 8 - 1;
+// absorb chunks chunk_hi, chunk_hi - 1, .., chunk_hi - count + 1 (chunks must be fed from eff_w / 8 - 1 down to 0); the
+// call that takes chunk eff_w / 8 - 1 seeds the state
+cudaError_t merkle_leaf_absorb_chunks(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
+                                      uint32_t full_w, uint32_t eff_w, uint32_t chunk_hi, uint32_t count, uint32_t* d_digests) {
+  if (!merkle_leaf_chunked_ok(stored_w, full_w, eff_w) || chunk_hi >= eff_w / 8 || count == 0 || count > chunk_hi + 1)
+    return cudaErrorInvalidValue;
+  if (h == 0) return cudaSuccess;
+  const int first = chunk_hi == eff_w / 8 - 1;
   State16 init{};
   if (first) init = zero_suffix_state_host((full_w - eff_w) / 8);
-  leaf_absorb_kernel<<<(unsigned)((h + LEAF_THREADS - 1) / LEAF_THREADS), LEAF_THREADS, 0, stream>>>(d_mat, h, stored_w, chunk, first,
-                                                                                                       init, d_digests);
+  leaf_absorb_kernel<<<(unsigned)leaf_grid(h), LEAF_THREADS, 0, stream>>>(d_mat, h, stored_w, chunk_hi, count, first, init,
+                                                                          d_digests);
   count_launch();
   return cudaGetLastError();
 }
@@ -240,7 +272,8 @@ cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, ui
   // wide levels: one launch per level, every thread busy
   while (n / 2 >= 8192) {
     uint32_t* next = cur + 8 * n;
-    tree_level_kernel<<<(unsigned)((n / 2 + 127) / 128), 128, 0, stream>>>(cur, n / 2, next); count_launch();
+    tree_level_kernel<<<(unsigned)((n / 2 + LEAF_THREADS - 1) / LEAF_THREADS), LEAF_THREADS, 0, stream>>>(cur, n / 2, next);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     cur = next;

@@ -9,8 +9,8 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
                                 uint32_t full_w, uint32_t eff_w, uint32_t* d_digests);
 // chunk-at-a-time variant of the leaf sponge (columns hashed as soon as they exist, right to left)
 bool merkle_leaf_chunked_ok(uint32_t stored_w, uint32_t full_w, uint32_t eff_w);
-cudaError_t merkle_leaf_absorb_chunk(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
-                                     uint32_t full_w, uint32_t eff_w, uint32_t chunk, uint32_t* d_digests);
+cudaError_t merkle_leaf_absorb_chunks(cudaStream_t stream, const uint32_t* d_mat, uint64_t h, uint32_t stored_w,
+                                      uint32_t full_w, uint32_t eff_w, uint32_t chunk_hi, uint32_t count, uint32_t* d_digests);
 // d_layers holds (2h - 1) digests: layer 0 (h leaf digests, already filled) then h/2, ..., 1.
 cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, uint64_t h);
 // rows (n x full_w, zero-extended) and sibling paths (n x log2(h) x 8, leaf level first) of n leaf indices
