@@ -189,6 +189,15 @@ typedef struct lm_gkr lm_gkr;
 int lm_finger_print(lm_ctx* ctx, const uint32_t* data, uint64_t n_rows, uint32_t n_data, const uint32_t* alphas,
                     const uint32_t c[5], uint32_t* out);
 int lm_gkr_new(lm_ctx* ctx, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, lm_gkr** out);
+/* One row-range shard of the fraction table split over several GPUs (leanmultisig_b200/sharded.py): the shard
+ * has 2^n_vars rows of which the first active_len (possibly 0) are given, the rest are (0, 1); the up pass stops at
+ * 2^top_vars fractions per shard (5 - log2(G), so that the gathered tops are the 2^5 values the prover sends). */
+int lm_gkr_new_shard(lm_ctx* ctx, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, uint32_t n_vars,
+                     uint32_t top_vars, lm_gkr** out);
+/* lm_gkr_layer_begin on a shard: point holds the claim_vars coordinates inside the shard, eq_scale the eq value of the
+ * shard's row prefix (multiplied into every weight, so that the per-rank (c0, c2) only need adding up). */
+int lm_gkr_layer_begin_shard(lm_gkr* gkr, uint32_t claim_vars, const uint32_t* claim_point, const uint32_t alpha[5],
+                             const uint32_t eq_scale[5]);
 int lm_gkr_num_vars(const lm_gkr* gkr, uint32_t* n_vars);
 /* the 2^5 numerators and denominators of the top layer, 32 x 5 words each (mod.rs:64-66) */
 int lm_gkr_top(lm_gkr* gkr, uint32_t* top_nums, uint32_t* top_dens);

@@ -175,6 +175,8 @@ struct lm_gkr {
   uint32_t cur_vars = 0;  // variables still unbound in the working columns
   int cur_src = 0, cur_buf = 0;
   uint32_t alpha[5] = {0, 0, 0, 0, 0};
+  uint32_t top_vars = 5;                             // the up pass stops at 2^top_vars fractions
+  uint32_t eq_scale[5] = {lm::KB_R1, 0, 0, 0, 0};    // constant factor of the current layer's eq weights (shards)
 };
 static const uint32_t LM_GKR_TOP_VARS = 5;  // N_VARS_TO_SEND_GKR_COEFFS (crates/sub_protocols/src/lib.rs:14)
 
@@ -1092,7 +1094,8 @@ int lm_gkr_free(lm_gkr* g) {
 }
 
 // takes ownership of d_n (2^n_vars words) and d_d (2^n_vars x 5 words), both already filled on [0, active_len)
-static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t active_len, uint32_t n_vars, lm_gkr** out) {
+static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t active_len, uint32_t n_vars, lm_gkr** out,
+                           uint32_t top_vars = LM_GKR_TOP_VARS) {
   lm_gkr* g = new (std::nothrow) lm_gkr();
   if (!g) {
     cudaFree(d_n), cudaFree(d_d);
@@ -1100,12 +1103,13 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
   }
   g->ctx = c;
   g->n_vars = n_vars;
+  g->top_vars = top_vars;
   g->nums.push_back(d_n);
   g->dens.push_back(d_d);
   const uint64_t n = (uint64_t)1 << n_vars;
   cudaError_t e = lm::gkr_pad(c->stream, d_n, 1, d_d, active_len, n);
   // up pass (mod.rs:52-62): halve until 2^5 fractions remain
-  for (uint32_t l = 1; e == cudaSuccess && l <= n_vars - LM_GKR_TOP_VARS; l++) {
+  for (uint32_t l = 1; e == cudaSuccess && l <= n_vars - top_vars; l++) {
     const uint64_t m = n >> l;
     uint32_t *nn = nullptr, *dd = nullptr;
     e = cudaMalloc(&nn, m * 5 * sizeof(uint32_t));
@@ -1156,6 +1160,29 @@ int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t a
     return cuda_fail(e, "lm_gkr_new");
   }
   return gkr_from_device(c, d_n, d_d, active_len, n_vars, out);
+}
+
+int lm_gkr_new_shard(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, uint32_t n_vars,
+                     uint32_t top_vars, lm_gkr** out) {
+  if (!c || !out || (active_len && (!nums || !dens))) return fail(LM_ERR_INVALID, "lm_gkr_new_shard: null argument");
+  *out = nullptr;
+  if (n_vars < 2 || n_vars > 31 || top_vars < 1 || top_vars >= n_vars)
+    return fail(LM_ERR_INVALID, "lm_gkr_new_shard: n_vars %u / top_vars %u out of range", n_vars, top_vars);
+  const uint64_t n = (uint64_t)1 << n_vars;
+  if (active_len > n) return fail(LM_ERR_INVALID, "lm_gkr_new_shard: active_len exceeds 2^n_vars");
+  CU(cudaSetDevice(c->device));
+  uint32_t *d_n = nullptr, *d_d = nullptr;
+  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess && active_len)
+    e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess && active_len)
+    e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d_n), cudaFree(d_d);
+    return cuda_fail(e, "lm_gkr_new_shard");
+  }
+  return gkr_from_device(c, d_n, d_d, active_len, n_vars, out, top_vars);
 }
 
 // evaluation of a device-resident base/extension polynomial at a host point, result to the host
@@ -1329,17 +1356,18 @@ int lm_gkr_top(lm_gkr* g, uint32_t* top_nums, uint32_t* top_dens) {
   if (!g || !top_nums || !top_dens) return fail(LM_ERR_INVALID, "lm_gkr_top: null argument");
   lm_ctx* c = g->ctx;
   CU(cudaSetDevice(c->device));
-  const size_t bytes = ((size_t)1 << LM_GKR_TOP_VARS) * 5 * sizeof(uint32_t);
+  const size_t bytes = ((size_t)1 << g->top_vars) * 5 * sizeof(uint32_t);
   CU(cudaMemcpyAsync(top_nums, g->nums.back(), bytes, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(top_dens, g->dens.back(), bytes, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return LM_OK;
 }
 
-int lm_gkr_layer_begin(lm_gkr* g, uint32_t claim_vars, const uint32_t* point, const uint32_t alpha[5]) {
+static int gkr_layer_begin_impl(lm_gkr* g, uint32_t claim_vars, const uint32_t* point, const uint32_t alpha[5],
+                                const uint32_t* eq_scale) {
   if (!g || !point || !alpha) return fail(LM_ERR_INVALID, "lm_gkr_layer_begin: null argument");
-  if (claim_vars < LM_GKR_TOP_VARS || claim_vars >= g->n_vars)
-    return fail(LM_ERR_INVALID, "lm_gkr_layer_begin: claim over %u variables, expected %u..%u", claim_vars, LM_GKR_TOP_VARS,
+  if (claim_vars < g->top_vars || claim_vars >= g->n_vars)
+    return fail(LM_ERR_INVALID, "lm_gkr_layer_begin: claim over %u variables, expected %u..%u", claim_vars, g->top_vars,
                 g->n_vars - 1);
   lm_ctx* c = g->ctx;
   CU(cudaSetDevice(c->device));
@@ -1349,7 +1377,19 @@ int lm_gkr_layer_begin(lm_gkr* g, uint32_t claim_vars, const uint32_t* point, co
   g->cur_src = 0;
   g->cur_buf = 0;
   memcpy(g->alpha, alpha, sizeof(g->alpha));
+  const uint32_t one[5] = {lm::KB_R1, 0, 0, 0, 0};
+  memcpy(g->eq_scale, eq_scale ? eq_scale : one, sizeof(g->eq_scale));
   return LM_OK;
+}
+
+int lm_gkr_layer_begin(lm_gkr* g, uint32_t claim_vars, const uint32_t* point, const uint32_t alpha[5]) {
+  return gkr_layer_begin_impl(g, claim_vars, point, alpha, nullptr);
+}
+
+int lm_gkr_layer_begin_shard(lm_gkr* g, uint32_t claim_vars, const uint32_t* point, const uint32_t alpha[5],
+                             const uint32_t eq_scale[5]) {
+  if (!eq_scale) return fail(LM_ERR_INVALID, "lm_gkr_layer_begin_shard: null argument");
+  return gkr_layer_begin_impl(g, claim_vars, point, alpha, eq_scale);
 }
 
 int lm_gkr_round(lm_gkr* g, uint32_t c0[5], uint32_t c2[5]) {
@@ -1360,7 +1400,7 @@ int lm_gkr_round(lm_gkr* g, uint32_t c0[5], uint32_t c2[5]) {
   const uint32_t* a = g->cur_src == 0 ? g->nums[g->cur_layer] : g->d_w[g->cur_buf];
   const uint32_t* b = g->cur_src == 0 ? g->dens[g->cur_layer] : nullptr;
   CU(lm::gkr_round(c->stream, g->cur_src, g->cur_layer == 0 ? 1 : 5, a, b, g->cur_vars, g->d_eq, g->alpha, g->d_scratch,
-                   g->d_out10));
+                   g->d_out10, g->eq_scale));
   uint32_t h[10];
   CU(cudaMemcpyAsync(h, g->d_out10, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));

@@ -230,7 +230,8 @@ size_t gkr_round_scratch_words(uint32_t n_vars) {
 // One round over `n_rows` rows of the 4 working columns.  src == 0: a = layer nums, b = layer dens (2 n_rows entries);
 // src == 1: a = working table W (n_rows x 20 words).  d_eq_point: log2(n_rows) - 1 EF entries.
 cudaError_t gkr_round(cudaStream_t stream, int src, uint32_t num_dim, const uint32_t* a, const uint32_t* b, uint32_t n_vars,
-                      const uint32_t* d_eq_point, const uint32_t alpha[5], uint32_t* d_scratch, uint32_t* d_out10) {
+                      const uint32_t* d_eq_point, const uint32_t alpha[5], uint32_t* d_scratch, uint32_t* d_out10,
+                      const uint32_t* eq_scale) {
   if (n_vars < 1) return cudaErrorInvalidValue;
   Ef al;
   for (int k = 0; k < 5; k++) al.c[k] = alpha[k];
@@ -243,7 +244,7 @@ cudaError_t gkr_round(cudaStream_t stream, int src, uint32_t num_dim, const uint
   uint32_t* d_part = d_lo + 5 * ((size_t)1 << lo_vars);
   const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
   cudaError_t e;
-  if ((e = eq_table(stream, d_eq_point, hi_vars, one, d_hi)) != cudaSuccess) return e;
+  if ((e = eq_table(stream, d_eq_point, hi_vars, eq_scale ? eq_scale : one, d_hi)) != cudaSuccess) return e;
   if ((e = eq_table(stream, d_eq_point + 5 * hi_vars, lo_vars, one, d_lo)) != cudaSuccess) return e;
   uint64_t blocks = (half + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;

@@ -34,7 +34,8 @@ cudaError_t gkr_layer_up(cudaStream_t stream, const uint32_t* d_nums, uint32_t n
                          uint32_t* d_out_nums, uint32_t* d_out_dens);
 size_t gkr_round_scratch_words(uint32_t n_vars);
 cudaError_t gkr_round(cudaStream_t stream, int src, uint32_t num_dim, const uint32_t* a, const uint32_t* b, uint32_t n_vars,
-                      const uint32_t* d_eq_point, const uint32_t alpha[5], uint32_t* d_scratch, uint32_t* d_out10);
+                      const uint32_t* d_eq_point, const uint32_t alpha[5], uint32_t* d_scratch, uint32_t* d_out10,
+                      const uint32_t* eq_scale = nullptr);  // host, 5 words: constant factor of every eq weight (nullptr = 1)
 cudaError_t gkr_fold(cudaStream_t stream, int src, uint32_t num_dim, const uint32_t* a, const uint32_t* b, uint32_t n_vars,
                      const uint32_t r[5], uint32_t* d_out);
 }  // namespace lm

@@ -66,6 +66,23 @@ class GkrQuotientProver:
         check(lib().lm_gkr_top(self.handle, _p(tn), _p(td)))
         return tn, td
 
+    # ---- device steps of one layer sumcheck; the sharded prover (leanmultisig_b200/sharded.py) overrides these five ----
+    def _layer_begin(self, k: int, point_m: np.ndarray, alpha_m: np.ndarray) -> None:
+        check(lib().lm_gkr_layer_begin(self.handle, k, _p(point_m), _p(alpha_m)))
+
+    def _round(self):
+        c0, c2 = np.empty(5, dtype=np.uint32), np.empty(5, dtype=np.uint32)
+        check(lib().lm_gkr_round(self.handle, _p(c0), _p(c2)))
+        return c0, c2
+
+    def _fold(self, r_m: np.ndarray) -> None:
+        check(lib().lm_gkr_fold(self.handle, _p(r_m)))
+
+    def _layer_end(self) -> np.ndarray:
+        inner = np.empty((4, 5), dtype=np.uint32)
+        check(lib().lm_gkr_layer_end(self.handle, _p(inner)))
+        return inner
+
     @classmethod
     def from_handle(cls, handle):
         self = cls.__new__(cls)
@@ -117,12 +134,11 @@ class GkrQuotientProver:
         s = F.add(claim_num, F.mul(alpha, claim_den))
         mmf = F.ONE
         pt = np.stack([F.to_monty(x) for x in point])
-        check(lib().lm_gkr_layer_begin(self.handle, k, _p(pt), _p(alpha_m)))
+        self._layer_begin(k, pt, alpha_m)
         remaining = list(point)
         q = []
-        c0, c2 = np.empty(5, dtype=np.uint32), np.empty(5, dtype=np.uint32)
         for _ in range(k):
-            check(lib().lm_gkr_round(self.handle, _p(c0), _p(c2)))
+            c0, c2 = self._round()
             eq_alpha = remaining[-1]
             bare = build_bare_from_coeffs(F.from_monty(c0), F.from_monty(c2), eq_alpha, s, mmf)
             add_sumcheck_poly(np.stack([F.to_monty(c) for c in bare]), F.to_monty(eq_alpha))
@@ -131,12 +147,11 @@ class GkrQuotientProver:
             eq_eval = F.add(F.mul(F.sub(F.ONE, eq_alpha), F.sub(F.ONE, r)), F.mul(eq_alpha, r))
             s = F.mul(eq_eval, F.poly_eval(bare, r))
             mmf = F.mul(mmf, eq_eval)
-            check(lib().lm_gkr_fold(self.handle, _p(r_m)))
+            self._fold(r_m)
             q.append(r)
             remaining.pop()
         q.reverse()
-        inner = np.empty((4, 5), dtype=np.uint32)
-        check(lib().lm_gkr_layer_end(self.handle, _p(inner)))
+        inner = self._layer_end()
         add_scalars(inner)
         beta = F.from_monty(sample())
         nl, nr, dl, dr = (F.from_monty(v) for v in inner)
@@ -147,6 +162,34 @@ class GkrQuotientProver:
         if self.handle:
             check(lib().lm_gkr_free(self.handle))
             self.handle = None
+
+
+class GkrShardSession:
+    """Device steps of the quotient GKR over ONE row-range shard of the fraction table (lm_gkr_new_shard): the compute
+    backend of leanmultisig_b200.sharded.ShardedGkrQuotientProver on a GPU."""
+
+    def __init__(self, ctx, nums, dens, n_vars: int, top_vars: int):
+        n_, d_ = _u32(nums).reshape(-1), _u32(dens).reshape(-1, 5)
+        assert n_.size == d_.shape[0] <= 1 << n_vars
+        h = C.c_void_p()
+        check(lib().lm_gkr_new_shard(ctx.handle, _p(n_) if n_.size else None, _p(d_) if n_.size else None, n_.size, n_vars,
+                                     top_vars, C.byref(h)))
+        self.handle, self.top_vars = h, top_vars
+
+    def top(self):
+        m = 1 << self.top_vars
+        tn, td = np.empty((m, 5), dtype=np.uint32), np.empty((m, 5), dtype=np.uint32)
+        check(lib().lm_gkr_top(self.handle, _p(tn), _p(td)))
+        return tn, td
+
+    def layer_begin(self, claim_vars: int, point_m, alpha_m, eq_scale_m) -> None:
+        pt = _u32(point_m).reshape(-1, 5)
+        check(lib().lm_gkr_layer_begin_shard(self.handle, claim_vars, _p(pt), _p(_u32(alpha_m)), _p(_u32(eq_scale_m))))
+
+    round = GkrQuotientProver._round
+    fold = GkrQuotientProver._fold
+    layer_end = GkrQuotientProver._layer_end
+    free = GkrQuotientProver.free
 
 
 # ======================================================================================================

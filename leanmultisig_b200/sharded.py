@@ -20,6 +20,11 @@ rows: every rank computes the round sums of its shard with the eq weight of its 
 n - g rounds every rank is left with one EF value per column: an all-gather of (n_cols + n_shift) x 5 words builds the
 2^g-row table on which the last g rounds run replicated (lm_air_new_folded).
 
+Quotient GKR (`ShardedGkrQuotientProver`): the fraction table is split the same way.  The up pass pairs adjacent rows
+and is local down to 2^(5-g) fractions per rank; an all-gather of those gives the 2^5 top values the prover sends.  Every
+layer sumcheck folds the least-significant variable first: k - g local rounds with ONE all-reduce of (c0, c2) = 10 field
+words each, then an all-gather of the four folded values per rank and the last g rounds on 4 x G values on the host.
+
 The compute steps go through a backend object so that the CPU test tier can run the same orchestration with the
 oracle over gloo; the product backend is the CUDA library (`CudaBackend`), there is no CPU product path.
 """
@@ -29,6 +34,7 @@ import numpy as np
 
 from . import field as F
 from .air import AIR_SHAPES, OuterSumcheckHost
+from .logup import N_VARS_TO_SEND_GKR_COEFFS, GkrQuotientProver
 
 P = 0x7F000001
 
@@ -197,6 +203,99 @@ class ShardedAirSumcheckSession(OuterSumcheckHost):
         self.local = self.tail = None
 
 
+def prefix_eq(point, g: int, rank: int):
+    """eq(point[:g], bits of rank), most significant bit first; point: list of EF tuples"""
+    scale = F.ONE
+    for k in range(g):
+        scale = F.mul(scale, point[k] if (rank >> (g - 1 - k)) & 1 else F.sub(F.ONE, point[k]))
+    return scale
+
+
+def _eq_table_small(point) -> list:
+    """[eq(point, j) for j < 2^len(point)], x_0 = most significant bit of j"""
+    table = [F.ONE]
+    for x in point:
+        table = [v for t in table for v in (F.mul(t, F.sub(F.ONE, x)), F.mul(t, x))]
+    return table
+
+
+class ShardedGkrQuotientProver(GkrQuotientProver):
+    """prove_gkr_quotient (quotient_gkr/mod.rs:31-141) over a fraction table split into one row range per rank.
+    Collective: every rank constructs it with its rows (`nums`, `dens` = the active part of rows
+    [rank 2^(n_vars-g), (rank+1) 2^(n_vars-g)), possibly empty) and drives prove() with the same transcript."""
+
+    def __init__(self, backend, dist, nums, dens, n_vars: int):
+        self.b, self.dist = backend, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.g = self.world.bit_length() - 1
+        assert self.world == 1 << self.g and self.g < N_VARS_TO_SEND_GKR_COEFFS
+        assert n_vars - self.g > N_VARS_TO_SEND_GKR_COEFFS, "table too small for this many ranks"
+        self.n_vars = n_vars
+        self.local = backend.gkr_session(nums, dens, n_vars - self.g, N_VARS_TO_SEND_GKR_COEFFS - self.g)
+        self.handle = None
+
+    def top(self):
+        tn, td = self.local.top()
+        if self.world == 1:
+            return tn, td
+        both = self.b.all_gather_words(self.dist, np.stack([tn, td]))      # world x 2 x 2^(5-g) x 5
+        return (np.ascontiguousarray(both[:, 0]).reshape(-1, 5), np.ascontiguousarray(both[:, 1]).reshape(-1, 5))
+
+    def _layer_begin(self, k, point_m, alpha_m):
+        g = self.g
+        point = [F.from_monty(x) for x in point_m]
+        self._local_rounds, self._round_no = k - g, 0
+        self._top_point, self._alpha, self._tail = point[:g], F.from_monty(alpha_m), None
+        self.local.layer_begin(k - g, point_m[g:], alpha_m, F.to_monty(prefix_eq(point, g, self.rank)))
+
+    def _round(self):
+        if self._round_no < self._local_rounds:
+            c0, c2 = self.local.round()
+            if self.world == 1:
+                return c0, c2
+            both = self.b.all_reduce_field(self.dist, np.stack([c0, c2]))
+            return both[0], both[1]
+        # tail: 4 columns of 2^m values on the host; G(nl, nr, dl, dr) = nl dr + nr dl + alpha dl dr  (sumcheck_utils.rs:65-79)
+        nl, nr, dl, dr = self._tail
+        m = len(nl).bit_length() - 1
+        eq = _eq_table_small(self._top_point[: m - 1])
+        al = self._alpha
+
+        def big_g(a, b, c, d):
+            return F.add(F.add(F.mul(a, d), F.mul(b, c)), F.mul(al, F.mul(c, d)))
+
+        c0 = c2 = F.ZERO
+        for j, e in enumerate(eq):
+            lo = [col[2 * j] for col in self._tail]
+            df = [F.sub(col[2 * j + 1], col[2 * j]) for col in self._tail]
+            c0 = F.add(c0, F.mul(e, big_g(*lo)))
+            c2 = F.add(c2, F.mul(e, big_g(*df)))
+        return F.to_monty(c0), F.to_monty(c2)
+
+    def _fold(self, r_m):
+        if self._round_no < self._local_rounds:
+            self.local.fold(r_m)
+            if self._round_no + 1 == self._local_rounds and self.g:
+                mine = self.local.layer_end()                                # 4 x 5
+                everyone = self.b.all_gather_words(self.dist, mine)           # world x 4 x 5, row index = rank
+                self._tail = [[F.from_monty(everyone[q, c]) for q in range(self.world)] for c in range(4)]
+        else:
+            r = F.from_monty(r_m)
+            self._tail = [[F.add(col[2 * j], F.mul(r, F.sub(col[2 * j + 1], col[2 * j]))) for j in range(len(col) // 2)]
+                          for col in self._tail]
+        self._round_no += 1
+
+    def _layer_end(self):
+        if self.g == 0:
+            return self.local.layer_end()
+        return np.stack([F.to_monty(col[0]) for col in self._tail])
+
+    def free(self):
+        if self.local is not None:
+            self.local.free()
+            self.local = None
+
+
 class CudaBackend:
     """Compute steps on one GPU through the C ABI; tensors are torch CUDA int32 (device memory + NCCL plumbing)."""
 
@@ -289,3 +388,9 @@ class CudaBackend:
         out = self.torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t)
         return out.cpu().numpy().view(np.uint32)
+
+    # ---- quotient GKR ---------------------------------------------------------------------------------------------
+    def gkr_session(self, nums, dens, n_vars, top_vars):
+        from .logup import GkrShardSession
+
+        return GkrShardSession(self.ctx, nums, dens, n_vars, top_vars)

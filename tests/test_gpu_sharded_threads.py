@@ -1,0 +1,158 @@
+"""The sharded AIR sumcheck and the sharded quotient GKR on ONE GPU: G "ranks" run as threads of this process, each with
+its own library context (own stream and scratch), and exchange through an in-memory stand-in for torch.distributed.
+Exercises lm_air_new_shard / lm_air_new_folded / lm_gkr_new_shard / lm_gkr_layer_begin_shard and the orchestration of
+leanmultisig_b200/sharded.py on boxes that have a single device; the multi-process NCCL versions are in
+test_sharded_air.py / test_sharded_gkr.py."""
+import threading
+
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import logup as OL
+from oracle import whir as W
+
+P = 0x7F000001
+
+
+class ThreadGroup:
+    def __init__(self, world):
+        self.world, self.barrier, self.slots = world, threading.Barrier(world), [None] * world
+
+    def exchange(self, rank, value):
+        self.slots[rank] = value
+        self.barrier.wait()
+        out = list(self.slots)
+        self.barrier.wait()
+        return out
+
+
+class ThreadDist:
+    def __init__(self, group, rank):
+        self.group, self.rank = group, rank
+
+    def get_rank(self):
+        return self.rank
+
+    def get_world_size(self):
+        return self.group.world
+
+
+class ThreadBackend:
+    """CUDA compute through the C ABI, collectives through the ThreadGroup"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def air_session(self, table_id, columns, eq_factor, ap, la, beta, **kw):
+        import leanmultisig_b200 as lm
+
+        return lm.AirSumcheckSession(self.ctx, table_id, columns, eq_factor, np.zeros(5, dtype=np.uint32), ap, la, beta, **kw)
+
+    def gkr_session(self, nums, dens, n_vars, top_vars):
+        from leanmultisig_b200.logup import GkrShardSession
+
+        return GkrShardSession(self.ctx, nums, dens, n_vars, top_vars)
+
+    def all_reduce_field(self, d, words):
+        parts = d.group.exchange(d.rank, np.asarray(words).astype(np.int64))
+        return (sum(parts) % P).astype(np.uint32)
+
+    def all_gather_words(self, d, words):
+        return np.stack(d.group.exchange(d.rank, np.array(words, dtype=np.uint32)))
+
+
+def run_ranks(world, fn):
+    import leanmultisig_b200 as lm
+
+    group, results, errors = ThreadGroup(world), [None] * world, []
+
+    def body(rank):
+        try:
+            ctx = lm.Context(0, 16)
+            try:
+                results[rank] = fn(ThreadBackend(ctx), ThreadDist(group, rank), rank)
+            finally:
+                ctx.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            group.barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n_vars,active", [(2, 10, 1000), (4, 11, 1030), (8, 12, 4096)])
+def test_gpu_sharded_gkr_threads(rng, world, n_vars, active):
+    from leanmultisig_b200.sharded import ShardedGkrQuotientProver
+
+    nums, dens = O.random_field(rng, active), O.random_field(rng, (active, 5))
+    ps_ref = W.ProverState()
+    q_ref, pt_ref, cn_ref, cd_ref = OL.prove_gkr_quotient_cpu(ps_ref, nums, dens)
+    per = (1 << n_vars) // world
+
+    def rank_main(backend, dist, rank):
+        lo, hi = min(rank * per, active), min((rank + 1) * per, active)
+        ps = W.ProverState()
+        prover = ShardedGkrQuotientProver(backend, dist, nums[lo:hi], dens[lo:hi], n_vars)
+        out = prover.prove_with_state(ps)
+        prover.free()
+        return ps.transcript, out
+
+    for transcript, (q, pt, cn, cd) in run_ranks(world, rank_main):
+        assert transcript == ps_ref.transcript
+        assert np.array_equal(q, W.tm(q_ref)) and np.array_equal(cn, W.tm(cn_ref)) and np.array_equal(cd, W.tm(cd_ref))
+    vs = W.VerifierState(ps_ref.transcript, [])
+    OL.verify_gkr_quotient(vs, n_vars)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,table,log_rows", [(2, 0, 10), (4, 1, 7), (8, 2, 6)])
+def test_gpu_sharded_air_threads(rng, world, table, log_rows):
+    from leanmultisig_b200.sharded import ShardedAirSumcheckSession
+    from test_air_tables import extras, oracle_rounds, with_shifts
+    from leanmultisig_b200 import field as F
+
+    n_cols, n_shift, deg = O.air_shape(table)
+    base = O.random_field(rng, (n_cols, 1 << log_rows))
+    eq_factor = O.random_field(rng, (log_rows, 5))
+    ap, la, beta = extras(rng)
+    challenges = O.random_field(rng, (log_rows, 5))
+    sum0 = O.random_field(rng, 5)
+    raws, finals = oracle_rounds(table, with_shifts(table, base), eq_factor, ap, la, beta, challenges)
+    # expected bare polynomials from the oracle's raw round sums (air_sumcheck.rs:242-265)
+    expected, s, mmf = [], F.from_monty(sum0), F.ONE
+    for r in range(log_rows):
+        alpha = F.from_monty(eq_factor[log_rows - 1 - r])
+        p_evals = [F.mul(F.from_monty(v), mmf) for v in raws[r]]
+        p1 = F.mul(F.sub(s, F.mul(F.sub(F.ONE, alpha), p_evals[0])), F.inv(alpha))
+        coeffs = F.lagrange_interpolation_at_integers([p_evals[0], p1] + p_evals[1:])
+        expected.append(np.stack([F.to_monty(c) for c in coeffs]))
+        ch = F.from_monty(challenges[r])
+        eq_eval = F.add(F.mul(F.sub(F.ONE, alpha), F.sub(F.ONE, ch)), F.mul(alpha, ch))
+        s, mmf = F.mul(F.poly_eval(coeffs, ch), eq_eval), F.mul(mmf, eq_eval)
+    per = (1 << log_rows) // world
+
+    def rank_main(backend, dist, rank):
+        shard = [base[c, rank * per:(rank + 1) * per] for c in range(n_cols)]
+        sess = ShardedAirSumcheckSession(backend, dist, table, shard, eq_factor, sum0, ap, la, beta)
+        bares = []
+        for r in range(log_rows):
+            bare = sess.compute_bare_round_poly()
+            bares.append(bare)
+            sess.process_challenge(challenges[r], bare)
+        out = sess.final_column_evals()
+        sess.free()
+        return bares, out
+
+    for bares, out in run_ranks(world, rank_main):
+        for r in range(log_rows):
+            assert np.array_equal(bares[r], expected[r]), f"round {r}"
+        assert np.array_equal(out, finals)
