@@ -117,12 +117,13 @@ def cpu_commit_sample(sample_log_rows: int, reps: int):
 
 
 def pick_cpu_sample(cores: int) -> int:
-    # ~1.7 us per scalar Poseidon1 compression per core, 9 compressions per row: aim at 10-30 s of CPU work in total
-    if cores >= 32:
-        return 20
-    if cores >= 8:
-        return 19
-    return 17
+    # AVX-512 oracle: ~1 us per Poseidon1 compression per core (16 lanes), 9 compressions per row -> the whole 2^22-row
+    # commit is ~10-20 core-seconds; hosts without AVX-512 fall back to the scalar path (~10x slower): smaller slice
+    import oracle as O
+
+    if O.lib().lm_or_have_avx512():
+        return 22 if cores >= 8 else 20
+    return 19 if cores >= 8 else 17
 
 
 def run_reference(args):
@@ -141,7 +142,11 @@ def run_reference(args):
         times.append(t)
     t_step = sum(times) / len(times)
     value = elems / t_step / 1e9
-    sample = f"2^{slr} x 64 slice of the 2^{args.log_rows} x 64 commit (rate 1/2, full width 128), all host threads (OpenMP)"
+    import oracle as O
+
+    simd = "AVX-512 16-lane" if O.lib().lm_or_have_avx512() else "scalar"
+    sample = (f"2^{slr} x 64 slice of the 2^{args.log_rows} x 64 commit (rate 1/2, full width 128), {simd} port, "
+              f"all host threads (OpenMP)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -151,7 +156,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference is Rust (no toolchain in this image): timed the C restatement in oracle/ (kind=port)",
+        "note": "reference is Rust (no toolchain in this image): timed the C restatement in oracle/ (kind=port; AVX-512 "
+                "vertical Poseidon1 + cache-blocked vector DFT when the host has AVX-512)",
     }
     print(json.dumps(line), flush=True)
 
@@ -300,8 +306,11 @@ def run_b200(args):
             slr = min(args.cpu_sample_log_rows or pick_cpu_sample(cores), args.log_rows)
             cpu_commit_sample(min(slr, 14), 1)  # warm-up: OpenMP pool start-up costs ~1 s on the first call
             t_cpu, elems, cores, cpu_root = cpu_commit_sample(slr, 1)
+            import oracle as O
+
+            simd = "AVX-512 (16 lanes, the reference's packing width)" if O.lib().lm_or_have_avx512() else "scalar"
             line["cpu_baseline"] = {"value": elems / t_cpu / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"2^{slr} x 64 slice of the commit, oracle/ C restatement with OpenMP on "
+                                    "sample": f"2^{slr} x 64 slice of the commit, oracle/ C restatement, {simd}, OpenMP on "
                                               f"all host threads, {t_cpu:.2f} s"}
         print(json.dumps(line), flush=True)
     ctx.close()

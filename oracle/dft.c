@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "kb.h"
+#include "kb_avx512.h"
 #include "oracle.h"
 
 /* utils.rs:128-150.  evals: 2^n_vars elements of `dim` u32 each (dim = 1 base, 5 extension).
@@ -32,6 +33,54 @@ void lm_or_prepare_evals(const uint32_t *evals, uint32_t n_vars, uint32_t dim, u
   }
 }
 
+/* One butterfly (dft.rs:546-568) between two rows of w elements, 16 columns per vector (w % 16 == 0). */
+TGT void bfly_rows16(uint32_t *lo, uint32_t *hi, uint64_t w, kb_t t) {
+  const __m512i tv = _mm512_set1_epi32((int)t);
+  for (uint64_t c = 0; c < w; c += 16) {
+    __m512i a = _mm512_loadu_si512(lo + c), b = _mm512_loadu_si512(hi + c);
+    __m512i x = mul16(sub16(b, a), tv);
+    _mm512_storeu_si512(lo + c, add16(a, x));
+    _mm512_storeu_si512(hi + c, sub16(a, x));
+  }
+}
+
+/* The same layer network as the scalar loop below, scheduled the way the reference schedules it for the cache
+ * (dft.rs:79-144: a first run of layers on chunks that fit the cache, then three layers per pass over the matrix) and
+ * with the butterflies of one row pair vectorised over the columns. */
+TGT_FN static void dft_batch_avx512(uint32_t *mat, uint64_t h, uint64_t w, unsigned log_h, const kb_t *roots) {
+  const unsigned LB = log_h < 10 ? log_h : 10;
+#pragma omp parallel for schedule(static)
+  for (uint64_t blk = 0; blk < (h >> LB); blk++) {
+    uint32_t *base = mat + (blk << LB) * w;
+    for (unsigned l = 0; l < LB; l++) {
+      const uint64_t m = (uint64_t)1 << l, stride = h >> (l + 1);
+      for (uint64_t pair = 0; pair < ((uint64_t)1 << LB) / 2; pair++) {
+        const uint64_t b2 = pair >> l, i = pair & (m - 1);
+        uint32_t *lo = base + (b2 * 2 * m + i) * w;
+        bfly_rows16(lo, lo + m * w, w, roots[i * stride]);
+      }
+    }
+  }
+  for (unsigned l0 = LB; l0 < log_h;) {
+    const unsigned g = log_h - l0 < 3 ? log_h - l0 : 3;
+#pragma omp parallel for schedule(static)
+    for (uint64_t u = 0; u < (h >> g); u++) {
+      const uint64_t lo_part = u & (((uint64_t)1 << l0) - 1), hi_part = u >> l0;
+      const uint64_t base_row = (hi_part << (l0 + g)) | lo_part;
+      for (unsigned s = 0; s < g; s++) {
+        const unsigned l = l0 + s;
+        const uint64_t m = (uint64_t)1 << l;
+        for (unsigned q = 0; q < (1u << g); q++) {
+          if (q & (1u << s)) continue;
+          const uint64_t ra = base_row + ((uint64_t)q << l0);
+          bfly_rows16(mat + ra * w, mat + (ra + m) * w, w, roots[(ra & (m - 1)) * (h >> (l + 1))]);
+        }
+      }
+    }
+    l0 += g;
+  }
+}
+
 /* dft.rs:79-144 on an h x w base-field matrix, in place. */
 void lm_or_dft_batch_by_evals(uint32_t *mat, uint64_t h, uint64_t w) {
   if (h < 2) return;
@@ -42,6 +91,11 @@ void lm_or_dft_batch_by_evals(uint32_t *mat, uint64_t h, uint64_t w) {
   kb_t *roots = (kb_t *)malloc((h / 2) * sizeof(kb_t));
   roots[0] = KB_ONE;
   for (uint64_t i = 1; i < h / 2; i++) roots[i] = kb_mul(roots[i - 1], g);
+  if (lm_or_have_avx512() && w % 16 == 0 && !getenv("LM_ORACLE_SCALAR_DFT")) {
+    dft_batch_avx512(mat, h, w, log_h, roots);
+    free(roots);
+    return;
+  }
   for (uint64_t m = 1; m < h; m <<= 1) {
     uint64_t stride = h / (2 * m);
 #pragma omp parallel for schedule(static)

@@ -77,8 +77,20 @@ void lm_or_first_digest_layer(const uint32_t *mat, uint64_t h, uint32_t stored_w
   uint32_t n_zero_chunks = (full_width - effective_width) / RATE;
   lm_or_poseidon1_init();
   if (n_zero_chunks >= 2) lm_or_zero_suffix_state(n_zero_chunks, zero_state);
+  /* 16 rows per step on AVX-512 hosts (the reference's packing width, whir/src/merkle.rs:215-288), scalar otherwise and
+   * for the ragged cases; both paths are compared in tests/test_oracle_poseidon.py */
+  uint64_t h16 = 0;
+  if (lm_or_have_avx512() && stored_width % 8 == 0 && effective_width % 8 == 0 && full_width >= 24 &&
+      (n_zero_chunks >= 2 ? effective_width <= stored_width && effective_width >= 8 : 1) &&
+      (uint64_t)stored_width * 16 < 0x7fffffffull) {
+    h16 = h / 16 * 16;
 #pragma omp parallel for schedule(static)
-  for (uint64_t r = 0; r < h; r++)
+    for (uint64_t r = 0; r < h16; r += 16)
+      lm_or_leaf_digest_x16(mat + r * stored_width, stored_width, full_width, effective_width,
+                            n_zero_chunks >= 2 ? zero_state : NULL, digests + 8 * r);
+  }
+#pragma omp parallel for schedule(static)
+  for (uint64_t r = h16; r < h; r++)
     leaf_digest(mat + r * stored_width, stored_width, full_width, effective_width, zero_state, digests + 8 * r);
 }
 
@@ -94,8 +106,15 @@ void lm_or_compress_pair(const uint32_t left[8], const uint32_t right[8], uint32
 /* symetric/src/merkle.rs:50-90 for power-of-two layers: next[i] = C(prev[2i] || prev[2i+1]). */
 void lm_or_compress_layer(const uint32_t *prev, uint64_t n_prev, uint32_t *next) {
   lm_or_poseidon1_init();
+  const uint64_t n = n_prev / 2;
+  uint64_t n16 = 0;
+  if (lm_or_have_avx512()) {
+    n16 = n / 16 * 16;
 #pragma omp parallel for schedule(static)
-  for (uint64_t i = 0; i < n_prev / 2; i++) lm_or_compress_pair(prev + 16 * i, prev + 16 * i + 8, next + 8 * i);
+    for (uint64_t i = 0; i < n16; i += 16) lm_or_compress_pairs_x16(prev + 16 * i, next + 8 * i);
+  }
+#pragma omp parallel for schedule(static)
+  for (uint64_t i = n16; i < n; i++) lm_or_compress_pair(prev + 16 * i, prev + 16 * i + 8, next + 8 * i);
 }
 
 /* Whole tree: layers stored back to back, layer 0 = h digests, then h/2, ... 1.

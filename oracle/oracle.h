@@ -27,6 +27,13 @@ void lm_or_poseidon1_permute(uint32_t s[16]);
 void lm_or_poseidon1_compress(uint32_t s[16]);
 void lm_or_poseidon1_permute_batch(uint32_t *states, uint64_t n, int dense);
 void lm_or_poseidon1_compress_batch(uint32_t *states, uint64_t n);
+/* poseidon1_avx512.c: 16 states per call, one per 32-bit lane; only when lm_or_have_avx512() (LM_ORACLE_NO_AVX512=1 forces
+ * the scalar path everywhere) */
+int lm_or_have_avx512(void);
+void lm_or_poseidon1_compress_x16(uint32_t *states);
+void lm_or_leaf_digest_x16(const uint32_t *rows, uint32_t stored_width, uint32_t full_width, uint32_t effective_width,
+                           const uint32_t *zero_state, uint32_t *digests);
+void lm_or_compress_pairs_x16(const uint32_t *prev, uint32_t *next);
 
 /* merkle.c */
 void lm_or_hash_slice(const uint32_t *data, uint64_t len, uint32_t out[8]);

@@ -1,5 +1,6 @@
 """Oracle pinned against the reference's only stored vector (Poseidon1 KAT) and cross-formulation checks."""
 import numpy as np
+import pytest
 
 import oracle as O
 
@@ -68,3 +69,49 @@ def test_quintic_extension(rng):
         base = O.ef_mul(base, base)
         e >>= 1
     assert O.from_monty(acc).tolist() == frob1
+
+
+# ---- AVX-512 batch path (the CPU baseline of bench.py) against the scalar oracle -------------------------------
+def _need_avx512():
+    if not O.lib().lm_or_have_avx512():
+        pytest.skip("host has no AVX-512 (the oracle then uses its scalar path everywhere)")
+
+
+def test_avx512_compress_matches_scalar(rng):
+    import ctypes as C
+
+    _need_avx512()
+    states = O.random_field(rng, (16, 16))
+    states[3] = 0
+    states[5] = 0x7F000000  # p - 1 in every lane of one state
+    exp = O.poseidon1_compress(states.copy())
+    got = np.ascontiguousarray(states.copy())
+    O.lib().lm_or_poseidon1_compress_x16(got.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("stored,full,eff", [(64, 128, 64), (128, 128, 128), (24, 32, 24), (16, 160, 16), (40, 48, 40)])
+def test_avx512_leaf_digests_match_hash_slice(rng, stored, full, eff):
+    _need_avx512()
+    h = 48 + 5  # three 16-row blocks through the vector path and a scalar tail
+    mat = O.random_field(rng, (h, stored))
+    mat[:, eff:] = 0
+    got = O.first_digest_layer(mat, full, eff)
+    for r in (0, 7, 15, 16, 47, 48, 52):
+        row = np.zeros(full, dtype=np.uint32)
+        row[:stored] = mat[r]
+        assert np.array_equal(got[r], O.hash_slice(row)), f"row {r}"
+
+
+def test_avx512_tree_layers_match_scalar_compress(rng):
+    _need_avx512()
+    h = 64
+    mat = O.random_field(rng, (h, 16))
+    layers = O.merkle_tree(mat, 16, 16)
+    off, n = 0, h
+    while n > 1:
+        prev = layers[off:off + n]
+        st = np.concatenate([prev[0::2], prev[1::2]], axis=1)
+        assert np.array_equal(layers[off + n:off + n + n // 2], O.poseidon1_compress(st)[:, :8])
+        off += n
+        n //= 2
