@@ -211,7 +211,7 @@ int lm_init(int device, uint32_t max_log_domain, lm_ctx** out_ctx) {
   CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   c->tw_log_n = max_log_domain;
   if (max_log_domain > 0) {
-    CU(cudaMalloc(&c->d_tw, sizeof(uint32_t) << (max_log_domain - 1)));
+    CU(cudaMalloc(&c->d_tw, (((size_t)1 << (max_log_domain - 1)) + lm::NTT_TW_SCRATCH_WORDS) * sizeof(uint32_t)));
     CU(lm::ntt_fill_twiddles(c->stream, c->d_tw, max_log_domain));
   }
   CU(cudaMalloc(&c->d_small, 64 * sizeof(uint32_t)));

@@ -15,6 +15,7 @@
 // is the contiguous slice evals[j << (n - k) ..] with every value repeated 2^r times, so the first r layers
 // (identities on repeated data) are skipped.
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <cstdint>
 #include "launch_count.h"
 #include "kb.cuh"
@@ -77,10 +78,10 @@ __device__ __forceinline__ void bfly4(uint4& a, uint4& b, uint32_t t) {
 }
 
 #ifndef NTT_THREADS
-#define NTT_THREADS 512
+#define NTT_THREADS 256
 #endif
 #ifndef NTT_MIN_BLOCKS
-#define NTT_MIN_BLOCKS 2
+#define NTT_MIN_BLOCKS 3
 #endif
 constexpr int TILE_COLS = 8;       // u32 columns per tile = 32 B per row
 constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory
@@ -120,13 +121,27 @@ __device__ __forceinline__ void tile_group(uint4* tile, const uint32_t* tw_s, in
   }
 }
 
+// Compact twiddle table of one pass: tw_pass[(1 << ll) + i] = w_h^((i << l0) << (log_h - (l0 + ll) - 1)), i < 2^ll, ll < L:
+// the twiddle of local layer ll for a tile whose rows start at a multiple of 2^(l0 + L).  Read contiguously by every
+// CTA of the pass (8 KiB, L1/L2 resident) instead of 2^L scattered words of the big table per tile.
+__global__ void ntt_pass_twiddles_kernel(uint32_t* __restrict__ tw_pass, int log_h, int l0, int L,
+                                         const uint32_t* __restrict__ tw, int tw_shift) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < 1 || k >= (1 << L)) return;
+  const int ll = 31 - __clz(k);
+  const uint64_t i = (uint64_t)k - ((uint64_t)1 << ll);
+  const uint64_t e = (i << l0) << (log_h - (l0 + ll) - 1);
+  tw_pass[k] = __ldg(tw + (e << tw_shift));
+}
+
 // Pass over layers [l0 + skip, l0 + L) of an h x w matrix; one CTA per (column tile, row group).
-// src == nullptr: in place on `mat`.  src != nullptr (only with l0 == 0): gather from the evaluation vector
-// (dim = 1): element (row, col) = src[(col << log_block) + (row >> r)].
+// src == nullptr: in place on `mat`; the tile arrives by 16-byte cp.async (all loads of a CTA in flight at once, no
+// register staging).  src != nullptr (only with l0 == 0): gather from the evaluation vector (dim = 1):
+// element (row, col) = src[(col << log_block) + (row >> r)].
 __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
 ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
                 int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift,
-                uint32_t tile0, uint32_t n_col_tiles) {
+                uint32_t tile0, uint32_t n_col_tiles, const uint32_t* __restrict__ tw_pass) {
   extern __shared__ uint4 tile[];  // [2^L][2] slots, then 2^L twiddle words
   uint32_t* tw_s = reinterpret_cast<uint32_t*>(tile + ((size_t)2 << L));
   const uint64_t col0 = (uint64_t)(tile0 + blockIdx.x % n_col_tiles) * TILE_COLS;  // column tile varies fastest: CTAs that
@@ -137,36 +152,60 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
   const int n_rows = 1 << L;
   const bool two_halves = col0 + 8 <= w;  // w % 4 == 0 guaranteed by the launcher
 
-  // twiddles of this CTA: layer l = l0 + ll pairs rows whose index mod 2^l is row_lo + (i << l0), i < 2^ll,
-  // with w_h^((row mod 2^l) << (log_h - l - 1))
-  for (int k = threadIdx.x + 1; k < n_rows; k += blockDim.x) {
-    const int ll = 31 - __clz(k);
-    const uint64_t i = (uint64_t)k - ((uint64_t)1 << ll);
-    const uint64_t e = (row_lo + (i << l0)) << (log_h - (l0 + ll) - 1);
-    tw_s[k] = __ldg(tw + (e << tw_shift));
-  }
-
   if (src == nullptr) {
     for (int item = threadIdx.x; item < 2 * n_rows; item += blockDim.x) {
       const int j = item >> 1, half = item & 1;
-      uint4 v = make_uint4(0, 0, 0, 0);
       if (half == 0 || two_halves) {
         const uint64_t row = row_base + ((uint64_t)j << l0);
-        v = *reinterpret_cast<const uint4*>(mat + row * w + col0 + 4 * half);
+        __pipeline_memcpy_async(&tile[tile_slot(j, half)], mat + row * w + col0 + 4 * half, 16);
+      } else {
+        tile[tile_slot(j, half)] = make_uint4(0, 0, 0, 0);
       }
-      tile[tile_slot(j, half)] = v;
     }
+    __pipeline_commit();
   } else {
-    // column c of the tile is contiguous in src: consecutive threads read consecutive rows of one column
     uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
     const int n_cols_here = two_halves ? 8 : 4;
-    for (int item = threadIdx.x; item < 8 * n_rows; item += blockDim.x) {
-      const int c = item >> L, j = item & (n_rows - 1);
-      const uint64_t row = row_base + j;
-      const uint32_t v = c < n_cols_here ? __ldg(src + ((((col0 + c) << log_block) + row) >> r)) : 0u;
-      t32[tile_slot(j, c >> 2) * 4 + (c & 3)] = v;
+    const int rpl = 4 << r;  // rows covered by one 16-byte load of a column (every value is repeated 2^r times)
+    if (log_block >= r + 2 && n_rows >= rpl && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      // lane -> (column c = lane & 7, row group): 4 lanes read 64 contiguous bytes of one column, and the 8 columns x
+      // 4 row groups of a warp store to 32 distinct banks (tile_slot swizzles rows 8 / 16 apart)
+      const int n_items = (n_rows / rpl) * 8;
+      for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+        const int c = item & 7, j_first = (item >> 3) * rpl;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < n_cols_here)
+          v = __ldg(reinterpret_cast<const uint4*>(src + (((col0 + c) << (log_block - r)) + ((row_base + j_first) >> r))));
+        const uint32_t vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          for (int rep = 0; rep < (1 << r); rep++) {
+            const int j = j_first + (e << r) + rep;
+            t32[tile_slot(j, c >> 2) * 4 + (c & 3)] = vals[e];
+          }
+      }
+    } else {
+      // column c of the tile is contiguous in src: consecutive threads read consecutive rows of one column
+      for (int item = threadIdx.x; item < 8 * n_rows; item += blockDim.x) {
+        const int c = item >> L, j = item & (n_rows - 1);
+        const uint64_t row = row_base + j;
+        const uint32_t v = c < n_cols_here ? __ldg(src + ((((col0 + c) << log_block) + row) >> r)) : 0u;
+        t32[tile_slot(j, c >> 2) * 4 + (c & 3)] = v;
+      }
     }
   }
+
+  // twiddles of this CTA: layer l = l0 + ll pairs rows whose index mod 2^l is row_lo + (i << l0), i < 2^ll, with
+  // w_h^((row mod 2^l) << (log_h - l - 1)) = tw_pass[2^ll + i] * w_h^(row_lo << (log_h - l - 1))
+  for (int k = threadIdx.x + 1; k < n_rows; k += blockDim.x) {
+    uint32_t t = __ldg(tw_pass + k);
+    if (row_lo) {
+      const int ll = 31 - __clz(k);
+      t = kb_mul(t, __ldg(tw + ((row_lo << (log_h - (l0 + ll) - 1)) << tw_shift)));
+    }
+    tw_s[k] = t;
+  }
+  if (src == nullptr) __pipeline_wait_prior(0);
   __syncthreads();
 
   int lp = skip;
@@ -281,8 +320,11 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     const uint32_t tiles = n_tiles ? n_tiles : (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
     const uint64_t n_cta = (uint64_t)tiles * (h >> L);
     const size_t smem = ((size_t)1 << L) * 36;  // tile + per-CTA twiddles
+    // compact twiddles of this pass, in the scratch words behind the big table (ntt.h: NTT_TW_SCRATCH_WORDS)
+    uint32_t* tw_pass = const_cast<uint32_t*>(d_tw) + ((size_t)1 << (tw_log_n - 1)) + (size_t)(p % 4) * ((size_t)1 << MAX_TILE_LOG);
+    ntt_pass_twiddles_kernel<<<((1 << L) + 255) / 256, 256, 0, stream>>>(tw_pass, log_h, l0, L, d_tw, tw_shift); count_launch();
     ntt_pass_kernel<<<(unsigned)n_cta, NTT_THREADS, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
-                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles); count_launch();
+                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     l0 += L;
