@@ -121,6 +121,11 @@ int lm_sc_eval_poly(lm_sumcheck* sc, const uint32_t* point, uint32_t out[5]);
 /* commit the current (folded) polynomial: reorder_and_dft + MerkleData::build of a WHIR round (open.rs:81-91) */
 int lm_sc_commit_poly(lm_sumcheck* sc, uint32_t folding_factor, uint32_t log_inv_rate, lm_tree** out_tree,
                       uint32_t out_root[8]);
+/* Row-sharded sumcheck (leanmultisig_b200/sharded.py): after the folding rounds that are local to a rank the
+ * folded tables are exchanged between devices.  lm_sc_export_dev copies the current EF tables (2^n_vars x 5 words each)
+ * into caller-owned DEVICE buffers, lm_sc_new_from_dev starts a session from gathered DEVICE tables. */
+int lm_sc_export_dev(lm_sumcheck* sc, uint32_t* d_poly_out, uint32_t* d_weights_out);
+int lm_sc_new_from_dev(lm_ctx* ctx, const uint32_t* d_poly, const uint32_t* d_weights, uint32_t n_vars, lm_sumcheck** out);
 int lm_sc_free(lm_sumcheck* sc);
 
 /* ---- AIR ("SuperSpartan") sumcheck session --------------------------------------------------------------

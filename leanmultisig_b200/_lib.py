@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
             "lm_sc_read": [vp, u32p, u32p],
             "lm_sc_eval_poly": [vp, u32p, u32p],
             "lm_sc_commit_poly": [vp, u32, u32, C.POINTER(vp), u32p],
+            "lm_sc_export_dev": [vp, vp, vp],
+            "lm_sc_new_from_dev": [vp, vp, vp, u32, C.POINTER(vp)],
             "lm_sc_free": [vp],
             "lm_air_new": [vp, u32, C.POINTER(vp), u32, u32, u32p, u32p, u32, u32p, u32, u32p, C.POINTER(vp)],
             "lm_air_new_shard": [vp, u32, C.POINTER(vp), u32, u32, u32p, u32p, u32, u32p, u32, u32p, u32p, u32p, C.POINTER(vp)],

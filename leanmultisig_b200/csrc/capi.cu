@@ -698,6 +698,39 @@ int lm_sc_new(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, u
   return LM_OK;
 }
 
+int lm_sc_new_from_dev(lm_ctx* c, const uint32_t* d_poly, const uint32_t* d_weights, uint32_t n_vars, lm_sumcheck** out) {
+  if (!d_poly || !d_weights) return fail(LM_ERR_INVALID, "lm_sc_new_from_dev: null argument");
+  int rc = sc_new_common(c, n_vars, out);
+  if (rc != LM_OK) return rc;
+  lm_sumcheck* s = *out;
+  const size_t bytes = ((size_t)5 << n_vars) * sizeof(uint32_t);
+  cudaError_t e = cudaMalloc(&s->d_p_owned, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_p_owned, d_poly, bytes, cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_w, d_weights, bytes, cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    lm_sc_free(s);
+    *out = nullptr;
+    return cuda_fail(e, "lm_sc_new_from_dev");
+  }
+  s->d_p = s->d_p_owned;
+  s->p_dim = 5;
+  s->p_live = (uint64_t)1 << n_vars;
+  return LM_OK;
+}
+
+int lm_sc_export_dev(lm_sumcheck* s, uint32_t* d_poly_out, uint32_t* d_weights_out) {
+  if (!s || !d_poly_out || !d_weights_out) return fail(LM_ERR_INVALID, "lm_sc_export_dev: null argument");
+  if (s->p_dim != 5) return fail(LM_ERR_INVALID, "lm_sc_export_dev: the polynomial has not been folded yet (base field)");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = ((size_t)5 << s->n_vars) * sizeof(uint32_t);
+  CU(cudaMemcpyAsync(d_poly_out, s->d_p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_weights_out, s->d_w, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
 static int sc_upload_point(lm_sumcheck* s, const uint32_t* point, uint32_t words) {
   lm_ctx* c = s->ctx;
   if (words > 64 * 5) return fail(LM_ERR_INVALID, "point too long");

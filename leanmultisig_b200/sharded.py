@@ -25,6 +25,12 @@ and is local down to 2^(5-g) fractions per rank; an all-gather of those gives th
 layer sumcheck folds the least-significant variable first: k - g local rounds with ONE all-reduce of (c0, c2) = 10 field
 words each, then an all-gather of the four folded values per rank and the last g rounds on 4 x G values on the host.
 
+WHIR product sumcheck (`ShardedProductSumcheck`): the first `folding` rounds fold the column bits (most significant
+first, poly/src/utils.rs:161-186), which every rank holds completely: local rounds with ONE all-reduce of (c0, c2) each.
+The next variables are the sharding bits; by then the tables are 2^(n - folding) EF entries in total, so one all-gather
+(device to device) rebuilds them on every rank and the remaining rounds, the STIR updates and the round commitments run
+replicated on the ordinary single-GPU session.
+
 The compute steps go through a backend object so that the CPU test tier can run the same orchestration with the
 oracle over gloo; the product backend is the CUDA library (`CudaBackend`), there is no CPU product path.
 """
@@ -296,6 +302,110 @@ class ShardedGkrQuotientProver(GkrQuotientProver):
             self.local = None
 
 
+def localize_statement(n_vars: int, folding: int, g: int, rank: int, selector: int, point):
+    """Restriction of the weight statement  w[x] += s * eq(point, x_inner) * [x_outer == selector]  (x = outer | inner,
+    inner = the low m = len(point) bits) to rank's shard.  Global index bits, most significant first: column (folding
+    bits), rank (g bits), position inside the shard.  Returns (local selector, local point, eq factor of the rank bits)
+    or None when the selector excludes this rank."""
+    m = len(point)
+    low = n_vars - folding - g                      # bits of the position inside the shard
+    keep, scale, sel = list(range(m)), F.ONE, selector
+    drop_sel = []
+    for t in range(g):                              # rank bit t sits at global bit position low + t
+        pos, bit = low + t, (rank >> t) & 1
+        if pos < m:                                 # inside the eq part: coordinate m - 1 - pos
+            x = point[m - 1 - pos]
+            scale = F.mul(scale, x if bit else F.sub(F.ONE, x))
+            keep.remove(m - 1 - pos)
+        else:                                       # inside the selector: bit pos - m
+            if ((selector >> (pos - m)) & 1) != bit:
+                return None
+            drop_sel.append(pos - m)
+    for b in sorted(drop_sel, reverse=True):
+        sel = ((sel >> (b + 1)) << b) | (sel & ((1 << b) - 1))
+    return sel, [point[j] for j in keep], scale
+
+
+class ShardedProductSumcheck:
+    """SumcheckSingle (crates/whir/src/open.rs:323-446) over the row-sharded stacked polynomial.  Collective: every rank
+    builds it from its shard (`shard_of`) and makes the same calls with the same challenges.  Statements (`add_eq`) must
+    be added before the first round; `add_base_eq`, `read`, `eval_poly`, `commit_poly` are available once the tables are
+    replicated, i.e. after `folding` folds."""
+
+    def __init__(self, backend, dist, shard_evals, n_vars: int, folding: int, live_len: int | None = None):
+        self.b, self.dist = backend, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.g = self.world.bit_length() - 1
+        assert self.world == 1 << self.g and n_vars - folding >= 2 * self.g and folding >= 1
+        self.n_vars_total, self.folding = n_vars, folding
+        self.local = backend.sumcheck(shard_evals, n_vars - self.g, live_len)
+        self.rep = None
+        self.folds = 0
+
+    @property
+    def n_vars(self) -> int:
+        return self.n_vars_total - self.folds
+
+    def add_eq(self, selector: int, point, scalar) -> None:
+        assert self.folds == 0, "statements are added before the first fold"
+        pt = [F.from_monty(x) for x in np.ascontiguousarray(point, dtype=np.uint32).reshape(-1, 5)]
+        loc = localize_statement(self.n_vars_total, self.folding, self.g, self.rank, selector, pt)
+        if loc is None:
+            return
+        sel, lp, scale = loc
+        lpm = np.stack([F.to_monty(x) for x in lp]) if lp else np.zeros((0, 5), dtype=np.uint32)
+        self.local.add_eq(sel, lpm, F.to_monty(F.mul(scale, F.from_monty(scalar))))
+
+    def _reduce(self, c0, c2):
+        if self.world == 1:
+            return c0, c2
+        both = self.b.all_reduce_field(self.dist, np.stack([c0, c2]))
+        return both[0], both[1]
+
+    def round(self):
+        return self.rep.round() if self.rep is not None else self._reduce(*self.local.round())
+
+    def _after_local_fold(self):
+        self.folds += 1
+        if self.folds == self.folding:
+            self.rep = self.b.sumcheck_gather(self.dist, self.local, self.n_vars_total - self.folding)
+            self.local.free()
+            self.local = None
+
+    def fold(self, r) -> None:
+        if self.rep is not None:
+            self.rep.fold(r)
+            self.folds += 1
+        else:
+            self.local.fold(r)
+            self._after_local_fold()
+
+    def fold_round(self, r):
+        if self.rep is not None:
+            self.folds += 1
+            return self.rep.fold_round(r)
+        if self.folds + 1 == self.folding:
+            self.local.fold(r)
+            self._after_local_fold()
+            return self.rep.round()
+        out = self._reduce(*self.local.fold_round(r))
+        self.folds += 1
+        return out
+
+    def __getattr__(self, name):
+        # add_base_eq / read / eval_poly / commit_poly / export_dev: the replicated single-GPU session
+        rep = self.__dict__.get("rep")
+        if rep is None or name.startswith("_"):
+            raise AttributeError(f"{name} is only available after the {self.__dict__.get('folding')} local folds")
+        return getattr(rep, name)
+
+    def free(self):
+        for s in (self.local, self.rep):
+            if s is not None:
+                s.free()
+        self.local = self.rep = None
+
+
 class CudaBackend:
     """Compute steps on one GPU through the C ABI; tensors are torch CUDA int32 (device memory + NCCL plumbing)."""
 
@@ -394,3 +504,23 @@ class CudaBackend:
         from .logup import GkrShardSession
 
         return GkrShardSession(self.ctx, nums, dens, n_vars, top_vars)
+
+    # ---- WHIR product sumcheck ------------------------------------------------------------------------------------
+    def sumcheck(self, evals, n_vars, live_len=None):
+        return self.ctx.sumcheck(evals, n_vars, live_len)
+
+    def sumcheck_gather(self, dist, local, n_vars_total):
+        """all-gather (device to device, rank order = the sharding bits) of the folded tables of `local` and a session on
+        the full tables"""
+        world = dist.get_world_size()
+        n_local = 5 << local.n_vars
+        mine = self.torch.empty((2, n_local), dtype=self.torch.int32, device="cuda")
+        local.export_dev(mine[0].data_ptr(), mine[1].data_ptr())
+        everyone = self.torch.empty((world, 2, n_local), dtype=self.torch.int32, device="cuda")
+        if world > 1:
+            dist.all_gather_into_tensor(everyone, mine)
+        else:
+            everyone[0] = mine
+        tables = everyone.permute(1, 0, 2).contiguous()          # [poly | weights][rank][local index]
+        self.torch.cuda.synchronize()
+        return self.ctx.sumcheck_from_dev(tables[0].data_ptr(), tables[1].data_ptr(), n_vars_total)

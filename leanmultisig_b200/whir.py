@@ -151,6 +151,10 @@ class ProductSumcheck:
         check(lib().lm_sc_eval_poly(self.handle, _p(_u32(point).reshape(-1, 5)), _p(out)))
         return out
 
+    def export_dev(self, d_poly_ptr: int, d_weights_ptr: int) -> None:
+        """copy the current EF tables into caller-owned device buffers (row-sharded sumcheck, sharded.py)"""
+        check(lib().lm_sc_export_dev(self.handle, C.c_void_p(d_poly_ptr), C.c_void_p(d_weights_ptr)))
+
     def commit_poly(self, folding_factor: int, log_inv_rate: int) -> Tree:
         root = np.empty(8, dtype=np.uint32)
         t = C.c_void_p()
@@ -232,6 +236,11 @@ class Context:
         live = (e.size // dim) if live_len is None else live_len
         h = C.c_void_p()
         check(lib().lm_sc_new(self.handle, e.ctypes.data_as(C.c_void_p), n_vars, dim, live, C.byref(h)))
+        return ProductSumcheck(self, h)
+
+    def sumcheck_from_dev(self, d_poly_ptr: int, d_weights_ptr: int, n_vars: int) -> ProductSumcheck:
+        h = C.c_void_p()
+        check(lib().lm_sc_new_from_dev(self.handle, C.c_void_p(d_poly_ptr), C.c_void_p(d_weights_ptr), n_vars, C.byref(h)))
         return ProductSumcheck(self, h)
 
     # ---- device-buffer API ------------------------------------------------------------------------------

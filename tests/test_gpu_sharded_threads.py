@@ -54,6 +54,21 @@ class ThreadBackend:
 
         return GkrShardSession(self.ctx, nums, dens, n_vars, top_vars)
 
+    def sumcheck(self, evals, n_vars, live_len=None):
+        return self.ctx.sumcheck(evals, n_vars, live_len)
+
+    def sumcheck_gather(self, d, local, n_vars_total):
+        import torch
+
+        n_local = 5 << local.n_vars
+        mine = torch.empty((2, n_local), dtype=torch.int32, device="cuda")
+        local.export_dev(mine[0].data_ptr(), mine[1].data_ptr())
+        torch.cuda.synchronize()
+        everyone = torch.stack(d.group.exchange(d.rank, mine))       # same device: the tensors are shared between threads
+        tables = everyone.permute(1, 0, 2).contiguous()
+        torch.cuda.synchronize()
+        return self.ctx.sumcheck_from_dev(tables[0].data_ptr(), tables[1].data_ptr(), n_vars_total)
+
     def all_reduce_field(self, d, words):
         parts = d.group.exchange(d.rank, np.asarray(words).astype(np.int64))
         return (sum(parts) % P).astype(np.uint32)
@@ -156,3 +171,49 @@ def test_gpu_sharded_air_threads(rng, world, table, log_rows):
         for r in range(log_rows):
             assert np.array_equal(bares[r], expected[r]), f"round {r}"
         assert np.array_equal(out, finals)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n_vars,folding,live_cols", [(2, 14, 5, 32), (4, 13, 4, 11), (8, 16, 7, 64)])
+def test_gpu_sharded_product_sumcheck_threads(rng, world, n_vars, folding, live_cols):
+    from leanmultisig_b200.sharded import ShardedProductSumcheck, shard_of
+
+    chunk = 1 << (n_vars - folding)
+    ev = np.zeros(1 << n_vars, dtype=np.uint32)
+    ev[: live_cols * chunk] = O.random_field(rng, live_cols * chunk)
+    g = world.bit_length() - 1
+    low = n_vars - folding - g
+    shapes = [(0, n_vars), (3 % (1 << folding), n_vars - folding), (5, low), (1, n_vars - 1), (2, low + 1), (0, low - 1)]
+    stmts = [(sel % (1 << (n_vars - m)), O.random_field(rng, (m, 5)), O.random_field(rng, 5)) for sel, m in shapes]
+    n_rounds = folding + 3
+    challenges = O.random_field(rng, (n_rounds, 5))
+    # single-process oracle session over the whole polynomial
+    w = np.zeros((1 << n_vars, 5), dtype=np.uint32)
+    for sel, pt, sc in stmts:
+        O.weights_add_eq(w, sel, pt, sc)
+    p, expected = ev, []
+    expected.append(O.prod_round(p, w))
+    for k in range(n_rounds):
+        p, w = O.fold_msb(p, challenges[k]), O.fold_msb(w, challenges[k])
+        expected.append(O.prod_round(p, w))
+
+    def rank_main(backend, dist, rank):
+        shard = shard_of(ev, n_vars, folding, rank, world).reshape(1 << folding, -1)[:live_cols].reshape(-1)
+        sc = ShardedProductSumcheck(backend, dist, shard, n_vars, folding)
+        for sel, pt, s in stmts:
+            sc.add_eq(sel, pt, s)
+        rounds = [sc.round()]
+        for k in range(n_rounds):
+            if k % 2 == 0:
+                rounds.append(sc.fold_round(challenges[k]))
+            else:
+                sc.fold(challenges[k])
+                rounds.append(sc.round())
+        tables = sc.read()
+        sc.free()
+        return rounds, tables
+
+    for rounds, (gp, gw) in run_ranks(world, rank_main):
+        for k, ((c0, c2), (e0, e2)) in enumerate(zip(rounds, expected)):
+            assert np.array_equal(c0, e0) and np.array_equal(c2, e2), f"round {k}"
+        assert np.array_equal(gp, p) and np.array_equal(gw, w)
