@@ -299,6 +299,35 @@ int lm_pow_grind(lm_ctx* ctx, const uint32_t state[16], uint32_t bits, uint64_t*
  * of challenger.rs:32-36 is sequential, one permutation per observation, so it is not a device job. */
 int lm_host_poseidon1_permute(uint32_t state[16]);
 
+/* ---- Host spine in C++ (csrc/spine.cu), built above the entry points of this header ---------------------------
+ * lm_fs mirrors ProverState + Challenger (crates/backend/fiat-shamir/src/prover.rs:28-178, challenger.rs:8-76): the
+ * Poseidon1 duplex runs on the host, pow_grinding searches on the device (lm_pow_grind).  A Rust integration keeps its
+ * own ProverState and does not need these; they exist so that callers without the Rust spine (the Python mirror, the
+ * benchmarks) do not pay an interpreter round trip per sumcheck round.  ctx may be NULL when pow_grinding is not used. */
+typedef struct lm_fs lm_fs;
+int lm_fs_new(lm_ctx* ctx, lm_fs** out);
+int lm_fs_free(lm_fs* fs);
+int lm_fs_add_scalars(lm_fs* fs, const uint32_t* words, uint64_t n);   /* add_base_scalars / add_extension_scalars */
+int lm_fs_observe(lm_fs* fs, const uint32_t* words, uint64_t n);       /* absorbed, not sent */
+int lm_fs_duplex(lm_fs* fs);
+/* prover.rs:105-128: coeffs n_coeffs x 5; eq_alpha != NULL absorbs expand_bare_to_full(coeffs, eq_alpha) */
+int lm_fs_add_sumcheck_polynomial(lm_fs* fs, const uint32_t* coeffs, uint32_t n_coeffs, const uint32_t* eq_alpha);
+int lm_fs_sample(lm_fs* fs, uint32_t n, uint32_t* out /* n x 5 */);     /* sample_vec */
+int lm_fs_sample_in_range(lm_fs* fs, uint32_t bits, uint32_t n, uint64_t* out);
+int lm_fs_pow_grinding(lm_fs* fs, uint32_t bits);
+int lm_fs_transcript_len(const lm_fs* fs, uint64_t* n_words);
+int lm_fs_transcript(const lm_fs* fs, uint32_t* out);
+int lm_fs_state(const lm_fs* fs, uint32_t state[16], int* rate_fresh);
+/* prove_gkr_quotient (crates/sub_protocols/src/quotient_gkr/mod.rs:31-141) end to end: top values, per-layer sumchecks
+ * (lm_gkr_round / build_bare_from_coeffs / lm_gkr_fold), inner evaluations.  out_point: n_vars x 5. */
+int lm_gkr_prove(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out_point, uint32_t out_claim_num[5],
+                 uint32_t out_claim_den[5]);
+/* prove_batched_air_sumcheck (crates/sub_protocols/src/air_sumcheck.rs:636-681) over n_sessions sessions: eq_factors =
+ * the sessions' eq_factor arrays one after the other (n_vars_i x 5 each), sums = n_sessions x 5 initial sums.
+ * out_challenges: max_i n_vars_i x 5; afterwards lm_air_final gives each session's column evaluations. */
+int lm_air_prove_batched(lm_air* const* airs, uint32_t n_sessions, const uint32_t* eq_factors, const uint32_t* sums,
+                         const uint32_t eta[5], lm_fs* fs, uint32_t* out_challenges, uint32_t* out_n_rounds);
+
 #ifdef __cplusplus
 }
 #endif

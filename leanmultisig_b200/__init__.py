@@ -6,8 +6,9 @@ Python host side used by the tests and the benchmark: it mirrors the reference's
 holds no arithmetic of its own.
 """
 from ._lib import LIB_PATH, LmError, build, declared_symbols, lib  # noqa: F401
-from .air import AirSumcheckSession, fill_trace_poseidon_16, prove_batched_air_sumcheck  # noqa: F401
-from .fiat_shamir import ProverState  # noqa: F401
+from .air import (AirSumcheckSession, fill_trace_poseidon_16, prove_batched_air_sumcheck,  # noqa: F401
+                  prove_batched_air_sumcheck_native)
+from .fiat_shamir import NativeProverState, ProverState  # noqa: F401
 from .logup import GkrQuotientProver, finger_print  # noqa: F401
 from .whir import Context, DeviceBuffer, ProductSumcheck, SparseStatement, Tree, WhirProver, Witness  # noqa: F401
 from .whir_config import WhirConfig  # noqa: F401

@@ -128,6 +128,20 @@ def lib() -> C.CDLL:
             "lm_poseidon16_fill_trace": [vp, C.POINTER(vp), u64],
             "lm_dev_poseidon16_fill_trace": [vp, vp, u64],
             "lm_host_poseidon1_permute": [u32p],
+            "lm_fs_new": [vp, C.POINTER(vp)],
+            "lm_fs_free": [vp],
+            "lm_fs_add_scalars": [vp, u32p, u64],
+            "lm_fs_observe": [vp, u32p, u64],
+            "lm_fs_duplex": [vp],
+            "lm_fs_add_sumcheck_polynomial": [vp, u32p, u32, u32p],
+            "lm_fs_sample": [vp, u32, u32p],
+            "lm_fs_sample_in_range": [vp, u32, u32, u64p],
+            "lm_fs_pow_grinding": [vp, u32],
+            "lm_fs_transcript_len": [vp, u64p],
+            "lm_fs_transcript": [vp, u32p],
+            "lm_fs_state": [vp, u32p, C.POINTER(C.c_int)],
+            "lm_gkr_prove": [vp, vp, u32p, u32p, u32p, u32p],
+            "lm_air_prove_batched": [C.POINTER(vp), u32, u32p, u32p, u32p, vp, u32p, u32p],
         }
         for name, args in sig.items():
             fn = getattr(L, name)

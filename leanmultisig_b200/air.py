@@ -183,6 +183,23 @@ def prove_batched_air_sumcheck(sessions, eta, absorb_and_sample):
     return challenges
 
 
+def prove_batched_air_sumcheck_native(sessions, eta, native_state):
+    """prove_batched_air_sumcheck with the round loop in the library's C++ spine (lm_air_prove_batched): the sessions'
+    device handles are driven directly, `native_state` is a fiat_shamir.NativeProverState.  Returns the challenges; the
+    sessions' `final_column_evals()` are valid afterwards (their Python-side round bookkeeping is not advanced)."""
+    n = len(sessions)
+    handles = (C.c_void_p * n)(*[s.handle for s in sessions])
+    eqs = np.concatenate([np.stack([F.to_monty(e) for e in s.eq_factor]) for s in sessions]).astype(np.uint32)
+    sums = np.stack([s.sum() for s in sessions]).astype(np.uint32)
+    n_rounds = max(s.initial_n_vars() for s in sessions)
+    out = np.empty((n_rounds, 5), dtype=np.uint32)
+    nr = C.c_uint32()
+    check(lib().lm_air_prove_batched(handles, n, _p(np.ascontiguousarray(eqs)), _p(np.ascontiguousarray(sums)), _p(_u32(eta)),
+                                     native_state.handle, _p(out), C.byref(nr)))
+    assert nr.value == n_rounds
+    return [out[i].copy() for i in range(n_rounds)]
+
+
 def fill_trace_poseidon_16(ctx, trace) -> None:
     """fill_trace_poseidon_16 (crates/lean_vm/src/tables/poseidon_16/trace_gen.rs:10-43): `trace` is the list of the 109
     base-field columns (numpy uint32, equal length); columns 25.. are overwritten in place from flag_permute and the inputs."""

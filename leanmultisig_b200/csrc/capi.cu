@@ -47,6 +47,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 }  // namespace
 
+// error reporting for the other translation units of the library (spine.cu)
+int lm_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+
 // Size-keyed cache of device allocations: a commit needs three GiB-scale buffers and cudaMalloc / cudaFree of that
 // size cost milliseconds each (the reference resets a bump arena per proof for the same reason,
 // crates/backend/zk-alloc/src/lib.rs:102-115).

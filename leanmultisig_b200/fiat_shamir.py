@@ -132,3 +132,80 @@ class ProverState:
         if lane & ((1 << bits) - 1):
             raise RuntimeError("device PoW witness rejected by the host sponge")
         self.transcript.append(int(wm[0]))
+
+
+class NativeProverState:
+    """The same trait surface on the C++ transcript of the library (lm_fs, csrc/spine.cu).  Use it with the native
+    drivers (`GkrQuotientProver.prove_native`, `prove_batched_air_sumcheck_native`), which run a whole protocol without
+    returning to Python between rounds; every method of `ProverState` is available, so the WHIR prover and the Logup
+    host code work on it unchanged."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib().lm_fs_new(ctx.handle if ctx is not None else None, C.byref(h)))
+        self.handle = h
+        self.merkle_paths: list[list] = []
+
+    def _words(self, a):
+        s = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1)
+        return s, s.ctypes.data_as(u32p)
+
+    def add_base_scalars(self, scalars) -> None:
+        s, p = self._words(scalars)
+        check(lib().lm_fs_add_scalars(self.handle, p, s.size))
+
+    add_extension_scalars = add_base_scalars
+
+    def observe_scalars(self, scalars) -> None:
+        s, p = self._words(scalars)
+        check(lib().lm_fs_observe(self.handle, p, s.size))
+
+    def duplex(self) -> None:
+        check(lib().lm_fs_duplex(self.handle))
+
+    def add_sumcheck_polynomial(self, coeffs, eq_alpha=None) -> None:
+        c, p = self._words(coeffs)
+        if eq_alpha is None:
+            check(lib().lm_fs_add_sumcheck_polynomial(self.handle, p, c.size // 5, None))
+        else:
+            a, pa = self._words(eq_alpha)
+            check(lib().lm_fs_add_sumcheck_polynomial(self.handle, p, c.size // 5, pa))
+
+    def hint_merkle_paths(self, paths) -> None:
+        self.merkle_paths.append(list(paths))
+
+    def sample_vec(self, n: int) -> list[np.ndarray]:
+        out = np.empty((max(n, 1), 5), dtype=np.uint32)
+        check(lib().lm_fs_sample(self.handle, n, out.ctypes.data_as(u32p)))
+        return [out[i].copy() for i in range(n)]
+
+    def sample(self) -> np.ndarray:
+        return self.sample_vec(1)[0]
+
+    def sample_in_range(self, bits: int, n_samples: int) -> list[int]:
+        out = np.empty(max(n_samples, 1), dtype=np.uint64)
+        check(lib().lm_fs_sample_in_range(self.handle, bits, n_samples, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return [int(x) for x in out[:n_samples]]
+
+    def pow_grinding(self, bits: int) -> None:
+        check(lib().lm_fs_pow_grinding(self.handle, bits))
+
+    @property
+    def transcript(self) -> list[int]:
+        n = C.c_uint64()
+        check(lib().lm_fs_transcript_len(self.handle, C.byref(n)))
+        out = np.empty(max(n.value, 1), dtype=np.uint32)
+        check(lib().lm_fs_transcript(self.handle, out.ctypes.data_as(u32p)))
+        return [int(x) for x in out[: n.value]]
+
+    @property
+    def state(self) -> np.ndarray:
+        st = np.empty(16, dtype=np.uint32)
+        check(lib().lm_fs_state(self.handle, st.ctypes.data_as(u32p), None))
+        return st
+
+    def free(self):
+        if self.handle:
+            check(lib().lm_fs_free(self.handle))
+            self.handle = None

@@ -108,6 +108,14 @@ class GkrQuotientProver:
 
     _sample_alpha = None
 
+    def prove_native(self, native_state):
+        """prove_gkr_quotient with the round loop, the transcript and the per-round field arithmetic in the library's C++
+        spine (lm_gkr_prove): same transcript and outputs as prove_with_state, no interpreter round trip per round."""
+        q, cn, cd = (np.empty(5, dtype=np.uint32) for _ in range(3))
+        pt = np.empty((self.n_vars, 5), dtype=np.uint32)
+        check(lib().lm_gkr_prove(self.handle, native_state.handle, _p(q), _p(pt), _p(cn), _p(cd)))
+        return q, pt, cn, cd
+
     def prove(self, add_scalars, add_sumcheck_poly, sample, sample_point=None):
         """returns (quotient, point, claim_num, claim_den) as Montgomery-form arrays"""
         tn, td = self.top()

@@ -368,3 +368,43 @@ def test_gpu_air_shard_sessions_add_up_to_the_whole_table(ctx, rng, table, L, G)
     assert np.array_equal(tail.final_column_evals(), finals)
     for s in shards + [tail]:
         s.free()
+
+
+@pytest.mark.gpu
+def test_gpu_batched_air_sumcheck_native_spine_matches_python_spine(ctx, rng):
+    """lm_air_prove_batched (C++ spine) against prove_batched_air_sumcheck driven from Python: three sessions of different
+    heights and degrees (execution 2^9, extension_op 2^7, poseidon16 2^6) joined back-loaded; same transcript, same
+    challenges, same final column evaluations."""
+    import leanmultisig_b200 as lm
+
+    shapes = [(0, 9), (1, 7), (2, 6)]
+    ap, la, beta = extras(rng)
+    data = []
+    for table, L in shapes:
+        n_cols, _, _ = O.air_shape(table)
+        data.append((table, O.random_field(rng, (n_cols, 1 << L)), O.random_field(rng, (L, 5)), O.random_field(rng, 5)))
+    eta = O.random_field(rng, 5)
+
+    def sessions():
+        return [lm.AirSumcheckSession(ctx, t, list(cols), eqf, s, ap, la, beta) for t, cols, eqf, s in data]
+
+    ps_py = lm.ProverState(ctx)
+
+    def absorb_and_sample(coeffs):
+        ps_py.add_sumcheck_polynomial(coeffs)
+        return ps_py.sample()
+
+    s_py = sessions()
+    ch_py = lm.prove_batched_air_sumcheck(s_py, eta, absorb_and_sample)
+    finals_py = [s.final_column_evals() for s in s_py]
+    ps_n = lm.NativeProverState(ctx)
+    s_n = sessions()
+    ch_n = lm.prove_batched_air_sumcheck_native(s_n, eta, ps_n)
+    finals_n = [s.final_column_evals() for s in s_n]
+    assert ps_n.transcript == ps_py.transcript
+    assert np.array_equal(np.stack(ch_n), np.stack(ch_py))
+    for a, b in zip(finals_n, finals_py):
+        assert np.array_equal(a, b)
+    for s in s_py + s_n:
+        s.free()
+    ps_n.free()

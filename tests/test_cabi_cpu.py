@@ -79,3 +79,39 @@ def test_kernel_arithmetic_on_host_matches_oracle(hostcheck, rng):
         assert hostcheck.hc_kb_add(u, v) == (u + v) % O.P
         assert hostcheck.hc_kb_sub(u, v) == (u - v) % O.P
     assert hostcheck.hc_r2() == pow(2, 64, O.P)
+
+
+def test_native_prover_state_matches_the_python_transcript():
+    """lm_fs (C++ ProverState, csrc/spine.cu) against the Python mirror and the oracle's challenger on one script of
+    absorb / squeeze operations: identical samples, transcript and sponge state.  Host code only (no device)."""
+    import numpy as np
+
+    import leanmultisig_b200 as lm
+    import oracle as O
+    from oracle import whir as W
+
+    rng = np.random.default_rng(5)
+    script = [("scalars", O.random_field(rng, 13)), ("sample_vec", 3), ("poly", O.random_field(rng, (4, 5)), None),
+              ("sample", None), ("poly", O.random_field(rng, (3, 5)), O.random_field(rng, 5)), ("sample", None),
+              ("duplex", None), ("sample_in_range", 9, 11), ("observe", O.random_field(rng, 8)), ("sample_vec", 4),
+              ("scalars", O.random_field(rng, 40)), ("sample", None)]
+    outs = []
+    for ps in (lm.ProverState(), lm.NativeProverState(), W.ProverState()):
+        got = []
+        for op in script:
+            if op[0] == "scalars":
+                ps.add_extension_scalars(op[1])
+            elif op[0] == "observe":
+                ps.observe_scalars(op[1])
+            elif op[0] == "poly":
+                ps.add_sumcheck_polynomial(op[1], op[2])
+            elif op[0] == "duplex":
+                ps.duplex()
+            elif op[0] == "sample":
+                got.append([int(x) for x in ps.sample()])
+            elif op[0] == "sample_vec":
+                got.append([[int(x) for x in v] for v in ps.sample_vec(op[1])])
+            elif op[0] == "sample_in_range":
+                got.append(ps.sample_in_range(op[1], op[2]))
+        outs.append((got, list(ps.transcript)))
+    assert outs[0] == outs[1] == outs[2]

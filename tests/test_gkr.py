@@ -177,3 +177,35 @@ def test_gpu_finger_print(rng):
     al, c = O.random_field(rng, (5, 5)), O.random_field(rng, 5)
     assert np.array_equal(lm.finger_print(ctx, data, al, c), O.finger_print(data, al, c))
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_vars,active", [(7, 100), (11, 2000), (14, 16000)])
+def test_gpu_gkr_native_spine_matches_python_spine(rng, n_vars, active):
+    """lm_gkr_prove (round loop + transcript in C++, csrc/spine.cu) produces the transcript and outputs of the Python-driven
+    prover and of the oracle's CPU prover; the oracle verifier accepts it."""
+    import leanmultisig_b200 as lm
+    from oracle import logup as OL
+    from oracle import whir as W
+
+    ctx = lm.Context(0, 20)
+    nums, dens = O.random_field(rng, active), O.random_field(rng, (active, 5))
+    ps_o = W.ProverState()
+    q_o, pt_o, cn_o, cd_o = OL.prove_gkr_quotient_cpu(ps_o, nums, dens)
+    p1 = lm.GkrQuotientProver(ctx, nums, dens)
+    ps_py = lm.ProverState(ctx)
+    out_py = p1.prove_with_state(ps_py)
+    p1.free()
+    p2 = lm.GkrQuotientProver(ctx, nums, dens)
+    ps_n = lm.NativeProverState(ctx)
+    out_n = p2.prove_native(ps_n)
+    p2.free()
+    assert ps_n.transcript == ps_py.transcript == ps_o.transcript
+    for a, b in zip(out_n, out_py):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out_n[0], W.tm(q_o)) and np.array_equal(out_n[2], W.tm(cn_o)) and np.array_equal(out_n[3], W.tm(cd_o))
+    vs = W.VerifierState(ps_n.transcript, [])
+    OL.verify_gkr_quotient(vs, n_vars)
+    assert vs.off == len(ps_n.transcript)
+    ps_n.free()
+    ctx.close()

@@ -36,6 +36,13 @@ bytes_unfused = 22 * n * 4 + 22 * (n // 2) * 20 + sum(22 * (n >> k) * 20 + 22 * 
 tot = sum(t_round) + sum(t_fold)
 print(f"  algorithmic bytes (unfused) {bytes_unfused/2**30:.2f} GiB -> {bytes_unfused/tot/1e9:.1f} GB/s")
 
+# ---- the same AIR sumcheck with the round loop in the C++ spine (lm_air_prove_batched)
+sess = lm.AirSumcheckSession(ctx, 0, cols, eqf, rf(5), ap, la, beta)
+ps = lm.NativeProverState(ctx)
+t0 = time.perf_counter(); lm.prove_batched_air_sumcheck_native([sess], rf(5), ps); t_nat = time.perf_counter() - t0
+sess.free()
+print(f"  native spine (C++ round loop + transcript): {t_nat*1e3:.1f} ms for {log_rows} rounds -> {bytes_unfused/t_nat/1e9:.1f} GB/s")
+
 # ---- GKR
 N = (1 << log_gkr) - 12345
 nums, dens = rf(N), rf((N, 5))
@@ -48,4 +55,10 @@ class T:
 tr = T()
 t0 = time.perf_counter(); g.prove(tr.add_scalars, tr.add_sumcheck_poly, tr.sample); t_down = time.perf_counter() - t0
 print(f"GKR 2^{log_gkr}: new (H2D + up pass) {t_up*1e3:.1f} ms; down pass {t_down*1e3:.1f} ms over {tr.n} rounds")
+g.free()
+g = lm.GkrQuotientProver(ctx, nums, dens)
+ps = lm.NativeProverState(ctx)
+t0 = time.perf_counter(); g.prove_native(ps); t_nat = time.perf_counter() - t0
+gkr_bytes = 230 * N
+print(f"  native spine: down pass {t_nat*1e3:.1f} ms; up + down algorithmic bytes ~230 N = {gkr_bytes/2**30:.2f} GiB")
 g.free(); ctx.close()
