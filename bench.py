@@ -365,6 +365,7 @@ def run_b200_sharded(args, rank, local_rank, world):
     barrier()
     launches = l.lm_kernel_launches() - launches0
     t_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    phases = backend.phase_times() if os.environ.get("LM_SHARD_TIMING") else None
     # e2e: pinned host shard -> device -> commit -> root on the host
     for _ in range(min(args.warmup, 3)):
         sc.commit(host.cuda(non_blocking=True))
@@ -404,6 +405,8 @@ def run_b200_sharded(args, rank, local_rank, world):
                     "h2d_bytes_per_step": live * 4, "d2h_bytes_per_step": 32 * world},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
+        if phases:
+            line["phases_ms_rank0_last_step"] = phases
         print(json.dumps(line), flush=True)
     ctx.close()
     dist.destroy_process_group()

@@ -271,12 +271,53 @@ __global__ void ntt_layer_mapped_kernel(uint32_t* __restrict__ mat, uint64_t w4,
   *hi = b;
 }
 
+// All log2(NB) mapped layers in one pass: a thread holds the NB rows (one per block m) of its (j', 16-byte column group)
+// in registers and runs the radix-NB butterfly network on them — one read and one write of the local matrix instead of
+// one per layer.  Requires 2^l_first == block (the row-sharded commit's case): layer l_first + s pairs m and m + 2^s.
+template <int NB_LOG>
+__global__ void __launch_bounds__(256)
+ntt_layers_mapped_fused_kernel(uint32_t* __restrict__ mat, uint64_t w4, int log_h, int l_first, uint64_t run, uint64_t block,
+                               uint64_t offset, const uint32_t* __restrict__ tw, int tw_shift) {
+  constexpr int NB = 1 << NB_LOG;
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= run * w4) return;
+  const uint64_t c4 = idx % w4, jp = idx / w4;
+  uint4 v[NB];
+#pragma unroll
+  for (int m = 0; m < NB; m++) v[m] = *(reinterpret_cast<const uint4*>(mat + ((uint64_t)m * run + jp) * (w4 * 4)) + c4);
+#pragma unroll
+  for (int s = 0; s < NB_LOG; s++) {
+    const int l = l_first + s;
+#pragma unroll
+    for (int m = 0; m < NB; m++) {
+      if (m & (1 << s)) continue;
+      const uint64_t grow = (uint64_t)m * block + offset + jp;  // global row of the low element
+      const uint64_t e = (grow & (((uint64_t)1 << l) - 1)) << (log_h - l - 1);
+      bfly4(v[m], v[m | (1 << s)], __ldg(tw + (e << tw_shift)));
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NB; m++) *(reinterpret_cast<uint4*>(mat + ((uint64_t)m * run + jp) * (w4 * 4)) + c4) = v[m];
+}
+
 cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, unsigned log_h, unsigned l_first,
                               uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, const uint32_t* d_tw,
                               unsigned tw_log_n) {
   if (w % 4 != 0 || log_h > tw_log_n || l_first > log_h || n_blocks < 2 || (((uint64_t)1 << l_first) < block))
     return cudaErrorInvalidValue;
   const int tw_shift = (int)tw_log_n - (int)log_h;
+  if ((((uint64_t)1 << l_first) == block) && n_blocks == ((uint64_t)1 << (log_h - l_first)) && n_blocks <= 8) {
+    const uint64_t items = run * (w / 4);
+    const unsigned grid = (unsigned)((items + 255) / 256);
+    if (n_blocks == 2)
+      ntt_layers_mapped_fused_kernel<1><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift);
+    else if (n_blocks == 4)
+      ntt_layers_mapped_fused_kernel<2><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift);
+    else
+      ntt_layers_mapped_fused_kernel<3><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift);
+    count_launch();
+    return cudaGetLastError();
+  }
   const uint64_t total = (n_blocks / 2) * run * (w / 4);
   for (unsigned l = l_first; l < log_h; l++) {
     ntt_layer_mapped_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l, n_blocks, run,

@@ -9,8 +9,8 @@ index (column c | position s); rank q holds, for every column, the slice of s wh
   2. all-to-all rank q sends rows [q' run, (q'+1) run) of T_q to rank q' (run = h / G^2): (G-1)/G of its block.
   3. combine    the last g layers pair rows that differ only in the block index m, now all local
                 (lm_dev_dft_layers_mapped).  Rank q' ends up with G runs of `run` consecutive codeword rows.
-  4. Merkle     leaf sponge + subtree per run (local), all-gather of the G^2 subtree roots (32 B each), the top
-                2g levels are replicated.
+  4. Merkle     leaf sponge over all local rows and the G subtrees (one per run) level by level as one forest, all-gather
+                of the G^2 subtree roots (32 B each), the top 2g levels are replicated.
 
 AIR sumcheck (`ShardedAirSumcheckSession`): rank q holds rows [q 2^(n-g), (q+1) 2^(n-g)) of every column of a table.  The
 session folds the least-significant row bit first (air_sumcheck.rs:144-151), so the first n - g rounds touch only local
@@ -94,25 +94,35 @@ class ShardedCommit:
     def commit(self, shard):
         geo, b = self.geo, self.b
         w = self.cols
+        mark = getattr(b, "mark", None) or (lambda name: None)  # optional per-phase device timestamps (CudaBackend)
+        mark("start")
         # 1. local transform of the shard
         t_local = b.reorder_and_dft(shard, geo.n_vars - geo.g, geo.folding, geo.log_inv_rate, w)  # block x w
+        mark("local_dft")
         # 2. exchange: equal splits of `run` rows, received in block order m = source rank
         mat = b.empty_like(t_local)
         if self.world > 1:
             b.all_to_all(self.dist, mat, t_local)
         else:
             mat = t_local
+        mark("all_to_all")
         # 3. last g layers on the local rows
         if geo.g:
             b.dft_layers_mapped(mat, w, geo.log_h, geo.log_h - geo.g, self.world, geo.run, geo.block, self.rank * geo.run)
+        mark("last_layers")
         self.codeword = mat
-        # 4. one subtree per run, then the replicated top
-        self.subtrees = [b.merkle_tree(b.rows(mat, m * geo.run, geo.run), self.full_cols, w) for m in range(self.world)]
-        my_roots = b.stack_roots(self.subtrees)                      # world x 8
+        # 4. the G subtrees of this rank as ONE forest: leaf digests of all local rows in one launch, then level by level
+        #    over the concatenated runs (a run is a power-of-two block of the local matrix, so level l of the forest is the
+        #    concatenation of level l of every subtree); the levels above log2(run) are not used
+        self.forest = b.merkle_tree(mat, self.full_cols, w)          # (2 block - 1) x 8, level-major
+        mark("subtrees")
+        off = 2 * geo.block - ((2 * geo.block) >> geo.log_run)
+        my_roots = b.rows(self.forest, off, self.world)              # world x 8: level log2(run) = the subtree roots
         all_roots = b.all_gather_roots(self.dist, my_roots)          # [rank][m] -> world x world x 8
         top_layer0 = b.permute_roots(all_roots)                      # index m * world + rank
         self.top = b.merkle_levels(top_layer0)                       # (2 G^2 - 1) x 8
         self.root = b.to_host(self.top)[-1]
+        mark("top")
         return self.root
 
     def open_local(self, row: int):
@@ -121,11 +131,10 @@ class ShardedCommit:
         assert geo.owner(row) == self.rank
         m, rest = divmod(row, geo.block)
         jp = rest % geo.run
-        sub = b.to_host(self.subtrees[m])
         path = []
-        off, n, idx = 0, geo.run, jp
+        off, n, idx = 0, geo.block, m * geo.run + jp
         for _ in range(geo.log_run):
-            path.append(sub[off + (idx ^ 1)])
+            path.append(b.to_host(b.rows(self.forest, off + (idx ^ 1), 1)).reshape(-1))
             off += n
             n >>= 1
             idx >>= 1
@@ -419,6 +428,9 @@ class CudaBackend:
         self.stream = torch.cuda.Stream()
         torch.cuda.set_stream(self.stream)
         ctx.set_stream(self.stream.cuda_stream)
+        import os
+
+        self._timing, self._marks = bool(os.environ.get("LM_SHARD_TIMING")), []
 
     def to_device(self, a: np.ndarray):
         return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
@@ -440,9 +452,23 @@ class CudaBackend:
         return out
 
     def all_to_all(self, dist, out, inp):
-        self.ctx.sync()
+        # torch's current stream IS the library's stream: NCCL orders itself after the transform and the next kernel after
+        # the exchange through stream events, no host synchronisation
         dist.all_to_all_single(out, inp)
+
+    def mark(self, name):
+        """per-phase device timestamps when LM_SHARD_TIMING is set (read with phase_times())"""
+        if not self._timing:
+            return
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.stream)
+        if name == "start":
+            self._marks = []
+        self._marks.append((name, ev))
+
+    def phase_times(self) -> dict:
         self.torch.cuda.synchronize()
+        return {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._marks, self._marks[1:])}
 
     def dft_layers_mapped(self, mat, w, log_h, l_first, n_blocks, run, block, offset):
         self.check(self.lib.lm_dev_dft_layers_mapped(self.ctx.handle, mat.data_ptr(), w, log_h, l_first, n_blocks, run, block, offset))
@@ -453,11 +479,7 @@ class CudaBackend:
         self.check(self.lib.lm_dev_merkle_tree(self.ctx.handle, rows.data_ptr(), h, w, full_cols, eff_cols, layers.data_ptr()))
         return layers
 
-    def stack_roots(self, subtrees):
-        return self.torch.stack([s[-1] for s in subtrees])
-
     def all_gather_roots(self, dist, my_roots):
-        self.ctx.sync()
         world = dist.get_world_size()
         out = self.torch.empty((world,) + tuple(my_roots.shape), dtype=my_roots.dtype, device=my_roots.device)
         if world > 1:
@@ -476,7 +498,6 @@ class CudaBackend:
         layers[:n] = layer0
         if n > 1:
             self.check(self.lib.lm_dev_merkle_levels(self.ctx.handle, layers.data_ptr(), n))
-        self.ctx.sync()
         return layers
 
     # ---- AIR sumcheck -----------------------------------------------------------------------------------------

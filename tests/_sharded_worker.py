@@ -43,9 +43,6 @@ class OracleBackend:
     def merkle_tree(self, rows, full_cols, eff_cols):
         return O.merkle_tree(rows, full_cols, eff_cols)
 
-    def stack_roots(self, subtrees):
-        return np.stack([s[-1] for s in subtrees])
-
     def all_gather_roots(self, d, my_roots):
         world = d.get_world_size()
         outs = [torch.empty(my_roots.shape, dtype=torch.int32) for _ in range(world)]

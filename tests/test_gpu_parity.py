@@ -174,3 +174,23 @@ def test_rs_linearity_at_full_size(ctx, rng):
         val = O.mle_eval(chunk, pt)
         assert val[0] == rows[0][col] and not val[1:].any()
     tree.free()
+
+
+@pytest.mark.parametrize("log_h,g,w", [(10, 1, 8), (11, 2, 16), (12, 3, 64), (9, 3, 4), (12, 4, 8)])
+def test_dft_layers_mapped(ctx, rng, log_h, g, w):
+    """last g butterfly layers on the rows one rank holds after the exchange of the row-sharded commit
+    (lm_dev_dft_layers_mapped: fused radix-2^g kernel for g <= 3, one launch per layer otherwise) against the oracle,
+    for every rank's row set"""
+    from leanmultisig_b200._lib import check, lib
+
+    G = 1 << g
+    h = 1 << log_h
+    block, run = h // G, h // (G * G)
+    for rank in (0, G - 1, G // 2):
+        mat = O.random_field(rng, (G * run, w))
+        exp = O.dft_layers_mapped(mat.copy(), log_h, log_h - g, G, run, block, rank * run)
+        d = ctx.to_device(mat)
+        check(lib().lm_dev_dft_layers_mapped(ctx.handle, d.ptr, w, log_h, log_h - g, G, run, block, rank * run))
+        got = d.download(mat.shape)
+        d.free()
+        assert np.array_equal(got, exp), (log_h, g, w, rank)
