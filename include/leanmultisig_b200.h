@@ -264,6 +264,21 @@ int lm_dev_reorder_and_dft(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars
                            uint32_t folding_factor, uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out);
 /* EvalsDft::dft_batch_by_evals (crates/whir/src/dft.rs:79), in place on a height x width matrix */
 int lm_dev_dft(lm_ctx* ctx, uint32_t* d_mat, uint64_t height, uint64_t width);
+/* Local transform of ONE rank of the row-sharded commit with the exchange fused into its last pass: row i of
+ * the rank's 2^(n_vars + log_inv_rate - folding) x dft_n_cols result is stored straight into peer_mats[i >> log_run] at
+ * local row (rank << log_run) | (i mod 2^log_run), log_run = log2(rows / world) — NVLink stores through peer pointers
+ * (CUDA IPC mappings of the other ranks' matrices; peer_mats[rank] = the caller's own), so no separate all-to-all runs.
+ * d_work: rows x dft_n_cols words of scratch for the passes before the last one.  The caller orders the ranks (a
+ * stream-ordered barrier) before reading its matrix.  Base field only, dft_n_cols % 4 == 0. */
+int lm_dev_reorder_and_dft_scatter(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding_factor,
+                                   uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_work, const uint64_t* peer_mats,
+                                   uint32_t world, uint32_t rank);
+/* CUDA IPC plumbing for the peer matrices (one process per GPU): the owner exports a buffer it got from lm_dev_alloc, the
+ * other ranks open the 64-byte handle from THEIR device (peer access over NVLink is enabled by the open) and close it at
+ * the end.  The handle bytes travel through the caller's own channel (torch.distributed all_gather_object here). */
+int lm_dev_ipc_export(lm_ctx* ctx, const void* d_ptr, uint8_t handle[64]);
+int lm_dev_ipc_open(lm_ctx* ctx, const uint8_t handle[64], void** d_peer);
+int lm_dev_ipc_close(lm_ctx* ctx, void* d_peer);
 /* the last layers [l_first, log_h) of dft_batch_by_evals on the rows one rank holds after the all-to-all of a
  * row-sharded commit: local row (m, j'), m < n_blocks, j' < run, is global row m * block + offset + j' */
 int lm_dev_dft_layers_mapped(lm_ctx* ctx, uint32_t* d_mat, uint64_t width, uint32_t log_h, uint32_t l_first,

@@ -329,6 +329,56 @@ int lm_dev_reorder_and_dft(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, 
   return LM_OK;
 }
 
+int lm_dev_reorder_and_dft_scatter(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding, uint32_t log_inv_rate,
+                                   uint32_t dft_n_cols, uint32_t* d_work, const uint64_t* peer_mats, uint32_t world,
+                                   uint32_t rank) {
+  if (!c || !d_evals || !d_work || !peer_mats) return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft_scatter: null argument");
+  if (world < 2 || world > 16 || (world & (world - 1)) || rank >= world)
+    return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft_scatter: world %u / rank %u", world, rank);
+  if (folding > n_vars) return fail(LM_ERR_INVALID, "folding_factor %u > n_vars %u", folding, n_vars);
+  if (dft_n_cols > (1u << folding) || dft_n_cols % 4 || dft_n_cols == 0)
+    return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft_scatter: dft_n_cols %u must be a multiple of 4 and <= 2^folding", dft_n_cols);
+  if (n_vars + log_inv_rate - folding > c->tw_log_n)
+    return fail(LM_ERR_INVALID, "domain 2^%u exceeds the twiddle table 2^%u given to lm_init",
+                n_vars + log_inv_rate - folding, c->tw_log_n);
+  CU(cudaSetDevice(c->device));
+  uint32_t* peers[16];
+  for (uint32_t q = 0; q < world; q++) {
+    if (!peer_mats[q]) return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft_scatter: peer %u is null", q);
+    peers[q] = reinterpret_cast<uint32_t*>(peer_mats[q]);
+  }
+  CU(lm::ntt_reorder_and_dft_scatter(c->stream, d_evals, n_vars, folding, log_inv_rate, dft_n_cols, d_work, peers, world, rank,
+                                     c->d_tw, c->tw_log_n));
+  return LM_OK;
+}
+
+int lm_dev_ipc_export(lm_ctx* c, const void* d_ptr, uint8_t handle[64]) {
+  if (!c || !d_ptr || !handle) return fail(LM_ERR_INVALID, "lm_dev_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+  memcpy(handle, &h, 64);
+  return LM_OK;
+}
+
+int lm_dev_ipc_open(lm_ctx* c, const uint8_t handle[64], void** d_peer) {
+  if (!c || !handle || !d_peer) return fail(LM_ERR_INVALID, "lm_dev_ipc_open: null argument");
+  CU(cudaSetDevice(c->device));  // opened from the device whose kernels will store through the mapping
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess));
+  return LM_OK;
+}
+
+int lm_dev_ipc_close(lm_ctx* c, void* d_peer) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_ipc_close: null argument");
+  if (!d_peer) return LM_OK;
+  CU(cudaSetDevice(c->device));
+  CU(cudaIpcCloseMemHandle(d_peer));
+  return LM_OK;
+}
+
 int lm_dev_dft(lm_ctx* c, uint32_t* d_mat, uint64_t h, uint64_t w) {
   if (!c) return fail(LM_ERR_INVALID, "lm_dev_dft: ctx is null");
   if (h == 0 || (h & (h - 1))) return fail(LM_ERR_INVALID, "lm_dev_dft: height %llu is not a power of two", (unsigned long long)h);

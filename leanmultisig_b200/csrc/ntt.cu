@@ -83,6 +83,7 @@ __device__ __forceinline__ void bfly4(uint4& a, uint4& b, uint32_t t) {
 #ifndef NTT_MIN_BLOCKS
 #define NTT_MIN_BLOCKS 3
 #endif
+constexpr int NTT_MAX_PEERS = 16;
 constexpr int TILE_COLS = 8;       // u32 columns per tile = 32 B per row
 constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory
 
@@ -134,6 +135,15 @@ __global__ void ntt_pass_twiddles_kernel(uint32_t* __restrict__ tw_pass, int log
   tw_pass[k] = __ldg(tw + (e << tw_shift));
 }
 
+// Fused all-to-all of the row-sharded commit: when enabled, the LAST pass of a rank's local transform
+// stores row i of its result straight into the matrix of the rank that owns it after the exchange — rank i >> log_run,
+// local row (this rank << log_run) | (i mod 2^log_run) — through peer pointers (NVLink stores, 32 contiguous bytes per
+// row and tile), so the exchange needs no separate collective and overlaps the butterflies of the other tiles.
+struct NttScatter {
+  uint32_t* dst[NTT_MAX_PEERS];
+  int log_run, rank, enabled;
+};
+
 // Pass over layers [l0 + skip, l0 + L) of an h x w matrix; one CTA per (column tile, row group).
 // src == nullptr: in place on `mat`; the tile arrives by 16-byte cp.async (all loads of a CTA in flight at once, no
 // register staging).  src != nullptr (only with l0 == 0): gather from the evaluation vector (dim = 1):
@@ -141,7 +151,7 @@ __global__ void ntt_pass_twiddles_kernel(uint32_t* __restrict__ tw_pass, int log
 __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
 ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
                 int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift,
-                uint32_t tile0, uint32_t n_col_tiles, const uint32_t* __restrict__ tw_pass) {
+                uint32_t tile0, uint32_t n_col_tiles, const uint32_t* __restrict__ tw_pass, const NttScatter sc) {
   extern __shared__ uint4 tile[];  // [2^L][2] slots, then 2^L twiddle words
   uint32_t* tw_s = reinterpret_cast<uint32_t*>(tile + ((size_t)2 << L));
   const uint64_t col0 = (uint64_t)(tile0 + blockIdx.x % n_col_tiles) * TILE_COLS;  // column tile varies fastest: CTAs that
@@ -226,7 +236,12 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
     const int j = item >> 1, half = item & 1;
     if (half == 1 && !two_halves) continue;
     const uint64_t row = row_base + ((uint64_t)j << l0);
-    *reinterpret_cast<uint4*>(mat + row * w + col0 + 4 * half) = tile[tile_slot(j, half)];
+    if (sc.enabled) {
+      const uint64_t lrow = ((uint64_t)sc.rank << sc.log_run) | (row & (((uint64_t)1 << sc.log_run) - 1));
+      *reinterpret_cast<uint4*>(sc.dst[row >> sc.log_run] + lrow * w + col0 + 4 * half) = tile[tile_slot(j, half)];
+    } else {
+      *reinterpret_cast<uint4*>(mat + row * w + col0 + 4 * half) = tile[tile_slot(j, half)];
+    }
   }
 }
 
@@ -330,7 +345,7 @@ cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, 
 // col_tile0 / n_tiles: restrict the pass kernels to a range of 8-column tiles (n_tiles == 0: all of them)
 static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32_t* d_src, uint32_t log_block,
                               uint32_t r, uint64_t h, uint64_t w, int skip, const uint32_t* d_tw, unsigned tw_log_n,
-                              uint32_t col_tile0 = 0, uint32_t n_tiles = 0) {
+                              uint32_t col_tile0 = 0, uint32_t n_tiles = 0, const NttScatter* scatter = nullptr) {
   int log_h = 0;
   while (((uint64_t)1 << log_h) < h) log_h++;
   if (((uint64_t)1 << log_h) != h || (unsigned)log_h > tw_log_n) return cudaErrorInvalidValue;
@@ -338,7 +353,7 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
   if (log_h == 0) return cudaSuccess;
 
   if (w % 4 != 0) {
-    if (d_src != nullptr) return cudaErrorInvalidValue;
+    if (d_src != nullptr || scatter) return cudaErrorInvalidValue;
     for (int l = skip; l < log_h; l++) {
       const uint64_t n = (h / 2) * w;
       ntt_layer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_mat, h, w, l, log_h, d_tw, tw_shift); count_launch();
@@ -364,8 +379,10 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     // compact twiddles of this pass, in the scratch words behind the big table (ntt.h: NTT_TW_SCRATCH_WORDS)
     uint32_t* tw_pass = const_cast<uint32_t*>(d_tw) + ((size_t)1 << (tw_log_n - 1)) + (size_t)(p % 4) * ((size_t)1 << MAX_TILE_LOG);
     ntt_pass_twiddles_kernel<<<((1 << L) + 255) / 256, 256, 0, stream>>>(tw_pass, log_h, l0, L, d_tw, tw_shift); count_launch();
+    NttScatter sc{};
+    if (scatter && p == n_pass - 1) sc = *scatter;
     ntt_pass_kernel<<<(unsigned)n_cta, NTT_THREADS, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
-                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass); count_launch();
+                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass, sc); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     l0 += L;
@@ -385,6 +402,28 @@ cudaError_t ntt_reorder_and_dft_cols(cudaStream_t stream, const uint32_t* d_eval
   const int skip = (int)(log_inv_rate < log_block ? log_inv_rate : log_block);
   return run_layers(stream, d_out, d_evals, log_block, log_inv_rate, h, dft_n_cols, skip, d_tw, tw_log_n, col_begin / 8,
                     col_count / 8);
+}
+
+// gather + DFT of a rank's shard with the exchange of the row-sharded commit fused into the last pass: d_work is the
+// rank's own block x w scratch, peers[q] the matrix of rank q (q == rank: its own), each block x w words
+cudaError_t ntt_reorder_and_dft_scatter(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding_factor,
+                                        uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_work, uint32_t* const* peers,
+                                        uint32_t world, uint32_t rank, const uint32_t* d_tw, unsigned tw_log_n) {
+  if (folding_factor > n_vars + log_inv_rate || dft_n_cols % 4 || dft_n_cols == 0 || world < 2 || world > NTT_MAX_PEERS ||
+      (world & (world - 1)) || rank >= world)
+    return cudaErrorInvalidValue;
+  const uint32_t log_block = n_vars + log_inv_rate - folding_factor;
+  uint32_t g = 0;
+  while ((1u << g) < world) g++;
+  if (log_block < 2 * g) return cudaErrorInvalidValue;
+  const uint64_t h = (uint64_t)1 << log_block;
+  const int skip = (int)(log_inv_rate < log_block ? log_inv_rate : log_block);
+  NttScatter sc{};
+  for (uint32_t q = 0; q < world; q++) sc.dst[q] = peers[q];
+  sc.log_run = (int)(log_block - g);
+  sc.rank = (int)rank;
+  sc.enabled = 1;
+  return run_layers(stream, d_work, d_evals, log_block, log_inv_rate, h, dft_n_cols, skip, d_tw, tw_log_n, 0, 0, &sc);
 }
 
 cudaError_t ntt_dft_batch_by_evals(cudaStream_t stream, uint32_t* d_mat, uint64_t h, uint64_t w, int skip_layers,

@@ -96,16 +96,24 @@ class ShardedCommit:
         w = self.cols
         mark = getattr(b, "mark", None) or (lambda name: None)  # optional per-phase device timestamps (CudaBackend)
         mark("start")
-        # 1. local transform of the shard
-        t_local = b.reorder_and_dft(shard, geo.n_vars - geo.g, geo.folding, geo.log_inv_rate, w)  # block x w
-        mark("local_dft")
-        # 2. exchange: equal splits of `run` rows, received in block order m = source rank
-        mat = b.empty_like(t_local)
-        if self.world > 1:
-            b.all_to_all(self.dist, mat, t_local)
+        scatter = getattr(b, "scatter_dft", None) if self.world > 1 else None
+        if scatter is not None:
+            # 1 + 2 fused: the last pass of the local transform stores every row into the matrix of the rank that owns it
+            # after the exchange, through peer pointers over NVLink; a stream-ordered barrier closes the exchange
+            mat = scatter(self.dist, shard, geo.n_vars - geo.g, geo.folding, geo.log_inv_rate, w)
+            mark("local_dft")
+            mark("all_to_all")
         else:
-            mat = t_local
-        mark("all_to_all")
+            # 1. local transform of the shard
+            t_local = b.reorder_and_dft(shard, geo.n_vars - geo.g, geo.folding, geo.log_inv_rate, w)  # block x w
+            mark("local_dft")
+            # 2. exchange: equal splits of `run` rows, received in block order m = source rank
+            mat = b.empty_like(t_local)
+            if self.world > 1:
+                b.all_to_all(self.dist, mat, t_local)
+            else:
+                mat = t_local
+            mark("all_to_all")
         # 3. last g layers on the local rows
         if geo.g:
             b.dft_layers_mapped(mat, w, geo.log_h, geo.log_h - geo.g, self.world, geo.run, geo.block, self.rank * geo.run)
@@ -431,6 +439,9 @@ class CudaBackend:
         import os
 
         self._timing, self._marks = bool(os.environ.get("LM_SHARD_TIMING")), []
+        self._scatter = {}   # (rows, cols) -> (own matrix, work buffer, peer tensors kept alive, pointer table)
+        if os.environ.get("LM_SHARD_EXCHANGE", "p2p") != "p2p":
+            self.scatter_dft = None  # fall back to the NCCL all-to-all after the local transform
 
     def to_device(self, a: np.ndarray):
         return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
@@ -450,6 +461,66 @@ class CudaBackend:
         self.check(self.lib.lm_dev_reorder_and_dft(self.ctx.handle, shard.data_ptr(), n_vars, 1, folding, log_inv_rate, cols,
                                                    out.data_ptr()))
         return out
+
+    def _scatter_buffers(self, dist, rows, cols):
+        """One matrix per rank (lm_dev_alloc), mapped into every other rank's address space by CUDA IPC (lm_dev_ipc_*: the
+        64-byte handles travel through all_gather_object), allocated once per shape: the commit's codeword lives in it."""
+        key = (rows, cols)
+        if key not in self._scatter:
+            import ctypes as C
+
+            torch, lib = self.torch, self.lib
+            own = self.ctx.alloc(rows * cols * 4)
+            work = torch.empty((rows, cols), dtype=torch.int32, device="cuda")
+            world, rank = dist.get_world_size(), dist.get_rank()
+            hbuf = C.create_string_buffer(64)
+            self.check(lib.lm_dev_ipc_export(self.ctx.handle, own.ptr, hbuf))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(hbuf.raw))
+            table = np.zeros(world, dtype=np.uint64)
+            opened = []
+            for q in range(world):
+                if q == rank:
+                    table[q] = own.ptr.value
+                else:
+                    p = C.c_void_p()
+                    self.check(lib.lm_dev_ipc_open(self.ctx.handle, handles[q], C.byref(p)))
+                    table[q] = p.value
+                    opened.append(p)
+
+            class _Raw:  # zero-copy torch view of the library allocation
+                __cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<i4", "data": (int(own.ptr.value), False),
+                                            "version": 3, "strides": None}
+
+            mat = torch.as_tensor(_Raw(), device="cuda")
+            dist.barrier()
+            self._scatter[key] = (mat, work, (own, opened), table)
+        return self._scatter[key]
+
+    def close(self):
+        """unmap the peer matrices and free the own ones (collective: call on every rank before the process group goes)"""
+        for mat, work, (own, opened), _ in self._scatter.values():
+            for p in opened:
+                self.lib.lm_dev_ipc_close(self.ctx.handle, p)
+            own.free()
+        self._scatter = {}
+
+    def scatter_dft(self, dist, shard, n_vars, folding, log_inv_rate, cols):
+        import ctypes as C
+
+        rows = 1 << (n_vars + log_inv_rate - folding)
+        mat, work, _, table = self._scatter_buffers(dist, rows, cols)
+        self.check(self.lib.lm_dev_reorder_and_dft_scatter(self.ctx.handle, shard.data_ptr(), n_vars, folding, log_inv_rate, cols,
+                                                           work.data_ptr(), table.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                           dist.get_world_size(), dist.get_rank()))
+        # every rank's stores must have landed before anyone reads its matrix: NCCL barrier, ordered on the stream
+        dist.all_reduce(self._flag())
+        return mat
+
+    def _flag(self):
+        if not hasattr(self, "_flag_t"):
+            self._flag_t = self.torch.zeros(1, dtype=self.torch.int32, device="cuda")
+        return self._flag_t
 
     def all_to_all(self, dist, out, inp):
         # torch's current stream IS the library's stream: NCCL orders itself after the transform and the next kernel after

@@ -194,3 +194,40 @@ def test_dft_layers_mapped(ctx, rng, log_h, g, w):
         got = d.download(mat.shape)
         d.free()
         assert np.array_equal(got, exp), (log_h, g, w, rank)
+
+
+@pytest.mark.parametrize("n_vars,k,r,cols,G", [(13, 4, 1, 16, 2), (15, 5, 1, 32, 4), (19, 7, 1, 64, 2), (20, 7, 1, 64, 8)])
+def test_reorder_and_dft_scatter_single_device(ctx, rng, n_vars, k, r, cols, G):
+    """lm_dev_reorder_and_dft_scatter with all "peer" matrices on this device: the transform of every rank's shard stores
+    row i into matrix i >> log_run at local row (rank << log_run) | (i mod run) — what the NCCL all-to-all of the
+    row-sharded commit would deliver (one and two passes)."""
+    import ctypes as C
+
+    from leanmultisig_b200._lib import check, lib
+    from leanmultisig_b200.sharded import shard_of
+
+    g = G.bit_length() - 1
+    chunk = 1 << (n_vars - k)
+    ev = np.zeros(1 << n_vars, dtype=np.uint32)
+    ev[: cols * chunk] = O.random_field(rng, cols * chunk)
+    block = 1 << (n_vars - g + r - k)
+    run = block // G
+    mats = [ctx.alloc(block * cols * 4) for _ in range(G)]
+    work = ctx.alloc(block * cols * 4)
+    table = np.array([int(m.ptr.value) for m in mats], dtype=np.uint64)
+    expected = [np.zeros((block, cols), dtype=np.uint32) for _ in range(G)]
+    for rank in range(G):
+        shard = shard_of(ev, n_vars, k, rank, G).reshape(1 << k, -1)[:cols].reshape(-1)
+        t_local = O.reorder_and_dft(np.concatenate([shard, np.zeros((1 << (n_vars - g)) - shard.size, dtype=np.uint32)]),
+                                    n_vars - g, 1, k, r, cols)
+        for q in range(G):
+            expected[q][rank * run:(rank + 1) * run] = t_local[q * run:(q + 1) * run]
+        d = ctx.to_device(shard)
+        check(lib().lm_dev_reorder_and_dft_scatter(ctx.handle, d.ptr, n_vars - g, k, r, cols, work.ptr,
+                                                   table.ctypes.data_as(C.POINTER(C.c_uint64)), G, rank))
+        ctx.sync()
+        d.free()
+    for q in range(G):
+        assert np.array_equal(mats[q].download((block, cols)), expected[q]), f"matrix {q}"
+    for m in mats + [work]:
+        m.free()
