@@ -67,6 +67,20 @@ int lm_commit_dev(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_
 /* MerkleData::open (crates/whir/src/commit.rs:34-45 -> crates/whir/src/merkle.rs:205-211): for each index the
  * full row zero-extended to full width (n x full_width words) and the sibling path, leaf level first
  * (n x log2(height) x 8 words). */
+/* Witness-side steps in front of the first commitment.
+ * lm_commit_stacked: stack_polynomials_and_commit (crates/sub_protocols/src/stacked_pcs.rs:100-157) without the host-side
+ * global_polynomial: every segment (memory, memory_acc, bytecode_acc, the table columns) is copied straight to its offset
+ * of the device-resident polynomial (zero elsewhere, actual_len = end of the last segment) and committed like lm_commit.
+ * lm_access_counts: memory_acc / bytecode_acc (crates/lean_prover/src/prove_execution.rs:91-110): for every index column k
+ * (Montgomery-form addresses) acc[addr + j] += 1, j < n_values[k]; out_acc: table_len field elements (Montgomery). */
+typedef struct {
+  const uint32_t* data; /* host, base field */
+  uint64_t len, offset; /* in elements */
+} lm_segment;
+int lm_commit_stacked(lm_ctx* ctx, const lm_segment* segments, uint32_t n_segments, uint32_t n_vars,
+                      uint32_t folding_factor, uint32_t log_inv_rate, lm_tree** out_tree, uint32_t out_root[8]);
+int lm_access_counts(lm_ctx* ctx, const uint32_t* const* index_cols, const uint64_t* n_rows, const uint32_t* n_values,
+                     uint32_t n_cols, uint64_t table_len, uint32_t* out_acc);
 int lm_open(lm_tree* tree, const uint64_t* indices, uint32_t n, uint32_t* out_rows, uint32_t* out_paths);
 /* height (rows), full row width in words, stored row width in words, elem_dim */
 int lm_tree_shape(const lm_tree* tree, uint64_t* height, uint32_t* full_width, uint32_t* stored_width,

@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
             "lm_host_unregister": [vp],
             "lm_commit": [vp, vp, u32, u32, u64, u32, u32, C.POINTER(vp), u32p],
             "lm_commit_dev": [vp, vp, u32, u32, u64, u32, u32, i, C.POINTER(vp), u32p],
+            "lm_commit_stacked": [vp, vp, u32, u32, u32, u32, C.POINTER(vp), u32p],
+            "lm_access_counts": [vp, C.POINTER(vp), u64p, u32p, u32, u64, u32p],
             "lm_open": [vp, u64p, u32, u32p, u32p],
             "lm_tree_shape": [vp, u64p, u32p, u32p, u32p],
             "lm_tree_eval": [vp, u32p, u32p],

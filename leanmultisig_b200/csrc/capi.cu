@@ -594,6 +594,72 @@ int lm_commit_dev(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t 
                      out_root);
 }
 
+int lm_commit_stacked(lm_ctx* c, const lm_segment* segments, uint32_t n_segments, uint32_t n_vars, uint32_t folding,
+                      uint32_t log_inv_rate, lm_tree** out_tree, uint32_t out_root[8]) {
+  if (!c || (!segments && n_segments) || !out_tree || !out_root) return fail(LM_ERR_INVALID, "lm_commit_stacked: null argument");
+  if (n_vars > 32) return fail(LM_ERR_INVALID, "lm_commit_stacked: n_vars %u too large", n_vars);
+  const uint64_t full = (uint64_t)1 << n_vars;
+  uint64_t actual = 0;
+  for (uint32_t i = 0; i < n_segments; i++) {
+    if (segments[i].len && !segments[i].data) return fail(LM_ERR_INVALID, "lm_commit_stacked: segment %u is null", i);
+    if (segments[i].offset + segments[i].len > full)
+      return fail(LM_ERR_INVALID, "lm_commit_stacked: segment %u ends beyond 2^%u", i, n_vars);
+    if (segments[i].offset + segments[i].len > actual) actual = segments[i].offset + segments[i].len;
+  }
+  CU(cudaSetDevice(c->device));
+  // the live prefix is assembled on the device: gaps between segments are zero (stacked_pcs.rs:118-135 starts from zero_vec)
+  uint32_t* d_tmp = nullptr;
+  const size_t bytes = (actual ? actual : 1) * sizeof(uint32_t);
+  CU(c->pool.get(bytes, reinterpret_cast<void**>(&d_tmp)));
+  cudaError_t e = cudaMemsetAsync(d_tmp, 0, bytes, c->stream);
+  for (uint32_t i = 0; e == cudaSuccess && i < n_segments; i++)
+    if (segments[i].len)
+      e = cudaMemcpyAsync(d_tmp + segments[i].offset, segments[i].data, segments[i].len * sizeof(uint32_t),
+                          cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(c->stream);
+    c->pool.put(bytes, d_tmp);
+    return cuda_fail(e, "lm_commit_stacked");
+  }
+  const int rc = commit_impl(c, d_tmp, true, n_vars, 1, actual, folding, log_inv_rate, true, out_tree, out_root);
+  c->pool.put(bytes, d_tmp);  // commit_impl synchronised the stream
+  return rc;
+}
+
+int lm_access_counts(lm_ctx* c, const uint32_t* const* index_cols, const uint64_t* n_rows, const uint32_t* n_values,
+                     uint32_t n_cols, uint64_t table_len, uint32_t* out_acc) {
+  if (!c || (n_cols && (!index_cols || !n_rows || !n_values)) || !out_acc)
+    return fail(LM_ERR_INVALID, "lm_access_counts: null argument");
+  if (table_len == 0) return LM_OK;
+  CU(cudaSetDevice(c->device));
+  uint64_t max_rows = 1;
+  for (uint32_t k = 0; k < n_cols; k++) {
+    if (n_rows[k] && !index_cols[k]) return fail(LM_ERR_INVALID, "lm_access_counts: column %u is null", k);
+    if (n_rows[k] > max_rows) max_rows = n_rows[k];
+  }
+  uint32_t *d_counts = nullptr, *d_col = nullptr;
+  CU(cudaMalloc(&d_counts, (table_len + 1) * sizeof(uint32_t)));  // last word: out-of-range flag
+  cudaError_t e = cudaMalloc(&d_col, max_rows * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, (table_len + 1) * sizeof(uint32_t), c->stream);
+  for (uint32_t k = 0; e == cudaSuccess && k < n_cols; k++) {
+    if (!n_rows[k]) continue;
+    e = cudaMemcpyAsync(d_col, index_cols[k], n_rows[k] * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = lm::access_count(c->stream, d_col, n_rows[k], n_values[k], table_len, d_counts, d_counts + table_len);
+  }
+  uint32_t bad = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_counts + table_len, sizeof(bad), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = lm::counts_to_monty(c->stream, d_counts, table_len);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_acc, d_counts, table_len * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_counts);
+  if (d_col) cudaFree(d_col);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_access_counts");
+  if (bad) return fail(LM_ERR_INVALID, "lm_access_counts: an address (+ its value count) lies outside the table of %llu entries",
+                       (unsigned long long)table_len);
+  return LM_OK;
+}
+
 int lm_tree_shape(const lm_tree* t, uint64_t* height, uint32_t* full_w, uint32_t* stored_w, uint32_t* dim) {
   if (!t) return fail(LM_ERR_INVALID, "lm_tree_shape: tree is null");
   if (height) *height = t->height;

@@ -220,4 +220,36 @@ cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, u
   return cudaGetLastError();
 }
 
+// ---- access counts (memory_acc / bytecode_acc, crates/lean_prover/src/prove_execution.rs:91-110) --------------------
+// counts[addr(i) + j] += 1 for every row i of an index column (Montgomery-form addresses) and j < n_values; the reference
+// does this sequentially on the host ("TODO parallelize").  *d_bad is set when an address falls outside the table.
+__global__ void access_count_kernel(const uint32_t* __restrict__ idx_col, uint64_t n, uint32_t n_values, uint64_t table_len,
+                                    uint32_t* __restrict__ counts, uint32_t* __restrict__ d_bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t addr = kb_canon(kb_redc_lazy((uint64_t)__ldg(idx_col + i)));  // Montgomery -> canonical integer
+  if (addr + n_values > table_len) {
+    *d_bad = 1;
+    return;
+  }
+  for (uint32_t j = 0; j < n_values; j++) atomicAdd(counts + addr + j, 1u);
+}
+__global__ void counts_to_monty_kernel(uint32_t* __restrict__ counts, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) counts[i] = kb_mul(counts[i] % KB_P, KB_R2);  // integer count -> field element in Montgomery form
+}
+cudaError_t access_count(cudaStream_t stream, const uint32_t* d_idx_col, uint64_t n, uint32_t n_values, uint64_t table_len,
+                         uint32_t* d_counts, uint32_t* d_bad) {
+  if (n == 0) return cudaSuccess;
+  access_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_idx_col, n, n_values, table_len, d_counts, d_bad);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t counts_to_monty(cudaStream_t stream, uint32_t* d_counts, uint64_t n) {
+  if (n == 0) return cudaSuccess;
+  counts_to_monty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_counts, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace lm

@@ -16,4 +16,8 @@ cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_va
 // (entries >= live are zero and not read; EF tables may be folded in place, d_out == d_in)
 cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, uint32_t dim, uint64_t live,
                      const uint32_t r[5], uint32_t* d_out);
+// counts[addr + j] += 1 (integer counters) for the Montgomery-form addresses of one index column; then integer -> field
+cudaError_t access_count(cudaStream_t stream, const uint32_t* d_idx_col, uint64_t n, uint32_t n_values, uint64_t table_len,
+                         uint32_t* d_counts, uint32_t* d_bad);
+cudaError_t counts_to_monty(cudaStream_t stream, uint32_t* d_counts, uint64_t n);
 }  // namespace lm

@@ -393,3 +393,37 @@ def embed(base) -> np.ndarray:
     out = np.zeros((b.size, 5), dtype=np.uint32)
     out[:, 0] = b
     return out
+
+
+# ---------------------------------------------------------------- witness-side steps
+def access_counts(index_columns, n_values, table_len: int) -> np.ndarray:
+    """memory_acc / bytecode_acc (crates/lean_prover/src/prove_execution.rs:91-110): acc[addr + j] += 1 for every entry
+    of every index column and j < n_values[k]; Montgomery-form addresses in, Montgomery-form counts out"""
+    acc = np.zeros(table_len, dtype=np.uint64)
+    for col, nv in zip(index_columns, n_values):
+        addr = from_monty(_u32(col)).astype(np.int64)
+        for j in range(nv):
+            np.add.at(acc, addr + j, 1)
+    return to_monty(acc % P)
+
+
+def stack_polynomials(memory, memory_acc, bytecode_acc, tables_sorted):
+    """global_polynomial of stack_polynomials_and_commit (crates/sub_protocols/src/stacked_pcs.rs:100-135).
+    tables_sorted: [(columns (list of arrays), log_n_rows)] tallest first.  -> (evals padded to 2^n_vars, n_vars, offset)"""
+    memory, memory_acc, bytecode_acc = _u32(memory), _u32(memory_acc), _u32(bytecode_acc)
+    largest = 1 << tables_sorted[0][1]
+    total = 2 * memory.size + max(largest, bytecode_acc.size) + sum(len(cols) << h for cols, h in tables_sorted)
+    n_vars = (total - 1).bit_length()
+    g = np.zeros(1 << n_vars, dtype=np.uint32)
+    g[: memory.size] = memory
+    off = memory.size
+    g[off:off + memory_acc.size] = memory_acc
+    off += memory_acc.size
+    g[off:off + bytecode_acc.size] = bytecode_acc
+    off += max(largest, bytecode_acc.size)
+    for cols, h in tables_sorted:
+        for c in cols:
+            g[off:off + (1 << h)] = _u32(c)[: 1 << h]
+            off += 1 << h
+    assert off == total
+    return g, n_vars, off
