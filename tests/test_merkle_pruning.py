@@ -1,0 +1,78 @@
+"""Merkle-path pruning: the product's prover-side `prune` against the oracle's verifier-side
+`restore` — the reference's own test scenarios (merkle_pruning.rs tests: basic [5, 1, 3], duplicates, adjacent leaves,
+single path, all leaves) on real Poseidon1 trees, plus the GPU openings of a committed tree."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import merkle_pruning as OMP
+from leanmultisig_b200.merkle_pruning import lca_level, prune
+
+
+def open_all(mat, full_w, layers, indices):
+    rows, paths = zip(*[O.merkle_open(mat, full_w, layers, i) for i in indices])
+    return np.stack(rows), np.stack(paths)
+
+
+def check_roundtrip(indices, rows, paths, root, log_h):
+    pruned = prune(indices, rows, paths)
+    restored = OMP.restore(pruned)
+    assert restored is not None and len(restored) == len(indices)
+    for q, (li, row, sibs) in enumerate(restored):
+        assert li == indices[q] and np.array_equal(row, rows[q]) and np.array_equal(sibs, paths[q])
+        assert O.merkle_verify(root, log_h, li, row, sibs)
+    return pruned
+
+
+@pytest.mark.parametrize("log_h,indices", [(3, [5, 1, 3]), (3, [5, 1, 5, 3, 1]), (3, [2, 3]), (3, [6]), (3, list(range(8))),
+                                           (6, [63, 0, 32, 31, 33, 1]), (1, [1, 0])])
+def test_prune_restore_roundtrip(rng, log_h, indices):
+    h, stored, full, eff = 1 << log_h, 24, 48, 24
+    mat = O.random_field(rng, (h, stored))
+    layers = O.merkle_tree(mat, full, eff)
+    rows, paths = open_all(mat, full, layers, indices)
+    pruned = check_roundtrip(indices, rows, paths, layers[-1], log_h)
+    assert pruned.n_trailing_zeros == full - stored and pruned.merkle_height == log_h
+    # fewer digests than the unpruned hint whenever two distinct leaves are opened
+    if len(set(indices)) > 1:
+        assert pruned.n_digests() < len(set(indices)) * log_h
+
+
+def test_lca_level():
+    assert lca_level(5, 4) == 1 and lca_level(0, 7) == 3 and lca_level(2, 3) == 1 and lca_level(1, 5) == 3
+
+
+def test_restore_rejects_malformed_hints(rng):
+    h, log_h = 8, 3
+    mat = O.random_field(rng, (h, 16))
+    layers = O.merkle_tree(mat, 16, 16)
+    rows, paths = open_all(mat, 16, layers, [1, 6])
+    pruned = prune([1, 6], rows, paths)
+    pruned.paths[0] = (pruned.paths[0][0], pruned.paths[0][1][:-1])   # a digest is missing
+    assert OMP.restore(pruned) is None
+    pruned = prune([1, 6], rows, paths)
+    pruned.paths[1] = (9, pruned.paths[1][1])                         # leaf index outside the tree
+    assert OMP.restore(pruned) is None
+    pruned = prune([1, 6], rows, paths)
+    pruned.leaf_data[0] = pruned.leaf_data[0].copy()
+    pruned.leaf_data[0][0] ^= 1                                       # tampered leaf: restores, but does not verify
+    li, row, sibs = OMP.restore(pruned)[0]
+    assert not O.merkle_verify(layers[-1], log_h, li, row, sibs)
+
+
+@pytest.mark.gpu
+def test_gpu_openings_prune_and_restore(rng):
+    import leanmultisig_b200 as lm
+
+    ctx = lm.Context(0, 20)
+    n_vars, k, r = 17, 7, 1
+    live = 1 << 16
+    ev = np.zeros(1 << n_vars, dtype=np.uint32)
+    ev[:live] = O.random_field(rng, live)
+    tree = ctx.commit(ev, n_vars, k, r, actual_len=live)
+    indices = [int(x) for x in rng.integers(0, tree.height, 40)] + [7, 7]
+    rows, paths = tree.open(indices)
+    pruned = check_roundtrip(indices, rows, paths, tree.root, tree.log_height)
+    assert pruned.n_trailing_zeros == 64 and pruned.n_digests() < len(set(indices)) * tree.log_height
+    tree.free()
+    ctx.close()
