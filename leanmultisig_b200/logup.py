@@ -311,7 +311,8 @@ def prove_generic_logup(ctx, prover_state, c, alphas_eq_poly, memory, memory_acc
     b = build_logup_table(ctx, c, al, memory, memory_acc, bytecode_multilinear, bytecode_acc, traces)
     gkr = b.finish()
     total_gkr_n_vars = gkr.n_vars
-    quotient, point, _, _ = gkr.prove_with_state(prover_state)
+    # a NativeProverState (C++ transcript) runs the whole GKR in the library's spine, anything else round by round here
+    quotient, point, _, _ = gkr.prove_native(prover_state) if hasattr(prover_state, "handle") else gkr.prove_with_state(prover_state)
     gkr.free()
     assert not quotient.any(), "logup sum is not zero"
     log_memory = memory.size.bit_length() - 1

@@ -1,0 +1,176 @@
+"""PROXY for BASELINE metric (i), "XMSS signatures/s proven": hot-path time of ONE proof on synthetic lean_vm tables of
+ASSUMED XMSS-aggregation shape, on one GPU.
+
+The real workload (`lean-multisig xmss --n-signatures N`) executes the compiled aggregation program in the zkVM; neither
+the compiler nor the VM runner is part of this repository (not reproducible here, the table heights
+are only logged at run time).  What this tool times is every data-parallel step the prover runs on tables of the assumed
+heights, in the order of prove_execution (lean_prover/src/prove_execution.rs): access counts, stacked commit, Logup (table
+assembly + quotient GKR + column evaluations), batched AIR sumcheck over the three tables, WHIR open.  The tables are
+random but CONSISTENT for Logup (lookups hit the memory, instruction columns are bytecode rows, every precompile row is
+pushed once), so the logup sum is zero as the prover asserts; they do not satisfy the AIR (the sumcheck is still well
+defined).  Assumed shapes: Poseidon rows = 165 N rounded up to a power of two (110 chain + 21 WOTS-pk + 32 Merkle + 2
+encode per signature, crates/xmss/src/lib.rs:19-32), cycles = 8 x that, memory = 2 x cycles, extension_op at its minimum
+2^8, bytecode 2^14.  EVERY sigs/s figure printed here is a proxy under these assumptions.
+
+    python tools/xmss_proxy.py [n_signatures=1550]
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import leanmultisig_b200 as lm
+from leanmultisig_b200 import field as F
+from leanmultisig_b200 import tables as T
+from leanmultisig_b200.logup import prove_generic_logup
+from leanmultisig_b200.stacked_pcs import build_bytecode_acc, build_memory_acc, stack_polynomials_and_commit
+from leanmultisig_b200.whir import Witness, _sample_ood
+
+P = 0x7F000001
+
+
+def monty(a):
+    return F.np_to_monty(np.asarray(a, dtype=np.uint64) % P)
+
+
+def make_instance(rng, log_memory, log_bytecode, log_cycles, log_ext, log_pos):
+    """vectorised version of tests/test_logup.py::make_instance (canonical integers)"""
+    M = 1 << log_memory
+    mem = rng.integers(0, P, M).astype(np.uint64)
+    bytecode = np.zeros((1 << log_bytecode, 16), dtype=np.uint64)
+    bytecode[:, :12] = rng.integers(0, P, (1 << log_bytecode, 12))
+    aux_values = np.array([64 + 8, 2 * 64 + 16 + 4, 3 * 64 + 32, 64 + 16], dtype=np.uint64)
+    pd_row = {1: 0}
+    for i, v in enumerate(aux_values):
+        pd_row[int(v)] = i + 1
+    for v, row in pd_row.items():
+        bytecode[row, 11] = v
+    n_ext, n_pos, n_cyc = 1 << log_ext, 1 << log_pos, 1 << log_cycles
+    ext = np.zeros((31, n_ext), dtype=np.uint64)
+    ia, ib, ir = (rng.integers(0, M - 8, n_ext) for _ in range(3))
+    ext[6], ext[7], ext[13] = ia, ib, ir
+    for k in range(5):
+        ext[14 + k], ext[19 + k], ext[24 + k] = mem[ia + k], mem[ib + k], mem[ir + k]
+    ext[29, : n_ext - 5] = 1
+    ext[30] = aux_values[np.arange(n_ext) % 4]
+    pos = np.zeros((111, n_pos), dtype=np.uint64)
+    il, pb, pr = (rng.integers(0, M - 20, n_pos) for _ in range(3))
+    pos[0, : n_pos - 3] = 1
+    pos[1], pos[2], pos[6], pos[7] = pb, pr, il, il + 4
+    for k in range(4):
+        pos[9 + k], pos[13 + k] = mem[il + k], mem[il + 4 + k]
+    for k in range(8):
+        pos[17 + k] = mem[pb + k]
+    for k in range(16):
+        pos[93 + k] = mem[pr + k]
+    pos[109], pos[110] = il, 1
+    ae, ap = n_ext - 5, n_pos - 3
+    n_push = ae + ap
+    assert n_push <= n_cyc
+    ex = np.zeros((24, n_cyc), dtype=np.uint64)
+    pc = rng.integers(0, 1 << log_bytecode, n_cyc)
+    pc[:ae] = np.array([pd_row[int(v)] for v in aux_values])[np.arange(ae) % 4]
+    pc[ae:n_push] = pd_row[1]
+    ex[20, :n_push] = 1
+    ex[21, :ae], ex[22, :ae], ex[23, :ae] = ia[:ae], ib[:ae], ir[:ae]
+    ex[21, ae:n_push], ex[22, ae:n_push], ex[23, ae:n_push] = il[:ap], pb[:ap], pr[:ap]
+    ex[0] = pc
+    ex[8:20] = bytecode[pc, :12].T
+    for k in range(3):
+        addr = rng.integers(0, M, n_cyc)
+        ex[2 + k], ex[5 + k] = addr, mem[addr]
+    return mem, bytecode, ex, ext, pos
+
+
+def main():
+    n_sigs = int(sys.argv[1]) if len(sys.argv) > 1 else 1550
+    log_pos = max(8, (165 * n_sigs - 1).bit_length())
+    log_cycles = log_pos + 3
+    log_memory = log_cycles + 1
+    log_bytecode, log_ext = 14, 8
+    rng = np.random.default_rng(0)
+    t0 = time.perf_counter()
+    mem, bytecode, ex, ext, pos = make_instance(rng, log_memory, log_bytecode, log_cycles, log_ext, log_pos)
+    cols = lambda a: [np.ascontiguousarray(monty(a[c])) for c in range(a.shape[0])]
+    traces = {T.EXECUTION: T.TableTrace(cols(ex), log_cycles), T.EXTENSION_OP: T.TableTrace(cols(ext), log_ext),
+              T.POSEIDON16: T.TableTrace(cols(pos), log_pos)}
+    memory, bytecode_m = monty(mem), monty(bytecode.reshape(-1))
+    print(f"assumed shapes for {n_sigs} signatures: poseidon16 2^{log_pos} rows, execution 2^{log_cycles} cycles, memory "
+          f"2^{log_memory}, extension_op 2^{log_ext}, bytecode 2^{log_bytecode}  (instance built in {time.perf_counter() - t0:.1f} s on the host)")
+
+    ctx = lm.Context(0, 26)
+    ps = lm.NativeProverState(ctx)
+    phases = {}
+
+    def timed(name, fn):
+        ctx.sync()
+        t = time.perf_counter()
+        out = fn()
+        ctx.sync()
+        phases[name] = time.perf_counter() - t
+        return out
+
+    memory_acc = timed("access counts (memory_acc, bytecode_acc)", lambda: build_memory_acc(ctx, 1 << log_memory, traces))
+    bytecode_acc = build_bytecode_acc(ctx, 1 << log_bytecode, traces[T.EXECUTION])
+    n_vars_guess = lm.stacked_pcs.compute_stacked_n_vars(log_memory, log_bytecode, {t: tr.log_n_rows for t, tr in traces.items()})
+    cfg = lm.WhirConfig(n_vars_guess)
+
+    def commit():
+        tree, n_vars, actual = stack_polynomials_and_commit(ctx, cfg.first_folding, cfg.starting_log_inv_rate, memory, memory_acc,
+                                                            bytecode_acc, traces)
+        ps.add_base_scalars(tree.root)
+        pts, answers = _sample_ood(ps, cfg.commitment_ood_samples, n_vars, tree.evaluate)
+        return Witness(tree, pts, answers), n_vars, actual
+
+    witness, n_vars, actual = timed("stacked commit (H2D of the witness + NTT + Merkle + OOD)", commit)
+    print(f"stacked polynomial: 2^{n_vars} variables, {actual} live entries ({actual * 4 / 2**30:.2f} GiB), codeword 2^{n_vars + 1 - 7} x 128")
+
+    c = ps.sample()
+    alphas = np.stack(ps.sample_vec(5))
+    al_eq = ctx.eq_table(alphas)
+    st = timed("logup (table assembly, quotient GKR, column evaluations)",
+               lambda: prove_generic_logup(ctx, ps, c, al_eq, memory, memory_acc, bytecode_m, bytecode_acc, traces))
+
+    def air():
+        eta = ps.sample()
+        alpha = F.from_monty(ps.sample())
+        ap = [F.ONE]
+        for _ in range(100):
+            ap.append(F.mul(ap[-1], alpha))
+        ap = np.stack([F.to_monty(x) for x in ap])
+        beta = ps.sample()
+        sessions = []
+        for table, tr in traces.items():
+            eqf = st["gkr_point"][st["gkr_point"].shape[0] - tr.log_n_rows:]
+            sessions.append(lm.AirSumcheckSession(ctx, table.air_id, tr.columns[: table.n_columns], eqf, np.zeros(5, dtype=np.uint32),
+                                                  ap, al_eq, beta))
+        chals = lm.prove_batched_air_sumcheck_native(sessions, eta, ps)
+        for s in sessions:
+            ps.add_extension_scalars(s.final_column_evals().reshape(-1))
+            s.free()
+        return chals
+
+    timed("batched AIR sumcheck (3 tables, incl. H2D of the columns)", air)
+
+    def whir_open():
+        stmts = []
+        for _ in range(8):  # a representative handful of evaluation claims on the stacked polynomial
+            pt = np.stack(ps.sample_vec(n_vars))
+            stmts.append(lm.SparseStatement.dense(pt, witness.tree.evaluate(pt)))
+        lm.WhirProver(ctx, lm.WhirConfig(n_vars)).prove(ps, stmts, witness)
+
+    timed("WHIR open (8 dense statements)", whir_open)
+    witness.free()
+    total = sum(phases.values())
+    for k, v in phases.items():
+        print(f"  {k:64s} {v * 1e3:9.1f} ms")
+    print(f"  {'total hot path':64s} {total * 1e3:9.1f} ms  ->  {n_sigs / total:.0f} signatures/s  (PROXY: assumed shapes, one GPU, "
+          f"witness generation / VM execution not included)")
+    ps.free()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
