@@ -100,7 +100,15 @@ def main():
     print(f"assumed shapes for {n_sigs} signatures: poseidon16 2^{log_pos} rows, execution 2^{log_cycles} cycles, memory "
           f"2^{log_memory}, extension_op 2^{log_ext}, bytecode 2^{log_bytecode}  (instance built in {time.perf_counter() - t0:.1f} s on the host)")
 
-    ctx = lm.Context(0, 26)
+    ctx = lm.Context(0, 24)
+    # the witness lives in page-locked host memory (as a Rust caller would arrange with lm_host_register once per run):
+    # every step below copies its inputs from there
+    from leanmultisig_b200._lib import check, lib
+
+    pinned = [memory, bytecode_m] + [c for tr in traces.values() for c in tr.columns]
+    if not os.environ.get("LM_PROXY_PAGEABLE"):
+        for a in pinned:
+            check(lib().lm_host_register(a.ctypes.data, a.nbytes))
     ps = lm.NativeProverState(ctx)
     phases = {}
 
@@ -127,20 +135,24 @@ def main():
     witness, n_vars, actual = timed("stacked commit (H2D of the witness + NTT + Merkle + OOD)", commit)
     print(f"stacked polynomial: 2^{n_vars} variables, {actual} live entries ({actual * 4 / 2**30:.2f} GiB), codeword 2^{n_vars + 1 - 7} x 128")
 
-    c = ps.sample()
-    alphas = np.stack(ps.sample_vec(5))
+    def sample(n=None):  # the challenger hands out one rate block per absorb: duplex between consecutive squeezes
+        ps.duplex()
+        return ps.sample() if n is None else np.stack(ps.sample_vec(n))
+
+    c = sample()
+    alphas = sample(5)
     al_eq = ctx.eq_table(alphas)
     st = timed("logup (table assembly, quotient GKR, column evaluations)",
                lambda: prove_generic_logup(ctx, ps, c, al_eq, memory, memory_acc, bytecode_m, bytecode_acc, traces))
 
     def air():
-        eta = ps.sample()
-        alpha = F.from_monty(ps.sample())
+        eta = sample()
+        alpha = F.from_monty(sample())
         ap = [F.ONE]
         for _ in range(100):
             ap.append(F.mul(ap[-1], alpha))
         ap = np.stack([F.to_monty(x) for x in ap])
-        beta = ps.sample()
+        beta = sample()
         sessions = []
         for table, tr in traces.items():
             eqf = st["gkr_point"][st["gkr_point"].shape[0] - tr.log_n_rows:]
@@ -157,7 +169,7 @@ def main():
     def whir_open():
         stmts = []
         for _ in range(8):  # a representative handful of evaluation claims on the stacked polynomial
-            pt = np.stack(ps.sample_vec(n_vars))
+            pt = sample(n_vars)
             stmts.append(lm.SparseStatement.dense(pt, witness.tree.evaluate(pt)))
         lm.WhirProver(ctx, lm.WhirConfig(n_vars)).prove(ps, stmts, witness)
 
@@ -168,6 +180,9 @@ def main():
         print(f"  {k:64s} {v * 1e3:9.1f} ms")
     print(f"  {'total hot path':64s} {total * 1e3:9.1f} ms  ->  {n_sigs / total:.0f} signatures/s  (PROXY: assumed shapes, one GPU, "
           f"witness generation / VM execution not included)")
+    if not os.environ.get("LM_PROXY_PAGEABLE"):
+        for a in pinned:
+            lib().lm_host_unregister(a.ctypes.data)
     ps.free()
     ctx.close()
 
