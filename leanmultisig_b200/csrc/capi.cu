@@ -47,17 +47,6 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 }  // namespace
 
-// Session buffers come from CUDA's stream-ordered allocator on the context's stream (the default memory pool keeps freed
-// blocks, lm_init sets its release threshold): a proof allocates a few hundred buffers — Logup column copies, GKR layers,
-// sumcheck tables — and cudaMalloc / cudaFree of each cost 0.1-1 ms and a device-wide synchronisation (the reference
-// resets a bump arena per proof for the same reason, crates/backend/zk-alloc/src/lib.rs:102-115).  Every kernel that
-// touches such a buffer runs on the same stream, so stream order is the only ordering needed.
-template <class T>
-static cudaError_t lm_malloc(cudaStream_t s, T** p, size_t bytes) {
-  return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 1, s);
-}
-static cudaError_t lm_free(cudaStream_t s, void* p) { return p ? cudaFreeAsync(p, s) : cudaSuccess; }
-
 // error reporting for the other translation units of the library (spine.cu)
 int lm_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 
@@ -74,15 +63,9 @@ struct DevicePool {
         return cudaSuccess;
       }
     cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
-    if (e == cudaErrorMemoryAllocation) {  // drop this cache and what the stream-ordered pool holds, retry once
+    if (e == cudaErrorMemoryAllocation) {  // drop the cache and retry once
       cudaGetLastError();
       release_all();
-      int dev = 0;
-      cudaMemPool_t mp;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
-        cudaDeviceSynchronize();
-        cudaMemPoolTrimTo(mp, 0);
-      }
       e = cudaMalloc(out, bytes ? bytes : 1);
     }
     return e;
@@ -118,10 +101,10 @@ struct lm_ctx {
 
   int ensure_scratch(size_t words) {
     if (words <= scratch_words) return LM_OK;
-    if (d_scratch) lm_free(stream, d_scratch);
+    if (d_scratch) cudaFree(d_scratch);
     d_scratch = nullptr;
     scratch_words = 0;
-    CU(lm_malloc(stream, &d_scratch, words * sizeof(uint32_t)));
+    CU(cudaMalloc(&d_scratch, words * sizeof(uint32_t)));
     scratch_words = words;
     return LM_OK;
   }
@@ -154,10 +137,10 @@ struct lm_sumcheck {
   size_t scratch_words = 0;
   int ensure_scratch(size_t words) {
     if (words <= scratch_words) return LM_OK;
-    if (d_scratch) lm_free(ctx->stream, d_scratch);
+    if (d_scratch) cudaFree(d_scratch);
     d_scratch = nullptr;
     scratch_words = 0;
-    CU(lm_malloc(ctx->stream, &d_scratch, words * sizeof(uint32_t)));
+    CU(cudaMalloc(&d_scratch, words * sizeof(uint32_t)));
     scratch_words = words;
     return LM_OK;
   }
@@ -229,12 +212,6 @@ int lm_init(int device, uint32_t max_log_domain, lm_ctx** out_ctx) {
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev_copy) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
-  {  // keep freed session buffers in the default stream-ordered pool (see lm_malloc)
-    cudaMemPool_t mp;
-    CU(cudaDeviceGetDefaultMemPool(&mp, device));
-    uint64_t keep = UINT64_MAX;
-    CU(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
   c->tw_log_n = max_log_domain;
   if (max_log_domain > 0) {
     CU(cudaMalloc(&c->d_tw, (((size_t)1 << (max_log_domain - 1)) + lm::NTT_TW_SCRATCH_WORDS) * sizeof(uint32_t)));
@@ -661,8 +638,8 @@ int lm_access_counts(lm_ctx* c, const uint32_t* const* index_cols, const uint64_
     if (n_rows[k] > max_rows) max_rows = n_rows[k];
   }
   uint32_t *d_counts = nullptr, *d_col = nullptr;
-  CU(lm_malloc(c->stream, &d_counts, (table_len + 1) * sizeof(uint32_t)));  // last word: out-of-range flag
-  cudaError_t e = lm_malloc(c->stream, &d_col, max_rows * sizeof(uint32_t));
+  CU(cudaMalloc(&d_counts, (table_len + 1) * sizeof(uint32_t)));  // last word: out-of-range flag
+  cudaError_t e = cudaMalloc(&d_col, max_rows * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, (table_len + 1) * sizeof(uint32_t), c->stream);
   for (uint32_t k = 0; e == cudaSuccess && k < n_cols; k++) {
     if (!n_rows[k]) continue;
@@ -675,8 +652,8 @@ int lm_access_counts(lm_ctx* c, const uint32_t* const* index_cols, const uint64_
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_acc, d_counts, table_len * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream);
-  lm_free(c->stream, d_counts);
-  if (d_col) lm_free(c->stream, d_col);
+  cudaFree(d_counts);
+  if (d_col) cudaFree(d_col);
   if (e != cudaSuccess) return cuda_fail(e, "lm_access_counts");
   if (bad) return fail(LM_ERR_INVALID, "lm_access_counts: an address (+ its value count) lies outside the table of %llu entries",
                        (unsigned long long)table_len);
@@ -705,8 +682,8 @@ int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows,
   if (n == 0) return LM_OK;
   uint64_t* d_idx = nullptr;
   uint32_t* d_buf = nullptr;
-  CU(lm_malloc(c->stream, &d_idx, n * sizeof(uint64_t)));
-  cudaError_t e = lm_malloc(c->stream, &d_buf, (rows_words + paths_words + 1) * sizeof(uint32_t));
+  CU(cudaMalloc(&d_idx, n * sizeof(uint64_t)));
+  cudaError_t e = cudaMalloc(&d_buf, (rows_words + paths_words + 1) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, indices, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess)
     e = lm::merkle_open_gather(c->stream, t->d_codeword, t->d_layers, t->height, t->stored_width, t->full_width, d_idx,
@@ -717,8 +694,8 @@ int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows,
     e = cudaMemcpyAsync(out_paths, d_buf + rows_words, paths_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream);
-  lm_free(c->stream, d_idx);
-  if (d_buf) lm_free(c->stream, d_buf);
+  cudaFree(d_idx);
+  if (d_buf) cudaFree(d_buf);
   if (e != cudaSuccess) return cuda_fail(e, "lm_open");
   return LM_OK;
 }
@@ -773,10 +750,10 @@ int lm_sc_free(lm_sumcheck* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
   }
-  if (s->d_p_owned) lm_free(s->ctx->stream, s->d_p_owned);
-  if (s->d_w) lm_free(s->ctx->stream, s->d_w);
-  if (s->d_out10) lm_free(s->ctx->stream, s->d_out10);
-  if (s->d_scratch) lm_free(s->ctx->stream, s->d_scratch);
+  if (s->d_p_owned) cudaFree(s->d_p_owned);
+  if (s->d_w) cudaFree(s->d_w);
+  if (s->d_out10) cudaFree(s->d_out10);
+  if (s->d_scratch) cudaFree(s->d_scratch);
   delete s;
   return LM_OK;
 }
@@ -791,9 +768,9 @@ static int sc_new_common(lm_ctx* c, uint32_t n_vars, lm_sumcheck** out) {
   s->ctx = c;
   s->n_vars = n_vars;
   const size_t w_bytes = ((size_t)5 << n_vars) * sizeof(uint32_t);
-  cudaError_t e = lm_malloc(c->stream, &s->d_w, w_bytes);
+  cudaError_t e = cudaMalloc(&s->d_w, w_bytes);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_w, 0, w_bytes, c->stream);
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &s->d_out10, 16 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_out10, 16 * sizeof(uint32_t));
   if (e != cudaSuccess) {
     lm_sc_free(s);
     return cuda_fail(e, "lm_sc_new");
@@ -825,7 +802,7 @@ int lm_sc_new(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, u
   int rc = sc_new_common(c, n_vars, out);
   if (rc != LM_OK) return rc;
   lm_sumcheck* s = *out;
-  cudaError_t e = lm_malloc(c->stream, &s->d_p_owned, (live_len ? live_len : 1) * dim * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&s->d_p_owned, (live_len ? live_len : 1) * dim * sizeof(uint32_t));
   if (e == cudaSuccess && live_len)
     e = cudaMemcpyAsync(s->d_p_owned, evals, live_len * dim * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -846,7 +823,7 @@ int lm_sc_new_from_dev(lm_ctx* c, const uint32_t* d_poly, const uint32_t* d_weig
   if (rc != LM_OK) return rc;
   lm_sumcheck* s = *out;
   const size_t bytes = ((size_t)5 << n_vars) * sizeof(uint32_t);
-  cudaError_t e = lm_malloc(c->stream, &s->d_p_owned, bytes);
+  cudaError_t e = cudaMalloc(&s->d_p_owned, bytes);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_p_owned, d_poly, bytes, cudaMemcpyDeviceToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_w, d_weights, bytes, cudaMemcpyDeviceToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -952,7 +929,7 @@ static int sc_prepare_fold_target(lm_sumcheck* s, uint32_t** p_out) {
     return LM_OK;
   }
   uint32_t* fresh = nullptr;
-  CU(lm_malloc(s->ctx->stream, &fresh, half * 5 * sizeof(uint32_t)));
+  CU(cudaMalloc(&fresh, half * 5 * sizeof(uint32_t)));
   *p_out = fresh;
   return LM_OK;
 }
@@ -960,7 +937,7 @@ static void sc_commit_fold(lm_sumcheck* s, uint32_t* p_out) {
   if (p_out != s->d_p_owned) {
     if (s->d_p_owned) {
       cudaStreamSynchronize(s->ctx->stream);
-      lm_free(s->ctx->stream, s->d_p_owned);
+      cudaFree(s->d_p_owned);
     }
     s->d_p_owned = p_out;
   }
@@ -1052,11 +1029,11 @@ int lm_air_free(lm_air* a) {
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->stream);
   }
-  if (a->d_cols) lm_free(a->ctx->stream, a->d_cols);
-  if (a->d_spare) lm_free(a->ctx->stream, a->d_spare);
-  if (a->d_eq) lm_free(a->ctx->stream, a->d_eq);
-  if (a->d_scratch) lm_free(a->ctx->stream, a->d_scratch);
-  if (a->d_out) lm_free(a->ctx->stream, a->d_out);
+  if (a->d_cols) cudaFree(a->d_cols);
+  if (a->d_spare) cudaFree(a->d_spare);
+  if (a->d_eq) cudaFree(a->d_eq);
+  if (a->d_scratch) cudaFree(a->d_scratch);
+  if (a->d_out) cudaFree(a->d_out);
   delete a;
   return LM_OK;
 }
@@ -1098,7 +1075,7 @@ static int air_new_impl(lm_ctx* c, uint32_t table_id, const uint32_t* const* col
   const uint32_t all = a->n_cols + a->n_shift;
   a->dim = cols_ef ? 5 : 1;
   a->cols_words = (size_t)all * n * a->dim;
-  cudaError_t e = lm_malloc(c->stream, &a->d_cols, a->cols_words * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&a->d_cols, a->cols_words * sizeof(uint32_t));
   if (cols_ef) {
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(a->d_cols, cols_ef, a->cols_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
@@ -1118,11 +1095,11 @@ static int air_new_impl(lm_ctx* c, uint32_t table_id, const uint32_t* const* col
                             cudaMemcpyHostToDevice, c->stream);
     }
   }
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &a->d_eq, (size_t)log_rows * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_eq, (size_t)log_rows * 5 * sizeof(uint32_t));
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(a->d_eq, eq_factor, (size_t)log_rows * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &a->d_scratch, lm::air_round_scratch_words(log_rows) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &a->d_out, 64 * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_scratch, lm::air_round_scratch_words(log_rows) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_out, 64 * 5 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
     lm_air_free(a);
@@ -1177,7 +1154,7 @@ int lm_poseidon16_fill_trace(lm_ctx* c, uint32_t* const* cols, uint64_t n_rows) 
   if (n_rows == 0) return LM_OK;
   CU(cudaSetDevice(c->device));
   uint32_t* d = nullptr;
-  CU(lm_malloc(c->stream, &d, (size_t)109 * n_rows * sizeof(uint32_t)));
+  CU(cudaMalloc(&d, (size_t)109 * n_rows * sizeof(uint32_t)));
   cudaError_t e = cudaSuccess;
   // inputs: flag_permute (column 8) and the 16 input lanes (columns 9..24)
   for (int k = 8; e == cudaSuccess && k < 25; k++)
@@ -1186,7 +1163,7 @@ int lm_poseidon16_fill_trace(lm_ctx* c, uint32_t* const* cols, uint64_t n_rows) 
   for (int k = 25; e == cudaSuccess && k < 109; k++)
     e = cudaMemcpyAsync(cols[k], d + (size_t)k * n_rows, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  lm_free(c->stream, d);
+  cudaFree(d);
   if (e != cudaSuccess) return cuda_fail(e, "lm_poseidon16_fill_trace");
   return LM_OK;
 }
@@ -1225,10 +1202,10 @@ int lm_air_fold(lm_air* a, const uint32_t r[5]) {
   const uint32_t all = a->n_cols + a->n_shift;
   const size_t need = (size_t)all * (n / 2) * 5;
   if (a->spare_words < need) {
-    if (a->d_spare) lm_free(c->stream, a->d_spare);
+    if (a->d_spare) cudaFree(a->d_spare);
     a->d_spare = nullptr;
     a->spare_words = 0;
-    CU(lm_malloc(c->stream, &a->d_spare, need * sizeof(uint32_t)));
+    CU(cudaMalloc(&a->d_spare, need * sizeof(uint32_t)));
     a->spare_words = need;
   }
   CU(lm::air_fold_lsb(c->stream, a->d_cols, a->dim, n, all, r, a->d_spare));
@@ -1257,13 +1234,13 @@ int lm_gkr_free(lm_gkr* g) {
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
   }
-  for (auto p : g->nums) lm_free(g->ctx->stream, p);
-  for (auto p : g->dens) lm_free(g->ctx->stream, p);
+  for (auto p : g->nums) cudaFree(p);
+  for (auto p : g->dens) cudaFree(p);
   for (int k = 0; k < 2; k++)
-    if (g->d_w[k]) lm_free(g->ctx->stream, g->d_w[k]);
-  if (g->d_eq) lm_free(g->ctx->stream, g->d_eq);
-  if (g->d_scratch) lm_free(g->ctx->stream, g->d_scratch);
-  if (g->d_out10) lm_free(g->ctx->stream, g->d_out10);
+    if (g->d_w[k]) cudaFree(g->d_w[k]);
+  if (g->d_eq) cudaFree(g->d_eq);
+  if (g->d_scratch) cudaFree(g->d_scratch);
+  if (g->d_out10) cudaFree(g->d_out10);
   delete g;
   return LM_OK;
 }
@@ -1273,7 +1250,7 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
                            uint32_t top_vars = LM_GKR_TOP_VARS) {
   lm_gkr* g = new (std::nothrow) lm_gkr();
   if (!g) {
-    lm_free(c->stream, d_n), lm_free(c->stream, d_d);
+    cudaFree(d_n), cudaFree(d_d);
     return fail(LM_ERR_OOM, "lm_gkr: host allocation failed");
   }
   g->ctx = c;
@@ -1287,18 +1264,18 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
   for (uint32_t l = 1; e == cudaSuccess && l <= n_vars - top_vars; l++) {
     const uint64_t m = n >> l;
     uint32_t *nn = nullptr, *dd = nullptr;
-    e = lm_malloc(c->stream, &nn, m * 5 * sizeof(uint32_t));
-    if (e == cudaSuccess) g->nums.push_back(nn), e = lm_malloc(c->stream, &dd, m * 5 * sizeof(uint32_t));
+    e = cudaMalloc(&nn, m * 5 * sizeof(uint32_t));
+    if (e == cudaSuccess) g->nums.push_back(nn), e = cudaMalloc(&dd, m * 5 * sizeof(uint32_t));
     if (e == cudaSuccess) g->dens.push_back(dd);
     if (e == cudaSuccess) e = lm::gkr_layer_up(c->stream, g->nums[l - 1], l == 1 ? 1 : 5, g->dens[l - 1], m * 2, nn, dd);
   }
   // working tables: the first fold of the largest layer produces 2^(n_vars - 2) rows of 20 words
   const size_t w_words = ((size_t)1 << (n_vars - 2)) * 20;
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &g->d_w[0], w_words * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &g->d_w[1], (w_words / 2 ? w_words / 2 : 20) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &g->d_eq, 64 * 5 * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &g->d_scratch, lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &g->d_out10, 16 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_w[0], w_words * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_w[1], (w_words / 2 ? w_words / 2 : 20) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_eq, 64 * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_scratch, lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_out10, 16 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
     lm_gkr_free(g);
@@ -1326,12 +1303,12 @@ int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t a
   CU(cudaSetDevice(c->device));
   const uint64_t n = (uint64_t)1 << n_vars;
   uint32_t *d_n = nullptr, *d_d = nullptr;
-  cudaError_t e = lm_malloc(c->stream, &d_n, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &d_d, n * 5 * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) {
-    lm_free(c->stream, d_n), lm_free(c->stream, d_d);
+    cudaFree(d_n), cudaFree(d_d);
     return cuda_fail(e, "lm_gkr_new");
   }
   return gkr_from_device(c, d_n, d_d, active_len, n_vars, out);
@@ -1347,14 +1324,14 @@ int lm_gkr_new_shard(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint
   if (active_len > n) return fail(LM_ERR_INVALID, "lm_gkr_new_shard: active_len exceeds 2^n_vars");
   CU(cudaSetDevice(c->device));
   uint32_t *d_n = nullptr, *d_d = nullptr;
-  cudaError_t e = lm_malloc(c->stream, &d_n, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &d_d, n * 5 * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
   if (e == cudaSuccess && active_len)
     e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess && active_len)
     e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) {
-    lm_free(c->stream, d_n), lm_free(c->stream, d_d);
+    cudaFree(d_n), cudaFree(d_d);
     return cuda_fail(e, "lm_gkr_new_shard");
   }
   return gkr_from_device(c, d_n, d_d, active_len, n_vars, out, top_vars);
@@ -1391,7 +1368,7 @@ struct lm_logup {
     }
     uint32_t* d = nullptr;
     const uint64_t padded = (len + 1023) / 1024 * 1024 + 1024;  // lm_dev_mle_eval reads whole 2^10-element chunks
-    CU(lm_malloc(ctx->stream, &d, padded * sizeof(uint32_t)));
+    CU(cudaMalloc(&d, padded * sizeof(uint32_t)));
     cache[key] = d;
     CU(cudaMemcpyAsync(d, host, len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(d + len, 0, (padded - len) * sizeof(uint32_t), ctx->stream));
@@ -1418,8 +1395,8 @@ int lm_logup_new(lm_ctx* c, uint64_t total_active_len, const uint32_t cc[5], con
   for (int k = 0; k < 5; k++) L->c.c[k] = cc[k];
   L->alphas.assign(alphas_eq_poly, alphas_eq_poly + 5 * (size_t)n_alphas);
   const uint64_t n = (uint64_t)1 << n_vars;
-  cudaError_t e = lm_malloc(c->stream, &L->d_nums, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &L->d_dens, n * 5 * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&L->d_nums, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&L->d_dens, n * 5 * sizeof(uint32_t));
   if (e != cudaSuccess) {
     lm_logup_free(L);
     return cuda_fail(e, "lm_logup_new");
@@ -1514,9 +1491,9 @@ int lm_logup_finish(lm_logup* L, lm_gkr** out) {
 int lm_logup_free(lm_logup* L) {
   if (!L) return LM_OK;
   if (L->ctx) cudaSetDevice(L->ctx->device);
-  if (L->d_nums) lm_free(L->ctx->stream, L->d_nums);
-  if (L->d_dens) lm_free(L->ctx->stream, L->d_dens);
-  for (auto& kv : L->cache) lm_free(L->ctx->stream, kv.second);
+  if (L->d_nums) cudaFree(L->d_nums);
+  if (L->d_dens) cudaFree(L->d_dens);
+  for (auto& kv : L->cache) cudaFree(kv.second);
   delete L;
   return LM_OK;
 }
@@ -1617,18 +1594,18 @@ int lm_finger_print(lm_ctx* c, const uint32_t* data, uint64_t n_rows, uint32_t n
   if (n_rows == 0) return LM_OK;
   CU(cudaSetDevice(c->device));
   uint32_t *d_data = nullptr, *d_al = nullptr, *d_out = nullptr;
-  cudaError_t e = lm_malloc(c->stream, &d_data, n_rows * n_data * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &d_al, (size_t)n_data * 5 * sizeof(uint32_t));
-  if (e == cudaSuccess) e = lm_malloc(c->stream, &d_out, n_rows * 5 * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&d_data, n_rows * n_data * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_al, (size_t)n_data * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, n_rows * 5 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_data, data, n_rows * n_data * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_al, alphas, (size_t)n_data * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = lm::finger_print(c->stream, d_data, n_rows, n_data, d_al, cc, d_out);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n_rows * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream);
-  if (d_data) lm_free(c->stream, d_data);
-  if (d_al) lm_free(c->stream, d_al);
-  if (d_out) lm_free(c->stream, d_out);
+  if (d_data) cudaFree(d_data);
+  if (d_al) cudaFree(d_al);
+  if (d_out) cudaFree(d_out);
   if (e != cudaSuccess) return cuda_fail(e, "lm_finger_print");
   return LM_OK;
 }
@@ -1646,7 +1623,7 @@ int lm_mle_eval(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim,
   const uint64_t chunk = n_vars < 10 ? len : 1024;
   uint64_t padded = (live_len + chunk - 1) / chunk * chunk;
   if (padded == 0) padded = chunk;
-  CU(lm_malloc(c->stream, &d_evals, padded * dim * sizeof(uint32_t)));
+  CU(cudaMalloc(&d_evals, padded * dim * sizeof(uint32_t)));
   cudaError_t e = cudaMemcpyAsync(d_evals, evals, live_len * dim * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess && padded > live_len)
     e = cudaMemsetAsync(d_evals + live_len * dim, 0, (padded - live_len) * dim * sizeof(uint32_t), c->stream);
@@ -1661,7 +1638,7 @@ int lm_mle_eval(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim,
     if (e != cudaSuccess) rc = cuda_fail(e, "lm_mle_eval download");
   }
   cudaStreamSynchronize(c->stream);
-  lm_free(c->stream, d_evals);
+  cudaFree(d_evals);
   return rc;
 }
 
