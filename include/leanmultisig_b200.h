@@ -260,6 +260,10 @@ int lm_logup_section(lm_logup* logup, uint64_t n_rows, uint32_t num_mode, const 
 int lm_logup_col_eval(lm_logup* logup, const uint32_t* col, uint64_t len, uint32_t n_vars, const uint32_t* point,
                       uint32_t out[5]);
 /* copy what has been filled so far back to the host (parity tests); either pointer may be NULL */
+/* the same for n_cols (<= 256) columns at ONE point: eq tables built once, one launch pair per column, one read-back
+ * (logup.rs:224-305 evaluates every looked-up column of a table at the same inner point); out: n_cols x 5 words */
+int lm_logup_col_eval_batch(lm_logup* logup, const uint32_t* const* cols, const uint64_t* lens, uint32_t n_cols,
+                            uint32_t n_vars, const uint32_t* point, uint32_t* out);
 int lm_logup_read(lm_logup* logup, uint32_t* out_nums, uint32_t* out_dens);
 /* all total_active_len rows filled: pad to the next power of two with (0, 1) and run the GKR up pass */
 int lm_logup_finish(lm_logup* logup, lm_gkr** out);

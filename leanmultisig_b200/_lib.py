@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
             "lm_logup_new": [vp, u64, u32p, u32p, u32, C.POINTER(vp)],
             "lm_logup_section": [vp, u64, u32, vp, C.c_int32, u32, vp, u32],
             "lm_logup_col_eval": [vp, vp, u64, u32, u32p, u32p],
+            "lm_logup_col_eval_batch": [vp, C.POINTER(vp), u64p, u32, u32, u32p, u32p],
             "lm_logup_read": [vp, vp, vp],
             "lm_logup_finish": [vp, C.POINTER(vp)],
             "lm_logup_free": [vp],

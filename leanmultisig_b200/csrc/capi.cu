@@ -178,6 +178,7 @@ struct lm_gkr {
   uint32_t cur_vars = 0;  // variables still unbound in the working columns
   int cur_src = 0, cur_buf = 0;
   uint32_t alpha[5] = {0, 0, 0, 0, 0};
+  void* arena = nullptr;                             // one allocation for the upper layers, working tables and small buffers
   uint32_t top_vars = 5;                             // the up pass stops at 2^top_vars fractions
   uint32_t eq_scale[5] = {lm::KB_R1, 0, 0, 0, 0};    // constant factor of the current layer's eq weights (shards)
 };
@@ -1234,13 +1235,10 @@ int lm_gkr_free(lm_gkr* g) {
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
   }
-  for (auto p : g->nums) cudaFree(p);
-  for (auto p : g->dens) cudaFree(p);
-  for (int k = 0; k < 2; k++)
-    if (g->d_w[k]) cudaFree(g->d_w[k]);
-  if (g->d_eq) cudaFree(g->d_eq);
-  if (g->d_scratch) cudaFree(g->d_scratch);
-  if (g->d_out10) cudaFree(g->d_out10);
+  // layer 0 is owned separately (uploaded by lm_gkr_new or handed over by lm_logup_finish); the rest is one arena
+  if (!g->nums.empty()) cudaFree(g->nums[0]);
+  if (!g->dens.empty()) cudaFree(g->dens[0]);
+  if (g->arena) cudaFree(g->arena);
   delete g;
   return LM_OK;
 }
@@ -1259,23 +1257,39 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
   g->nums.push_back(d_n);
   g->dens.push_back(d_d);
   const uint64_t n = (uint64_t)1 << n_vars;
-  cudaError_t e = lm::gkr_pad(c->stream, d_n, 1, d_d, active_len, n);
-  // up pass (mod.rs:52-62): halve until 2^5 fractions remain
+  // one allocation for everything but layer 0 (40 cudaMalloc calls of up to hundreds of MiB cost more than the up pass)
+  auto align = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t w_words = ((size_t)1 << (n_vars - 2)) * 20;
+  const size_t w1_words = w_words / 2 ? w_words / 2 : 20;
+  size_t total = 0;
+  for (uint32_t l = 1; l <= n_vars - top_vars; l++) total += 2 * align((n >> l) * 5 * sizeof(uint32_t));
+  total += align(w_words * sizeof(uint32_t)) + align(w1_words * sizeof(uint32_t)) + align(64 * 5 * sizeof(uint32_t)) +
+           align(lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t)) + align(16 * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&g->arena, total);
+  uint8_t* cur = static_cast<uint8_t*>(g->arena);
+  auto carve = [&](size_t bytes) {
+    uint32_t* p = reinterpret_cast<uint32_t*>(cur);
+    cur += align(bytes);
+    return p;
+  };
+  if (e == cudaSuccess) e = lm::gkr_pad(c->stream, d_n, 1, d_d, active_len, n);
+  // up pass (mod.rs:52-62): halve until 2^top_vars fractions remain
   for (uint32_t l = 1; e == cudaSuccess && l <= n_vars - top_vars; l++) {
     const uint64_t m = n >> l;
-    uint32_t *nn = nullptr, *dd = nullptr;
-    e = cudaMalloc(&nn, m * 5 * sizeof(uint32_t));
-    if (e == cudaSuccess) g->nums.push_back(nn), e = cudaMalloc(&dd, m * 5 * sizeof(uint32_t));
-    if (e == cudaSuccess) g->dens.push_back(dd);
-    if (e == cudaSuccess) e = lm::gkr_layer_up(c->stream, g->nums[l - 1], l == 1 ? 1 : 5, g->dens[l - 1], m * 2, nn, dd);
+    uint32_t* nn = carve(m * 5 * sizeof(uint32_t));
+    uint32_t* dd = carve(m * 5 * sizeof(uint32_t));
+    g->nums.push_back(nn);
+    g->dens.push_back(dd);
+    e = lm::gkr_layer_up(c->stream, g->nums[l - 1], l == 1 ? 1 : 5, g->dens[l - 1], m * 2, nn, dd);
   }
-  // working tables: the first fold of the largest layer produces 2^(n_vars - 2) rows of 20 words
-  const size_t w_words = ((size_t)1 << (n_vars - 2)) * 20;
-  if (e == cudaSuccess) e = cudaMalloc(&g->d_w[0], w_words * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&g->d_w[1], (w_words / 2 ? w_words / 2 : 20) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&g->d_eq, 64 * 5 * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&g->d_scratch, lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&g->d_out10, 16 * sizeof(uint32_t));
+  if (e == cudaSuccess) {
+    // working tables: the first fold of the largest layer produces 2^(n_vars - 2) rows of 20 words
+    g->d_w[0] = carve(w_words * sizeof(uint32_t));
+    g->d_w[1] = carve(w1_words * sizeof(uint32_t));
+    g->d_eq = carve(64 * 5 * sizeof(uint32_t));
+    g->d_scratch = carve(lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t));
+    g->d_out10 = carve(16 * sizeof(uint32_t));
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
     lm_gkr_free(g);
@@ -1358,6 +1372,27 @@ struct lm_logup {
   lm::Ef c;
   std::vector<uint32_t> alphas;  // n x 5
   std::map<std::pair<const void*, uint64_t>, uint32_t*> cache;  // host array -> device copy
+  // the ~150 column copies of a proof are carved from a few large chunks: one cudaMalloc per column cost more than its copy
+  std::vector<void*> chunks;
+  uint8_t* arena_cur = nullptr;
+  size_t arena_left = 0;
+  uint32_t* d_batch_out = nullptr;  // results of lm_logup_col_eval_batch (256 x 5 words)
+
+  int arena_get(size_t bytes, uint32_t** out) {
+    bytes = (bytes + 255) / 256 * 256;
+    if (bytes > arena_left) {
+      const size_t chunk = bytes > ((size_t)256 << 20) ? bytes : ((size_t)256 << 20);
+      void* p = nullptr;
+      CU(cudaMalloc(&p, chunk));
+      chunks.push_back(p);
+      arena_cur = static_cast<uint8_t*>(p);
+      arena_left = chunk;
+    }
+    *out = reinterpret_cast<uint32_t*>(arena_cur);
+    arena_cur += bytes;
+    arena_left -= bytes;
+    return LM_OK;
+  }
 
   int device_copy(const uint32_t* host, uint64_t len, uint32_t** out) {
     auto key = std::make_pair((const void*)host, len);
@@ -1368,7 +1403,7 @@ struct lm_logup {
     }
     uint32_t* d = nullptr;
     const uint64_t padded = (len + 1023) / 1024 * 1024 + 1024;  // lm_dev_mle_eval reads whole 2^10-element chunks
-    CU(cudaMalloc(&d, padded * sizeof(uint32_t)));
+    if (int rc = arena_get(padded * sizeof(uint32_t), &d)) return rc;
     cache[key] = d;
     CU(cudaMemcpyAsync(d, host, len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(d + len, 0, (padded - len) * sizeof(uint32_t), ctx->stream));
@@ -1466,6 +1501,31 @@ int lm_logup_col_eval(lm_logup* L, const uint32_t* col, uint64_t len, uint32_t n
   return mle_eval_on_device(c, d, n_vars, 1, len, point, out);
 }
 
+int lm_logup_col_eval_batch(lm_logup* L, const uint32_t* const* cols, const uint64_t* lens, uint32_t n_cols, uint32_t n_vars,
+                            const uint32_t* point, uint32_t* out) {
+  if (!L || (n_cols && (!cols || !lens || !out)) || (n_vars && !point)) return fail(LM_ERR_INVALID, "lm_logup_col_eval_batch: null argument");
+  if (n_cols == 0) return LM_OK;
+  if (n_cols > 256) return fail(LM_ERR_INVALID, "lm_logup_col_eval_batch: at most 256 columns per call, got %u", n_cols);
+  if (n_vars > 40) return fail(LM_ERR_INVALID, "lm_logup_col_eval_batch: n_vars %u too large", n_vars);
+  lm_ctx* c = L->ctx;
+  CU(cudaSetDevice(c->device));
+  std::vector<const uint32_t*> d_cols(n_cols);
+  for (uint32_t k = 0; k < n_cols; k++) {
+    if (!cols[k]) return fail(LM_ERR_INVALID, "lm_logup_col_eval_batch: column %u is null", k);
+    if (lens[k] > ((uint64_t)1 << n_vars)) return fail(LM_ERR_INVALID, "lm_logup_col_eval_batch: column %u longer than 2^n_vars", k);
+    uint32_t* d = nullptr;
+    if (int rc = L->device_copy(cols[k], lens[k], &d)) return rc;
+    d_cols[k] = d;
+  }
+  if (!L->d_batch_out) CU(cudaMalloc(&L->d_batch_out, 256 * 5 * sizeof(uint32_t)));
+  if (int rc = c->ensure_scratch(lm::mle_eval_scratch_words(n_vars))) return rc;
+  if (n_vars) CU(cudaMemcpyAsync(c->d_point, point, (size_t)n_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(lm::mle_eval_batch(c->stream, d_cols.data(), lens, n_cols, n_vars, c->d_point, c->d_scratch, L->d_batch_out));
+  CU(cudaMemcpyAsync(out, L->d_batch_out, (size_t)n_cols * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
 int lm_logup_read(lm_logup* L, uint32_t* out_nums, uint32_t* out_dens) {
   if (!L) return fail(LM_ERR_INVALID, "lm_logup_read: null argument");
   lm_ctx* c = L->ctx;
@@ -1493,7 +1553,9 @@ int lm_logup_free(lm_logup* L) {
   if (L->ctx) cudaSetDevice(L->ctx->device);
   if (L->d_nums) cudaFree(L->d_nums);
   if (L->d_dens) cudaFree(L->d_dens);
-  for (auto& kv : L->cache) cudaFree(kv.second);
+  if (L->ctx) cudaStreamSynchronize(L->ctx->stream);
+  for (void* p : L->chunks) cudaFree(p);
+  if (L->d_batch_out) cudaFree(L->d_batch_out);
   delete L;
   return LM_OK;
 }

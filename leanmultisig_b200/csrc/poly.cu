@@ -181,6 +181,39 @@ cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_va
   return cudaGetLastError();
 }
 
+// n_cols base-field columns at ONE point: the two eq tables are built once, every column is one streaming launch plus its
+// partial-sum reduction, results land in d_out[5 k ..] — no host round trip between columns (Logup evaluates ~100 columns
+// of a table at the same point, logup.rs:224-305).  d_cols / live_lens are host arrays.
+cudaError_t mle_eval_batch(cudaStream_t stream, const uint32_t* const* d_cols, const uint64_t* live_lens, uint32_t n_cols,
+                           uint32_t n_vars, const uint32_t* d_point, uint32_t* d_scratch, uint32_t* d_out) {
+  const int lo_vars = n_vars < (uint32_t)LO_VARS ? (int)n_vars : LO_VARS;
+  const int hi_vars = (int)n_vars - lo_vars;
+  const uint64_t n_hi = (uint64_t)1 << hi_vars, n_lo = (uint64_t)1 << lo_vars;
+  uint32_t* d_eq_hi = d_scratch;
+  uint32_t* d_eq_lo = d_eq_hi + 5 * n_hi;
+  uint32_t* d_partial = d_eq_lo + 5 * n_lo;
+  const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
+  cudaError_t e;
+  if ((e = eq_table(stream, d_point, hi_vars, one, d_eq_hi)) != cudaSuccess) return e;
+  if ((e = eq_table(stream, d_point + 5 * hi_vars, lo_vars, one, d_eq_lo)) != cudaSuccess) return e;
+  for (uint32_t k = 0; k < n_cols; k++) {
+    uint64_t live_rows = (live_lens[k] + n_lo - 1) / n_lo;
+    if (live_rows > n_hi) live_rows = n_hi;
+    uint64_t n_cta = live_rows < 4096 ? live_rows : 4096;
+    if (n_cta == 0) n_cta = 1;
+    const uint64_t rows_per_cta = (live_rows + n_cta - 1) / n_cta;
+    n_cta = rows_per_cta ? (live_rows + rows_per_cta - 1) / rows_per_cta : 1;
+    if (n_cta == 0) n_cta = 1;
+    mle_eval_kernel<1><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_cols[k], lo_vars, live_rows, rows_per_cta, d_eq_hi, d_eq_lo,
+                                                                     d_partial);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    sum_partials_kernel<<<1, 256, 0, stream>>>(d_partial, (int)n_cta, d_out + 5 * k);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
 // out[i] = in[i] + r * (in[i + half] - in[i]),  i < half;   EF output
 template <int DIM>
 __global__ void fold_msb_kernel(const uint32_t* in, uint64_t half, uint64_t live, Ef r, uint32_t* out) {

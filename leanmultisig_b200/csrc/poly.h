@@ -20,4 +20,7 @@ cudaError_t fold_msb(cudaStream_t stream, const uint32_t* d_in, uint64_t n_in, u
 cudaError_t access_count(cudaStream_t stream, const uint32_t* d_idx_col, uint64_t n, uint32_t n_values, uint64_t table_len,
                          uint32_t* d_counts, uint32_t* d_bad);
 cudaError_t counts_to_monty(cudaStream_t stream, uint32_t* d_counts, uint64_t n);
+// n_cols base-field columns (host array of device pointers) at one point; d_out: n_cols x 5 words
+cudaError_t mle_eval_batch(cudaStream_t stream, const uint32_t* const* d_cols, const uint64_t* live_lens, uint32_t n_cols,
+                           uint32_t n_vars, const uint32_t* d_point, uint32_t* d_scratch, uint32_t* d_out);
 }  // namespace lm

@@ -241,6 +241,21 @@ class LogupBuilder:
             ncol = num_col.ctypes.data
         check(lib().lm_logup_section(self.handle, n_rows, num_mode, ncol, den_sign, domainsep, C.byref(arr), len(data)))
 
+    def col_eval_batch(self, cols, n_vars: int, point) -> np.ndarray:
+        """evaluations (len(cols) x 5) of several columns at ONE point: eq tables built once, one read-back"""
+        pt = _u32(point).reshape(-1, 5)
+        assert pt.shape[0] == n_vars
+        out = np.empty((len(cols), 5), dtype=np.uint32)
+        for k0 in range(0, len(cols), 256):
+            part = cols[k0:k0 + 256]
+            for c in part:
+                assert c.dtype == np.uint32 and c.flags["C_CONTIGUOUS"]
+            ptrs = (C.c_void_p * len(part))(*[c.ctypes.data for c in part])
+            lens = np.array([c.size for c in part], dtype=np.uint64)
+            check(lib().lm_logup_col_eval_batch(self.handle, ptrs, lens.ctypes.data_as(C.POINTER(C.c_uint64)), len(part), n_vars,
+                                                _p(pt), _p(out[k0:k0 + len(part)])))
+        return out
+
     def col_eval(self, col, n_vars: int, point) -> np.ndarray:
         assert col.dtype == np.uint32 and col.flags["C_CONTIGUOUS"]
         out = np.empty(5, dtype=np.uint32)
@@ -303,17 +318,29 @@ def build_logup_table(ctx, c, alphas_eq_poly, memory, memory_acc, bytecode_multi
     return b
 
 
-def prove_generic_logup(ctx, prover_state, c, alphas_eq_poly, memory, memory_acc, bytecode_multilinear, bytecode_acc, traces):
-    """logup.rs:27-320 -> dict mirroring GenericLogupStatements (Montgomery arrays)"""
+def prove_generic_logup(ctx, prover_state, c, alphas_eq_poly, memory, memory_acc, bytecode_multilinear, bytecode_acc, traces,
+                        timings: dict | None = None):
+    """logup.rs:27-320 -> dict mirroring GenericLogupStatements (Montgomery arrays).  `timings`, when given, receives the
+    wall-clock seconds of the three phases (table assembly, GKR, column evaluations)."""
+    import time
+
     from . import tables as T
 
+    t_start = time.perf_counter()
     al = _u32(alphas_eq_poly).reshape(-1, 5)
     b = build_logup_table(ctx, c, al, memory, memory_acc, bytecode_multilinear, bytecode_acc, traces)
     gkr = b.finish()
+    if timings is not None:
+        ctx.sync()
+        timings["table assembly + GKR up pass"] = time.perf_counter() - t_start
+        t_start = time.perf_counter()
     total_gkr_n_vars = gkr.n_vars
     # a NativeProverState (C++ transcript) runs the whole GKR in the library's spine, anything else round by round here
     quotient, point, _, _ = gkr.prove_native(prover_state) if hasattr(prover_state, "handle") else gkr.prove_with_state(prover_state)
     gkr.free()
+    if timings is not None:
+        timings["GKR down pass"] = time.perf_counter() - t_start
+        t_start = time.perf_counter()
     assert not quotient.any(), "logup sum is not zero"
     log_memory = memory.size.bit_length() - 1
     stride = 1 << (T.N_INSTRUCTION_COLUMNS - 1).bit_length()
@@ -328,8 +355,9 @@ def prove_generic_logup(ctx, prover_state, c, alphas_eq_poly, memory, memory_acc
 
     out = dict(gkr_point=point, total_gkr_n_vars=total_gkr_n_vars)
     out["memory_and_acc_point"] = from_end(log_memory)
-    out["value_memory_acc"] = add(b.col_eval(memory_acc, log_memory, from_end(log_memory)))
-    out["value_memory"] = add(b.col_eval(memory, log_memory, from_end(log_memory)))
+    mem_evals = b.col_eval_batch([memory_acc, memory], log_memory, from_end(log_memory))
+    out["value_memory_acc"] = add(mem_evals[0])
+    out["value_memory"] = add(mem_evals[1])
     out["bytecode_and_acc_point"] = from_end(log_bytecode)
     out["value_bytecode_acc"] = add(b.col_eval(bytecode_acc, log_bytecode, from_end(log_bytecode)))
     out["bus_numerators_values"], out["bus_denominators_values"], out["columns_values"] = {}, {}, {}
@@ -338,27 +366,38 @@ def prove_generic_logup(ctx, prover_state, c, alphas_eq_poly, memory, memory_acc
     for table, log_n_rows in T.sort_tables_by_height({t: tr.log_n_rows for t, tr in traces.items()}):
         cols = traces[table].columns
         inner = from_end(log_n_rows)
+        # every column of this table that logup.rs:224-305 evaluates, at the one inner point, in one batch
+        needed = [bus_col for bus_col in (table.bus.selector, *table.bus.data)]
+        if table.is_execution:
+            needed += [T.COL_PC] + [T.N_RUNTIME_COLUMNS + k for k in range(T.N_INSTRUCTION_COLUMNS)]
+        for lk in table.lookups:
+            needed += [lk.index, *lk.values]
+        needed = sorted(set(needed))
+        batch = b.col_eval_batch([cols[k] for k in needed], log_n_rows, inner)
+        ev = {k: batch[i] for i, k in enumerate(needed)}
         values = {}
         if table.is_execution:
-            values[T.COL_PC] = add(b.col_eval(cols[T.COL_PC], log_n_rows, inner))
-            instr = [b.col_eval(cols[T.N_RUNTIME_COLUMNS + k], log_n_rows, inner) for k in range(T.N_INSTRUCTION_COLUMNS)]
+            values[T.COL_PC] = add(ev[T.COL_PC])
+            instr = [ev[T.N_RUNTIME_COLUMNS + k] for k in range(T.N_INSTRUCTION_COLUMNS)]
             prover_state.add_extension_scalars(np.concatenate(instr))
             for k, v in enumerate(instr):
                 values[T.N_RUNTIME_COLUMNS + k] = v
         bus = table.bus
-        sel = F.from_monty(b.col_eval(cols[bus.selector], log_n_rows, inner))
+        sel = F.from_monty(ev[bus.selector])
         if bus.pull:
             sel = F.neg(sel)
         out["bus_numerators_values"][table] = add(F.to_monty(sel))
-        data_evals = [F.from_monty(b.col_eval(cols[k], log_n_rows, inner)) for k in bus.data]
+        data_evals = [F.from_monty(ev[k]) for k in bus.data]
         fp = F.scal(al_c[-1], T.LOGUP_PRECOMPILE_DOMAINSEP)
         for a, d in zip(al_c, data_evals):
             fp = F.add(fp, F.mul(a, d))
         out["bus_denominators_values"][table] = add(F.to_monty(F.add(c_c, fp)))
         for lk in table.lookups:
-            values[lk.index] = add(b.col_eval(cols[lk.index], log_n_rows, inner))
+            values[lk.index] = add(ev[lk.index])
             for vcol in lk.values:
-                values[vcol] = add(b.col_eval(cols[vcol], log_n_rows, inner))
+                values[vcol] = add(ev[vcol])
         out["columns_values"][table] = values
     b.free()
+    if timings is not None:
+        timings["column evaluations"] = time.perf_counter() - t_start
     return out

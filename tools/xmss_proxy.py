@@ -142,8 +142,9 @@ def main():
     c = sample()
     alphas = sample(5)
     al_eq = ctx.eq_table(alphas)
+    logup_t = {}
     st = timed("logup (table assembly, quotient GKR, column evaluations)",
-               lambda: prove_generic_logup(ctx, ps, c, al_eq, memory, memory_acc, bytecode_m, bytecode_acc, traces))
+               lambda: prove_generic_logup(ctx, ps, c, al_eq, memory, memory_acc, bytecode_m, bytecode_acc, traces, timings=logup_t))
 
     def air():
         eta = sample()
@@ -178,6 +179,9 @@ def main():
     total = sum(phases.values())
     for k, v in phases.items():
         print(f"  {k:64s} {v * 1e3:9.1f} ms")
+        if k.startswith("logup"):
+            for kk, vv in logup_t.items():
+                print(f"      {kk:60s} {vv * 1e3:9.1f} ms")
     print(f"  {'total hot path':64s} {total * 1e3:9.1f} ms  ->  {n_sigs / total:.0f} signatures/s  (PROXY: assumed shapes, one GPU, "
           f"witness generation / VM execution not included)")
     if not os.environ.get("LM_PROXY_PAGEABLE"):
