@@ -97,6 +97,8 @@ class ShardedCommit:
         mark = getattr(b, "mark", None) or (lambda name: None)  # optional per-phase device timestamps (CudaBackend)
         mark("start")
         scatter = getattr(b, "scatter_dft", None) if self.world > 1 else None
+        if scatter is not None and not b.scatter_ready(self.dist, geo.block, w):
+            scatter = None
         if scatter is not None:
             # 1 + 2 fused: the last pass of the local transform stores every row into the matrix of the rank that owns it
             # after the exchange, through peer pointers over NVLink; a stream-ordered barrier closes the exchange
@@ -440,6 +442,7 @@ class CudaBackend:
 
         self._timing, self._marks = bool(os.environ.get("LM_SHARD_TIMING")), []
         self._scatter = {}   # (rows, cols) -> (own matrix, work buffer, peer tensors kept alive, pointer table)
+        self._scatter_ok, self._scatter_error = {}, None
         if os.environ.get("LM_SHARD_EXCHANGE", "p2p") != "p2p":
             self.scatter_dft = None  # fall back to the NCCL all-to-all after the local transform
 
@@ -474,9 +477,12 @@ class CudaBackend:
             work = torch.empty((rows, cols), dtype=torch.int32, device="cuda")
             world, rank = dist.get_world_size(), dist.get_rank()
             hbuf = C.create_string_buffer(64)
-            self.check(lib.lm_dev_ipc_export(self.ctx.handle, own.ptr, hbuf))
+            exported = lib.lm_dev_ipc_export(self.ctx.handle, own.ptr, hbuf) == 0
             handles = [None] * world
-            dist.all_gather_object(handles, bytes(hbuf.raw))
+            dist.all_gather_object(handles, bytes(hbuf.raw) if exported else None)  # every rank reaches this collective
+            if any(h is None for h in handles):
+                own.free()
+                raise RuntimeError("CUDA IPC export failed on a rank")
             table = np.zeros(world, dtype=np.uint64)
             opened = []
             for q in range(world):
@@ -493,7 +499,6 @@ class CudaBackend:
                                             "version": 3, "strides": None}
 
             mat = torch.as_tensor(_Raw(), device="cuda")
-            dist.barrier()
             self._scatter[key] = (mat, work, (own, opened), table)
         return self._scatter[key]
 
@@ -504,6 +509,23 @@ class CudaBackend:
                 self.lib.lm_dev_ipc_close(self.ctx.handle, p)
             own.free()
         self._scatter = {}
+
+    def scatter_ready(self, dist, rows, cols) -> bool:
+        """Collective: map the peer matrices for this shape; False on EVERY rank when any rank could not (no peer access, IPC
+        disabled in the container, ...) — the commit then takes the NCCL all-to-all path instead."""
+        key = (rows, cols)
+        if key in self._scatter_ok:
+            return self._scatter_ok[key]
+        ok = 1
+        try:
+            self._scatter_buffers(dist, rows, cols)
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            self._scatter_error = e
+        flag = self.torch.tensor([ok], dtype=self.torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self._scatter_ok[key] = bool(int(flag.item()))
+        return self._scatter_ok[key]
 
     def scatter_dft(self, dist, shard, n_vars, folding, log_inv_rate, cols):
         import ctypes as C

@@ -426,16 +426,32 @@ class WhirProver:
         # combine_statement (open.rs:518-584): OOD constraints first, then the caller's
         stm = [SparseStatement.dense(_points_to_monty(_expand_from_univariate(y, nv)), a)
                for y, a in zip(witness.ood_points, witness.ood_answers)] + list(statements)
+        import os
+        import time
+
+        tm = {} if os.environ.get("LM_WHIR_TIMING") else None
+        t_last = [time.perf_counter()]
+
+        def lap(name):  # wall-clock phase accounting (LM_WHIR_TIMING=1), printed at the end
+            if tm is not None:
+                self.ctx.sync()
+                now = time.perf_counter()
+                tm[name] = tm.get(name, 0.0) + now - t_last[0]
+                t_last[0] = now
+
         ps.duplex()
         gamma = F.from_monty(ps.sample())
         sc = self.ctx.sumcheck_from_tree(witness.tree)
+        lap("session (weights alloc)")
         total, gp = F.ZERO, F.ONE
         for smt in stm:
             for sel, val in smt.values:
                 (sc.add_next if smt.is_next else sc.add_eq)(sel, smt.point, F.to_monty(gp))
                 total = F.add(total, F.mul(F.from_monty(val), gp))
                 gp = F.mul(gp, gamma)
+        lap("combine_statement")
         randomness, total = self._rounds(sc, ps, cfg.first_folding, cfg.starting_folding_pow_bits, total)
+        lap("sumcheck rounds (incl. PoW)")
 
         trees = []
         tree = witness.tree
@@ -455,6 +471,7 @@ class WhirProver:
                 if cfg.final_sumcheck_rounds:
                     r, total = self._rounds(sc, ps, cfg.final_sumcheck_rounds, 0, total)
                     randomness += r
+                lap("final round")
                 break
             rp = cfg.round_parameters[round_index]
             ff_next = cfg.folding_at(round_index + 1)
@@ -463,11 +480,14 @@ class WhirProver:
             new_tree = sc.commit_poly(ff_next, log_inv_rate)
             trees.append(new_tree)
             ps.add_base_scalars(new_tree.root)
+            lap("round commit")
             ood_points, ood_answers = _sample_ood(ps, rp.ood_samples, num_variables, sc.eval_poly)
             ps.pow_grinding(rp.query_pow_bits)
+            lap("ood + query PoW")
             idx = ps.sample_in_range(log_folded, rp.num_queries)
             rows, paths = tree.open(idx)
             ps.hint_merkle_paths([(rows[q], paths[q], i) for q, i in enumerate(idx)])
+            lap("openings")
             # STIR answers: each opened leaf folded at this round's challenges (open.rs:161-190)
             dim = tree.elem_dim
             leaves = F.np_from_monty(rows)
@@ -499,7 +519,9 @@ class WhirProver:
                 sc.add_base_eq(stir_pts, _points_to_monty(stir_rand))
             for rnd, ev in zip(stir_rand, stir_evals):
                 total = F.add(total, F.mul(rnd, tuple(int(x) for x in ev)))
+            lap("STIR answers + weights update")
             r, total = self._rounds(sc, ps, ff_next, rp.folding_pow_bits, total)
+            lap("sumcheck rounds (incl. PoW)")
             randomness += r
             domain_size = new_domain_size
             gen = two_adic_generator(new_domain_size.bit_length() - 1 - ff_next)
@@ -507,4 +529,7 @@ class WhirProver:
         sc.free()
         for t in trees:
             t.free()
+        lap("free")
+        if tm is not None:
+            print("    WHIR open phases (ms):", {k: round(v * 1e3, 1) for k, v in tm.items()})
         return randomness
