@@ -291,6 +291,19 @@ int lm_dev_dft(lm_ctx* ctx, uint32_t* d_mat, uint64_t height, uint64_t width);
 int lm_dev_reorder_and_dft_scatter(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding_factor,
                                    uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_work, const uint64_t* peer_mats,
                                    uint32_t world, uint32_t rank);
+/* Column-range forms for the pipelined host-input path of the sharded commit (copy of the next column group overlaps the
+ * transform / exchange / hash of the current one): the transform + exchange of columns [col_begin, col_begin + col_count)
+ * (multiples of 8), the last layers on a column range of the received matrix (multiples of 4), and `count` sponge steps
+ * absorbing rate chunks chunk_hi, chunk_hi - 1, .. of every row into the 8-word states kept in d_digests (the call that
+ * takes chunk eff_w / 8 - 1 seeds them from the zero-suffix state; needs >= 2 all-zero trailing chunks). */
+int lm_dev_reorder_and_dft_scatter_cols(lm_ctx* ctx, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding_factor,
+                                        uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_work, const uint64_t* peer_mats,
+                                        uint32_t world, uint32_t rank, uint32_t col_begin, uint32_t col_count);
+int lm_dev_dft_layers_mapped_cols(lm_ctx* ctx, uint32_t* d_mat, uint64_t width, uint32_t log_h, uint32_t l_first,
+                                  uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, uint64_t col_begin,
+                                  uint64_t col_count);
+int lm_dev_merkle_absorb(lm_ctx* ctx, const uint32_t* d_mat, uint64_t height, uint32_t stored_width, uint32_t full_width,
+                         uint32_t effective_width, uint32_t chunk_hi, uint32_t count, uint32_t* d_digests);
 /* CUDA IPC plumbing for the peer matrices (one process per GPU): the owner exports a buffer it got from lm_dev_alloc, the
  * other ranks open the 64-byte handle from THEIR device (peer access over NVLink is enabled by the open) and close it at
  * the end.  The handle bytes travel through the caller's own channel (torch.distributed all_gather_object here). */

@@ -113,6 +113,9 @@ def lib() -> C.CDLL:
             "lm_dev_poseidon1": [vp, vp, u64, i],
             "lm_dev_reorder_and_dft": [vp, vp, u32, u32, u32, u32, u32, vp],
             "lm_dev_reorder_and_dft_scatter": [vp, vp, u32, u32, u32, u32, vp, u64p, u32, u32],
+            "lm_dev_reorder_and_dft_scatter_cols": [vp, vp, u32, u32, u32, u32, vp, u64p, u32, u32, u32, u32],
+            "lm_dev_dft_layers_mapped_cols": [vp, vp, u64, u32, u32, u64, u64, u64, u64, u64, u64],
+            "lm_dev_merkle_absorb": [vp, vp, u64, u32, u32, u32, u32, u32, vp],
             "lm_dev_ipc_export": [vp, vp, C.c_char_p],
             "lm_dev_ipc_open": [vp, C.c_char_p, C.POINTER(vp)],
             "lm_dev_ipc_close": [vp, vp],

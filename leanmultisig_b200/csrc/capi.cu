@@ -333,7 +333,16 @@ int lm_dev_reorder_and_dft(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, 
 int lm_dev_reorder_and_dft_scatter(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding, uint32_t log_inv_rate,
                                    uint32_t dft_n_cols, uint32_t* d_work, const uint64_t* peer_mats, uint32_t world,
                                    uint32_t rank) {
+  return lm_dev_reorder_and_dft_scatter_cols(c, d_evals, n_vars, folding, log_inv_rate, dft_n_cols, d_work, peer_mats, world, rank,
+                                             0, dft_n_cols);
+}
+
+int lm_dev_reorder_and_dft_scatter_cols(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding,
+                                        uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_work, const uint64_t* peer_mats,
+                                        uint32_t world, uint32_t rank, uint32_t col_begin, uint32_t col_count) {
   if (!c || !d_evals || !d_work || !peer_mats) return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft_scatter: null argument");
+  if (col_count == 0 || col_begin % 8 || col_begin + col_count > dft_n_cols || (col_count % 8 && col_begin + col_count != dft_n_cols))
+    return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft_scatter_cols: column range [%u, +%u) of %u", col_begin, col_count, dft_n_cols);
   if (world < 2 || world > 16 || (world & (world - 1)) || rank >= world)
     return fail(LM_ERR_INVALID, "lm_dev_reorder_and_dft_scatter: world %u / rank %u", world, rank);
   if (folding > n_vars) return fail(LM_ERR_INVALID, "folding_factor %u > n_vars %u", folding, n_vars);
@@ -349,7 +358,7 @@ int lm_dev_reorder_and_dft_scatter(lm_ctx* c, const uint32_t* d_evals, uint32_t 
     peers[q] = reinterpret_cast<uint32_t*>(peer_mats[q]);
   }
   CU(lm::ntt_reorder_and_dft_scatter(c->stream, d_evals, n_vars, folding, log_inv_rate, dft_n_cols, d_work, peers, world, rank,
-                                     c->d_tw, c->tw_log_n));
+                                     c->d_tw, c->tw_log_n, col_begin, col_count));
   return LM_OK;
 }
 
@@ -396,6 +405,32 @@ int lm_dev_dft_layers_mapped(lm_ctx* c, uint32_t* d_mat, uint64_t w, uint32_t lo
   if (log_h > c->tw_log_n) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped: domain exceeds the twiddle table");
   CU(cudaSetDevice(c->device));
   CU(lm::ntt_layers_mapped(c->stream, d_mat, w, log_h, l_first, n_blocks, run, block, offset, c->d_tw, c->tw_log_n));
+  return LM_OK;
+}
+
+int lm_dev_dft_layers_mapped_cols(lm_ctx* c, uint32_t* d_mat, uint64_t w, uint32_t log_h, uint32_t l_first, uint64_t n_blocks,
+                                  uint64_t run, uint64_t block, uint64_t offset, uint64_t col_begin, uint64_t col_count) {
+  if (!c) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped_cols: ctx is null");
+  if (w % 4 || col_begin % 4 || col_count % 4 || col_count == 0 || col_begin + col_count > w)
+    return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped_cols: column range [%llu, +%llu) of %llu", (unsigned long long)col_begin,
+                (unsigned long long)col_count, (unsigned long long)w);
+  if (log_h > c->tw_log_n) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped_cols: domain exceeds the twiddle table");
+  CU(cudaSetDevice(c->device));
+  CU(lm::ntt_layers_mapped(c->stream, d_mat, w, log_h, l_first, n_blocks, run, block, offset, c->d_tw, c->tw_log_n, col_begin,
+                           col_count));
+  return LM_OK;
+}
+
+int lm_dev_merkle_absorb(lm_ctx* c, const uint32_t* d_mat, uint64_t h, uint32_t stored_w, uint32_t full_w, uint32_t eff_w,
+                         uint32_t chunk_hi, uint32_t count, uint32_t* d_digests) {
+  if (!c || !d_mat || !d_digests) return fail(LM_ERR_INVALID, "lm_dev_merkle_absorb: null argument");
+  if (!lm::merkle_leaf_chunked_ok(stored_w, full_w, eff_w))
+    return fail(LM_ERR_INVALID, "lm_dev_merkle_absorb: widths full=%u stored=%u effective=%u cannot be hashed chunk by chunk", full_w,
+                stored_w, eff_w);
+  if (chunk_hi >= eff_w / 8 || count == 0 || count > chunk_hi + 1)
+    return fail(LM_ERR_INVALID, "lm_dev_merkle_absorb: chunks %u down %u of %u", chunk_hi, count, eff_w / 8);
+  CU(cudaSetDevice(c->device));
+  CU(lm::merkle_leaf_absorb_chunks(c->stream, d_mat, h, stored_w, full_w, eff_w, chunk_hi, count, d_digests));
   return LM_OK;
 }
 

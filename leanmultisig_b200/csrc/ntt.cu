@@ -292,11 +292,11 @@ __global__ void ntt_layer_mapped_kernel(uint32_t* __restrict__ mat, uint64_t w4,
 template <int NB_LOG>
 __global__ void __launch_bounds__(256)
 ntt_layers_mapped_fused_kernel(uint32_t* __restrict__ mat, uint64_t w4, int log_h, int l_first, uint64_t run, uint64_t block,
-                               uint64_t offset, const uint32_t* __restrict__ tw, int tw_shift) {
+                               uint64_t offset, const uint32_t* __restrict__ tw, int tw_shift, uint64_t c4_begin, uint64_t c4_count) {
   constexpr int NB = 1 << NB_LOG;
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= run * w4) return;
-  const uint64_t c4 = idx % w4, jp = idx / w4;
+  if (idx >= run * c4_count) return;
+  const uint64_t c4 = c4_begin + idx % c4_count, jp = idx / c4_count;
   uint4 v[NB];
 #pragma unroll
   for (int m = 0; m < NB; m++) v[m] = *(reinterpret_cast<const uint4*>(mat + ((uint64_t)m * run + jp) * (w4 * 4)) + c4);
@@ -317,22 +317,26 @@ ntt_layers_mapped_fused_kernel(uint32_t* __restrict__ mat, uint64_t w4, int log_
 
 cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, unsigned log_h, unsigned l_first,
                               uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, const uint32_t* d_tw,
-                              unsigned tw_log_n) {
+                              unsigned tw_log_n, uint64_t col_begin, uint64_t col_count) {
   if (w % 4 != 0 || log_h > tw_log_n || l_first > log_h || n_blocks < 2 || (((uint64_t)1 << l_first) < block))
     return cudaErrorInvalidValue;
+  if (col_count == 0) col_begin = 0, col_count = w;
+  if (col_begin % 4 || col_count % 4 || col_begin + col_count > w) return cudaErrorInvalidValue;
   const int tw_shift = (int)tw_log_n - (int)log_h;
   if ((((uint64_t)1 << l_first) == block) && n_blocks == ((uint64_t)1 << (log_h - l_first)) && n_blocks <= 8) {
-    const uint64_t items = run * (w / 4);
+    const uint64_t c4b = col_begin / 4, c4n = col_count / 4;
+    const uint64_t items = run * c4n;
     const unsigned grid = (unsigned)((items + 255) / 256);
     if (n_blocks == 2)
-      ntt_layers_mapped_fused_kernel<1><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift);
+      ntt_layers_mapped_fused_kernel<1><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
     else if (n_blocks == 4)
-      ntt_layers_mapped_fused_kernel<2><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift);
+      ntt_layers_mapped_fused_kernel<2><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
     else
-      ntt_layers_mapped_fused_kernel<3><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift);
+      ntt_layers_mapped_fused_kernel<3><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
     count_launch();
     return cudaGetLastError();
   }
+  if (col_begin != 0 || col_count != w) return cudaErrorInvalidValue;  // the per-layer fallback works on whole rows
   const uint64_t total = (n_blocks / 2) * run * (w / 4);
   for (unsigned l = l_first; l < log_h; l++) {
     ntt_layer_mapped_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l, n_blocks, run,
@@ -408,9 +412,13 @@ cudaError_t ntt_reorder_and_dft_cols(cudaStream_t stream, const uint32_t* d_eval
 // rank's own block x w scratch, peers[q] the matrix of rank q (q == rank: its own), each block x w words
 cudaError_t ntt_reorder_and_dft_scatter(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding_factor,
                                         uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_work, uint32_t* const* peers,
-                                        uint32_t world, uint32_t rank, const uint32_t* d_tw, unsigned tw_log_n) {
+                                        uint32_t world, uint32_t rank, const uint32_t* d_tw, unsigned tw_log_n,
+                                        uint32_t col_begin, uint32_t col_count) {
   if (folding_factor > n_vars + log_inv_rate || dft_n_cols % 4 || dft_n_cols == 0 || world < 2 || world > NTT_MAX_PEERS ||
       (world & (world - 1)) || rank >= world)
+    return cudaErrorInvalidValue;
+  if (col_count == 0) col_begin = 0, col_count = dft_n_cols;
+  if (col_begin % 8 || (col_count % 8 && col_begin + col_count != dft_n_cols) || col_begin + col_count > dft_n_cols)
     return cudaErrorInvalidValue;
   const uint32_t log_block = n_vars + log_inv_rate - folding_factor;
   uint32_t g = 0;
@@ -423,7 +431,8 @@ cudaError_t ntt_reorder_and_dft_scatter(cudaStream_t stream, const uint32_t* d_e
   sc.log_run = (int)(log_block - g);
   sc.rank = (int)rank;
   sc.enabled = 1;
-  return run_layers(stream, d_work, d_evals, log_block, log_inv_rate, h, dft_n_cols, skip, d_tw, tw_log_n, 0, 0, &sc);
+  return run_layers(stream, d_work, d_evals, log_block, log_inv_rate, h, dft_n_cols, skip, d_tw, tw_log_n, col_begin / 8,
+                    (col_count + 7) / 8, &sc);
 }
 
 cudaError_t ntt_dft_batch_by_evals(cudaStream_t stream, uint32_t* d_mat, uint64_t h, uint64_t w, int skip_layers,

@@ -24,9 +24,10 @@ cudaError_t ntt_reorder_and_dft_cols(cudaStream_t stream, const uint32_t* d_eval
 // local transform of one rank of the row-sharded commit with the all-to-all fused into the stores of its last pass
 cudaError_t ntt_reorder_and_dft_scatter(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_vars, uint32_t folding_factor,
                                         uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_work, uint32_t* const* peers,
-                                        uint32_t world, uint32_t rank, const uint32_t* d_tw, unsigned tw_log_n);
+                                        uint32_t world, uint32_t rank, const uint32_t* d_tw, unsigned tw_log_n,
+                                        uint32_t col_begin = 0, uint32_t col_count = 0);  // column range (0, 0 = all)
 // layers [l_first, log_h) on the rows a rank holds after the exchange of the row-sharded commit
 cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, unsigned log_h, unsigned l_first,
                               uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, const uint32_t* d_tw,
-                              unsigned tw_log_n);
+                              unsigned tw_log_n, uint64_t col_begin = 0, uint64_t col_count = 0);  // column range (0, 0 = all)
 }  // namespace lm

@@ -126,6 +126,22 @@ class ShardedCommit:
         #    concatenation of level l of every subtree); the levels above log2(run) are not used
         self.forest = b.merkle_tree(mat, self.full_cols, w)          # (2 block - 1) x 8, level-major
         mark("subtrees")
+        return self._finish(mark)
+
+    def commit_host(self, host_shard):
+        """commit() for a shard in (pinned) HOST memory.  Backends that can (CudaBackend with the fused exchange) pipeline
+        it over column groups taken right to left, as lm_commit does on one GPU: while group k is transformed, exchanged
+        and absorbed by the leaf sponge, the copy of group k+1 crosses PCIe.  Otherwise: upload, then commit()."""
+        pipelined = getattr(self.b, "commit_host_pipelined", None) if self.world > 1 else None
+        if pipelined is not None:
+            out = pipelined(self, host_shard)
+            if out is not None:
+                self.codeword, self.forest = out
+                return self._finish(lambda name: None)
+        return self.commit(self.b.to_device(host_shard) if isinstance(host_shard, np.ndarray) else host_shard.cuda(non_blocking=True))
+
+    def _finish(self, mark):
+        geo, b = self.geo, self.b
         off = 2 * geo.block - ((2 * geo.block) >> geo.log_run)
         my_roots = b.rows(self.forest, off, self.world)              # world x 8: level log2(run) = the subtree roots
         all_roots = b.all_gather_roots(self.dist, my_roots)          # [rank][m] -> world x world x 8
@@ -538,6 +554,52 @@ class CudaBackend:
         # every rank's stores must have landed before anyone reads its matrix: NCCL barrier, ordered on the stream
         dist.all_reduce(self._flag())
         return mat
+
+    def commit_host_pipelined(self, sc, host_shard):
+        """-> (codeword matrix, forest) or None when the shape is not eligible.  host_shard: pinned torch int32 tensor, the
+        shard polynomial (live columns x positions)."""
+        import ctypes as C
+
+        torch, lib, geo, dist = self.torch, self.lib, sc.geo, sc.dist
+        w, full = sc.cols, sc.full_cols
+        n_chunks = w // 8
+        if self.scatter_dft is None or w % 8 or n_chunks < 2 or (full - w) // 8 < 2 or not torch.is_tensor(host_shard):
+            return None
+        if not self.scatter_ready(dist, geo.block, w):
+            return None
+        mat, work, _, table = self._scatter_buffers(dist, geo.block, w)
+        sub = host_shard.numel() // w                       # positions per column in the shard
+        d_evals = torch.empty(host_shard.numel(), dtype=torch.int32, device="cuda")
+        forest = torch.empty((2 * geo.block - 1, 8), dtype=torch.int32, device="cuda")
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+        self._copy_stream.wait_stream(self.stream)
+        n_vars, world, rank = geo.n_vars - geo.g, dist.get_world_size(), dist.get_rank()
+        tptr = table.ctypes.data_as(C.POINTER(C.c_uint64))
+        chunk_end, take, first = n_chunks, 1, True
+        while chunk_end > 0:                                # column groups of 1, 1, 2, 4, .. rate chunks, right to left
+            take = min(take, chunk_end)
+            col_begin, count = (chunk_end - take) * 8, take * 8
+            with torch.cuda.stream(self._copy_stream):
+                d_evals[col_begin * sub:(col_begin + count) * sub].copy_(host_shard[col_begin * sub:(col_begin + count) * sub],
+                                                                         non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self.stream.wait_event(ev)
+            self.check(lib.lm_dev_reorder_and_dft_scatter_cols(self.ctx.handle, d_evals.data_ptr(), n_vars, geo.folding,
+                                                               geo.log_inv_rate, w, work.data_ptr(), tptr, world, rank, col_begin, count))
+            dist.all_reduce(self._flag())                   # every rank's stores of this group have landed
+            self.check(lib.lm_dev_dft_layers_mapped_cols(self.ctx.handle, mat.data_ptr(), w, geo.log_h, geo.log_h - geo.g, world,
+                                                         geo.run, geo.block, rank * geo.run, col_begin, count))
+            self.check(lib.lm_dev_merkle_absorb(self.ctx.handle, mat.data_ptr(), geo.block, w, full, w, chunk_end - 1, take,
+                                                forest.data_ptr()))
+            chunk_end -= take
+            if not first:
+                take *= 2
+            first = False
+        self.check(lib.lm_dev_merkle_levels(self.ctx.handle, forest.data_ptr(), geo.block))
+        d_evals.record_stream(self._copy_stream)
+        return mat, forest
 
     def _flag(self):
         if not hasattr(self, "_flag_t"):

@@ -104,6 +104,21 @@ def main():
         er, ep = O.merkle_open(cw_ref, cols, layers_ref, row)
         assert np.array_equal(data, er) and np.array_equal(path, ep), f"rank {rank}: opening {row} differs"
         assert O.merkle_verify(root_ref, log_h, row, data, path)
+    # the host-input path (pipelined over column groups on the CUDA backend, plain upload + commit otherwise)
+    if mode == "gpu":
+        host = torch.from_numpy(np.ascontiguousarray(shard).view(np.int32)).pin_memory()
+        root2 = sc.commit_host(host)
+    else:
+        root2 = sc.commit_host(np.ascontiguousarray(shard))
+    assert np.array_equal(np.asarray(root2).view(np.uint32).reshape(-1), root_ref), f"rank {rank}: root of the host-input path differs"
+    local2 = backend.to_host(sc.codeword)
+    for m in range(world):
+        g0 = m * geo.block + rank * geo.run
+        assert np.array_equal(local2[m * geo.run:(m + 1) * geo.run], cw_ref[g0:g0 + geo.run]), f"rank {rank}: run {m} differs (host path)"
+    row = rank * geo.run + 1
+    data, path = sc.open_local(row)
+    er, ep = O.merkle_open(cw_ref, cols, layers_ref, row)
+    assert np.array_equal(data, er) and np.array_equal(path, ep), f"rank {rank}: opening {row} differs (host path)"
     dist.barrier()
     if rank == 0:
         print("SHARDED_OK", world, mode)
