@@ -231,3 +231,49 @@ def test_reorder_and_dft_scatter_single_device(ctx, rng, n_vars, k, r, cols, G):
         assert np.array_equal(mats[q].download((block, cols)), expected[q]), f"matrix {q}"
     for m in mats + [work]:
         m.free()
+
+
+@pytest.mark.parametrize("G,cols", [(2, 64), (4, 32), (8, 64)])
+def test_sharded_pipeline_pieces_by_column_groups(ctx, rng, G, cols):
+    """The column-range forms used by the pipelined host-input sharded commit, on one device: transform + scatter, last
+    layers and leaf absorb applied group by group (1, 1, 2, 4 .. chunks, right to left) give the same matrices and leaf
+    digests as the whole-width calls / the oracle."""
+    import ctypes as C
+
+    from leanmultisig_b200._lib import check, lib
+    from leanmultisig_b200.sharded import shard_of
+
+    n_vars, k, r = 17, 7, 1
+    g = G.bit_length() - 1
+    chunk = 1 << (n_vars - k)
+    ev = np.zeros(1 << n_vars, dtype=np.uint32)
+    ev[: cols * chunk] = O.random_field(rng, cols * chunk)
+    log_h = n_vars + r - k
+    block, run = (1 << log_h) // G, (1 << log_h) // (G * G)
+    mats = [ctx.alloc(block * cols * 4) for _ in range(G)]
+    work = ctx.alloc(block * cols * 4)
+    table = np.array([int(m.ptr.value) for m in mats], dtype=np.uint64)
+    tptr = table.ctypes.data_as(C.POINTER(C.c_uint64))
+    groups, chunk_end, take, first = [], cols // 8, 1, True
+    while chunk_end > 0:
+        take = min(take, chunk_end)
+        groups.append((chunk_end, take))
+        chunk_end -= take
+        take, first = (take if first else take * 2), False
+    shards = [ctx.to_device(shard_of(ev, n_vars, k, q, G).reshape(1 << k, -1)[:cols].reshape(-1)) for q in range(G)]
+    digests = [ctx.alloc(block * 8 * 4) for _ in range(G)]
+    for chunk_end, take in groups:
+        cb, cnt = (chunk_end - take) * 8, take * 8
+        for q in range(G):   # every "rank" scatters this group, then every rank finishes it
+            check(lib().lm_dev_reorder_and_dft_scatter_cols(ctx.handle, shards[q].ptr, n_vars - g, k, r, cols, work.ptr, tptr, G, q, cb, cnt))
+        for q in range(G):
+            check(lib().lm_dev_dft_layers_mapped_cols(ctx.handle, mats[q].ptr, cols, log_h, log_h - g, G, run, block, q * run, cb, cnt))
+            check(lib().lm_dev_merkle_absorb(ctx.handle, mats[q].ptr, block, cols, 128, cols, chunk_end - 1, take, digests[q].ptr))
+    ctx.sync()
+    cw = O.reorder_and_dft(ev, n_vars, 1, k, r, cols)
+    for q in range(G):
+        exp = np.concatenate([cw[m * block + q * run: m * block + (q + 1) * run] for m in range(G)])
+        assert np.array_equal(mats[q].download((block, cols)), exp), f"matrix {q}"
+        assert np.array_equal(digests[q].download((block, 8)), O.first_digest_layer(exp, 128, cols)), f"digests {q}"
+    for b in mats + digests + shards + [work]:
+        b.free()
