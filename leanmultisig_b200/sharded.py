@@ -82,7 +82,11 @@ class ShardGeometry:
 
 
 class ShardedCommit:
-    """Collective: every rank calls commit() with its shard; all ranks return the same root."""
+    """Collective: every rank calls commit() with its shard; all ranks return the same root.
+
+    With the CUDA backend's fused exchange the codeword matrix of a rank is a buffer the OTHER ranks store into during a
+    commit (one buffer per shape, reused by the next commit of that shape): ranks that read their codeword or serve openings
+    after commit() must synchronise (dist.barrier()) before any rank starts the next commit of the same shape."""
 
     def __init__(self, backend, dist, n_vars: int, folding: int, log_inv_rate: int, live_cols: int | None = None):
         self.b, self.dist = backend, dist

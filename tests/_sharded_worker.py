@@ -104,7 +104,10 @@ def main():
         er, ep = O.merkle_open(cw_ref, cols, layers_ref, row)
         assert np.array_equal(data, er) and np.array_equal(path, ep), f"rank {rank}: opening {row} differs"
         assert O.merkle_verify(root_ref, log_h, row, data, path)
-    # the host-input path (pipelined over column groups on the CUDA backend, plain upload + commit otherwise)
+    # the host-input path (pipelined over column groups on the CUDA backend, plain upload + commit otherwise).  The
+    # codeword matrix of the CUDA backend is written by the OTHER ranks during a commit: every rank must be done reading
+    # the previous codeword before anyone starts the next commit.
+    dist.barrier()
     if mode == "gpu":
         host = torch.from_numpy(np.ascontiguousarray(shard).view(np.int32)).pin_memory()
         root2 = sc.commit_host(host)
