@@ -218,7 +218,9 @@ int lm_gkr_new_shard(lm_ctx* ctx, const uint32_t* nums, const uint32_t* dens, ui
 int lm_gkr_layer_begin_shard(lm_gkr* gkr, uint32_t claim_vars, const uint32_t* claim_point, const uint32_t alpha[5],
                              const uint32_t eq_scale[5]);
 int lm_gkr_num_vars(const lm_gkr* gkr, uint32_t* n_vars);
-/* the 2^5 numerators and denominators of the top layer, 32 x 5 words each (mod.rs:64-66) */
+/* log2 of the number of fractions the up pass stops at: 5 (N_VARS_TO_SEND_GKR_COEFFS), 5 - log2(G) for a shard session */
+int lm_gkr_top_vars(const lm_gkr* gkr, uint32_t* top_vars);
+/* the 2^top_vars numerators and denominators of the top layer, 5 words each: 32 x 5 for a whole table (mod.rs:64-66) */
 int lm_gkr_top(lm_gkr* gkr, uint32_t* top_nums, uint32_t* top_dens);
 int lm_gkr_layer_begin(lm_gkr* gkr, uint32_t claim_vars, const uint32_t* claim_point, const uint32_t alpha[5]);
 int lm_gkr_round(lm_gkr* gkr, uint32_t c0[5], uint32_t c2[5]);

@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
             "lm_gkr_new_shard": [vp, u32p, u32p, u64, u32, u32, C.POINTER(vp)],
             "lm_gkr_layer_begin_shard": [vp, u32, u32p, u32p, u32p],
             "lm_gkr_num_vars": [vp, u32p],
+            "lm_gkr_top_vars": [vp, u32p],
             "lm_gkr_top": [vp, u32p, u32p],
             "lm_gkr_layer_begin": [vp, u32, u32p, u32p],
             "lm_gkr_round": [vp, u32p, u32p],

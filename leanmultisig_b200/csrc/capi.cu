@@ -1601,6 +1601,12 @@ int lm_gkr_num_vars(const lm_gkr* g, uint32_t* n_vars) {
   return LM_OK;
 }
 
+int lm_gkr_top_vars(const lm_gkr* g, uint32_t* top_vars) {
+  if (!g || !top_vars) return fail(LM_ERR_INVALID, "lm_gkr_top_vars: null argument");
+  *top_vars = g->top_vars;
+  return LM_OK;
+}
+
 int lm_gkr_top(lm_gkr* g, uint32_t* top_nums, uint32_t* top_dens) {
   if (!g || !top_nums || !top_dens) return fail(LM_ERR_INVALID, "lm_gkr_top: null argument");
   lm_ctx* c = g->ctx;

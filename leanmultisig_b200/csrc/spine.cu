@@ -274,6 +274,9 @@ int lm_gkr_prove(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out
   uint32_t n_vars = 0;
   if (int rc = lm_gkr_num_vars(gkr, &n_vars)) return rc;
   const uint32_t TOP = 5;  // N_VARS_TO_SEND_GKR_COEFFS
+  uint32_t top_vars = 0;
+  if (int rc = lm_gkr_top_vars(gkr, &top_vars)) return rc;
+  if (top_vars != TOP) return lm_internal_fail(LM_ERR_INVALID, "lm_gkr_prove: shard sessions are driven by the caller (sharded.py)");
   std::vector<uint32_t> tn(32 * 5), td(32 * 5);
   if (int rc = lm_gkr_top(gkr, tn.data(), td.data())) return rc;
   fs->add_scalars(tn.data(), tn.size());
