@@ -132,6 +132,29 @@ struct KbDot {
   LM_HD uint32_t finish() const { return kb_canon(finish_lazy()); }
 };
 
+// 96-bit accumulator for long dot products (the Poseidon1 partial section: 16-20 terms): no intermediate folds, one
+// IMAD.WIDE per term plus a three-word carry chain; finish folds the three words with 2^32 and 2^64 mod p.
+struct KbAcc96 {
+  uint32_t lo, hi, top;
+  LM_HD explicit KbAcc96(uint64_t init = 0) : lo((uint32_t)init), hi((uint32_t)(init >> 32)), top(0) {}
+  LM_HD void mac(uint32_t a, uint32_t c) {
+    const uint64_t p = mul_wide(a, c);
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(lo), "+r"(hi), "+r"(top)
+        : "r"((uint32_t)p), "r"((uint32_t)(p >> 32)));
+#else
+    const uint64_t cur = ((uint64_t)hi << 32) | lo, sum = cur + p;
+    top += sum < cur;
+    lo = (uint32_t)sum, hi = (uint32_t)(sum >> 32);
+#endif
+  }
+  // (top 2^64 + hi 2^32 + lo) * 2^-32 mod p in [0, p + 2^26), provided top < 2^6
+  LM_HD uint32_t finish_lazy() const {
+    return kb_redc_lazy(mad_wide(top, KB_R2, mad_wide(hi, KB_R1, (uint64_t)lo)));
+  }
+};
+
 // ---- quintic extension EF = F[X]/(X^5 + X^2 - 1), AoS [c0..c4] -------------------------------------------
 struct Ef {
   uint32_t c[5];

@@ -126,7 +126,17 @@ LM_HD void p1_mds_redc(const uint32_t a3[16], const uint32_t* init, const double
 }
 
 // dot(x[0..16), row) on top of `init`
+#ifdef LM_P1_ACC96
+LM_HD KbAcc96 p1_dot16(const uint32_t x[16], const uint32_t* row, uint64_t init) {
+  KbAcc96 d(init);
+#pragma unroll
+  for (int j = 0; j < 16; j++) d.mac(x[j], row[j]);
+  return d;
+}
+LM_HD KbDot p1_dot16_folded(const uint32_t x[16], const uint32_t* row, uint64_t init) {
+#else
 LM_HD KbDot p1_dot16(const uint32_t x[16], const uint32_t* row, uint64_t init) {
+#endif
   KbDot d(init);
   d.mac<0>(x[0], row[0]);
   d.mac<1>(x[1], row[1]);
@@ -201,6 +211,13 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
   for (int r = 0; r < 20; r++) {
     z[r] = kb_canon(p1_sbox_lazy(s0));
     // s0_{r+1} = D_r + FR0[r] z_r + sum_{k<r} GTRI[r][k] z_k ;  D_r enters as D_r * 2^32 == D_r * R
+#ifdef LM_P1_ACC96
+    KbAcc96 acc(mul_wide(d[r], KB_R1));
+    acc.mac(z[r], T.FR0[r]);
+#pragma unroll
+    for (int k = 0; k < r; k++) acc.mac(z[k], T.GTRI[r][k]);
+    s0 = acc.finish_lazy();
+#else
     uint64_t acc = mul_wide(d[r], KB_R1);
     acc = mad_wide(z[r], T.FR0[r], acc);
     int terms = 1;  // products on top of the (small) D_r term
@@ -211,12 +228,19 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
       terms++;
     }
     s0 = kb_redc_lazy(kb_fold(acc));
+#endif
     if (r % 4 == 3) LM_P1_BARRIER();
   }
 
   a[0] = s0;
 #pragma unroll
   for (int i = 0; i < 15; i++) {
+#ifdef LM_P1_ACC96
+    KbAcc96 acc(mul_wide(lane_lin[i], KB_R1));
+#pragma unroll
+    for (int k = 0; k < 20; k++) acc.mac(z[k], T.V[i][k]);
+    a[i + 1] = acc.finish_lazy();
+#else
     uint64_t acc = mul_wide(lane_lin[i], KB_R1);
     int terms = 0;  // canonical z (< p) times constants (< p): four products per fold
 #pragma unroll
@@ -226,6 +250,7 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
       terms++;
     }
     a[i + 1] = kb_redc_lazy(kb_fold(acc));
+#endif
     if (i % 5 == 4) LM_P1_BARRIER();
   }
 
