@@ -19,6 +19,7 @@
 //
 // Inputs/outputs are canonical Montgomery-form residues in [0, p).
 #pragma once
+#include <utility>
 #include "kb.cuh"
 
 namespace lm {
@@ -157,6 +158,94 @@ LM_HD KbDot p1_dot16(const uint32_t x[16], const uint32_t* row, uint64_t init) {
   return d;
 }
 
+// ---- partial section with the matrix entries as IMMEDIATE operands (device) ------------------------------------------
+// Read from constant memory, the ~1.1 k matrix entries of the partial section cost ~390 LDCU (mostly 128-bit) and ~500
+// UMOV per permutation on top of the IMAD.WIDE that consume them — 12 % of the issue slots of a kernel that is limited
+// by issue slots and the multiplier pipe jointly.  As compile-time constants (template indices into a constexpr copy of
+// the generated tables) they become the 32-bit immediate of the IMAD.WIDE itself.  -DLM_P1_NO_IMMEDIATES restores the
+// constant-memory form.
+LM_HD constexpr P1Tables p1_tables_constexpr() {
+  return P1Tables
+#include "poseidon1_tables.inc"
+      ;
+}
+#if defined(__CUDA_ARCH__) && !defined(LM_P1_NO_IMMEDIATES)
+#define LM_P1_IMM 1
+template <int N>
+using p1_seq = std::make_integer_sequence<int, N>;
+
+// WHICH = 0: row R of G on top of G_CONST[R] (row 0: on top of 0); WHICH = 1: row R of MI on top of LANE_CONST[R]
+template <int WHICH, int R, int... J>
+__device__ __forceinline__ uint32_t p1_dot16_imm(const uint32_t x[16], std::integer_sequence<int, J...>) {
+  constexpr P1Tables t = p1_tables_constexpr();
+  constexpr uint32_t init = WHICH == 1 ? t.LANE_CONST[WHICH == 1 ? R : 0] : (R == 0 ? 0u : t.G_CONST[WHICH == 0 ? R : 0]);
+  KbDot d(init);
+  (([&] {
+     constexpr uint32_t c = WHICH == 1 ? t.MI[WHICH == 1 ? R : 0][J] : t.G[WHICH == 0 ? R : 0][J];
+     d.template mac<J>(x[J], c);
+   }()),
+   ...);
+  return d.finish_lazy();
+}
+template <int... R>
+__device__ __forceinline__ void p1_all_d_imm(const uint32_t x[16], uint32_t d[20], std::integer_sequence<int, R...>) {
+  ((d[R] = p1_dot16_imm<0, R + 1>(x, p1_seq<16>{})), ...);
+}
+template <int... I>
+__device__ __forceinline__ void p1_all_lane_lin_imm(const uint32_t x[16], uint32_t lane_lin[15], std::integer_sequence<int, I...>) {
+  ((lane_lin[I] = p1_dot16_imm<1, I>(x, p1_seq<16>{})), ...);
+}
+// s0_{R+1} = D_R + FR0[R] z_R + sum_{K<R} GTRI[R][K] z_K
+template <int R, int... K>
+__device__ __forceinline__ uint32_t p1_tri_imm(uint32_t d_r, const uint32_t z[20], std::integer_sequence<int, K...>) {
+  constexpr P1Tables t = p1_tables_constexpr();
+  uint64_t acc = mul_wide(d_r, KB_R1);
+  {
+    constexpr uint32_t c = t.FR0[R];
+    acc = mad_wide(z[R], c, acc);
+  }
+  (([&] {
+     if ((1 + K) % 4 == 0) acc = kb_fold(acc);
+     constexpr uint32_t c = t.GTRI[R][K];
+     acc = mad_wide(z[K], c, acc);
+   }()),
+   ...);
+  return kb_redc_lazy(kb_fold(acc));
+}
+template <bool SYNC, int... R>
+__device__ __forceinline__ void p1_partial_rounds_imm(uint32_t& s0, const uint32_t d[20], uint32_t z[20],
+                                                      std::integer_sequence<int, R...>) {
+  (([&] {
+     z[R] = kb_canon(p1_sbox_lazy(s0));
+     s0 = p1_tri_imm<R>(d[R], z, p1_seq<R>{});
+     if (SYNC && R % 4 == 3) __syncthreads();
+   }()),
+   ...);
+}
+// lane I + 1 leaving the section: lane_lin[I] + sum_K V[I][K] z_K
+template <int I, int... K>
+__device__ __forceinline__ uint32_t p1_lane_imm(uint32_t lin, const uint32_t z[20], std::integer_sequence<int, K...>) {
+  constexpr P1Tables t = p1_tables_constexpr();
+  uint64_t acc = mul_wide(lin, KB_R1);
+  (([&] {
+     if (K > 0 && K % 4 == 0) acc = kb_fold(acc);
+     constexpr uint32_t c = t.V[I][K];
+     acc = mad_wide(z[K], c, acc);
+   }()),
+   ...);
+  return kb_redc_lazy(kb_fold(acc));
+}
+template <bool SYNC, int... I>
+__device__ __forceinline__ void p1_all_lanes_imm(const uint32_t lane_lin[15], const uint32_t z[20], uint32_t a[16],
+                                                 std::integer_sequence<int, I...>) {
+  (([&] {
+     a[I + 1] = p1_lane_imm<I>(lane_lin[I], z, p1_seq<20>{});
+     if (SYNC && I % 5 == 4) __syncthreads();
+   }()),
+   ...);
+}
+#endif
+
 // Permutation; N_OUT = 16 for the full permutation, 8 when only the digest half is needed.
 // s: canonical in, canonical out (lanes >= N_OUT are left unspecified).
 // SYNC: the device code places a CTA-wide barrier after every full round and a few times inside the partial
@@ -194,6 +283,19 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
   // x = x' (state entering the partial section, first_rc already added), held at R^-39, lanes < p + 2^9
 
   // ---- partial section
+#ifdef LM_P1_IMM
+  {
+    uint32_t d[20], lane_lin[15], z[20];
+    p1_all_d_imm(x, d, p1_seq<20>{});
+    uint32_t s0 = p1_dot16_imm<0, 0>(x, p1_seq<16>{});
+    LM_P1_BARRIER();
+    p1_all_lane_lin_imm(x, lane_lin, p1_seq<15>{});
+    LM_P1_BARRIER();
+    p1_partial_rounds_imm<SYNC>(s0, d, z, p1_seq<20>{});
+    a[0] = s0;
+    p1_all_lanes_imm<SYNC>(lane_lin, z, a, p1_seq<15>{});
+  }
+#else
   uint32_t d[20];  // D_r, canonical-ish (< p + 2^25), held at R^1
 #pragma unroll
   for (int r = 0; r < 20; r++) d[r] = p1_dot16(x, T.G[r + 1], T.G_CONST[r + 1]).finish_lazy();
@@ -253,6 +355,8 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
 #endif
     if (i % 5 == 4) LM_P1_BARRIER();
   }
+
+#endif
 
   // ---- 4 terminal full rounds (first round constant already inside a[]); three looped, the last one only
   // produces the lanes that are kept
