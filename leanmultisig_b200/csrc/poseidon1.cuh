@@ -179,12 +179,21 @@ template <int WHICH, int R, int... J>
 __device__ __forceinline__ uint32_t p1_dot16_imm(const uint32_t x[16], std::integer_sequence<int, J...>) {
   constexpr P1Tables t = p1_tables_constexpr();
   constexpr uint32_t init = WHICH == 1 ? t.LANE_CONST[WHICH == 1 ? R : 0] : (R == 0 ? 0u : t.G_CONST[WHICH == 0 ? R : 0]);
+#ifdef LM_P1_ACC96
+  KbAcc96 d(init);
+  (([&] {
+     constexpr uint32_t c = WHICH == 1 ? t.MI[WHICH == 1 ? R : 0][J] : t.G[WHICH == 0 ? R : 0][J];
+     d.mac(x[J], c);
+   }()),
+   ...);
+#else
   KbDot d(init);
   (([&] {
      constexpr uint32_t c = WHICH == 1 ? t.MI[WHICH == 1 ? R : 0][J] : t.G[WHICH == 0 ? R : 0][J];
      d.template mac<J>(x[J], c);
    }()),
    ...);
+#endif
   return d.finish_lazy();
 }
 template <int... R>
@@ -199,6 +208,19 @@ __device__ __forceinline__ void p1_all_lane_lin_imm(const uint32_t x[16], uint32
 template <int R, int... K>
 __device__ __forceinline__ uint32_t p1_tri_imm(uint32_t d_r, const uint32_t z[20], std::integer_sequence<int, K...>) {
   constexpr P1Tables t = p1_tables_constexpr();
+#ifdef LM_P1_ACC96
+  KbAcc96 acc(mul_wide(d_r, KB_R1));
+  {
+    constexpr uint32_t c = t.FR0[R];
+    acc.mac(z[R], c);
+  }
+  (([&] {
+     constexpr uint32_t c = t.GTRI[R][K];
+     acc.mac(z[K], c);
+   }()),
+   ...);
+  return acc.finish_lazy();
+#else
   uint64_t acc = mul_wide(d_r, KB_R1);
   {
     constexpr uint32_t c = t.FR0[R];
@@ -211,6 +233,7 @@ __device__ __forceinline__ uint32_t p1_tri_imm(uint32_t d_r, const uint32_t z[20
    }()),
    ...);
   return kb_redc_lazy(kb_fold(acc));
+#endif
 }
 template <bool SYNC, int... R>
 __device__ __forceinline__ void p1_partial_rounds_imm(uint32_t& s0, const uint32_t d[20], uint32_t z[20],
@@ -226,6 +249,15 @@ __device__ __forceinline__ void p1_partial_rounds_imm(uint32_t& s0, const uint32
 template <int I, int... K>
 __device__ __forceinline__ uint32_t p1_lane_imm(uint32_t lin, const uint32_t z[20], std::integer_sequence<int, K...>) {
   constexpr P1Tables t = p1_tables_constexpr();
+#ifdef LM_P1_ACC96
+  KbAcc96 acc(mul_wide(lin, KB_R1));
+  (([&] {
+     constexpr uint32_t c = t.V[I][K];
+     acc.mac(z[K], c);
+   }()),
+   ...);
+  return acc.finish_lazy();
+#else
   uint64_t acc = mul_wide(lin, KB_R1);
   (([&] {
      if (K > 0 && K % 4 == 0) acc = kb_fold(acc);
@@ -234,6 +266,7 @@ __device__ __forceinline__ uint32_t p1_lane_imm(uint32_t lin, const uint32_t z[2
    }()),
    ...);
   return kb_redc_lazy(kb_fold(acc));
+#endif
 }
 template <bool SYNC, int... I>
 __device__ __forceinline__ void p1_all_lanes_imm(const uint32_t lane_lin[15], const uint32_t z[20], uint32_t a[16],
