@@ -500,12 +500,12 @@ class WhirProver:
             stir_evals = F.np_mle_eval_rows(leaves, randomness[len(randomness) - ff:])
             # in-domain points gen^i expanded to (x, x^2, x^4, ...), base field
             g = gen * F._RINV % F.P
+            p64, r64 = np.uint64(F.P), np.uint64(F._R)
+            y = np.array([pow(g, i, F.P) for i in idx], dtype=np.uint64)      # canonical, < 2^31: products fit in u64
             stir_pts = np.empty((len(idx), num_variables), dtype=np.uint32)
-            for q, i in enumerate(idx):
-                y = pow(g, i, F.P)
-                for k in range(num_variables):
-                    stir_pts[q, k] = y * F._R % F.P
-                    y = y * y % F.P
+            for k in range(num_variables):
+                stir_pts[:, k] = (y * r64) % p64
+                y = (y * y) % p64
             ps.duplex()
             comb = F.from_monty(ps.sample())
             powers = [F.ONE]
