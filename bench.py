@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self) -> dict:
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
