@@ -290,6 +290,11 @@ def run_b200(args):
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": leaf_bytes,
                          "note": "kernel is bound by the IMAD.WIDE/DFMA dispatch (fmaheavy 79 %, issue slots 54 %), ~6.7k SASS instr per compression, see DESIGN.md",
                          "gperm_per_s": n_perm_leaf / (t_leaf * 1e-3) / 1e9},
+            # the bound that actually limits the dominant kernel (not measured live: from the committed ncu capture of this
+            # command, same kernel build) - SURVEY 8d asks for a second roofline against the integer pipe
+            "roofline_alu": {"bound": "fmaheavy pipe (IMAD.WIDE / IMAD / DFMA dispatch)", "kernel": "leaf_sponge_kernel",
+                             "frac": 0.786, "issue_slot_frac": 0.538, "unit": "pipe-active fraction",
+                             "source": "ncu sm__pipe_fmaheavy_cycles_active / smsp__issue_active, profiles/r01_ncu_commit_kernels_v5.txt"},
             "roofline_commit": {"bound": "hbm", "achieved": (live * 4 + rows * 64 * 4 + (2 * rows - 1) * 32) / (t_step * 1e-3) / 1e9,
                                 "peak": peak, "unit": "GB/s"},
             "roofline_ntt": {"bound": "hbm", "achieved": (live * 4 + rows * 64 * 4) / (t_ntt * 1e-3) / 1e9, "peak": peak,
