@@ -386,6 +386,8 @@ class ShardedProductSumcheck:
         return self.n_vars_total - self.folds
 
     def add_eq(self, selector: int, point, scalar) -> None:
+        if self.rep is not None:          # replicated tables (the STIR / OOD updates of the later WHIR rounds)
+            return self.rep.add_eq(selector, point, scalar)
         assert self.folds == 0, "statements are added before the first fold"
         pt = [F.from_monty(x) for x in np.ascontiguousarray(point, dtype=np.uint32).reshape(-1, 5)]
         loc = localize_statement(self.n_vars_total, self.folding, self.g, self.rank, selector, pt)
@@ -443,6 +445,95 @@ class ShardedProductSumcheck:
             if s is not None:
                 s.free()
         self.local = self.rep = None
+
+
+# ======================================================================================================
+# WhirConfig::commit / prove over the row-sharded initial commitment
+# ======================================================================================================
+class ShardedTree:
+    """The `Tree` surface WhirProver.prove uses (root, open, elem_dim) on a ShardedCommit: openings are served by the rank
+    that owns the codeword row and exchanged, so that every rank holds every hint (the transcript is replicated)."""
+
+    elem_dim = 1
+
+    def __init__(self, commit: ShardedCommit):
+        self.sc, self.dist = commit, commit.dist
+        self.root, self.height, self.log_height = commit.root, commit.geo.h, commit.geo.log_h
+
+    def open(self, indices):
+        idx = [int(i) for i in indices]
+        mine = {q: self.sc.open_local(i) for q, i in enumerate(idx) if self.sc.geo.owner(i) == self.sc.rank}
+        everyone = [None] * self.sc.world
+        self.dist.all_gather_object(everyone, mine)
+        merged = {}
+        for part in everyone:
+            merged.update(part)
+        rows = np.stack([merged[q][0] for q in range(len(idx))]) if idx else np.zeros((0, self.sc.full_cols), dtype=np.uint32)
+        paths = np.stack([merged[q][1] for q in range(len(idx))]) if idx else np.zeros((0, self.log_height, 8), dtype=np.uint32)
+        return rows, paths
+
+    def free(self):
+        pass
+
+
+class ShardedWhirProver:
+    """`WhirConfig::commit` / `WhirConfig::prove` (crates/whir/src/commit.rs:64-99, open.rs:37-248) for a stacked polynomial
+    that is row-sharded over the ranks.  Round 0 — the commit (ShardedCommit), the out-of-domain evaluations (one all-reduce
+    of 5 words each), the first `first_folding` sumcheck rounds (ShardedProductSumcheck) and the STIR openings of the first
+    tree (owner-routed) — runs on the shards; from the first fold on the tables are 2^first_folding times smaller and every
+    rank continues on the ordinary single-device sessions (the first commit is >= 8x all later ones).  The host
+    logic is WhirProver.prove itself; every rank runs it with its own (identical) transcript.  Statements with next-row
+    weights (`is_next`) are not supported on shards."""
+
+    def __init__(self, backend, dist, cfg):
+        from .whir import WhirProver
+
+        self.b, self.dist, self.cfg = backend, dist, cfg
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.g = self.world.bit_length() - 1
+        outer = self
+
+        class _Prover(WhirProver):
+            def _session(self, witness):
+                return ShardedProductSumcheck(outer.b, outer.dist, witness.shard, cfg.num_variables, cfg.first_folding,
+                                              witness.live_len)
+
+        self._prover = _Prover(getattr(backend, "ctx", None), cfg)
+
+    def evaluate(self, shard_padded, point_m) -> np.ndarray:
+        """value of the whole polynomial at `point_m` (n x 5 Montgomery words) from the shards: the g coordinates that
+        select the rank become an eq factor, the local evaluations are added up with one all-reduce"""
+        cfg, g = self.cfg, self.g
+        k = cfg.first_folding
+        pt = np.ascontiguousarray(point_m, dtype=np.uint32).reshape(-1, 5)
+        local_pt = np.concatenate([pt[:k], pt[k + g:]])
+        scale = prefix_eq([F.from_monty(x) for x in pt[k:k + g]], g, self.rank)
+        local = F.mul(F.from_monty(self.b.mle_eval(shard_padded, local_pt)), scale)
+        if self.world == 1:
+            return F.to_monty(local)
+        return self.b.all_reduce_field(self.dist, F.to_monty(local))
+
+    def commit(self, prover_state, shard, live_cols: int | None = None):
+        """shard: this rank's part of the polynomial (shard_of layout restricted to the live columns), host numpy"""
+        from .whir import Witness, _sample_ood
+
+        cfg = self.cfg
+        nv = cfg.num_variables
+        cols = (1 << cfg.first_folding) if live_cols is None else live_cols
+        shard = np.ascontiguousarray(shard, dtype=np.uint32)
+        sc = ShardedCommit(self.b, self.dist, nv, cfg.first_folding, cfg.starting_log_inv_rate, live_cols=cols)
+        root = np.asarray(sc.commit(self.b.to_device(shard))).view(np.uint32).reshape(-1)
+        prover_state.add_base_scalars(root)
+        padded = np.zeros(1 << (nv - self.g), dtype=np.uint32)
+        padded[: shard.size] = shard
+        pts, answers = _sample_ood(prover_state, cfg.commitment_ood_samples, nv, lambda pt: self.evaluate(padded, pt))
+        w = Witness(ShardedTree(sc), pts, answers)
+        w.shard, w.live_len = shard, shard.size
+        return w
+
+    def prove(self, prover_state, statements, witness):
+        assert not any(s.is_next for s in statements), "next-row statements are not supported on shards"
+        return self._prover.prove(prover_state, statements, witness)
 
 
 class CudaBackend:
@@ -704,3 +795,6 @@ class CudaBackend:
         tables = everyone.permute(1, 0, 2).contiguous()          # [poly | weights][rank][local index]
         self.torch.cuda.synchronize()
         return self.ctx.sumcheck_from_dev(tables[0].data_ptr(), tables[1].data_ptr(), n_vars_total)
+
+    def mle_eval(self, evals, point_m) -> np.ndarray:
+        return self.ctx.mle_eval(evals, point_m)

@@ -395,6 +395,10 @@ class WhirProver:
         pts, answers = _sample_ood(prover_state, cfg.commitment_ood_samples, cfg.num_variables, tree.evaluate)
         return Witness(tree, pts, answers)
 
+    def _session(self, witness: Witness):
+        """the product-sumcheck session over the committed polynomial (the sharded prover overrides this)"""
+        return self.ctx.sumcheck_from_tree(witness.tree)
+
     # -- sumcheck_prove_many_rounds with the product-sumcheck kernels (sumcheck/src/prove.rs:86-151) ------
     @staticmethod
     def _rounds(sc: ProductSumcheck, prover_state, n_rounds: int, pow_bits: int, total):
@@ -434,14 +438,15 @@ class WhirProver:
 
         def lap(name):  # wall-clock phase accounting (LM_WHIR_TIMING=1), printed at the end
             if tm is not None:
-                self.ctx.sync()
+                if self.ctx is not None:
+                    self.ctx.sync()
                 now = time.perf_counter()
                 tm[name] = tm.get(name, 0.0) + now - t_last[0]
                 t_last[0] = now
 
         ps.duplex()
         gamma = F.from_monty(ps.sample())
-        sc = self.ctx.sumcheck_from_tree(witness.tree)
+        sc = self._session(witness)
         lap("session (weights alloc)")
         total, gp = F.ZERO, F.ONE
         for smt in stm:
