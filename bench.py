@@ -8,11 +8,18 @@ A step is one WHIR commit of the stacked witness: gather + evals-DFT (Reed-Solom
 (8 sponge compressions per leaf + 2^22 - 1 tree compressions).  `value` is codeword field elements per second
 (2^28 per commit and GPU) with the polynomial already resident in HBM; `e2e` is the same metric through the
 reference-facing C-ABI call `lm_commit` with a pinned HOST buffer, host->device copy and root read-back inside
-the timed region.  N > 1: one process per GPU, independent commits per rank (proofs are independent, SURVEY
-section 8e "replicas"), no data-path collective; weak scaling, aggregate = sum over ranks / max-over-ranks time.
+the timed region.  N > 1 (default `--multi sharded`): ONE commit of the same shape row-sharded over the ranks
+(leanmultisig_b200/sharded.py: exchange inside the NTT, all-gather of the subtree roots) - the total work is fixed, so the
+line says "scaling": "strong"; the root is checked against a single-GPU commit of the whole polynomial outside the timed
+region.  `--multi replicas` runs one independent commit per GPU instead (weak scaling).
+
+At N = 1 the line also carries `config3` (BASELINE config 3: execution-table AIR sumcheck, Logup quotient GKR, WHIR open,
+each with ms, algorithmic bytes, roofline, e2e and cpu_baseline) and `xmss_proxy` (metric (i) PROXY, best and worst of 5
+passes); `--no-extras` skips both (bench_extra.py).
 
 `--impl reference` times the reference algorithm's CPU restatement (oracle/, the reference is Rust and cannot
-be built in this image) on the host cores over a bounded sample of the same workload.
+be built in this image) on ALL host cores over a bounded sample of the same workload; under torchrun the launcher exports
+OMP_NUM_THREADS=1, which this arm overrides before the OpenMP runtime starts.
 """
 from __future__ import annotations
 
@@ -44,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-sample-log-rows", type=int, default=0, help="0 = pick from the core count")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1: one commit row-sharded over the GPUs (strong scaling) or one commit per GPU (weak)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config3 and xmss_proxy blocks of the N = 1 line")
+    ap.add_argument("--quick-extras", action="store_true", help="config3 / proxy at reduced sizes (smoke runs of bench.py itself)")
     return ap.parse_args()
 
 
@@ -92,6 +101,20 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+def use_all_host_threads() -> int:
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm is the reference's Rayon-style
+    all-core path, so the thread count is set explicitly - in the environment BEFORE liboracle.so (libgomp) is loaded,
+    and through the library's own export in case the OpenMP runtime is already up."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    import oracle as O
+
+    lib = O.lib()
+    lib.lm_or_set_num_threads(n)
+    return int(lib.lm_or_max_threads())
+
+
 def cpu_commit_sample(sample_log_rows: int, reps: int):
     """Oracle (CPU restatement of the reference algorithms, OpenMP over rows) on a 2^sample_log_rows x 64 slice
     of the workload; returns (seconds per commit of the sample, elements per sample, cores)."""
@@ -130,7 +153,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = use_all_host_threads()
     slr = args.cpu_sample_log_rows or pick_cpu_sample(cores)
     slr = min(slr, args.log_rows)
     for _ in range(max(args.warmup, 1)):
@@ -138,7 +161,7 @@ def run_reference(args):
     times = []
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
-        t, elems, cores, _ = cpu_commit_sample(slr, 1)
+        t, elems, _, _ = cpu_commit_sample(slr, 1)
         times.append(t)
     t_step = sum(times) / len(times)
     value = elems / t_step / 1e9
@@ -149,10 +172,13 @@ def run_reference(args):
               f"all host threads (OpenMP)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "strong" if (args.gpus > 1 and args.multi == "sharded") else "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"WHIR commit 2^{args.log_rows}x64 KoalaBear, rate 1/2 (evals-DFT + Poseidon1 Merkle)",
-                   "sample": sample},
+                   "n_vars": args.log_rows + FOLDING - LOG_INV_RATE, "folding_factor": FOLDING, "log_inv_rate": LOG_INV_RATE,
+                   "live_cols": 64, "full_cols": 128, "elements_per_commit": 1 << (args.log_rows + FOLDING - LOG_INV_RATE),
+                   "sample": sample, "omp_threads": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -277,7 +303,8 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": world * elems_per_commit / (t_step * 1e-3) / 1e9, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
             "config": {"workload": f"WHIR commit 2^{args.log_rows}x64 KoalaBear, rate 1/2 (evals-DFT + Poseidon1 Merkle)",
                        "n_vars": n_vars, "folding_factor": FOLDING, "log_inv_rate": LOG_INV_RATE,
                        "live_cols": 64, "full_cols": 128, "elements_per_commit": elems_per_commit,
@@ -307,7 +334,7 @@ def run_b200(args):
         line["roofline_commit"]["frac"] = line["roofline_commit"]["achieved"] / peak
         line["roofline_ntt"]["frac"] = line["roofline_ntt"]["achieved"] / peak
         if world == 1:
-            cores = os.cpu_count()
+            cores = use_all_host_threads()
             slr = min(args.cpu_sample_log_rows or pick_cpu_sample(cores), args.log_rows)
             cpu_commit_sample(min(slr, 14), 1)  # warm-up: OpenMP pool start-up costs ~1 s on the first call
             t_cpu, elems, cores, cpu_root = cpu_commit_sample(slr, 1)
@@ -317,10 +344,46 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": elems / t_cpu / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"2^{slr} x 64 slice of the commit, oracle/ C restatement, {simd}, OpenMP on "
                                               f"all host threads, {t_cpu:.2f} s"}
-        print(json.dumps(line), flush=True)
+            if slr == args.log_rows:
+                # same seed, same shape: the GPU root of the timed commits must be the oracle's (full-size parity, every run)
+                line["cpu_baseline"]["root_matches_gpu"] = bool(np.array_equal(np.asarray(cpu_root).reshape(-1), gpu_root_of_cpu_input(
+                    l, ctx, torch, n_vars, live)))
+            if not args.no_extras:
+                del ev, cw, layers, host
+                torch.cuda.empty_cache()
+                import bench_extra
+
+                line["config3"] = bench_extra.measure_config3(ctx, torch, peak, quick=args.quick_extras)
+        print(json.dumps(line), flush=True) if (world > 1 or args.no_extras) else None
     ctx.close()
+    if rank == 0 and world == 1 and not args.no_extras:
+        # metric (i) PROXY on its own context (the proxy creates and destroys one per run), after the commit context is gone
+        import bench_extra
+
+        torch.cuda.empty_cache()
+        try:
+            line["xmss_proxy"] = bench_extra.measure_xmss_proxy(64 if args.quick_extras else 1550, 5)
+        except Exception as exc:  # the proxy must never cost the headline line
+            line["xmss_proxy"] = {"error": repr(exc)}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_root_of_cpu_input(l, ctx, torch, n_vars, live):
+    """lm_commit of the polynomial the CPU arm commits (numpy seed 0), root only"""
+    import numpy as np
+
+    from leanmultisig_b200._lib import check
+
+    rng = np.random.default_rng(0)
+    ev = rng.integers(0, P, size=live, dtype=np.uint32)
+    root = np.empty(8, dtype=np.uint32)
+    t = C.c_void_p()
+    check(l.lm_commit(ctx.handle, ev.ctypes.data_as(C.c_void_p), n_vars, 1, live, FOLDING, LOG_INV_RATE, C.byref(t),
+                      root.ctypes.data_as(C.POINTER(C.c_uint32))))
+    check(l.lm_tree_free(t))
+    return root
 
 
 def run_b200_sharded(args, rank, local_rank, world):
@@ -387,8 +450,27 @@ def run_b200_sharded(args, rank, local_rank, world):
     t_step, t_e2e = tt.tolist()
     roots = [None] * world
     dist.all_gather_object(roots, [int(x) for x in np.asarray(root).reshape(-1)])
+    # outside the timed region: the sharded root must be the root of ONE single-GPU commit of the whole polynomial
+    # (rank q holds, for every column chunk of 2^(n - k) entries, the positions whose top log2(N) bits are q)
+    gathered = [torch.empty_like(shard) for _ in range(world)] if rank == 0 else None
+    dist.gather(shard, gathered, dst=0)
+    single_root = None
+    if rank == 0:
+        n_cols = live >> (n_vars - FOLDING)
+        full = torch.stack([g.view(n_cols, -1) for g in gathered], dim=1).contiguous().view(-1)  # [column][rank][position]
+        del gathered
+
+        class _Buf:
+            ptr = full.data_ptr()
+
+        torch.cuda.synchronize()
+        tree = ctx.commit_dev(_Buf, n_vars, 1, FOLDING, LOG_INV_RATE, live)
+        single_root = [int(x) for x in tree.root]
+        tree.free()
+        del full
     if rank == 0:
         assert all(r == roots[0] for r in roots), "ranks disagree on the Merkle root"
+        assert single_root == roots[0], "sharded Merkle root differs from the single-GPU commit of the same polynomial"
         peak, peak_src = peaks()
         rows = wl["rows"]
         commit_bytes = live * 4 + rows * 64 * 4 + (2 * rows - 1) * 32
@@ -409,6 +491,7 @@ def run_b200_sharded(args, rank, local_rank, world):
             "e2e": {"value": elems_per_commit / (t_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": t_e2e,
                     "h2d_bytes_per_step": live * 4, "d2h_bytes_per_step": 32 * world},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "root_check": "sharded root == single-GPU lm_commit_dev root of the gathered polynomial (outside the timed region)",
         }
         if phases:
             line["phases_ms_rank0_last_step"] = phases

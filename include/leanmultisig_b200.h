@@ -177,6 +177,13 @@ int lm_air_new_shard(lm_ctx* ctx, uint32_t table_id, const uint32_t* const* cols
 int lm_air_new_folded(lm_ctx* ctx, uint32_t table_id, const uint32_t* cols_ef, uint32_t n_cols_total, uint32_t log_rows,
                       const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
                       const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5], lm_air** out);
+/* Session over columns that ALREADY live on this context's device, e.g. inside the committed stacked polynomial (the
+ * columns of one table are consecutive 2^log_rows-element segments there, stacked_pcs.rs:118-135): d_cols = n_cols
+ * columns of 2^log_rows base-field elements, column after column.  The execution table BORROWS them (no copy; they must
+ * stay valid and unchanged until lm_air_free), the wide tables copy them next to their shifted columns on the device. */
+int lm_air_new_dev(lm_ctx* ctx, uint32_t table_id, const uint32_t* d_cols, uint32_t n_cols, uint32_t log_rows,
+                   const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* logup_alphas_eq,
+                   uint32_t n_la, const uint32_t bus_beta[5], lm_air** out);
 int lm_air_info(const lm_air* air, uint32_t* n_vars, uint32_t* degree, uint32_t* n_cols_total);
 /* out_evals: degree x 5 words = sum_j eq(j) C(row pair j at z) for z = 0, 2, 3, .., degree over the WHOLE
  * hypercube (no separate padding term), before the missing_mul_factor scaling (air_sumcheck.rs:242-249) */
@@ -208,6 +215,8 @@ typedef struct lm_gkr lm_gkr;
 int lm_finger_print(lm_ctx* ctx, const uint32_t* data, uint64_t n_rows, uint32_t n_data, const uint32_t* alphas,
                     const uint32_t c[5], uint32_t* out);
 int lm_gkr_new(lm_ctx* ctx, const uint32_t* nums, const uint32_t* dens, uint64_t active_len, lm_gkr** out);
+/* the same from device-resident arrays (d_nums: active_len F, d_dens: active_len x 5 words); both are copied */
+int lm_gkr_new_dev(lm_ctx* ctx, const uint32_t* d_nums, const uint32_t* d_dens, uint64_t active_len, lm_gkr** out);
 /* One row-range shard of the fraction table split over several GPUs (leanmultisig_b200/sharded.py): the shard
  * has 2^n_vars rows of which the first active_len (possibly 0) are given, the rest are (0, 1); the up pass stops at
  * 2^top_vars fractions per shard (5 - log2(G), so that the gathered tops are the 2^5 values the prover sends). */
@@ -366,10 +375,20 @@ int lm_fs_pow_grinding(lm_fs* fs, uint32_t bits);
 int lm_fs_transcript_len(const lm_fs* fs, uint64_t* n_words);
 int lm_fs_transcript(const lm_fs* fs, uint32_t* out);
 int lm_fs_state(const lm_fs* fs, uint32_t state[16], int* rate_fresh);
+/* Hand-over of the sponge to a caller-owned transcript and back (state 16 words, rate_fresh as in challenger.rs): a Rust
+ * ProverState that wants the device-resident challenger of lm_gkr_prove / lm_air_prove_batched exports its Challenger into
+ * an lm_fs, runs the phase, and re-imports state + the transcript words the phase appended. */
+int lm_fs_set_state(lm_fs* fs, const uint32_t state[16], int rate_fresh);
 /* prove_gkr_quotient (crates/sub_protocols/src/quotient_gkr/mod.rs:31-141) end to end: top values, per-layer sumchecks
- * (lm_gkr_round / build_bare_from_coeffs / lm_gkr_fold), inner evaluations.  out_point: n_vars x 5. */
+ * (compute_round / build_bare_from_coeffs / fold), inner evaluations.  out_point: n_vars x 5.  The challenger of the layer
+ * sumchecks runs ON THE DEVICE (csrc/devfs.cuh: Poseidon1 duplex of challenger.rs:8-76, add_sumcheck_polynomial and
+ * sample of prover.rs:74-128 inside the round kernels): the launches of all layers are enqueued back to back and the sponge
+ * state + appended transcript words come back once, at the end. */
 int lm_gkr_prove(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out_point, uint32_t out_claim_num[5],
                  uint32_t out_claim_den[5]);
+/* the same with the round loop and the sponge on the host (one synchronisation per round); cross-check of lm_gkr_prove */
+int lm_gkr_prove_hostloop(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out_point, uint32_t out_claim_num[5],
+                          uint32_t out_claim_den[5]);
 /* prove_batched_air_sumcheck (crates/sub_protocols/src/air_sumcheck.rs:636-681) over n_sessions sessions: eq_factors =
  * the sessions' eq_factor arrays one after the other (n_vars_i x 5 each), sums = n_sessions x 5 initial sums.
  * out_challenges: max_i n_vars_i x 5; afterwards lm_air_final gives each session's column evaluations. */

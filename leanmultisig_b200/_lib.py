@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
             "lm_air_free": [vp],
             "lm_finger_print": [vp, u32p, u64, u32, u32p, u32p, u32p],
             "lm_gkr_new": [vp, u32p, u32p, u64, C.POINTER(vp)],
+            "lm_gkr_new_dev": [vp, vp, vp, u64, C.POINTER(vp)],
+            "lm_air_new_dev": [vp, u32, vp, u32, u32, u32p, u32p, u32, u32p, u32, u32p, C.POINTER(vp)],
             "lm_gkr_new_shard": [vp, u32p, u32p, u64, u32, u32, C.POINTER(vp)],
             "lm_gkr_layer_begin_shard": [vp, u32, u32p, u32p, u32p],
             "lm_gkr_num_vars": [vp, u32p],
@@ -152,6 +154,8 @@ def lib() -> C.CDLL:
             "lm_fs_transcript": [vp, u32p],
             "lm_fs_state": [vp, u32p, C.POINTER(C.c_int)],
             "lm_gkr_prove": [vp, vp, u32p, u32p, u32p, u32p],
+            "lm_gkr_prove_hostloop": [vp, vp, u32p, u32p, u32p, u32p],
+            "lm_fs_set_state": [vp, u32p, i],
             "lm_air_prove_batched": [C.POINTER(vp), u32, u32p, u32p, u32p, vp, u32p, u32p],
         }
         for name, args in sig.items():

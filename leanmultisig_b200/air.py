@@ -82,7 +82,7 @@ class OuterSumcheckHost:
 
 class AirSumcheckSession(OuterSumcheckHost):
     def __init__(self, ctx, table_id: int, columns, eq_factor, sum_, alpha_powers, logup_alphas_eq_poly, bus_beta, *,
-                 halo_next_row=None, eq_scale=None, folded_columns=None):
+                 halo_next_row=None, eq_scale=None, folded_columns=None, device_columns=None):
         """columns: the table's base-field columns (natural row order).  Keyword forms used by the sharded session
         (leanmultisig_b200/sharded.py): `halo_next_row` / `eq_scale` make this the session of ONE row-range shard
         (lm_air_new_shard), `folded_columns` ((n_cols + n_shift) x rows x 5) starts from already folded EF columns
@@ -90,7 +90,14 @@ class AirSumcheckSession(OuterSumcheckHost):
         eq = _u32(eq_factor).reshape(-1, 5)
         ap, la, beta = _u32(alpha_powers).reshape(-1, 5), _u32(logup_alphas_eq_poly).reshape(-1, 5), _u32(bus_beta)
         h = C.c_void_p()
-        if folded_columns is not None:
+        if device_columns is not None:
+            # (device pointer, n_cols): the table's base columns, contiguous, already on the device (lm_air_new_dev) - e.g.
+            # the table's segment of the committed stacked polynomial; the execution table borrows them without a copy
+            ptr, n_cols = device_columns
+            n_vars = eq.shape[0]
+            check(lib().lm_air_new_dev(ctx.handle, table_id, C.c_void_p(ptr), n_cols, n_vars, _p(eq), _p(ap), ap.shape[0], _p(la),
+                                       la.shape[0], _p(beta), C.byref(h)))
+        elif folded_columns is not None:
             fc = _u32(folded_columns)
             assert fc.ndim == 3 and fc.shape[2] == 5
             n = fc.shape[1]

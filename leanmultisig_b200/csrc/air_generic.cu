@@ -17,6 +17,7 @@
 #include <cstdint>
 #include "air.h"
 #include "air_values.cuh"
+#include "eqtab.cuh"
 #include "kb.cuh"
 #include "launch_count.h"
 #include "poly.h"
@@ -145,20 +146,16 @@ struct ColView<Fb, 1> {
 };
 template <>
 struct ColView<Ef, 5> {
-  const uint32_t* cols;
+  const uint32_t* cols;  // coefficient planes u32[c][5][n] (air.h)
   uint64_t n, j;
   uint32_t zm;
   __device__ __forceinline__ Ef operator()(int c) const {
-    const uint2* p = reinterpret_cast<const uint2*>(cols + ((uint64_t)c * n + 2 * j) * 5);
-    uint32_t w[10];
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-      const uint2 v = __ldg(p + k);
-      w[2 * k] = v.x, w[2 * k + 1] = v.y;
-    }
     Ef r;
 #pragma unroll
-    for (int k = 0; k < 5; k++) r.c[k] = kb_add(w[k], kb_mul(zm, kb_sub(w[5 + k], w[k])));
+    for (int k = 0; k < 5; k++) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(cols + (uint64_t)(c * 5 + k) * n + 2 * j));
+      r.c[k] = kb_add(v.x, kb_mul(zm, kb_sub(v.y, v.x)));
+    }
     return r;
   }
 };
@@ -363,21 +360,15 @@ struct Poseidon16Air {
 constexpr int AIRG_THREADS = 128;
 template <class Air, class T, int DIM>
 __global__ void __launch_bounds__(AIRG_THREADS)
-air_stream_round_kernel(const uint32_t* __restrict__ cols, uint64_t n, uint64_t half, const uint32_t* __restrict__ eq_hi,
-                        const uint32_t* __restrict__ eq_lo, int lo_vars, const __grid_constant__ AirExtraBig X,
-                        uint32_t* __restrict__ partial) {
+air_stream_round_kernel(const uint32_t* __restrict__ cols, uint64_t n, uint64_t half, const uint32_t* __restrict__ eq_tab, uint32_t k_vars,
+                        uint32_t m_vars, const __grid_constant__ AirExtraBig X, uint32_t* __restrict__ partial) {
   __shared__ uint32_t acc_s[Air::DEG * 5][AIRG_THREADS];
   const int tid = threadIdx.x;
 #pragma unroll
   for (int k = 0; k < Air::DEG * 5; k++) acc_s[k][tid] = 0;
+  const EqView eqv(eq_tab, k_vars, m_vars);
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + tid; j < half; j += (uint64_t)gridDim.x * blockDim.x) {
-    Ef eh, el;
-#pragma unroll
-    for (int c = 0; c < 5; c++) {
-      eh.c[c] = __ldg(eq_hi + 5 * (j >> lo_vars) + c);
-      el.c[c] = __ldg(eq_lo + 5 * (j & (((uint64_t)1 << lo_vars) - 1)) + c);
-    }
-    const Ef eq = ef_mul(eh, el);
+    const Ef eq = eqv(j);
 #pragma unroll 1
     for (int zi = 0; zi < Air::DEG; zi++) {
       const uint32_t z = zi == 0 ? 0u : (uint32_t)zi + 1u;
@@ -415,14 +406,14 @@ bool air_table_shape(uint32_t table, uint32_t* n_cols, uint32_t* n_shift, uint32
 
 template <class Air>
 static cudaError_t launch_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t dim, uint64_t n, uint64_t half,
-                                const uint32_t* d_hi, const uint32_t* d_lo, int lo_vars, const AirExtraBig& X, uint32_t* d_part,
+                                const uint32_t* d_eq_tab, uint32_t k_vars, uint32_t m_vars, const AirExtraBig& X, uint32_t* d_part,
                                 uint32_t* d_out) {
   uint64_t blocks = (half + AIRG_THREADS - 1) / AIRG_THREADS;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (dim == 1)
-    air_stream_round_kernel<Air, Fb, 1><<<(unsigned)blocks, AIRG_THREADS, 0, stream>>>(d_cols, n, half, d_hi, d_lo, lo_vars, X, d_part);
+    air_stream_round_kernel<Air, Fb, 1><<<(unsigned)blocks, AIRG_THREADS, 0, stream>>>(d_cols, n, half, d_eq_tab, k_vars, m_vars, X, d_part);
   else
-    air_stream_round_kernel<Air, Ef, 5><<<(unsigned)blocks, AIRG_THREADS, 0, stream>>>(d_cols, n, half, d_hi, d_lo, lo_vars, X, d_part);
+    air_stream_round_kernel<Air, Ef, 5><<<(unsigned)blocks, AIRG_THREADS, 0, stream>>>(d_cols, n, half, d_eq_tab, k_vars, m_vars, X, d_part);
   count_launch();
   airg_sum_partials_kernel<<<1, 64, 0, stream>>>(d_part, (int)blocks, Air::DEG * 5, d_out);
   count_launch();
@@ -430,9 +421,8 @@ static cudaError_t launch_round(cudaStream_t stream, const uint32_t* d_cols, uin
 }
 
 cudaError_t air_generic_round(cudaStream_t stream, uint32_t table, const uint32_t* d_cols, uint32_t dim, uint32_t log_n,
-                              const uint32_t* d_eq_point, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* la,
-                              uint32_t n_la, const uint32_t beta[5], uint32_t* d_scratch, uint32_t* d_out,
-                              const uint32_t* eq_scale) {
+                              const uint32_t* d_eq_tab, uint32_t k_vars, const uint32_t* alpha_powers, uint32_t n_alpha,
+                              const uint32_t* la, uint32_t n_la, const uint32_t beta[5], uint32_t* d_scratch, uint32_t* d_out) {
   uint32_t nc, ns, deg, maxc;
   if (!air_table_shape(table, &nc, &ns, &deg, &maxc) || (table & 0xffu) == 0) return cudaErrorInvalidValue;
   const int bus = (table & 0x100u) ? 0 : 1;
@@ -448,18 +438,9 @@ cudaError_t air_generic_round(cudaStream_t stream, uint32_t table, const uint32_
   X.bus = bus;
 
   const uint64_t n = (uint64_t)1 << log_n, half = n / 2;
-  const uint32_t lv = log_n - 1;
-  const int lo_vars = lv < (uint32_t)AIR_LO ? (int)lv : AIR_LO;
-  const int hi_vars = (int)lv - lo_vars;
-  uint32_t* d_hi = d_scratch;
-  uint32_t* d_lo = d_hi + 5 * ((size_t)1 << hi_vars);
-  uint32_t* d_part = d_lo + 5 * ((size_t)1 << lo_vars);
-  const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
-  cudaError_t e;
-  if ((e = eq_table(stream, d_eq_point, hi_vars, eq_scale ? eq_scale : one, d_hi)) != cudaSuccess) return e;
-  if ((e = eq_table(stream, d_eq_point + 5 * hi_vars, lo_vars, one, d_lo)) != cudaSuccess) return e;
-  if ((table & 0xffu) == 1) return launch_round<ExtOpAir>(stream, d_cols, dim, n, half, d_hi, d_lo, lo_vars, X, d_part, d_out);
-  return launch_round<Poseidon16Air>(stream, d_cols, dim, n, half, d_hi, d_lo, lo_vars, X, d_part, d_out);
+  uint32_t* d_part = d_scratch;
+  if ((table & 0xffu) == 1) return launch_round<ExtOpAir>(stream, d_cols, dim, n, half, d_eq_tab, k_vars, log_n - 1, X, d_part, d_out);
+  return launch_round<Poseidon16Air>(stream, d_cols, dim, n, half, d_eq_tab, k_vars, log_n - 1, X, d_part, d_out);
 }
 
 // ---- fill_trace_poseidon_16 (trace_gen.rs:10-165): one row per thread, columns 25..109 from columns 8..25 ------

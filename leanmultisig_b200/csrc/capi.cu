@@ -3,6 +3,7 @@
 // WhirConfig::commit (crates/whir/src/commit.rs:64-85), device memory ownership, stream plumbing.
 #include <cuda_runtime.h>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +18,7 @@
 #include "poly.h"
 #include "sumcheck.h"
 #include "air.h"
+#include "eqtab.cuh"
 #include "gkr.h"
 #include "launch_count.h"
 
@@ -150,37 +152,63 @@ struct lm_sumcheck {
 struct lm_air {
   lm_ctx* ctx = nullptr;
   uint32_t table_id = 0, n_cols = 0, n_shift = 0, degree = 0;
-  uint32_t log_n = 0;       // current number of variables
-  uint32_t dim = 1;         // 1 until the first fold
-  uint32_t* d_cols = nullptr;   // current SoA columns
+  uint32_t n_vars0 = 0;     // variables at creation (the eq tables are indexed by it)
+  uint32_t log_n = 0;       // current number of variables = rounds left
+  bool round_done = false;  // lm_air_round has run for the current variable and lm_air_fold has not yet
+  // extension_op / poseidon16 (air_generic.cu): the fold is a pass of its own
+  uint32_t dim = 1;             // 1 until the first fold
+  uint32_t* d_cols = nullptr;   // current columns (base u32[c][n] or planes u32[c][5][n])
   uint32_t* d_spare = nullptr;  // ping-pong target of the next fold
   size_t cols_words = 0, spare_words = 0;
-  uint32_t* d_eq = nullptr;     // eq_factor, initial log_n x 5
+  // execution table (air.cu): folds are fused into the rounds, see air.h AirExecMode
+  bool exec = false;
+  bool borrowed = false;  // d_cols belongs to the caller (lm_air_new_dev)
+  bool src_is_base = true;
+  uint32_t src_log_rows = 0;  // rows of the table the next round reads
+  uint32_t pending = 0;       // challenges not yet applied to it (base: <= 2, extension: <= 1)
+  uint32_t halo[2] = {0, 0};
+  uint32_t* d_ef[2] = {nullptr, nullptr};
+  size_t ef_words[2] = {0, 0};
+  int src_buf = 0;
+  lm::AirDev* d_dev = nullptr;
+  uint32_t* d_eq_tab = nullptr;
   uint32_t* d_scratch = nullptr;
   uint32_t* d_out = nullptr;
   std::vector<uint32_t> alpha, la;
   uint32_t beta[5] = {0, 0, 0, 0, 0};
-  uint32_t eq_scale[5] = {lm::KB_R1, 0, 0, 0, 0};  // constant factor of every eq weight (shard prefix), default 1
 };
 
 // Quotient-GKR session (reference: prove_gkr_quotient, crates/sub_protocols/src/quotient_gkr/mod.rs:31-141)
 struct lm_gkr {
   lm_ctx* ctx = nullptr;
   uint32_t n_vars = 0;  // of layer 0
-  // layer l has n_vars - l variables; layer 0 numerators are base field
+  // layer l has n_vars - l variables; layer 0 numerators are base field; every EF array is five coefficient planes (gkr.h)
   std::vector<uint32_t*> nums, dens;
   uint32_t* d_w[2] = {nullptr, nullptr};  // ping-pong working tables of the current layer sumcheck
-  uint32_t* d_eq = nullptr;               // claim point of the current layer (<= 64 x 5)
-  uint32_t* d_scratch = nullptr;
-  uint32_t* d_out10 = nullptr;
-  // current layer sumcheck
+  uint32_t* d_eq_tab = nullptr;           // prefix eq tables of the current layer
+  uint32_t* d_partial = nullptr;          // per-CTA partial sums
+  lm::GkrDev* d_g = nullptr;              // device-side state of the layer sumcheck (claim point, challenges, running sum)
+  lm::DevFs* d_fs = nullptr;              // device challenger (lm_gkr_prove)
+  uint32_t* d_tr = nullptr;               // transcript words appended by the device
+  uint32_t tr_cap = 0;
+  // current layer sumcheck when the transcript is driven by the caller (lm_gkr_layer_begin / round / fold / layer_end)
   int cur_layer = -1;
-  uint32_t cur_vars = 0;  // variables still unbound in the working columns
-  int cur_src = 0, cur_buf = 0;
-  uint32_t alpha[5] = {0, 0, 0, 0, 0};
+  uint32_t cur_k = 0;     // claim variables = rounds of the current layer
+  uint32_t cur_rnd = 0;   // next round
+  bool round_done = false;  // lm_gkr_round has run for cur_rnd and lm_gkr_fold has not yet
   void* arena = nullptr;                             // one allocation for the upper layers, working tables and small buffers
   uint32_t top_vars = 5;                             // the up pass stops at 2^top_vars fractions
-  uint32_t eq_scale[5] = {lm::KB_R1, 0, 0, 0, 0};    // constant factor of the current layer's eq weights (shards)
+  lm::GkrLayerArgs layer_args(int layer, uint32_t k, bool device_fs) const {
+    lm::GkrLayerArgs a{};
+    a.nums = nums[layer], a.dens = dens[layer];
+    a.num_dim = layer == 0 ? 1 : 5;
+    a.k = k;
+    a.w[0] = d_w[0], a.w[1] = d_w[1];
+    a.eq_tab = d_eq_tab, a.partial = d_partial, a.g = d_g;
+    a.fs = device_fs ? d_fs : nullptr;
+    a.tr = device_fs ? d_tr : nullptr;
+    return a;
+  }
 };
 static const uint32_t LM_GKR_TOP_VARS = 5;  // N_VARS_TO_SEND_GKR_COEFFS (crates/sub_protocols/src/lib.rs:14)
 
@@ -1065,9 +1093,19 @@ int lm_air_free(lm_air* a) {
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->stream);
   }
-  if (a->d_cols) cudaFree(a->d_cols);
-  if (a->d_spare) cudaFree(a->d_spare);
-  if (a->d_eq) cudaFree(a->d_eq);
+  // the table-sized buffers go back to the context's size-keyed cache: the next session of the same shape reuses them
+  // (cudaMalloc / cudaFree of GiB buffers cost milliseconds each and used to sit inside the first rounds)
+  auto give_back = [&](uint32_t* p, size_t words) {
+    if (!p) return;
+    if (a->ctx) a->ctx->pool.put(words * sizeof(uint32_t), p);
+    else cudaFree(p);
+  };
+  if (!a->borrowed) give_back(a->d_cols, a->cols_words);
+  give_back(a->d_spare, a->spare_words);
+  give_back(a->d_ef[0], a->ef_words[0]);
+  give_back(a->d_ef[1], a->ef_words[1]);
+  if (a->d_dev) cudaFree(a->d_dev);
+  if (a->d_eq_tab) cudaFree(a->d_eq_tab);
   if (a->d_scratch) cudaFree(a->d_scratch);
   if (a->d_out) cudaFree(a->d_out);
   delete a;
@@ -1079,8 +1117,8 @@ int lm_air_free(lm_air* a) {
 static int air_new_impl(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, const uint32_t* cols_ef, uint32_t n_cols,
                         uint32_t log_rows, const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha,
                         const uint32_t* logup_alphas_eq, uint32_t n_la, const uint32_t bus_beta[5],
-                        const uint32_t* halo_next_row, const uint32_t* eq_scale, lm_air** out) {
-  if (!c || (!cols && !cols_ef) || !eq_factor || !alpha_powers || !bus_beta || !out || (!logup_alphas_eq && n_la))
+                        const uint32_t* halo_next_row, const uint32_t* eq_scale, lm_air** out, const uint32_t* d_cols_in = nullptr) {
+  if (!c || (!cols && !cols_ef && !d_cols_in) || !eq_factor || !alpha_powers || !bus_beta || !out || (!logup_alphas_eq && n_la))
     return fail(LM_ERR_INVALID, "lm_air_new: null argument");
   *out = nullptr;
   uint32_t t_cols, t_shift, t_deg, t_maxc;
@@ -1102,41 +1140,104 @@ static int air_new_impl(lm_ctx* c, uint32_t table_id, const uint32_t* const* col
   a->n_cols = t_cols;
   a->n_shift = t_shift;
   a->degree = t_deg;
-  a->log_n = log_rows;
+  a->n_vars0 = a->log_n = log_rows;
+  a->exec = (table_id & 0xffu) == 0;
   a->alpha.assign(alpha_powers, alpha_powers + 5 * (size_t)n_alpha);
   a->la.assign(logup_alphas_eq, logup_alphas_eq + 5 * (size_t)n_la);
   memcpy(a->beta, bus_beta, sizeof(a->beta));
-  if (eq_scale) memcpy(a->eq_scale, eq_scale, sizeof(a->eq_scale));
   const uint64_t n = (uint64_t)1 << log_rows;
   const uint32_t all = a->n_cols + a->n_shift;
   a->dim = cols_ef ? 5 : 1;
-  a->cols_words = (size_t)all * n * a->dim;
-  cudaError_t e = cudaMalloc(&a->d_cols, a->cols_words * sizeof(uint32_t));
+  cudaError_t e = cudaSuccess;
   if (cols_ef) {
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(a->d_cols, cols_ef, a->cols_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    // [all][n][5] from the host -> planes; for the execution table this is the extension-field source table
+    uint32_t* tmp = nullptr;
+    const size_t words = (size_t)all * n * 5;
+    e = cudaMalloc(&tmp, words * sizeof(uint32_t));
+    uint32_t* planes = nullptr;
+    if (e == cudaSuccess) e = c->pool.get(words * sizeof(uint32_t), reinterpret_cast<void**>(&planes));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, cols_ef, words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = lm::air_aos_to_planes(c->stream, tmp, all, n, planes);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (tmp) cudaFree(tmp);
+    if (a->exec) {
+      a->d_ef[0] = planes, a->ef_words[0] = words;
+      a->src_is_base = false, a->src_buf = 0, a->src_log_rows = log_rows, a->pending = 0;
+    } else {
+      a->d_cols = planes, a->cols_words = words;
+    }
+  } else if (d_cols_in) {
+    // device-resident base columns: borrowed by the execution table, copied (next to their shifts) by the wide tables
+    if (a->exec) {
+      a->d_cols = const_cast<uint32_t*>(d_cols_in);
+      a->borrowed = true;
+      a->cols_words = (size_t)a->n_cols * n;
+      uint32_t last[2] = {0, 0};
+      for (uint32_t k = 0; e == cudaSuccess && k < 2; k++)
+        e = cudaMemcpyAsync(&last[k], d_cols_in + (size_t)k * n + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      a->halo[0] = last[0], a->halo[1] = last[1];
+      a->src_is_base = true, a->src_log_rows = log_rows, a->pending = 0;
+      for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+        if (log_rows < 3u + b) break;
+        const size_t words = (size_t)22 * 5 * (n >> (2 + b));
+        e = c->pool.get(words * sizeof(uint32_t), reinterpret_cast<void**>(&a->d_ef[b]));
+        if (e == cudaSuccess) a->ef_words[b] = words;
+      }
+    } else {
+      a->cols_words = (size_t)all * n;
+      e = c->pool.get(a->cols_words * sizeof(uint32_t), reinterpret_cast<void**>(&a->d_cols));
+      if (e != cudaSuccess) a->cols_words = 0;
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(a->d_cols, d_cols_in, (size_t)a->n_cols * n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream);
+      for (uint32_t k = 0; e == cudaSuccess && k < a->n_shift; k++)
+        e = lm::air_shift_column(c->stream, a->d_cols + (size_t)k * n, n, a->d_cols + (size_t)(a->n_cols + k) * n);
+    }
   } else {
-    for (uint32_t k = 0; e == cudaSuccess && k < a->n_cols; k++) {
+    for (uint32_t k = 0; k < a->n_cols; k++)
       if (!cols[k]) {
         lm_air_free(a);
         return fail(LM_ERR_INVALID, "lm_air_new: column %u is null", k);
       }
-      e = cudaMemcpyAsync(a->d_cols + (size_t)k * n, cols[k], n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    const uint32_t stored = a->exec ? a->n_cols : all;  // the execution table derives its shifted columns on the fly
+    a->cols_words = (size_t)stored * n;
+    e = c->pool.get(a->cols_words * sizeof(uint32_t), reinterpret_cast<void**>(&a->d_cols));
+    if (e != cudaSuccess) a->cols_words = 0;
+    if (a->exec && e == cudaSuccess) {
+      // both extension tables of the fused rounds (a quarter and an eighth of the rows), so that no round allocates
+      for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+        if (log_rows < 3u + b) break;
+        const size_t words = (size_t)22 * 5 * (n >> (2 + b));
+        e = c->pool.get(words * sizeof(uint32_t), reinterpret_cast<void**>(&a->d_ef[b]));
+        if (e == cudaSuccess) a->ef_words[b] = words;
+      }
     }
-    // shifted copies of the first n_shift columns (compute_shifted_columns, air_sumcheck.rs:683-694)
-    for (uint32_t k = 0; e == cudaSuccess && k < a->n_shift; k++) {
-      e = lm::air_shift_column(c->stream, a->d_cols + (size_t)k * n, n, a->d_cols + (size_t)(a->n_cols + k) * n);
-      if (e == cudaSuccess && halo_next_row)
-        e = cudaMemcpyAsync(a->d_cols + (size_t)(a->n_cols + k) * n + (n - 1), halo_next_row + k, sizeof(uint32_t),
-                            cudaMemcpyHostToDevice, c->stream);
+    for (uint32_t k = 0; e == cudaSuccess && k < a->n_cols; k++)
+      e = cudaMemcpyAsync(a->d_cols + (size_t)k * n, cols[k], n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (a->exec) {
+      for (uint32_t k = 0; k < 2; k++) a->halo[k] = halo_next_row ? halo_next_row[k] : cols[k][n - 1];
+      a->src_is_base = true, a->src_log_rows = log_rows, a->pending = 0;
+    } else {
+      // shifted copies of the first n_shift columns (compute_shifted_columns, air_sumcheck.rs:683-694)
+      for (uint32_t k = 0; e == cudaSuccess && k < a->n_shift; k++) {
+        e = lm::air_shift_column(c->stream, a->d_cols + (size_t)k * n, n, a->d_cols + (size_t)(a->n_cols + k) * n);
+        if (e == cudaSuccess && halo_next_row)
+          e = cudaMemcpyAsync(a->d_cols + (size_t)(a->n_cols + k) * n + (n - 1), halo_next_row + k, sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, c->stream);
+      }
     }
   }
-  if (e == cudaSuccess) e = cudaMalloc(&a->d_eq, (size_t)log_rows * 5 * sizeof(uint32_t));
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(a->d_eq, eq_factor, (size_t)log_rows * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = cudaMalloc(&a->d_scratch, lm::air_round_scratch_words(log_rows) * sizeof(uint32_t));
+  uint32_t* d_eq = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&d_eq, (size_t)log_rows * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_eq, eq_factor, (size_t)log_rows * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_eq_tab, lm::eqtab_words(log_rows) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = lm::air_build_eq_tables(c->stream, d_eq, log_rows, eq_scale, a->d_eq_tab);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_scratch, lm::air_round_scratch_words() * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&a->d_out, 64 * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_dev, sizeof(lm::AirDev));
+  if (e == cudaSuccess) e = cudaMemsetAsync(a->d_dev, 0, sizeof(lm::AirDev), c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (d_eq) cudaFree(d_eq);
   if (e != cudaSuccess) {
     lm_air_free(a);
     return cuda_fail(e, "lm_air_new");
@@ -1151,6 +1252,14 @@ int lm_air_new(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32
   if (!cols) return fail(LM_ERR_INVALID, "lm_air_new: null argument");
   return air_new_impl(c, table_id, cols, nullptr, n_cols, log_rows, eq_factor, alpha_powers, n_alpha, logup_alphas_eq, n_la,
                       bus_beta, nullptr, nullptr, out);
+}
+
+int lm_air_new_dev(lm_ctx* c, uint32_t table_id, const uint32_t* d_cols, uint32_t n_cols, uint32_t log_rows,
+                   const uint32_t* eq_factor, const uint32_t* alpha_powers, uint32_t n_alpha, const uint32_t* logup_alphas_eq,
+                   uint32_t n_la, const uint32_t bus_beta[5], lm_air** out) {
+  if (!d_cols) return fail(LM_ERR_INVALID, "lm_air_new_dev: null argument");
+  return air_new_impl(c, table_id, nullptr, nullptr, n_cols, log_rows, eq_factor, alpha_powers, n_alpha, logup_alphas_eq, n_la,
+                      bus_beta, nullptr, nullptr, out, d_cols);
 }
 
 int lm_air_new_shard(lm_ctx* c, uint32_t table_id, const uint32_t* const* cols, uint32_t n_cols, uint32_t log_rows,
@@ -1212,20 +1321,66 @@ int lm_air_info(const lm_air* a, uint32_t* n_vars, uint32_t* degree, uint32_t* n
   return LM_OK;
 }
 
+// execution table: which kernel variant reads the current source table, and what it needs (air.h AirExecMode)
+static int air_exec_args(lm_air* a, lm::AirExecArgs* A, int* mode, bool for_final) {
+  const uint32_t need = for_final ? 0u : 1u;  // a round needs one unbound variable on top of the pending ones
+  if (a->src_log_rows < a->pending + need) return fail(LM_ERR_INVALID, "lm_air: no variables left");
+  *A = lm::AirExecArgs{};
+  A->k = a->n_vars0;
+  A->eq_tab = a->d_eq_tab;
+  A->partial = a->d_scratch;
+  A->d = a->d_dev;
+  A->m = for_final ? 0 : a->src_log_rows - a->pending - 1;
+  if (a->src_is_base) {
+    A->base = a->d_cols;
+    A->n_base = (uint64_t)1 << a->src_log_rows;
+    A->halo[0] = a->halo[0], A->halo[1] = a->halo[1];
+    *mode = a->pending == 0 ? lm::AIR_B0 : (a->pending == 1 ? lm::AIR_B1 : lm::AIR_B2);
+  } else {
+    A->src = a->d_ef[a->src_buf];
+    *mode = a->pending == 0 ? lm::AIR_E0 : lm::AIR_E1;
+  }
+  if (!for_final && (*mode == lm::AIR_B2 || *mode == lm::AIR_E1)) {
+    const int dst = a->src_is_base ? 0 : (a->src_buf ^ 1);
+    const size_t words = (size_t)22 * 5 * ((size_t)2 << A->m);
+    if (a->ef_words[dst] < words) {
+      if (a->d_ef[dst]) a->ctx->pool.put(a->ef_words[dst] * sizeof(uint32_t), a->d_ef[dst]);
+      a->d_ef[dst] = nullptr, a->ef_words[dst] = 0;
+      CU(a->ctx->pool.get(words * sizeof(uint32_t), reinterpret_cast<void**>(&a->d_ef[dst])));
+      a->ef_words[dst] = words;
+    }
+    A->dst = a->d_ef[dst];
+  }
+  return LM_OK;
+}
+
 int lm_air_round(lm_air* a, uint32_t* out_evals) {
   if (!a || !out_evals) return fail(LM_ERR_INVALID, "lm_air_round: null argument");
   if (a->log_n < 1) return fail(LM_ERR_INVALID, "lm_air_round: no variables left");
+  if (a->round_done) return fail(LM_ERR_INVALID, "lm_air_round: the previous round has not been folded (lm_air_fold)");
   lm_ctx* c = a->ctx;
   CU(cudaSetDevice(c->device));
-  if (a->table_id == 0)
-    CU(lm::air_exec_round(c->stream, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(), a->la.data(),
-                          (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch, a->d_out, a->eq_scale));
-  else
-    CU(lm::air_generic_round(c->stream, a->table_id, a->d_cols, a->dim, a->log_n, a->d_eq, a->alpha.data(),
+  if (a->exec) {
+    lm::AirExecArgs A;
+    int mode = 0;
+    if (int rc = air_exec_args(a, &A, &mode, false)) return rc;
+    CU(lm::air_exec_round(c->stream, mode, A, a->alpha.data(), a->la.data(), (uint32_t)(a->la.size() / 5), a->beta));
+    if (mode == lm::AIR_B2 || mode == lm::AIR_E1) {  // the round materialised the folded table: it is the source from now on
+      a->src_buf = a->src_is_base ? 0 : (a->src_buf ^ 1);
+      a->src_log_rows -= a->pending;
+      a->src_is_base = false;
+      a->pending = 0;
+    }
+    CU(cudaMemcpyAsync(out_evals, reinterpret_cast<uint8_t*>(a->d_dev) + offsetof(lm::AirDev, out),
+                       (size_t)a->degree * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CU(lm::air_generic_round(c->stream, a->table_id, a->d_cols, a->dim, a->log_n, a->d_eq_tab, a->n_vars0, a->alpha.data(),
                              (uint32_t)(a->alpha.size() / 5), a->la.data(), (uint32_t)(a->la.size() / 5), a->beta, a->d_scratch,
-                             a->d_out, a->eq_scale));
-  CU(cudaMemcpyAsync(out_evals, a->d_out, (size_t)a->degree * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                             a->d_out));
+    CU(cudaMemcpyAsync(out_evals, a->d_out, (size_t)a->degree * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaStreamSynchronize(c->stream));
+  a->round_done = true;
   return LM_OK;
 }
 
@@ -1234,31 +1389,50 @@ int lm_air_fold(lm_air* a, const uint32_t r[5]) {
   if (a->log_n < 1) return fail(LM_ERR_INVALID, "lm_air_fold: no variables left");
   lm_ctx* c = a->ctx;
   CU(cudaSetDevice(c->device));
-  const uint64_t n = (uint64_t)1 << a->log_n;
-  const uint32_t all = a->n_cols + a->n_shift;
-  const size_t need = (size_t)all * (n / 2) * 5;
-  if (a->spare_words < need) {
-    if (a->d_spare) cudaFree(a->d_spare);
-    a->d_spare = nullptr;
-    a->spare_words = 0;
-    CU(cudaMalloc(&a->d_spare, need * sizeof(uint32_t)));
-    a->spare_words = need;
+  if (a->exec) {
+    // deferred: the next round (or lm_air_final) applies the challenge while it reads the table
+    if (!a->round_done) return fail(LM_ERR_INVALID, "lm_air_fold: call lm_air_round first (the fold is fused into the next round)");
+    uint8_t* d = reinterpret_cast<uint8_t*>(a->d_dev) + offsetof(lm::AirDev, r);
+    CU(cudaMemcpyAsync(d + sizeof(lm::Ef), d, sizeof(lm::Ef), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(d, r, sizeof(lm::Ef), cudaMemcpyHostToDevice, c->stream));
+    a->pending += 1;
+  } else {
+    const uint64_t n = (uint64_t)1 << a->log_n;
+    const uint32_t all = a->n_cols + a->n_shift;
+    const size_t need = (size_t)all * (n / 2) * 5;
+    if (a->spare_words < need) {
+      if (a->d_spare) c->pool.put(a->spare_words * sizeof(uint32_t), a->d_spare);
+      a->d_spare = nullptr;
+      a->spare_words = 0;
+      CU(c->pool.get(need * sizeof(uint32_t), reinterpret_cast<void**>(&a->d_spare)));
+      a->spare_words = need;
+    }
+    CU(lm::air_fold_lsb(c->stream, a->d_cols, a->dim, n, all, r, a->d_spare));
+    std::swap(a->d_cols, a->d_spare);
+    std::swap(a->cols_words, a->spare_words);
+    a->dim = 5;
   }
-  CU(lm::air_fold_lsb(c->stream, a->d_cols, a->dim, n, all, r, a->d_spare));
-  std::swap(a->d_cols, a->d_spare);
-  std::swap(a->cols_words, a->spare_words);
-  a->dim = 5;
   a->log_n -= 1;
-  CU(cudaStreamSynchronize(c->stream));
+  a->round_done = false;
   return LM_OK;
 }
 
 int lm_air_final(lm_air* a, uint32_t* out) {
   if (!a || !out) return fail(LM_ERR_INVALID, "lm_air_final: null argument");
-  if (a->log_n != 0 || a->dim != 5) return fail(LM_ERR_INVALID, "lm_air_final: %u variables are still unbound", a->log_n);
+  if (a->log_n != 0) return fail(LM_ERR_INVALID, "lm_air_final: %u variables are still unbound", a->log_n);
   lm_ctx* c = a->ctx;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(out, a->d_cols, (size_t)(a->n_cols + a->n_shift) * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  const size_t bytes = (size_t)(a->n_cols + a->n_shift) * 5 * sizeof(uint32_t);
+  if (a->exec) {
+    lm::AirExecArgs A;
+    int mode = 0;
+    if (int rc = air_exec_args(a, &A, &mode, true)) return rc;
+    CU(lm::air_exec_final(c->stream, mode, A, a->d_out));
+    CU(cudaMemcpyAsync(out, a->d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    if (a->dim != 5) return fail(LM_ERR_INVALID, "lm_air_final: the table was never folded");
+    CU(cudaMemcpyAsync(out, a->d_cols, bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaStreamSynchronize(c->stream));
   return LM_OK;
 }
@@ -1278,7 +1452,7 @@ int lm_gkr_free(lm_gkr* g) {
   return LM_OK;
 }
 
-// takes ownership of d_n (2^n_vars words) and d_d (2^n_vars x 5 words), both already filled on [0, active_len)
+// takes ownership of d_n (2^n_vars words) and d_d (five planes of 2^n_vars words), both already filled on [0, active_len)
 static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t active_len, uint32_t n_vars, lm_gkr** out,
                            uint32_t top_vars = LM_GKR_TOP_VARS) {
   lm_gkr* g = new (std::nothrow) lm_gkr();
@@ -1294,12 +1468,14 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
   const uint64_t n = (uint64_t)1 << n_vars;
   // one allocation for everything but layer 0 (40 cudaMalloc calls of up to hundreds of MiB cost more than the up pass)
   auto align = [](size_t b) { return (b + 255) / 256 * 256; };
-  const size_t w_words = ((size_t)1 << (n_vars - 2)) * 20;
-  const size_t w1_words = w_words / 2 ? w_words / 2 : 20;
+  const size_t w_words = n_vars >= 2 ? ((size_t)1 << (n_vars - 2)) * 20 : 20;
+  const size_t w1_words = w_words / 2 > 40 ? w_words / 2 : 40;
+  g->tr_cap = 10 * n_vars * n_vars + 40 * n_vars + 256;
   size_t total = 0;
   for (uint32_t l = 1; l <= n_vars - top_vars; l++) total += 2 * align((n >> l) * 5 * sizeof(uint32_t));
-  total += align(w_words * sizeof(uint32_t)) + align(w1_words * sizeof(uint32_t)) + align(64 * 5 * sizeof(uint32_t)) +
-           align(lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t)) + align(16 * sizeof(uint32_t));
+  total += align(w_words * sizeof(uint32_t)) + align(w1_words * sizeof(uint32_t)) + align(lm::gkr_eq_table_words(n_vars) * sizeof(uint32_t)) +
+           align((size_t)lm::GKR_MAX_BLOCKS * 10 * sizeof(uint32_t)) + align(sizeof(lm::GkrDev)) + align(sizeof(lm::DevFs)) +
+           align((size_t)g->tr_cap * sizeof(uint32_t));
   cudaError_t e = cudaMalloc(&g->arena, total);
   uint8_t* cur = static_cast<uint8_t*>(g->arena);
   auto carve = [&](size_t bytes) {
@@ -1307,7 +1483,7 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
     cur += align(bytes);
     return p;
   };
-  if (e == cudaSuccess) e = lm::gkr_pad(c->stream, d_n, 1, d_d, active_len, n);
+  if (e == cudaSuccess) e = lm::gkr_pad(c->stream, d_n, d_d, active_len, n);
   // up pass (mod.rs:52-62): halve until 2^top_vars fractions remain
   for (uint32_t l = 1; e == cudaSuccess && l <= n_vars - top_vars; l++) {
     const uint64_t m = n >> l;
@@ -1318,12 +1494,15 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
     e = lm::gkr_layer_up(c->stream, g->nums[l - 1], l == 1 ? 1 : 5, g->dens[l - 1], m * 2, nn, dd);
   }
   if (e == cudaSuccess) {
-    // working tables: the first fold of the largest layer produces 2^(n_vars - 2) rows of 20 words
+    // working tables: the first fused fold of the largest layer produces 2^(n_vars - 2) rows of 20 words
     g->d_w[0] = carve(w_words * sizeof(uint32_t));
     g->d_w[1] = carve(w1_words * sizeof(uint32_t));
-    g->d_eq = carve(64 * 5 * sizeof(uint32_t));
-    g->d_scratch = carve(lm::gkr_round_scratch_words(n_vars) * sizeof(uint32_t));
-    g->d_out10 = carve(16 * sizeof(uint32_t));
+    g->d_eq_tab = carve(lm::gkr_eq_table_words(n_vars) * sizeof(uint32_t));
+    g->d_partial = carve((size_t)lm::GKR_MAX_BLOCKS * 10 * sizeof(uint32_t));
+    g->d_g = reinterpret_cast<lm::GkrDev*>(carve(sizeof(lm::GkrDev)));
+    g->d_fs = reinterpret_cast<lm::DevFs*>(carve(sizeof(lm::DevFs)));
+    g->d_tr = carve((size_t)g->tr_cap * sizeof(uint32_t));
+    e = cudaMemsetAsync(g->d_g, 0, sizeof(lm::GkrDev), c->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
@@ -1332,6 +1511,19 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
   }
   *out = g;
   return LM_OK;
+}
+
+// host AoS denominators (active_len x 5) -> device coefficient planes of stride n
+static cudaError_t upload_dens_planes(lm_ctx* c, const uint32_t* dens, uint64_t active_len, uint64_t n, uint32_t* d_planes) {
+  if (active_len == 0) return cudaSuccess;
+  uint32_t* tmp = nullptr;
+  cudaError_t e = cudaMalloc(&tmp, active_len * 5 * sizeof(uint32_t));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(tmp, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = lm::gkr_aos_to_planes(c->stream, tmp, active_len, n, d_planes);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  return e;
 }
 
 static int gkr_vars_for(uint64_t active_len, uint32_t* n_vars_out, const char* who) {
@@ -1355,10 +1547,29 @@ int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t a
   cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = upload_dens_planes(c, dens, active_len, n, d_d);
   if (e != cudaSuccess) {
     cudaFree(d_n), cudaFree(d_d);
     return cuda_fail(e, "lm_gkr_new");
+  }
+  return gkr_from_device(c, d_n, d_d, active_len, n_vars, out);
+}
+
+int lm_gkr_new_dev(lm_ctx* c, const uint32_t* d_nums_in, const uint32_t* d_dens_in, uint64_t active_len, lm_gkr** out) {
+  if (!c || !d_nums_in || !d_dens_in || !out) return fail(LM_ERR_INVALID, "lm_gkr_new_dev: null argument");
+  *out = nullptr;
+  uint32_t n_vars = 0;
+  if (int rc = gkr_vars_for(active_len, &n_vars, "lm_gkr_new_dev")) return rc;
+  CU(cudaSetDevice(c->device));
+  const uint64_t n = (uint64_t)1 << n_vars;
+  uint32_t *d_n = nullptr, *d_d = nullptr;
+  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, d_nums_in, active_len * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess) e = lm::gkr_aos_to_planes(c->stream, d_dens_in, active_len, n, d_d);
+  if (e != cudaSuccess) {
+    cudaFree(d_n), cudaFree(d_d);
+    return cuda_fail(e, "lm_gkr_new_dev");
   }
   return gkr_from_device(c, d_n, d_d, active_len, n_vars, out);
 }
@@ -1377,8 +1588,7 @@ int lm_gkr_new_shard(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint
   if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
   if (e == cudaSuccess && active_len)
     e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess && active_len)
-    e = cudaMemcpyAsync(d_d, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess && active_len) e = upload_dens_planes(c, dens, active_len, n, d_d);
   if (e != cudaSuccess) {
     cudaFree(d_n), cudaFree(d_d);
     return cuda_fail(e, "lm_gkr_new_shard");
@@ -1521,7 +1731,7 @@ int lm_logup_section(lm_logup* L, uint64_t n_rows, uint32_t num_mode, const uint
       return fail(LM_ERR_INVALID, "lm_logup_section: data kind %u", d.kind);
     }
   }
-  CU(lm::logup_fill_section(c->stream, S, L->d_nums + L->offset, L->d_dens + 5 * L->offset));
+  CU(lm::logup_fill_section(c->stream, S, L->d_nums + L->offset, L->d_dens + L->offset, (uint64_t)1 << L->n_vars));
   L->offset += n_rows;
   return LM_OK;
 }
@@ -1566,8 +1776,14 @@ int lm_logup_read(lm_logup* L, uint32_t* out_nums, uint32_t* out_dens) {
   lm_ctx* c = L->ctx;
   CU(cudaSetDevice(c->device));
   if (out_nums) CU(cudaMemcpyAsync(out_nums, L->d_nums, L->offset * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (out_dens) CU(cudaMemcpyAsync(out_dens, L->d_dens, L->offset * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (out_dens && L->offset) {  // the device holds coefficient planes; the caller gets [F; 5] per row
+    std::vector<uint32_t> plane(L->offset);
+    for (int k = 0; k < 5; k++) {
+      CU(cudaMemcpy(plane.data(), L->d_dens + ((size_t)k << L->n_vars), L->offset * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (uint64_t i = 0; i < L->offset; i++) out_dens[5 * i + k] = plane[i];
+    }
+  }
   return LM_OK;
 }
 
@@ -1611,29 +1827,37 @@ int lm_gkr_top(lm_gkr* g, uint32_t* top_nums, uint32_t* top_dens) {
   if (!g || !top_nums || !top_dens) return fail(LM_ERR_INVALID, "lm_gkr_top: null argument");
   lm_ctx* c = g->ctx;
   CU(cudaSetDevice(c->device));
-  const size_t bytes = ((size_t)1 << g->top_vars) * 5 * sizeof(uint32_t);
-  CU(cudaMemcpyAsync(top_nums, g->nums.back(), bytes, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(top_dens, g->dens.back(), bytes, cudaMemcpyDeviceToHost, c->stream));
+  const size_t m = (size_t)1 << g->top_vars;
+  const bool base_nums = g->nums.size() == 1;  // no up pass at all (shards): numerators are still base field
+  std::vector<uint32_t> pn(base_nums ? m : 5 * m), pd(5 * m);
+  CU(cudaMemcpyAsync(pn.data(), g->nums.back(), pn.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(pd.data(), g->dens.back(), pd.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < m; i++)
+    for (int k = 0; k < 5; k++) {
+      top_nums[5 * i + k] = base_nums ? (k == 0 ? pn[i] : 0u) : pn[k * m + i];
+      top_dens[5 * i + k] = pd[k * m + i];
+    }
   return LM_OK;
 }
 
 static int gkr_layer_begin_impl(lm_gkr* g, uint32_t claim_vars, const uint32_t* point, const uint32_t alpha[5],
                                 const uint32_t* eq_scale) {
   if (!g || !point || !alpha) return fail(LM_ERR_INVALID, "lm_gkr_layer_begin: null argument");
-  if (claim_vars < g->top_vars || claim_vars >= g->n_vars)
+  if (claim_vars < g->top_vars || claim_vars >= g->n_vars || claim_vars > (uint32_t)lm::GKR_MAX_VARS)
     return fail(LM_ERR_INVALID, "lm_gkr_layer_begin: claim over %u variables, expected %u..%u", claim_vars, g->top_vars,
                 g->n_vars - 1);
   lm_ctx* c = g->ctx;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(g->d_eq, point, (size_t)claim_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(g->d_g) + offsetof(lm::GkrDev, point), point,
+                     (size_t)claim_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(g->d_g) + offsetof(lm::GkrDev, alpha), alpha, 5 * sizeof(uint32_t),
+                     cudaMemcpyHostToDevice, c->stream));
   g->cur_layer = (int)(g->n_vars - (claim_vars + 1));  // the layer below the claim has claim_vars + 1 variables
-  g->cur_vars = claim_vars;                            // its even/odd halves have claim_vars variables
-  g->cur_src = 0;
-  g->cur_buf = 0;
-  memcpy(g->alpha, alpha, sizeof(g->alpha));
-  const uint32_t one[5] = {lm::KB_R1, 0, 0, 0, 0};
-  memcpy(g->eq_scale, eq_scale ? eq_scale : one, sizeof(g->eq_scale));
+  g->cur_k = claim_vars;                               // its even/odd halves have claim_vars variables
+  g->cur_rnd = 0;
+  g->round_done = false;
+  CU(lm::gkr_begin(c->stream, g->layer_args(g->cur_layer, g->cur_k, false), eq_scale, false));
   return LM_OK;
 }
 
@@ -1647,49 +1871,105 @@ int lm_gkr_layer_begin_shard(lm_gkr* g, uint32_t claim_vars, const uint32_t* poi
   return gkr_layer_begin_impl(g, claim_vars, point, alpha, eq_scale);
 }
 
+// The fold of lm_gkr_fold is deferred: the round that follows folds the previous table with the stored challenge while it
+// reads it (one pass over the table per round), the last one is applied by lm_gkr_layer_end.
 int lm_gkr_round(lm_gkr* g, uint32_t c0[5], uint32_t c2[5]) {
   if (!g || !c0 || !c2) return fail(LM_ERR_INVALID, "lm_gkr_round: null argument");
-  if (g->cur_layer < 0 || g->cur_vars < 1) return fail(LM_ERR_INVALID, "lm_gkr_round: no layer sumcheck in progress");
+  if (g->cur_layer < 0 || g->cur_rnd >= g->cur_k) return fail(LM_ERR_INVALID, "lm_gkr_round: no layer sumcheck in progress");
+  if (g->round_done) return fail(LM_ERR_INVALID, "lm_gkr_round: the previous round has not been folded");
   lm_ctx* c = g->ctx;
   CU(cudaSetDevice(c->device));
-  const uint32_t* a = g->cur_src == 0 ? g->nums[g->cur_layer] : g->d_w[g->cur_buf];
-  const uint32_t* b = g->cur_src == 0 ? g->dens[g->cur_layer] : nullptr;
-  CU(lm::gkr_round(c->stream, g->cur_src, g->cur_layer == 0 ? 1 : 5, a, b, g->cur_vars, g->d_eq, g->alpha, g->d_scratch,
-                   g->d_out10, g->eq_scale));
+  CU(lm::gkr_round(c->stream, g->layer_args(g->cur_layer, g->cur_k, false), g->cur_rnd));
   uint32_t h[10];
-  CU(cudaMemcpyAsync(h, g->d_out10, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h, reinterpret_cast<uint8_t*>(g->d_g) + offsetof(lm::GkrDev, out), sizeof(h), cudaMemcpyDeviceToHost,
+                     c->stream));
   CU(cudaStreamSynchronize(c->stream));
   memcpy(c0, h, 5 * sizeof(uint32_t));
   memcpy(c2, h + 5, 5 * sizeof(uint32_t));
+  g->round_done = true;
   return LM_OK;
 }
 
 int lm_gkr_fold(lm_gkr* g, const uint32_t r[5]) {
   if (!g || !r) return fail(LM_ERR_INVALID, "lm_gkr_fold: null argument");
-  if (g->cur_layer < 0 || g->cur_vars < 1) return fail(LM_ERR_INVALID, "lm_gkr_fold: no layer sumcheck in progress");
+  if (g->cur_layer < 0 || g->cur_rnd >= g->cur_k) return fail(LM_ERR_INVALID, "lm_gkr_fold: no layer sumcheck in progress");
   lm_ctx* c = g->ctx;
   CU(cudaSetDevice(c->device));
-  const uint32_t* a = g->cur_src == 0 ? g->nums[g->cur_layer] : g->d_w[g->cur_buf];
-  const uint32_t* b = g->cur_src == 0 ? g->dens[g->cur_layer] : nullptr;
-  const int dst = g->cur_src == 0 ? 0 : (g->cur_buf ^ 1);
-  CU(lm::gkr_fold(c->stream, g->cur_src, g->cur_layer == 0 ? 1 : 5, a, b, g->cur_vars, r, g->d_w[dst]));
-  g->cur_src = 1;
-  g->cur_buf = dst;
-  g->cur_vars -= 1;
+  if (!g->round_done) return fail(LM_ERR_INVALID, "lm_gkr_fold: call lm_gkr_round first (the fold is fused into the next round)");
+  CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(g->d_g) + offsetof(lm::GkrDev, r), r, 5 * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                     c->stream));
+  g->cur_rnd += 1;
+  g->round_done = false;
   return LM_OK;
 }
 
 int lm_gkr_layer_end(lm_gkr* g, uint32_t* inner_evals) {
   if (!g || !inner_evals) return fail(LM_ERR_INVALID, "lm_gkr_layer_end: null argument");
-  if (g->cur_layer < 0 || g->cur_vars != 0 || g->cur_src != 1)
-    return fail(LM_ERR_INVALID, "lm_gkr_layer_end: %u variables are still unbound", g->cur_vars);
+  if (g->cur_layer < 0 || g->cur_rnd != g->cur_k)
+    return fail(LM_ERR_INVALID, "lm_gkr_layer_end: %u variables are still unbound", g->cur_k - g->cur_rnd);
   lm_ctx* c = g->ctx;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(inner_evals, g->d_w[g->cur_buf], 20 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(lm::gkr_end(c->stream, g->layer_args(g->cur_layer, g->cur_k, false)));
+  CU(cudaMemcpyAsync(inner_evals, reinterpret_cast<uint8_t*>(g->d_g) + offsetof(lm::GkrDev, inner), 20 * sizeof(uint32_t),
+                     cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   g->cur_layer = -1;
   return LM_OK;
 }
+
+}  // extern "C"
+
+// Every layer sumcheck of prove_gkr_quotient with the challenger on the device (spine.cu's lm_gkr_prove is the caller): the
+// sponge state goes in, all launches are enqueued back to back, and the state, the transcript words the device appended,
+// the final point and the two claims come back with ONE synchronisation.
+int lm_internal_gkr_device_layers(lm_gkr* g, uint32_t state[16], int* rate_fresh, const uint32_t* point, const uint32_t claim_num[5],
+                                  const uint32_t claim_den[5], std::vector<uint32_t>* transcript, uint32_t* out_point,
+                                  uint32_t out_claim_num[5], uint32_t out_claim_den[5]) {
+  lm_ctx* c = g->ctx;
+  CU(cudaSetDevice(c->device));
+  if (g->n_vars > (uint32_t)lm::GKR_MAX_VARS) return fail(LM_ERR_INVALID, "lm_gkr_prove: too many variables");
+  std::vector<uint8_t> host(sizeof(lm::GkrDev), 0);
+  lm::GkrDev* hg = reinterpret_cast<lm::GkrDev*>(host.data());
+  memcpy(hg->point, point, (size_t)g->top_vars * 5 * sizeof(uint32_t));
+  memcpy(hg->claim_num.c, claim_num, 5 * sizeof(uint32_t));
+  memcpy(hg->claim_den.c, claim_den, 5 * sizeof(uint32_t));
+  hg->k = g->top_vars;
+  lm::DevFs hf{};
+  memcpy(hf.state, state, sizeof(hf.state));
+  hf.rate_fresh = *rate_fresh ? 1u : 0u;
+  hf.n_words = 0;
+  hf.cap_words = g->tr_cap;
+  hf.error = 0;
+  CU(cudaMemcpyAsync(g->d_g, hg, sizeof(lm::GkrDev), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(g->d_fs, &hf, sizeof(hf), cudaMemcpyHostToDevice, c->stream));
+  CU(lm::gkr_begin(c->stream, g->layer_args((int)(g->n_vars - (g->top_vars + 1)), g->top_vars, true), nullptr, true));
+  for (uint32_t k = g->top_vars; k < g->n_vars; k++) {
+    const lm::GkrLayerArgs a = g->layer_args((int)(g->n_vars - (k + 1)), k, true);
+    if (k + 1 < g->n_vars) {
+      const lm::GkrLayerArgs nx = g->layer_args((int)(g->n_vars - (k + 2)), k + 1, true);
+      CU(lm::gkr_layer_device(c->stream, a, &nx));
+    } else {
+      CU(lm::gkr_layer_device(c->stream, a, nullptr));
+    }
+  }
+  CU(cudaMemcpyAsync(hg, g->d_g, sizeof(lm::GkrDev), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&hf, g->d_fs, sizeof(hf), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (hf.error) return fail(LM_ERR_INVALID, "lm_gkr_prove: device challenger error 0x%x (1 stale rate, 2 transcript overflow, 4 zero eq coordinate)", hf.error);
+  if (hf.n_words) {
+    const size_t at = transcript->size();
+    transcript->resize(at + hf.n_words);
+    CU(cudaMemcpy(transcript->data() + at, g->d_tr, (size_t)hf.n_words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  memcpy(state, hf.state, sizeof(hf.state));
+  *rate_fresh = hf.rate_fresh ? 1 : 0;
+  memcpy(out_point, hg->point, (size_t)g->n_vars * 5 * sizeof(uint32_t));
+  memcpy(out_claim_num, hg->claim_num.c, 5 * sizeof(uint32_t));
+  memcpy(out_claim_den, hg->claim_den.c, 5 * sizeof(uint32_t));
+  return LM_OK;
+}
+
+extern "C" {
 
 int lm_finger_print(lm_ctx* c, const uint32_t* data, uint64_t n_rows, uint32_t n_data, const uint32_t* alphas,
                     const uint32_t cc[5], uint32_t* out) {

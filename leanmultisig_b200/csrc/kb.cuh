@@ -210,4 +210,47 @@ LM_HD Ef ef_mul(const Ef& a, const Ef& b) {
 }
 LM_HD Ef ef_sqr(const Ef& a) { return ef_mul(a, a); }
 
+// the nine distinct entries of ef_mul's row matrix for a fixed right operand
+struct EfRows {
+  uint32_t b0, b1, b2, b3, b4, b0m3, b1m4, b4m2, b3m14;
+};
+LM_HD EfRows ef_rows(const Ef& b) {
+  EfRows r;
+  r.b0 = b.c[0], r.b1 = b.c[1], r.b2 = b.c[2], r.b3 = b.c[3], r.b4 = b.c[4];
+  r.b0m3 = kb_sub(r.b0, r.b3), r.b1m4 = kb_sub(r.b1, r.b4), r.b4m2 = kb_sub(r.b4, r.b2);
+  r.b3m14 = kb_sub(r.b3, r.b1m4);
+  return r;
+}
+// a * b + c * d with one reduction per coefficient (ten delayed products)
+LM_HD Ef ef_mul2_add(const Ef& a, const Ef& b, const Ef& c, const Ef& d) {
+  const EfRows x = ef_rows(b), y = ef_rows(d);
+  const uint32_t rx[5][5] = {{x.b0, x.b4, x.b3, x.b2, x.b1m4},
+                             {x.b1, x.b0, x.b4, x.b3, x.b2},
+                             {x.b2, x.b1m4, x.b0m3, x.b4m2, x.b3m14},
+                             {x.b3, x.b2, x.b1m4, x.b0m3, x.b4m2},
+                             {x.b4, x.b3, x.b2, x.b1m4, x.b0m3}};
+  const uint32_t ry[5][5] = {{y.b0, y.b4, y.b3, y.b2, y.b1m4},
+                             {y.b1, y.b0, y.b4, y.b3, y.b2},
+                             {y.b2, y.b1m4, y.b0m3, y.b4m2, y.b3m14},
+                             {y.b3, y.b2, y.b1m4, y.b0m3, y.b4m2},
+                             {y.b4, y.b3, y.b2, y.b1m4, y.b0m3}};
+  Ef r;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    KbDot t;
+    t.mac<0>(a.c[0], rx[i][0]);
+    t.mac<1>(a.c[1], rx[i][1]);
+    t.mac<2>(a.c[2], rx[i][2]);
+    t.mac<3>(a.c[3], rx[i][3]);
+    t.mac<4>(a.c[4], rx[i][4]);
+    t.mac<5>(c.c[0], ry[i][0]);
+    t.mac<6>(c.c[1], ry[i][1]);
+    t.mac<7>(c.c[2], ry[i][2]);
+    t.mac<8>(c.c[3], ry[i][3]);
+    t.mac<9>(c.c[4], ry[i][4]);
+    r.c[i] = t.finish();
+  }
+  return r;
+}
+
 }  // namespace lm

@@ -22,6 +22,10 @@
 #include "merkle.h"
 
 int lm_internal_fail(int code, const char* msg);  // capi.cu: sets lm_last_error
+// capi.cu: all layer sumchecks of the quotient GKR with the challenger on the device (devfs.cuh)
+int lm_internal_gkr_device_layers(lm_gkr* g, uint32_t state[16], int* rate_fresh, const uint32_t* point, const uint32_t claim_num[5],
+                                  const uint32_t claim_den[5], std::vector<uint32_t>* transcript, uint32_t* out_point,
+                                  uint32_t out_claim_num[5], uint32_t out_claim_den[5]);
 
 namespace {
 using lm::Ef;
@@ -259,6 +263,12 @@ int lm_fs_transcript(const lm_fs* fs, uint32_t* out) {
   if (!fs->transcript.empty()) memcpy(out, fs->transcript.data(), fs->transcript.size() * sizeof(uint32_t));
   return LM_OK;
 }
+int lm_fs_set_state(lm_fs* fs, const uint32_t state[16], int rate_fresh) {
+  if (!fs || !state) return lm_internal_fail(LM_ERR_INVALID, "lm_fs_set_state: null argument");
+  memcpy(fs->state, state, sizeof(fs->state));
+  fs->rate_fresh = rate_fresh != 0;
+  return LM_OK;
+}
 int lm_fs_state(const lm_fs* fs, uint32_t state[16], int* rate_fresh) {
   if (!fs || !state) return lm_internal_fail(LM_ERR_INVALID, "lm_fs_state: null argument");
   memcpy(state, fs->state, sizeof(fs->state));
@@ -292,6 +302,56 @@ int lm_gkr_prove(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out
   }
   std::vector<Ef> point;
   if (!fs->sample_ef(TOP, &point)) return lm_internal_fail(LM_ERR_INVALID, "lm_gkr_prove: stale rate");
+  auto mle_small = [&](std::vector<Ef> cur) {
+    for (const Ef& x : point) {
+      const size_t half = cur.size() / 2;
+      for (size_t i = 0; i < half; i++) cur[i] = lm::ef_add(cur[i], lm::ef_mul(x, lm::ef_sub(cur[i + half], cur[i])));
+      cur.resize(half);
+    }
+    return cur[0];
+  };
+  Ef claim_num = mle_small(top_n), claim_den = mle_small(top_d);
+
+  // prove_gkr_layer for every layer (mod.rs:64-75) on the device: no host round trip per round
+  std::vector<uint32_t> pt(5 * (size_t)TOP), out_pt(5 * (size_t)n_vars);
+  for (uint32_t i = 0; i < TOP; i++) ef_store(pt.data() + 5 * i, point[i]);
+  int fresh = fs->rate_fresh ? 1 : 0;
+  if (int rc = lm_internal_gkr_device_layers(gkr, fs->state, &fresh, pt.data(), claim_num.c, claim_den.c, &fs->transcript,
+                                             out_pt.data(), out_claim_num, out_claim_den))
+    return rc;
+  fs->rate_fresh = fresh != 0;
+  ef_store(out_quotient, quotient);
+  memcpy(out_point, out_pt.data(), out_pt.size() * sizeof(uint32_t));
+  return LM_OK;
+}
+
+// The same driver with the round loop and the transcript on the host (one synchronisation per round): what a caller that
+// keeps its own ProverState does through lm_gkr_layer_begin / round / fold / layer_end; kept to cross-check lm_gkr_prove.
+int lm_gkr_prove_hostloop(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out_point, uint32_t out_claim_num[5],
+                 uint32_t out_claim_den[5]) {
+  if (!gkr || !fs || !out_quotient || !out_point || !out_claim_num || !out_claim_den)
+    return lm_internal_fail(LM_ERR_INVALID, "lm_gkr_prove_hostloop: null argument");
+  uint32_t n_vars = 0;
+  if (int rc = lm_gkr_num_vars(gkr, &n_vars)) return rc;
+  const uint32_t TOP = 5;  // N_VARS_TO_SEND_GKR_COEFFS
+  uint32_t top_vars = 0;
+  if (int rc = lm_gkr_top_vars(gkr, &top_vars)) return rc;
+  if (top_vars != TOP) return lm_internal_fail(LM_ERR_INVALID, "lm_gkr_prove_hostloop: shard sessions are driven by the caller (sharded.py)");
+  std::vector<uint32_t> tn(32 * 5), td(32 * 5);
+  if (int rc = lm_gkr_top(gkr, tn.data(), td.data())) return rc;
+  fs->add_scalars(tn.data(), tn.size());
+  fs->add_scalars(td.data(), td.size());
+  std::vector<Ef> top_n, top_d;
+  Ef quotient = EF_ZERO;
+  for (int i = 0; i < 32; i++) {
+    top_n.push_back(ef_load(tn.data() + 5 * i));
+    top_d.push_back(ef_load(td.data() + 5 * i));
+    Ef inv;
+    if (!ef_inv(top_d[i], &inv)) return lm_internal_fail(LM_ERR_INVALID, "lm_gkr_prove_hostloop: a top-layer denominator is zero");
+    quotient = lm::ef_add(quotient, lm::ef_mul(top_n[i], inv));
+  }
+  std::vector<Ef> point;
+  if (!fs->sample_ef(TOP, &point)) return lm_internal_fail(LM_ERR_INVALID, "lm_gkr_prove_hostloop: stale rate");
   auto mle_small = [&](std::vector<Ef> cur) {
     for (const Ef& x : point) {
       const size_t half = cur.size() / 2;

@@ -205,6 +205,17 @@ class NativeProverState:
         check(lib().lm_fs_state(self.handle, st.ctypes.data_as(u32p), None))
         return st
 
+    def state_and_freshness(self):
+        """(sponge state, rate_fresh): what `set_state` takes to resume this transcript elsewhere"""
+        st, fresh = np.empty(16, dtype=np.uint32), C.c_int()
+        check(lib().lm_fs_state(self.handle, st.ctypes.data_as(u32p), C.byref(fresh)))
+        return st, bool(fresh.value)
+
+    def set_state(self, state, rate_fresh: bool) -> None:
+        s, p = self._words(state)
+        assert s.size == 16
+        check(lib().lm_fs_set_state(self.handle, p, 1 if rate_fresh else 0))
+
     def free(self):
         if self.handle:
             check(lib().lm_fs_free(self.handle))

@@ -84,6 +84,13 @@ class GkrQuotientProver:
         return inner
 
     @classmethod
+    def from_device(cls, ctx, d_nums: int, d_dens: int, active_len: int):
+        """lm_gkr_new_dev: numerators (active_len F) and denominators (active_len x 5 words) already on the device"""
+        h = C.c_void_p()
+        check(lib().lm_gkr_new_dev(ctx.handle, C.c_void_p(d_nums), C.c_void_p(d_dens), active_len, C.byref(h)))
+        return cls.from_handle(h)
+
+    @classmethod
     def from_handle(cls, handle):
         self = cls.__new__(cls)
         self.handle = handle
@@ -109,11 +116,19 @@ class GkrQuotientProver:
     _sample_alpha = None
 
     def prove_native(self, native_state):
-        """prove_gkr_quotient with the round loop, the transcript and the per-round field arithmetic in the library's C++
-        spine (lm_gkr_prove): same transcript and outputs as prove_with_state, no interpreter round trip per round."""
+        """prove_gkr_quotient through lm_gkr_prove: top layer on the host, every layer sumcheck on the device INCLUDING the
+        challenger (csrc/devfs.cuh), so no round costs a host round trip; same transcript and outputs as prove_with_state."""
         q, cn, cd = (np.empty(5, dtype=np.uint32) for _ in range(3))
         pt = np.empty((self.n_vars, 5), dtype=np.uint32)
         check(lib().lm_gkr_prove(self.handle, native_state.handle, _p(q), _p(pt), _p(cn), _p(cd)))
+        return q, pt, cn, cd
+
+    def prove_native_hostloop(self, native_state):
+        """lm_gkr_prove_hostloop: the C++ driver with the sponge on the host, one synchronisation per round (cross-check of
+        the device-resident challenger that prove_native uses)."""
+        q, cn, cd = (np.empty(5, dtype=np.uint32) for _ in range(3))
+        pt = np.empty((self.n_vars, 5), dtype=np.uint32)
+        check(lib().lm_gkr_prove_hostloop(self.handle, native_state.handle, _p(q), _p(pt), _p(cn), _p(cd)))
         return q, pt, cn, cd
 
     def prove(self, add_scalars, add_sumcheck_poly, sample, sample_point=None):

@@ -71,6 +71,8 @@ uint32_t lm_or_kb_from_u32(uint32_t a);
 uint32_t lm_or_kb_to_u32(uint32_t a);
 uint32_t lm_or_kb_inv(uint32_t a);
 uint32_t lm_or_kb_two_adic_generator(uint32_t bits);
+void lm_or_set_num_threads(int n);
+int lm_or_max_threads(void);
 
 /* sumcheck.c */
 void lm_or_weights_add_eq(uint32_t *weights, uint64_t selector, const uint32_t *point, uint32_t m,

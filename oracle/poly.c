@@ -114,3 +114,10 @@ uint32_t lm_or_kb_from_u32(uint32_t a) { return kb_from_u32(a); }
 uint32_t lm_or_kb_to_u32(uint32_t a) { return kb_to_u32(a); }
 uint32_t lm_or_kb_inv(uint32_t a) { return kb_inv(a); }
 uint32_t lm_or_kb_two_adic_generator(uint32_t bits) { return kb_two_adic_generator(bits); }
+
+/* OpenMP thread count of the oracle (bench.py's CPU arms: torchrun exports OMP_NUM_THREADS=1 to its workers) */
+#include <omp.h>
+void lm_or_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+int lm_or_max_threads(void) { return omp_get_max_threads(); }

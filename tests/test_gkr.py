@@ -180,7 +180,7 @@ def test_gpu_finger_print(rng):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_vars,active", [(7, 100), (11, 2000), (14, 16000)])
+@pytest.mark.parametrize("n_vars,active", [(6, 40), (7, 100), (11, 2000), (14, 16000), (17, 100000)])
 def test_gpu_gkr_native_spine_matches_python_spine(rng, n_vars, active):
     """lm_gkr_prove (round loop + transcript in C++, csrc/spine.cu) produces the transcript and outputs of the Python-driven
     prover and of the oracle's CPU prover; the oracle verifier accepts it."""
@@ -208,4 +208,33 @@ def test_gpu_gkr_native_spine_matches_python_spine(rng, n_vars, active):
     OL.verify_gkr_quotient(vs, n_vars)
     assert vs.off == len(ps_n.transcript)
     ps_n.free()
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_vars,active", [(12, 4000), (20, 1000000), (22, (1 << 22) - 77)])
+def test_gpu_gkr_device_challenger_matches_host_loop(rng, n_vars, active):
+    """The device-resident challenger (lm_gkr_prove: Poseidon1 duplex, add_sumcheck_polynomial and sample inside the round
+    kernels, csrc/devfs.cuh) against the host-driven loop (lm_gkr_prove_hostloop: lm_fs sponge on the host, one
+    synchronisation per round) at sizes where every kernel variant (multi-CTA rounds, last-block reduction, one-CTA tails)
+    runs: identical transcript, sponge state, point and claims; the final claims are the MLEs of the inputs."""
+    import leanmultisig_b200 as lm
+
+    ctx = lm.Context(0, 20)
+    nums, dens = O.random_field(rng, active), O.random_field(rng, (active, 5))
+    outs, states = [], []
+    for device in (True, False):
+        p = lm.GkrQuotientProver(ctx, nums, dens)
+        ps = lm.NativeProverState(ctx)
+        ps.add_base_scalars(np.arange(11, dtype=np.uint32))
+        outs.append(p.prove_native(ps) if device else p.prove_native_hostloop(ps))
+        states.append((ps.transcript, ps.state_and_freshness()))
+        p.free()
+        ps.free()
+    assert states[0][0] == states[1][0]
+    assert np.array_equal(states[0][1][0], states[1][1][0]) and states[0][1][1] == states[1][1][1]
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    pn, pd = padded(nums, dens, n_vars)
+    assert np.array_equal(outs[0][2], O.mle_eval(pn, outs[0][1])) and np.array_equal(outs[0][3], O.mle_eval(pd, outs[0][1]))
     ctx.close()

@@ -44,6 +44,8 @@ sess.free()
 print(f"  native spine (C++ round loop + transcript): {t_nat*1e3:.1f} ms for {log_rows} rounds -> {bytes_unfused/t_nat/1e9:.1f} GB/s")
 
 # ---- GKR
+if log_gkr < 15:
+    ctx.close(); sys.exit(0)
 N = (1 << log_gkr) - 12345
 nums, dens = rf(N), rf((N, 5))
 t0 = time.perf_counter(); g = lm.GkrQuotientProver(ctx, nums, dens); t_up = time.perf_counter() - t0
