@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <new>
 #include <utility>
@@ -52,37 +53,69 @@ int cuda_fail(cudaError_t e, const char* what) {
 // error reporting for the other translation units of the library (spine.cu)
 int lm_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 
-// Size-keyed cache of device allocations: a commit needs three GiB-scale buffers and cudaMalloc / cudaFree of that
-// size cost milliseconds each (the reference resets a bump arena per proof for the same reason,
-// crates/backend/zk-alloc/src/lib.rs:102-115).
+// Cache of device allocations, the GPU analogue of the reference's per-proof bump arena
+// (crates/backend/zk-alloc/src/lib.rs:102-115): a proof allocates the same few dozen buffer sizes every time, and
+// cudaMalloc / cudaFree of GiB-sized buffers cost milliseconds each and synchronise the device, which is where the 2-10x
+// run-to-run spread of whole-proof times came from.  Freed buffers are kept by exact size and handed out again; the cache
+// is bounded by a byte budget and dropped on allocation failure.
 struct DevicePool {
-  std::vector<std::pair<size_t, void*>> free_list;
+  std::multimap<size_t, void*> cache;   // size -> free buffer
+  std::map<void*, size_t> live;         // buffers handed out by alloc()
+  size_t cached_bytes = 0;
+  size_t budget_bytes = (size_t)64 << 30;
   cudaError_t get(size_t bytes, void** out) {
-    for (size_t i = 0; i < free_list.size(); i++)
-      if (free_list[i].first == bytes) {
-        *out = free_list[i].second;
-        free_list.erase(free_list.begin() + i);
-        return cudaSuccess;
-      }
-    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (bytes == 0) bytes = 1;
+    auto it = cache.find(bytes);
+    if (it != cache.end()) {
+      *out = it->second;
+      cached_bytes -= bytes;
+      cache.erase(it);
+      return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
     if (e == cudaErrorMemoryAllocation) {  // drop the cache and retry once
       cudaGetLastError();
       release_all();
-      e = cudaMalloc(out, bytes ? bytes : 1);
+      e = cudaMalloc(out, bytes);
     }
     return e;
   }
   void put(size_t bytes, void* p) {
     if (!p) return;
-    if (free_list.size() >= 12) {
-      cudaFree(free_list.front().second);
-      free_list.erase(free_list.begin());
+    if (bytes == 0) bytes = 1;
+    while (!cache.empty() && cached_bytes + bytes > budget_bytes) {  // evict the largest entries first
+      auto last = std::prev(cache.end());
+      cudaFree(last->second);
+      cached_bytes -= last->first;
+      cache.erase(last);
     }
-    free_list.emplace_back(bytes, p);
+    cache.emplace(bytes, p);
+    cached_bytes += bytes;
+  }
+  // address-keyed form: the size is remembered, free() needs only the pointer
+  template <class T>
+  cudaError_t alloc(T** out, size_t bytes) {
+    void* p = nullptr;
+    const cudaError_t e = get(bytes, &p);
+    if (e == cudaSuccess) live[p] = bytes ? bytes : 1;
+    *out = static_cast<T*>(p);
+    return e;
+  }
+  void free(void* p) {
+    if (!p) return;
+    auto it = live.find(p);
+    if (it == live.end()) {
+      cudaFree(p);
+      return;
+    }
+    const size_t bytes = it->second;
+    live.erase(it);
+    put(bytes, p);
   }
   void release_all() {
-    for (auto& e : free_list) cudaFree(e.second);
-    free_list.clear();
+    for (auto& e : cache) cudaFree(e.second);
+    cache.clear();
+    cached_bytes = 0;
   }
 };
 
@@ -139,10 +172,10 @@ struct lm_sumcheck {
   size_t scratch_words = 0;
   int ensure_scratch(size_t words) {
     if (words <= scratch_words) return LM_OK;
-    if (d_scratch) cudaFree(d_scratch);
+    if (d_scratch) ctx->pool.free(d_scratch);
     d_scratch = nullptr;
     scratch_words = 0;
-    CU(cudaMalloc(&d_scratch, words * sizeof(uint32_t)));
+    CU(ctx->pool.alloc(&d_scratch, words * sizeof(uint32_t)));
     scratch_words = words;
     return LM_OK;
   }
@@ -702,8 +735,8 @@ int lm_access_counts(lm_ctx* c, const uint32_t* const* index_cols, const uint64_
     if (n_rows[k] > max_rows) max_rows = n_rows[k];
   }
   uint32_t *d_counts = nullptr, *d_col = nullptr;
-  CU(cudaMalloc(&d_counts, (table_len + 1) * sizeof(uint32_t)));  // last word: out-of-range flag
-  cudaError_t e = cudaMalloc(&d_col, max_rows * sizeof(uint32_t));
+  CU(c->pool.alloc(&d_counts, (table_len + 1) * sizeof(uint32_t)));  // last word: out-of-range flag
+  cudaError_t e = c->pool.alloc(&d_col, max_rows * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, (table_len + 1) * sizeof(uint32_t), c->stream);
   for (uint32_t k = 0; e == cudaSuccess && k < n_cols; k++) {
     if (!n_rows[k]) continue;
@@ -716,8 +749,8 @@ int lm_access_counts(lm_ctx* c, const uint32_t* const* index_cols, const uint64_
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_acc, d_counts, table_len * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream);
-  cudaFree(d_counts);
-  if (d_col) cudaFree(d_col);
+  c->pool.free(d_counts);
+  if (d_col) c->pool.free(d_col);
   if (e != cudaSuccess) return cuda_fail(e, "lm_access_counts");
   if (bad) return fail(LM_ERR_INVALID, "lm_access_counts: an address (+ its value count) lies outside the table of %llu entries",
                        (unsigned long long)table_len);
@@ -746,8 +779,8 @@ int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows,
   if (n == 0) return LM_OK;
   uint64_t* d_idx = nullptr;
   uint32_t* d_buf = nullptr;
-  CU(cudaMalloc(&d_idx, n * sizeof(uint64_t)));
-  cudaError_t e = cudaMalloc(&d_buf, (rows_words + paths_words + 1) * sizeof(uint32_t));
+  CU(t->ctx->pool.alloc(&d_idx, n * sizeof(uint64_t)));
+  cudaError_t e = t->ctx->pool.alloc(&d_buf, (rows_words + paths_words + 1) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, indices, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess)
     e = lm::merkle_open_gather(c->stream, t->d_codeword, t->d_layers, t->height, t->stored_width, t->full_width, d_idx,
@@ -758,8 +791,8 @@ int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows,
     e = cudaMemcpyAsync(out_paths, d_buf + rows_words, paths_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream);
-  cudaFree(d_idx);
-  if (d_buf) cudaFree(d_buf);
+  t->ctx->pool.free(d_idx);
+  if (d_buf) t->ctx->pool.free(d_buf);
   if (e != cudaSuccess) return cuda_fail(e, "lm_open");
   return LM_OK;
 }
@@ -814,10 +847,10 @@ int lm_sc_free(lm_sumcheck* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
   }
-  if (s->d_p_owned) cudaFree(s->d_p_owned);
-  if (s->d_w) cudaFree(s->d_w);
-  if (s->d_out10) cudaFree(s->d_out10);
-  if (s->d_scratch) cudaFree(s->d_scratch);
+  if (s->d_p_owned) s->ctx->pool.free(s->d_p_owned);
+  if (s->d_w) s->ctx->pool.free(s->d_w);
+  if (s->d_out10) s->ctx->pool.free(s->d_out10);
+  if (s->d_scratch) s->ctx->pool.free(s->d_scratch);
   delete s;
   return LM_OK;
 }
@@ -832,9 +865,9 @@ static int sc_new_common(lm_ctx* c, uint32_t n_vars, lm_sumcheck** out) {
   s->ctx = c;
   s->n_vars = n_vars;
   const size_t w_bytes = ((size_t)5 << n_vars) * sizeof(uint32_t);
-  cudaError_t e = cudaMalloc(&s->d_w, w_bytes);
+  cudaError_t e = s->ctx->pool.alloc(&s->d_w, w_bytes);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_w, 0, w_bytes, c->stream);
-  if (e == cudaSuccess) e = cudaMalloc(&s->d_out10, 16 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = s->ctx->pool.alloc(&s->d_out10, 16 * sizeof(uint32_t));
   if (e != cudaSuccess) {
     lm_sc_free(s);
     return cuda_fail(e, "lm_sc_new");
@@ -866,7 +899,7 @@ int lm_sc_new(lm_ctx* c, const uint32_t* evals, uint32_t n_vars, uint32_t dim, u
   int rc = sc_new_common(c, n_vars, out);
   if (rc != LM_OK) return rc;
   lm_sumcheck* s = *out;
-  cudaError_t e = cudaMalloc(&s->d_p_owned, (live_len ? live_len : 1) * dim * sizeof(uint32_t));
+  cudaError_t e = s->ctx->pool.alloc(&s->d_p_owned, (live_len ? live_len : 1) * dim * sizeof(uint32_t));
   if (e == cudaSuccess && live_len)
     e = cudaMemcpyAsync(s->d_p_owned, evals, live_len * dim * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -887,7 +920,7 @@ int lm_sc_new_from_dev(lm_ctx* c, const uint32_t* d_poly, const uint32_t* d_weig
   if (rc != LM_OK) return rc;
   lm_sumcheck* s = *out;
   const size_t bytes = ((size_t)5 << n_vars) * sizeof(uint32_t);
-  cudaError_t e = cudaMalloc(&s->d_p_owned, bytes);
+  cudaError_t e = s->ctx->pool.alloc(&s->d_p_owned, bytes);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_p_owned, d_poly, bytes, cudaMemcpyDeviceToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_w, d_weights, bytes, cudaMemcpyDeviceToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -993,7 +1026,7 @@ static int sc_prepare_fold_target(lm_sumcheck* s, uint32_t** p_out) {
     return LM_OK;
   }
   uint32_t* fresh = nullptr;
-  CU(cudaMalloc(&fresh, half * 5 * sizeof(uint32_t)));
+  CU(s->ctx->pool.alloc(&fresh, half * 5 * sizeof(uint32_t)));
   *p_out = fresh;
   return LM_OK;
 }
@@ -1001,7 +1034,7 @@ static void sc_commit_fold(lm_sumcheck* s, uint32_t* p_out) {
   if (p_out != s->d_p_owned) {
     if (s->d_p_owned) {
       cudaStreamSynchronize(s->ctx->stream);
-      cudaFree(s->d_p_owned);
+      s->ctx->pool.free(s->d_p_owned);
     }
     s->d_p_owned = p_out;
   }
@@ -1299,7 +1332,7 @@ int lm_poseidon16_fill_trace(lm_ctx* c, uint32_t* const* cols, uint64_t n_rows) 
   if (n_rows == 0) return LM_OK;
   CU(cudaSetDevice(c->device));
   uint32_t* d = nullptr;
-  CU(cudaMalloc(&d, (size_t)109 * n_rows * sizeof(uint32_t)));
+  CU(c->pool.alloc(&d, (size_t)109 * n_rows * sizeof(uint32_t)));
   cudaError_t e = cudaSuccess;
   // inputs: flag_permute (column 8) and the 16 input lanes (columns 9..24)
   for (int k = 8; e == cudaSuccess && k < 25; k++)
@@ -1308,7 +1341,7 @@ int lm_poseidon16_fill_trace(lm_ctx* c, uint32_t* const* cols, uint64_t n_rows) 
   for (int k = 25; e == cudaSuccess && k < 109; k++)
     e = cudaMemcpyAsync(cols[k], d + (size_t)k * n_rows, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(d);
+  c->pool.free(d);
   if (e != cudaSuccess) return cuda_fail(e, "lm_poseidon16_fill_trace");
   return LM_OK;
 }
@@ -1445,9 +1478,9 @@ int lm_gkr_free(lm_gkr* g) {
     cudaStreamSynchronize(g->ctx->stream);
   }
   // layer 0 is owned separately (uploaded by lm_gkr_new or handed over by lm_logup_finish); the rest is one arena
-  if (!g->nums.empty()) cudaFree(g->nums[0]);
-  if (!g->dens.empty()) cudaFree(g->dens[0]);
-  if (g->arena) cudaFree(g->arena);
+  if (!g->nums.empty()) g->ctx->pool.free(g->nums[0]);
+  if (!g->dens.empty()) g->ctx->pool.free(g->dens[0]);
+  if (g->arena) g->ctx->pool.free(g->arena);
   delete g;
   return LM_OK;
 }
@@ -1457,7 +1490,7 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
                            uint32_t top_vars = LM_GKR_TOP_VARS) {
   lm_gkr* g = new (std::nothrow) lm_gkr();
   if (!g) {
-    cudaFree(d_n), cudaFree(d_d);
+    c->pool.free(d_n), c->pool.free(d_d);
     return fail(LM_ERR_OOM, "lm_gkr: host allocation failed");
   }
   g->ctx = c;
@@ -1476,7 +1509,7 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
   total += align(w_words * sizeof(uint32_t)) + align(w1_words * sizeof(uint32_t)) + align(lm::gkr_eq_table_words(n_vars) * sizeof(uint32_t)) +
            align((size_t)lm::GKR_MAX_BLOCKS * 10 * sizeof(uint32_t)) + align(sizeof(lm::GkrDev)) + align(sizeof(lm::DevFs)) +
            align((size_t)g->tr_cap * sizeof(uint32_t));
-  cudaError_t e = cudaMalloc(&g->arena, total);
+  cudaError_t e = g->ctx->pool.alloc(&g->arena, total);
   uint8_t* cur = static_cast<uint8_t*>(g->arena);
   auto carve = [&](size_t bytes) {
     uint32_t* p = reinterpret_cast<uint32_t*>(cur);
@@ -1517,12 +1550,12 @@ static int gkr_from_device(lm_ctx* c, uint32_t* d_n, uint32_t* d_d, uint64_t act
 static cudaError_t upload_dens_planes(lm_ctx* c, const uint32_t* dens, uint64_t active_len, uint64_t n, uint32_t* d_planes) {
   if (active_len == 0) return cudaSuccess;
   uint32_t* tmp = nullptr;
-  cudaError_t e = cudaMalloc(&tmp, active_len * 5 * sizeof(uint32_t));
+  cudaError_t e = c->pool.alloc(&tmp, active_len * 5 * sizeof(uint32_t));
   if (e != cudaSuccess) return e;
   e = cudaMemcpyAsync(tmp, dens, active_len * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = lm::gkr_aos_to_planes(c->stream, tmp, active_len, n, d_planes);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(tmp);
+  c->pool.free(tmp);
   return e;
 }
 
@@ -1544,12 +1577,12 @@ int lm_gkr_new(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint64_t a
   CU(cudaSetDevice(c->device));
   const uint64_t n = (uint64_t)1 << n_vars;
   uint32_t *d_n = nullptr, *d_d = nullptr;
-  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
+  cudaError_t e = c->pool.alloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = c->pool.alloc(&d_d, n * 5 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = upload_dens_planes(c, dens, active_len, n, d_d);
   if (e != cudaSuccess) {
-    cudaFree(d_n), cudaFree(d_d);
+    c->pool.free(d_n), c->pool.free(d_d);
     return cuda_fail(e, "lm_gkr_new");
   }
   return gkr_from_device(c, d_n, d_d, active_len, n_vars, out);
@@ -1563,12 +1596,12 @@ int lm_gkr_new_dev(lm_ctx* c, const uint32_t* d_nums_in, const uint32_t* d_dens_
   CU(cudaSetDevice(c->device));
   const uint64_t n = (uint64_t)1 << n_vars;
   uint32_t *d_n = nullptr, *d_d = nullptr;
-  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
+  cudaError_t e = c->pool.alloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = c->pool.alloc(&d_d, n * 5 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, d_nums_in, active_len * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream);
   if (e == cudaSuccess) e = lm::gkr_aos_to_planes(c->stream, d_dens_in, active_len, n, d_d);
   if (e != cudaSuccess) {
-    cudaFree(d_n), cudaFree(d_d);
+    c->pool.free(d_n), c->pool.free(d_d);
     return cuda_fail(e, "lm_gkr_new_dev");
   }
   return gkr_from_device(c, d_n, d_d, active_len, n_vars, out);
@@ -1584,13 +1617,13 @@ int lm_gkr_new_shard(lm_ctx* c, const uint32_t* nums, const uint32_t* dens, uint
   if (active_len > n) return fail(LM_ERR_INVALID, "lm_gkr_new_shard: active_len exceeds 2^n_vars");
   CU(cudaSetDevice(c->device));
   uint32_t *d_n = nullptr, *d_d = nullptr;
-  cudaError_t e = cudaMalloc(&d_n, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_d, n * 5 * sizeof(uint32_t));
+  cudaError_t e = c->pool.alloc(&d_n, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = c->pool.alloc(&d_d, n * 5 * sizeof(uint32_t));
   if (e == cudaSuccess && active_len)
     e = cudaMemcpyAsync(d_n, nums, active_len * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess && active_len) e = upload_dens_planes(c, dens, active_len, n, d_d);
   if (e != cudaSuccess) {
-    cudaFree(d_n), cudaFree(d_d);
+    c->pool.free(d_n), c->pool.free(d_d);
     return cuda_fail(e, "lm_gkr_new_shard");
   }
   return gkr_from_device(c, d_n, d_d, active_len, n_vars, out, top_vars);
@@ -1628,7 +1661,7 @@ struct lm_logup {
     if (bytes > arena_left) {
       const size_t chunk = bytes > ((size_t)256 << 20) ? bytes : ((size_t)256 << 20);
       void* p = nullptr;
-      CU(cudaMalloc(&p, chunk));
+      CU(ctx->pool.alloc(&p, chunk));
       chunks.push_back(p);
       arena_cur = static_cast<uint8_t*>(p);
       arena_left = chunk;
@@ -1675,8 +1708,8 @@ int lm_logup_new(lm_ctx* c, uint64_t total_active_len, const uint32_t cc[5], con
   for (int k = 0; k < 5; k++) L->c.c[k] = cc[k];
   L->alphas.assign(alphas_eq_poly, alphas_eq_poly + 5 * (size_t)n_alphas);
   const uint64_t n = (uint64_t)1 << n_vars;
-  cudaError_t e = cudaMalloc(&L->d_nums, n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&L->d_dens, n * 5 * sizeof(uint32_t));
+  cudaError_t e = c->pool.alloc(&L->d_nums, n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = c->pool.alloc(&L->d_dens, n * 5 * sizeof(uint32_t));
   if (e != cudaSuccess) {
     lm_logup_free(L);
     return cuda_fail(e, "lm_logup_new");
@@ -1762,7 +1795,7 @@ int lm_logup_col_eval_batch(lm_logup* L, const uint32_t* const* cols, const uint
     if (int rc = L->device_copy(cols[k], lens[k], &d)) return rc;
     d_cols[k] = d;
   }
-  if (!L->d_batch_out) CU(cudaMalloc(&L->d_batch_out, 256 * 5 * sizeof(uint32_t)));
+  if (!L->d_batch_out) CU(c->pool.alloc(&L->d_batch_out, 256 * 5 * sizeof(uint32_t)));
   if (int rc = c->ensure_scratch(lm::mle_eval_scratch_words(n_vars))) return rc;
   if (n_vars) CU(cudaMemcpyAsync(c->d_point, point, (size_t)n_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   CU(lm::mle_eval_batch(c->stream, d_cols.data(), lens, n_cols, n_vars, c->d_point, c->d_scratch, L->d_batch_out));
@@ -1802,11 +1835,11 @@ int lm_logup_finish(lm_logup* L, lm_gkr** out) {
 int lm_logup_free(lm_logup* L) {
   if (!L) return LM_OK;
   if (L->ctx) cudaSetDevice(L->ctx->device);
-  if (L->d_nums) cudaFree(L->d_nums);
-  if (L->d_dens) cudaFree(L->d_dens);
+  if (L->d_nums) L->ctx->pool.free(L->d_nums);
+  if (L->d_dens) L->ctx->pool.free(L->d_dens);
   if (L->ctx) cudaStreamSynchronize(L->ctx->stream);
-  for (void* p : L->chunks) cudaFree(p);
-  if (L->d_batch_out) cudaFree(L->d_batch_out);
+  for (void* p : L->chunks) L->ctx->pool.free(p);
+  if (L->d_batch_out) L->ctx->pool.free(L->d_batch_out);
   delete L;
   return LM_OK;
 }

@@ -114,6 +114,9 @@ def run(n_sigs: int = 1550, reps: int = 5, verbose: bool = False) -> dict:
             check(lib().lm_host_register(a.ctypes.data, a.nbytes))
     passes = []
     info = {}
+    # one untimed pass first, as the reference's own benchmark does (rec_aggregation/src/benchmark.rs:401-410): it loads the
+    # kernel images and fills the context's buffer cache; its time is reported separately as `ms_cold`
+    cold_phases, _ = one_pass(ctx, traces, memory, bytecode_m, log_memory, log_bytecode, info)
     for _ in range(reps):
         phases, logup_t = one_pass(ctx, traces, memory, bytecode_m, log_memory, log_bytecode, info)
         passes.append((sum(phases.values()), phases, logup_t))
@@ -125,7 +128,7 @@ def run(n_sigs: int = 1550, reps: int = 5, verbose: bool = False) -> dict:
     best, worst = passes[0], passes[-1]
     ms = lambda d: {k: v * 1e3 for k, v in d.items()}
     return {
-        "n": n_sigs, "reps": reps, "ms": best[0] * 1e3, "ms_worst": worst[0] * 1e3,
+        "n": n_sigs, "reps": reps, "ms": best[0] * 1e3, "ms_worst": worst[0] * 1e3, "ms_cold": sum(cold_phases.values()) * 1e3,
         "ms_all": [p[0] * 1e3 for p in passes],
         "phases": ms(best[1]), "phases_worst": ms(worst[1]), "logup_phases": ms(best[2]),
         "sigs_per_s_proxy": n_sigs / best[0], "sigs_per_s_proxy_worst": n_sigs / worst[0],
