@@ -356,35 +356,31 @@ struct Poseidon16Air {
 };
 
 // ---- the streaming round kernel -----------------------------------------------------------------------------
-// partial[blockIdx.x][zi] = sum over this CTA's row pairs j of eq(j) * C(row pair j at z), z = 0, 2, 3, .., DEG
-constexpr int AIRG_THREADS = 128;
+// partial[blockIdx.x][zi] = sum over this CTA's row pairs j of eq(j) * C(row pair j at z), z = 0, 2, 3, .., DEG.
+// One warp per evaluation point: a CTA is DEG warps working on the same 32 row pairs, so a round over a handful of pairs
+// costs one constraint evaluation of latency instead of DEG of them in sequence (the last ~10 rounds of every session
+// are such rounds, and the poseidon16 body is ~50 k instructions), and the warps of a CTA share their column loads in L1.
 template <class Air, class T, int DIM>
-__global__ void __launch_bounds__(AIRG_THREADS)
+__global__ void __launch_bounds__(32 * Air::DEG)
 air_stream_round_kernel(const uint32_t* __restrict__ cols, uint64_t n, uint64_t half, const uint32_t* __restrict__ eq_tab, uint32_t k_vars,
                         uint32_t m_vars, const __grid_constant__ AirExtraBig X, uint32_t* __restrict__ partial) {
-  __shared__ uint32_t acc_s[Air::DEG * 5][AIRG_THREADS];
-  const int tid = threadIdx.x;
-#pragma unroll
-  for (int k = 0; k < Air::DEG * 5; k++) acc_s[k][tid] = 0;
+  const int lane = threadIdx.x & 31, zi = threadIdx.x >> 5;
+  const uint32_t z = zi == 0 ? 0u : (uint32_t)zi + 1u;
+  const uint32_t zm = kb_mul(z, KB_R2);
+  Ef acc = ef_zero();
   const EqView eqv(eq_tab, k_vars, m_vars);
-  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + tid; j < half; j += (uint64_t)gridDim.x * blockDim.x) {
-    const Ef eq = eqv(j);
-#pragma unroll 1
-    for (int zi = 0; zi < Air::DEG; zi++) {
-      const uint32_t z = zi == 0 ? 0u : (uint32_t)zi + 1u;
-      const ColView<T, DIM> view{cols, n, j, kb_mul(z, KB_R2)};
-      const Ef v = ef_mul(Air::template eval<T>(view, X), eq);
+  for (uint64_t j = (uint64_t)blockIdx.x * 32 + lane; j < half; j += (uint64_t)gridDim.x * 32) {
+    const ColView<T, DIM> view{cols, n, j, zm};
+    acc = ef_add(acc, ef_mul(Air::template eval<T>(view, X), eqv(j)));
+  }
 #pragma unroll
-      for (int c = 0; c < 5; c++) acc_s[zi * 5 + c][tid] = kb_add(acc_s[zi * 5 + c][tid], v.c[c]);
-    }
+  for (int off = 16; off > 0; off >>= 1) {
+    Ef o;
+#pragma unroll
+    for (int c = 0; c < 5; c++) o.c[c] = __shfl_down_sync(0xffffffffu, acc.c[c], off);
+    acc = ef_add(acc, o);
   }
-  __syncthreads();
-  // Air::DEG * 5 words per CTA: thread t < DEG * 5 sums its row of the accumulator table
-  if (tid < Air::DEG * 5) {
-    uint32_t s = 0;
-    for (int t = 0; t < AIRG_THREADS; t++) s = kb_add(s, acc_s[tid][(t + tid) % AIRG_THREADS]);
-    partial[(uint64_t)blockIdx.x * Air::DEG * 5 + tid] = s;
-  }
+  if (lane == 0) st_ef(partial + ((uint64_t)blockIdx.x * Air::DEG + zi) * 5, acc);
 }
 
 __global__ void airg_sum_partials_kernel(const uint32_t* __restrict__ partial, int n_part, int n_words, uint32_t* __restrict__ out) {
@@ -408,8 +404,9 @@ template <class Air>
 static cudaError_t launch_round(cudaStream_t stream, const uint32_t* d_cols, uint32_t dim, uint64_t n, uint64_t half,
                                 const uint32_t* d_eq_tab, uint32_t k_vars, uint32_t m_vars, const AirExtraBig& X, uint32_t* d_part,
                                 uint32_t* d_out) {
-  uint64_t blocks = (half + AIRG_THREADS - 1) / AIRG_THREADS;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  uint64_t blocks = (half + 31) / 32;
+  if (blocks > (uint64_t)AIR_MAX_BLOCKS) blocks = AIR_MAX_BLOCKS;
+  constexpr int AIRG_THREADS = 32 * Air::DEG;
   if (dim == 1)
     air_stream_round_kernel<Air, Fb, 1><<<(unsigned)blocks, AIRG_THREADS, 0, stream>>>(d_cols, n, half, d_eq_tab, k_vars, m_vars, X, d_part);
   else
