@@ -82,6 +82,11 @@ int lm_commit_stacked(lm_ctx* ctx, const lm_segment* segments, uint32_t n_segmen
 int lm_access_counts(lm_ctx* ctx, const uint32_t* const* index_cols, const uint64_t* n_rows, const uint32_t* n_values,
                      uint32_t n_cols, uint64_t table_len, uint32_t* out_acc);
 int lm_open(lm_tree* tree, const uint64_t* indices, uint32_t n, uint32_t* out_rows, uint32_t* out_paths);
+/* lm_open plus the STIR answer of every opened leaf (crates/whir/src/open.rs:161-190): out_evals[q] = the leaf of index q,
+ * read as a multilinear polynomial in fold_vars = log2(elements per leaf) variables, evaluated at fold_point (fold_vars x 5,
+ * the folding randomness of the round); the fold runs on the device next to the gather. */
+int lm_open_fold(lm_tree* tree, const uint64_t* indices, uint32_t n, const uint32_t* fold_point, uint32_t fold_vars,
+                 uint32_t* out_rows, uint32_t* out_paths, uint32_t* out_evals);
 /* height (rows), full row width in words, stored row width in words, elem_dim */
 int lm_tree_shape(const lm_tree* tree, uint64_t* height, uint32_t* full_width, uint32_t* stored_width,
                   uint32_t* elem_dim);
@@ -375,6 +380,14 @@ int lm_fs_pow_grinding(lm_fs* fs, uint32_t bits);
 int lm_fs_transcript_len(const lm_fs* fs, uint64_t* n_words);
 int lm_fs_transcript(const lm_fs* fs, uint32_t* out);
 int lm_fs_state(const lm_fs* fs, uint32_t state[16], int* rate_fresh);
+/* The weight update that closes a WHIR round (crates/whir/src/open.rs:192-231): with comb the combination randomness, the
+ * OOD constraints eq(expand(y_k)) get weight comb^k and the STIR constraints eq(expand(gen^idx_q)) weight comb^(n_ood + q);
+ * total_io += sum_k comb^k ood_answers[k] + sum_q comb^(n_ood + q) stir_evals[q].  ood_ys: n_ood x 5 (the sampled
+ * univariate points), gen: Montgomery form of the folded domain's generator.  Host arithmetic in C++, weights through
+ * lm_sc_add_eq / lm_sc_add_base_eq. */
+int lm_whir_stir_update(lm_sumcheck* sc, const uint64_t* idx, uint32_t n_q, uint32_t gen, uint32_t num_variables,
+                        const uint32_t comb[5], const uint32_t* ood_ys, const uint32_t* ood_answers, uint32_t n_ood,
+                        const uint32_t* stir_evals, uint32_t total_io[5]);
 /* Hand-over of the sponge to a caller-owned transcript and back (state 16 words, rate_fresh as in challenger.rs): a Rust
  * ProverState that wants the device-resident challenger of lm_gkr_prove / lm_air_prove_batched exports its Challenger into
  * an lm_fs, runs the phase, and re-imports state + the transcript words the phase appended. */

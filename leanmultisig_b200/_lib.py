@@ -154,6 +154,8 @@ def lib() -> C.CDLL:
             "lm_fs_transcript": [vp, u32p],
             "lm_fs_state": [vp, u32p, C.POINTER(C.c_int)],
             "lm_gkr_prove": [vp, vp, u32p, u32p, u32p, u32p],
+            "lm_open_fold": [vp, u64p, u32, u32p, u32, u32p, u32p, u32p],
+            "lm_whir_stir_update": [vp, u64p, u32, u32, u32, u32p, u32p, u32p, u32, u32p, u32p],
             "lm_gkr_prove_hostloop": [vp, vp, u32p, u32p, u32p, u32p],
             "lm_fs_set_state": [vp, u32p, i],
             "lm_air_prove_batched": [C.POINTER(vp), u32, u32p, u32p, u32p, vp, u32p, u32p],

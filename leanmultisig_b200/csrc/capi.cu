@@ -766,7 +766,8 @@ int lm_tree_shape(const lm_tree* t, uint64_t* height, uint32_t* full_w, uint32_t
   return LM_OK;
 }
 
-int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows, uint32_t* out_paths) {
+static int open_impl(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows, uint32_t* out_paths,
+                     const uint32_t* fold_point, uint32_t fold_vars, uint32_t* out_evals) {
   if (!t || (n && (!indices || !out_rows || !out_paths))) return fail(LM_ERR_INVALID, "lm_open: null argument");
   lm_ctx* c = t->ctx;
   CU(cudaSetDevice(c->device));
@@ -775,12 +776,15 @@ int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows,
   for (uint32_t q = 0; q < n; q++)
     if (indices[q] >= t->height) return fail(LM_ERR_INVALID, "lm_open: index %llu >= height %llu",
                                              (unsigned long long)indices[q], (unsigned long long)t->height);
+  if (fold_point && (((uint32_t)1 << fold_vars) * t->elem_dim != t->full_width || fold_vars > 12))
+    return fail(LM_ERR_INVALID, "lm_open_fold: a leaf has %u elements, not 2^%u", t->full_width / t->elem_dim, fold_vars);
   const size_t rows_words = (size_t)n * t->full_width, paths_words = (size_t)n * log_h * 8;
+  const size_t evals_words = fold_point ? (size_t)n * 5 + (size_t)fold_vars * 5 : 0;
   if (n == 0) return LM_OK;
   uint64_t* d_idx = nullptr;
   uint32_t* d_buf = nullptr;
   CU(t->ctx->pool.alloc(&d_idx, n * sizeof(uint64_t)));
-  cudaError_t e = t->ctx->pool.alloc(&d_buf, (rows_words + paths_words + 1) * sizeof(uint32_t));
+  cudaError_t e = t->ctx->pool.alloc(&d_buf, (rows_words + paths_words + evals_words + 1) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, indices, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess)
     e = lm::merkle_open_gather(c->stream, t->d_codeword, t->d_layers, t->height, t->stored_width, t->full_width, d_idx,
@@ -789,12 +793,30 @@ int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows,
     e = cudaMemcpyAsync(out_rows, d_buf, rows_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess && paths_words)
     e = cudaMemcpyAsync(out_paths, d_buf + rows_words, paths_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (fold_point) {
+    uint32_t* d_ev = d_buf + rows_words + paths_words;
+    uint32_t* d_pt = d_ev + (size_t)n * 5;
+    if (e == cudaSuccess && fold_vars)
+      e = cudaMemcpyAsync(d_pt, fold_point, (size_t)fold_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = lm::rows_mle_eval(c->stream, d_buf, n, t->elem_dim, fold_vars, d_pt, d_ev);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_evals, d_ev, (size_t)n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream);
   t->ctx->pool.free(d_idx);
   if (d_buf) t->ctx->pool.free(d_buf);
   if (e != cudaSuccess) return cuda_fail(e, "lm_open");
   return LM_OK;
+}
+
+int lm_open(lm_tree* t, const uint64_t* indices, uint32_t n, uint32_t* out_rows, uint32_t* out_paths) {
+  return open_impl(t, indices, n, out_rows, out_paths, nullptr, 0, nullptr);
+}
+
+int lm_open_fold(lm_tree* t, const uint64_t* indices, uint32_t n, const uint32_t* fold_point, uint32_t fold_vars, uint32_t* out_rows,
+                 uint32_t* out_paths, uint32_t* out_evals) {
+  if (!fold_point || !out_evals) return fail(LM_ERR_INVALID, "lm_open_fold: null argument");
+  return open_impl(t, indices, n, out_rows, out_paths, fold_point, fold_vars, out_evals);
 }
 
 int lm_tree_eval(lm_tree* t, const uint32_t* point, uint32_t out[5]) {

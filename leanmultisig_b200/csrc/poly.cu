@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "launch_count.h"
+#include "reduce.cuh"
 #include "kb.cuh"
 #include "poly.h"
 
@@ -281,6 +282,43 @@ cudaError_t access_count(cudaStream_t stream, const uint32_t* d_idx_col, uint64_
 cudaError_t counts_to_monty(cudaStream_t stream, uint32_t* d_counts, uint64_t n) {
   if (n == 0) return cudaSuccess;
   counts_to_monty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_counts, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// one CTA per opened leaf: the leaf in shared memory as extension elements, folded most-significant variable first
+__global__ void __launch_bounds__(256) rows_mle_eval_kernel(const uint32_t* __restrict__ rows, int dim, int k, const uint32_t* __restrict__ point,
+                                                            uint32_t* __restrict__ out) {
+  extern __shared__ uint32_t sm_row[];  // 2^k x 5
+  const uint32_t len = 1u << k;
+  const uint32_t* row = rows + (uint64_t)blockIdx.x * len * dim;
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 5; c++) sm_row[5 * i + c] = dim == 5 ? row[5 * i + c] : (c == 0 ? row[i] : 0u);
+  }
+  __syncthreads();
+  for (int v = 0; v < k; v++) {
+    const uint32_t half = len >> (v + 1);
+    const Ef x = ld_ef(point + 5 * v);
+    Ef res[1];
+    // every thread handles at most one pair per level for leaves up to 2^9 elements; larger leaves loop
+    for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+      const Ef lo = ld_ef_rw(sm_row + 5 * i), hi = ld_ef_rw(sm_row + 5 * (i + half));
+      res[0] = ef_add(lo, ef_mul(x, ef_sub(hi, lo)));
+      st_ef(sm_row + 5 * i, res[0]);  // in place: slot i is only read by its own thread at this level
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 5) out[5 * blockIdx.x + threadIdx.x] = sm_row[threadIdx.x];
+}
+
+cudaError_t rows_mle_eval(cudaStream_t stream, const uint32_t* d_rows, uint32_t n_rows, uint32_t dim, uint32_t k, const uint32_t* d_point,
+                          uint32_t* d_out) {
+  if (n_rows == 0) return cudaSuccess;
+  if ((dim != 1 && dim != 5) || k > 12) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)5 << k) * sizeof(uint32_t);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(rows_mle_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  rows_mle_eval_kernel<<<n_rows, 256, smem, stream>>>(d_rows, (int)dim, (int)k, d_point, d_out);
   count_launch();
   return cudaGetLastError();
 }

@@ -23,4 +23,8 @@ cudaError_t counts_to_monty(cudaStream_t stream, uint32_t* d_counts, uint64_t n)
 // n_cols base-field columns (host array of device pointers) at one point; d_out: n_cols x 5 words
 cudaError_t mle_eval_batch(cudaStream_t stream, const uint32_t* const* d_cols, const uint64_t* live_lens, uint32_t n_cols,
                            uint32_t n_vars, const uint32_t* d_point, uint32_t* d_scratch, uint32_t* d_out);
+// d_out[q] = MLE of row q (2^k elements of `dim` words, index MSB = first coordinate) at d_point (k x 5 words): the STIR answer of
+// an opened leaf (open.rs:161-190)
+cudaError_t rows_mle_eval(cudaStream_t stream, const uint32_t* d_rows, uint32_t n_rows, uint32_t dim, uint32_t k, const uint32_t* d_point,
+                          uint32_t* d_out);
 }  // namespace lm

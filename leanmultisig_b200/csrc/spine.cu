@@ -276,6 +276,45 @@ int lm_fs_state(const lm_fs* fs, uint32_t state[16], int* rate_fresh) {
   return LM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ WHIR round bookkeeping
+int lm_whir_stir_update(lm_sumcheck* sc, const uint64_t* idx, uint32_t n_q, uint32_t gen, uint32_t num_variables,
+                        const uint32_t comb[5], const uint32_t* ood_ys, const uint32_t* ood_answers, uint32_t n_ood,
+                        const uint32_t* stir_evals, uint32_t total_io[5]) {
+  if (!sc || !comb || !total_io || (n_q && (!idx || !stir_evals)) || (n_ood && (!ood_ys || !ood_answers)))
+    return lm_internal_fail(LM_ERR_INVALID, "lm_whir_stir_update: null argument");
+  const Ef c = ef_load(comb);
+  Ef total = ef_load(total_io), pw = EF_ONE;
+  std::vector<uint32_t> pt(5 * (size_t)num_variables);
+  for (uint32_t k = 0; k < n_ood; k++) {
+    // MultilinearPoint::expand_from_univariate (poly/src/point.rs:51-61): y, y^2, y^4, ...
+    Ef cur = ef_load(ood_ys + 5 * k);
+    for (uint32_t v = 0; v < num_variables; v++) {
+      ef_store(pt.data() + 5 * v, cur);
+      cur = lm::ef_mul(cur, cur);
+    }
+    if (int rc = lm_sc_add_eq(sc, 0, pt.data(), num_variables, pw.c)) return rc;
+    total = lm::ef_add(total, lm::ef_mul(pw, ef_load(ood_answers + 5 * k)));
+    pw = lm::ef_mul(pw, c);
+  }
+  if (n_q) {
+    // in-domain points gen^idx expanded to (x, x^2, x^4, ...) in the base field, one scalar comb^(n_ood + q) each
+    std::vector<uint32_t> pts((size_t)n_q * num_variables), scal(5 * (size_t)n_q);
+    for (uint32_t q = 0; q < n_q; q++) {
+      uint32_t y = kb_pow(gen, idx[q]);
+      for (uint32_t v = 0; v < num_variables; v++) {
+        pts[(size_t)q * num_variables + v] = y;
+        y = lm::kb_mul(y, y);
+      }
+      ef_store(scal.data() + 5 * q, pw);
+      total = lm::ef_add(total, lm::ef_mul(pw, ef_load(stir_evals + 5 * q)));
+      pw = lm::ef_mul(pw, c);
+    }
+    if (int rc = lm_sc_add_base_eq(sc, pts.data(), n_q, scal.data())) return rc;
+  }
+  ef_store(total_io, total);
+  return LM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ quotient GKR
 int lm_gkr_prove(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out_point, uint32_t out_claim_num[5],
                  uint32_t out_claim_den[5]) {

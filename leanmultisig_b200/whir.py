@@ -71,6 +71,17 @@ class Tree:
         check(lib().lm_open(self.handle, idx.ctypes.data_as(u64p), n, _p(rows), _p(paths)))
         return rows, paths
 
+    def open_fold(self, indices, fold_point):
+        """open() plus the STIR answer of every opened leaf: its multilinear evaluation at `fold_point` (lm_open_fold)"""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        pt = _u32(fold_point).reshape(-1, 5)
+        n = idx.size
+        rows = np.empty((n, self.full_width), dtype=np.uint32)
+        paths = np.empty((n, self.log_height, 8), dtype=np.uint32)
+        evals = np.empty((n, 5), dtype=np.uint32)
+        check(lib().lm_open_fold(self.handle, idx.ctypes.data_as(u64p), n, _p(pt), pt.shape[0], _p(rows), _p(paths), _p(evals)))
+        return rows, paths, evals
+
     def evaluate(self, point) -> np.ndarray:
         pt = _u32(point).reshape(-1, 5)
         out = np.empty(5, dtype=np.uint32)
@@ -125,6 +136,18 @@ class ProductSumcheck:
     def add_base_eq(self, points, scalars):
         pts, sc = _u32(points), _u32(scalars).reshape(-1, 5)
         check(lib().lm_sc_add_base_eq(self.handle, _p(pts), pts.shape[0], _p(sc)))
+
+    def stir_update(self, idx, gen_monty: int, comb, ood_ys, ood_answers, stir_evals, total):
+        """the weight update closing a WHIR round (lm_whir_stir_update); returns the new running sum (Montgomery words)"""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        oy = _u32(ood_ys).reshape(-1, 5)
+        oa = _u32(ood_answers).reshape(-1, 5)
+        se = _u32(stir_evals).reshape(-1, 5)
+        tot = _u32(total).copy()
+        check(lib().lm_whir_stir_update(self.handle, idx.ctypes.data_as(u64p), idx.size, int(gen_monty), self.n_vars, _p(_u32(comb)),
+                                        _p(oy) if oy.size else None, _p(oa) if oa.size else None, oy.shape[0],
+                                        _p(se) if se.size else None, _p(tot)))
+        return tot
 
     def round(self):
         c0, c2 = np.empty(5, dtype=np.uint32), np.empty(5, dtype=np.uint32)
@@ -395,6 +418,54 @@ class WhirProver:
         pts, answers = _sample_ood(prover_state, cfg.commitment_ood_samples, cfg.num_variables, tree.evaluate)
         return Witness(tree, pts, answers)
 
+    @staticmethod
+    def _open_fold(tree, idx, fold_point):
+        """(rows, paths, STIR answers) of the queried leaves; trees without a device fold (the sharded first tree) fold on the host"""
+        if hasattr(tree, "open_fold"):
+            return tree.open_fold(idx, fold_point)
+        from . import field as F
+
+        rows, paths = tree.open(idx)
+        ff = fold_point.shape[0]
+        leaves = F.np_from_monty(rows)
+        if tree.elem_dim == 5:
+            leaves = leaves.reshape(len(idx), 1 << ff, 5)
+        else:
+            z = np.zeros((len(idx), 1 << ff, 5), dtype=np.uint64)
+            z[:, :, 0] = leaves
+            leaves = z
+        ev = F.np_mle_eval_rows(leaves, [F.from_monty(x) for x in fold_point])
+        return rows, paths, F.np_to_monty(ev)
+
+    @staticmethod
+    def _stir_update(sc, idx, gen, comb_m, ood_points, ood_answers, stir_evals, total, num_variables):
+        """open.rs:192-231; sessions without the C++ entry (compute doubles of the CPU test tier) take the host path"""
+        from . import field as F
+
+        if getattr(sc, "stir_update", None) is not None and not getattr(sc, "host_stir_update", False):
+            oa = np.array(ood_answers, dtype=np.uint32).reshape(-1, 5)
+            return F.from_monty(sc.stir_update(idx, gen, comb_m, _points_to_monty(ood_points), oa, stir_evals, F.to_monty(total)))
+        comb = F.from_monty(comb_m)
+        g = gen * F._RINV % F.P
+        p64, r64 = np.uint64(F.P), np.uint64(F._R)
+        y = np.array([pow(g, int(i), F.P) for i in idx], dtype=np.uint64)      # canonical, < 2^31: products fit in u64
+        stir_pts = np.empty((len(idx), num_variables), dtype=np.uint32)
+        for k in range(num_variables):
+            stir_pts[:, k] = (y * r64) % p64
+            y = (y * y) % p64
+        powers = [F.ONE]
+        for _ in range(len(ood_points) + len(idx)):
+            powers.append(F.mul(powers[-1], comb))
+        for k, (yk, ans) in enumerate(zip(ood_points, ood_answers)):
+            sc.add_eq(0, _points_to_monty(_expand_from_univariate(yk, num_variables)), F.to_monty(powers[k]))
+            total = F.add(total, F.mul(powers[k], F.from_monty(ans)))
+        stir_rand = powers[len(ood_points):len(ood_points) + len(idx)]
+        if len(idx):
+            sc.add_base_eq(stir_pts, _points_to_monty(stir_rand))
+        for rnd, ev in zip(stir_rand, F.np_from_monty(_u32(stir_evals).reshape(-1, 5))):
+            total = F.add(total, F.mul(rnd, tuple(int(x) for x in ev)))
+        return total
+
     def _session(self, witness: Witness):
         """the product-sumcheck session over the committed polynomial (the sharded prover overrides this)"""
         return self.ctx.sumcheck_from_tree(witness.tree)
@@ -490,40 +561,15 @@ class WhirProver:
             ps.pow_grinding(rp.query_pow_bits)
             lap("ood + query PoW")
             idx = ps.sample_in_range(log_folded, rp.num_queries)
-            rows, paths = tree.open(idx)
+            # openings + STIR answers: each opened leaf folded at this round's challenges, on the device (open.rs:161-190)
+            fold_pt = _points_to_monty(randomness[len(randomness) - ff:])
+            rows, paths, stir_evals = self._open_fold(tree, idx, fold_pt)
             ps.hint_merkle_paths([(rows[q], paths[q], i) for q, i in enumerate(idx)])
             lap("openings")
-            # STIR answers: each opened leaf folded at this round's challenges (open.rs:161-190)
-            dim = tree.elem_dim
-            leaves = F.np_from_monty(rows)
-            if dim == 5:
-                leaves = leaves.reshape(len(idx), 1 << ff, 5)
-            else:
-                z = np.zeros((len(idx), 1 << ff, 5), dtype=np.uint64)
-                z[:, :, 0] = leaves
-                leaves = z
-            stir_evals = F.np_mle_eval_rows(leaves, randomness[len(randomness) - ff:])
-            # in-domain points gen^i expanded to (x, x^2, x^4, ...), base field
-            g = gen * F._RINV % F.P
-            p64, r64 = np.uint64(F.P), np.uint64(F._R)
-            y = np.array([pow(g, i, F.P) for i in idx], dtype=np.uint64)      # canonical, < 2^31: products fit in u64
-            stir_pts = np.empty((len(idx), num_variables), dtype=np.uint32)
-            for k in range(num_variables):
-                stir_pts[:, k] = (y * r64) % p64
-                y = (y * y) % p64
             ps.duplex()
-            comb = F.from_monty(ps.sample())
-            powers = [F.ONE]
-            for _ in range(len(ood_points) + len(idx)):
-                powers.append(F.mul(powers[-1], comb))
-            for k, (y, ans) in enumerate(zip(ood_points, ood_answers)):
-                sc.add_eq(0, _points_to_monty(_expand_from_univariate(y, num_variables)), F.to_monty(powers[k]))
-                total = F.add(total, F.mul(powers[k], F.from_monty(ans)))
-            stir_rand = powers[len(ood_points):len(ood_points) + len(idx)]
-            if len(idx):
-                sc.add_base_eq(stir_pts, _points_to_monty(stir_rand))
-            for rnd, ev in zip(stir_rand, stir_evals):
-                total = F.add(total, F.mul(rnd, tuple(int(x) for x in ev)))
+            comb = ps.sample()
+            # combination randomness, OOD + in-domain constraints into the weights, running sum (open.rs:192-231) in C++
+            total = self._stir_update(sc, idx, gen, comb, ood_points, ood_answers, stir_evals, total, num_variables)
             lap("STIR answers + weights update")
             r, total = self._rounds(sc, ps, ff_next, rp.folding_pow_bits, total)
             lap("sumcheck rounds (incl. PoW)")
