@@ -1,0 +1,140 @@
+"""Exact comparisons with the oracle AT THE BENCHMARK SIZES (round-2 verdict, item 2): the largest exact comparisons of the
+other test files stop at 2^15 - 2^18, which leaves the index-width, grid-cap, multi-pass and arena paths of the sizes that
+bench.py measures untested.  Everything here is bit-exact: same seeded inputs, oracle (CPU restatement of the reference)
+on one side, CUDA path through the C ABI on the other."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle as O
+from leanmultisig_b200 import field as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8)).hexdigest()
+
+
+def test_commit_2_22_x_64_equals_oracle():
+    """BASELINE config 2 itself: root, the whole 1 GiB codeword and all 2^23 - 1 digests (merkle.rs:215-288, dft.rs:79-144)."""
+    import leanmultisig_b200 as lm
+
+    ctx = lm.Context(0, 24)
+    n_vars, k, r = 28, 7, 1
+    live = 1 << 27
+    ev = np.random.default_rng(0).integers(0, O.P, size=live, dtype=np.uint32)
+    full = np.zeros(1 << n_vars, dtype=np.uint32)
+    full[:live] = ev
+    cw = O.reorder_and_dft(full, n_vars, 1, k, r, 64)
+    del full
+    layers = O.merkle_tree(cw, 128, 64)
+    tree = ctx.commit(ev, n_vars, k, r, actual_len=live)
+    assert tree.height == 1 << 22 and tree.stored_width == 64
+    assert np.array_equal(tree.root, layers[-1])
+    assert _sha(tree.codeword()) == _sha(cw)
+    assert _sha(tree.layers()) == _sha(layers)
+    idx = [0, 1, (1 << 22) - 1, 123456]
+    rows, paths = tree.open(idx)
+    for q, i in enumerate(idx):
+        orow, opath = O.merkle_open(cw, 128, layers, i)
+        assert np.array_equal(rows[q], orow) and np.array_equal(paths[q], opath)
+    tree.free()
+    ctx.close()
+
+
+def test_air_execution_2_20_rows_equals_oracle():
+    """every round's raw evaluations and the final column evaluations of the execution-table sumcheck at 2^20 rows (all five
+    kernel variants: base pairs, the two on-the-fly base folds, fused extension folds, and the one-CTA rounds)"""
+    import leanmultisig_b200 as lm
+
+    rng = np.random.default_rng(21)
+    L = 20
+    n = 1 << L
+    cols = O.random_field(rng, (20, n))
+    cols[:, n - 5000:] = O.random_field(rng, 20)[:, None]  # padding rows repeat one row, as the reference's tables do
+    cur = np.concatenate([cols, np.stack([O.shift_column(cols[0]), O.shift_column(cols[1])])])
+    eqf, la, beta = O.random_field(rng, (L, 5)), O.random_field(rng, (8, 5)), O.random_field(rng, 5)
+    ap = [np.array([int(O.to_monty(1)), 0, 0, 0, 0], dtype=np.uint32)]
+    alpha = O.random_field(rng, 5)
+    for _ in range(13):
+        ap.append(O.ef_mul(ap[-1], alpha))
+    ap = np.stack(ap)
+    challenges = O.random_field(rng, (L, 5))
+    ctx = lm.Context(0, 20)
+    sess = lm.AirSumcheckSession(ctx, 0, list(cols), eqf, np.zeros(5, dtype=np.uint32), ap, la, beta)
+    for r in range(L):
+        want = O.air_exec_round(cur, eqf[: L - r - 1], ap, la, beta)
+        got = sess._raw_round()
+        assert np.array_equal(got, want), f"round {r}"
+        sess._fold(challenges[r])
+        cur = np.stack([O.fold_lsb(cur[c], challenges[r]) for c in range(22)])
+    assert np.array_equal(sess.final_column_evals(), cur[:, 0, :])
+    sess.free()
+    ctx.close()
+
+
+def test_gkr_2_20_fractions_equals_oracle():
+    """whole prove_gkr_quotient at 2^20 fractions: the transcript of the device-resident challenger equals the oracle CPU
+    prover's word for word, and the oracle verifier accepts it"""
+    import leanmultisig_b200 as lm
+    from oracle import logup as OL
+    from oracle import whir as W
+
+    rng = np.random.default_rng(22)
+    n_vars, active = 20, (1 << 20) - 4321
+    nums, dens = O.random_field(rng, active), O.random_field(rng, (active, 5))
+    ps_o = W.ProverState()
+    q_o, pt_o, cn_o, cd_o = OL.prove_gkr_quotient_cpu(ps_o, nums, dens)
+    ctx = lm.Context(0, 20)
+    g = lm.GkrQuotientProver(ctx, nums, dens)
+    ps = lm.NativeProverState(ctx)
+    q, pt, cn, cd = g.prove_native(ps)
+    g.free()
+    assert ps.transcript == ps_o.transcript
+    assert np.array_equal(q, W.tm(q_o)) and np.array_equal(cn, W.tm(cn_o)) and np.array_equal(cd, W.tm(cd_o))
+    vs = W.VerifierState(ps.transcript, [])
+    OL.verify_gkr_quotient(vs, n_vars)
+    assert vs.off == len(ps.transcript)
+    ps.free()
+    ctx.close()
+
+
+def test_product_sumcheck_2_22_equals_oracle():
+    """WHIR's product sumcheck at 2^22 entries: statement weights (eq, next and STIR base-field equalities), every round's
+    (c0, c2) and the folded tables against the oracle"""
+    import leanmultisig_b200 as lm
+
+    rng = np.random.default_rng(23)
+    n = 22
+    p = O.random_field(rng, 1 << n)
+    w = np.zeros((1 << n, 5), dtype=np.uint32)
+    ctx = lm.Context(0, 20)
+    sc = ctx.sumcheck(p, n)
+    for sel_bits, is_next in ((0, False), (3, False), (2, True)):
+        m = n - sel_bits
+        pt, scal = O.random_field(rng, (m, 5)), O.random_field(rng, 5)
+        sel = int(rng.integers(0, 1 << sel_bits)) if sel_bits else 0
+        if is_next:
+            O.weights_add_next(w, sel, pt, scal)
+            sc.add_next(sel, pt, scal)
+        else:
+            O.weights_add_eq(w, sel, pt, scal)
+            sc.add_eq(sel, pt, scal)
+    cur_p, cur_w = p, w
+    pending = None
+    for rnd in range(8):
+        c0, c2 = sc.round() if pending is None else sc.fold_round(pending)
+        o0, o2 = O.prod_round(cur_p, cur_w)
+        assert np.array_equal(c0, o0) and np.array_equal(c2, o2), f"round {rnd}"
+        pending = O.random_field(rng, 5)
+        cur_p, cur_w = O.fold_msb(cur_p, pending), O.fold_msb(cur_w, pending)
+    sc.fold(pending)
+    pts, scal = O.random_field(rng, (33, n - 8)), O.random_field(rng, (33, 5))
+    O.weights_add_base_eq(cur_w, pts, scal)
+    sc.add_base_eq(pts, scal)
+    gp, gw = sc.read()
+    assert np.array_equal(gp, cur_p) and np.array_equal(gw, cur_w)
+    sc.free()
+    ctx.close()
