@@ -217,3 +217,160 @@ def test_gpu_sharded_product_sumcheck_threads(rng, world, n_vars, folding, live_
         for k, ((c0, c2), (e0, e2)) in enumerate(zip(rounds, expected)):
             assert np.array_equal(c0, e0) and np.array_equal(c2, e2), f"round {k}"
         assert np.array_equal(gp, p) and np.array_equal(gw, w)
+
+
+# ---- the row-sharded COMMIT and WHIR commit + open with the real CudaBackend ------------------------------------------
+class TorchLikeThreadDist(ThreadDist):
+    """torch.distributed's collectives (the subset CudaBackend / sharded.py call) between the rank-threads of one process:
+    tensors live on the one device, so a collective is a synchronise + device-to-device copies around two barriers."""
+
+    class ReduceOp:
+        SUM, MIN = "sum", "min"
+
+    def _sync(self):
+        import torch
+
+        torch.cuda.synchronize()
+
+    def barrier(self):
+        self._sync()
+        self.group.barrier.wait()
+
+    def all_gather_object(self, out_list, obj):
+        out_list[:] = self.group.exchange(self.rank, obj)
+
+    def all_reduce(self, t, op="sum"):
+        import torch
+
+        self._sync()
+        parts = self.group.exchange(self.rank, t.clone())
+        acc = torch.stack(parts)
+        t.copy_(acc.min(dim=0).values if op == "min" else acc.sum(dim=0))
+        self._sync()
+        self.group.barrier.wait()
+
+    def all_gather_into_tensor(self, out, t):
+        import torch
+
+        self._sync()
+        parts = self.group.exchange(self.rank, t)
+        out.copy_(torch.stack(parts).reshape(out.shape))
+        self._sync()
+        self.group.barrier.wait()
+
+    def all_to_all_single(self, out, inp):
+        self._sync()
+        parts = self.group.exchange(self.rank, inp)
+        world = self.group.world
+        chunk = inp.shape[0] // world
+        for q in range(world):
+            out[q * chunk:(q + 1) * chunk].copy_(parts[q][self.rank * chunk:(self.rank + 1) * chunk])
+        self._sync()
+        self.group.barrier.wait()
+
+
+def run_cuda_ranks(world, fn):
+    """fn(CudaBackend, dist, rank) on `world` threads of this process, one library context and one torch stream each"""
+    import leanmultisig_b200 as lm
+    from leanmultisig_b200.sharded import CudaBackend
+
+    group, results, errors = ThreadGroup(world), [None] * world, []
+
+    def body(rank):
+        try:
+            ctx = lm.Context(0, 20)
+            try:
+                backend = CudaBackend(ctx)
+                backend.scatter_dft = None  # CUDA IPC cannot map a buffer into its own process: all-to-all exchange path
+                results[rank] = fn(backend, TorchLikeThreadDist(group, rank), rank)
+                backend.torch.cuda.synchronize()
+            finally:
+                ctx.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            group.barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n_vars,folding,live_cols", [(2, 13, 4, 16), (4, 15, 5, 20), (8, 19, 7, 64)])
+def test_gpu_sharded_commit_threads(rng, world, n_vars, folding, live_cols):
+    """ShardedCommit (local transform, exchange, last layers, subtree forest, root all-gather, replicated top) with the
+    CUDA backend on a single device: root, every rank's codeword runs and openings equal the single-process oracle commit"""
+    from leanmultisig_b200.sharded import ShardedCommit, shard_of
+
+    chunk = 1 << (n_vars - folding)
+    ev = np.zeros(1 << n_vars, dtype=np.uint32)
+    ev[: live_cols * chunk] = O.random_field(rng, live_cols * chunk)
+    cw = O.reorder_and_dft(ev, n_vars, 1, folding, 1, live_cols)
+    layers = O.merkle_tree(cw, 1 << folding, live_cols)
+    h = cw.shape[0]
+    queries = [0, 1, h // 2 + 3, h - 1] + [int(x) for x in rng.integers(0, h, 6)]
+
+    def fn(backend, dist, rank):
+        sc = ShardedCommit(backend, dist, n_vars, folding, 1, live_cols=live_cols)
+        shard = shard_of(ev, n_vars, folding, rank, world).reshape(1 << folding, -1)[:live_cols].reshape(-1)
+        root = sc.commit(backend.to_device(shard))
+        mine = backend.to_host(sc.codeword)
+        geo = sc.geo
+        for m in range(world):  # block m of the local matrix = global rows m * block + rank * run ...
+            lo = m * geo.block + rank * geo.run
+            assert np.array_equal(mine[m * geo.run:(m + 1) * geo.run], cw[lo:lo + geo.run]), f"rank {rank} run {m}"
+        opened = {i: sc.open_local(i) for i in queries if geo.owner(i) == rank}
+        dist.barrier()
+        return np.asarray(root), opened
+
+    out = run_cuda_ranks(world, fn)
+    for root, opened in out:
+        assert np.array_equal(root, layers[-1])
+        for i, (row, path) in opened.items():
+            orow, opath = O.merkle_open(cw, 1 << folding, layers, i)
+            assert np.array_equal(row, orow) and np.array_equal(path, opath)
+    assert sorted(i for _, opened in out for i in opened) == sorted(set(queries))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,nv,live_frac_16", [(2, 12, 16), (4, 13, 8)])
+def test_gpu_sharded_whir_threads(world, nv, live_frac_16):
+    """ShardedWhirProver (sharded commit, OOD evaluation from the shards, sharded product sumcheck, owner-routed STIR
+    openings, replicated tail) with the CUDA backend on a single device: transcript, hints and final point equal the
+    single-process oracle prover's, the oracle verifier accepts"""
+    import leanmultisig_b200 as lm
+    from leanmultisig_b200 import whir_config as WC
+    from leanmultisig_b200.sharded import ShardedWhirProver, shard_of
+    from test_whir_protocol import SMALL, make_statements, oracle_prove, oracle_verify, to_product_statements
+
+    rs = np.random.default_rng(31 + nv + live_frac_16)
+    cfg_o, cfg_p = W.WhirConfig(nv, **SMALL), WC.WhirConfig(nv, **SMALL)
+    k = cfg_p.first_folding
+    live_cols = (1 << k) * live_frac_16 // 16
+    live = live_cols << (nv - k)
+    poly = O.random_field(rs, 1 << nv)
+    poly[live:] = 0
+    stm = make_statements(rs, poly, nv)
+    ps_o, point_o = oracle_prove(cfg_o, poly, stm, live)
+
+    def fn(backend, dist, rank):
+        ps = lm.ProverState(backend.ctx)
+        shard = shard_of(poly, nv, k, rank, world).reshape(1 << k, -1)[:live_cols].reshape(-1)
+        prover = ShardedWhirProver(backend, dist, cfg_p)
+        wit = prover.commit(ps, shard, live_cols)
+        point = prover.prove(ps, to_product_statements(stm), wit)
+        dist.barrier()
+        return ps.transcript, ps.merkle_paths, point
+
+    for transcript, paths, point in run_cuda_ranks(world, fn):
+        assert transcript == ps_o.transcript and point == point_o
+        assert len(paths) == len(ps_o.merkle_paths)
+        for ga, oa in zip(paths, ps_o.merkle_paths):
+            for (gl, gp, gi), (ol, op, oi) in zip(ga, oa):
+                assert gi == oi and np.array_equal(gl, ol) and np.array_equal(gp, op)
+        assert oracle_verify(cfg_o, transcript, paths, stm) == point
