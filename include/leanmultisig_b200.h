@@ -408,6 +408,14 @@ int lm_gkr_prove_hostloop(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint
 int lm_air_prove_batched(lm_air* const* airs, uint32_t n_sessions, const uint32_t* eq_factors, const uint32_t* sums,
                          const uint32_t eta[5], lm_fs* fs, uint32_t* out_challenges, uint32_t* out_n_rounds);
 
+/* ---- proof wire format (csrc/wire.cpp, leanmultisig_b200/wire.py): host code -----------------------------------------
+ * The compression half of TypeOneMultiSignature::compress / decompress (crates/rec_aggregation/src/type_1_aggregation.rs:
+ * 81-89): lz4_flex::compress_prepend_size / decompress_size_prepended = 4-byte little-endian uncompressed length + one LZ4
+ * block.  lm_lz4_decompress_size_prepended with dst == NULL only reports the uncompressed length. */
+uint64_t lm_lz4_compress_bound(uint64_t n);
+int lm_lz4_compress_prepend_size(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, uint64_t* out_len);
+int lm_lz4_decompress_size_prepended(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, uint64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,10 +160,15 @@ def lib() -> C.CDLL:
             "lm_fs_set_state": [vp, u32p, i],
             "lm_air_prove_batched": [C.POINTER(vp), u32, u32p, u32p, u32p, vp, u32p, u32p],
         }
+        u8p = C.POINTER(C.c_uint8)
+        sig["lm_lz4_compress_prepend_size"] = [u8p, u64, u8p, u64, u64p]
+        sig["lm_lz4_decompress_size_prepended"] = [u8p, u64, u8p, u64, u64p]
         for name, args in sig.items():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        L.lm_lz4_compress_bound.argtypes = [u64]
+        L.lm_lz4_compress_bound.restype = C.c_uint64
         _lib = L
     return _lib
 

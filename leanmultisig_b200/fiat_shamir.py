@@ -106,6 +106,13 @@ class ProverState:
     def hint_merkle_paths(self, paths) -> None:
         self.merkle_paths.append(list(paths))
 
+    def into_proof(self):
+        """ProverState::into_proof (fiat-shamir/src/prover.rs:48-53): transcript + the query batches pruned as
+        hint_merkle_paths_base does (prover.rs:116-118, merkle_pruning.rs:18-84) -> wire.Proof (postcard / lz4 ready)"""
+        from .wire import Proof
+
+        return Proof.from_prover_state(self)
+
     # -- squeeze -----------------------------------------------------------------------------------------
     def sample_vec(self, n: int) -> list[np.ndarray]:
         fes = self.challenger.sample_many(-(-(n * 5) // RATE))[: n * 5]
@@ -174,6 +181,13 @@ class NativeProverState:
 
     def hint_merkle_paths(self, paths) -> None:
         self.merkle_paths.append(list(paths))
+
+    def into_proof(self):
+        """ProverState::into_proof (fiat-shamir/src/prover.rs:48-53): transcript + the query batches pruned as
+        hint_merkle_paths_base does (prover.rs:116-118, merkle_pruning.rs:18-84) -> wire.Proof (postcard / lz4 ready)"""
+        from .wire import Proof
+
+        return Proof.from_prover_state(self)
 
     def sample_vec(self, n: int) -> list[np.ndarray]:
         out = np.empty((max(n, 1), 5), dtype=np.uint32)

@@ -84,9 +84,9 @@ class ShardGeometry:
 class ShardedCommit:
     """Collective: every rank calls commit() with its shard; all ranks return the same root.
 
-    With the CUDA backend's fused exchange the codeword matrix of a rank is a buffer the OTHER ranks store into during a
-    commit (one buffer per shape, reused by the next commit of that shape): ranks that read their codeword or serve openings
-    after commit() must synchronise (dist.barrier()) before any rank starts the next commit of the same shape."""
+    With the CUDA backend's fused exchange the matrix the OTHER ranks store into during a commit is one buffer per shape,
+    reused by the next commit of that shape; `self.codeword` is a private copy taken before the commit's closing collective,
+    so a witness stays valid however many commits of the same shape follow (round-1 advisor finding)."""
 
     def __init__(self, backend, dist, n_vars: int, folding: int, log_inv_rate: int, live_cols: int | None = None):
         self.b, self.dist = backend, dist
@@ -123,6 +123,11 @@ class ShardedCommit:
         # 3. last g layers on the local rows
         if geo.g:
             b.dft_layers_mapped(mat, w, geo.log_h, geo.log_h - geo.g, self.world, geo.run, geo.block, self.rank * geo.run)
+        if scatter is not None:
+            # the exchange buffer is shared: the peers store the NEXT commit of this shape into it.  The witness keeps a
+            # private copy (1/G of the codeword, a device-to-device copy ordered before this commit's root all-gather, which
+            # no peer can pass - and hence start its next scatter - before this rank has reached it)
+            mat = b.private_copy(mat)
         mark("last_layers")
         self.codeword = mat
         # 4. the G subtrees of this rank as ONE forest: leaf digests of all local rows in one launch, then level by level
@@ -566,6 +571,9 @@ class CudaBackend:
     def empty_like(self, t):
         return self.torch.empty_like(t)
 
+    def private_copy(self, t):
+        return t.clone()
+
     def rows(self, t, start: int, count: int):
         return t[start:start + count]
 
@@ -584,26 +592,41 @@ class CudaBackend:
             import ctypes as C
 
             torch, lib = self.torch, self.lib
-            own = self.ctx.alloc(rows * cols * 4)
-            work = torch.empty((rows, cols), dtype=torch.int32, device="cuda")
             world, rank = dist.get_world_size(), dist.get_rank()
-            hbuf = C.create_string_buffer(64)
-            exported = lib.lm_dev_ipc_export(self.ctx.handle, own.ptr, hbuf) == 0
+            # every rank reaches the handle all-gather, whatever failed locally before it (an out-of-memory here must not
+            # leave the other ranks blocked in the collective): a failed rank contributes None
+            own = work = None
+            payload = None
+            try:
+                own = self.ctx.alloc(rows * cols * 4)
+                work = torch.empty((rows, cols), dtype=torch.int32, device="cuda")
+                hbuf = C.create_string_buffer(64)
+                if lib.lm_dev_ipc_export(self.ctx.handle, own.ptr, hbuf) == 0:
+                    payload = bytes(hbuf.raw)
+            except Exception:  # noqa: BLE001
+                payload = None
             handles = [None] * world
-            dist.all_gather_object(handles, bytes(hbuf.raw) if exported else None)  # every rank reaches this collective
+            dist.all_gather_object(handles, payload)
             if any(h is None for h in handles):
-                own.free()
-                raise RuntimeError("CUDA IPC export failed on a rank")
+                if own is not None:
+                    own.free()
+                raise RuntimeError("CUDA IPC export (or the exchange buffer allocation) failed on a rank")
             table = np.zeros(world, dtype=np.uint64)
             opened = []
-            for q in range(world):
-                if q == rank:
-                    table[q] = own.ptr.value
-                else:
-                    p = C.c_void_p()
-                    self.check(lib.lm_dev_ipc_open(self.ctx.handle, handles[q], C.byref(p)))
-                    table[q] = p.value
-                    opened.append(p)
+            try:
+                for q in range(world):
+                    if q == rank:
+                        table[q] = own.ptr.value
+                    else:
+                        p = C.c_void_p()
+                        self.check(lib.lm_dev_ipc_open(self.ctx.handle, handles[q], C.byref(p)))
+                        table[q] = p.value
+                        opened.append(p)
+            except Exception:
+                for p in opened:  # do not leak the mappings opened so far, nor the own buffer
+                    lib.lm_dev_ipc_close(self.ctx.handle, p)
+                own.free()
+                raise
 
             class _Raw:  # zero-copy torch view of the library allocation
                 __cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<i4", "data": (int(own.ptr.value), False),
@@ -694,7 +717,7 @@ class CudaBackend:
             first = False
         self.check(lib.lm_dev_merkle_levels(self.ctx.handle, forest.data_ptr(), geo.block))
         d_evals.record_stream(self._copy_stream)
-        return mat, forest
+        return self.private_copy(mat), forest  # the exchange buffer is reused by the next commit (see ShardedCommit.commit)
 
     def _flag(self):
         if not hasattr(self, "_flag_t"):
