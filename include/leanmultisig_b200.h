@@ -123,6 +123,12 @@ int lm_sc_new(lm_ctx* ctx, const uint32_t* evals, uint32_t n_vars, uint32_t elem
  * (open.rs:337-358) with selector 0 and m = n_vars. */
 int lm_sc_add_eq(lm_sumcheck* sc, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]);
 int lm_sc_add_next(lm_sumcheck* sc, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]);
+/* weights[base + (b << shift) + offset] += scalar * eq(point, b) for b < 2^pre (point: pre x 5 words, first coordinate = most
+ * significant bit of b).  The building block of the next-row statement (crates/backend/poly/src/next_mle.rs:35-58: term k has
+ * shift = k + 1, offset = 2^k) in the form a row-range SHARD of the weight table needs, where the index bits that select the
+ * shard are fixed and drop out of the local index (leanmultisig_b200/sharded.py). */
+int lm_sc_add_strided_eq(lm_sumcheck* sc, uint64_t base, uint32_t shift, uint64_t offset, const uint32_t* point, uint32_t pre,
+                         const uint32_t scalar[5]);
 /* add_new_base_equality (open.rs:360-382): w[x] += sum_q scalars[q] * eq(points[q], x); points: n_q x n_vars
  * base-field words, scalars: n_q x 5 */
 int lm_sc_add_base_eq(lm_sumcheck* sc, const uint32_t* points, uint32_t n_q, const uint32_t* scalars);

@@ -1004,6 +1004,24 @@ int lm_sc_add_next(lm_sumcheck* s, uint64_t selector, const uint32_t* point, uin
   return LM_OK;
 }
 
+int lm_sc_add_strided_eq(lm_sumcheck* s, uint64_t base, uint32_t shift, uint64_t offset, const uint32_t* point, uint32_t pre,
+                         const uint32_t scalar[5]) {
+  if (!s || !scalar || (pre && !point)) return fail(LM_ERR_INVALID, "lm_sc_add_strided_eq: null argument");
+  const uint64_t n = (uint64_t)1 << s->n_vars;
+  if (pre > s->n_vars || shift > 63 || pre + shift > 63 || offset >= n || base >= n ||
+      base + ((((uint64_t)1 << pre) - 1) << shift) + offset >= n)
+    return fail(LM_ERR_INVALID, "lm_sc_add_strided_eq: index set leaves the table");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  if (pre) {
+    int rc = sc_upload_point(s, point, 5 * pre);
+    if (rc != LM_OK) return rc;
+  }
+  CU(lm::weights_add_strided_eq(c->stream, s->d_w, base, shift, offset, c->d_point, pre, scalar));
+  CU(cudaStreamSynchronize(c->stream));
+  return LM_OK;
+}
+
 int lm_sc_add_base_eq(lm_sumcheck* s, const uint32_t* points, uint32_t n_q, const uint32_t* scalars) {
   if (!s || (n_q && (!points || !scalars))) return fail(LM_ERR_INVALID, "lm_sc_add_base_eq: null argument");
   if (n_q == 0) return LM_OK;

@@ -107,6 +107,37 @@ cudaError_t weights_add_next(cudaStream_t stream, uint32_t* d_w, uint64_t select
   return cudaGetLastError();
 }
 
+// w[base + (b << shift) + offset] += scalar * eq(pt[0 .. pre), b), b < 2^pre: the index set of one term of the next-row
+// polynomial (shift = k + 1, offset = 2^k) and of every restriction of such a term to a row-range shard, where some index
+// bits are fixed and drop out of the local index (leanmultisig_b200/sharded.py ShardedProductSumcheck.add_next)
+__global__ void weights_add_strided_eq_kernel(uint32_t* __restrict__ w, uint64_t base, int shift, uint64_t offset,
+                                              const uint32_t* __restrict__ pt, int pre, Ef scalar) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ((uint64_t)1 << pre)) return;
+  Ef acc = scalar;
+  for (int i = 0; i < pre; i++) {
+    Ef z = ld_ef(pt + 5 * i);
+    if (!((b >> (pre - 1 - i)) & 1)) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) z.c[c] = kb_neg(z.c[c]);
+      z.c[0] = kb_add(z.c[0], KB_R1);
+    }
+    acc = ef_mul(acc, z);
+  }
+  uint32_t* dst = w + 5 * (base + (b << shift) + offset);
+  st_ef(dst, ef_add(ld_ef_rw(dst), acc));
+}
+
+cudaError_t weights_add_strided_eq(cudaStream_t stream, uint32_t* d_w, uint64_t base, uint32_t shift, uint64_t offset,
+                                   const uint32_t* d_point, uint32_t pre, const uint32_t scalar[5]) {
+  Ef s;
+  for (int c = 0; c < 5; c++) s.c[c] = scalar[c];
+  const uint64_t n = (uint64_t)1 << pre;
+  weights_add_strided_eq_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_w, base, (int)shift, offset, d_point, (int)pre, s);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // ---- batched base-field equality (STIR queries): w[x] += sum_q s_q eq(pt_q, x), pt_q in F^m
 // tables: a[q][xh] = s_q * eq(pt_q[0..hi), xh)  (EF),  l[q][xl] = eq(pt_q[hi..m), xl)  (F)
 __global__ void base_eq_tables_kernel(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, int m,

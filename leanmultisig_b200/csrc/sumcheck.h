@@ -24,4 +24,6 @@ cudaError_t prod_round(cudaStream_t stream, const uint32_t* d_p, uint32_t dim, u
 cudaError_t prod_fold_round(cudaStream_t stream, const uint32_t* d_p, uint32_t dim, uint64_t live, const uint32_t* d_w,
                             uint64_t n, const uint32_t r[5], uint32_t* d_p_out, uint32_t* d_w_out, uint32_t* d_scratch,
                             uint32_t* d_out10);
+cudaError_t weights_add_strided_eq(cudaStream_t stream, uint32_t* d_w, uint64_t base, uint32_t shift, uint64_t offset,
+                                   const uint32_t* d_point, uint32_t pre, const uint32_t scalar[5]);
 }  // namespace lm

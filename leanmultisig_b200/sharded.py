@@ -402,6 +402,65 @@ class ShardedProductSumcheck:
         lpm = np.stack([F.to_monty(x) for x in lp]) if lp else np.zeros((0, 5), dtype=np.uint32)
         self.local.add_eq(sel, lpm, F.to_monty(F.mul(scale, F.from_monty(scalar))))
 
+    def add_next(self, selector: int, point, scalar) -> None:
+        """The next-row statement (SparseStatement::new_next, what the stacked-PCS opening emits for every table column,
+        sub_protocols/src/stacked_pcs.rs:73-82) on shards.  matrix_next_mle_folded (poly/src/next_mle.rs:35-58) is the sum of
+        m + 1 terms; term k lives on the inner indices x = (b << (k + 1)) | (1 << k) with weight
+        (1 - oc[m-k-1]) prod_{j >= m-k} oc[j] eq(oc[0 .. m-k-1), b), the last term on x = 2^m - 1 with weight prod_j oc[j].
+        On a row-range shard the g index bits that select the rank are constants: a term survives on this rank only if its
+        fixed bits agree with the rank's, the coordinates of b that fall on rank bits turn into scalar factors, and the
+        remaining index set is again of the strided form `add_strided_eq` takes."""
+        if self.rep is not None:
+            return self.rep.add_next(selector, point, scalar)
+        assert self.folds == 0, "statements are added before the first fold"
+        oc = [F.from_monty(x) for x in np.ascontiguousarray(point, dtype=np.uint32).reshape(-1, 5)]
+        m, g = len(oc), self.g
+        low = self.n_vars_total - self.folding - g
+        rank_pos = [(low + t, (self.rank >> t) & 1) for t in range(g)]          # (global bit position, required value)
+        sel_local = selector
+        for pos, bit in sorted(rank_pos, reverse=True):                          # rank bits inside the selector
+            if pos >= m:
+                if ((selector >> (pos - m)) & 1) != bit:
+                    return
+                b = pos - m
+                sel_local = ((sel_local >> (b + 1)) << b) | (sel_local & ((1 << b) - 1))
+        inner = [(pos, bit) for pos, bit in rank_pos if pos < m]
+        m_local = m - len(inner)
+        base = sel_local << m_local
+        s0 = F.from_monty(scalar)
+
+        def emit(shift, offset, pt, coeff):
+            ptm = np.stack([F.to_monty(x) for x in pt]) if pt else np.zeros((0, 5), dtype=np.uint32)
+            self.local.add_strided_eq(base, shift, offset, ptm, F.to_monty(coeff))
+
+        for k in range(m):
+            pre = m - k - 1
+            coeff = F.mul(s0, F.sub(F.ONE, oc[pre]))
+            for j in range(pre + 1, m):
+                coeff = F.mul(coeff, oc[j])
+            keep, ok = list(range(pre)), True
+            for pos, bit in inner:
+                if pos > k:                      # a bit of b: coordinate oc[m - 1 - pos]
+                    c = oc[m - 1 - pos]
+                    coeff = F.mul(coeff, c if bit else F.sub(F.ONE, c))
+                    keep.remove(m - 1 - pos)
+                elif pos == k:                   # the set bit of the pattern
+                    ok = ok and bit == 1
+                else:                            # one of the zero bits below it
+                    ok = ok and bit == 0
+            if not ok:
+                continue
+            below = sum(1 for pos, _ in inner if pos < k)
+            at = any(pos == k for pos, _ in inner)
+            shift = k + 1 - below - (1 if at else 0)
+            offset = 0 if at else 1 << (k - below)
+            emit(shift, offset, [oc[i] for i in keep], coeff)
+        if all(bit == 1 for _, bit in inner):     # the all-ones index (the last row repeats)
+            coeff = s0
+            for c in oc:
+                coeff = F.mul(coeff, c)
+            emit(0, (1 << m_local) - 1, [], coeff)
+
     def _reduce(self, c0, c2):
         if self.world == 1:
             return c0, c2
@@ -487,8 +546,9 @@ class ShardedWhirProver:
     of 5 words each), the first `first_folding` sumcheck rounds (ShardedProductSumcheck) and the STIR openings of the first
     tree (owner-routed) — runs on the shards; from the first fold on the tables are 2^first_folding times smaller and every
     rank continues on the ordinary single-device sessions (the first commit is >= 8x all later ones).  The host
-    logic is WhirProver.prove itself; every rank runs it with its own (identical) transcript.  Statements with next-row
-    weights (`is_next`) are not supported on shards."""
+    logic is WhirProver.prove itself; every rank runs it with its own (identical) transcript.  Next-row statements
+    (`is_next`, what the stacked-PCS opening emits for table columns) are restricted to the shards term by term
+    (ShardedProductSumcheck.add_next)."""
 
     def __init__(self, backend, dist, cfg):
         from .whir import WhirProver
@@ -537,7 +597,6 @@ class ShardedWhirProver:
         return w
 
     def prove(self, prover_state, statements, witness):
-        assert not any(s.is_next for s in statements), "next-row statements are not supported on shards"
         return self._prover.prove(prover_state, statements, witness)
 
 

@@ -133,6 +133,11 @@ class ProductSumcheck:
         pt = _u32(point).reshape(-1, 5)
         check(lib().lm_sc_add_next(self.handle, selector, _p(pt), pt.shape[0], _p(_u32(scalar))))
 
+    def add_strided_eq(self, base: int, shift: int, offset: int, point, scalar):
+        """w[base + (b << shift) + offset] += scalar * eq(point, b), b < 2^len(point)  (lm_sc_add_strided_eq)"""
+        pt = _u32(point).reshape(-1, 5)
+        check(lib().lm_sc_add_strided_eq(self.handle, base, shift, offset, _p(pt) if pt.size else None, pt.shape[0], _p(_u32(scalar))))
+
     def add_base_eq(self, points, scalars):
         pts, sc = _u32(points), _u32(scalars).reshape(-1, 5)
         check(lib().lm_sc_add_base_eq(self.handle, _p(pts), pts.shape[0], _p(sc)))

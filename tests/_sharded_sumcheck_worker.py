@@ -32,6 +32,15 @@ class OracleSumcheck:
     def add_eq(self, selector, point, scalar):
         O.weights_add_eq(self.w, selector, np.ascontiguousarray(point, dtype=np.uint32).reshape(-1, 5), scalar)
 
+    def add_next(self, selector, point, scalar):
+        O.weights_add_next(self.w, selector, np.ascontiguousarray(point, dtype=np.uint32).reshape(-1, 5), scalar)
+
+    def add_strided_eq(self, base, shift, offset, point, scalar):
+        pt = np.ascontiguousarray(point, dtype=np.uint32).reshape(-1, 5)
+        tab = O.eq_table(pt, np.ascontiguousarray(scalar, dtype=np.uint32)) if pt.shape[0] else np.ascontiguousarray(scalar, dtype=np.uint32)[None, :]
+        idx = base + (np.arange(tab.shape[0], dtype=np.int64) << shift) + offset
+        self.w[idx] = O.ef_add(self.w[idx], tab)
+
     def round(self):
         return O.prod_round(self.p, self.w)
 
@@ -80,12 +89,19 @@ def main():
     stmts = [(0, n_vars), (3 % (1 << folding), n_vars - folding), (5 % (1 << (n_vars - low)), low),
              (1, n_vars - 1), (2 % (1 << (n_vars - low - 1)), low + 1), (0, low - 1 if low > 1 else low)]
     stmts = [(sel % (1 << (n_vars - m)), m, O.random_field(rng, (m, 5)), O.random_field(rng, 5)) for sel, m in stmts]
+    # next-row statements (stacked_pcs.rs:73-82) of every position relative to the rank bits: point entirely below them, ending
+    # inside them, covering them, and covering the column bits too
+    nexts = [(0, n_vars), (1, n_vars - 1), (3 % (1 << folding), n_vars - folding), (5 % (1 << (n_vars - low)), low),
+             (2 % (1 << (n_vars - low - 1)), low + 1), (0, max(low - 1, 1)), (7 % (1 << (n_vars - low - g)), low + g)]
+    nexts = [(sel % (1 << (n_vars - m)), m, O.random_field(rng, (m, 5)), O.random_field(rng, 5)) for sel, m in nexts]
     n_rounds = folding + 3
     challenges = O.random_field(rng, (n_rounds, 5))
 
     ref = OracleSumcheck(ev)
     for sel, m, pt, sc in stmts:
         ref.add_eq(sel, pt, sc)
+    for sel, m, pt, sc in nexts:
+        ref.add_next(sel, pt, sc)
     if mode == "gpu":
         import leanmultisig_b200 as lm
         from leanmultisig_b200.sharded import CudaBackend
@@ -98,6 +114,8 @@ def main():
     sc = ShardedProductSumcheck(backend, dist, shard, n_vars, folding)
     for sel, m, pt, s in stmts:
         sc.add_eq(sel, pt, s)
+    for sel, m, pt, s in nexts:
+        sc.add_next(sel, pt, s)
     got, exp = sc.round(), ref.round()
     assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]), f"rank {rank}: round 0 differs"
     for k in range(n_rounds):

@@ -85,7 +85,7 @@ def main():
     live = live_cols << (nv - k)
     poly = O.random_field(rng, 1 << nv)
     poly[live:] = 0
-    stm = make_statements(rng, poly, nv)
+    stm = make_statements(rng, poly, nv, with_next=True)  # incl. a next-row statement (stacked_pcs.rs:73-82)
     ps_o, point_o = oracle_prove(cfg_o, poly, stm, live)
 
     if mode == "gpu":

@@ -355,7 +355,7 @@ def test_gpu_sharded_whir_threads(world, nv, live_frac_16):
     live = live_cols << (nv - k)
     poly = O.random_field(rs, 1 << nv)
     poly[live:] = 0
-    stm = make_statements(rs, poly, nv)
+    stm = make_statements(rs, poly, nv, with_next=True)
     ps_o, point_o = oracle_prove(cfg_o, poly, stm, live)
 
     def fn(backend, dist, rank):
