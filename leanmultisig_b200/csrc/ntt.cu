@@ -14,9 +14,18 @@
 // (l0 = first layer of the pass); the first pass can gather straight from the evaluation vector, where column j
 // is the contiguous slice evals[j << (n - k) ..] with every value repeated 2^r times, so the first r layers
 // (identities on repeated data) are skipped.
+//
+// Tile movement.  In-place passes load their tile with TMA: the matrix is described to the hardware as a 3-D tensor
+// (column, row mod 2^l0, row div 2^l0), a tile is 2^L / 256 boxes of 8 columns x 1 x 256 rows, fetched by ONE elected
+// thread with cp.async.bulk.tensor into shared memory and signalled through an mbarrier; every pass writes its tile back
+// with TMA stores (cp.async.bulk.tensor global <- shared).  This replaces 16 cp.async + 16 st.global and their address
+// arithmetic per thread (the pass kernels are issue-slot bound, ncu 66-68 %): 2.31 -> 2.00 ms on the 2^22 x 64 transform.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_pipeline.h>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include "launch_count.h"
 #include "kb.cuh"
 #include "ntt.h"
@@ -87,10 +96,52 @@ constexpr int NTT_MAX_PEERS = 16;
 constexpr int TILE_COLS = 8;       // u32 columns per tile = 32 B per row
 constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory
 
-// 16-byte slot of (row j, half) inside the shared tile.  The XOR folds row bits 3..4 into the slot index so that the
-// 8 threads of an LDS.128 phase hit 8 distinct slots both for consecutive rows and for rows 8/16 apart (the
-// first register group of a pass); the un-swizzled layout was 2- to 4-way bank conflicted there (ncu: 50 %).
+// 16-byte slot of (row j, half) inside the shared tile: dense row-major, 32 B per row - the layout a TMA box has.
+// Layout study on the 2^22 x 64 transform (tools/sweep_ntt_tma.sh, profiles/r02_ntt_tma_sweep.txt): dense + TMA 2.00 ms, dense
+// or XOR-swizzled with cp.async loads / st.global stores 2.31-2.32 ms, i.e. once the tile moves by TMA the 4-way bank
+// conflicts of the first register group (rows 8 apart, 32-byte pitch) no longer decide the time.  TMA's own swizzle modes
+// cannot remove them at this row pitch: the 128-byte pattern needs 128-byte rows (a 32-byte inner box faults), the 32-byte
+// pattern does not touch the bits that conflict.
+#if defined(NTT_SWIZZLE_XOR)
 __device__ __forceinline__ int tile_slot(int j, int half) { return ((j << 1) | half) ^ (((j >> 3) & 3) << 1); }
+#else
+__device__ __forceinline__ int tile_slot(int j, int half) { return (j << 1) | half; }
+#endif
+
+// ---- TMA / mbarrier primitives (PTX ISA: cp.async.bulk.tensor, mbarrier) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  // bounded: a transaction count that never completes (a malformed tensor map) must fault, not hang the device
+  for (uint32_t spins = 0;; spins++) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+constexpr int NTT_TMA_LOAD = 1, NTT_TMA_STORE = 2;
+constexpr int NTT_BOX_ROWS = 256;  // TMA box dimensions are at most 256
 
 // One group of G layers (local layers lp .. lp+G-1) on the shared tile, radix 2^G in registers.
 // Work item = (u, half): rows j0 + q * 2^lp (q < 2^G) of 16-byte half `half`.
@@ -151,9 +202,13 @@ struct NttScatter {
 __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
 ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
                 int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift,
-                uint32_t tile0, uint32_t n_col_tiles, const uint32_t* __restrict__ tw_pass, const NttScatter sc) {
-  extern __shared__ uint4 tile[];  // [2^L][2] slots, then 2^L twiddle words
+                uint32_t tile0, uint32_t n_col_tiles, const uint32_t* __restrict__ tw_pass, const NttScatter sc,
+                const __grid_constant__ CUtensorMap tmap, int tma) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // [2^L][2] slots (TMA destination / source: 128-byte aligned), 2^L twiddle words, the mbarrier of the tile load
+  uint4* tile = reinterpret_cast<uint4*>(smem_raw);
   uint32_t* tw_s = reinterpret_cast<uint32_t*>(tile + ((size_t)2 << L));
+  uint64_t& tma_bar = *reinterpret_cast<uint64_t*>(tw_s + ((size_t)1 << L));
   const uint64_t col0 = (uint64_t)(tile0 + blockIdx.x % n_col_tiles) * TILE_COLS;  // column tile varies fastest: CTAs that
   const uint64_t grp = blockIdx.x / n_col_tiles;                           // run together cover whole rows
   // rows of this tile: row(j) = ((grp >> l0) << (l0 + L)) + (grp & (2^l0 - 1)) + j * 2^l0
@@ -162,7 +217,16 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
   const int n_rows = 1 << L;
   const bool two_halves = col0 + 8 <= w;  // w % 4 == 0 guaranteed by the launcher
 
-  if (src == nullptr) {
+  const int box_rows = n_rows < NTT_BOX_ROWS ? n_rows : NTT_BOX_ROWS;
+  const int row_hi0 = (int)((grp >> l0) << L);  // coordinate of the tile's first row in the (row div 2^l0) dimension
+  if (src == nullptr && (tma & NTT_TMA_LOAD)) {
+    if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&tma_bar, (uint32_t)n_rows * 32u);
+      for (int t = 0; t < n_rows; t += box_rows) tma_load_3d(tile + 2 * t, &tmap, (int)col0, (int)row_lo, row_hi0 + t, &tma_bar);
+    }
+  } else if (src == nullptr) {
     for (int item = threadIdx.x; item < 2 * n_rows; item += blockDim.x) {
       const int j = item >> 1, half = item & 1;
       if (half == 0 || two_halves) {
@@ -215,7 +279,10 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
     }
     tw_s[k] = t;
   }
-  if (src == nullptr) __pipeline_wait_prior(0);
+  if (src == nullptr && (tma & NTT_TMA_LOAD))
+    mbar_wait(&tma_bar, 0);
+  else if (src == nullptr)
+    __pipeline_wait_prior(0);
   __syncthreads();
 
   int lp = skip;
@@ -232,6 +299,16 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
     __syncthreads();
   }
 
+  if ((tma & NTT_TMA_STORE) && !sc.enabled) {
+    // generic-proxy writes of the butterflies -> visible to the async proxy, then one thread hands the tile to TMA
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < n_rows; t += box_rows) tma_store_3d(&tmap, (int)col0, (int)row_lo, row_hi0 + t, tile + 2 * t);
+      tma_store_commit_wait();
+    }
+    return;
+  }
   for (int item = threadIdx.x; item < 2 * n_rows; item += blockDim.x) {
     const int j = item >> 1, half = item & 1;
     if (half == 1 && !two_halves) continue;
@@ -347,6 +424,35 @@ cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, 
 }
 
 // col_tile0 / n_tiles: restrict the pass kernels to a range of 8-column tiles (n_tiles == 0: all of them)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links only the static runtime)
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encode_fn() {
+  static TmaEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TmaEncodeFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+// the h x w matrix as the tensor (column, row mod 2^l0, row div 2^l0); box = 8 columns x 1 x min(2^L, 256) rows, dense in shared memory
+static bool tma_make_map(CUtensorMap* map, uint32_t* d_mat, uint64_t h, uint64_t w, int l0, int L) {
+  const cuuint64_t dims[3] = {w, (cuuint64_t)1 << l0, h >> l0};
+  const cuuint64_t strides[2] = {w * 4, (w * 4) << l0};  // bytes, dimensions 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)TILE_COLS, 1, (cuuint32_t)((1 << L) < NTT_BOX_ROWS ? (1 << L) : NTT_BOX_ROWS)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
+  return tma_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_mat, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32_t* d_src, uint32_t log_block,
                               uint32_t r, uint64_t h, uint64_t w, int skip, const uint32_t* d_tw, unsigned tw_log_n,
                               uint32_t col_tile0 = 0, uint32_t n_tiles = 0, const NttScatter* scatter = nullptr) {
@@ -367,9 +473,16 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG) * 36);
+    cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG) * 36 + 16);
     attr_set = true;
   }
+#if defined(NTT_SWIZZLE_XOR)
+  const bool tma_allowed = false;  // the XOR layout is not a TMA box
+#else
+  const bool tma_allowed = getenv("LM_NTT_NO_TMA") == nullptr;
+#endif
+  const bool tma_ok = tma_allowed && tma_encode_fn() != nullptr && (reinterpret_cast<uintptr_t>(d_mat) & 15) == 0 &&
+                      h < ((uint64_t)1 << 31) && w < ((uint64_t)1 << 31);
   // split log_h layers into ceil(log_h / 11) passes of nearly equal depth
   const int n_pass = (log_h + MAX_TILE_LOG - 1) / MAX_TILE_LOG;
   int l0 = 0, skip_left = skip;
@@ -379,14 +492,18 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     skip_left -= sk;
     const uint32_t tiles = n_tiles ? n_tiles : (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
     const uint64_t n_cta = (uint64_t)tiles * (h >> L);
-    const size_t smem = ((size_t)1 << L) * 36;  // tile + per-CTA twiddles
+    const size_t smem = ((size_t)1 << L) * 36 + 16;  // tile + per-CTA twiddles + mbarrier
     // compact twiddles of this pass, in the scratch words behind the big table (ntt.h: NTT_TW_SCRATCH_WORDS)
     uint32_t* tw_pass = const_cast<uint32_t*>(d_tw) + ((size_t)1 << (tw_log_n - 1)) + (size_t)(p % 4) * ((size_t)1 << MAX_TILE_LOG);
     ntt_pass_twiddles_kernel<<<((1 << L) + 255) / 256, 256, 0, stream>>>(tw_pass, log_h, l0, L, d_tw, tw_shift); count_launch();
     NttScatter sc{};
     if (scatter && p == n_pass - 1) sc = *scatter;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int tma = 0;
+    if (tma_ok && tma_make_map(&tmap, d_mat, h, w, l0, L)) tma = NTT_TMA_LOAD | NTT_TMA_STORE;
     ntt_pass_kernel<<<(unsigned)n_cta, NTT_THREADS, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
-                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass, sc); count_launch();
+                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass, sc, tmap, tma); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     l0 += L;
