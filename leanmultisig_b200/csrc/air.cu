@@ -25,6 +25,7 @@
 // and the transcript (air_sumcheck.rs:250-266).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 #include "air.h"
 #include "air_values.cuh"
@@ -327,6 +328,230 @@ air_exec_round_kernel(const __grid_constant__ AirExecArgs A, const __grid_consta
   if (tid == 0) A.d->counter = 0;
 }
 
+
+// ---- round 1 in the base field --------------------------------------------------------------------------------------
+// After ONE fold the table's values are a + r0 b with a, b in the base field.  At an evaluation point z every column is
+// P(z) + r0 Q(z) with P, Q base-field rows, so every constraint is a polynomial in r0 of degree <= 5 with BASE-FIELD
+// coefficients: the 21 extension products of the constraint code become small polynomial products over the base field
+// (140 base multiplications with delayed reduction instead of 21 x 25), and sum_k alpha^k C_k = sum_{k,i} (alpha^k r0^i)
+// c_{k,i} is the same delayed accumulation as before against weights the host multiplied by the powers of r0.  Same field
+// elements as evaluating in the extension field (exact arithmetic); ~1.3 k instead of ~5.6 k instructions per (pair, z) for
+// the round that is half of all extension work of a session.
+template <int N>
+struct Pl {  // c[0] + c[1] t + ... + c[N-1] t^(N-1)
+  uint32_t c[N];
+};
+template <int N, int M>
+__device__ __forceinline__ Pl<(N > M ? N : M)> operator+(const Pl<N>& a, const Pl<M>& b) {
+  Pl<(N > M ? N : M)> r;
+#pragma unroll
+  for (int i = 0; i < (N > M ? N : M); i++) r.c[i] = i < N ? (i < M ? kb_add(a.c[i], b.c[i]) : a.c[i]) : b.c[i];
+  return r;
+}
+template <int N, int M>
+__device__ __forceinline__ Pl<(N > M ? N : M)> operator-(const Pl<N>& a, const Pl<M>& b) {
+  Pl<(N > M ? N : M)> r;
+#pragma unroll
+  for (int i = 0; i < (N > M ? N : M); i++) r.c[i] = i < N ? (i < M ? kb_sub(a.c[i], b.c[i]) : a.c[i]) : kb_neg(b.c[i]);
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Pl<N> operator-(const Pl<N>& a) {
+  Pl<N> r;
+#pragma unroll
+  for (int i = 0; i < N; i++) r.c[i] = kb_neg(a.c[i]);
+  return r;
+}
+// product with one reduction per output coefficient
+template <int N, int M>
+__device__ __forceinline__ Pl<N + M - 1> operator*(const Pl<N>& a, const Pl<M>& b) {
+  Pl<N + M - 1> r;
+#pragma unroll
+  for (int k = 0; k < N + M - 1; k++) {
+    uint64_t acc = 0;
+    int terms = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const int j = k - i;
+      if (j < 0 || j >= M) continue;
+      if (terms == 4) acc = kb_fold(acc), terms = 0;
+      acc = mad_wide(a.c[i], b.c[j], acc);
+      terms++;
+    }
+    r.c[k] = kb_canon(kb_redc_lazy(kb_fold(acc)));
+  }
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Pl<N> pl_sub_one(Pl<N> a) {
+  a.c[0] = kb_sub(a.c[0], KB_R1);
+  return a;
+}
+template <int N>
+__device__ __forceinline__ Pl<N> pl_add_one(Pl<N> a) {
+  a.c[0] = kb_add(a.c[0], KB_R1);
+  return a;
+}
+template <int N>
+__device__ __forceinline__ Pl<N> pl_dbl(const Pl<N>& a) { return a + a; }
+template <int N>
+__device__ __forceinline__ Pl<N> pl_halve(Pl<N> a) {
+#pragma unroll
+  for (int i = 0; i < N; i++) a.c[i] = kb_halve(a.c[i]);
+  return a;
+}
+
+struct AirExecConstsB1 {
+  EfRows w[17][6];  // weight of term t (AirExecConsts::w) times r0^i
+  Ef k0;
+};
+template <int N>
+__device__ __forceinline__ void mac_poly(AlphaAcc& acc, const EfRows (&w)[6], const Pl<N>& v) {
+#pragma unroll
+  for (int i = 0; i < N; i++) acc.mac(w[i], Fb{v.c[i]});
+}
+
+// the thread's staged point: word 2c = P_c(z), word 2c + 1 = Q_c(z)
+struct SmViewB1 {
+  const uint32_t* pt;
+  __device__ __forceinline__ Pl<2> operator()(int c) const { return Pl<2>{{pt[(2 * c) * EXEC_PAIRS], pt[(2 * c + 1) * EXEC_PAIRS]}}; }
+};
+
+// ExecutionTable::eval (execution/air.rs:56-130) on columns that are degree-1 polynomials in the first challenge
+__device__ __forceinline__ Ef exec_air_eval_b1(const SmViewB1& col, const AirExecConstsB1& X) {
+  AlphaAcc acc;
+  const Pl<2> fp = col(1);
+  const Pl<2> op_a = col(8), op_b = col(9), op_c = col(10);
+  const Pl<2> val_a = col(5), val_b = col(6), val_c = col(7);
+  const Pl<2> flag_a = col(11), flag_b = col(12), flag_c = col(13), flag_c_fp = col(14), flag_ab_fp = col(15);
+  const Pl<2> fp_op_a = fp + op_a, fp_op_b = fp + op_b, fp_op_c = fp + op_c;
+  const Pl<3> nu_a = val_a + flag_a * (op_a - val_a) + flag_ab_fp * (fp_op_a - val_a);
+  const Pl<3> nu_b = val_b + flag_b * (op_b - val_b) + flag_ab_fp * (fp_op_b - val_b);
+  const Pl<3> nu_c = val_c + flag_c * (op_c - val_c) + flag_c_fp * (fp_op_c - val_c);
+  const Pl<2> aux = col(18), mul = col(16), jump = col(17);
+  const Pl<3> aux2 = aux * aux;
+  const Pl<3> add = pl_dbl(aux) - aux2;
+  const Pl<3> deref = pl_halve(aux2 - aux);
+  const Pl<3> is_precompile = -pl_sub_one(add + mul + deref + jump);
+  mac_poly(acc, X.w[0], col(19));
+  mac_poly(acc, X.w[1], nu_a);
+  mac_poly(acc, X.w[2], nu_b);
+  mac_poly(acc, X.w[3], nu_c);
+  mac_poly(acc, X.w[4], is_precompile);
+  const Pl<2> om_a = -pl_sub_one(flag_a + flag_ab_fp);
+  const Pl<2> om_b = -pl_sub_one(flag_b + flag_ab_fp);
+  const Pl<2> om_c = -pl_sub_one(flag_c + flag_c_fp);
+  const Pl<2> addr_b = col(3);
+  mac_poly(acc, X.w[5], om_a * (col(2) - fp_op_a));
+  mac_poly(acc, X.w[6], om_b * (addr_b - fp_op_b));
+  mac_poly(acc, X.w[7], om_c * (col(4) - fp_op_c));
+  mac_poly(acc, X.w[8], add * (nu_b - (nu_a + nu_c)));
+  mac_poly(acc, X.w[9], mul * (nu_b - nu_a * nu_c));
+  mac_poly(acc, X.w[10], deref * (addr_b - (val_a + op_b)));
+  mac_poly(acc, X.w[11], deref * (val_b - nu_c));
+  const Pl<4> jc = jump * nu_a;
+  mac_poly(acc, X.w[12], jc * pl_sub_one(nu_a));
+  const Pl<2> pc_shift = col(20), fp_shift = col(21);
+  mac_poly(acc, X.w[13], jc * (pc_shift - nu_b));
+  mac_poly(acc, X.w[14], jc * (fp_shift - nu_c));
+  const Pl<4> njc = -pl_sub_one(jc);
+  mac_poly(acc, X.w[15], njc * (pc_shift - pl_add_one(col(0))));
+  mac_poly(acc, X.w[16], njc * (fp_shift - fp));
+  return acc.finish(X.k0);
+}
+
+// round 1 (one pending challenge on the base table): out[z] as in air_exec_round_kernel, columns staged as (P(z), Q(z))
+__global__ void __launch_bounds__(EXEC_THREADS, 3)
+air_exec_round_b1_kernel(const __grid_constant__ AirExecArgs A, const __grid_constant__ AirExecConstsB1 X) {
+  constexpr int W = 2 * EXEC_ALL;
+  constexpr int ZS = W * EXEC_PAIRS;
+  __shared__ uint32_t sm_pt[EXEC_DEG * ZS];  // 27.5 KiB
+  __shared__ uint32_t sm_eq[5 * EXEC_PAIRS];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ef acc = ef_zero();
+  const uint64_t pairs = (uint64_t)1 << A.m, n = A.n_base;
+  const EqView eqv(A.eq_tab, A.k, A.m);
+  // The evaluation is short (~1.3 k instructions), so the global loads of the NEXT 32 pairs are issued before the current ones
+  // are evaluated and land in registers meanwhile: item it = tid + 160 s, s < 5, is (column it >> 5, pair it & 31)
+  constexpr int SLOTS = ((EXEC_COLS + 1) * EXEC_PAIRS + EXEC_THREADS - 1) / EXEC_THREADS;
+  uint4 pre[SLOTS];
+  uint32_t pre_nx[SLOTS];
+  auto prefetch = [&](uint64_t j0) {
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; sl++) {
+      const int it = tid + sl * EXEC_THREADS;
+      const int c = it >> 5;
+      const uint64_t j = j0 + (it & 31);
+      pre[sl] = make_uint4(0, 0, 0, 0);
+      pre_nx[sl] = 0;
+      if (c < EXEC_COLS && j < pairs) {
+        pre[sl] = a_ldg4(A.base + (uint64_t)c * n + 4 * j);
+        if (c < 2) pre_nx[sl] = 4 * j + 4 < n ? __ldg(A.base + (uint64_t)c * n + 4 * j + 4) : A.halo[c];
+      }
+    }
+  };
+  const uint64_t stride = (uint64_t)gridDim.x * EXEC_PAIRS;
+  uint64_t j0 = (uint64_t)blockIdx.x * EXEC_PAIRS;
+  if (j0 < pairs) prefetch(j0);
+  for (; j0 < pairs; j0 += stride) {
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; sl++) {
+      const int it = tid + sl * EXEC_THREADS;
+      const int c = it >> 5, p = it & 31;
+      const uint64_t j = j0 + p;
+      if (it >= (EXEC_COLS + 1) * EXEC_PAIRS || j >= pairs) continue;
+      uint32_t* pt = sm_pt + p;
+      if (c < EXEC_COLS) {
+        // base rows 4j .. 4j+3 = (A0, A1, B0, B1): P(z) = A0 + z (B0 - A0), Q(z) = (A1 - A0) + z ((B1 - B0) - (A1 - A0))
+        const uint4 v = pre[sl];
+        stage_word(pt, ZS, 2 * c, v.x, v.z);
+        stage_word(pt, ZS, 2 * c + 1, kb_sub(v.y, v.x), kb_sub(v.w, v.z));
+        if (c < 2) {  // shifted column: rows 4j+1 .. 4j+4
+          const uint32_t nx = pre_nx[sl];
+          stage_word(pt, ZS, 2 * (EXEC_COLS + c), v.y, v.w);
+          stage_word(pt, ZS, 2 * (EXEC_COLS + c) + 1, kb_sub(v.z, v.y), kb_sub(nx, v.w));
+        }
+      } else {
+        const Ef e = eqv(j);
+#pragma unroll
+        for (int k = 0; k < 5; k++) sm_eq[k * EXEC_PAIRS + p] = e.c[k];
+      }
+    }
+    __syncthreads();
+    if (j0 + stride < pairs) prefetch(j0 + stride);
+    if (j0 + lane < pairs) {
+      Ef eq;
+#pragma unroll
+      for (int k = 0; k < 5; k++) eq.c[k] = sm_eq[k * EXEC_PAIRS + lane];
+      acc = ef_add(acc, ef_mul(exec_air_eval_b1(SmViewB1{sm_pt + warp * ZS + lane}, X), eq));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Ef o;
+#pragma unroll
+    for (int c = 0; c < 5; c++) o.c[c] = __shfl_down_sync(0xffffffffu, acc.c[c], off);
+    acc = ef_add(acc, o);
+  }
+  if (lane == 0) st_ef(A.partial + ((uint64_t)blockIdx.x * EXEC_DEG + warp) * 5, acc);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(&A.d->counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid < EXEC_DEG * 5) {
+    uint32_t s = 0;
+    for (uint32_t b = 0; b < gridDim.x; b++) s = kb_add(s, __ldcg(A.partial + (uint64_t)b * EXEC_DEG * 5 + tid));
+    A.d->out[tid / 5].c[tid % 5] = s;
+  }
+  if (tid == 0) A.d->counter = 0;
+}
+
 __global__ void air_exec_final_kernel(int mode, AirExecArgs A, uint32_t* out) {
   const int c = threadIdx.x;
   if (c >= EXEC_ALL) return;
@@ -373,7 +598,7 @@ static Ef host_ef(const uint32_t* p) {
 }
 
 cudaError_t air_exec_round(cudaStream_t stream, int mode, const AirExecArgs& a, const uint32_t* alpha_powers, const uint32_t* la,
-                           uint32_t n_la, const uint32_t beta[5]) {
+                           uint32_t n_la, const uint32_t beta[5], const uint32_t* r0_host) {
   if (n_la < 5 || mode < 0 || mode > AIR_E1) return cudaErrorInvalidValue;
   AirExecConsts X;
   const Ef a0 = host_ef(alpha_powers), be = host_ef(beta);
@@ -388,6 +613,24 @@ cudaError_t air_exec_round(cudaStream_t stream, int mode, const AirExecArgs& a, 
   uint64_t blocks = (pairs + EXEC_PAIRS - 1) / EXEC_PAIRS;
   if (blocks > (uint64_t)AIR_MAX_BLOCKS) blocks = AIR_MAX_BLOCKS;
   const unsigned g = (unsigned)blocks;
+  if (mode == AIR_B1 && r0_host && getenv("LM_AIR_B1_EXT") == nullptr) {
+    // round 1 with base-field polynomial arithmetic: weights times the powers of the first challenge
+    static AirExecConstsB1 Y;  // 3.7 KiB: keep it off the stack
+    const Ef r0 = host_ef(r0_host);
+    Ef pw[6];
+    pw[0] = Ef{{KB_R1, 0, 0, 0, 0}};
+    for (int i = 1; i < 6; i++) pw[i] = ef_mul(pw[i - 1], r0);
+    Ef wts[17];
+    for (int i = 0; i < 4; i++) wts[i] = ef_mul(a0b, host_ef(la + 5 * i));
+    wts[4] = a0;
+    for (int k = 1; k < 13; k++) wts[4 + k] = host_ef(alpha_powers + 5 * k);
+    for (int t = 0; t < 17; t++)
+      for (int i = 0; i < 6; i++) Y.w[t][i] = ef_rows(ef_mul(wts[t], pw[i]));
+    Y.k0 = X.k0;
+    air_exec_round_b1_kernel<<<g, EXEC_THREADS, 0, stream>>>(a, Y);
+    count_launch();
+    return cudaGetLastError();
+  }
   const size_t smem_b = (size_t)EXEC_DEG * EXEC_ALL * EXEC_PAIRS * sizeof(uint32_t);  // 13.75 KiB
   const size_t smem_ef = 5 * smem_b;                                                    // 68.75 KiB: three CTAs per SM
   static bool attr_set = false;

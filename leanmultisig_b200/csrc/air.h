@@ -40,8 +40,10 @@ struct AirExecArgs {
   AirDev* d;
 };
 // alpha_powers: >= 13 x 5, la: logup alphas (n_la x 5, first 4 and last used), beta: bus challenge (host arrays)
+// r0_host (5 words, may be nullptr): the first challenge, known to the host; with it round 1 (mode AIR_B1) runs in the base
+// field as polynomials in r0 (air.cu, "round 1 in the base field")
 cudaError_t air_exec_round(cudaStream_t stream, int mode, const AirExecArgs& a, const uint32_t* alpha_powers, const uint32_t* la,
-                           uint32_t n_la, const uint32_t beta[5]);
+                           uint32_t n_la, const uint32_t beta[5], const uint32_t* r0_host = nullptr);
 // the pending folds applied to the last rows: d_out[22][5]
 cudaError_t air_exec_final(cudaStream_t stream, int mode, const AirExecArgs& a, uint32_t* d_out);
 

@@ -200,6 +200,7 @@ struct lm_air {
   uint32_t src_log_rows = 0;  // rows of the table the next round reads
   uint32_t pending = 0;       // challenges not yet applied to it (base: <= 2, extension: <= 1)
   uint32_t halo[2] = {0, 0};
+  uint32_t r_host[5] = {0, 0, 0, 0, 0};  // the latest challenge (round 1 of the execution table runs on its powers)
   uint32_t* d_ef[2] = {nullptr, nullptr};
   size_t ef_words[2] = {0, 0};
   int src_buf = 0;
@@ -1437,7 +1438,7 @@ int lm_air_round(lm_air* a, uint32_t* out_evals) {
     lm::AirExecArgs A;
     int mode = 0;
     if (int rc = air_exec_args(a, &A, &mode, false)) return rc;
-    CU(lm::air_exec_round(c->stream, mode, A, a->alpha.data(), a->la.data(), (uint32_t)(a->la.size() / 5), a->beta));
+    CU(lm::air_exec_round(c->stream, mode, A, a->alpha.data(), a->la.data(), (uint32_t)(a->la.size() / 5), a->beta, a->r_host));
     if (mode == lm::AIR_B2 || mode == lm::AIR_E1) {  // the round materialised the folded table: it is the source from now on
       a->src_buf = a->src_is_base ? 0 : (a->src_buf ^ 1);
       a->src_log_rows -= a->pending;
@@ -1468,6 +1469,7 @@ int lm_air_fold(lm_air* a, const uint32_t r[5]) {
     uint8_t* d = reinterpret_cast<uint8_t*>(a->d_dev) + offsetof(lm::AirDev, r);
     CU(cudaMemcpyAsync(d + sizeof(lm::Ef), d, sizeof(lm::Ef), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(d, r, sizeof(lm::Ef), cudaMemcpyHostToDevice, c->stream));
+    memcpy(a->r_host, r, sizeof(a->r_host));
     a->pending += 1;
   } else {
     const uint64_t n = (uint64_t)1 << a->log_n;

@@ -379,8 +379,7 @@ __device__ void gkr_step_round(GkrDev* g, DevFs* fs, uint32_t* tr, const Ef& c0r
   const uint32_t k = g->k;
   const Ef eq_alpha = g->point[k - 1 - rnd], mmf = g->mmf, s = g->s, one = fs_ef_one();
   const Ef c0 = fs_ef_mul(c0r, mmf), c2 = fs_ef_mul(c2r, mmf);
-  Ef ainv;
-  if (!fs_ef_inv(eq_alpha, &ainv)) w.flag(DEVFS_ERR_ZERO_INV);
+  const Ef ainv = g->inv_point[k - 1 - rnd];  // off the critical path: inverted when the layer began (gkr_invert_point)
   const Ef h1 = fs_ef_mul(ef_sub(s, fs_ef_mul(ef_sub(one, eq_alpha), c0)), ainv);
   const Ef b1 = ef_sub(ef_sub(h1, c0), c2);
   if ((threadIdx.x & 31) == 0) st_ef(sbuf, c0), st_ef(sbuf + 5, b1), st_ef(sbuf + 10, c2);
@@ -431,6 +430,16 @@ __device__ void gkr_step_begin(GkrDev* g, DevFs* fs, uint32_t* tr, const uint32_
   w.store();
 }
 
+// inverses of the k coordinates of the claim point, one thread each (a round's p(1) = (s - (1 - a) p(0)) / a needs 1 / a; on
+// the transcript warp the inversion was 5 k of the ~45 k cycles of every round)
+__device__ __forceinline__ void gkr_invert_point(GkrDev* g, DevFs* fs, uint32_t k) {
+  if (threadIdx.x < k) {
+    Ef inv;
+    if (!fs_ef_inv(g->point[threadIdx.x], &inv) && fs) atomicOr(&fs->error, (uint32_t)DEVFS_ERR_ZERO_INV);
+    g->inv_point[threadIdx.x] = inv;
+  }
+}
+
 __global__ void __launch_bounds__(512) gkr_begin_kernel(GkrLayerArgs A, Ef scale, int sample_alpha) {
   __shared__ uint32_t rc_s[DEVFS_RC_WORDS];
   if (sample_alpha && threadIdx.x < 32) {
@@ -439,6 +448,7 @@ __global__ void __launch_bounds__(512) gkr_begin_kernel(GkrLayerArgs A, Ef scale
   }
   if (!sample_alpha && threadIdx.x == 0) A.g->mmf = Ef{{KB_R1, 0, 0, 0, 0}};
   __syncthreads();
+  if (sample_alpha) gkr_invert_point(A.g, A.fs, A.k);
   gkr_build_tables(A.eq_tab, A.g, A.k, scale);
   if (threadIdx.x == 0) A.g->k = A.k, A.g->counter = 0;
 }
@@ -551,6 +561,7 @@ __global__ void __launch_bounds__(512) gkr_tail_kernel(GkrLayerArgs A, uint32_t 
   }
   __syncthreads();
   if (has_next) {
+    gkr_invert_point(A.g, A.fs, next.k);
     gkr_build_tables(next.eq_tab, A.g, next.k, Ef{{KB_R1, 0, 0, 0, 0}});
     if (threadIdx.x == 0) A.g->counter = 0;
   }

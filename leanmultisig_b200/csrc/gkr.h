@@ -41,6 +41,7 @@ constexpr int GKR_MAX_VARS = 40;
 struct GkrDev {  // per-session state of the layer sumcheck in device memory
   Ef point[GKR_MAX_VARS];  // claim point of the current layer (k coordinates)
   Ef q[GKR_MAX_VARS];      // challenges of the current layer, round order
+  Ef inv_point[GKR_MAX_VARS];  // inverses of the claim point's coordinates, computed in parallel when the layer begins
   Ef claim_num, claim_den, alpha, s, mmf, r;
   Ef inner[4];             // (nl, nr, dl, dr) at the end of the layer
   Ef out[2];               // (c0, c2) of the last round when the transcript is driven by the host
