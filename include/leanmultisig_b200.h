@@ -122,6 +122,10 @@ int lm_sc_new(lm_ctx* ctx, const uint32_t* evals, uint32_t n_vars, uint32_t elem
  * resp. scalar * next_mle(point, x) (crates/backend/poly/src/next_mle.rs:35).  Also add_new_equality
  * (open.rs:337-358) with selector 0 and m = n_vars. */
 int lm_sc_add_eq(lm_sumcheck* sc, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]);
+/* n_statements eq statements that share selector and point length, added in ONE pass over the weight table (combine_statement
+ * adds them one after the other; the sums are the same field elements): points n_statements x m x 5, scalars n_statements x 5 */
+int lm_sc_add_eq_batch(lm_sumcheck* sc, uint64_t selector, const uint32_t* points, uint32_t m, const uint32_t* scalars,
+                       uint32_t n_statements);
 int lm_sc_add_next(lm_sumcheck* sc, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]);
 /* weights[base + (b << shift) + offset] += scalar * eq(point, b) for b < 2^pre (point: pre x 5 words, first coordinate = most
  * significant bit of b).  The building block of the next-row statement (crates/backend/poly/src/next_mle.rs:35-58: term k has

@@ -154,6 +154,7 @@ def lib() -> C.CDLL:
             "lm_fs_transcript": [vp, u32p],
             "lm_fs_state": [vp, u32p, C.POINTER(C.c_int)],
             "lm_gkr_prove": [vp, vp, u32p, u32p, u32p, u32p],
+            "lm_sc_add_eq_batch": [vp, u64, u32p, u32, u32p, u32],
             "lm_sc_add_strided_eq": [vp, u64, u32, u64, u32p, u32, u32p],
             "lm_open_fold": [vp, u64p, u32, u32p, u32, u32p, u32p, u32p],
             "lm_whir_stir_update": [vp, u64p, u32, u32, u32, u32p, u32p, u32p, u32, u32p, u32p],

@@ -992,6 +992,25 @@ int lm_sc_add_eq(lm_sumcheck* s, uint64_t selector, const uint32_t* point, uint3
   return LM_OK;
 }
 
+int lm_sc_add_eq_batch(lm_sumcheck* s, uint64_t selector, const uint32_t* points, uint32_t m, const uint32_t* scalars, uint32_t n_st) {
+  if (!s || !scalars || !points) return fail(LM_ERR_INVALID, "lm_sc_add_eq_batch: null argument");
+  if (m < 1 || m > s->n_vars || (selector >> (s->n_vars - m)) != 0 || n_st == 0)
+    return fail(LM_ERR_INVALID, "lm_sc_add_eq_batch: bad selector / point length / count");
+  lm_ctx* c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  for (uint32_t k0 = 0; k0 < n_st; k0 += 16) {  // at most 16 statements per pass (table footprint)
+    const uint32_t K = n_st - k0 < 16 ? n_st - k0 : 16;
+    const size_t tab = lm::weights_add_eq_batch_scratch_words(m, K);
+    int rc = s->ensure_scratch(tab + (size_t)K * m * 5 + lm::prod_round_scratch_words());
+    if (rc != LM_OK) return rc;
+    uint32_t* d_pts = s->d_scratch + tab;
+    CU(cudaMemcpyAsync(d_pts, points + (size_t)k0 * m * 5, (size_t)K * m * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(lm::weights_add_eq_batch(c->stream, s->d_w, selector, d_pts, m, scalars + 5 * k0, K, s->d_scratch));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return LM_OK;
+}
+
 int lm_sc_add_next(lm_sumcheck* s, uint64_t selector, const uint32_t* point, uint32_t m, const uint32_t scalar[5]) {
   if (!s || !scalar || !point) return fail(LM_ERR_INVALID, "lm_sc_add_next: null argument");
   if (m < 1 || m > s->n_vars || (selector >> (s->n_vars - m)) != 0)

@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t fs_kb_inv(uint32_t a) {
   }
   return r;
 }
-static __device__ __noinline__ Ef fs_ef_mul(const Ef& a, const Ef& b) { return ef_mul(a, b); }
+__device__ __forceinline__ Ef fs_ef_mul(const Ef& a, const Ef& b) { return ef_mul(a, b); }
 __device__ __forceinline__ Ef fs_ef_frobenius(const Ef& a) {
   Ef out = {{a.c[0], 0, 0, 0, 0}};
 #pragma unroll

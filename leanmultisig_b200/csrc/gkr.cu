@@ -16,6 +16,7 @@
 // launches with no host synchronisation, and everything below 2^9 row pairs is one CTA.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdio>
 #include "gkr.h"
 #include "kb.cuh"
 #include "launch_count.h"
@@ -542,6 +543,9 @@ __global__ void __launch_bounds__(512) gkr_tail_kernel(GkrLayerArgs A, uint32_t 
   __shared__ uint32_t rc_s[DEVFS_RC_WORDS];
   if (threadIdx.x < 32) fs_load_rc(rc_s);
   for (uint32_t rnd = rnd_start; rnd < A.k; rnd++) {
+#ifdef LM_GKR_PROFILE
+    long long t_a = clock64();
+#endif
     Ef c0 = ef_zero(), c2 = ef_zero();
     if (rnd == 0)
       gkr_accumulate<0, NUM_DIM>(A, rnd, threadIdx.x, blockDim.x, c0, c2);
@@ -549,10 +553,19 @@ __global__ void __launch_bounds__(512) gkr_tail_kernel(GkrLayerArgs A, uint32_t 
       gkr_accumulate<1, NUM_DIM>(A, rnd, threadIdx.x, blockDim.x, c0, c2);
     else
       gkr_accumulate<2, NUM_DIM>(A, rnd, threadIdx.x, blockDim.x, c0, c2);
+#ifdef LM_GKR_PROFILE
+    long long t_b = clock64();
+#endif
     gkr_block_reduce(c0, c2, red);
+#ifdef LM_GKR_PROFILE
+    long long t_c = clock64();
+#endif
     if (threadIdx.x < 32) gkr_step_round(A.g, A.fs, A.tr, red[0], red[1], rnd, sbuf, rc_s);
     __threadfence_block();
     __syncthreads();
+#ifdef LM_GKR_PROFILE
+    if (threadIdx.x == 0 && A.k == 12) printf("k %u rnd %u: accumulate %lld, reduce %lld, step+sync %lld cycles\n", A.k, rnd, t_b - t_a, t_c - t_b, clock64() - t_c);
+#endif
   }
   if (threadIdx.x < 32) {
     gkr_final_fold<NUM_DIM>(A);

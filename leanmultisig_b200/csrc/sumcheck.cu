@@ -51,6 +51,72 @@ cudaError_t weights_add_eq(cudaStream_t stream, uint32_t* d_w, uint64_t selector
   count_launch();
   return cudaGetLastError();
 }
+// K statements with the same selector and point length in ONE pass over the weights (combine_statement, open.rs:518-584,
+// adds them one after the other; at 2^27 entries each separate pass is a 5.4 GB read-modify-write):
+// w[base + x] += sum_k hi_k[x >> lo_vars] * lo_k[x & mask], one reduction per coefficient for all K products.
+// hi / lo: K tables one after the other.
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+weights_add_split_batch_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t n, int lo_vars, const uint32_t* __restrict__ hi,
+                               const uint32_t* __restrict__ lo, int K) {
+  const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const uint64_t n_hi = n >> lo_vars, n_lo = (uint64_t)1 << lo_vars;
+  const uint64_t xh = x >> lo_vars, xl = x & (n_lo - 1);
+  uint64_t acc[5] = {0, 0, 0, 0, 0};
+  int pending = 0;
+  for (int k = 0; k < K; k++) {
+    const Ef a = ld_ef(hi + 5 * (k * n_hi + xh));
+    const EfRows b = ef_rows(ld_ef(lo + 5 * (k * n_lo + xl)));
+    const uint32_t rows[5][5] = {{b.b0, b.b4, b.b3, b.b2, b.b1m4},
+                                 {b.b1, b.b0, b.b4, b.b3, b.b2},
+                                 {b.b2, b.b1m4, b.b0m3, b.b4m2, b.b3m14},
+                                 {b.b3, b.b2, b.b1m4, b.b0m3, b.b4m2},
+                                 {b.b4, b.b3, b.b2, b.b1m4, b.b0m3}};
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+      if (pending == 4) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) acc[i] = kb_fold(acc[i]);
+        pending = 0;
+      }
+      pending++;
+#pragma unroll
+      for (int i = 0; i < 5; i++) acc[i] = mad_wide(a.c[t], rows[i][t], acc[i]);
+    }
+  }
+  uint32_t* dst = w + 5 * (base + x);
+  Ef cur = ld_ef_rw(dst);
+#pragma unroll
+  for (int i = 0; i < 5; i++) cur.c[i] = kb_add(cur.c[i], kb_canon(kb_redc_lazy(kb_fold(acc[i]))));
+  st_ef(dst, cur);
+}
+
+// d_points: K points of m coordinates (K x m x 5 words), scalars: host, K x 5 words
+cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_points, uint32_t m,
+                                 const uint32_t* scalars, uint32_t K, uint32_t* d_scratch) {
+  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  const int hi_vars = (int)m - lo_vars;
+  const size_t n_hi = (size_t)1 << hi_vars, n_lo = (size_t)1 << lo_vars;
+  uint32_t* d_hi = d_scratch;
+  uint32_t* d_lo = d_hi + 5 * n_hi * K;
+  const uint32_t one[5] = {KB_R1, 0, 0, 0, 0};
+  cudaError_t e;
+  for (uint32_t k = 0; k < K; k++) {
+    const uint32_t* pt = d_points + (size_t)k * m * 5;
+    if ((e = eq_table(stream, pt, hi_vars, scalars + 5 * k, d_hi + 5 * n_hi * k)) != cudaSuccess) return e;
+    if ((e = eq_table(stream, pt + 5 * hi_vars, lo_vars, one, d_lo + 5 * n_lo * k)) != cudaSuccess) return e;
+  }
+  const uint64_t n = (uint64_t)1 << m;
+  weights_add_split_batch_kernel<16><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_w, selector << m, n, lo_vars, d_hi, d_lo, (int)K);
+  count_launch();
+  return cudaGetLastError();
+}
+size_t weights_add_eq_batch_scratch_words(uint32_t m, uint32_t K) {
+  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  return 5 * (size_t)K * (((size_t)1 << (m - lo_vars)) + ((size_t)1 << lo_vars)) + 8;
+}
+
 size_t weights_add_eq_scratch_words(uint32_t m) {
   const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
   return 5 * (((size_t)1 << (m - lo_vars)) + ((size_t)1 << lo_vars)) + 8;

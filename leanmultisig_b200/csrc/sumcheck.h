@@ -26,4 +26,7 @@ cudaError_t prod_fold_round(cudaStream_t stream, const uint32_t* d_p, uint32_t d
                             uint32_t* d_out10);
 cudaError_t weights_add_strided_eq(cudaStream_t stream, uint32_t* d_w, uint64_t base, uint32_t shift, uint64_t offset,
                                    const uint32_t* d_point, uint32_t pre, const uint32_t scalar[5]);
+size_t weights_add_eq_batch_scratch_words(uint32_t m, uint32_t K);
+cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_points, uint32_t m,
+                                 const uint32_t* scalars, uint32_t K, uint32_t* d_scratch);
 }  // namespace lm

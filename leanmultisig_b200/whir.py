@@ -129,6 +129,14 @@ class ProductSumcheck:
         pt = _u32(point).reshape(-1, 5)
         check(lib().lm_sc_add_eq(self.handle, selector, _p(pt), pt.shape[0], _p(_u32(scalar))))
 
+    def add_eq_batch(self, selector: int, points, scalars):
+        """several eq statements with the same selector and point length in one pass over the weights (lm_sc_add_eq_batch)"""
+        pts = _u32(points)
+        assert pts.ndim == 3 and pts.shape[2] == 5
+        sc = _u32(scalars).reshape(-1, 5)
+        assert sc.shape[0] == pts.shape[0]
+        check(lib().lm_sc_add_eq_batch(self.handle, selector, _p(pts), pts.shape[1], _p(sc), pts.shape[0]))
+
     def add_next(self, selector: int, point, scalar):
         pt = _u32(point).reshape(-1, 5)
         check(lib().lm_sc_add_next(self.handle, selector, _p(pt), pt.shape[0], _p(_u32(scalar))))
@@ -525,11 +533,20 @@ class WhirProver:
         sc = self._session(witness)
         lap("session (weights alloc)")
         total, gp = F.ZERO, F.ONE
+        groups = {}  # eq statements by (selector, point length): added in one pass over the weights each
         for smt in stm:
             for sel, val in smt.values:
-                (sc.add_next if smt.is_next else sc.add_eq)(sel, smt.point, F.to_monty(gp))
+                if smt.is_next or smt.point.shape[0] == 0 or not hasattr(sc, "add_eq_batch"):
+                    (sc.add_next if smt.is_next else sc.add_eq)(sel, smt.point, F.to_monty(gp))
+                else:
+                    groups.setdefault((sel, smt.point.shape[0]), []).append((smt.point, F.to_monty(gp)))
                 total = F.add(total, F.mul(F.from_monty(val), gp))
                 gp = F.mul(gp, gamma)
+        for (sel, m), items in groups.items():
+            if len(items) == 1:
+                sc.add_eq(sel, items[0][0], items[0][1])
+            else:
+                sc.add_eq_batch(sel, np.stack([p for p, _ in items]), np.stack([s for _, s in items]))
         lap("combine_statement")
         randomness, total = self._rounds(sc, ps, cfg.first_folding, cfg.starting_folding_pow_bits, total)
         lap("sumcheck rounds (incl. PoW)")

@@ -173,3 +173,28 @@ def test_whir_round_commit_and_ood_on_folded_polynomial(ctx, rng):
     for q, i in enumerate([3, 17]):
         assert O.merkle_verify(tree1.root, tree1.log_height, i, rows[q], paths[q])
     tree0.free(), tree1.free(), sc.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,sel_bits,k", [(6, 0, 2), (12, 0, 10), (14, 3, 5), (16, 0, 19), (11, 11, 3)])
+def test_add_eq_batch_equals_separate_statements(rng, n, sel_bits, k):
+    """lm_sc_add_eq_batch (all statements of one selector and length in ONE pass over the weights, delayed reduction over the
+    statements) produces the weight table of adding them one by one, i.e. the oracle's"""
+    import leanmultisig_b200 as lm
+
+    if n - sel_bits < 1:
+        pytest.skip("needs at least one inner variable")
+    ctx = lm.Context(0, 16)
+    m = n - sel_bits
+    p = O.random_field(rng, 1 << n)
+    w = np.zeros((1 << n, 5), dtype=np.uint32)
+    sel = int(rng.integers(0, 1 << sel_bits)) if sel_bits else 0
+    pts, scs = O.random_field(rng, (k, m, 5)), O.random_field(rng, (k, 5))
+    for i in range(k):
+        O.weights_add_eq(w, sel, pts[i], scs[i])
+    sc = ctx.sumcheck(p, n)
+    sc.add_eq_batch(sel, pts, scs)
+    _, gw = sc.read()
+    assert np.array_equal(gw, w)
+    sc.free()
+    ctx.close()
