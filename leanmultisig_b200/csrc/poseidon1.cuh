@@ -291,31 +291,11 @@ __device__ __forceinline__ void p1_all_lanes_imm(const uint32_t lane_lin[15], co
 #else
 #define LM_P1_BARRIER() do { } while (0)
 #endif
-template <int N_OUT, class Tab, bool SYNC = false>
-LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
-  uint32_t a[16], x[16];
-
-  // ---- 4 initial full rounds.  Kept as a real loop on the device (constants indexed by the round): the fully
-  // unrolled permutation is ~140 KiB of SASS and was starved by instruction fetch (ncu: 19 % of warp cycles in
-  // stall_no_instruction, I-cache hit rate 68 %).
-#pragma unroll
-  for (int i = 0; i < 16; i++) a[i] = kb_add(s[i], T.RC0[i]);
-#ifdef __CUDA_ARCH__
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
-  for (int r = 0; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
-    p1_mds_redc<16>(a, T.RC_INIT[r], T.RC_INIT_D[r], x);
-#pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = x[i];
-    LM_P1_BARRIER();
-  }
-  // x = x' (state entering the partial section, first_rc already added), held at R^-39, lanes < p + 2^9
-
-  // ---- partial section
+// Partial section (20 partial rounds and the linear maps around them) on one state held by one thread:
+// x = state entering the section (first_rc already added, lanes < p + 2^9), a = state leaving it (first terminal
+// round constant included).
+template <class Tab, bool SYNC>
+LM_HD void p1_partial_section(const uint32_t x[16], uint32_t a[16], const Tab& T) {
 #ifdef LM_P1_IMM
   {
     uint32_t d[20], lane_lin[15], z[20];
@@ -390,6 +370,34 @@ LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
   }
 
 #endif
+
+}
+
+template <int N_OUT, class Tab, bool SYNC = false>
+LM_HD void p1_permute(uint32_t s[16], const Tab& T) {
+  uint32_t a[16], x[16];
+
+  // ---- 4 initial full rounds.  Kept as a real loop on the device (constants indexed by the round): the fully
+  // unrolled permutation is ~140 KiB of SASS and was starved by instruction fetch (ncu: 19 % of warp cycles in
+  // stall_no_instruction, I-cache hit rate 68 %).
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = kb_add(s[i], T.RC0[i]);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
+    p1_mds_redc<16>(a, T.RC_INIT[r], T.RC_INIT_D[r], x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = x[i];
+    LM_P1_BARRIER();
+  }
+  // x = x' (state entering the partial section, first_rc already added), held at R^-39, lanes < p + 2^9
+
+  p1_partial_section<Tab, SYNC>(x, a, T);
 
   // ---- 4 terminal full rounds (first round constant already inside a[]); three looped, the last one only
   // produces the lanes that are kept

@@ -1,0 +1,301 @@
+// Poseidon1-KoalaBear width-16 for sm_100a with every "constant matrix x state" product on the 5th-generation tensor cores
+// (tcgen05.mma.kind::i8, accumulators in tensor memory), one state per thread, 128 states per MMA.
+//
+// Same function as poseidon1.cuh (poseidon1_koalabear_16.rs:873-912 permute_generic / :1020-1030 compress_in_place of the
+// reference), bit for bit on the canonical outputs.  What moves off the multiplier pipe (IMAD.WIDE 4 cycles, DFMA ~2.2 cycles per
+// warp instruction and sub-partition; the one-state-per-thread kernels keep it 79 % busy):
+//   * the circulant MDS of the 8 full rounds           16 x 16, entries <= 101          (was 96 DFMA + 48 DADD per state and round)
+//   * D = G x' and the first lane (21 x 16) entering the partial section                 (was 336 IMAD.WIDE + folds)
+//   * lanes 1..15 leaving it, MI x' + V z (15 x 36)                                      (was 540 IMAD.WIDE + folds)
+// What stays: the S-boxes, the serial chain s0_{r+1} = FR0[r] z_r + D_r + sum_{k<r} GTRI[r][k] z_k of the 20 partial rounds, and
+// one Montgomery reduction per produced lane.
+//
+// Why tcgen05 and not mma.sync: on B200 the legacy warp-level IMMA.16832.U8.U8 does NOT overlap with the multiplier pipe
+// (tools/microbench/imma_mix.cu, profiles/r02_imma_gonogo.txt: 16 IMMA + 16 IMAD.WIDE take 248 cycles, 128 + 82 apart); a first
+// version of this file on mma.sync was bit-exact and 18 % SLOWER.  tcgen05.mma is asynchronous: one thread issues it for 128
+// states, the product runs in the tensor unit while the other warps of the SM keep the integer pipes busy.
+//
+// Mapping.  M = 128 states = the 4 warps of a "group" (thread i of the group = row i = TMEM lane i, so tcgen05.ld.32x32b hands
+// every thread the accumulators of ITS state: the one-state-per-thread layout of poseidon1.cuh is kept, no transposition).
+// A (shared memory, K-major, no swizzle: 8 rows x 16 bytes core matrices, LBO = 128, SBO = 1280): row = the state's words as
+// they stand — the four bytes of a word are its four u8 limbs: k = 4 e + i  <->  limb i of word e.  Chunks 0..3 hold the 16 state
+// words, chunks 4..8 the 20 S-box outputs z of the partial rounds.
+// B (shared memory, N x K, K-major):
+//   MDS   column 4 o + l:  C[(o - e) mod 16] at k = 4 e + l, else 0; S_l = sum_e C[..] limb_l(x_e) < 2^17 and
+//         4 (C x)_o + rc = 4 (S0 + 2^8 S1 + 2^16 S2 + 2^24 S3) + rc — the exact integer p1_mds_redc reduces;
+//   G, MI, V (entries are 31-bit constants): limb i of an input is multiplied by the constant PRE-SHIFTED mod p,
+//         M_i = M 2^(8 i) mod p, whose four bytes j go to columns 4 o + j:  T_j = sum_(e,i) limb_i(x_e) byte_j(M_i[o][e]) < 2^24,
+//         sum_e M[o][e] x_e  ==  T0 + 2^8 T1 + 2^16 T2 + 2^24 T3  (mod p), < 2^47: four accumulator columns and ONE reduction per
+//         output instead of 16-36 multiply-accumulates with folds.
+// The recombination is shifts and adds; the reduction is kb_redc_lazy as before.  Intermediate lanes are congruent to those of
+// poseidon1.cuh (not always the same lazy representative); the bounds the S-boxes need (< 1.43 p) hold with room: every
+// reduction here sees less than 2^47, i.e. returns less than p + 2^15.
+//
+// Cost per permutation and group: 10 round trips (store row -> fence.proxy.async -> 128-thread barrier -> MMA issue -> commit ->
+// mbarrier -> tcgen05.ld), ~450 cycles each when nothing else runs (tools/microbench/umma_i8_probe.cu); with two 256-thread CTAs
+// per SM four groups interleave, so a group's round trip is covered by the S-boxes of the other three.
+#pragma once
+#include "poseidon1.cuh"
+
+namespace lm {
+
+// image of the three B matrices in their shared-memory (canonical K-major) layout
+constexpr int P1U_B_MDS = 0;              // 64 x 64
+constexpr int P1U_B_G = 4096;             // 96 x 64 (84 live columns)
+constexpr int P1U_B_MV = 4096 + 6144;     // 64 x 160 (60 live columns, 144 live k)
+constexpr int P1U_B_BYTES = 4096 + 6144 + 10240;
+constexpr int P1U_A_BYTES = 128 * 160;    // one group's A rows
+constexpr int P1U_TMEM_COLS_PER_GROUP = 128;
+
+// host: fill `img` (P1U_B_BYTES) from the generated tables
+inline void p1u_build_b_image(const P1Tables& T, uint8_t* img) {
+  for (int i = 0; i < P1U_B_BYTES; i++) img[i] = 0;
+  auto at = [&](int base, int kchunks, int n, int k) -> uint8_t& {
+    return img[base + (n / 8) * (kchunks * 128) + (k / 16) * 128 + (n % 8) * 16 + (k % 16)];
+  };
+  const uint32_t C[16] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
+  for (int o = 0; o < 16; o++)
+    for (int e = 0; e < 16; e++)
+      for (int l = 0; l < 4; l++) at(P1U_B_MDS, 4, 4 * o + l, 4 * e + l) = (uint8_t)C[(o - e) & 15];
+  auto put = [&](int base, int kchunks, int o, int kword, uint32_t m) {
+    for (int i = 0; i < 4; i++) {
+      const uint32_t mi = (uint32_t)((((uint64_t)m) << (8 * i)) % KB_P);
+      for (int j = 0; j < 4; j++) at(base, kchunks, 4 * o + j, 4 * kword + i) = (uint8_t)(mi >> (8 * j));
+    }
+  };
+  for (int r = 0; r < 21; r++)
+    for (int e = 0; e < 16; e++) put(P1U_B_G, 4, r, e, T.G[r][e]);
+  for (int o = 0; o < 15; o++) {
+    for (int e = 0; e < 16; e++) put(P1U_B_MV, 10, o, e, T.MI[o][e]);
+    for (int q = 0; q < 20; q++) put(P1U_B_MV, 10, o, 16 + q, T.V[o][q]);
+  }
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t p1u_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: start address, LBO = 128 (K-adjacent core matrices are contiguous), SBO = bytes per 8-row group
+__device__ __forceinline__ uint64_t p1u_desc(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void p1u_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ bool p1u_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void p1u_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+      "%26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+LM_HD constexpr uint32_t p1u_idesc(uint32_t n) { return (2u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// Per-thread view of the group's tensor-core plumbing.  Kernels: dynamic shared memory of p1u_smem_bytes(groups), blockDim.x =
+// 128 * groups, every thread of the CTA calls p1u_setup once, the permutation the same number of times, p1u_teardown once.
+struct P1uCtx {
+  uint32_t a_row;    // shared address of this thread's row, chunk 0
+  uint32_t a_base;   // shared address of the group's A rows
+  uint32_t b_base;   // shared address of the B image
+  uint32_t bar;      // the group's mbarrier
+  uint32_t tmem;     // TMEM address of this warp's lanes, first column of the group
+  uint32_t tmem_d;   // TMEM address of the group's accumulator (lane 0, first column of the group)
+  uint32_t tmem_alloc;
+  uint32_t parity;
+  uint32_t group;
+  bool leader;
+};
+LM_HD constexpr int p1u_smem_bytes(int groups) { return P1U_B_BYTES + groups * P1U_A_BYTES + 64; }
+
+__device__ __forceinline__ P1uCtx p1u_setup(uint8_t* smem /* 1024-byte aligned */, const uint8_t* __restrict__ b_image, int groups) {
+  const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, r = tid & 127;
+  uint8_t* sb = smem;
+  uint8_t* sa = smem + P1U_B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P1U_B_BYTES + groups * P1U_A_BYTES);
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  for (int i = tid; i < P1U_B_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sb)[i] = __ldg(reinterpret_cast<const uint4*>(b_image) + i);
+  const uint32_t cols = groups * P1U_TMEM_COLS_PER_GROUP;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p1u_smem_u32(tm_slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < groups) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(p1u_smem_u32(bars + tid)), "r"(1) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  P1uCtx c;
+  c.a_base = p1u_smem_u32(sa + g * P1U_A_BYTES);
+  c.a_row = c.a_base + (r >> 3) * 1280 + (r & 7) * 16;
+  c.b_base = p1u_smem_u32(sb);
+  c.bar = p1u_smem_u32(bars + g);
+  c.tmem_alloc = *tm_slot;
+  c.tmem_d = c.tmem_alloc + g * P1U_TMEM_COLS_PER_GROUP;
+  c.tmem = c.tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+  c.parity = 0;
+  c.group = g;
+  c.leader = r == 0;
+  return c;
+}
+__device__ __forceinline__ void p1u_teardown(const P1uCtx& c, int groups) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem_alloc), "r"(groups * P1U_TMEM_COLS_PER_GROUP) : "memory");
+}
+
+__device__ __forceinline__ void p1u_store_chunk(const P1uCtx& c, int chunk, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.a_row + chunk * 128), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+}
+
+// rows are written: run K_STEPS MMAs of N columns against the B matrix at b_off and wait for the accumulators
+template <int N, int K_STEPS, int B_OFF, int B_KCHUNKS>
+__device__ __forceinline__ void p1u_product(P1uCtx& c) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (c.group == 0)
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  else
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+  if (c.leader) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint64_t da = p1u_desc(c.a_base, 1280), db = p1u_desc(c.b_base + B_OFF, B_KCHUNKS * 128);
+#pragma unroll
+    for (int k = 0; k < K_STEPS; k++) p1u_mma(c.tmem_d, da + (uint64_t)(k * 256 >> 4), db + (uint64_t)(k * 256 >> 4), p1u_idesc(N), k > 0);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.bar) : "memory");
+  }
+  for (uint32_t spins = 0; !p1u_try_wait(c.bar, c.parity);)
+    if (++spins > (1u << 26)) __trap();  // a lost MMA completion must not hang the device
+  c.parity ^= 1;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// value-preserving recombination of four accumulator columns: v0 + 2^8 v1 + 2^16 v2 + 2^24 v3 (each < 2^24) shifted left by
+// SHIFT, plus init (< 2^32)
+template <int SHIFT>
+__device__ __forceinline__ uint64_t p1u_combine(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
+  const uint32_t x = v0 + (v1 << 8), y = v2 + (v3 << 8);
+  return (((uint64_t)x) << SHIFT) + (((uint64_t)y) << (16 + SHIFT)) + init;
+}
+
+// out[i] = redc(rc[i] + 4 * sum_j C[(i - j) mod 16] a3[j]), i < N_OUT: p1_mds_redc on the tensor cores
+template <int N_OUT>
+__device__ __forceinline__ void p1u_mds_redc(P1uCtx& c, const uint32_t a3[16], const uint32_t* rc, uint32_t out[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) p1u_store_chunk(c, k, a3[4 * k], a3[4 * k + 1], a3[4 * k + 2], a3[4 * k + 3]);
+  p1u_product<4 * N_OUT, 2, P1U_B_MDS, 4>(c);
+#pragma unroll
+  for (int h = 0; h < N_OUT / 8; h++) {
+    uint32_t v[32];
+    p1u_ld32(c.tmem + 32 * h, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      out[8 * h + i] = kb_redc_lazy(p1u_combine<2>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], rc ? rc[8 * h + i] : 0u));
+  }
+}
+
+// The partial section of p1_partial_section: x = state entering (lanes < p + 2^9), a = state leaving.
+template <bool SYNC>
+__device__ __forceinline__ void p1u_partial_section(P1uCtx& c, const uint32_t x[16], uint32_t a[16], const P1Tables& t) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) p1u_store_chunk(c, k, x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+  p1u_product<96, 2, P1U_B_G, 4>(c);
+  uint32_t d[21];  // d[0] = first lane entering round 0, d[1 + r] = D_r
+#pragma unroll
+  for (int h = 0; h < 3; h++) {
+    uint32_t v[32];
+    p1u_ld32(c.tmem + 32 * h, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int r = 8 * h + i;
+      if (r < 21) d[r] = kb_redc_lazy(p1u_combine<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], r == 0 ? 0u : t.G_CONST[r < 21 ? r : 0]));
+    }
+  }
+  LM_P1_BARRIER();
+  uint32_t z[20];
+  uint32_t s0 = d[0];
+#ifdef LM_P1_IMM  // (the host pass of nvcc parses this body too)
+  p1_partial_rounds_imm<SYNC>(s0, d + 1, z, p1_seq<20>{});
+#endif
+  a[0] = s0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) p1u_store_chunk(c, 4 + k, z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+  p1u_product<64, 5, P1U_B_MV, 10>(c);
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t v[32];
+    p1u_ld32(c.tmem + 32 * h, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int o = 8 * h + i;
+      if (o < 15) a[o + 1] = kb_redc_lazy(p1u_combine<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], t.LANE_CONST[o < 15 ? o : 0]));
+    }
+  }
+}
+
+// Permutation; N_OUT = 16 or 8 (digest half).  s: canonical in, canonical out.
+template <int N_OUT, bool SYNC>
+__device__ __forceinline__ void p1u_permute(P1uCtx& c, uint32_t s[16], const P1Tables& T) {
+  uint32_t a[16], x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = kb_add(s[i], T.RC0[i]);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
+    p1u_mds_redc<16>(c, a, T.RC_INIT[r], x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = x[i];
+  }
+  p1u_partial_section<SYNC>(c, x, a, T);
+#pragma unroll 1
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
+    p1u_mds_redc<16>(c, a, T.RC_TERM[r], x);
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = x[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
+  p1u_mds_redc<N_OUT>(c, a, nullptr, x);
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) s[i] = kb_mul(x[i], T.FIX);
+}
+
+template <int N_OUT, bool SYNC>
+__device__ __forceinline__ void p1u_compress(P1uCtx& c, uint32_t s[16], const P1Tables& T) {
+  uint32_t in[N_OUT];
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) in[i] = s[i];
+  p1u_permute<N_OUT, SYNC>(c, s, T);
+#pragma unroll
+  for (int i = 0; i < N_OUT; i++) s[i] = kb_add(s[i], in[i]);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lm
