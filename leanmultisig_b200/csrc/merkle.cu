@@ -18,6 +18,8 @@
 #include "launch_count.h"
 #include "merkle.h"
 #include "poseidon1.cuh"
+#include "poseidon1_umma.cuh"
+#include <mutex>
 
 namespace lm {
 
@@ -47,6 +49,48 @@ struct State16 {
   uint32_t v[16];
 };
 
+// ---- tensor-core formulation (poseidon1_umma.cuh) ---------------------------------------------------------------------
+// The wide kernels (leaf sponge, leaf absorb, wide tree levels, explicit states) run the permutation with its linear maps on
+// tcgen05; LM_P1_SCALAR=1 selects the one-state-per-thread form of poseidon1.cuh (same outputs, kept for cross-checks).
+static_assert(LEAF_THREADS % 128 == 0, "the tensor-core permutation works on groups of 128 threads");
+constexpr int LEAF_GROUPS = LEAF_THREADS / 128;
+
+static bool use_umma() {
+  static const bool on = [] {
+    const char* e = getenv("LM_P1_SCALAR");
+    return !(e && atoi(e) != 0);
+  }();
+  return on;
+}
+// the B matrices in shared-memory layout, uploaded once per device
+static cudaError_t umma_b_image(const uint8_t** out) {
+  static std::mutex mu;
+  static uint8_t* per_device[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!per_device[dev]) {
+    static uint8_t img[P1U_B_BYTES];
+    p1u_build_b_image(h_p1, img);
+    uint8_t* d = nullptr;
+    if ((e = cudaMalloc(&d, P1U_B_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(d, img, P1U_B_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      cudaFree(d);
+      return e;
+    }
+    per_device[dev] = d;
+  }
+  *out = per_device[dev];
+  return cudaSuccess;
+}
+// opt a kernel in to its dynamic shared memory once per device
+template <class K>
+static cudaError_t umma_attr(K kernel, int groups) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p1u_smem_bytes(groups));
+}
+
 // Element `pos` of the virtual row: stored value if pos < lim else 0.
 // Fast path: whole 8-chunk below lim and 16-byte aligned -> two 128-bit loads.
 __device__ __forceinline__ void load_chunk8(const uint32_t* __restrict__ row, int64_t first, uint32_t lim, bool vec_ok,
@@ -67,9 +111,13 @@ __device__ __forceinline__ void load_chunk8(const uint32_t* __restrict__ row, in
 
 // Grid-stride over blocks of LEAF_THREADS rows: the launcher may start one CTA per block or a persistent grid (a multiple
 // of the SM count) whose CTAs keep the ~100 KiB permutation hot in the instruction cache.
+template <bool U>
 __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
 leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t lim, uint32_t virt_w,
-                   int from_state, State16 init, uint32_t* __restrict__ digests) {
+                   int from_state, State16 init, uint32_t* __restrict__ digests, const uint8_t* __restrict__ b_image) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  P1uCtx uc;
+  if constexpr (U) uc = p1u_setup(dsm, b_image, LEAF_GROUPS);
   const bool vec_ok = (stored_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mat) & 15) == 0);
   const int64_t n_chunks = virt_w / 8;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < h; base += (uint64_t)gridDim.x * blockDim.x) {
@@ -91,7 +139,10 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
     }
     for (int64_t it = 0; it < n_comp; it++) {
       load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
-      p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
+      if constexpr (U)
+        p1u_compress<8, LEAF_SYNC != 0>(uc, s, c_p1);
+      else
+        p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
       chunk -= (it == 0 && !from_state) ? 2 : 1;
     }
     if (live) {
@@ -100,14 +151,19 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
       out[1] = make_uint4(s[4], s[5], s[6], s[7]);
     }
   }
+  if constexpr (U) p1u_teardown(uc, LEAF_GROUPS);
 }
 
 // `count` sponge steps for every row: state (lanes 0..7, kept in the digest buffer between launches) absorbs rate chunks
 // chunk_hi, chunk_hi - 1, ..., chunk_hi - count + 1 of the row.  Lets the commit hash columns as soon as they are
 // transformed, right to left, while the host-to-device copy of the columns further left is still in flight.
+template <bool U>
 __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
 leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t chunk_hi, uint32_t count, int first,
-                   State16 init, uint32_t* __restrict__ digests) {
+                   State16 init, uint32_t* __restrict__ digests, const uint8_t* __restrict__ b_image) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  P1uCtx uc;
+  if constexpr (U) uc = p1u_setup(dsm, b_image, LEAF_GROUPS);
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < h; base += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t r = base + threadIdx.x;
     const bool live = r < h;
@@ -125,19 +181,27 @@ leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
     for (uint32_t k = 0; k < count; k++, src -= 2) {
       const uint4 lo = __ldg(src), hi = __ldg(src + 1);
       s[8] = lo.x, s[9] = lo.y, s[10] = lo.z, s[11] = lo.w, s[12] = hi.x, s[13] = hi.y, s[14] = hi.z, s[15] = hi.w;
-      p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
+      if constexpr (U)
+        p1u_compress<8, LEAF_SYNC != 0>(uc, s, c_p1);
+      else
+        p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
     }
     if (live) {
       dg[0] = make_uint4(s[0], s[1], s[2], s[3]);
       dg[1] = make_uint4(s[4], s[5], s[6], s[7]);
     }
   }
+  if constexpr (U) p1u_teardown(uc, LEAF_GROUPS);
 }
 
 // One level: next[i] = C(prev[2i] || prev[2i+1])[0..8), one thread per parent.  Used while a level still fills
 // the machine; the short tail of the tree goes through tree_levels_kernel below.
+template <bool U>
 __global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
-tree_level_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* __restrict__ next) {
+tree_level_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* __restrict__ next, const uint8_t* __restrict__ b_image) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  P1uCtx uc;
+  if constexpr (U) uc = p1u_setup(dsm, b_image, LEAF_GROUPS);
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n_next; base += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t i = base + threadIdx.x;
     const bool live = i < n_next;
@@ -147,13 +211,17 @@ tree_level_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* 
     const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
     s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
     s[8] = c.x, s[9] = c.y, s[10] = c.z, s[11] = c.w, s[12] = d.x, s[13] = d.y, s[14] = d.z, s[15] = d.w;
-    p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
+    if constexpr (U)
+      p1u_compress<8, LEAF_SYNC != 0>(uc, s, c_p1);
+    else
+      p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
     if (live) {
       uint4* dst = reinterpret_cast<uint4*>(next + 8 * i);
       dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
       dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
     }
   }
+  if constexpr (U) p1u_teardown(uc, LEAF_GROUPS);
 }
 
 // layer0: n0 digests (n0 = 2 * T * gridDim.x at full size). CTA b owns digests [b*2T, (b+1)*2T) and writes
@@ -240,7 +308,17 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
   }
   const int T = LEAF_THREADS;
   const uint64_t blocks = leaf_grid(h);
-  leaf_sponge_kernel<<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests); count_launch();
+  if (use_umma()) {
+    const uint8_t* img = nullptr;
+    cudaError_t e = umma_b_image(&img);
+    if (e != cudaSuccess) return e;
+    if ((e = umma_attr(leaf_sponge_kernel<true>, LEAF_GROUPS)) != cudaSuccess) return e;
+    leaf_sponge_kernel<true><<<(unsigned)blocks, T, p1u_smem_bytes(LEAF_GROUPS), stream>>>(d_mat, h, stored_w, lim, virt_w, from_state,
+                                                                                            init, d_digests, img);
+  } else {
+    leaf_sponge_kernel<false><<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests, nullptr);
+  }
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -258,8 +336,17 @@ cudaError_t merkle_leaf_absorb_chunks(cudaStream_t stream, const uint32_t* d_mat
   const int first = chunk_hi == eff_w / 8 - 1;
   State16 init{};
   if (first) init = zero_suffix_state_host((full_w - eff_w) / 8);
-  leaf_absorb_kernel<<<(unsigned)leaf_grid(h), LEAF_THREADS, 0, stream>>>(d_mat, h, stored_w, chunk_hi, count, first, init,
-                                                                          d_digests);
+  if (use_umma()) {
+    const uint8_t* img = nullptr;
+    cudaError_t e = umma_b_image(&img);
+    if (e != cudaSuccess) return e;
+    if ((e = umma_attr(leaf_absorb_kernel<true>, LEAF_GROUPS)) != cudaSuccess) return e;
+    leaf_absorb_kernel<true><<<(unsigned)leaf_grid(h), LEAF_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
+        d_mat, h, stored_w, chunk_hi, count, first, init, d_digests, img);
+  } else {
+    leaf_absorb_kernel<false><<<(unsigned)leaf_grid(h), LEAF_THREADS, 0, stream>>>(d_mat, h, stored_w, chunk_hi, count, first, init,
+                                                                                   d_digests, nullptr);
+  }
   count_launch();
   return cudaGetLastError();
 }
@@ -270,9 +357,19 @@ cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, ui
   uint32_t* cur = d_layers;
   uint64_t n = h;
   // wide levels: one launch per level, every thread busy
+  const uint8_t* img = nullptr;
+  if (use_umma() && h / 2 >= 8192) {
+    cudaError_t e = umma_b_image(&img);
+    if (e != cudaSuccess) return e;
+    if ((e = umma_attr(tree_level_kernel<true>, LEAF_GROUPS)) != cudaSuccess) return e;
+  }
   while (n / 2 >= 8192) {
     uint32_t* next = cur + 8 * n;
-    tree_level_kernel<<<(unsigned)((n / 2 + LEAF_THREADS - 1) / LEAF_THREADS), LEAF_THREADS, 0, stream>>>(cur, n / 2, next);
+    const unsigned blocks = (unsigned)((n / 2 + LEAF_THREADS - 1) / LEAF_THREADS);
+    if (img)
+      tree_level_kernel<true><<<blocks, LEAF_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(cur, n / 2, next, img);
+    else
+      tree_level_kernel<false><<<blocks, LEAF_THREADS, 0, stream>>>(cur, n / 2, next, nullptr);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -343,9 +440,45 @@ __global__ void __launch_bounds__(128) permute_states_kernel(uint32_t* states, u
   for (int k = 0; k < 4; k++) p[k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
 }
 
+// the same on the tensor cores: one group of 128 states per CTA, every thread runs the permutation (clamped index)
+__global__ void __launch_bounds__(128) permute_states_umma_kernel(uint32_t* states, uint64_t n, int compress,
+                                                                  const uint8_t* __restrict__ b_image) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  P1uCtx uc = p1u_setup(dsm, b_image, 1);
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  if (!live) i = n - 1;
+  uint32_t s[16];
+  uint4* p = reinterpret_cast<uint4*>(states + 16 * i);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint4 v = p[k];
+    s[4 * k] = v.x, s[4 * k + 1] = v.y, s[4 * k + 2] = v.z, s[4 * k + 3] = v.w;
+  }
+  if (compress)
+    p1u_compress<16, false>(uc, s, c_p1);
+  else
+    p1u_permute<16, false>(uc, s, c_p1);
+  // a dead thread re-computed state n - 1: it must not race with the live thread's store
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+  }
+  p1u_teardown(uc, 1);
+}
+
 cudaError_t poseidon1_states(cudaStream_t stream, uint32_t* d_states, uint64_t n, int compress) {
   if (n == 0) return cudaSuccess;
-  permute_states_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_states, n, compress); count_launch();
+  if (use_umma()) {
+    const uint8_t* img = nullptr;
+    cudaError_t e = umma_b_image(&img);
+    if (e != cudaSuccess) return e;
+    if ((e = umma_attr(permute_states_umma_kernel, 1)) != cudaSuccess) return e;
+    permute_states_umma_kernel<<<(unsigned)((n + 127) / 128), 128, p1u_smem_bytes(1), stream>>>(d_states, n, compress, img);
+  } else {
+    permute_states_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_states, n, compress);
+  }
+  count_launch();
   return cudaGetLastError();
 }
 
