@@ -52,8 +52,17 @@ struct State16 {
 // ---- tensor-core formulation (poseidon1_umma.cuh) ---------------------------------------------------------------------
 // The wide kernels (leaf sponge, leaf absorb, wide tree levels, explicit states) run the permutation with its linear maps on
 // tcgen05; LM_P1_SCALAR=1 selects the one-state-per-thread form of poseidon1.cuh (same outputs, kept for cross-checks).
-static_assert(LEAF_THREADS % 128 == 0, "the tensor-core permutation works on groups of 128 threads");
-constexpr int LEAF_GROUPS = LEAF_THREADS / 128;
+// CTA shape of the tensor-core kernels: ONE group of 128 threads per CTA, four CTAs per SM (TMEM: 4 x 128 columns; measured
+// against 2 x 256 and 1 x 512 threads in profiles/r02_p1_umma.txt — independent groups cover each other's MMA round trips best)
+#ifndef UMMA_THREADS
+#define UMMA_THREADS 128
+#endif
+#ifndef UMMA_MIN_BLOCKS
+#define UMMA_MIN_BLOCKS 4
+#endif
+static_assert(UMMA_THREADS % 128 == 0 && UMMA_THREADS <= 512, "the tensor-core permutation works on groups of 128 threads");
+constexpr int LEAF_GROUPS = UMMA_THREADS / 128;
+constexpr bool UMMA_SYNC = LEAF_SYNC != 0 && UMMA_THREADS > 128;
 
 static bool use_umma() {
   static const bool on = [] {
@@ -112,7 +121,7 @@ __device__ __forceinline__ void load_chunk8(const uint32_t* __restrict__ row, in
 // Grid-stride over blocks of LEAF_THREADS rows: the launcher may start one CTA per block or a persistent grid (a multiple
 // of the SM count) whose CTAs keep the ~100 KiB permutation hot in the instruction cache.
 template <bool U>
-__global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
+__global__ void __launch_bounds__(U ? UMMA_THREADS : LEAF_THREADS, U ? UMMA_MIN_BLOCKS : LEAF_MIN_BLOCKS)
 leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t lim, uint32_t virt_w,
                    int from_state, State16 init, uint32_t* __restrict__ digests, const uint8_t* __restrict__ b_image) {
   extern __shared__ __align__(1024) uint8_t dsm[];
@@ -140,7 +149,7 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
     for (int64_t it = 0; it < n_comp; it++) {
       load_chunk8(row, 8 * chunk, lim, vec_ok, s + 8);
       if constexpr (U)
-        p1u_compress<8, LEAF_SYNC != 0>(uc, s, c_p1);
+        p1u_compress<8, UMMA_SYNC>(uc, s, c_p1);
       else
         p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
       chunk -= (it == 0 && !from_state) ? 2 : 1;
@@ -158,7 +167,7 @@ leaf_sponge_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
 // chunk_hi, chunk_hi - 1, ..., chunk_hi - count + 1 of the row.  Lets the commit hash columns as soon as they are
 // transformed, right to left, while the host-to-device copy of the columns further left is still in flight.
 template <bool U>
-__global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
+__global__ void __launch_bounds__(U ? UMMA_THREADS : LEAF_THREADS, U ? UMMA_MIN_BLOCKS : LEAF_MIN_BLOCKS)
 leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored_w, uint32_t chunk_hi, uint32_t count, int first,
                    State16 init, uint32_t* __restrict__ digests, const uint8_t* __restrict__ b_image) {
   extern __shared__ __align__(1024) uint8_t dsm[];
@@ -182,7 +191,7 @@ leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
       const uint4 lo = __ldg(src), hi = __ldg(src + 1);
       s[8] = lo.x, s[9] = lo.y, s[10] = lo.z, s[11] = lo.w, s[12] = hi.x, s[13] = hi.y, s[14] = hi.z, s[15] = hi.w;
       if constexpr (U)
-        p1u_compress<8, LEAF_SYNC != 0>(uc, s, c_p1);
+        p1u_compress<8, UMMA_SYNC>(uc, s, c_p1);
       else
         p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
     }
@@ -197,7 +206,7 @@ leaf_absorb_kernel(const uint32_t* __restrict__ mat, uint64_t h, uint32_t stored
 // One level: next[i] = C(prev[2i] || prev[2i+1])[0..8), one thread per parent.  Used while a level still fills
 // the machine; the short tail of the tree goes through tree_levels_kernel below.
 template <bool U>
-__global__ void __launch_bounds__(LEAF_THREADS, LEAF_MIN_BLOCKS)
+__global__ void __launch_bounds__(U ? UMMA_THREADS : LEAF_THREADS, U ? UMMA_MIN_BLOCKS : LEAF_MIN_BLOCKS)
 tree_level_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* __restrict__ next, const uint8_t* __restrict__ b_image) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   P1uCtx uc;
@@ -212,7 +221,7 @@ tree_level_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* 
     s[0] = a.x, s[1] = a.y, s[2] = a.z, s[3] = a.w, s[4] = b.x, s[5] = b.y, s[6] = b.z, s[7] = b.w;
     s[8] = c.x, s[9] = c.y, s[10] = c.z, s[11] = c.w, s[12] = d.x, s[13] = d.y, s[14] = d.z, s[15] = d.w;
     if constexpr (U)
-      p1u_compress<8, LEAF_SYNC != 0>(uc, s, c_p1);
+      p1u_compress<8, UMMA_SYNC>(uc, s, c_p1);
     else
       p1_compress<8, P1Tables, LEAF_SYNC != 0>(s, c_p1);
     if (live) {
@@ -280,12 +289,12 @@ static State16 zero_suffix_state_host(uint32_t n_zero_chunks) {
 }
 
 // CTAs of a leaf kernel over h rows: one per LEAF_THREADS rows, capped at LM_LEAF_GRID (environment, 0 = no cap) CTAs
-static uint64_t leaf_grid(uint64_t h) {
+static uint64_t leaf_grid(uint64_t h, int threads = LEAF_THREADS) {
   static const long cap = [] {
     const char* e = getenv("LM_LEAF_GRID");
     return e ? atol(e) : (long)LEAF_DEFAULT_GRID;
   }();
-  const uint64_t blocks = (h + LEAF_THREADS - 1) / LEAF_THREADS;
+  const uint64_t blocks = (h + threads - 1) / threads;
   return cap > 0 && blocks > (uint64_t)cap ? (uint64_t)cap : blocks;
 }
 
@@ -309,12 +318,13 @@ cudaError_t merkle_leaf_digests(cudaStream_t stream, const uint32_t* d_mat, uint
   const int T = LEAF_THREADS;
   const uint64_t blocks = leaf_grid(h);
   if (use_umma()) {
+    const uint64_t ublocks = leaf_grid(h, UMMA_THREADS);
     const uint8_t* img = nullptr;
     cudaError_t e = umma_b_image(&img);
     if (e != cudaSuccess) return e;
     if ((e = umma_attr(leaf_sponge_kernel<true>, LEAF_GROUPS)) != cudaSuccess) return e;
-    leaf_sponge_kernel<true><<<(unsigned)blocks, T, p1u_smem_bytes(LEAF_GROUPS), stream>>>(d_mat, h, stored_w, lim, virt_w, from_state,
-                                                                                            init, d_digests, img);
+    leaf_sponge_kernel<true><<<(unsigned)ublocks, UMMA_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
+        d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests, img);
   } else {
     leaf_sponge_kernel<false><<<(unsigned)blocks, T, 0, stream>>>(d_mat, h, stored_w, lim, virt_w, from_state, init, d_digests, nullptr);
   }
@@ -341,7 +351,7 @@ cudaError_t merkle_leaf_absorb_chunks(cudaStream_t stream, const uint32_t* d_mat
     cudaError_t e = umma_b_image(&img);
     if (e != cudaSuccess) return e;
     if ((e = umma_attr(leaf_absorb_kernel<true>, LEAF_GROUPS)) != cudaSuccess) return e;
-    leaf_absorb_kernel<true><<<(unsigned)leaf_grid(h), LEAF_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
+    leaf_absorb_kernel<true><<<(unsigned)leaf_grid(h, UMMA_THREADS), UMMA_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
         d_mat, h, stored_w, chunk_hi, count, first, init, d_digests, img);
   } else {
     leaf_absorb_kernel<false><<<(unsigned)leaf_grid(h), LEAF_THREADS, 0, stream>>>(d_mat, h, stored_w, chunk_hi, count, first, init,
@@ -365,11 +375,11 @@ cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, ui
   }
   while (n / 2 >= 8192) {
     uint32_t* next = cur + 8 * n;
-    const unsigned blocks = (unsigned)((n / 2 + LEAF_THREADS - 1) / LEAF_THREADS);
     if (img)
-      tree_level_kernel<true><<<blocks, LEAF_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(cur, n / 2, next, img);
+      tree_level_kernel<true><<<(unsigned)((n / 2 + UMMA_THREADS - 1) / UMMA_THREADS), UMMA_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
+          cur, n / 2, next, img);
     else
-      tree_level_kernel<false><<<blocks, LEAF_THREADS, 0, stream>>>(cur, n / 2, next, nullptr);
+      tree_level_kernel<false><<<(unsigned)((n / 2 + LEAF_THREADS - 1) / LEAF_THREADS), LEAF_THREADS, 0, stream>>>(cur, n / 2, next, nullptr);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

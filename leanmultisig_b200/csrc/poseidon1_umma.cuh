@@ -40,10 +40,10 @@
 namespace lm {
 
 // image of the three B matrices in their shared-memory (canonical K-major) layout
-constexpr int P1U_B_MDS = 0;              // 64 x 64
-constexpr int P1U_B_G = 4096;             // 96 x 64 (84 live columns)
-constexpr int P1U_B_MV = 4096 + 6144;     // 64 x 160 (60 live columns, 144 live k)
-constexpr int P1U_B_BYTES = 4096 + 6144 + 10240;
+constexpr int P1U_B_MDS = 0;              // 64 x 128
+constexpr int P1U_B_G = 8192;             // 96 x 64 (84 live columns)
+constexpr int P1U_B_MV = 8192 + 6144;     // 64 x 160 (60 live columns, 145 live k)
+constexpr int P1U_B_BYTES = 8192 + 6144 + 10240;
 constexpr int P1U_A_BYTES = 128 * 160;    // one group's A rows
 constexpr int P1U_TMEM_COLS_PER_GROUP = 128;
 
@@ -53,21 +53,28 @@ inline void p1u_build_b_image(const P1Tables& T, uint8_t* img) {
   auto at = [&](int base, int kchunks, int n, int k) -> uint8_t& {
     return img[base + (n / 8) * (kchunks * 128) + (k / 16) * 128 + (n % 8) * 16 + (k % 16)];
   };
-  const uint32_t C[16] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
-  for (int o = 0; o < 16; o++)
-    for (int e = 0; e < 16; e++)
-      for (int l = 0; l < 4; l++) at(P1U_B_MDS, 4, 4 * o + l, 4 * e + l) = (uint8_t)C[(o - e) & 15];
-  auto put = [&](int base, int kchunks, int o, int kword, uint32_t m) {
-    for (int i = 0; i < 4; i++) {
-      const uint32_t mi = (uint32_t)((((uint64_t)m) << (8 * i)) % KB_P);
-      for (int j = 0; j < 4; j++) at(base, kchunks, 4 * o + j, 4 * kword + i) = (uint8_t)(mi >> (8 * j));
+  // limb i of input word `kword` (words of LIMBS bytes) times the constant m: byte j of m 2^(8 i) mod p goes to column 4 o + j
+  auto put = [&](int base, int kchunks, int o, int kword, uint32_t m, int limbs = 4) {
+    uint64_t mi = m % KB_P;
+    for (int i = 0; i < limbs; i++) {
+      for (int j = 0; j < 4; j++) at(base, kchunks, 4 * o + j, limbs * kword + i) = (uint8_t)(mi >> (8 * j));
+      mi = (mi << 8) % KB_P;
     }
   };
+  // MDS: the inputs are the UNREDUCED 64-bit S-box products w = a^2 R^-1 * a (8 limbs), the constant is 4 C R^-1 mod p
+  uint64_t rinv = 1, base = (1ull << 32) % KB_P;
+  for (uint32_t e = KB_P - 2; e; e >>= 1, base = base * base % KB_P)
+    if (e & 1) rinv = rinv * base % KB_P;
+  const uint32_t C[16] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
+  for (int o = 0; o < 16; o++)
+    for (int e = 0; e < 16; e++) put(P1U_B_MDS, 8, o, e, (uint32_t)(4 * C[(o - e) & 15] * rinv % KB_P), 8);
   for (int r = 0; r < 21; r++)
     for (int e = 0; e < 16; e++) put(P1U_B_G, 4, r, e, T.G[r][e]);
   for (int o = 0; o < 15; o++) {
     for (int e = 0; e < 16; e++) put(P1U_B_MV, 10, o, e, T.MI[o][e]);
     for (int q = 0; q < 20; q++) put(P1U_B_MV, 10, o, 16 + q, T.V[o][q]);
+    // the additive constant rides on a byte of the A rows that is always 1 (k = 144, chunk 9)
+    for (int j = 0; j < 4; j++) at(P1U_B_MV, 10, 4 * o + j, 144) = (uint8_t)(T.LANE_CONST[o] >> (8 * j));
   }
 }
 
@@ -128,6 +135,10 @@ struct P1uCtx {
 };
 LM_HD constexpr int p1u_smem_bytes(int groups) { return P1U_B_BYTES + groups * P1U_A_BYTES + 64; }
 
+__device__ __forceinline__ void p1u_store_chunk(const P1uCtx& c, int chunk, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.a_row + chunk * 128), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+}
+
 __device__ __forceinline__ P1uCtx p1u_setup(uint8_t* smem /* 1024-byte aligned */, const uint8_t* __restrict__ b_image, int groups) {
   const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, r = tid & 127;
   uint8_t* sb = smem;
@@ -158,6 +169,7 @@ __device__ __forceinline__ P1uCtx p1u_setup(uint8_t* smem /* 1024-byte aligned *
   c.parity = 0;
   c.group = g;
   c.leader = r == 0;
+  p1u_store_chunk(c, 9, 1u, 0u, 0u, 0u);  // k = 144 is the constant 1 (LANE_CONST column of the MI | V product), the rest padding
   return c;
 }
 __device__ __forceinline__ void p1u_teardown(const P1uCtx& c, int groups) {
@@ -167,19 +179,17 @@ __device__ __forceinline__ void p1u_teardown(const P1uCtx& c, int groups) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem_alloc), "r"(groups * P1U_TMEM_COLS_PER_GROUP) : "memory");
 }
 
-__device__ __forceinline__ void p1u_store_chunk(const P1uCtx& c, int chunk, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.a_row + chunk * 128), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-}
-
 // rows are written: run K_STEPS MMAs of N columns against the B matrix at b_off and wait for the accumulators
 template <int N, int K_STEPS, int B_OFF, int B_KCHUNKS>
 __device__ __forceinline__ void p1u_product(P1uCtx& c) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  if (c.group == 0)
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-  else
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+  switch (c.group) {  // immediate barrier ids: a register operand makes ptxas reserve all 16
+    case 0: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+  }
   if (c.leader) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint64_t da = p1u_desc(c.a_base, 1280), db = p1u_desc(c.b_base + B_OFF, B_KCHUNKS * 128);
@@ -193,27 +203,42 @@ __device__ __forceinline__ void p1u_product(P1uCtx& c) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// value-preserving recombination of four accumulator columns: v0 + 2^8 v1 + 2^16 v2 + 2^24 v3 (each < 2^24) shifted left by
-// SHIFT, plus init (< 2^32)
+// Recombination of four accumulator columns and Montgomery reduction in one: returns a value congruent to
+//   ((v0 + 2^8 v1 + 2^16 v2 + 2^24 v3) 2^SHIFT + init) / 2^32   in (., . + p],   provided init + (v0 << SHIFT) + (v1 << (8 + SHIFT)) < 2^32 (MDS: v <= 128 * 255^2 < 2^23, init < p: < 2^32 - 2^24;
+// G: v < 2^22, init < p; MI | V: v < 2^23.2, init = 0 — its constant is a column of B).
+// The 64-bit sum is never formed by the multiplier: its low word and its high word (a shift and a carry) are built on the ALU
+// pipe and handed to the two multiplications of the reduction (m = lo p^-1, hi(m p)) — the multiplier pipe is what bounds the
+// kernel, and a mad.wide with a 64-bit addend per shift would put 10 of its cycles on every output.
 template <int SHIFT>
-__device__ __forceinline__ uint64_t p1u_combine(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
-  const uint32_t x = v0 + (v1 << 8), y = v2 + (v3 << 8);
-  return (((uint64_t)x) << SHIFT) + (((uint64_t)y) << (16 + SHIFT)) + init;
+__device__ __forceinline__ uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
+  const uint32_t a = init + (v0 << SHIFT) + (v1 << (8 + SHIFT));  // < 2^32: no carry
+  const uint32_t b = v2 + (v3 << 8);
+  const uint32_t lo = a + (b << (16 + SHIFT));
+  const uint32_t hi = (b >> (16 - SHIFT)) + (lo < a ? 1u : 0u);
+  const uint32_t m = lo * 0x81000001u;
+  const uint64_t u = mul_wide(m, c_kb.p);
+  return hi - (uint32_t)(u >> 32) + c_kb.p;
 }
 
-// out[i] = redc(rc[i] + 4 * sum_j C[(i - j) mod 16] a3[j]), i < N_OUT: p1_mds_redc on the tensor cores
+// S-boxes and MDS of one full round: out[i] == (rc[i] + 4 sum_j C[(i - j) mod 16] a[j]^3 R^-2 R^-1) R^-1, i < N_OUT — what
+// p1_sbox_lazy + p1_mds_redc compute, with the second reduction of every S-box folded into the matrix: the product
+// w = (a^2 R^-1) a is stored UNREDUCED (8 limbs per lane, K = 128) and B carries 4 C R^-1 2^(8 i) mod p for limb i.
 template <int N_OUT>
-__device__ __forceinline__ void p1u_mds_redc(P1uCtx& c, const uint32_t a3[16], const uint32_t* rc, uint32_t out[16]) {
+__device__ __forceinline__ void p1u_sbox_mds_redc(P1uCtx& c, const uint32_t a[16], const uint32_t* rc, uint32_t out[16]) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) p1u_store_chunk(c, k, a3[4 * k], a3[4 * k + 1], a3[4 * k + 2], a3[4 * k + 3]);
-  p1u_product<4 * N_OUT, 2, P1U_B_MDS, 4>(c);
+  for (int k = 0; k < 8; k++) {
+    const uint64_t w0 = mul_wide(kb_mul_lazy(a[2 * k], a[2 * k]), a[2 * k]);
+    const uint64_t w1 = mul_wide(kb_mul_lazy(a[2 * k + 1], a[2 * k + 1]), a[2 * k + 1]);
+    p1u_store_chunk(c, k, (uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+  }
+  p1u_product<4 * N_OUT, 4, P1U_B_MDS, 8>(c);
 #pragma unroll
   for (int h = 0; h < N_OUT / 8; h++) {
     uint32_t v[32];
     p1u_ld32(c.tmem + 32 * h, v);
 #pragma unroll
     for (int i = 0; i < 8; i++)
-      out[8 * h + i] = kb_redc_lazy(p1u_combine<2>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], rc ? rc[8 * h + i] : 0u));
+      out[8 * h + i] = p1u_combine_redc<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], rc ? rc[8 * h + i] : 0u);
   }
 }
 
@@ -231,7 +256,7 @@ __device__ __forceinline__ void p1u_partial_section(P1uCtx& c, const uint32_t x[
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const int r = 8 * h + i;
-      if (r < 21) d[r] = kb_redc_lazy(p1u_combine<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], r == 0 ? 0u : t.G_CONST[r < 21 ? r : 0]));
+      if (r < 21) d[r] = p1u_combine_redc<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], r == 0 ? 0u : t.G_CONST[r < 21 ? r : 0]);
     }
   }
   LM_P1_BARRIER();
@@ -251,7 +276,7 @@ __device__ __forceinline__ void p1u_partial_section(P1uCtx& c, const uint32_t x[
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const int o = 8 * h + i;
-      if (o < 15) a[o + 1] = kb_redc_lazy(p1u_combine<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], t.LANE_CONST[o < 15 ? o : 0]));
+      if (o < 15) a[o + 1] = p1u_combine_redc<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], 0u);
     }
   }
 }
@@ -264,24 +289,18 @@ __device__ __forceinline__ void p1u_permute(P1uCtx& c, uint32_t s[16], const P1T
   for (int i = 0; i < 16; i++) a[i] = kb_add(s[i], T.RC0[i]);
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
-    p1u_mds_redc<16>(c, a, T.RC_INIT[r], x);
+    p1u_sbox_mds_redc<16>(c, a, T.RC_INIT[r], x);
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = x[i];
   }
   p1u_partial_section<SYNC>(c, x, a, T);
 #pragma unroll 1
   for (int r = 0; r < 3; r++) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
-    p1u_mds_redc<16>(c, a, T.RC_TERM[r], x);
+    p1u_sbox_mds_redc<16>(c, a, T.RC_TERM[r], x);
 #pragma unroll
     for (int i = 0; i < 16; i++) a[i] = x[i];
   }
-#pragma unroll
-  for (int i = 0; i < 16; i++) a[i] = p1_sbox_lazy(a[i]);
-  p1u_mds_redc<N_OUT>(c, a, nullptr, x);
+  p1u_sbox_mds_redc<N_OUT>(c, a, nullptr, x);
 #pragma unroll
   for (int i = 0; i < N_OUT; i++) s[i] = kb_mul(x[i], T.FIX);
 }

@@ -18,6 +18,9 @@ __constant__ P1Tables c_p1 =
 #ifndef THREADS
 #define THREADS 256
 #endif
+#ifndef USYNC
+#define USYNC 1
+#endif
 #ifndef MINB
 #define MINB 2
 #endif
@@ -77,12 +80,12 @@ __global__ void __launch_bounds__(THREADS, MINB) umma_chain(const uint32_t* in, 
   uint32_t s[16];
   for (int k = 0; k < 16; k++) s[k] = in[16 * i + k];
   if (full) {
-    p1u_permute<16, true>(c, s, c_p1);
+    p1u_permute<16, USYNC != 0>(c, s, c_p1);
     for (int k = 0; k < 16; k++) out[16 * i + k] = s[k];
   } else {
     for (int it = 0; it < iters; it++) {
       for (int k = 0; k < 8; k++) s[8 + k] = kb_add(s[k], (uint32_t)(it * 8 + k));
-      p1u_compress<8, true>(c, s, c_p1);
+      p1u_compress<8, USYNC != 0>(c, s, c_p1);
     }
     for (int k = 0; k < 8; k++) out[16 * i + k] = s[k];
   }
