@@ -645,9 +645,11 @@ static int commit_impl(lm_ctx* c, const uint32_t* evals, bool evals_on_device, u
     CUT(lm::merkle_leaf_digests(c->stream, t->d_codeword, t->height, t->stored_width, t->full_width, t->effective_width,
                                 t->d_layers));
   } else {
-    // Column groups of 1, 1, 2, 4, 8, .. rate chunks (8 columns each): the first copy is short, every later copy is
-    // hidden behind the transform + hash of the groups before it, and the wide groups absorb several chunks per launch.
-    static const bool even_groups = getenv("LM_COMMIT_EVEN_GROUPS") != nullptr;  // A/B switch: 8 equal groups
+    // Up to 8 equal column groups of whole rate chunks (8 columns each).  With the tensor-core sponge the transform + hash of
+    // a group takes about as long as its copy over PCIe (1.2 ms each per 64 MiB at config 2), so equal groups keep both busy
+    // and leave one group's compute + the tree after the last byte: 13.7 ms end to end against 15.7 ms with the round-1
+    // schedule of 1, 1, 2, 4, .. chunks (LM_COMMIT_DOUBLING_GROUPS=1), whose last group is half of the matrix.
+    static const bool even_groups = getenv("LM_COMMIT_DOUBLING_GROUPS") == nullptr;
     if (need_words > live_words)
       CUT(cudaMemsetAsync(t->d_evals + live_words, 0, (need_words - live_words) * sizeof(uint32_t), c->stream));
     CUT(cudaEventRecord(c->ev_start, c->stream));

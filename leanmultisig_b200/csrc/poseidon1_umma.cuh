@@ -43,7 +43,9 @@ namespace lm {
 constexpr int P1U_B_MDS = 0;              // 64 x 128
 constexpr int P1U_B_G = 8192;             // 96 x 64 (84 live columns)
 constexpr int P1U_B_MV = 8192 + 6144;     // 64 x 160 (60 live columns, 145 live k)
-constexpr int P1U_B_BYTES = 8192 + 6144 + 10240;
+constexpr int P1U_B_T0 = 8192 + 6144 + 10240;  // 48 x 32: z_0..7 into D_8..19
+constexpr int P1U_B_T1 = P1U_B_T0 + 1536;      // 16 x 32: z_8..15 into D_16..19
+constexpr int P1U_B_BYTES = P1U_B_T1 + 512;
 constexpr int P1U_A_BYTES = 128 * 160;    // one group's A rows
 constexpr int P1U_TMEM_COLS_PER_GROUP = 128;
 
@@ -68,8 +70,15 @@ inline void p1u_build_b_image(const P1Tables& T, uint8_t* img) {
   const uint32_t C[16] = {1, 3, 13, 22, 67, 2, 15, 63, 101, 1, 2, 17, 11, 1, 51, 1};
   for (int o = 0; o < 16; o++)
     for (int e = 0; e < 16; e++) put(P1U_B_MDS, 8, o, e, (uint32_t)(4 * C[(o - e) & 15] * rinv % KB_P), 8);
+  // G: output r < 20 is D_r (row r + 1 of G), output 20 the lane entering round 0 (row 0)
   for (int r = 0; r < 21; r++)
-    for (int e = 0; e < 16; e++) put(P1U_B_G, 4, r, e, T.G[r][e]);
+    for (int e = 0; e < 16; e++) put(P1U_B_G, 4, r, e, T.G[r < 20 ? r + 1 : 0][e]);
+  // the strictly lower triangle of the partial rounds, by blocks of 8 rounds: once z_0..7 (z_8..15) are known their
+  // contribution to every LATER block's D_r is one more product accumulated into the same columns
+  for (int r = 8; r < 20; r++)
+    for (int k = 0; k < 8; k++) put(P1U_B_T0, 2, r - 8, k, T.GTRI[r][k]);
+  for (int r = 16; r < 20; r++)
+    for (int k = 8; k < 16; k++) put(P1U_B_T1, 2, r - 16, k - 8, T.GTRI[r][k]);
   for (int o = 0; o < 15; o++) {
     for (int e = 0; e < 16; e++) put(P1U_B_MV, 10, o, e, T.MI[o][e]);
     for (int q = 0; q < 20; q++) put(P1U_B_MV, 10, o, 16 + q, T.V[o][q]);
@@ -94,6 +103,11 @@ __device__ __forceinline__ void p1u_mma(uint32_t tmem_d, uint64_t da, uint64_t d
       : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0)
       : "memory");
 }
+__device__ __forceinline__ bool p1u_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ bool p1u_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -117,6 +131,14 @@ __device__ __forceinline__ void p1u_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void p1u_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 LM_HD constexpr uint32_t p1u_idesc(uint32_t n) { return (2u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
 // Per-thread view of the group's tensor-core plumbing.  Kernels: dynamic shared memory of p1u_smem_bytes(groups), blockDim.x =
@@ -131,7 +153,7 @@ struct P1uCtx {
   uint32_t tmem_alloc;
   uint32_t parity;
   uint32_t group;
-  bool leader;
+  bool issuer_warp;  // warp 0 of the group (warp-uniform): one elected lane of it issues the MMAs
 };
 LM_HD constexpr int p1u_smem_bytes(int groups) { return P1U_B_BYTES + groups * P1U_A_BYTES + 64; }
 
@@ -168,7 +190,7 @@ __device__ __forceinline__ P1uCtx p1u_setup(uint8_t* smem /* 1024-byte aligned *
   c.tmem = c.tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
   c.parity = 0;
   c.group = g;
-  c.leader = r == 0;
+  c.issuer_warp = __shfl_sync(0xffffffffu, r >> 5, 0) == 0;
   p1u_store_chunk(c, 9, 1u, 0u, 0u, 0u);  // k = 144 is the constant 1 (LANE_CONST column of the MI | V product), the rest padding
   return c;
 }
@@ -180,22 +202,31 @@ __device__ __forceinline__ void p1u_teardown(const P1uCtx& c, int groups) {
 }
 
 // rows are written: run K_STEPS MMAs of N columns against the B matrix at b_off and wait for the accumulators
-template <int N, int K_STEPS, int B_OFF, int B_KCHUNKS>
+// A_CHUNK0: first 16-byte chunk of the rows that takes part; D_COL0: first accumulator column; ACC: add to what the columns hold
+template <int N, int K_STEPS, int B_OFF, int B_KCHUNKS, int A_CHUNK0 = 0, int D_COL0 = 0, bool ACC = false>
 __device__ __forceinline__ void p1u_product(P1uCtx& c) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  switch (c.group) {  // immediate barrier ids: a register operand makes ptxas reserve all 16
-    case 0: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
-    case 1: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
-    default: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+  if (blockDim.x == 128) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  } else {
+    switch (c.group) {  // immediate barrier ids: a register operand makes ptxas reserve all 16
+      case 0: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
+      case 1: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+      case 2: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+      default: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+    }
   }
-  if (c.leader) {
+  if (c.issuer_warp) {  // warp-uniform branch, then one elected lane: the other warps skip the issue code altogether
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint64_t da = p1u_desc(c.a_base, 1280), db = p1u_desc(c.b_base + B_OFF, B_KCHUNKS * 128);
+    if (p1u_elect_one()) {
+      const uint64_t da = p1u_desc(c.a_base + A_CHUNK0 * 128, 1280), db = p1u_desc(c.b_base + B_OFF, B_KCHUNKS * 128);
 #pragma unroll
-    for (int k = 0; k < K_STEPS; k++) p1u_mma(c.tmem_d, da + (uint64_t)(k * 256 >> 4), db + (uint64_t)(k * 256 >> 4), p1u_idesc(N), k > 0);
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.bar) : "memory");
+      for (int k = 0; k < K_STEPS; k++)
+        p1u_mma(c.tmem_d + D_COL0, da + (uint64_t)(k * 256 >> 4), db + (uint64_t)(k * 256 >> 4), p1u_idesc(N), ACC || k > 0);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.bar) : "memory");
+    }
+    __syncwarp();
   }
   for (uint32_t spins = 0; !p1u_try_wait(c.bar, c.parity);)
     if (++spins > (1u << 26)) __trap();  // a lost MMA completion must not hang the device
@@ -226,10 +257,11 @@ __device__ __forceinline__ uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, u
 template <int N_OUT>
 __device__ __forceinline__ void p1u_sbox_mds_redc(P1uCtx& c, const uint32_t a[16], const uint32_t* rc, uint32_t out[16]) {
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const uint64_t w0 = mul_wide(kb_mul_lazy(a[2 * k], a[2 * k]), a[2 * k]);
-    const uint64_t w1 = mul_wide(kb_mul_lazy(a[2 * k + 1], a[2 * k + 1]), a[2 * k + 1]);
-    p1u_store_chunk(c, k, (uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+  for (int k = 0; k < 16; k++) {
+    // 64-bit stores: the product is an aligned register pair as it leaves the multiplier (128-bit stores cost ~24 register
+    // moves per round to line up quads; the 2-way bank conflict of the 8-byte pattern is invisible next to that)
+    const uint64_t w = mul_wide(kb_mul_lazy(a[k], a[k]), a[k]);
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(c.a_row + (k >> 1) * 128 + (k & 1) * 8), "l"(w) : "memory");
   }
   p1u_product<4 * N_OUT, 4, P1U_B_MDS, 8>(c);
 #pragma unroll
@@ -242,32 +274,88 @@ __device__ __forceinline__ void p1u_sbox_mds_redc(P1uCtx& c, const uint32_t a[16
   }
 }
 
-// The partial section of p1_partial_section: x = state entering (lanes < p + 2^9), a = state leaving.
+// the 64-bit value v0 + 2^8 v1 + 2^16 v2 + 2^24 v3 + init (same no-carry condition as p1u_combine_redc), built on the ALU pipe
+__device__ __forceinline__ uint64_t p1u_combine64(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
+  const uint32_t a = init + v0 + (v1 << 8);
+  const uint32_t b = v2 + (v3 << 8);
+  const uint32_t lo = a + (b << 16);
+  const uint32_t hi = (b >> 16) + (lo < a ? 1u : 0u);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+#ifdef LM_P1_IMM
+// one partial round: z_R = s0^3, s0 <- (y + FR0[R] z_R + sum_{K0 <= k < R} GTRI[R][k] z_k) / 2^32, where y (< 2^48) already
+// holds D_R R and the triangle terms of the earlier blocks.  At most 4 products (< 0.2462 * 2^64 each) sit on a folded accumulator.
+template <int R, int K0, int... I>
+__device__ __forceinline__ void p1u_partial_round(uint32_t& s0, uint64_t y, uint32_t z[20], std::integer_sequence<int, I...>) {
+  constexpr P1Tables t = p1_tables_constexpr();
+  z[R] = kb_canon(p1_sbox_lazy(s0));
+  uint64_t acc = y;
+  {
+    constexpr uint32_t c = t.FR0[R];
+    acc = mad_wide(z[R], c, acc);
+  }
+  (([&] {
+     if ((1 + I) % 4 == 0) acc = kb_fold(acc);
+     constexpr uint32_t c = t.GTRI[R][K0 + I];
+     acc = mad_wide(z[K0 + I], c, acc);
+   }()),
+   ...);
+  s0 = kb_redc_lazy(kb_fold(acc));
+}
+template <int K0, int... J>
+__device__ __forceinline__ void p1u_partial_block(uint32_t& s0, const uint64_t* y, uint32_t z[20], std::integer_sequence<int, J...>) {
+  ((p1u_partial_round<K0 + J, K0>(s0, y[J], z, p1_seq<J>{})), ...);
+}
+#endif
+
+// The partial section of p1_partial_section: x = state entering (lanes < p + 2^15), a = state leaving.
+// D = G x' stays in tensor memory as four columns per round; the rounds run in blocks of 8, 8 and 4: a block reads its columns
+// (64-bit values, no reduction), runs its rounds with the triangle terms of its OWN block as scalar multiply-accumulates, stores
+// its z and lets one more product add GTRI z to the columns of the later blocks: 62 + 20 scalar multiply-accumulates instead of 210.
 template <bool SYNC>
 __device__ __forceinline__ void p1u_partial_section(P1uCtx& c, const uint32_t x[16], uint32_t a[16], const P1Tables& t) {
+#ifdef LM_P1_IMM  // (the host pass of nvcc parses this body too)
 #pragma unroll
   for (int k = 0; k < 4; k++) p1u_store_chunk(c, k, x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
   p1u_product<96, 2, P1U_B_G, 4>(c);
-  uint32_t d[21];  // d[0] = first lane entering round 0, d[1 + r] = D_r
-#pragma unroll
-  for (int h = 0; h < 3; h++) {
-    uint32_t v[32];
-    p1u_ld32(c.tmem + 32 * h, v);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int r = 8 * h + i;
-      if (r < 21) d[r] = p1u_combine_redc<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], r == 0 ? 0u : t.G_CONST[r < 21 ? r : 0]);
-    }
-  }
-  LM_P1_BARRIER();
   uint32_t z[20];
-  uint32_t s0 = d[0];
-#ifdef LM_P1_IMM  // (the host pass of nvcc parses this body too)
-  p1_partial_rounds_imm<SYNC>(s0, d + 1, z, p1_seq<20>{});
-#endif
-  a[0] = s0;
+  uint32_t s0;
+  uint64_t y[8];
+  {
+    uint32_t v[4];
+    p1u_ld4(c.tmem + 80, v);
+    s0 = p1u_combine_redc<0>(v[0], v[1], v[2], v[3], 0u);
+  }
+  {
+    uint32_t v[32];
+    p1u_ld32(c.tmem, v);
 #pragma unroll
-  for (int k = 0; k < 5; k++) p1u_store_chunk(c, 4 + k, z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+    for (int i = 0; i < 8; i++) y[i] = p1u_combine64(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], t.G_CONST[1 + i]);
+  }
+  p1u_partial_block<0>(s0, y, z, p1_seq<8>{});
+  p1u_store_chunk(c, 4, z[0], z[1], z[2], z[3]);
+  p1u_store_chunk(c, 5, z[4], z[5], z[6], z[7]);
+  p1u_product<48, 1, P1U_B_T0, 2, 4, 32, true>(c);
+  {
+    uint32_t v[32];
+    p1u_ld32(c.tmem + 32, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) y[i] = p1u_combine64(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], t.G_CONST[9 + i]);
+  }
+  p1u_partial_block<8>(s0, y, z, p1_seq<8>{});
+  p1u_store_chunk(c, 6, z[8], z[9], z[10], z[11]);
+  p1u_store_chunk(c, 7, z[12], z[13], z[14], z[15]);
+  p1u_product<16, 1, P1U_B_T1, 2, 6, 64, true>(c);
+  {
+    uint32_t v[32];  // columns 64..79 are D_16..19 (80..83: the first lane, already used; the rest is not written)
+    p1u_ld32(c.tmem + 64, v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) y[i] = p1u_combine64(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], t.G_CONST[17 + i]);
+  }
+  p1u_partial_block<16>(s0, y, z, p1_seq<4>{});
+  a[0] = s0;
+  p1u_store_chunk(c, 8, z[16], z[17], z[18], z[19]);
   p1u_product<64, 5, P1U_B_MV, 10>(c);
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -279,6 +367,7 @@ __device__ __forceinline__ void p1u_partial_section(P1uCtx& c, const uint32_t x[
       if (o < 15) a[o + 1] = p1u_combine_redc<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], 0u);
     }
   }
+#endif
 }
 
 // Permutation; N_OUT = 16 or 8 (digest half).  s: canonical in, canonical out.
