@@ -370,6 +370,11 @@ int lm_pow_grind(lm_ctx* ctx, const uint32_t state[16], uint32_t bits, uint64_t*
 /* Poseidon1KoalaBear16::permute_mut on ONE state on the host (poseidon1_koalabear_16.rs:873): the duplex sponge
  * of challenger.rs:32-36 is sequential, one permutation per observation, so it is not a device job. */
 int lm_host_poseidon1_permute(uint32_t state[16]);
+/* The same permutation through a CPU model of the tensor-core formulation the Merkle kernels run (csrc/poseidon1_umma.cuh:
+ * identical B-matrix image, row layout, recombination and block structure, every tcgen05.mma replaced by the integer dot
+ * products it stands for).  A test hook: lets the CPU tier pin the formulation against poseidon1_koalabear_16.rs:873 without a
+ * GPU.  Not a product path. */
+int lm_host_poseidon1_umma_model(uint32_t state[16]);
 
 /* ---- Host spine in C++ (csrc/spine.cu), built above the entry points of this header ---------------------------
  * lm_fs mirrors ProverState + Challenger (crates/backend/fiat-shamir/src/prover.rs:28-178, challenger.rs:8-76): the

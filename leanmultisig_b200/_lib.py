@@ -141,6 +141,7 @@ def lib() -> C.CDLL:
             "lm_poseidon16_fill_trace": [vp, C.POINTER(vp), u64],
             "lm_dev_poseidon16_fill_trace": [vp, vp, u64],
             "lm_host_poseidon1_permute": [u32p],
+            "lm_host_poseidon1_umma_model": [u32p],
             "lm_fs_new": [vp, C.POINTER(vp)],
             "lm_fs_free": [vp],
             "lm_fs_add_scalars": [vp, u32p, u64],

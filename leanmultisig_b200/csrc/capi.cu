@@ -376,6 +376,11 @@ int lm_host_poseidon1_permute(uint32_t* state) {
   lm::poseidon1_permute_host(state);
   return LM_OK;
 }
+int lm_host_poseidon1_umma_model(uint32_t* state) {
+  if (!state) return fail(LM_ERR_INVALID, "lm_host_poseidon1_umma_model: null state");
+  lm::poseidon1_permute_umma_model_host(state);
+  return LM_OK;
+}
 
 int lm_dev_reorder_and_dft(lm_ctx* c, const uint32_t* d_evals, uint32_t n_vars, uint32_t dim, uint32_t folding,
                            uint32_t log_inv_rate, uint32_t dft_n_cols, uint32_t* d_out) {

@@ -20,6 +20,7 @@
 #include "poseidon1.cuh"
 #include "poseidon1_umma.cuh"
 #include <mutex>
+#include <vector>
 
 namespace lm {
 
@@ -376,7 +377,7 @@ cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, ui
   while (n / 2 >= 8192) {
     uint32_t* next = cur + 8 * n;
     if (img)
-      tree_level_kernel<true><<<(unsigned)((n / 2 + UMMA_THREADS - 1) / UMMA_THREADS), UMMA_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
+      tree_level_kernel<true><<<(unsigned)leaf_grid(n / 2, UMMA_THREADS), UMMA_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
           cur, n / 2, next, img);
     else
       tree_level_kernel<false><<<(unsigned)((n / 2 + LEAF_THREADS - 1) / LEAF_THREADS), LEAF_THREADS, 0, stream>>>(cur, n / 2, next, nullptr);
@@ -543,5 +544,15 @@ cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bi
 // The transcript sponge itself (challenger.rs:8-76) is one permutation per 8 absorbed words, strictly sequential:
 // it stays on the host, evaluated with the same arithmetic header as the device code.
 void poseidon1_permute_host(uint32_t state[16]) { p1_permute<16>(state, h_p1); }
+
+// CPU model of the tensor-core formulation (poseidon1_umma.cuh): the B image the kernels load, the MMAs as integer dot products
+void poseidon1_permute_umma_model_host(uint32_t state[16]) {
+  static const std::vector<uint8_t> img = [] {
+    std::vector<uint8_t> v(P1U_B_BYTES);
+    p1u_build_b_image(h_p1, v.data());
+    return v;
+  }();
+  p1u_model_permute(h_p1, img.data(), state);
+}
 
 }  // namespace lm

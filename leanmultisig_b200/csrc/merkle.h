@@ -24,4 +24,6 @@ cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bi
                       unsigned long long* d_best, uint64_t* witness);
 // one Poseidon1 permutation on the host (Fiat-Shamir transcript sponge)
 void poseidon1_permute_host(uint32_t state[16]);
+// the same permutation through the CPU model of the tensor-core formulation (test hook for the CPU tier)
+void poseidon1_permute_umma_model_host(uint32_t state[16]);
 }  // namespace lm

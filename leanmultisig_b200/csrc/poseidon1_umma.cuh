@@ -1,39 +1,41 @@
 // Poseidon1-KoalaBear width-16 for sm_100a with every "constant matrix x state" product on the 5th-generation tensor cores
-// (tcgen05.mma.kind::i8, accumulators in tensor memory), one state per thread, 128 states per MMA.
+// (tcgen05.mma.kind::i8, accumulators in tensor memory), one state per thread, 128 states per MMA.  DESIGN.md 2.1b.
 //
 // Same function as poseidon1.cuh (poseidon1_koalabear_16.rs:873-912 permute_generic / :1020-1030 compress_in_place of the
-// reference), bit for bit on the canonical outputs.  What moves off the multiplier pipe (IMAD.WIDE 4 cycles, DFMA ~2.2 cycles per
-// warp instruction and sub-partition; the one-state-per-thread kernels keep it 79 % busy):
-//   * the circulant MDS of the 8 full rounds           16 x 16, entries <= 101          (was 96 DFMA + 48 DADD per state and round)
-//   * D = G x' and the first lane (21 x 16) entering the partial section                 (was 336 IMAD.WIDE + folds)
-//   * lanes 1..15 leaving it, MI x' + V z (15 x 36)                                      (was 540 IMAD.WIDE + folds)
-// What stays: the S-boxes, the serial chain s0_{r+1} = FR0[r] z_r + D_r + sum_{k<r} GTRI[r][k] z_k of the 20 partial rounds, and
-// one Montgomery reduction per produced lane.
+// reference), bit for bit on the canonical outputs.  What moves off the multiplier pipe (IMAD.WIDE 4 cycles, IMAD 2, DFMA ~2.2
+// per warp instruction and sub-partition; the one-state-per-thread kernels keep it 79 % busy):
+//   * the circulant MDS of the 8 full rounds, 16 x 16 (was 96 DFMA + 48 DADD per state and round) AND the second Montgomery
+//     reduction of every full-round S-box (the MDS takes the unreduced 64-bit product, its constant is 4 C R^-1)
+//   * D = G x' and the first lane entering the partial section, 21 x 16                  (was 336 IMAD.WIDE + folds)
+//   * lanes 1..15 leaving it, MI x' + V z + const, 15 x 37                               (was 540 IMAD.WIDE + folds)
+//   * the strictly lower triangle GTRI z of the partial rounds across blocks of 8 rounds (128 of its 190 IMAD.WIDE)
+// What stays: the S-boxes, the serial chain of the 20 partial rounds with the triangle terms of its own block, and one
+// Montgomery reduction per produced lane.
 //
 // Why tcgen05 and not mma.sync: on B200 the legacy warp-level IMMA.16832.U8.U8 does NOT overlap with the multiplier pipe
-// (tools/microbench/imma_mix.cu, profiles/r02_imma_gonogo.txt: 16 IMMA + 16 IMAD.WIDE take 248 cycles, 128 + 82 apart); a first
-// version of this file on mma.sync was bit-exact and 18 % SLOWER.  tcgen05.mma is asynchronous: one thread issues it for 128
-// states, the product runs in the tensor unit while the other warps of the SM keep the integer pipes busy.
+// (tools/microbench/imma_mix.cu, profiles/r02_p1_umma.txt: 16 IMMA + 16 IMAD.WIDE take 248 cycles, 128 + 82 apart); the
+// mma.sync version of this file (poseidon1_mma.cuh) is bit-exact and 18 % SLOWER than the scalar kernel.  tcgen05.mma is
+// asynchronous: one thread issues it for 128 states, the product runs in the tensor unit while the other warps of the SM keep
+// the integer pipes busy.
 //
 // Mapping.  M = 128 states = the 4 warps of a "group" (thread i of the group = row i = TMEM lane i, so tcgen05.ld.32x32b hands
 // every thread the accumulators of ITS state: the one-state-per-thread layout of poseidon1.cuh is kept, no transposition).
-// A (shared memory, K-major, no swizzle: 8 rows x 16 bytes core matrices, LBO = 128, SBO = 1280): row = the state's words as
-// they stand — the four bytes of a word are its four u8 limbs: k = 4 e + i  <->  limb i of word e.  Chunks 0..3 hold the 16 state
-// words, chunks 4..8 the 20 S-box outputs z of the partial rounds.
-// B (shared memory, N x K, K-major):
-//   MDS   column 4 o + l:  C[(o - e) mod 16] at k = 4 e + l, else 0; S_l = sum_e C[..] limb_l(x_e) < 2^17 and
-//         4 (C x)_o + rc = 4 (S0 + 2^8 S1 + 2^16 S2 + 2^24 S3) + rc — the exact integer p1_mds_redc reduces;
-//   G, MI, V (entries are 31-bit constants): limb i of an input is multiplied by the constant PRE-SHIFTED mod p,
-//         M_i = M 2^(8 i) mod p, whose four bytes j go to columns 4 o + j:  T_j = sum_(e,i) limb_i(x_e) byte_j(M_i[o][e]) < 2^24,
-//         sum_e M[o][e] x_e  ==  T0 + 2^8 T1 + 2^16 T2 + 2^24 T3  (mod p), < 2^47: four accumulator columns and ONE reduction per
-//         output instead of 16-36 multiply-accumulates with folds.
-// The recombination is shifts and adds; the reduction is kb_redc_lazy as before.  Intermediate lanes are congruent to those of
-// poseidon1.cuh (not always the same lazy representative); the bounds the S-boxes need (< 1.43 p) hold with room: every
-// reduction here sees less than 2^47, i.e. returns less than p + 2^15.
+// A (shared memory, K-major, no swizzle: 8 rows x 16 bytes core matrices, LBO = 128, SBO = 1280): a row of ten 16-byte chunks
+// written by its thread with ordinary stores — the bytes of a word are its u8 limbs.  Full rounds: chunks 0..7 = the sixteen
+// 64-bit S-box products (k = 8 e + i).  Partial section: chunks 0..3 = the 16 words of x' (k = 4 e + i), chunks 4..8 = the 20
+// S-box outputs z, byte 144 = the constant 1.
+// B (shared memory, N x K, K-major; image built on the host by p1u_build_b_image): for a 31-bit constant M, limb i of the input
+// is multiplied by M_i = M 2^(8 i) mod p, whose four bytes j go to columns 4 o + j:
+//         T_j = sum_(e,i) limb_i(x_e) byte_j(M_i[o][e]) < 2^24,   sum_e M[o][e] x_e  ==  T0 + 2^8 T1 + 2^16 T2 + 2^24 T3  (mod p),
+// four accumulator columns and ONE reduction per output lane instead of 16-37 multiply-accumulates with folds.
+// The recombination is shifts and adds on the ALU pipe (T0 + 2^8 T1 + const < 2^32 by construction), the reduction is
+// kb_redc_lazy.  Intermediate lanes are congruent to those of poseidon1.cuh (not always the same lazy representative); the
+// bounds the S-boxes need (< 1.43 p) hold with room: every reduction here sees less than 2^48, i.e. returns less than p + 2^16.
 //
-// Cost per permutation and group: 10 round trips (store row -> fence.proxy.async -> 128-thread barrier -> MMA issue -> commit ->
-// mbarrier -> tcgen05.ld), ~450 cycles each when nothing else runs (tools/microbench/umma_i8_probe.cu); with two 256-thread CTAs
-// per SM four groups interleave, so a group's round trip is covered by the S-boxes of the other three.
+// Cost per permutation and group: 12 round trips (store row -> fence.proxy.async -> 128-thread barrier -> MMA issue by one
+// elected lane -> commit -> mbarrier -> tcgen05.ld), ~450 cycles each when nothing else runs
+// (tools/microbench/umma_i8_probe.cu); four 128-thread CTAs per SM interleave, so a group's round trip is covered by the
+// S-boxes of the other three.
 #pragma once
 #include "poseidon1.cuh"
 
@@ -85,6 +87,113 @@ inline void p1u_build_b_image(const P1Tables& T, uint8_t* img) {
     // the additive constant rides on a byte of the A rows that is always 1 (k = 144, chunk 9)
     for (int j = 0; j < 4; j++) at(P1U_B_MV, 10, 4 * o + j, 144) = (uint8_t)(T.LANE_CONST[o] >> (8 * j));
   }
+}
+
+// Recombination of four accumulator columns and Montgomery reduction in one: returns a value congruent to
+//   ((v0 + 2^8 v1 + 2^16 v2 + 2^24 v3) 2^SHIFT + init) / 2^32   in (., . + p],   provided init + (v0 << SHIFT) + (v1 << (8 + SHIFT)) < 2^32 (MDS: v <= 128 * 255^2 < 2^23, init < p: < 2^32 - 2^24;
+// G: v < 2^22, init < p; MI | V: v < 2^23.2, init = 0 — its constant is a column of B).
+// The 64-bit sum is never formed by the multiplier: its low word and its high word (a shift and a carry) are built on the ALU
+// pipe and handed to the two multiplications of the reduction (m = lo p^-1, hi(m p)) — the multiplier pipe is what bounds the
+// kernel, and a mad.wide with a 64-bit addend per shift would put 10 of its cycles on every output.
+template <int SHIFT>
+LM_HD uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
+  const uint32_t a = init + (v0 << SHIFT) + (v1 << (8 + SHIFT));  // < 2^32: no carry
+  const uint32_t b = v2 + (v3 << 8);
+  const uint32_t lo = a + (b << (16 + SHIFT));
+  const uint32_t hi = (b >> (16 - SHIFT)) + (lo < a ? 1u : 0u);
+  const uint32_t m = lo * 0x81000001u;
+  const uint64_t u = mul_wide(m, LM_KB_P_OPAQUE);
+  return hi - (uint32_t)(u >> 32) + LM_KB_P_OPAQUE;
+}
+
+// the 64-bit value v0 + 2^8 v1 + 2^16 v2 + 2^24 v3 + init (same no-carry condition as p1u_combine_redc), built on the ALU pipe
+LM_HD uint64_t p1u_combine64(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
+  const uint32_t a = init + v0 + (v1 << 8);
+  const uint32_t b = v2 + (v3 << 8);
+  const uint32_t lo = a + (b << 16);
+  const uint32_t hi = (b >> 16) + (lo < a ? 1u : 0u);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+
+// ---- CPU model of the formulation -------------------------------------------------------------------------------------------
+// The permutation exactly as the kernels below run it — same B image, same row layout, same recombination and block structure —
+// with every tcgen05.mma replaced by the integer dot products it stands for.  Host test infrastructure for the CPU tier
+// (lm_host_poseidon1_umma_model): pins the image builder, the pre-shifted constants and the no-carry bounds against the oracle
+// without a GPU.
+struct P1uModel {
+  const uint8_t* img;
+  uint8_t row[160];
+  uint32_t col[128];
+  void store_words(int chunk, const uint32_t* w, int n) {
+    for (int i = 0; i < n; i++)
+      for (int b = 0; b < 4; b++) row[16 * chunk + 4 * i + b] = (uint8_t)(w[i] >> (8 * b));
+  }
+  void product(int n, int k_steps, int b_off, int b_kchunks, int a_chunk0 = 0, int d_col0 = 0, bool acc = false) {
+    for (int j = 0; j < n; j++) {
+      uint32_t sum = acc ? col[d_col0 + j] : 0u;
+      for (int k = 0; k < 32 * k_steps; k++)
+        sum += (uint32_t)row[16 * a_chunk0 + k] * img[b_off + (j / 8) * (b_kchunks * 128) + (k / 16) * 128 + (j % 8) * 16 + (k % 16)];
+      col[d_col0 + j] = sum;
+    }
+  }
+};
+inline uint32_t p1u_model_redc(uint64_t t) {  // kb_redc_lazy in the form the device uses
+  const uint32_t m = (uint32_t)t * 0x81000001u;
+  return (uint32_t)(t >> 32) - (uint32_t)(((uint64_t)m * KB_P) >> 32) + KB_P;
+}
+inline void p1u_model_full_round(P1uModel& M, const uint32_t a[16], const uint32_t* rc, uint32_t out[16]) {
+  for (int k = 0; k < 16; k++) {
+    const uint64_t w = (uint64_t)p1u_model_redc((uint64_t)a[k] * a[k]) * a[k];
+    const uint32_t words[2] = {(uint32_t)w, (uint32_t)(w >> 32)};
+    for (int i = 0; i < 2; i++)
+      for (int b = 0; b < 4; b++) M.row[8 * k + 4 * i + b] = (uint8_t)(words[i] >> (8 * b));
+  }
+  M.product(64, 4, P1U_B_MDS, 8);
+  for (int i = 0; i < 16; i++)
+    out[i] = p1u_combine_redc<0>(M.col[4 * i], M.col[4 * i + 1], M.col[4 * i + 2], M.col[4 * i + 3], rc ? rc[i] : 0u);
+}
+inline void p1u_model_permute(const P1Tables& T, const uint8_t* img, uint32_t s[16]) {
+  P1uModel M;
+  M.img = img;
+  for (int i = 0; i < 160; i++) M.row[i] = 0;
+  M.row[144] = 1;
+  uint32_t a[16], x[16];
+  for (int i = 0; i < 16; i++) a[i] = kb_add(s[i], T.RC0[i]);
+  for (int r = 0; r < 4; r++) {
+    p1u_model_full_round(M, a, T.RC_INIT[r], x);
+    for (int i = 0; i < 16; i++) a[i] = x[i];
+  }
+  // partial section
+  M.store_words(0, x, 16);
+  M.product(96, 2, P1U_B_G, 4);
+  uint32_t z[20];
+  uint32_t s0 = p1u_combine_redc<0>(M.col[80], M.col[81], M.col[82], M.col[83], 0u);
+  const int block_begin[4] = {0, 8, 16, 20};
+  for (int b = 0; b < 3; b++) {
+    const int k0 = block_begin[b];
+    for (int r = k0; r < block_begin[b + 1]; r++) {
+      z[r] = kb_canon(p1u_model_redc((uint64_t)p1u_model_redc((uint64_t)s0 * s0) * s0));
+      uint64_t acc = p1u_combine64(M.col[4 * r], M.col[4 * r + 1], M.col[4 * r + 2], M.col[4 * r + 3], T.G_CONST[1 + r]);
+      acc += (uint64_t)z[r] * T.FR0[r];
+      for (int i = 0; k0 + i < r; i++) {
+        if ((1 + i) % 4 == 0) acc = kb_fold(acc);
+        acc += (uint64_t)z[k0 + i] * T.GTRI[r][k0 + i];
+      }
+      s0 = p1u_model_redc(kb_fold(acc));
+    }
+    M.store_words(4 + k0 / 4, z + k0, block_begin[b + 1] - k0);
+    if (b == 0) M.product(48, 1, P1U_B_T0, 2, 4, 32, true);
+    if (b == 1) M.product(16, 1, P1U_B_T1, 2, 6, 64, true);
+  }
+  a[0] = s0;
+  M.product(64, 5, P1U_B_MV, 10);
+  for (int o = 0; o < 15; o++) a[o + 1] = p1u_combine_redc<0>(M.col[4 * o], M.col[4 * o + 1], M.col[4 * o + 2], M.col[4 * o + 3], 0u);
+  for (int r = 0; r < 4; r++) {
+    p1u_model_full_round(M, a, r < 3 ? T.RC_TERM[r] : nullptr, x);
+    for (int i = 0; i < 16; i++) a[i] = x[i];
+  }
+  for (int i = 0; i < 16; i++) s[i] = kb_mul(x[i], T.FIX);
 }
 
 #ifdef __CUDACC__
@@ -234,23 +343,6 @@ __device__ __forceinline__ void p1u_product(P1uCtx& c) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// Recombination of four accumulator columns and Montgomery reduction in one: returns a value congruent to
-//   ((v0 + 2^8 v1 + 2^16 v2 + 2^24 v3) 2^SHIFT + init) / 2^32   in (., . + p],   provided init + (v0 << SHIFT) + (v1 << (8 + SHIFT)) < 2^32 (MDS: v <= 128 * 255^2 < 2^23, init < p: < 2^32 - 2^24;
-// G: v < 2^22, init < p; MI | V: v < 2^23.2, init = 0 — its constant is a column of B).
-// The 64-bit sum is never formed by the multiplier: its low word and its high word (a shift and a carry) are built on the ALU
-// pipe and handed to the two multiplications of the reduction (m = lo p^-1, hi(m p)) — the multiplier pipe is what bounds the
-// kernel, and a mad.wide with a 64-bit addend per shift would put 10 of its cycles on every output.
-template <int SHIFT>
-__device__ __forceinline__ uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
-  const uint32_t a = init + (v0 << SHIFT) + (v1 << (8 + SHIFT));  // < 2^32: no carry
-  const uint32_t b = v2 + (v3 << 8);
-  const uint32_t lo = a + (b << (16 + SHIFT));
-  const uint32_t hi = (b >> (16 - SHIFT)) + (lo < a ? 1u : 0u);
-  const uint32_t m = lo * 0x81000001u;
-  const uint64_t u = mul_wide(m, c_kb.p);
-  return hi - (uint32_t)(u >> 32) + c_kb.p;
-}
-
 // S-boxes and MDS of one full round: out[i] == (rc[i] + 4 sum_j C[(i - j) mod 16] a[j]^3 R^-2 R^-1) R^-1, i < N_OUT — what
 // p1_sbox_lazy + p1_mds_redc compute, with the second reduction of every S-box folded into the matrix: the product
 // w = (a^2 R^-1) a is stored UNREDUCED (8 limbs per lane, K = 128) and B carries 4 C R^-1 2^(8 i) mod p for limb i.
@@ -272,15 +364,6 @@ __device__ __forceinline__ void p1u_sbox_mds_redc(P1uCtx& c, const uint32_t a[16
     for (int i = 0; i < 8; i++)
       out[8 * h + i] = p1u_combine_redc<0>(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], rc ? rc[8 * h + i] : 0u);
   }
-}
-
-// the 64-bit value v0 + 2^8 v1 + 2^16 v2 + 2^24 v3 + init (same no-carry condition as p1u_combine_redc), built on the ALU pipe
-__device__ __forceinline__ uint64_t p1u_combine64(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
-  const uint32_t a = init + v0 + (v1 << 8);
-  const uint32_t b = v2 + (v3 << 8);
-  const uint32_t lo = a + (b << 16);
-  const uint32_t hi = (b >> 16) + (lo < a ? 1u : 0u);
-  return ((uint64_t)hi << 32) | lo;
 }
 
 #ifdef LM_P1_IMM

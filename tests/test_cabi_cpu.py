@@ -81,6 +81,28 @@ def test_kernel_arithmetic_on_host_matches_oracle(hostcheck, rng):
     assert hostcheck.hc_r2() == pow(2, 64, O.P)
 
 
+def test_tensor_core_poseidon_formulation_model_matches_oracle(rng):
+    """csrc/poseidon1_umma.cuh on the CPU: the B-matrix image the Merkle kernels load (u8 limbs of 4 C R^-1 2^(8i), G, MI | V and the
+    triangle blocks pre-shifted mod p), the row layout, the no-carry recombination and the 8 / 8 / 4 block structure of the
+    partial rounds, with every tcgen05.mma replaced by the integer dot products it stands for — against the reference's KAT
+    (poseidon1_koalabear_16.rs:1066-1093) and the oracle permutation on random and extreme states."""
+    from leanmultisig_b200._lib import lib
+
+    kat_in = O.to_monty(np.arange(16))
+    st = kat_in.copy()
+    assert lib().lm_host_poseidon1_umma_model(st.ctypes.data_as(O.u32p)) == 0
+    assert np.array_equal(st, O.poseidon1_permute(kat_in[None, :])[0])
+    x = O.random_field(rng, (300, 16))
+    x[0] = O.P - 1
+    x[1] = 0
+    x[2, ::2] = O.P - 1
+    exp = O.poseidon1_permute(x)
+    for i in range(len(x)):
+        st = x[i].copy()
+        assert lib().lm_host_poseidon1_umma_model(st.ctypes.data_as(O.u32p)) == 0
+        assert np.array_equal(st, exp[i]), i
+
+
 def test_native_prover_state_matches_the_python_transcript():
     """lm_fs (C++ ProverState, csrc/spine.cu) against the Python mirror and the oracle's challenger on one script of
     absorb / squeeze operations: identical samples, transcript and sponge state.  Host code only (no device)."""

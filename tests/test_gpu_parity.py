@@ -29,9 +29,36 @@ def test_poseidon1_kat_and_random(ctx, rng):
     assert np.array_equal(ctx.poseidon1(s, compress=True), O.poseidon1_compress(s))
 
 
+def test_scalar_poseidon_kernels_subprocess():
+    """LM_P1_SCALAR=1 selects the one-state-per-thread kernels (poseidon1.cuh) instead of the tensor-core formulation: same
+    permutation, sponge and tree, bit for bit (the switch is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, oracle as O, leanmultisig_b200 as L\n"
+        "rng = np.random.default_rng(7)\n"
+        "c = L.Context(0, 20)\n"
+        "s = O.random_field(rng, (3000, 16))\n"
+        "assert np.array_equal(c.poseidon1(s), O.poseidon1_permute(s))\n"
+        "assert np.array_equal(c.poseidon1(s, compress=True), O.poseidon1_compress(s))\n"
+        "for log_h, stored, full, eff in [(14, 64, 128, 64), (9, 64, 128, 57), (15, 24, 24, 24)]:\n"
+        "    m = O.random_field(rng, (1 << log_h, stored)); m[:, eff:] = 0\n"
+        "    assert np.array_equal(c.merkle_tree(m, full, eff), O.merkle_tree(m, full, eff))\n"
+        "c.close()\n"
+        "print('scalar path ok')\n"
+    )
+    env = dict(os.environ, LM_P1_SCALAR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "scalar path ok" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("log_h,stored,full,eff", [
     (0, 16, 16, 16), (1, 16, 16, 16), (3, 64, 128, 64), (5, 128, 128, 128), (9, 64, 128, 57), (10, 160, 160, 160),
     (7, 90, 160, 85), (4, 16, 64, 8), (4, 16, 64, 1), (12, 64, 128, 64), (6, 20, 160, 20), (8, 6, 16, 6), (8, 24, 24, 24),
+    (15, 16, 16, 16), (14, 90, 160, 85), (16, 8, 64, 8),
 ])
 def test_merkle_tree_layers(ctx, rng, log_h, stored, full, eff):
     h = 1 << log_h
