@@ -330,6 +330,12 @@ int lm_dev_dft_layers_mapped_cols(lm_ctx* ctx, uint32_t* d_mat, uint64_t width, 
                                   uint64_t col_count);
 int lm_dev_merkle_absorb(lm_ctx* ctx, const uint32_t* d_mat, uint64_t height, uint32_t stored_width, uint32_t full_width,
                          uint32_t effective_width, uint32_t chunk_hi, uint32_t count, uint32_t* d_digests);
+/* lm_dev_dft_layers_mapped(_cols) with the result written to a second matrix of the same shape (col_count = 0: all columns).
+ * The row-sharded commit reads the matrix its peers stored into and writes the witness's private codeword in the same pass, so
+ * the exchange buffer is free for the next commit without a device-to-device copy. */
+int lm_dev_dft_layers_mapped_out(lm_ctx* ctx, const uint32_t* d_mat, uint32_t* d_out, uint64_t width, uint32_t log_h,
+                                 uint32_t l_first, uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset,
+                                 uint64_t col_begin, uint64_t col_count);
 /* CUDA IPC plumbing for the peer matrices (one process per GPU): the owner exports a buffer it got from lm_dev_alloc, the
  * other ranks open the 64-byte handle from THEIR device (peer access over NVLink is enabled by the open) and close it at
  * the end.  The handle bytes travel through the caller's own channel (torch.distributed all_gather_object here). */

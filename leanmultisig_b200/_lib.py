@@ -124,6 +124,7 @@ def lib() -> C.CDLL:
             "lm_dev_ipc_close": [vp, vp],
             "lm_dev_dft": [vp, vp, u64, u64],
             "lm_dev_dft_layers_mapped": [vp, vp, u64, u32, u32, u64, u64, u64, u64],
+            "lm_dev_dft_layers_mapped_out": [vp, vp, vp, u64, u32, u32, u64, u64, u64, u64, u64, u64],
             "lm_dev_merkle_tree": [vp, vp, u64, u32, u32, u32, vp],
             "lm_dev_merkle_leaves": [vp, vp, u64, u32, u32, u32, vp],
             "lm_dev_merkle_levels": [vp, vp, u64],

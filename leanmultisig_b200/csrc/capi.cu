@@ -488,6 +488,20 @@ int lm_dev_dft_layers_mapped_cols(lm_ctx* c, uint32_t* d_mat, uint64_t w, uint32
   return LM_OK;
 }
 
+int lm_dev_dft_layers_mapped_out(lm_ctx* c, const uint32_t* d_mat, uint32_t* d_out, uint64_t w, uint32_t log_h, uint32_t l_first,
+                                 uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, uint64_t col_begin,
+                                 uint64_t col_count) {
+  if (!c || !d_mat || !d_out) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped_out: null argument");
+  if (w % 4 || col_begin % 4 || col_count % 4 || col_begin + col_count > w)
+    return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped_out: column range [%llu, +%llu) of %llu", (unsigned long long)col_begin,
+                (unsigned long long)col_count, (unsigned long long)w);
+  if (log_h > c->tw_log_n) return fail(LM_ERR_INVALID, "lm_dev_dft_layers_mapped_out: domain exceeds the twiddle table");
+  CU(cudaSetDevice(c->device));
+  CU(lm::ntt_layers_mapped(c->stream, const_cast<uint32_t*>(d_mat), w, log_h, l_first, n_blocks, run, block, offset, c->d_tw,
+                           c->tw_log_n, col_begin, col_count, d_out));
+  return LM_OK;
+}
+
 int lm_dev_merkle_absorb(lm_ctx* c, const uint32_t* d_mat, uint64_t h, uint32_t stored_w, uint32_t full_w, uint32_t eff_w,
                          uint32_t chunk_hi, uint32_t count, uint32_t* d_digests) {
   if (!c || !d_mat || !d_digests) return fail(LM_ERR_INVALID, "lm_dev_merkle_absorb: null argument");

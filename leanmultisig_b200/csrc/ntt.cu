@@ -368,7 +368,7 @@ __global__ void ntt_layer_mapped_kernel(uint32_t* __restrict__ mat, uint64_t w4,
 // one per layer.  Requires 2^l_first == block (the row-sharded commit's case): layer l_first + s pairs m and m + 2^s.
 template <int NB_LOG>
 __global__ void __launch_bounds__(256)
-ntt_layers_mapped_fused_kernel(uint32_t* __restrict__ mat, uint64_t w4, int log_h, int l_first, uint64_t run, uint64_t block,
+ntt_layers_mapped_fused_kernel(const uint32_t* mat, uint32_t* out, uint64_t w4, int log_h, int l_first, uint64_t run, uint64_t block,
                                uint64_t offset, const uint32_t* __restrict__ tw, int tw_shift, uint64_t c4_begin, uint64_t c4_count) {
   constexpr int NB = 1 << NB_LOG;
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,12 +389,13 @@ ntt_layers_mapped_fused_kernel(uint32_t* __restrict__ mat, uint64_t w4, int log_
     }
   }
 #pragma unroll
-  for (int m = 0; m < NB; m++) *(reinterpret_cast<uint4*>(mat + ((uint64_t)m * run + jp) * (w4 * 4)) + c4) = v[m];
+  for (int m = 0; m < NB; m++) *(reinterpret_cast<uint4*>(out + ((uint64_t)m * run + jp) * (w4 * 4)) + c4) = v[m];
 }
 
 cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, unsigned log_h, unsigned l_first,
                               uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, const uint32_t* d_tw,
-                              unsigned tw_log_n, uint64_t col_begin, uint64_t col_count) {
+                              unsigned tw_log_n, uint64_t col_begin, uint64_t col_count, uint32_t* d_out) {
+  if (!d_out) d_out = d_mat;  // in place
   if (w % 4 != 0 || log_h > tw_log_n || l_first > log_h || n_blocks < 2 || (((uint64_t)1 << l_first) < block))
     return cudaErrorInvalidValue;
   if (col_count == 0) col_begin = 0, col_count = w;
@@ -405,15 +406,20 @@ cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, 
     const uint64_t items = run * c4n;
     const unsigned grid = (unsigned)((items + 255) / 256);
     if (n_blocks == 2)
-      ntt_layers_mapped_fused_kernel<1><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
+      ntt_layers_mapped_fused_kernel<1><<<grid, 256, 0, stream>>>(d_mat, d_out, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
     else if (n_blocks == 4)
-      ntt_layers_mapped_fused_kernel<2><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
+      ntt_layers_mapped_fused_kernel<2><<<grid, 256, 0, stream>>>(d_mat, d_out, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
     else
-      ntt_layers_mapped_fused_kernel<3><<<grid, 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
+      ntt_layers_mapped_fused_kernel<3><<<grid, 256, 0, stream>>>(d_mat, d_out, w / 4, (int)log_h, (int)l_first, run, block, offset, d_tw, tw_shift, c4b, c4n);
     count_launch();
     return cudaGetLastError();
   }
   if (col_begin != 0 || col_count != w) return cudaErrorInvalidValue;  // the per-layer fallback works on whole rows
+  if (d_out != d_mat) {  // per-layer fallback: copy once, then in place on the copy
+    cudaError_t e = cudaMemcpyAsync(d_out, d_mat, n_blocks * run * w * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return e;
+    d_mat = d_out;
+  }
   const uint64_t total = (n_blocks / 2) * run * (w / 4);
   for (unsigned l = l_first; l < log_h; l++) {
     ntt_layer_mapped_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_mat, w / 4, (int)log_h, (int)l, n_blocks, run,

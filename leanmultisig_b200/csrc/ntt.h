@@ -29,5 +29,6 @@ cudaError_t ntt_reorder_and_dft_scatter(cudaStream_t stream, const uint32_t* d_e
 // layers [l_first, log_h) on the rows a rank holds after the exchange of the row-sharded commit
 cudaError_t ntt_layers_mapped(cudaStream_t stream, uint32_t* d_mat, uint64_t w, unsigned log_h, unsigned l_first,
                               uint64_t n_blocks, uint64_t run, uint64_t block, uint64_t offset, const uint32_t* d_tw,
-                              unsigned tw_log_n, uint64_t col_begin = 0, uint64_t col_count = 0);  // column range (0, 0 = all)
+                              unsigned tw_log_n, uint64_t col_begin = 0, uint64_t col_count = 0,  // column range (0, 0 = all)
+                              uint32_t* d_out = nullptr);                                          // result matrix (null = in place)
 }  // namespace lm

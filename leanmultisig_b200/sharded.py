@@ -36,6 +36,8 @@ oracle over gloo; the product backend is the CUDA library (`CudaBackend`), there
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import field as F
@@ -120,14 +122,16 @@ class ShardedCommit:
             else:
                 mat = t_local
             mark("all_to_all")
-        # 3. last g layers on the local rows
-        if geo.g:
-            b.dft_layers_mapped(mat, w, geo.log_h, geo.log_h - geo.g, self.world, geo.run, geo.block, self.rank * geo.run)
+        # 3. last g layers on the local rows.  With the fused exchange `mat` is the buffer the peers store the NEXT commit of
+        #    this shape into, so the pass writes its result to a private matrix of the witness (same traffic as in place, no
+        #    copy); it is ordered before this commit's root all-gather, which no peer can pass - and hence start its next
+        #    scatter - before this rank has reached it (round-1 advisor finding)
         if scatter is not None:
-            # the exchange buffer is shared: the peers store the NEXT commit of this shape into it.  The witness keeps a
-            # private copy (1/G of the codeword, a device-to-device copy ordered before this commit's root all-gather, which
-            # no peer can pass - and hence start its next scatter - before this rank has reached it)
-            mat = b.private_copy(mat)
+            priv = b.empty_like(mat)
+            b.dft_layers_mapped(mat, w, geo.log_h, geo.log_h - geo.g, self.world, geo.run, geo.block, self.rank * geo.run, out=priv)
+            mat = priv
+        elif geo.g:
+            b.dft_layers_mapped(mat, w, geo.log_h, geo.log_h - geo.g, self.world, geo.run, geo.block, self.rank * geo.run)
         mark("last_layers")
         self.codeword = mat
         # 4. the G subtrees of this rank as ONE forest: leaf digests of all local rows in one launch, then level by level
@@ -630,9 +634,6 @@ class CudaBackend:
     def empty_like(self, t):
         return self.torch.empty_like(t)
 
-    def private_copy(self, t):
-        return t.clone()
-
     def rows(self, t, start: int, count: int):
         return t[start:start + count]
 
@@ -748,13 +749,18 @@ class CudaBackend:
         sub = host_shard.numel() // w                       # positions per column in the shard
         d_evals = torch.empty(host_shard.numel(), dtype=torch.int32, device="cuda")
         forest = torch.empty((2 * geo.block - 1, 8), dtype=torch.int32, device="cuda")
+        priv = self.empty_like(mat)                         # the witness's codeword (the exchange buffer is reused by the next commit)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream()
         self._copy_stream.wait_stream(self.stream)
         n_vars, world, rank = geo.n_vars - geo.g, dist.get_world_size(), dist.get_rank()
         tptr = table.ctypes.data_as(C.POINTER(C.c_uint64))
-        chunk_end, take, first = n_chunks, 1, True
-        while chunk_end > 0:                                # column groups of 1, 1, 2, 4, .. rate chunks, right to left
+        # up to 8 equal column groups of whole rate chunks, right to left (as lm_commit: with the tensor-core sponge a group's
+        # transform + hash takes about as long as its copy, so equal groups keep PCIe and the SMs busy and leave one group's
+        # compute after the last byte; LM_COMMIT_DOUBLING_GROUPS=1: the round-1 schedule 1, 1, 2, 4, ..)
+        doubling = bool(os.environ.get("LM_COMMIT_DOUBLING_GROUPS"))
+        chunk_end, take, first = n_chunks, (1 if doubling else (n_chunks + 7) // 8), True
+        while chunk_end > 0:
             take = min(take, chunk_end)
             col_begin, count = (chunk_end - take) * 8, take * 8
             with torch.cuda.stream(self._copy_stream):
@@ -766,17 +772,17 @@ class CudaBackend:
             self.check(lib.lm_dev_reorder_and_dft_scatter_cols(self.ctx.handle, d_evals.data_ptr(), n_vars, geo.folding,
                                                                geo.log_inv_rate, w, work.data_ptr(), tptr, world, rank, col_begin, count))
             dist.all_reduce(self._flag())                   # every rank's stores of this group have landed
-            self.check(lib.lm_dev_dft_layers_mapped_cols(self.ctx.handle, mat.data_ptr(), w, geo.log_h, geo.log_h - geo.g, world,
-                                                         geo.run, geo.block, rank * geo.run, col_begin, count))
-            self.check(lib.lm_dev_merkle_absorb(self.ctx.handle, mat.data_ptr(), geo.block, w, full, w, chunk_end - 1, take,
+            self.check(lib.lm_dev_dft_layers_mapped_out(self.ctx.handle, mat.data_ptr(), priv.data_ptr(), w, geo.log_h, geo.log_h - geo.g,
+                                                        world, geo.run, geo.block, rank * geo.run, col_begin, count))
+            self.check(lib.lm_dev_merkle_absorb(self.ctx.handle, priv.data_ptr(), geo.block, w, full, w, chunk_end - 1, take,
                                                 forest.data_ptr()))
             chunk_end -= take
-            if not first:
+            if doubling and not first:
                 take *= 2
             first = False
         self.check(lib.lm_dev_merkle_levels(self.ctx.handle, forest.data_ptr(), geo.block))
         d_evals.record_stream(self._copy_stream)
-        return self.private_copy(mat), forest  # the exchange buffer is reused by the next commit (see ShardedCommit.commit)
+        return priv, forest
 
     def _flag(self):
         if not hasattr(self, "_flag_t"):
@@ -802,8 +808,12 @@ class CudaBackend:
         self.torch.cuda.synchronize()
         return {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._marks, self._marks[1:])}
 
-    def dft_layers_mapped(self, mat, w, log_h, l_first, n_blocks, run, block, offset):
-        self.check(self.lib.lm_dev_dft_layers_mapped(self.ctx.handle, mat.data_ptr(), w, log_h, l_first, n_blocks, run, block, offset))
+    def dft_layers_mapped(self, mat, w, log_h, l_first, n_blocks, run, block, offset, out=None):
+        if out is None:
+            self.check(self.lib.lm_dev_dft_layers_mapped(self.ctx.handle, mat.data_ptr(), w, log_h, l_first, n_blocks, run, block, offset))
+        else:
+            self.check(self.lib.lm_dev_dft_layers_mapped_out(self.ctx.handle, mat.data_ptr(), out.data_ptr(), w, log_h, l_first, n_blocks,
+                                                             run, block, offset, 0, 0))
 
     def merkle_tree(self, rows, full_cols, eff_cols):
         h, w = rows.shape

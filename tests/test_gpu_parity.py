@@ -221,6 +221,19 @@ def test_dft_layers_mapped(ctx, rng, log_h, g, w):
         got = d.download(mat.shape)
         d.free()
         assert np.array_equal(got, exp), (log_h, g, w, rank)
+        # out-of-place form (what the sharded commit uses to leave the exchange buffer): source untouched, result in `out`;
+        # a column range leaves the other columns of `out` alone
+        d, out = ctx.to_device(mat), ctx.to_device(np.zeros_like(mat))
+        check(lib().lm_dev_dft_layers_mapped_out(ctx.handle, d.ptr, out.ptr, w, log_h, log_h - g, G, run, block, rank * run, 0, 0))
+        assert np.array_equal(out.download(mat.shape), exp) and np.array_equal(d.download(mat.shape), mat)
+        if g <= 3 and w >= 8:
+            out2 = ctx.to_device(np.zeros_like(mat))
+            check(lib().lm_dev_dft_layers_mapped_out(ctx.handle, d.ptr, out2.ptr, w, log_h, log_h - g, G, run, block, rank * run, 4, w - 4))
+            part = out2.download(mat.shape)
+            assert np.array_equal(part[:, 4:], exp[:, 4:]) and not part[:, :4].any()
+            out2.free()
+        d.free()
+        out.free()
 
 
 @pytest.mark.parametrize("n_vars,k,r,cols,G", [(13, 4, 1, 16, 2), (15, 5, 1, 32, 4), (19, 7, 1, 64, 2), (20, 7, 1, 64, 8)])
