@@ -38,6 +38,7 @@
 // S-boxes of the other three.
 #pragma once
 #include "poseidon1.cuh"
+#include "umma.cuh"
 
 namespace lm {
 
@@ -49,7 +50,10 @@ constexpr int P1U_B_T0 = 8192 + 6144 + 10240;  // 48 x 32: z_0..7 into D_8..19
 constexpr int P1U_B_T1 = P1U_B_T0 + 1536;      // 16 x 32: z_8..15 into D_16..19
 constexpr int P1U_B_BYTES = P1U_B_T1 + 512;
 constexpr int P1U_A_BYTES = 128 * 160;    // one group's A rows
-constexpr int P1U_TMEM_COLS_PER_GROUP = 128;
+constexpr int P1U_TMEM_COLS_PER_GROUP = 96;   // the widest product (G) has 96 columns
+LM_HD constexpr uint32_t p1u_tmem_alloc_cols(int groups) {  // allocations are powers of two >= 32
+  return groups * 96 <= 128 ? 128u : groups * 96 <= 256 ? 256u : 512u;
+}
 
 // host: fill `img` (P1U_B_BYTES) from the generated tables
 inline void p1u_build_b_image(const P1Tables& T, uint8_t* img) {
@@ -88,33 +92,6 @@ inline void p1u_build_b_image(const P1Tables& T, uint8_t* img) {
     for (int j = 0; j < 4; j++) at(P1U_B_MV, 10, 4 * o + j, 144) = (uint8_t)(T.LANE_CONST[o] >> (8 * j));
   }
 }
-
-// Recombination of four accumulator columns and Montgomery reduction in one: returns a value congruent to
-//   ((v0 + 2^8 v1 + 2^16 v2 + 2^24 v3) 2^SHIFT + init) / 2^32   in (., . + p],   provided init + (v0 << SHIFT) + (v1 << (8 + SHIFT)) < 2^32 (MDS: v <= 128 * 255^2 < 2^23, init < p: < 2^32 - 2^24;
-// G: v < 2^22, init < p; MI | V: v < 2^23.2, init = 0 — its constant is a column of B).
-// The 64-bit sum is never formed by the multiplier: its low word and its high word (a shift and a carry) are built on the ALU
-// pipe and handed to the two multiplications of the reduction (m = lo p^-1, hi(m p)) — the multiplier pipe is what bounds the
-// kernel, and a mad.wide with a 64-bit addend per shift would put 10 of its cycles on every output.
-template <int SHIFT>
-LM_HD uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
-  const uint32_t a = init + (v0 << SHIFT) + (v1 << (8 + SHIFT));  // < 2^32: no carry
-  const uint32_t b = v2 + (v3 << 8);
-  const uint32_t lo = a + (b << (16 + SHIFT));
-  const uint32_t hi = (b >> (16 - SHIFT)) + (lo < a ? 1u : 0u);
-  const uint32_t m = lo * 0x81000001u;
-  const uint64_t u = mul_wide(m, LM_KB_P_OPAQUE);
-  return hi - (uint32_t)(u >> 32) + LM_KB_P_OPAQUE;
-}
-
-// the 64-bit value v0 + 2^8 v1 + 2^16 v2 + 2^24 v3 + init (same no-carry condition as p1u_combine_redc), built on the ALU pipe
-LM_HD uint64_t p1u_combine64(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
-  const uint32_t a = init + v0 + (v1 << 8);
-  const uint32_t b = v2 + (v3 << 8);
-  const uint32_t lo = a + (b << 16);
-  const uint32_t hi = (b >> 16) + (lo < a ? 1u : 0u);
-  return ((uint64_t)hi << 32) | lo;
-}
-
 
 // ---- CPU model of the formulation -------------------------------------------------------------------------------------------
 // The permutation exactly as the kernels below run it — same B image, same row layout, same recombination and block structure —
@@ -198,58 +175,6 @@ inline void p1u_model_permute(const P1Tables& T, const uint8_t* img, uint32_t s[
 
 #ifdef __CUDACC__
 
-__device__ __forceinline__ uint32_t p1u_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, no swizzle: start address, LBO = 128 (K-adjacent core matrices are contiguous), SBO = bytes per 8-row group
-__device__ __forceinline__ uint64_t p1u_desc(uint32_t saddr, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void p1u_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
-      :
-      : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0)
-      : "memory");
-}
-__device__ __forceinline__ bool p1u_elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ bool p1u_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void p1u_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
-      "%26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void p1u_ld4(uint32_t taddr, uint32_t (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-LM_HD constexpr uint32_t p1u_idesc(uint32_t n) { return (2u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
-
 // Per-thread view of the group's tensor-core plumbing.  Kernels: dynamic shared memory of p1u_smem_bytes(groups), blockDim.x =
 // 128 * groups, every thread of the CTA calls p1u_setup once, the permutation the same number of times, p1u_teardown once.
 struct P1uCtx {
@@ -275,10 +200,10 @@ __device__ __forceinline__ P1uCtx p1u_setup(uint8_t* smem /* 1024-byte aligned *
   uint8_t* sb = smem;
   uint8_t* sa = smem + P1U_B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P1U_B_BYTES + groups * P1U_A_BYTES);
-  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(bars + 6);
   for (int i = tid; i < P1U_B_BYTES / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(sb)[i] = __ldg(reinterpret_cast<const uint4*>(b_image) + i);
-  const uint32_t cols = groups * P1U_TMEM_COLS_PER_GROUP;
+  const uint32_t cols = p1u_tmem_alloc_cols(groups);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p1u_smem_u32(tm_slot)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -307,7 +232,7 @@ __device__ __forceinline__ void p1u_teardown(const P1uCtx& c, int groups) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if ((threadIdx.x >> 5) == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem_alloc), "r"(groups * P1U_TMEM_COLS_PER_GROUP) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem_alloc), "r"(p1u_tmem_alloc_cols(groups)) : "memory");
 }
 
 // rows are written: run K_STEPS MMAs of N columns against the B matrix at b_off and wait for the accumulators
@@ -323,7 +248,8 @@ __device__ __forceinline__ void p1u_product(P1uCtx& c) {
       case 0: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
       case 1: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
       case 2: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
-      default: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+      case 3: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+      default: asm volatile("bar.sync 5, 128;" ::: "memory"); break;
     }
   }
   if (c.issuer_warp) {  // warp-uniform branch, then one elected lane: the other warps skip the issue code altogether

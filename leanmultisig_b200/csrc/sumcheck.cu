@@ -14,9 +14,11 @@
 // modular reduction in 64-bit accumulators; sums are reduced warp -> CTA -> one partial per CTA -> final kernel.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include "launch_count.h"
 #include "kb.cuh"
 #include "reduce.cuh"
+#include "umma.cuh"
 #include "poly.h"
 #include "sumcheck.h"
 
@@ -92,6 +94,147 @@ weights_add_split_batch_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t
   st_ef(dst, cur);
 }
 
+
+// ---- the same batch as ONE integer GEMM on the tensor cores --------------------------------------------------------------
+// For a fixed x_lo the K tables lo_k[x_lo] are constants shared by every x_hi:  out[x_hi][x_lo] = sum_k hi_k[x_hi] * lo_k[x_lo]
+// is the product of the (n_hi x 5K) matrix of hi coefficients with a (5K x 5 * 1024) matrix built from the lo tables (entry
+// ((k, t), (x_lo, i)) = row matrix of ef_mul: coefficient i of the product takes a_t * rows[i][t]).  Evaluated like the
+// Poseidon1 products (umma.cuh, poseidon1_umma.cuh): the words of A are their own u8 limbs, limb l of an input meets the
+// constant pre-shifted mod p (c 2^(8 l) mod p) split into four byte columns, so one output coefficient is four s32 accumulator
+// columns, recombined on the ALU pipe and reduced ONCE — 25 K multiply-accumulates with folds per table entry become 5
+// reductions.  M = 128 values of x_hi per CTA (thread r = row r = TMEM lane r), N = 80 columns = 4 values of x_lo per tile,
+// 256 tiles per CTA; the B image (80 columns x 20K bytes per tile, shared-memory layout) is built once per call by
+// weights_gemm_image_kernel and streamed from L2.
+constexpr int WG_TILE_XLO = 4;                      // x_lo values per N tile
+constexpr int WG_TILE_N = WG_TILE_XLO * 5 * 4;      // 80 accumulator columns
+constexpr int WG_TMEM_COLS = 128;
+constexpr int WG_KMAX = 16;
+
+__host__ __device__ inline uint32_t wg_kbytes(int K) { return (uint32_t)((20 * K + 31) / 32 * 32); }
+
+// one thread per (x_lo, k, t): the five constants rows[i][t] of ef_mul for b = lo_k[x_lo], pre-shifted for the four limbs of a_t
+__global__ void weights_gemm_image_kernel(const uint32_t* __restrict__ lo, int K, int lo_vars, uint8_t* __restrict__ img) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_lo = 1u << lo_vars;
+  if (idx >= n_lo * (uint32_t)K * 5) return;
+  const uint32_t t = idx % 5, k = (idx / 5) % K, xl = idx / (5 * K);
+  const EfRows b = ef_rows(ld_ef(lo + 5 * ((size_t)k * n_lo + xl)));
+  const uint32_t rows[5][5] = {{b.b0, b.b4, b.b3, b.b2, b.b1m4},
+                               {b.b1, b.b0, b.b4, b.b3, b.b2},
+                               {b.b2, b.b1m4, b.b0m3, b.b4m2, b.b3m14},
+                               {b.b3, b.b2, b.b1m4, b.b0m3, b.b4m2},
+                               {b.b4, b.b3, b.b2, b.b1m4, b.b0m3}};
+  const uint32_t kb = wg_kbytes(K), kchunks = kb / 16;
+  uint8_t* tile = img + (size_t)(xl / WG_TILE_XLO) * WG_TILE_N * kb;
+  const uint32_t q = 5 * k + t;  // word index of a_t of statement k in the A row
+  for (int i = 0; i < 5; i++) {
+    uint64_t m = rows[i][t];
+    for (int l = 0; l < 4; l++) {
+      const uint32_t kbyte = 4 * q + l;
+      for (int j = 0; j < 4; j++) {
+        const uint32_t n = ((xl % WG_TILE_XLO) * 5 + i) * 4 + j;
+        tile[(n / 8) * (kchunks * 128) + (kbyte / 16) * 128 + (n % 8) * 16 + (kbyte % 16)] = (uint8_t)(m >> (8 * j));
+      }
+      m = (m << 8) % KB_P;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 4)
+weights_gemm_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t n_hi, int lo_vars, const uint32_t* __restrict__ hi, int K,
+                    const uint8_t* __restrict__ img) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  const uint32_t kb = wg_kbytes(K), kchunks = kb / 16, k_steps = kb / 32;
+  uint8_t* sa = dsm;                                  // 128 rows x kb
+  uint8_t* sb = dsm + 128 * kb;                       // one B tile: 80 x kb
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + WG_TILE_N * kb);
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int r = threadIdx.x, warp = r >> 5;
+  const uint64_t xh = (uint64_t)blockIdx.x * 128 + r;
+  // A row of this thread: the 5K words of hi_k[xh], zero padding up to kb
+  const uint32_t a_row = p1u_smem_u32(sa) + (r >> 3) * (kchunks * 128) + (r & 7) * 16;
+  for (uint32_t c = 0; c < kchunks; c++) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_row + c * 128), "r"(0) : "memory");
+  for (int k = 0; k < K; k++) {
+    const Ef a = ld_ef(hi + 5 * ((size_t)k * n_hi + xh));
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+      const uint32_t q = 5 * k + t;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_row + (q >> 2) * 128 + (q & 3) * 4), "r"(a.c[t]) : "memory");
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p1u_smem_u32(tm_slot)), "r"(WG_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (r == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(p1u_smem_u32(bar)), "r"(1) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tm_slot, tmem = tmem_d + ((uint32_t)(warp * 32) << 16);
+  const bool issuer_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;
+  const uint32_t n_tiles = (1u << lo_vars) / WG_TILE_XLO;
+  const uint32_t tile_bytes = WG_TILE_N * kb;
+  uint32_t parity = 0;
+  uint32_t* wrow = w + 5 * (base + (xh << lo_vars));
+  for (uint32_t tile = 0; tile < n_tiles; tile++) {
+    // B tile: global (L2) -> shared, already in the descriptor's layout
+    const uint4* src = reinterpret_cast<const uint4*>(img + (size_t)tile * tile_bytes);
+    for (uint32_t i = r; i < tile_bytes / 16; i += 128) reinterpret_cast<uint4*>(sb)[i] = __ldg(src + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (issuer_warp) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p1u_elect_one()) {
+        const uint64_t da = p1u_desc(p1u_smem_u32(sa), kchunks * 128), db = p1u_desc(p1u_smem_u32(sb), kchunks * 128);
+        for (uint32_t k = 0; k < k_steps; k++)
+          p1u_mma(tmem_d, da + (uint64_t)(k * 256 >> 4), db + (uint64_t)(k * 256 >> 4), p1u_idesc(WG_TILE_N), k > 0);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(p1u_smem_u32(bar)) : "memory");
+      }
+      __syncwarp();
+    }
+    // this tile's 4 table entries (80 bytes of w) while the product runs
+    uint4 cur[5];
+    uint4* wp = reinterpret_cast<uint4*>(wrow + 5 * WG_TILE_XLO * tile);
+#pragma unroll
+    for (int i = 0; i < 5; i++) cur[i] = wp[i];
+    for (uint32_t spins = 0; !p1u_try_wait(p1u_smem_u32(bar), parity);)
+      if (++spins > (1u << 26)) __trap();
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t* cw = reinterpret_cast<uint32_t*>(cur);
+#pragma unroll
+    for (int h = 0; h < 5; h++) {  // 16 columns = 4 output coefficients at a time
+      uint32_t v[16];
+      p1u_ld16(tmem + 16 * h, v);
+      p1u_wait_ld();
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        const uint32_t y = kb_canon(p1u_combine_redc<0>(v[4 * o], v[4 * o + 1], v[4 * o + 2], v[4 * o + 3], 0u));
+        cw[4 * h + o] = kb_add(cw[4 * h + o], y);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) wp[i] = cur[i];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(WG_TMEM_COLS) : "memory");
+}
+
+static bool weights_gemm_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LM_EQ_GEMM");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+static size_t weights_gemm_image_bytes(uint32_t K, int lo_vars) { return ((size_t)1 << lo_vars) / WG_TILE_XLO * WG_TILE_N * wg_kbytes((int)K); }
+static bool weights_gemm_ok(uint32_t m, uint32_t K) {
+  return weights_gemm_enabled() && m >= (uint32_t)SPLIT_LO + 7 && K >= 1 && K <= (uint32_t)WG_KMAX;
+}
+
 // d_points: K points of m coordinates (K x m x 5 words), scalars: host, K x 5 words
 cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_points, uint32_t m,
                                  const uint32_t* scalars, uint32_t K, uint32_t* d_scratch) {
@@ -108,13 +251,30 @@ cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t se
     if ((e = eq_table(stream, pt + 5 * hi_vars, lo_vars, one, d_lo + 5 * n_lo * k)) != cudaSuccess) return e;
   }
   const uint64_t n = (uint64_t)1 << m;
+  if (weights_gemm_ok(m, K)) {
+    // tensor-core path: B image behind the tables (16-byte aligned), then one CTA per 128 values of x_hi
+    uint8_t* d_img = reinterpret_cast<uint8_t*>(d_lo + 5 * n_lo * K + ((4 - (5 * (n_hi + n_lo) * K) % 4) % 4));
+    const size_t img_bytes = weights_gemm_image_bytes(K, lo_vars);
+    if ((e = cudaMemsetAsync(d_img, 0, img_bytes, stream)) != cudaSuccess) return e;
+    const unsigned items = (unsigned)(n_lo * K * 5);
+    weights_gemm_image_kernel<<<(items + 127) / 128, 128, 0, stream>>>(d_lo, (int)K, lo_vars, d_img);
+    count_launch();
+    const uint32_t kb = wg_kbytes((int)K);
+    const int dyn = (int)((128 + WG_TILE_N) * kb + 64);
+    if ((e = cudaFuncSetAttribute(weights_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return e;
+    weights_gemm_kernel<<<(unsigned)(n_hi / 128), 128, dyn, stream>>>(d_w, selector << m, n_hi, lo_vars, d_hi, (int)K, d_img);
+    count_launch();
+    return cudaGetLastError();
+  }
   weights_add_split_batch_kernel<16><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_w, selector << m, n, lo_vars, d_hi, d_lo, (int)K);
   count_launch();
   return cudaGetLastError();
 }
 size_t weights_add_eq_batch_scratch_words(uint32_t m, uint32_t K) {
   const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
-  return 5 * (size_t)K * (((size_t)1 << (m - lo_vars)) + ((size_t)1 << lo_vars)) + 8;
+  size_t words = 5 * (size_t)K * (((size_t)1 << (m - lo_vars)) + ((size_t)1 << lo_vars)) + 8;
+  if (weights_gemm_ok(m, K)) words += weights_gemm_image_bytes(K, lo_vars) / 4 + 8;
+  return words;
 }
 
 size_t weights_add_eq_scratch_words(uint32_t m) {
