@@ -25,6 +25,7 @@
 namespace lm {
 
 constexpr int SPLIT_LO = 10;  // eq(point, x) = hi[x >> 10] * lo[x & 1023]
+constexpr int WG_HI_VARS = 10;  // tensor-core path: eq(point, x) = hi[x >> (m - 10)] * lo[x & (2^(m-10) - 1)], 1024 constants
 
 // ---------------------------------------------------------------------------------------------- weights
 // w[base + x] += hi[x >> lo_vars] * lo[x & mask]
@@ -96,16 +97,17 @@ weights_add_split_batch_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t
 
 
 // ---- the same batch as ONE integer GEMM on the tensor cores --------------------------------------------------------------
-// For a fixed x_lo the K tables lo_k[x_lo] are constants shared by every x_hi:  out[x_hi][x_lo] = sum_k hi_k[x_hi] * lo_k[x_lo]
-// is the product of the (n_hi x 5K) matrix of hi coefficients with a (5K x 5 * 1024) matrix built from the lo tables (entry
-// ((k, t), (x_lo, i)) = row matrix of ef_mul: coefficient i of the product takes a_t * rows[i][t]).  Evaluated like the
+// Split the index as x = (x_hi, x_lo) with only 10 HIGH variables: for a fixed x_hi the K values hi_k[x_hi] are constants shared
+// by every x_lo, so  out[x_lo][x_hi] = sum_k lo_k[x_lo] * hi_k[x_hi]  is the product of the (n_lo x 5K) matrix of lo coefficients
+// with a (5K x 5 * 1024) matrix built from the hi tables (entry ((k, t), (x_hi, i)) = row matrix of ef_mul: coefficient i of
+// the product takes a_t * rows[i][t]).  Rows = x_lo = consecutive table entries, so a warp's accesses to w are contiguous.  Evaluated like the
 // Poseidon1 products (umma.cuh, poseidon1_umma.cuh): the words of A are their own u8 limbs, limb l of an input meets the
 // constant pre-shifted mod p (c 2^(8 l) mod p) split into four byte columns, so one output coefficient is four s32 accumulator
 // columns, recombined on the ALU pipe and reduced ONCE — 25 K multiply-accumulates with folds per table entry become 5
-// reductions.  M = 128 values of x_hi per CTA (thread r = row r = TMEM lane r), N = 80 columns = 4 values of x_lo per tile,
-// 256 tiles per CTA; the B image (80 columns x 20K bytes per tile, shared-memory layout) is built once per call by
-// weights_gemm_image_kernel and streamed from L2.
-constexpr int WG_TILE_XLO = 4;                      // x_lo values per N tile
+// reductions.  M = 128 values of x_lo per CTA (thread r = row r = TMEM lane r), N = 80 columns = 4 values of x_hi per tile,
+// 256 tiles split over WG_SPLIT CTAs; the B image (80 columns x 20K bytes per tile, shared-memory layout) is built once per
+// call by weights_gemm_image_kernel and streamed from L2 with cp.async, double buffered.
+constexpr int WG_TILE_XLO = 4;                      // values of the 10-variable index per N tile
 constexpr int WG_TILE_N = WG_TILE_XLO * 5 * 4;      // 80 accumulator columns
 constexpr int WG_TMEM_COLS = 128;
 constexpr int WG_KMAX = 16;
@@ -140,22 +142,36 @@ __global__ void weights_gemm_image_kernel(const uint32_t* __restrict__ lo, int K
   }
 }
 
+// grid = (n_hi / 128) x WG_SPLIT: CTA (rb, sp) takes x_hi in [128 rb, 128 rb + 128) and the tiles t = sp (mod WG_SPLIT)
+constexpr int WG_SPLIT = 4;
 __global__ void __launch_bounds__(128, 4)
-weights_gemm_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t n_hi, int lo_vars, const uint32_t* __restrict__ hi, int K,
+weights_gemm_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t n_rows, int row_vars, const uint32_t* __restrict__ a_tab, int K,
                     const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   const uint32_t kb = wg_kbytes(K), kchunks = kb / 16, k_steps = kb / 32;
+  const uint32_t tile_bytes = WG_TILE_N * kb;
   uint8_t* sa = dsm;                                  // 128 rows x kb
-  uint8_t* sb = dsm + 128 * kb;                       // one B tile: 80 x kb
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + WG_TILE_N * kb);
+  uint8_t* sb = dsm + 128 * kb;                       // two B tiles: 80 x kb each
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 2 * tile_bytes);
   uint32_t* tm_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int r = threadIdx.x, warp = r >> 5;
-  const uint64_t xh = (uint64_t)blockIdx.x * 128 + r;
-  // A row of this thread: the 5K words of hi_k[xh], zero padding up to kb
+  const uint64_t xr = (uint64_t)blockIdx.x * 128 + r;  // this thread's row: the low index, entry base + (x_hi << row_vars) + xr
+  const uint32_t n_tiles = (1u << WG_HI_VARS) / WG_TILE_XLO;
+  const uint32_t sb_addr = p1u_smem_u32(sb);
+  // B tile `tile` -> buffer `buf`, asynchronously (the image is already in the descriptor's layout)
+  auto fetch_b = [&](uint32_t tile, uint32_t buf) {
+    const uint8_t* src = img + (size_t)tile * tile_bytes;
+    for (uint32_t i = r; i < tile_bytes / 16; i += 128)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_addr + buf * tile_bytes + 16 * i), "l"(src + 16 * (size_t)i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  uint32_t tile = blockIdx.y;
+  if (tile < n_tiles) fetch_b(tile, 0);
+  // A row of this thread: the 5K words of lo_k[xr], zero padding up to kb
   const uint32_t a_row = p1u_smem_u32(sa) + (r >> 3) * (kchunks * 128) + (r & 7) * 16;
   for (uint32_t c = 0; c < kchunks; c++) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_row + c * 128), "r"(0) : "memory");
   for (int k = 0; k < K; k++) {
-    const Ef a = ld_ef(hi + 5 * ((size_t)k * n_hi + xh));
+    const Ef a = ld_ef(a_tab + 5 * ((size_t)k * n_rows + xr));
 #pragma unroll
     for (int t = 0; t < 5; t++) {
       const uint32_t q = 5 * k + t;
@@ -173,37 +189,47 @@ weights_gemm_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t n_hi, int 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tm_slot, tmem = tmem_d + ((uint32_t)(warp * 32) << 16);
   const bool issuer_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;
-  const uint32_t n_tiles = (1u << lo_vars) / WG_TILE_XLO;
-  const uint32_t tile_bytes = WG_TILE_N * kb;
-  uint32_t parity = 0;
-  uint32_t* wrow = w + 5 * (base + (xh << lo_vars));
-  for (uint32_t tile = 0; tile < n_tiles; tile++) {
-    // B tile: global (L2) -> shared, already in the descriptor's layout
-    const uint4* src = reinterpret_cast<const uint4*>(img + (size_t)tile * tile_bytes);
-    for (uint32_t i = r; i < tile_bytes / 16; i += 128) reinterpret_cast<uint4*>(sb)[i] = __ldg(src + i);
+  uint32_t parity = 0, buf = 0;
+  uint32_t* wcol = w + 5 * (base + xr);
+  const uint64_t hi_stride = (uint64_t)5 << row_vars;  // words between x_hi and x_hi + 1
+  // this thread's 4 table entries of a tile (one per x_hi of the tile; the 32 entries of a warp are contiguous in w)
+  uint32_t cur[20], nxt[20];
+  if (tile < n_tiles) {
+#pragma unroll
+    for (int e = 0; e < WG_TILE_XLO; e++)
+#pragma unroll
+      for (int i = 0; i < 5; i++) cur[5 * e + i] = wcol[(uint64_t)(WG_TILE_XLO * tile + e) * hi_stride + i];
+  }
+  for (; tile < n_tiles; tile += WG_SPLIT, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (issuer_warp) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (p1u_elect_one()) {
-        const uint64_t da = p1u_desc(p1u_smem_u32(sa), kchunks * 128), db = p1u_desc(p1u_smem_u32(sb), kchunks * 128);
+        const uint64_t da = p1u_desc(p1u_smem_u32(sa), kchunks * 128), db = p1u_desc(sb_addr + buf * tile_bytes, kchunks * 128);
         for (uint32_t k = 0; k < k_steps; k++)
           p1u_mma(tmem_d, da + (uint64_t)(k * 256 >> 4), db + (uint64_t)(k * 256 >> 4), p1u_idesc(WG_TILE_N), k > 0);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(p1u_smem_u32(bar)) : "memory");
       }
       __syncwarp();
     }
-    // this tile's 4 table entries (80 bytes of w) while the product runs
-    uint4 cur[5];
-    uint4* wp = reinterpret_cast<uint4*>(wrow + 5 * WG_TILE_XLO * tile);
+    // while the product runs: the next tile's B (the other buffer was last read by the product we waited for one iteration
+    // ago) and the next tile's table entries
+    const uint32_t next = tile + WG_SPLIT;
+    if (next < n_tiles) {
+      fetch_b(next, buf ^ 1);
 #pragma unroll
-    for (int i = 0; i < 5; i++) cur[i] = wp[i];
+      for (int e = 0; e < WG_TILE_XLO; e++)
+#pragma unroll
+        for (int i = 0; i < 5; i++) nxt[5 * e + i] = wcol[(uint64_t)(WG_TILE_XLO * next + e) * hi_stride + i];
+    }
     for (uint32_t spins = 0; !p1u_try_wait(p1u_smem_u32(bar), parity);)
       if (++spins > (1u << 26)) __trap();
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t* cw = reinterpret_cast<uint32_t*>(cur);
+    uint32_t* cw = cur;
 #pragma unroll
     for (int h = 0; h < 5; h++) {  // 16 columns = 4 output coefficients at a time
       uint32_t v[16];
@@ -216,7 +242,11 @@ weights_gemm_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t n_hi, int 
       }
     }
 #pragma unroll
-    for (int i = 0; i < 5; i++) wp[i] = cur[i];
+    for (int e = 0; e < WG_TILE_XLO; e++)
+#pragma unroll
+      for (int i = 0; i < 5; i++) wcol[(uint64_t)(WG_TILE_XLO * tile + e) * hi_stride + i] = cur[5 * e + i];
+#pragma unroll
+    for (int i = 0; i < 20; i++) cur[i] = nxt[i];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -230,15 +260,16 @@ static bool weights_gemm_enabled() {
   }();
   return on;
 }
-static size_t weights_gemm_image_bytes(uint32_t K, int lo_vars) { return ((size_t)1 << lo_vars) / WG_TILE_XLO * WG_TILE_N * wg_kbytes((int)K); }
+static size_t weights_gemm_image_bytes(uint32_t K) { return ((size_t)1 << WG_HI_VARS) / WG_TILE_XLO * WG_TILE_N * wg_kbytes((int)K); }
 static bool weights_gemm_ok(uint32_t m, uint32_t K) {
-  return weights_gemm_enabled() && m >= (uint32_t)SPLIT_LO + 7 && K >= 1 && K <= (uint32_t)WG_KMAX;
+  return weights_gemm_enabled() && m >= (uint32_t)WG_HI_VARS + 7 && K >= 1 && K <= (uint32_t)WG_KMAX;
 }
 
 // d_points: K points of m coordinates (K x m x 5 words), scalars: host, K x 5 words
 cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_points, uint32_t m,
                                  const uint32_t* scalars, uint32_t K, uint32_t* d_scratch) {
-  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  const bool gemm = weights_gemm_ok(m, K);
+  const int lo_vars = gemm ? (int)m - WG_HI_VARS : (m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO);
   const int hi_vars = (int)m - lo_vars;
   const size_t n_hi = (size_t)1 << hi_vars, n_lo = (size_t)1 << lo_vars;
   uint32_t* d_hi = d_scratch;
@@ -251,18 +282,18 @@ cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t se
     if ((e = eq_table(stream, pt + 5 * hi_vars, lo_vars, one, d_lo + 5 * n_lo * k)) != cudaSuccess) return e;
   }
   const uint64_t n = (uint64_t)1 << m;
-  if (weights_gemm_ok(m, K)) {
-    // tensor-core path: B image behind the tables (16-byte aligned), then one CTA per 128 values of x_hi
+  if (gemm) {
+    // tensor-core path: B image (from the 1024-entry tables of the high variables) behind the tables, 16-byte aligned
     uint8_t* d_img = reinterpret_cast<uint8_t*>(d_lo + 5 * n_lo * K + ((4 - (5 * (n_hi + n_lo) * K) % 4) % 4));
-    const size_t img_bytes = weights_gemm_image_bytes(K, lo_vars);
+    const size_t img_bytes = weights_gemm_image_bytes(K);
     if ((e = cudaMemsetAsync(d_img, 0, img_bytes, stream)) != cudaSuccess) return e;
-    const unsigned items = (unsigned)(n_lo * K * 5);
-    weights_gemm_image_kernel<<<(items + 127) / 128, 128, 0, stream>>>(d_lo, (int)K, lo_vars, d_img);
+    const unsigned items = (unsigned)(n_hi * K * 5);
+    weights_gemm_image_kernel<<<(items + 127) / 128, 128, 0, stream>>>(d_hi, (int)K, hi_vars, d_img);
     count_launch();
     const uint32_t kb = wg_kbytes((int)K);
-    const int dyn = (int)((128 + WG_TILE_N) * kb + 64);
+    const int dyn = (int)((128 + 2 * WG_TILE_N) * kb + 64);
     if ((e = cudaFuncSetAttribute(weights_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return e;
-    weights_gemm_kernel<<<(unsigned)(n_hi / 128), 128, dyn, stream>>>(d_w, selector << m, n_hi, lo_vars, d_hi, (int)K, d_img);
+    weights_gemm_kernel<<<dim3((unsigned)(n_lo / 128), WG_SPLIT), 128, dyn, stream>>>(d_w, selector << m, n_lo, lo_vars, d_lo, (int)K, d_img);
     count_launch();
     return cudaGetLastError();
   }
@@ -271,9 +302,9 @@ cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t se
   return cudaGetLastError();
 }
 size_t weights_add_eq_batch_scratch_words(uint32_t m, uint32_t K) {
-  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;
+  const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;  // (the GEMM path splits the other way round: same table sizes)
   size_t words = 5 * (size_t)K * (((size_t)1 << (m - lo_vars)) + ((size_t)1 << lo_vars)) + 8;
-  if (weights_gemm_ok(m, K)) words += weights_gemm_image_bytes(K, lo_vars) / 4 + 8;
+  if (weights_gemm_ok(m, K)) words += weights_gemm_image_bytes(K) / 4 + 8;
   return words;
 }
 
