@@ -11,8 +11,9 @@
 // together with the transcript words the device appended, afterwards: both sides stay one transcript.
 //
 // Permutation: textbook form (add round constants, S-box, circulant MDS) with the 16 lanes of the state spread over
-// the lanes of a warp; the MDS row is 16 shuffles + 16 multiply-accumulates with uniform constants.  Latency, not
-// throughput, is what matters here (one sponge per proof): ~2 us per permutation instead of ~10 us single-threaded.
+// the lanes of a warp (both half-warps carry the state); an MDS row is split between the two half-warps — 8 shuffles + 8
+// multiply-accumulates each, one 64-bit exchange to join the halves.  Latency, not throughput, is what matters here (one
+// sponge per proof).
 #pragma once
 #include <cstdint>
 #include "kb.cuh"
@@ -119,6 +120,7 @@ struct FsWarp {
   uint32_t* tr;  // transcript buffer (device), nullptr = do not record
   uint32_t n_words;
   const uint32_t* rc_s;  // shared-memory copy of the round constants (DEVFS_RC_WORDS words, fs_load_rc)
+  uint32_t mds_h[8];     // this half-warp's eight MDS coefficients: mds[8 h + k], h = lane >> 4
 
   __device__ __forceinline__ void load(DevFs* f, uint32_t* transcript, const uint32_t* rc_shared) {
     fs = f;
@@ -127,6 +129,8 @@ struct FsWarp {
     x = f->state[threadIdx.x & 15];
     fresh = f->rate_fresh != 0;
     n_words = f->n_words;
+#pragma unroll
+    for (int k = 0; k < 8; k++) mds_h[k] = c_fs_mds[8 * ((threadIdx.x >> 4) & 1) + k];
   }
   __device__ __forceinline__ void store() {
     __syncwarp();
@@ -145,7 +149,7 @@ struct FsWarp {
   // round ahead: measured 36 us per transcript step with the constants loaded from global memory inside the loop, 30 us
   // fully unrolled (45 KiB of code fetched per permutation), a few us this way.
   __device__ __noinline__ void permute() {
-    const int i = threadIdx.x & 15;
+    const int i = threadIdx.x & 15, kh = (threadIdx.x >> 1) & 8;  // kh = 8 h
     uint32_t v = x;
     uint32_t rc = rc_s[i];
 #pragma unroll 1
@@ -154,16 +158,16 @@ struct FsWarp {
       rc = rc_s[((r + 1) % 28) * 16 + i];
       const bool full = r < 4 || r >= 24;
       if (full || i == 0) v = kb_mul(kb_mul(v, v), v);
-      // y_i = sum_k mds[k] x_{(i - k) mod 16}
-      uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      // y_i = sum_k mds[k] x_{(i - k) mod 16}: half-warp h sums k = 8 h .. 8 h + 7 (canonical x, constants < p: four products
+      // per 64-bit accumulator), the halves meet through one 64-bit exchange
+      uint64_t a0 = 0, a1 = 0;
 #pragma unroll
-      for (int k = 0; k < 16; k += 4) {
-        a0 = mad_wide(__shfl_sync(0xffffffffu, v, (i - k) & 15), c_fs_mds[k], a0);
-        a1 = mad_wide(__shfl_sync(0xffffffffu, v, (i - k - 1) & 15), c_fs_mds[k + 1], a1);
-        a2 = mad_wide(__shfl_sync(0xffffffffu, v, (i - k - 2) & 15), c_fs_mds[k + 2], a2);
-        a3 = mad_wide(__shfl_sync(0xffffffffu, v, (i - k - 3) & 15), c_fs_mds[k + 3], a3);
+      for (int k = 0; k < 8; k += 2) {
+        a0 = mad_wide(__shfl_sync(0xffffffffu, v, (i - kh - k) & 15), mds_h[k], a0);
+        a1 = mad_wide(__shfl_sync(0xffffffffu, v, (i - kh - k - 1) & 15), mds_h[k + 1], a1);
       }
-      v = kb_canon(kb_redc_lazy(kb_fold(a0) + kb_fold(a1) + kb_fold(a2) + kb_fold(a3)));
+      const uint64_t mine = kb_fold(a0) + kb_fold(a1);
+      v = kb_canon(kb_redc_lazy(mine + __shfl_xor_sync(0xffffffffu, mine, 16)));
     }
     x = v;
   }
