@@ -18,10 +18,21 @@ namespace lm {
 // kernel, and a mad.wide with a 64-bit addend per shift would put 10 of its cycles on every output.
 template <int SHIFT>
 LM_HD uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
+#if defined(__CUDA_ARCH__) && defined(LM_COMBINE_PRMT)
+  // Experiment (off): byte shifts as PRMT and three-input adds, forms ptxas cannot turn into IMAD.  ptxas balances the ALU and FMA
+  // pipes by instruction count and so puts ~3 IMAD per output on the pipe that bounds the kernel; forcing them onto the ALU pipe
+  // costs two more instructions per output and measured SLOWER (6.35 against 6.05 ms, profiles/r02_p1_umma.txt): issue slots.
+  static_assert(SHIFT == 0, "the byte-permute form is for byte-aligned columns");
+  const uint32_t a = init + v0 + __byte_perm(v1, 0, 0x2104);                                       // < 2^32: no carry
+  const uint64_t s = (uint64_t)a + __byte_perm(v2, 0, 0x1044) + __byte_perm(v3, 0, 0x0444);        // + (v2 << 16) + (v3 << 24), mod 2^32 each
+  const uint32_t lo = (uint32_t)s;
+  const uint32_t hi = (uint32_t)(s >> 32) + __byte_perm(v2, 0, 0x4432) + __byte_perm(v3, 0, 0x4321);  // + (v2 >> 16) + (v3 >> 8)
+#else
   const uint32_t a = init + (v0 << SHIFT) + (v1 << (8 + SHIFT));  // < 2^32: no carry
   const uint32_t b = v2 + (v3 << 8);
   const uint32_t lo = a + (b << (16 + SHIFT));
   const uint32_t hi = (b >> (16 - SHIFT)) + (lo < a ? 1u : 0u);
+#endif
   const uint32_t m = lo * 0x81000001u;
   const uint64_t u = mul_wide(m, LM_KB_P_OPAQUE);
   return hi - (uint32_t)(u >> 32) + LM_KB_P_OPAQUE;
