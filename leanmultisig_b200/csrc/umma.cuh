@@ -27,6 +27,11 @@ LM_HD uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t 
   const uint64_t s = (uint64_t)a + __byte_perm(v2, 0, 0x1044) + __byte_perm(v3, 0, 0x0444);        // + (v2 << 16) + (v3 << 24), mod 2^32 each
   const uint32_t lo = (uint32_t)s;
   const uint32_t hi = (uint32_t)(s >> 32) + __byte_perm(v2, 0, 0x4432) + __byte_perm(v3, 0, 0x4321);  // + (v2 >> 16) + (v3 >> 8)
+#elif defined(__CUDA_ARCH__) && !defined(LM_COMBINE_NO_CARRY_ASM)
+  const uint32_t a = init + (v0 << SHIFT) + (v1 << (8 + SHIFT));  // < 2^32: no carry
+  const uint32_t b = v2 + (v3 << 8);
+  uint32_t lo, hi;  // the carry of the low word travels in the carry flag (IADD3 / IADD3.X), not through a compare + select
+  asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b << (16 + SHIFT)), "r"(b >> (16 - SHIFT)));
 #else
   const uint32_t a = init + (v0 << SHIFT) + (v1 << (8 + SHIFT));  // < 2^32: no carry
   const uint32_t b = v2 + (v3 << 8);
@@ -42,8 +47,13 @@ LM_HD uint32_t p1u_combine_redc(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t 
 LM_HD uint64_t p1u_combine64(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t init) {
   const uint32_t a = init + v0 + (v1 << 8);
   const uint32_t b = v2 + (v3 << 8);
+#ifdef __CUDA_ARCH__
+  uint32_t lo, hi;
+  asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b << 16), "r"(b >> 16));
+#else
   const uint32_t lo = a + (b << 16);
   const uint32_t hi = (b >> 16) + (lo < a ? 1u : 0u);
+#endif
   return ((uint64_t)hi << 32) | lo;
 }
 
