@@ -313,15 +313,15 @@ def run_b200(args):
             "breakdown_ms": {"reorder_and_dft": t_ntt, "leaf_sponge": t_leaf, "tree_levels": t_lvl},
             "roofline": {"bound": "hbm", "kernel": "leaf_sponge_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": LEAF_DRAM_TRAFFIC_2_22 if args.log_rows == 22 else None,
-                         "traffic_source": "profiles/r02b_ncu_commit_kernels.txt (ncu --set full, dram read + write per launch)",
+                         "traffic_source": "profiles/r02c_ncu_commit_kernels.txt (ncu --set full, dram read + write per launch)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": leaf_bytes,
-                         "note": "Poseidon1 with its linear maps on tcgen05 (kind::i8, TMEM accumulators); what is left is bound by the IMAD.WIDE / IMAD dispatch of the S-boxes and reductions (fmaheavy 77 %, issue slots 57 %, tensor pipe 15 %), ~4.6k SASS instr per compression, see DESIGN.md 2.1b",
+                         "note": "Poseidon1 with its linear maps on tcgen05 (kind::i8, TMEM accumulators); what is left is bound by the IMAD.WIDE / IMAD dispatch of the S-boxes and reductions (fmaheavy 79 %, issue slots 48 %, tensor pipe 19 %), ~3.1k SASS instr per compression (6.7k before), see DESIGN.md 2.1b",
                          "gperm_per_s": n_perm_leaf / (t_leaf * 1e-3) / 1e9},
             # the bound that actually limits the dominant kernel (not measured live: from the committed ncu capture of this
             # command, same kernel build) - SURVEY 8d asks for a second roofline against the integer pipe
             "roofline_alu": {"bound": "fmaheavy pipe (IMAD.WIDE / IMAD dispatch)", "kernel": "leaf_sponge_kernel",
-                             "frac": 0.769, "issue_slot_frac": 0.572, "tensor_pipe_frac": 0.150, "unit": "pipe-active fraction",
-                             "source": "ncu sm__pipe_fmaheavy_cycles_active / smsp__issue_active / sm__pipe_tensor_cycles_active, profiles/r02b_ncu_commit_kernels.txt"},
+                             "frac": 0.792, "issue_slot_frac": 0.481, "tensor_pipe_frac": 0.195, "unit": "pipe-active fraction",
+                             "source": "ncu sm__pipe_fmaheavy_cycles_active / smsp__issue_active / sm__pipe_tensor_cycles_active, profiles/r02c_ncu_commit_kernels.txt"},
             "roofline_commit": {"bound": "hbm", "achieved": (live * 4 + rows * 64 * 4 + (2 * rows - 1) * 32) / (t_step * 1e-3) / 1e9,
                                 "peak": peak, "unit": "GB/s"},
             "roofline_ntt": {"bound": "hbm", "achieved": (live * 4 + rows * 64 * 4) / (t_ntt * 1e-3) / 1e9, "peak": peak,
@@ -502,7 +502,7 @@ def run_b200_sharded(args, rank, local_rank, world):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE leaf_sponge_kernel launch at the default workload (2^22 rows), from
 # the committed ncu capture; the algorithmic figure is 1 207 959 552 B, i.e. no re-reads.
-LEAF_DRAM_TRAFFIC_2_22 = 1_206_009_000  # ncu --set full: dram__bytes_read.sum 1.075640 GB + dram__bytes_write.sum 0.130369 GB per launch
+LEAF_DRAM_TRAFFIC_2_22 = 1_203_177_000  # ncu --set full: dram__bytes_read.sum 1.074693 GB + dram__bytes_write.sum 0.128484 GB per launch
 
 
 def main():
