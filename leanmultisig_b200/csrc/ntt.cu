@@ -22,6 +22,7 @@
 // arithmetic per thread (the pass kernels are issue-slot bound, ncu 66-68 %): 2.31 -> 2.00 ms on the 2^22 x 64 transform.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <cuda_pipeline.h>
 #include <cstdint>
 #include <cstdlib>
@@ -193,6 +194,13 @@ __global__ void ntt_pass_twiddles_kernel(uint32_t* __restrict__ tw_pass, int log
 struct NttScatter {
   uint32_t* dst[NTT_MAX_PEERS];
   int log_run, rank, enabled;
+  int tma_box_rows;  // > 0: the tile leaves through TMA stores into the peers' tensor maps, boxes of this many rows
+};
+// Tensor maps of the peers' matrices for the scattering pass, (column, row mod 2^l0, row div 2^l0) like the local one.
+// tools/microbench/peer_store_probe.cu: SM stores reach a peer's memory at 176 GB/s whatever their width (32 or 128 bytes per
+// thread), TMA stores of the same 32-byte row pieces at 426 GB/s — and they do not hold the storing warps.
+struct NttPeerMaps {
+  CUtensorMap m[NTT_MAX_PEERS];
 };
 
 // Pass over layers [l0 + skip, l0 + L) of an h x w matrix; one CTA per (column tile, row group).
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
 ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
                 int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift,
                 uint32_t tile0, uint32_t n_col_tiles, const uint32_t* __restrict__ tw_pass, const NttScatter sc,
-                const __grid_constant__ CUtensorMap tmap, int tma) {
+                const __grid_constant__ CUtensorMap tmap, int tma, const __grid_constant__ NttPeerMaps peer_maps) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // [2^L][2] slots (TMA destination / source: 128-byte aligned), 2^L twiddle words, the mbarrier of the tile load
   uint4* tile = reinterpret_cast<uint4*>(smem_raw);
@@ -305,6 +313,21 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int t = 0; t < n_rows; t += box_rows) tma_store_3d(&tmap, (int)col0, (int)row_lo, row_hi0 + t, tile + 2 * t);
+      tma_store_commit_wait();
+    }
+    return;
+  }
+  if (sc.enabled && sc.tma_box_rows > 0) {
+    // fused exchange through TMA: rows j of the tile with the same (row div 2^l0) >> (log_run - l0) go to one peer, to
+    // consecutive positions of its (row div 2^l0) dimension: local row (rank << log_run) | (row mod 2^log_run)
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int sh = sc.log_run - l0;
+      for (int t = 0; t < n_rows; t += sc.tma_box_rows) {
+        const int row_hi = row_hi0 + t;
+        tma_store_3d(&peer_maps.m[row_hi >> sh], (int)col0, (int)row_lo, (sc.rank << sh) | (row_hi & ((1 << sh) - 1)), tile + 2 * t);
+      }
       tma_store_commit_wait();
     }
     return;
@@ -449,10 +472,11 @@ static TmaEncodeFn tma_encode_fn() {
   return fn;
 }
 // the h x w matrix as the tensor (column, row mod 2^l0, row div 2^l0); box = 8 columns x 1 x min(2^L, 256) rows, dense in shared memory
-static bool tma_make_map(CUtensorMap* map, uint32_t* d_mat, uint64_t h, uint64_t w, int l0, int L) {
+static bool tma_make_map(CUtensorMap* map, uint32_t* d_mat, uint64_t h, uint64_t w, int l0, int L, int box_rows = 0) {
   const cuuint64_t dims[3] = {w, (cuuint64_t)1 << l0, h >> l0};
   const cuuint64_t strides[2] = {w * 4, (w * 4) << l0};  // bytes, dimensions 1 and 2
-  const cuuint32_t box[3] = {(cuuint32_t)TILE_COLS, 1, (cuuint32_t)((1 << L) < NTT_BOX_ROWS ? (1 << L) : NTT_BOX_ROWS)};
+  if (box_rows <= 0) box_rows = (1 << L) < NTT_BOX_ROWS ? (1 << L) : NTT_BOX_ROWS;
+  const cuuint32_t box[3] = {(cuuint32_t)TILE_COLS, 1, (cuuint32_t)box_rows};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
   return tma_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_mat, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -503,13 +527,31 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     uint32_t* tw_pass = const_cast<uint32_t*>(d_tw) + ((size_t)1 << (tw_log_n - 1)) + (size_t)(p % 4) * ((size_t)1 << MAX_TILE_LOG);
     ntt_pass_twiddles_kernel<<<((1 << L) + 255) / 256, 256, 0, stream>>>(tw_pass, log_h, l0, L, d_tw, tw_shift); count_launch();
     NttScatter sc{};
-    if (scatter && p == n_pass - 1) sc = *scatter;
+    NttPeerMaps peer_maps;  // only read by the scattering pass (2 KiB of kernel parameters; per call: rank threads share the process)
+    memset(&peer_maps.m[0], 0, sizeof(CUtensorMap));
+    if (scatter && p == n_pass - 1) {
+      sc = *scatter;
+      // TMA stores into the peers' matrices when a run holds at least 8 rows of the (row div 2^l0) dimension
+      static const bool tma_scatter_allowed = getenv("LM_NTT_NO_TMA_SCATTER") == nullptr;
+      const int sh = sc.log_run - l0;
+      if (tma_ok && tma_scatter_allowed && sh >= 3) {
+        int box = 1 << (sh < L ? sh : L);
+        if (box > NTT_BOX_ROWS) box = NTT_BOX_ROWS;
+        bool ok = true;
+        for (int q = 0; q < NTT_MAX_PEERS && sc.dst[q] && ok; q++)
+          ok = (reinterpret_cast<uintptr_t>(sc.dst[q]) & 15) == 0 && tma_make_map(&peer_maps.m[q], sc.dst[q], h, w, l0, L, box);
+        if (ok) sc.tma_box_rows = box;
+        static const bool dbg = getenv("LM_NTT_DEBUG") != nullptr;
+        if (dbg) fprintf(stderr, "[lm ntt] scatter pass l0=%d L=%d log_run=%d: %s (box %d rows)\n", l0, L, sc.log_run, ok ? "TMA stores into the peer matrices" : "tensor map of a peer matrix refused, SM stores", box);
+      }
+    }
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     int tma = 0;
     if (tma_ok && tma_make_map(&tmap, d_mat, h, w, l0, L)) tma = NTT_TMA_LOAD | NTT_TMA_STORE;
     ntt_pass_kernel<<<(unsigned)n_cta, NTT_THREADS, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
-                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass, sc, tmap, tma); count_launch();
+                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass, sc, tmap, tma,
+                                                            peer_maps); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     l0 += L;
