@@ -329,6 +329,89 @@ air_exec_round_kernel(const __grid_constant__ AirExecArgs A, const __grid_consta
 }
 
 
+// ---- round 0 from registers --------------------------------------------------------------------------------------------
+// The first round reads base-field rows: a pair is 2 x 22 words and its five evaluation points are five additions per word, so
+// the staging through shared memory (two barriers per 32 pairs, one warp per point) costs more than the constraints it feeds.
+// Here a thread owns a pair, keeps row(2j) + z (row(2j+1) - row(2j)) in registers and walks z = 0, 2, 3, 4, 5 itself; the eq
+// weight is computed once per pair.  Same sums, same partial-sum layout and last-CTA reduction as air_exec_round_kernel.
+struct RegViewB0 {
+  const uint32_t* cur;
+  __device__ __forceinline__ Fb operator()(int c) const { return Fb{cur[c]}; }
+};
+constexpr int EXEC_B0_THREADS = 128;
+__global__ void __launch_bounds__(EXEC_B0_THREADS, 4)
+air_exec_round_b0_reg_kernel(const __grid_constant__ AirExecArgs A, const __grid_constant__ AirExecConsts X) {
+  __shared__ uint32_t sm_red[EXEC_B0_THREADS / 32][EXEC_DEG * 5];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ef acc[EXEC_DEG];
+#pragma unroll
+  for (int z = 0; z < EXEC_DEG; z++) acc[z] = ef_zero();
+  const uint64_t pairs = (uint64_t)1 << A.m, n = A.n_base;
+  const EqView eqv(A.eq_tab, A.k, A.m);
+  for (uint64_t j = (uint64_t)blockIdx.x * EXEC_B0_THREADS + tid; j < pairs; j += (uint64_t)gridDim.x * EXEC_B0_THREADS) {
+    uint32_t cur[EXEC_ALL], d[EXEC_ALL];
+#pragma unroll
+    for (int c = 0; c < EXEC_COLS; c++) {
+      const uint2 v = a_ldg2(A.base + (uint64_t)c * n + 2 * j);
+      cur[c] = v.x;
+      d[c] = kb_sub(v.y, v.x);
+      if (c < 2) {  // the shifted columns: rows i + 1 of columns 0 and 1
+        const uint32_t nx = 2 * j + 2 < n ? __ldg(A.base + (uint64_t)c * n + 2 * j + 2) : A.halo[c];
+        cur[EXEC_COLS + c] = v.y;
+        d[EXEC_COLS + c] = kb_sub(nx, v.y);
+      }
+    }
+    const Ef eq = eqv(j);
+#pragma unroll
+    for (int zi = 0; zi < EXEC_DEG; zi++) {
+      if (zi == 1) {
+#pragma unroll
+        for (int c = 0; c < EXEC_ALL; c++) cur[c] = kb_add(kb_add(cur[c], d[c]), d[c]);  // z = 2
+      } else if (zi > 1) {
+#pragma unroll
+        for (int c = 0; c < EXEC_ALL; c++) cur[c] = kb_add(cur[c], d[c]);
+      }
+      acc[zi] = ef_add(acc[zi], ef_mul(exec_air_eval<Fb>(RegViewB0{cur}, X), eq));
+    }
+  }
+#pragma unroll
+  for (int zi = 0; zi < EXEC_DEG; zi++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      Ef o;
+#pragma unroll
+      for (int c = 0; c < 5; c++) o.c[c] = __shfl_down_sync(0xffffffffu, acc[zi].c[c], off);
+      acc[zi] = ef_add(acc[zi], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) sm_red[warp][zi * 5 + c] = acc[zi].c[c];
+    }
+  }
+  __syncthreads();
+  if (tid < EXEC_DEG * 5) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < EXEC_B0_THREADS / 32; w++) s = kb_add(s, sm_red[w][tid]);
+    A.partial[(uint64_t)blockIdx.x * EXEC_DEG * 5 + tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(&A.d->counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid < EXEC_DEG * 5) {
+    uint32_t s = 0;
+    for (uint32_t b = 0; b < gridDim.x; b++) s = kb_add(s, __ldcg(A.partial + (uint64_t)b * EXEC_DEG * 5 + tid));
+    A.d->out[tid / 5].c[tid % 5] = s;
+  }
+  if (tid == 0) A.d->counter = 0;
+}
+
 // ---- round 1 in the base field --------------------------------------------------------------------------------------
 // After ONE fold the table's values are a + r0 b with a, b in the base field.  At an evaluation point z every column is
 // P(z) + r0 Q(z) with P, Q base-field rows, so every constraint is a polynomial in r0 of degree <= 5 with BASE-FIELD
@@ -640,6 +723,14 @@ cudaError_t air_exec_round(cudaStream_t stream, int mode, const AirExecArgs& a, 
     cudaFuncSetAttribute(air_exec_round_kernel<AIR_E0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ef);
     cudaFuncSetAttribute(air_exec_round_kernel<AIR_E1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ef);
     attr_set = true;
+  }
+  static const bool b0_smem = getenv("LM_AIR_B0_SMEM") != nullptr;  // the staged round-0 kernel, for cross-checks
+  if (mode == AIR_B0 && !b0_smem) {
+    uint64_t nb = (pairs + EXEC_B0_THREADS - 1) / EXEC_B0_THREADS;
+    if (nb > (uint64_t)AIR_MAX_BLOCKS) nb = AIR_MAX_BLOCKS;
+    air_exec_round_b0_reg_kernel<<<(unsigned)nb, EXEC_B0_THREADS, 0, stream>>>(a, X);
+    count_launch();
+    return cudaGetLastError();
   }
   switch (mode) {
     case AIR_B0: air_exec_round_kernel<AIR_B0><<<g, EXEC_THREADS, smem_b, stream>>>(a, X); break;
