@@ -513,6 +513,28 @@ __global__ void __launch_bounds__(128) pow_grind_kernel(State16 base, uint64_t s
   if ((canon & mask) == 0) atomicMin(best, (unsigned long long)w);
 }
 
+// the same search with the permutation on the tensor cores (every thread of a CTA runs it: out-of-range candidates are clamped
+// to the last one and not reported)
+__global__ void __launch_bounds__(128, 4) pow_grind_umma_kernel(State16 base, uint64_t start, uint64_t n, uint32_t mask,
+                                                                unsigned long long* best, const uint8_t* __restrict__ b_image) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  P1uCtx uc = p1u_setup(dsm, b_image, 1);
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  if (!live) i = n - 1;
+  const uint64_t w = start + i;
+  uint32_t s[16];
+#pragma unroll
+  for (int k = 0; k < 8; k++) s[k] = base.v[k];
+  s[8] = kb_mul((uint32_t)w, KB_R2);
+#pragma unroll
+  for (int k = 9; k < 16; k++) s[k] = 0;
+  p1u_permute<16, false>(uc, s, c_p1);
+  const uint32_t canon = kb_canon(kb_redc_lazy((uint64_t)s[8]));
+  if (live && (canon & mask) == 0) atomicMin(best, (unsigned long long)w);
+  p1u_teardown(uc, 1);
+}
+
 cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bits, uint64_t start,
                       unsigned long long* d_best, uint64_t* witness) {
   if (bits >= 31) return cudaErrorInvalidValue;
@@ -528,7 +550,15 @@ cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bi
     const uint64_t n = at + batch <= KB_P ? batch : KB_P - at;
     cudaError_t e = cudaMemcpyAsync(d_best, &none, sizeof(none), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
-    pow_grind_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(base, at, n, mask, d_best); count_launch();
+    if (use_umma()) {
+      const uint8_t* img = nullptr;
+      if ((e = umma_b_image(&img)) != cudaSuccess) return e;
+      if ((e = umma_attr(pow_grind_umma_kernel, 1)) != cudaSuccess) return e;
+      pow_grind_umma_kernel<<<(unsigned)((n + 127) / 128), 128, p1u_smem_bytes(1), stream>>>(base, at, n, mask, d_best, img);
+    } else {
+      pow_grind_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(base, at, n, mask, d_best);
+    }
+    count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     unsigned long long got = none;
     if ((e = cudaMemcpyAsync(&got, d_best, sizeof(got), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
