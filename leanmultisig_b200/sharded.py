@@ -190,6 +190,48 @@ class ShardedCommit:
         return full, np.stack(path)
 
 
+def _open_local_batch(sc, rows):
+    """open_local for several rows this rank owns with ONE device gather + read-back per array (forest siblings, codeword rows)
+    and one download of the replicated top layers — the single-GPU path's lm_open does the same with one gather kernel; a
+    proof opens ~230 rows of the first tree.  -> [(row zero-extended, path)] in the order of `rows`."""
+    geo, b = sc.geo, sc.b
+    take = getattr(b, "take_rows", None)
+    if take is None or not rows:
+        return [sc.open_local(r) for r in rows]
+    f_idx, c_idx, tops = [], [], []
+    for row in rows:
+        assert geo.owner(row) == sc.rank
+        m, rest = divmod(row, geo.block)
+        jp = rest % geo.run
+        off, n, idx = 0, geo.block, m * geo.run + jp
+        c_idx.append(idx)
+        for _ in range(geo.log_run):
+            f_idx.append(off + (idx ^ 1))
+            off += n
+            n >>= 1
+            idx >>= 1
+        tops.append(geo.subtree_index(sc.rank, m))
+    forest_rows = take(sc.forest, f_idx).reshape(len(rows), geo.log_run, 8) if geo.log_run else np.zeros((len(rows), 0, 8), np.uint32)
+    code_rows = take(sc.codeword, c_idx)
+    top = b.to_host(sc.top)
+    out = []
+    for q in range(len(rows)):
+        path = [forest_rows[q]]
+        off, n, idx = 0, sc.world * sc.world, tops[q]
+        tail = []
+        while n > 1:
+            tail.append(top[off + (idx ^ 1)])
+            off += n
+            n >>= 1
+            idx >>= 1
+        if tail:
+            path.append(np.stack(tail))
+        full = np.zeros(sc.full_cols, dtype=np.uint32)
+        full[: code_rows.shape[1]] = code_rows[q]
+        out.append((full, np.concatenate(path, axis=0)))
+    return out
+
+
 class ShardedAirSumcheckSession(OuterSumcheckHost):
     """trait OuterSumcheckSession (air_sumcheck.rs:34-42) over one row-range shard per rank.  Collective: every rank
     constructs it with its rows and then makes the same calls with the same challenges (the transcript is replicated);
@@ -530,7 +572,8 @@ class ShardedTree:
 
     def open(self, indices):
         idx = [int(i) for i in indices]
-        mine = {q: self.sc.open_local(i) for q, i in enumerate(idx) if self.sc.geo.owner(i) == self.sc.rank}
+        own = [(q, i) for q, i in enumerate(idx) if self.sc.geo.owner(i) == self.sc.rank]
+        mine = {q: o for (q, _), o in zip(own, _open_local_batch(self.sc, [i for _, i in own]))}
         everyone = [None] * self.sc.world
         self.dist.all_gather_object(everyone, mine)
         merged = {}
@@ -636,6 +679,11 @@ class CudaBackend:
 
     def rows(self, t, start: int, count: int):
         return t[start:start + count]
+
+    def take_rows(self, t, idx) -> np.ndarray:
+        """rows `idx` of a device matrix on the host: one gather kernel, one read-back"""
+        sel = self.torch.as_tensor(idx, dtype=self.torch.int64, device=t.device)
+        return t.index_select(0, sel).cpu().numpy().view(np.uint32)
 
     def reorder_and_dft(self, shard, n_vars, folding, log_inv_rate, cols):
         h = 1 << (n_vars + log_inv_rate - folding)

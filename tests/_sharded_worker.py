@@ -30,6 +30,9 @@ class OracleBackend:
     def rows(self, t, start, count):
         return t[start:start + count]
 
+    def take_rows(self, t, idx):
+        return np.asarray(t)[np.asarray(idx, dtype=np.int64)]
+
     def reorder_and_dft(self, shard, n_vars, folding, log_inv_rate, cols):
         return O.reorder_and_dft(shard, n_vars, 1, folding, log_inv_rate, cols)
 
