@@ -345,6 +345,97 @@ ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, ui
   }
 }
 
+// ---- the scattering pass on WIDE tiles ----------------------------------------------------------------------------------
+// tools/microbench/peer_store_probe.cu (profiles/r02_peer_store_probe.txt): with both directions of the fabric busy, TMA stores of
+// 32-byte row pieces (8 columns) reach a peer at 290 GB/s, of 128-byte pieces (32 columns) at 663 GB/s.  The last pass of the
+// sharded commit's local transform therefore runs on tiles of COLS = 16 or 32 columns x 2^L rows (64 KiB: L <= 10 / 9), loaded
+// and stored by TMA only; everything else (twiddles, radix-8 groups in registers) is the 8-column pass.
+template <int G, int H>
+__device__ __forceinline__ void tile_group_wide(uint4* tile, const uint32_t* tw_s, int L, int lp) {
+  constexpr int Q = 1 << G;
+  const int n_items = (1 << (L - G)) * H;
+  for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+    const int h = item % H, u = item / H;
+    const int j_lo = u & ((1 << lp) - 1);
+    const int j0 = ((u >> lp) << (lp + G)) | j_lo;
+    uint4 v[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) v[q] = tile[(j0 + (q << lp)) * H + h];
+#pragma unroll
+    for (int s = 0; s < G; s++) {
+      const uint32_t* tw_l = tw_s + (1 << (lp + s));
+#pragma unroll
+      for (int q = 0; q < Q; q++) {
+        if (q & (1 << s)) continue;
+        const uint32_t t = tw_l[j_lo + ((q & ((1 << s) - 1)) << lp)];
+        bfly4(v[q], v[q | (1 << s)], t);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) tile[(j0 + (q << lp)) * H + h] = v[q];
+  }
+}
+template <int COLS>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
+ntt_pass_wide_kernel(int log_h, int l0, int L, const uint32_t* __restrict__ tw, int tw_shift, uint32_t tile0, uint32_t n_col_tiles,
+                     const uint32_t* __restrict__ tw_pass, const NttScatter sc, const __grid_constant__ CUtensorMap tmap,
+                     const __grid_constant__ NttPeerMaps peer_maps) {
+  constexpr int H = COLS / 4;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint4* tile = reinterpret_cast<uint4*>(smem_raw);  // [2^L][H]
+  uint32_t* tw_s = reinterpret_cast<uint32_t*>(tile + ((size_t)H << L));
+  uint64_t& tma_bar = *reinterpret_cast<uint64_t*>(tw_s + ((size_t)1 << L));
+  const uint64_t col0 = (uint64_t)(tile0 + blockIdx.x % n_col_tiles) * COLS;
+  const uint64_t grp = blockIdx.x / n_col_tiles;
+  const uint64_t row_lo = grp & (((uint64_t)1 << l0) - 1);
+  const int n_rows = 1 << L;
+  const int box_rows = n_rows < NTT_BOX_ROWS ? n_rows : NTT_BOX_ROWS;
+  const int row_hi0 = (int)((grp >> l0) << L);
+  if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&tma_bar, (uint32_t)n_rows * COLS * 4u);
+    for (int t = 0; t < n_rows; t += box_rows) tma_load_3d(tile + (size_t)t * H, &tmap, (int)col0, (int)row_lo, row_hi0 + t, &tma_bar);
+  }
+  for (int k = threadIdx.x + 1; k < n_rows; k += blockDim.x) {
+    uint32_t t = __ldg(tw_pass + k);
+    if (row_lo) {
+      const int ll = 31 - __clz(k);
+      t = kb_mul(t, __ldg(tw + ((row_lo << (log_h - (l0 + ll) - 1)) << tw_shift)));
+    }
+    tw_s[k] = t;
+  }
+  mbar_wait(&tma_bar, 0);
+  __syncthreads();
+  int lp = 0;
+  while (lp < L) {
+    const int rem = L - lp;
+    const int g = rem <= 4 ? (rem == 4 ? 2 : rem) : 3;
+    if (g == 3)
+      tile_group_wide<3, H>(tile, tw_s, L, lp);
+    else if (g == 2)
+      tile_group_wide<2, H>(tile, tw_s, L, lp);
+    else
+      tile_group_wide<1, H>(tile, tw_s, L, lp);
+    lp += g;
+    __syncthreads();
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sc.enabled) {
+      const int sh = sc.log_run - l0;
+      for (int t = 0; t < n_rows; t += sc.tma_box_rows) {
+        const int row_hi = row_hi0 + t;
+        tma_store_3d(&peer_maps.m[row_hi >> sh], (int)col0, (int)row_lo, (sc.rank << sh) | (row_hi & ((1 << sh) - 1)), tile + (size_t)t * H);
+      }
+    } else {
+      for (int t = 0; t < n_rows; t += box_rows) tma_store_3d(&tmap, (int)col0, (int)row_lo, row_hi0 + t, tile + (size_t)t * H);
+    }
+    tma_store_commit_wait();
+  }
+}
+
 // Generic single-layer kernel for widths that are not a multiple of 4 (not on the benchmark path).
 __global__ void ntt_layer_kernel(uint32_t* __restrict__ mat, uint64_t h, uint64_t w, int l, int log_h,
                                  const uint32_t* __restrict__ tw, int tw_shift) {
@@ -472,11 +563,12 @@ static TmaEncodeFn tma_encode_fn() {
   return fn;
 }
 // the h x w matrix as the tensor (column, row mod 2^l0, row div 2^l0); box = 8 columns x 1 x min(2^L, 256) rows, dense in shared memory
-static bool tma_make_map(CUtensorMap* map, uint32_t* d_mat, uint64_t h, uint64_t w, int l0, int L, int box_rows = 0) {
+static bool tma_make_map(CUtensorMap* map, uint32_t* d_mat, uint64_t h, uint64_t w, int l0, int L, int box_rows = 0,
+                         int box_cols = TILE_COLS) {
   const cuuint64_t dims[3] = {w, (cuuint64_t)1 << l0, h >> l0};
   const cuuint64_t strides[2] = {w * 4, (w * 4) << l0};  // bytes, dimensions 1 and 2
   if (box_rows <= 0) box_rows = (1 << L) < NTT_BOX_ROWS ? (1 << L) : NTT_BOX_ROWS;
-  const cuuint32_t box[3] = {(cuuint32_t)TILE_COLS, 1, (cuuint32_t)box_rows};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, 1, (cuuint32_t)box_rows};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
   return tma_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_mat, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -515,9 +607,17 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
                       h < ((uint64_t)1 << 31) && w < ((uint64_t)1 << 31);
   // split log_h layers into ceil(log_h / 11) passes of nearly equal depth
   const int n_pass = (log_h + MAX_TILE_LOG - 1) / MAX_TILE_LOG;
+  // the scattering pass of a two-pass transform prefers 9 layers: its tile can then be 32 columns wide (128-byte row pieces over NVLink)
+  static const bool wide_allowed = getenv("LM_NTT_NO_WIDE_SCATTER") == nullptr;
+  const uint32_t tiles8 = n_tiles ? n_tiles : (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
+  const bool wide_possible = scatter && wide_allowed && tma_ok && n_pass == 2 && getenv("LM_NTT_NO_TMA_SCATTER") == nullptr &&
+                             w % 16 == 0 && (col_tile0 * TILE_COLS) % 16 == 0 && (tiles8 * TILE_COLS) % 16 == 0;
+  const int last_L_pref = (wide_possible && log_h - 9 <= MAX_TILE_LOG && w % 32 == 0 && (col_tile0 * TILE_COLS) % 32 == 0 &&
+                           (tiles8 * TILE_COLS) % 32 == 0 && log_h >= 10) ? 9 : 0;
   int l0 = 0, skip_left = skip;
   for (int p = 0; p < n_pass; p++) {
-    const int L = (log_h - l0 + (n_pass - p) - 1) / (n_pass - p);
+    int L = (log_h - l0 + (n_pass - p) - 1) / (n_pass - p);
+    if (last_L_pref && n_pass == 2) L = p == 0 ? log_h - last_L_pref : last_L_pref;
     const int sk = skip_left < L ? skip_left : L;
     skip_left -= sk;
     const uint32_t tiles = n_tiles ? n_tiles : (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
@@ -540,6 +640,37 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
         bool ok = true;
         for (int q = 0; q < NTT_MAX_PEERS && sc.dst[q] && ok; q++)
           ok = (reinterpret_cast<uintptr_t>(sc.dst[q]) & 15) == 0 && tma_make_map(&peer_maps.m[q], sc.dst[q], h, w, l0, L, box);
+        // wide tile for this pass: 32 columns when it has <= 9 layers, 16 when it has 10
+        int wide_cols = 0;
+        if (wide_possible && p > 0 && sk == 0) wide_cols = (L <= 9 && last_L_pref) ? 32 : (L <= 10 ? 16 : 0);
+        if (ok && wide_cols) {
+          for (int q = 0; q < NTT_MAX_PEERS && sc.dst[q] && ok; q++) ok = tma_make_map(&peer_maps.m[q], sc.dst[q], h, w, l0, L, box, wide_cols);
+          CUtensorMap wmap;
+          if (ok && tma_make_map(&wmap, d_mat, h, w, l0, L, 0, wide_cols)) {
+            sc.tma_box_rows = box;
+            const uint32_t wtiles = tiles8 * TILE_COLS / wide_cols, wtile0 = col_tile0 * TILE_COLS / wide_cols;
+            const size_t wsmem = ((size_t)1 << L) * (wide_cols * 4 + 4) + 16;
+            static bool wattr = false;
+            if (!wattr) {
+              cudaFuncSetAttribute(ntt_pass_wide_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 68 + 16);
+              cudaFuncSetAttribute(ntt_pass_wide_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 9) * 132 + 16);
+              wattr = true;
+            }
+            const unsigned wg = (unsigned)((uint64_t)wtiles * (h >> L));
+            if (wide_cols == 32)
+              ntt_pass_wide_kernel<32><<<wg, NTT_THREADS, wsmem, stream>>>(log_h, l0, L, d_tw, tw_shift, wtile0, wtiles, tw_pass, sc, wmap, peer_maps);
+            else
+              ntt_pass_wide_kernel<16><<<wg, NTT_THREADS, wsmem, stream>>>(log_h, l0, L, d_tw, tw_shift, wtile0, wtiles, tw_pass, sc, wmap, peer_maps);
+            count_launch();
+            static const bool dbgw = getenv("LM_NTT_DEBUG") != nullptr;
+            if (dbgw) fprintf(stderr, "[lm ntt] scatter pass l0=%d L=%d on %d-column tiles (box %d rows)\n", l0, L, wide_cols, box);
+            cudaError_t ew = cudaGetLastError();
+            if (ew != cudaSuccess) return ew;
+            l0 += L;
+            continue;
+          }
+          ok = false;  // fall back to the 8-column pass with SM stores (the peer maps now describe wide boxes)
+        }
         if (ok) sc.tma_box_rows = box;
         static const bool dbg = getenv("LM_NTT_DEBUG") != nullptr;
         if (dbg) fprintf(stderr, "[lm ntt] scatter pass l0=%d L=%d log_run=%d: %s (box %d rows)\n", l0, L, sc.log_run, ok ? "TMA stores into the peer matrices" : "tensor map of a peer matrix refused, SM stores", box);

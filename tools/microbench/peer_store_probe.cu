@@ -37,18 +37,20 @@ __global__ void __launch_bounds__(256) sm128_kernel(uint32_t* dst) {
     for (int k = 0; k < 8; k++) p[k] = v;
   }
 }
-template <int BOX_ROWS>
+// a CTA writes a tile of 64 KiB = (TILE_ROWS * 8 / BOX_COLS) rows x BOX_COLS columns, in boxes of BOX_ROWS rows
+template <int BOX_ROWS, int BOX_COLS = 8>
 __global__ void __launch_bounds__(256) tma_kernel(const __grid_constant__ CUtensorMap map) {
   extern __shared__ __align__(128) uint8_t sm[];
-  const int ct = blockIdx.x % (W / 8), rb = blockIdx.x / (W / 8);
+  constexpr int T_ROWS = TILE_ROWS * 8 / BOX_COLS;
+  const int ct = blockIdx.x % (W / BOX_COLS), rb = blockIdx.x / (W / BOX_COLS);
   for (int i = threadIdx.x; i < TILE_ROWS * 8; i += 256) reinterpret_cast<uint32_t*>(sm)[i] = i + blockIdx.x;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int b = 0; b < TILE_ROWS / BOX_ROWS; b++) {
-      const uint32_t src = (uint32_t)__cvta_generic_to_shared(sm + (size_t)b * BOX_ROWS * 32);
-      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map), "r"(src), "r"(8 * ct),
-                   "r"(rb * TILE_ROWS + b * BOX_ROWS)
+    for (int b = 0; b < T_ROWS / BOX_ROWS; b++) {
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(sm + (size_t)b * BOX_ROWS * BOX_COLS * 4);
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map), "r"(src), "r"(BOX_COLS * ct),
+                   "r"(rb * T_ROWS + b * BOX_ROWS)
                    : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -56,9 +58,9 @@ __global__ void __launch_bounds__(256) tma_kernel(const __grid_constant__ CUtens
   }
 }
 
-static int make_map(CUtensorMap* m, void* base, int box_rows) {
+static int make_map(CUtensorMap* m, void* base, int box_rows, int box_cols = 8) {
   cuuint64_t dims[2] = {W, ROWS}, strides[1] = {W * 4};
-  cuuint32_t box[2] = {8, (cuuint32_t)box_rows}, el[2] = {1, 1};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, el[2] = {1, 1};
   CUresult r = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled failed: %d\n", (int)r);
@@ -107,5 +109,52 @@ int main() {
   res[5] = {"local  tma32 ", time_it([&] { tma_kernel<32><<<ctas, 256, TILE_ROWS * 32>>>(l32); })};
   CK(cudaDeviceSynchronize());
   for (auto& r : res) printf("%s  %7.3f ms  %7.1f GB/s\n", r.name, r.ms, bytes / r.ms * 1e-6);
+  // wider row pieces through TMA (64 and 128 bytes per row), one direction
+  CUtensorMap m16, m32c;
+  if (make_map(&m16, d_peer, 128, 16) || make_map(&m32c, d_peer, 64, 32)) return 1;
+  CK(cudaFuncSetAttribute(tma_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_ROWS * 32));
+  CK(cudaFuncSetAttribute(tma_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_ROWS * 32));
+  const float t16 = time_it([&] { tma_kernel<128, 16><<<ctas, 256, TILE_ROWS * 32>>>(m16); });
+  const float t32 = time_it([&] { tma_kernel<64, 32><<<ctas, 256, TILE_ROWS * 32>>>(m32c); });
+  printf("peer   tma 16 cols (64 B per row)   %7.3f ms  %7.1f GB/s\n", t16, bytes / t16 * 1e-6);
+  printf("peer   tma 32 cols (128 B per row)  %7.3f ms  %7.1f GB/s\n", t32, bytes / t32 * 1e-6);
+  // both directions at once (what the exchange of the sharded commit does): device 1 writes into device 0 at the same time
+  CK(cudaSetDevice(1));
+  CK(cudaDeviceEnablePeerAccess(0, 0));
+  CUtensorMap r8, r32;
+  if (make_map(&r8, d_local, 32, 8) || make_map(&r32, d_local, 64, 32)) return 1;
+  CK(cudaFuncSetAttribute(tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_ROWS * 32));
+  CK(cudaFuncSetAttribute(tma_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_ROWS * 32));
+  cudaStream_t s1;
+  CK(cudaStreamCreate(&s1));
+  CK(cudaSetDevice(0));
+  auto both = [&](int which) {
+    // device 1 runs 8 launches back to back while device 0's single launch is timed
+    CK(cudaSetDevice(1));
+    for (int k = 0; k < 8; k++) {
+      if (which == 0) sm32_kernel<<<ctas, 256, 0, s1>>>(d_local);
+      if (which == 1) tma_kernel<32><<<ctas, 256, TILE_ROWS * 32, s1>>>(r8);
+      if (which == 2) tma_kernel<64, 32><<<ctas, 256, TILE_ROWS * 32, s1>>>(r32);
+    }
+    CK(cudaSetDevice(0));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    if (which == 0) sm32_kernel<<<ctas, 256>>>(d_peer);
+    if (which == 1) tma_kernel<32><<<ctas, 256, TILE_ROWS * 32>>>(m32);
+    if (which == 2) tma_kernel<64, 32><<<ctas, 256, TILE_ROWS * 32>>>(m32c);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    CK(cudaSetDevice(1));
+    CK(cudaStreamSynchronize(s1));
+    CK(cudaSetDevice(0));
+    const char* names[3] = {"sm32", "tma 8 cols", "tma 32 cols"};
+    printf("both directions busy, %-12s %7.3f ms  %7.1f GB/s per direction\n", names[which], ms, bytes / ms * 1e-6);
+    return 0;
+  };
+  for (int w = 0; w < 3; w++)
+    if (both(w)) return 1;
   return 0;
 }
