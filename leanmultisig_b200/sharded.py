@@ -807,7 +807,11 @@ class CudaBackend:
         # transform + hash takes about as long as its copy, so equal groups keep PCIe and the SMs busy and leave one group's
         # compute after the last byte; LM_COMMIT_DOUBLING_GROUPS=1: the round-1 schedule 1, 1, 2, 4, ..)
         doubling = bool(os.environ.get("LM_COMMIT_DOUBLING_GROUPS"))
-        chunk_end, take, first = n_chunks, (1 if doubling else (n_chunks + 7) // 8), True
+        # a group is at least as wide as the tile of the scattering pass (32 columns at 4+ ranks, 16 at 2: 128- / 64-byte row
+        # pieces over NVLink instead of 32-byte ones, csrc/ntt.cu ntt_pass_wide_kernel), which also bounds the number of
+        # exchange barriers per commit
+        wide_chunks = (4 if world >= 4 else 2) if n_chunks % (4 if world >= 4 else 2) == 0 else 1
+        chunk_end, take, first = n_chunks, (1 if doubling else max((n_chunks + 7) // 8, wide_chunks)), True
         while chunk_end > 0:
             take = min(take, chunk_end)
             col_begin, count = (chunk_end - take) * 8, take * 8
