@@ -112,6 +112,39 @@ __device__ __forceinline__ void fs_load_rc(uint32_t* rc_shared) {
   __syncwarp();
 }
 
+// The permutation on one warp: lane l holds state[l & 15] (both half-warps carry the same values); rc_s = shared-memory copy of
+// the round constants (fs_load_rc), mds_h = this half-warp's eight MDS coefficients mds[8 h + k], h = lane >> 4.
+// One warp runs straight-line code at the speed of its instruction fetches, so the round loop is NOT unrolled (the body
+// stays in the instruction cache) and the round constants come from shared memory, fetched one round ahead: measured 36 us
+// per transcript step with the constants loaded from global memory inside the loop, 30 us fully unrolled (45 KiB of code
+// fetched per permutation), a few us this way.
+__device__ __forceinline__ void fs_load_mds_half(uint32_t (&mds_h)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; k++) mds_h[k] = c_fs_mds[8 * ((threadIdx.x >> 4) & 1) + k];
+}
+static __device__ __noinline__ uint32_t fs_warp_permute(uint32_t v, const uint32_t* rc_s, const uint32_t (&mds_h)[8]) {
+  const int i = threadIdx.x & 15, kh = (threadIdx.x >> 1) & 8;  // kh = 8 h
+  uint32_t rc = rc_s[i];
+#pragma unroll 1
+  for (int r = 0; r < 28; r++) {
+    v = kb_add(v, rc);
+    rc = rc_s[((r + 1) % 28) * 16 + i];
+    const bool full = r < 4 || r >= 24;
+    if (full || i == 0) v = kb_mul(kb_mul(v, v), v);
+    // y_i = sum_k mds[k] x_{(i - k) mod 16}: half-warp h sums k = 8 h .. 8 h + 7 (canonical x, constants < p: four products
+    // per 64-bit accumulator), the halves meet through one 64-bit exchange
+    uint64_t a0 = 0, a1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      a0 = mad_wide(__shfl_sync(0xffffffffu, v, (i - kh - k) & 15), mds_h[k], a0);
+      a1 = mad_wide(__shfl_sync(0xffffffffu, v, (i - kh - k - 1) & 15), mds_h[k + 1], a1);
+    }
+    const uint64_t mine = kb_fold(a0) + kb_fold(a1);
+    v = kb_canon(kb_redc_lazy(mine + __shfl_xor_sync(0xffffffffu, mine, 16)));
+  }
+  return v;
+}
+
 // ---- the sponge, one warp; lane l holds state[l & 15] (both half-warps carry the same values) -----------------
 struct FsWarp {
   uint32_t x;
@@ -129,8 +162,7 @@ struct FsWarp {
     x = f->state[threadIdx.x & 15];
     fresh = f->rate_fresh != 0;
     n_words = f->n_words;
-#pragma unroll
-    for (int k = 0; k < 8; k++) mds_h[k] = c_fs_mds[8 * ((threadIdx.x >> 4) & 1) + k];
+    fs_load_mds_half(mds_h);
   }
   __device__ __forceinline__ void store() {
     __syncwarp();
@@ -144,33 +176,7 @@ struct FsWarp {
     if ((threadIdx.x & 31) == 0) atomicOr(&fs->error, bits);
   }
 
-  // One warp runs straight-line code at the speed of its instruction fetches, so the round loop is NOT unrolled (the body
-  // stays in the instruction cache) and the round constants come from the shared-memory copy made by load(), fetched one
-  // round ahead: measured 36 us per transcript step with the constants loaded from global memory inside the loop, 30 us
-  // fully unrolled (45 KiB of code fetched per permutation), a few us this way.
-  __device__ __noinline__ void permute() {
-    const int i = threadIdx.x & 15, kh = (threadIdx.x >> 1) & 8;  // kh = 8 h
-    uint32_t v = x;
-    uint32_t rc = rc_s[i];
-#pragma unroll 1
-    for (int r = 0; r < 28; r++) {
-      v = kb_add(v, rc);
-      rc = rc_s[((r + 1) % 28) * 16 + i];
-      const bool full = r < 4 || r >= 24;
-      if (full || i == 0) v = kb_mul(kb_mul(v, v), v);
-      // y_i = sum_k mds[k] x_{(i - k) mod 16}: half-warp h sums k = 8 h .. 8 h + 7 (canonical x, constants < p: four products
-      // per 64-bit accumulator), the halves meet through one 64-bit exchange
-      uint64_t a0 = 0, a1 = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        a0 = mad_wide(__shfl_sync(0xffffffffu, v, (i - kh - k) & 15), mds_h[k], a0);
-        a1 = mad_wide(__shfl_sync(0xffffffffu, v, (i - kh - k - 1) & 15), mds_h[k + 1], a1);
-      }
-      const uint64_t mine = kb_fold(a0) + kb_fold(a1);
-      v = kb_canon(kb_redc_lazy(mine + __shfl_xor_sync(0xffffffffu, mine, 16)));
-    }
-    x = v;
-  }
+  __device__ __noinline__ void permute() { x = fs_warp_permute(x, rc_s, mds_h); }
   // state[8..16] = chunk, permute (challenger.rs observe); `w` is this lane's chunk word for lanes with (l & 15) >= 8
   __device__ __forceinline__ void observe8(uint32_t w) {
     if ((threadIdx.x & 15) >= 8) x = w;

@@ -19,6 +19,7 @@
 #include "merkle.h"
 #include "poseidon1.cuh"
 #include "poseidon1_umma.cuh"
+#include "devfs.cuh"
 #include <mutex>
 #include <vector>
 
@@ -277,6 +278,48 @@ tree_levels_kernel(const uint32_t* __restrict__ layer0, uint64_t n0, int levels,
   }
 }
 
+// ---- the narrow levels: one WARP per parent ------------------------------------------------------------------------------
+// A level with fewer parents than the machine has lanes costs one compression of LATENCY, whatever kernel runs it: ~15-25 us
+// with one state per thread, 13 such levels per tree (a quarter of the tree's time on one GPU, a fifth of a whole sharded commit
+// on eight).  The transcript's warp-wide permutation (devfs.cuh: the 16 words of a state across the lanes, an MDS row split
+// between the half-warps) has ~3.3 us of latency: levels of at most 4096 parents run one warp per parent, one launch per level
+// (2^15: measured slower, the warp-wide form has a quarter of the throughput),
+// and the last levels (<= 32 parents) in ONE CTA with a barrier between levels.
+constexpr int TREE_WARP_MAX_PARENTS = 4096, TREE_WARP_TOP = 32;
+__device__ __forceinline__ void tree_warp_compress(const uint32_t* __restrict__ children, uint32_t* __restrict__ parent,
+                                                   const uint32_t* rc_s, const uint32_t (&mds_h)[8]) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t x = children[lane & 15];
+  const uint32_t y = kb_add(fs_warp_permute(x, rc_s, mds_h), x);  // compress_in_place: permute + feed-forward, first 8 words kept
+  if (lane < 8) parent[lane] = y;
+}
+__global__ void __launch_bounds__(256) tree_level_warp_kernel(const uint32_t* __restrict__ prev, uint64_t n_next, uint32_t* __restrict__ next) {
+  __shared__ uint32_t rc_s[DEVFS_RC_WORDS];
+  for (int t = threadIdx.x; t < DEVFS_RC_WORDS; t += blockDim.x) rc_s[t] = (&d_fs_tables.rc[0][0])[t];
+  __syncthreads();
+  uint32_t mds_h[8];
+  fs_load_mds_half(mds_h);
+  const uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_next) return;  // whole warps leave together
+  tree_warp_compress(prev + 16 * i, next + 8 * i, rc_s, mds_h);
+}
+// layer0: n0 <= 2 * TREE_WARP_TOP digests; all remaining levels, layer (l + 1) behind layer l
+__global__ void __launch_bounds__(32 * TREE_WARP_TOP) tree_top_warp_kernel(uint32_t* layer0, uint64_t n0) {
+  __shared__ uint32_t rc_s[DEVFS_RC_WORDS];
+  for (int t = threadIdx.x; t < DEVFS_RC_WORDS; t += blockDim.x) rc_s[t] = (&d_fs_tables.rc[0][0])[t];
+  __syncthreads();
+  uint32_t mds_h[8];
+  fs_load_mds_half(mds_h);
+  const uint64_t w = threadIdx.x >> 5;
+  uint32_t* cur = layer0;
+  for (uint64_t n = n0; n > 1; n >>= 1) {
+    uint32_t* next = cur + 8 * n;
+    if (w < n / 2) tree_warp_compress(cur + 16 * w, next + 8 * w, rc_s, mds_h);
+    __syncthreads();  // the next level reads what this CTA just wrote to global memory
+    cur = next;
+  }
+}
+
 static State16 zero_suffix_state_host(uint32_t n_zero_chunks) {
   // sponge.rs:28-48 evaluated with the same arithmetic header on the host (a 16-word constant per commit shape)
   State16 st;
@@ -369,18 +412,35 @@ cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, ui
   uint64_t n = h;
   // wide levels: one launch per level, every thread busy
   const uint8_t* img = nullptr;
-  if (use_umma() && h / 2 >= 8192) {
+  static const bool warp_tail = getenv("LM_TREE_TAIL_THREADS") == nullptr;  // =1: the one-state-per-thread tail kernels
+  const uint64_t wide_min = 2 * (uint64_t)TREE_WARP_MAX_PARENTS;  // parents of the narrowest "wide" level (8192)
+  if (use_umma() && h / 2 >= wide_min) {
     cudaError_t e = umma_b_image(&img);
     if (e != cudaSuccess) return e;
     if ((e = umma_attr(tree_level_kernel<true>, LEAF_GROUPS)) != cudaSuccess) return e;
   }
-  while (n / 2 >= 8192) {
+  while (n / 2 >= wide_min) {
     uint32_t* next = cur + 8 * n;
     if (img)
       tree_level_kernel<true><<<(unsigned)leaf_grid(n / 2, UMMA_THREADS), UMMA_THREADS, p1u_smem_bytes(LEAF_GROUPS), stream>>>(
           cur, n / 2, next, img);
     else
       tree_level_kernel<false><<<(unsigned)((n / 2 + LEAF_THREADS - 1) / LEAF_THREADS), LEAF_THREADS, 0, stream>>>(cur, n / 2, next, nullptr);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    cur = next;
+    n >>= 1;
+  }
+  while (warp_tail && n > 1) {
+    if (n / 2 > (uint64_t)TREE_WARP_MAX_PARENTS) break;
+    if (n <= 2 * (uint64_t)TREE_WARP_TOP) {
+      tree_top_warp_kernel<<<1, 32 * TREE_WARP_TOP, 0, stream>>>(cur, n);
+      count_launch();
+      return cudaGetLastError();
+    }
+    uint32_t* next = cur + 8 * n;
+    tree_level_warp_kernel<<<(unsigned)((n / 2 + 7) / 8), 256, 0, stream>>>(cur, n / 2, next);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
