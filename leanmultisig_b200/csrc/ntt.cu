@@ -95,7 +95,11 @@ __device__ __forceinline__ void bfly4(uint4& a, uint4& b, uint32_t t) {
 #endif
 constexpr int NTT_MAX_PEERS = 16;
 constexpr int TILE_COLS = 8;       // u32 columns per tile = 32 B per row
-constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory
+constexpr int MAX_TILE_LOG = 11;   // 2048 rows x 32 B = 64 KiB of shared memory: three 256-thread CTAs per SM
+// Domains above 2^22 rows: tiles of 2^12 rows (128 KiB, ONE 1024-thread CTA per SM - the same 32 warps) keep 2^23 and 2^24 rows
+// at two passes over HBM; with 2^11-row tiles 2^24 rows need three 8-layer passes of small, sector-granular tiles (16.5 ms
+// against 1.85 ms for 2^22 rows, profiles/r02_p1_umma.txt section 8).
+constexpr int BIG_TILE_LOG = 12;
 
 // 16-byte slot of (row j, half) inside the shared tile: dense row-major, 32 B per row - the layout a TMA box has.
 // Layout study on the 2^22 x 64 transform (tools/sweep_ntt_tma.sh, profiles/r02_ntt_tma_sweep.txt): dense + TMA 2.00 ms, dense
@@ -207,7 +211,8 @@ struct NttPeerMaps {
 // src == nullptr: in place on `mat`; the tile arrives by 16-byte cp.async (all loads of a CTA in flight at once, no
 // register staging).  src != nullptr (only with l0 == 0): gather from the evaluation vector (dim = 1):
 // element (row, col) = src[(col << log_block) + (row >> r)].
-__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS)
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 ntt_pass_kernel(uint32_t* __restrict__ mat, const uint32_t* __restrict__ src, uint64_t w, int log_h, int l0, int L,
                 int skip, uint32_t log_block, uint32_t r, const uint32_t* __restrict__ tw, int tw_shift,
                 uint32_t tile0, uint32_t n_col_tiles, const uint32_t* __restrict__ tw_pass, const NttScatter sc,
@@ -595,7 +600,8 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG) * 36 + 16);
+    cudaFuncSetAttribute(ntt_pass_kernel<NTT_THREADS, NTT_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << MAX_TILE_LOG) * 36 + 16);
+    cudaFuncSetAttribute(ntt_pass_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << BIG_TILE_LOG) * 36 + 16);
     attr_set = true;
   }
 #if defined(NTT_SWIZZLE_XOR)
@@ -606,7 +612,9 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
   const bool tma_ok = tma_allowed && tma_encode_fn() != nullptr && (reinterpret_cast<uintptr_t>(d_mat) & 15) == 0 &&
                       h < ((uint64_t)1 << 31) && w < ((uint64_t)1 << 31);
   // split log_h layers into ceil(log_h / 11) passes of nearly equal depth
-  const int n_pass = (log_h + MAX_TILE_LOG - 1) / MAX_TILE_LOG;
+  static const bool big_tiles = getenv("LM_NTT_NO_BIG_TILES") == nullptr;
+  const int max_tile_log = (big_tiles && log_h > 2 * MAX_TILE_LOG && log_h <= 2 * BIG_TILE_LOG) ? BIG_TILE_LOG : MAX_TILE_LOG;
+  const int n_pass = (log_h + max_tile_log - 1) / max_tile_log;
   // the scattering pass of a two-pass transform prefers 9 layers: its tile can then be 32 columns wide (128-byte row pieces over NVLink)
   static const bool wide_allowed = getenv("LM_NTT_NO_WIDE_SCATTER") == nullptr;
   const uint32_t tiles8 = n_tiles ? n_tiles : (uint32_t)((w + TILE_COLS - 1) / TILE_COLS);
@@ -624,7 +632,7 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     const uint64_t n_cta = (uint64_t)tiles * (h >> L);
     const size_t smem = ((size_t)1 << L) * 36 + 16;  // tile + per-CTA twiddles + mbarrier
     // compact twiddles of this pass, in the scratch words behind the big table (ntt.h: NTT_TW_SCRATCH_WORDS)
-    uint32_t* tw_pass = const_cast<uint32_t*>(d_tw) + ((size_t)1 << (tw_log_n - 1)) + (size_t)(p % 4) * ((size_t)1 << MAX_TILE_LOG);
+    uint32_t* tw_pass = const_cast<uint32_t*>(d_tw) + ((size_t)1 << (tw_log_n - 1)) + (size_t)(p % 4) * ((size_t)1 << BIG_TILE_LOG);
     ntt_pass_twiddles_kernel<<<((1 << L) + 255) / 256, 256, 0, stream>>>(tw_pass, log_h, l0, L, d_tw, tw_shift); count_launch();
     NttScatter sc{};
     NttPeerMaps peer_maps;  // only read by the scattering pass (2 KiB of kernel parameters; per call: rank threads share the process)
@@ -680,9 +688,13 @@ static cudaError_t run_layers(cudaStream_t stream, uint32_t* d_mat, const uint32
     memset(&tmap, 0, sizeof(tmap));
     int tma = 0;
     if (tma_ok && tma_make_map(&tmap, d_mat, h, w, l0, L)) tma = NTT_TMA_LOAD | NTT_TMA_STORE;
-    ntt_pass_kernel<<<(unsigned)n_cta, NTT_THREADS, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk,
-                                                            log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass, sc, tmap, tma,
-                                                            peer_maps); count_launch();
+    if (L > MAX_TILE_LOG)
+      ntt_pass_kernel<1024, 1><<<(unsigned)n_cta, 1024, smem, stream>>>(d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk, log_block, r,
+                                                                         d_tw, tw_shift, col_tile0, tiles, tw_pass, sc, tmap, tma, peer_maps);
+    else
+      ntt_pass_kernel<NTT_THREADS, NTT_MIN_BLOCKS><<<(unsigned)n_cta, NTT_THREADS, smem, stream>>>(
+          d_mat, p == 0 ? d_src : nullptr, w, log_h, l0, L, sk, log_block, r, d_tw, tw_shift, col_tile0, tiles, tw_pass, sc, tmap, tma, peer_maps);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     l0 += L;

@@ -8,7 +8,7 @@ namespace lm {
 uint32_t two_adic_generator_monty(unsigned bits);
 // Every d_tw passed to this interface holds 2^(log_n - 1) + NTT_TW_SCRATCH_WORDS words: the table, then scratch for the
 // compact per-pass twiddle tables the pass kernels read (written by the launcher, stream-ordered).
-constexpr size_t NTT_TW_SCRATCH_WORDS = 4 * 2048;
+constexpr size_t NTT_TW_SCRATCH_WORDS = 4 * 4096;
 // d_tw[e] = g^e, e < 2^(log_n - 1), g = primitive 2^log_n-th root of unity (Montgomery form)
 cudaError_t ntt_fill_twiddles(cudaStream_t stream, uint32_t* d_tw, unsigned log_n);
 // in-place evals-DFT of an h x w row-major matrix, skipping the first `skip_layers` layers

@@ -138,3 +138,24 @@ def test_product_sumcheck_2_22_equals_oracle():
     assert np.array_equal(gp, cur_p) and np.array_equal(gw, cur_w)
     sc.free()
     ctx.close()
+
+
+@pytest.mark.parametrize("log_h", [23, 24])
+def test_transform_above_2_22_rows_equals_oracle(log_h):
+    """Domains above 2^22 rows take two passes over 2^12-row tiles (one 1024-thread CTA per SM, csrc/ntt.cu BIG_TILE_LOG) instead of
+    three passes over 2^11-row tiles: the gather + evals-DFT of 8 columns and the in-place DFT of a random matrix, exact
+    (dft.rs:79-144, utils.rs:128-150).  KoalaBear's two-adicity caps the domain at 2^24 rows."""
+    import leanmultisig_b200 as lm
+
+    ctx = lm.Context(0, 24)
+    rng = np.random.default_rng(log_h)
+    k, r, cols = 3, 1, 8
+    n_vars = log_h + k - r
+    ev = rng.integers(0, O.P, size=1 << n_vars, dtype=np.uint32)
+    got = ctx.reorder_and_dft(ev, n_vars, k, r, cols)
+    exp = O.reorder_and_dft(ev, n_vars, 1, k, r, cols)
+    assert got.shape == (1 << log_h, cols) and _sha(got) == _sha(exp)
+    del got, exp, ev
+    mat = rng.integers(0, O.P, size=(1 << log_h, 4), dtype=np.uint32)
+    assert _sha(ctx.dft_batch_by_evals(mat)) == _sha(O.dft_batch_by_evals(mat))
+    ctx.close()
