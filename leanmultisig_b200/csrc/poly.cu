@@ -12,6 +12,7 @@
 // reduction; the kernel is HBM-bound (4 B per element read once).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include "launch_count.h"
 #include "reduce.cuh"
 #include "kb.cuh"
@@ -121,6 +122,99 @@ mle_eval_kernel(const uint32_t* __restrict__ evals, int lo_vars, uint64_t live_r
   }
 }
 
+// Base-field polynomials, four consecutive low indices per thread: per row ONE 16-byte load and the five (CTA-uniform) words of
+// eq_hi[row] feed twenty multiply-accumulates.  mle_eval_kernel<1> issues six loads per element (the eq_hi words once per
+// thread and row) and is bound by the load / L1 pipe, not by HBM: 0.31 ms for 2^27 live entries = 1.7 TB/s (round 1: "0.23 of HBM").
+constexpr int EVAL_VEC_THREADS = 256;
+__global__ void __launch_bounds__(EVAL_VEC_THREADS)
+mle_eval_vec4_kernel(const uint32_t* __restrict__ evals, int lo_vars, uint64_t live_rows, uint64_t rows_per_cta,
+                     const uint32_t* __restrict__ eq_hi, const uint32_t* __restrict__ eq_lo, uint32_t* __restrict__ partial) {
+  __shared__ Ef red[EVAL_VEC_THREADS / 32];
+  const int t = threadIdx.x;
+  const uint64_t n_lo = (uint64_t)1 << lo_vars;
+  const uint64_t row0 = (uint64_t)blockIdx.x * rows_per_cta;
+  uint64_t row1 = row0 + rows_per_cta;
+  if (row1 > live_rows) row1 = live_rows;
+  Ef acc = ef_zero();
+  if ((uint64_t)(4 * t) < n_lo) {
+    uint64_t a[4][5];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int c = 0; c < 5; c++) a[q][c] = 0;
+    // rows in groups of three: the three 16-byte loads are in flight together, one fold per group (three products of
+    // < 0.2462 * 2^64 on a folded accumulator)
+    uint64_t row = row0;
+    for (; row + 3 <= row1; row += 3) {
+      uint4 f4[3];
+      uint32_t e[3][5];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        f4[r] = __ldg(reinterpret_cast<const uint4*>(evals + (row + r) * n_lo) + t);
+#pragma unroll
+        for (int c = 0; c < 5; c++) e[r][c] = __ldg(eq_hi + 5 * (row + r) + c);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) a[q][c] = kb_fold(a[q][c]);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const uint32_t f[4] = {f4[r].x, f4[r].y, f4[r].z, f4[r].w};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+          for (int c = 0; c < 5; c++) a[q][c] = mad_wide(f[q], e[r][c], a[q][c]);
+      }
+    }
+    if (row < row1) {  // up to two rows left
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) a[q][c] = kb_fold(a[q][c]);
+      for (; row < row1; row++) {
+        const uint4 f4 = __ldg(reinterpret_cast<const uint4*>(evals + row * n_lo) + t);
+        const uint32_t f[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+          const uint32_t ec = __ldg(eq_hi + 5 * row + c);
+#pragma unroll
+          for (int q = 0; q < 4; q++) a[q][c] = mad_wide(f[q], ec, a[q][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      Ef s, l;
+#pragma unroll
+      for (int c = 0; c < 5; c++) s.c[c] = kb_canon(kb_redc_lazy(kb_fold(a[q][c])));
+#pragma unroll
+      for (int c = 0; c < 5; c++) l.c[c] = __ldg(eq_lo + 5 * (4 * t + q) + c);
+      acc = ef_add(acc, ef_mul(s, l));
+    }
+  }
+  acc = warp_reduce_ef(acc);
+  if ((t & 31) == 0) red[t >> 5] = acc;
+  __syncthreads();
+  if (t < 32) {
+    Ef v = (t < EVAL_VEC_THREADS / 32) ? red[t] : ef_zero();
+    v = warp_reduce_ef(v);
+    if (t == 0) {
+#pragma unroll
+      for (int c = 0; c < 5; c++) partial[5 * blockIdx.x + c] = v.c[c];
+    }
+  }
+}
+// base-field evaluation kernel of choice for this shape
+static void launch_mle_eval_base(cudaStream_t stream, const uint32_t* d_evals, int lo_vars, uint64_t live_rows, uint64_t rows_per_cta,
+                                 uint64_t n_cta, const uint32_t* d_eq_hi, const uint32_t* d_eq_lo, uint32_t* d_partial) {
+  static const bool vec_ok = getenv("LM_MLE_EVAL_SCALAR") == nullptr;
+  if (vec_ok && lo_vars >= 2 && ((1u << lo_vars) / 4) <= (unsigned)EVAL_VEC_THREADS && (reinterpret_cast<uintptr_t>(d_evals) & 15) == 0)
+    mle_eval_vec4_kernel<<<(unsigned)n_cta, EVAL_VEC_THREADS, 0, stream>>>(d_evals, lo_vars, live_rows, rows_per_cta, d_eq_hi, d_eq_lo, d_partial);
+  else
+    mle_eval_kernel<1><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_evals, lo_vars, live_rows, rows_per_cta, d_eq_hi, d_eq_lo, d_partial);
+}
+
 __global__ void sum_partials_kernel(const uint32_t* __restrict__ partial, int n, uint32_t* __restrict__ out) {
   // single CTA of 256 threads
   __shared__ Ef red[8];
@@ -172,8 +266,7 @@ cudaError_t mle_eval(cudaStream_t stream, const uint32_t* d_evals, uint32_t n_va
   n_cta = rows_per_cta ? (live_rows + rows_per_cta - 1) / rows_per_cta : 1;
   if (n_cta == 0) n_cta = 1;
   if (dim == 1)
-    mle_eval_kernel<1><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_evals, lo_vars, live_rows, rows_per_cta, d_eq_hi,
-                                                                     d_eq_lo, d_partial);
+    launch_mle_eval_base(stream, d_evals, lo_vars, live_rows, rows_per_cta, n_cta, d_eq_hi, d_eq_lo, d_partial);
   else
     mle_eval_kernel<5><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_evals, lo_vars, live_rows, rows_per_cta, d_eq_hi,
                                                                      d_eq_lo, d_partial); count_launch();
@@ -205,8 +298,7 @@ cudaError_t mle_eval_batch(cudaStream_t stream, const uint32_t* const* d_cols, c
     const uint64_t rows_per_cta = (live_rows + n_cta - 1) / n_cta;
     n_cta = rows_per_cta ? (live_rows + rows_per_cta - 1) / rows_per_cta : 1;
     if (n_cta == 0) n_cta = 1;
-    mle_eval_kernel<1><<<(unsigned)n_cta, EVAL_THREADS, 0, stream>>>(d_cols[k], lo_vars, live_rows, rows_per_cta, d_eq_hi, d_eq_lo,
-                                                                     d_partial);
+    launch_mle_eval_base(stream, d_cols[k], lo_vars, live_rows, rows_per_cta, n_cta, d_eq_hi, d_eq_lo, d_partial);
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     sum_partials_kernel<<<1, 256, 0, stream>>>(d_partial, (int)n_cta, d_out + 5 * k);
