@@ -381,6 +381,10 @@ int lm_host_poseidon1_permute(uint32_t state[16]);
  * products it stands for).  A test hook: lets the CPU tier pin the formulation against poseidon1_koalabear_16.rs:873 without a
  * GPU.  Not a product path. */
 int lm_host_poseidon1_umma_model(uint32_t state[16]);
+/* The B-matrix image those kernels stage in shared memory (test hook: the CPU tier checks on the actual constants that every s32
+ * accumulator column and every carry-free recombination stays inside its bound).  Returns the image size in bytes; copies it to
+ * `out` when `capacity` is large enough (out may be NULL to query the size). */
+uint64_t lm_host_poseidon1_umma_image(uint8_t* out, uint64_t capacity);
 
 /* ---- Host spine in C++ (csrc/spine.cu), built above the entry points of this header ---------------------------
  * lm_fs mirrors ProverState + Challenger (crates/backend/fiat-shamir/src/prover.rs:28-178, challenger.rs:8-76): the

@@ -143,6 +143,7 @@ def lib() -> C.CDLL:
             "lm_dev_poseidon16_fill_trace": [vp, vp, u64],
             "lm_host_poseidon1_permute": [u32p],
             "lm_host_poseidon1_umma_model": [u32p],
+            "lm_host_poseidon1_umma_image": [vp, u64],
             "lm_fs_new": [vp, C.POINTER(vp)],
             "lm_fs_free": [vp],
             "lm_fs_add_scalars": [vp, u32p, u64],
@@ -173,6 +174,7 @@ def lib() -> C.CDLL:
             fn.restype = C.c_int
         L.lm_lz4_compress_bound.argtypes = [u64]
         L.lm_lz4_compress_bound.restype = C.c_uint64
+        L.lm_host_poseidon1_umma_image.restype = C.c_uint64
         _lib = L
     return _lib
 

@@ -376,6 +376,9 @@ int lm_host_poseidon1_permute(uint32_t* state) {
   lm::poseidon1_permute_host(state);
   return LM_OK;
 }
+uint64_t lm_host_poseidon1_umma_image(uint8_t* out, uint64_t capacity) {
+  return (uint64_t)lm::poseidon1_umma_image_host(out, (size_t)capacity);
+}
 int lm_host_poseidon1_umma_model(uint32_t* state) {
   if (!state) return fail(LM_ERR_INVALID, "lm_host_poseidon1_umma_model: null state");
   lm::poseidon1_permute_umma_model_host(state);

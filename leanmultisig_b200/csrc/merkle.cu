@@ -635,6 +635,11 @@ cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bi
 // it stays on the host, evaluated with the same arithmetic header as the device code.
 void poseidon1_permute_host(uint32_t state[16]) { p1_permute<16>(state, h_p1); }
 
+// the B image of the tensor-core formulation as the kernels load it (P1U_B_BYTES bytes, layout in poseidon1_umma.cuh)
+size_t poseidon1_umma_image_host(uint8_t* out, size_t capacity) {
+  if (out && capacity >= (size_t)P1U_B_BYTES) p1u_build_b_image(h_p1, out);
+  return (size_t)P1U_B_BYTES;
+}
 // CPU model of the tensor-core formulation (poseidon1_umma.cuh): the B image the kernels load, the MMAs as integer dot products
 void poseidon1_permute_umma_model_host(uint32_t state[16]) {
   static const std::vector<uint8_t> img = [] {

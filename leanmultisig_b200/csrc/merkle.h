@@ -26,4 +26,6 @@ cudaError_t pow_grind(cudaStream_t stream, const uint32_t state[16], uint32_t bi
 void poseidon1_permute_host(uint32_t state[16]);
 // the same permutation through the CPU model of the tensor-core formulation (test hook for the CPU tier)
 void poseidon1_permute_umma_model_host(uint32_t state[16]);
+// the B-matrix image of that formulation; returns its size (copies when `capacity` suffices)
+size_t poseidon1_umma_image_host(uint8_t* out, size_t capacity);
 }  // namespace lm

@@ -103,6 +103,48 @@ def test_tensor_core_poseidon_formulation_model_matches_oracle(rng):
         assert np.array_equal(st, exp[i]), i
 
 
+def test_tensor_core_poseidon_image_bounds():
+    """The exactness argument of csrc/poseidon1_umma.cuh on the ACTUAL constants: every s32 accumulator column of every product
+    stays below 2^24 for all-255 input bytes (so the u8 x u8 -> s32 MMAs never wrap and the byte recombination has room), and
+    the carry-free low word `init + T0 + 2^8 T1` of the recombination stays below 2^32 with the largest additive constant.
+    Columns that accumulate several products (D = G x' plus the triangle blocks) are checked on their totals."""
+    from leanmultisig_b200._lib import lib
+
+    n = int(lib().lm_host_poseidon1_umma_image(None, 0))
+    img = np.zeros(n, dtype=np.uint8)
+    assert int(lib().lm_host_poseidon1_umma_image(img.ctypes.data_as(C.c_void_p), n)) == n
+
+    def col_sums(base, n_cols, k_bytes):  # K-major canonical layout: 8-column x 16-byte core matrices, LBO 128, SBO = k_bytes / 16 * 128
+        kchunks = k_bytes // 16
+        out = np.zeros(n_cols, dtype=np.int64)
+        for c in range(n_cols):
+            for kc in range(kchunks):
+                off = base + (c // 8) * (kchunks * 128) + kc * 128 + (c % 8) * 16
+                out[c] += int(img[off:off + 16].astype(np.int64).sum())
+        return out
+
+    B_MDS, B_G, B_MV = 0, 8192, 8192 + 6144
+    B_T0 = B_MV + 10240
+    B_T1 = B_T0 + 1536
+    assert n == B_T1 + 512
+    mds = 255 * col_sums(B_MDS, 64, 128)
+    g = 255 * col_sums(B_G, 96, 64)
+    g[32:80] += 255 * col_sums(B_T0, 48, 32)   # z_0..7 accumulate into D_8..19
+    g[64:80] += 255 * col_sums(B_T1, 16, 32)   # z_8..15 into D_16..19
+    mv = 255 * col_sums(B_MV, 64, 160)
+    assert g[84:].max() == 0 and mv[60:].max() == 0                      # padding columns are empty
+    for name, t, init in (("mds", mds, O.P - 1), ("g", g[:84], O.P - 1), ("mv", mv[:60], 0)):
+        assert int(t.max()) < 1 << 24, name
+        t = t.reshape(-1, 4)
+        low = init + t[:, 0] + (t[:, 1] << 8)
+        assert int(low.max()) < 1 << 32, (name, int(low.max()))
+        # the reduced lane is < p + 2^16: the whole recombined value stays below 2^48
+        full = init + t[:, 0] + (t[:, 1] << 8) + (t[:, 2] << 16) + (t[:, 3] << 24)
+        assert int(full.max()) < 1 << 48, name
+    # no output column is identically zero (every lane depends on its inputs)
+    assert (mds > 0).all() and (g[:84] > 0).all() and (mv[:60] > 0).all()
+
+
 def test_native_prover_state_matches_the_python_transcript():
     """lm_fs (C++ ProverState, csrc/spine.cu) against the Python mirror and the oracle's challenger on one script of
     absorb / squeeze operations: identical samples, transcript and sponge state.  Host code only (no device)."""
