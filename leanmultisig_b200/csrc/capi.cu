@@ -1022,8 +1022,9 @@ int lm_sc_add_eq_batch(lm_sumcheck* s, uint64_t selector, const uint32_t* points
     return fail(LM_ERR_INVALID, "lm_sc_add_eq_batch: bad selector / point length / count");
   lm_ctx* c = s->ctx;
   CU(cudaSetDevice(c->device));
-  for (uint32_t k0 = 0; k0 < n_st; k0 += 16) {  // at most 16 statements per pass (table footprint)
-    const uint32_t K = n_st - k0 < 16 ? n_st - k0 : 16;
+  const uint32_t k_max = lm::weights_add_eq_batch_max(m);  // statements per pass (table footprint / accumulator bounds)
+  for (uint32_t k0 = 0; k0 < n_st; k0 += k_max) {
+    const uint32_t K = n_st - k0 < k_max ? n_st - k0 : k_max;
     const size_t tab = lm::weights_add_eq_batch_scratch_words(m, K);
     int rc = s->ensure_scratch(tab + (size_t)K * m * 5 + lm::prod_round_scratch_words());
     if (rc != LM_OK) return rc;

@@ -110,7 +110,9 @@ weights_add_split_batch_kernel(uint32_t* __restrict__ w, uint64_t base, uint64_t
 constexpr int WG_TILE_XLO = 4;                      // values of the 10-variable index per N tile
 constexpr int WG_TILE_N = WG_TILE_XLO * 5 * 4;      // 80 accumulator columns
 constexpr int WG_TMEM_COLS = 128;
-constexpr int WG_KMAX = 16;
+// 12 statements = 240 input bytes per row: every accumulator column stays below 240 * 255^2 < 2^24 and the carry-free low word
+// T0 + 2^8 T1 below 2^32 for ANY inputs (13 would not); larger batches are split by the caller (weights_add_eq_batch_max)
+constexpr int WG_KMAX = 12;
 
 __host__ __device__ inline uint32_t wg_kbytes(int K) { return (uint32_t)((20 * K + 31) / 32 * 32); }
 
@@ -301,6 +303,8 @@ cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t se
   count_launch();
   return cudaGetLastError();
 }
+// statements one call of weights_add_eq_batch takes for points of m coordinates
+uint32_t weights_add_eq_batch_max(uint32_t m) { return weights_gemm_ok(m, 1) ? (uint32_t)WG_KMAX : 16u; }
 size_t weights_add_eq_batch_scratch_words(uint32_t m, uint32_t K) {
   const int lo_vars = m < (uint32_t)SPLIT_LO ? (int)m : SPLIT_LO;  // (the GEMM path splits the other way round: same table sizes)
   size_t words = 5 * (size_t)K * (((size_t)1 << (m - lo_vars)) + ((size_t)1 << lo_vars)) + 8;

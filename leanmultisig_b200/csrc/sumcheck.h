@@ -26,6 +26,9 @@ cudaError_t prod_fold_round(cudaStream_t stream, const uint32_t* d_p, uint32_t d
                             uint32_t* d_out10);
 cudaError_t weights_add_strided_eq(cudaStream_t stream, uint32_t* d_w, uint64_t base, uint32_t shift, uint64_t offset,
                                    const uint32_t* d_point, uint32_t pre, const uint32_t scalar[5]);
+// K <= weights_add_eq_batch_max(m) statements per call (12 on the tensor-core path, whose accumulator bounds hold for up to 240
+// input bytes per row; 16 on the scalar path)
+uint32_t weights_add_eq_batch_max(uint32_t m);
 size_t weights_add_eq_batch_scratch_words(uint32_t m, uint32_t K);
 cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_points, uint32_t m,
                                  const uint32_t* scalars, uint32_t K, uint32_t* d_scratch);

@@ -177,7 +177,7 @@ def test_whir_round_commit_and_ood_on_folded_polynomial(ctx, rng):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,sel_bits,k", [(6, 0, 2), (12, 0, 10), (14, 3, 5), (16, 0, 19), (11, 11, 3),
-                                          # m >= 17: the tensor-core GEMM path (csrc/sumcheck.cu weights_gemm_kernel), 1..16 statements
+                                          # m >= 17: the tensor-core GEMM path (csrc/sumcheck.cu weights_gemm_kernel), 12 statements per pass
                                           (17, 0, 1), (18, 1, 8), (19, 0, 3), (18, 0, 16), (19, 2, 21)])
 def test_add_eq_batch_equals_separate_statements(rng, n, sel_bits, k):
     """lm_sc_add_eq_batch (all statements of one selector and length in ONE pass over the weights, delayed reduction over the
