@@ -385,6 +385,12 @@ int lm_host_poseidon1_umma_model(uint32_t state[16]);
  * accumulator column and every carry-free recombination stays inside its bound).  Returns the image size in bytes; copies it to
  * `out` when `capacity` is large enough (out may be NULL to query the size). */
 uint64_t lm_host_poseidon1_umma_image(uint8_t* out, uint64_t capacity);
+/* CPU model of the tensor-core statement-weights kernel behind lm_sc_add_eq_batch (csrc/sumcheck.cu weights_gemm_kernel: same
+ * image builder, row layout and recombination, the MMAs as integer dot products) - test hook of the CPU tier:
+ * w[(x_hi << lo_vars) + x_lo] += sum_k hi_k[x_hi] * lo_k[x_lo], all extension elements as 5 words; hi: n_statements tables of
+ * 2^hi_vars entries one after the other, lo likewise. */
+int lm_host_eq_gemm_model(uint32_t* w, const uint32_t* hi, const uint32_t* lo, uint32_t n_statements, uint32_t hi_vars,
+                          uint32_t lo_vars);
 
 /* ---- Host spine in C++ (csrc/spine.cu), built above the entry points of this header ---------------------------
  * lm_fs mirrors ProverState + Challenger (crates/backend/fiat-shamir/src/prover.rs:28-178, challenger.rs:8-76): the

@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
             "lm_host_poseidon1_permute": [u32p],
             "lm_host_poseidon1_umma_model": [u32p],
             "lm_host_poseidon1_umma_image": [vp, u64],
+            "lm_host_eq_gemm_model": [u32p, u32p, u32p, u32, u32, u32],
             "lm_fs_new": [vp, C.POINTER(vp)],
             "lm_fs_free": [vp],
             "lm_fs_add_scalars": [vp, u32p, u64],

@@ -376,6 +376,13 @@ int lm_host_poseidon1_permute(uint32_t* state) {
   lm::poseidon1_permute_host(state);
   return LM_OK;
 }
+int lm_host_eq_gemm_model(uint32_t* w, const uint32_t* hi, const uint32_t* lo, uint32_t n_statements, uint32_t hi_vars, uint32_t lo_vars) {
+  if (!w || !hi || !lo) return fail(LM_ERR_INVALID, "lm_host_eq_gemm_model: null argument");
+  if (n_statements < 1 || n_statements > 12 || hi_vars < 2 || hi_vars > 16 || lo_vars > 20)
+    return fail(LM_ERR_INVALID, "lm_host_eq_gemm_model: 1..12 statements, 2..16 high variables, <= 20 low variables");
+  lm::weights_gemm_model_host(w, hi, lo, (int)n_statements, (int)hi_vars, (int)lo_vars);
+  return LM_OK;
+}
 uint64_t lm_host_poseidon1_umma_image(uint8_t* out, uint64_t capacity) {
   return (uint64_t)lm::poseidon1_umma_image_host(out, (size_t)capacity);
 }

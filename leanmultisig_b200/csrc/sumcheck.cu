@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
+#include <vector>
 #include "launch_count.h"
 #include "kb.cuh"
 #include "reduce.cuh"
@@ -116,30 +117,72 @@ constexpr int WG_KMAX = 12;
 
 __host__ __device__ inline uint32_t wg_kbytes(int K) { return (uint32_t)((20 * K + 31) / 32 * 32); }
 
-// one thread per (x_lo, k, t): the five constants rows[i][t] of ef_mul for b = lo_k[x_lo], pre-shifted for the four limbs of a_t
-__global__ void weights_gemm_image_kernel(const uint32_t* __restrict__ lo, int K, int lo_vars, uint8_t* __restrict__ img) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n_lo = 1u << lo_vars;
-  if (idx >= n_lo * (uint32_t)K * 5) return;
-  const uint32_t t = idx % 5, k = (idx / 5) % K, xl = idx / (5 * K);
-  const EfRows b = ef_rows(ld_ef(lo + 5 * ((size_t)k * n_lo + xl)));
+// image bytes of one (x, k, t): the five constants rows[i][t] of ef_mul for b = tab_k[x], pre-shifted for the four limbs of a_t
+// (shared by the device kernel and the CPU model below)
+LM_HD void wg_image_fill(const Ef& bval, uint32_t x, uint32_t k, uint32_t t, int K, uint8_t* img) {
+  const EfRows b = ef_rows(bval);
   const uint32_t rows[5][5] = {{b.b0, b.b4, b.b3, b.b2, b.b1m4},
                                {b.b1, b.b0, b.b4, b.b3, b.b2},
                                {b.b2, b.b1m4, b.b0m3, b.b4m2, b.b3m14},
                                {b.b3, b.b2, b.b1m4, b.b0m3, b.b4m2},
                                {b.b4, b.b3, b.b2, b.b1m4, b.b0m3}};
   const uint32_t kb = wg_kbytes(K), kchunks = kb / 16;
-  uint8_t* tile = img + (size_t)(xl / WG_TILE_XLO) * WG_TILE_N * kb;
+  uint8_t* tile = img + (size_t)(x / WG_TILE_XLO) * WG_TILE_N * kb;
   const uint32_t q = 5 * k + t;  // word index of a_t of statement k in the A row
   for (int i = 0; i < 5; i++) {
     uint64_t m = rows[i][t];
     for (int l = 0; l < 4; l++) {
       const uint32_t kbyte = 4 * q + l;
       for (int j = 0; j < 4; j++) {
-        const uint32_t n = ((xl % WG_TILE_XLO) * 5 + i) * 4 + j;
+        const uint32_t n = ((x % WG_TILE_XLO) * 5 + i) * 4 + j;
         tile[(n / 8) * (kchunks * 128) + (kbyte / 16) * 128 + (n % 8) * 16 + (kbyte % 16)] = (uint8_t)(m >> (8 * j));
       }
       m = (m << 8) % KB_P;
+    }
+  }
+}
+// one thread per (x, k, t) of the 2^vars-entry tables tab_k (K tables one after the other)
+__global__ void weights_gemm_image_kernel(const uint32_t* __restrict__ tab, int K, int vars, uint8_t* __restrict__ img) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = 1u << vars;
+  if (idx >= n * (uint32_t)K * 5) return;
+  const uint32_t t = idx % 5, k = (idx / 5) % K, x = idx / (5 * K);
+  wg_image_fill(ld_ef(tab + 5 * ((size_t)k * n + x)), x, k, t, K, img);
+}
+
+// CPU model of weights_gemm_kernel (test hook of the CPU tier, lm_host_eq_gemm_model): the same image builder, the same row
+// layout and recombination, the MMAs as the integer dot products they stand for.
+//   w[(x_hi << lo_vars) + x_lo] += sum_k hi_k[x_hi] * lo_k[x_lo];   hi: K x 2^hi_vars EF, lo: K x 2^lo_vars EF, hi_vars >= 2
+void weights_gemm_model_host(uint32_t* w, const uint32_t* hi, const uint32_t* lo, int K, int hi_vars, int lo_vars) {
+  const uint32_t n_hi = 1u << hi_vars, n_lo = 1u << lo_vars, kb = wg_kbytes(K), kchunks = kb / 16;
+  std::vector<uint8_t> img((size_t)n_hi / WG_TILE_XLO * WG_TILE_N * kb, 0), row(kb, 0);
+  for (uint32_t x = 0; x < n_hi; x++)
+    for (int k = 0; k < K; k++)
+      for (uint32_t t = 0; t < 5; t++) {
+        Ef b;
+        for (int c = 0; c < 5; c++) b.c[c] = hi[5 * ((size_t)k * n_hi + x) + c];
+        wg_image_fill(b, x, (uint32_t)k, t, K, img.data());
+      }
+  for (uint32_t xr = 0; xr < n_lo; xr++) {
+    for (int k = 0; k < K; k++)
+      for (int t = 0; t < 5; t++) {
+        const uint32_t word = lo[5 * ((size_t)k * n_lo + xr) + t];
+        for (int l = 0; l < 4; l++) row[4 * (5 * k + t) + l] = (uint8_t)(word >> (8 * l));
+      }
+    for (uint32_t xh = 0; xh < n_hi; xh++) {
+      const uint8_t* tile = img.data() + (size_t)(xh / WG_TILE_XLO) * WG_TILE_N * kb;
+      uint32_t* dst = w + 5 * (((size_t)xh << lo_vars) + xr);
+      for (int i = 0; i < 5; i++) {
+        uint32_t T[4];
+        for (int j = 0; j < 4; j++) {
+          const uint32_t n = ((xh % WG_TILE_XLO) * 5 + i) * 4 + j;
+          uint32_t sum = 0;
+          for (uint32_t kbyte = 0; kbyte < kb; kbyte++)
+            sum += (uint32_t)row[kbyte] * tile[(n / 8) * (kchunks * 128) + (kbyte / 16) * 128 + (n % 8) * 16 + (kbyte % 16)];
+          T[j] = sum;
+        }
+        dst[i] = kb_add(dst[i], kb_canon(p1u_combine_redc<0>(T[0], T[1], T[2], T[3], 0u)));
+      }
     }
   }
 }

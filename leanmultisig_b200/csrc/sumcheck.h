@@ -32,4 +32,6 @@ uint32_t weights_add_eq_batch_max(uint32_t m);
 size_t weights_add_eq_batch_scratch_words(uint32_t m, uint32_t K);
 cudaError_t weights_add_eq_batch(cudaStream_t stream, uint32_t* d_w, uint64_t selector, const uint32_t* d_points, uint32_t m,
                                  const uint32_t* scalars, uint32_t K, uint32_t* d_scratch);
+// CPU model of the tensor-core statement-weights kernel (test hook): w[(x_hi << lo_vars) + x_lo] += sum_k hi_k[x_hi] lo_k[x_lo]
+void weights_gemm_model_host(uint32_t* w, const uint32_t* hi, const uint32_t* lo, int K, int hi_vars, int lo_vars);
 }  // namespace lm

@@ -145,6 +145,26 @@ def test_tensor_core_poseidon_image_bounds():
     assert (mds > 0).all() and (g[:84] > 0).all() and (mv[:60] > 0).all()
 
 
+@pytest.mark.parametrize("k,hi_vars,lo_vars", [(1, 2, 3), (3, 4, 5), (8, 3, 4), (12, 2, 6)])
+def test_tensor_core_statement_weights_model_matches_oracle(rng, k, hi_vars, lo_vars):
+    """csrc/sumcheck.cu weights_gemm_kernel on the CPU: the statement weights sum_k scalar_k eq(point_k, x) as an integer GEMM of u8
+    limbs against pre-shifted row matrices (same image builder, row layout and recombination as the kernel, every MMA replaced by
+    its dot products) equals the oracle's weights_add_eq (open.rs:518-584), on top of existing weights."""
+    from leanmultisig_b200._lib import check, lib
+
+    m = hi_vars + lo_vars
+    pts, scs = O.random_field(rng, (k, m, 5)), O.random_field(rng, (k, 5))
+    w = O.random_field(rng, (1 << m, 5))
+    exp = w.copy()
+    for i in range(k):
+        O.weights_add_eq(exp, 0, pts[i], scs[i])
+    hi = np.ascontiguousarray(np.stack([O.eq_table(pts[i][:hi_vars], scs[i]) for i in range(k)]))
+    lo = np.ascontiguousarray(np.stack([O.eq_table(pts[i][hi_vars:]) for i in range(k)]))
+    assert hi.shape == (k, 1 << hi_vars, 5) and lo.shape == (k, 1 << lo_vars, 5)
+    check(lib().lm_host_eq_gemm_model(w.ctypes.data_as(O.u32p), hi.ctypes.data_as(O.u32p), lo.ctypes.data_as(O.u32p), k, hi_vars, lo_vars))
+    assert np.array_equal(w, exp)
+
+
 def test_native_prover_state_matches_the_python_transcript():
     """lm_fs (C++ ProverState, csrc/spine.cu) against the Python mirror and the oracle's challenger on one script of
     absorb / squeeze operations: identical samples, transcript and sponge state.  Host code only (no device)."""
