@@ -20,6 +20,11 @@
 // thread with cp.async.bulk.tensor into shared memory and signalled through an mbarrier; every pass writes its tile back
 // with TMA stores (cp.async.bulk.tensor global <- shared).  This replaces 16 cp.async + 16 st.global and their address
 // arithmetic per thread (the pass kernels are issue-slot bound, ncu 66-68 %): 2.31 -> 2.00 ms on the 2^22 x 64 transform.
+//
+// Variants of the pass (round 2).  Domains above 2^22 rows: tiles of 2^12 rows, one 1024-thread CTA per SM, so that 2^23 and 2^24
+// rows stay at two passes (BIG_TILE_LOG).  Row-sharded commit: the last pass stores its tile into the matrices of the ranks that
+// own the rows after the exchange, by TMA through one tensor map per peer (NttPeerMaps), and runs on tiles of 16 or 32 columns
+// (ntt_pass_wide_kernel) because the NVLink fabric carries 128-byte row pieces 2.3x faster than 32-byte ones.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
