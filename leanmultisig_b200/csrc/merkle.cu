@@ -5,13 +5,19 @@
 //   crates/backend/symetric/src/sponge.rs:28-108 precompute_zero_suffix_state, hash_rtl_iter, absorb_rtl_chunks
 //   crates/backend/symetric/src/merkle.rs:21-35,50-90  MerkleTree::from_first_layer, compress_layer
 //
-// Kernels
-//   leaf_sponge_kernel   one thread per matrix row; the row is hashed right to left, rate 8 / width 16, as if
-//                        zero-extended to `full_w`; a run of >= 2 all-zero trailing rate chunks is replaced by the
-//                        pre-computed sponge state of those zeros (passed by value).  INT32-ALU bound: ~5k integer
-//                        instructions per compression against 32 B of row data.
-//   tree_levels_kernel   one CTA folds 2*T consecutive digests of a layer through up to log2(2T) levels, writing
-//                        every intermediate layer (all layers are retained for openings).
+// Kernels (the wide ones run Poseidon1 with its constant-matrix products on the tensor cores, poseidon1_umma.cuh; LM_P1_SCALAR=1
+// selects the one-state-per-thread form of poseidon1.cuh)
+//   leaf_sponge_kernel     one thread per matrix row; the row is hashed right to left, rate 8 / width 16, as if zero-extended to
+//                          `full_w`; a run of >= 2 all-zero trailing rate chunks is replaced by the pre-computed sponge state of
+//                          those zeros (passed by value).  Multiplier-pipe bound: ~3.1 k instructions per compression against 32 B
+//                          of row data (6.7 k one state per thread).
+//   leaf_absorb_kernel     the same sponge a run of chunks at a time (state kept in the digest buffer): lets the commit hash
+//                          columns while later columns are still crossing PCIe
+//   tree_level_kernel      one level, one thread per parent (levels with >= 8192 parents)
+//   tree_level_warp_kernel, tree_top_warp_kernel   the narrow levels, one WARP per parent (latency, not throughput)
+//   tree_levels_kernel     one CTA folds 2*T consecutive digests of a layer through up to log2(2T) levels (LM_TREE_TAIL_THREADS=1)
+//   pow_grind_umma_kernel  Fiat-Shamir proof-of-work search, one candidate per thread
+// Every intermediate layer is written (all layers are retained for openings).
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
