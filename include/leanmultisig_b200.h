@@ -87,6 +87,19 @@ int lm_open(lm_tree* tree, const uint64_t* indices, uint32_t n, uint32_t* out_ro
  * the folding randomness of the round); the fold runs on the device next to the gather. */
 int lm_open_fold(lm_tree* tree, const uint64_t* indices, uint32_t n, const uint32_t* fold_point, uint32_t fold_vars,
                  uint32_t* out_rows, uint32_t* out_paths, uint32_t* out_evals);
+/* Verifier side of the same openings: replaces the per-query loops of
+ * crates/whir/src/verify.rs:229-345 (verify_stir_challenges: merkle_verify of every opening of a round against the
+ * round's root, crates/whir/src/merkle.rs:115-150 -> crates/backend/symetric/src/merkle.rs:92-122 with hash_slice,
+ * sponge.rs:7-25) and, when fold_point is given, the fold of every opened leaf at the round's folding randomness that
+ * follows it (verify.rs: answers -> evaluate(folding_randomness)).  All pointers are HOST memory.
+ *   rows      n x width words (leaf data as the proof carries it: width = elements per leaf x elem_dim, a multiple of 8, >= 16)
+ *   paths     n x log_height x 8 words, leaf level first (restored paths: fiat-shamir/src/merkle_pruning.rs)
+ *   out_ok    n bytes: 1 = the opening hashes to root.  An index >= 2^log_height or a word that is not a canonical
+ *             Montgomery residue fails its opening (out_ok = 0); it is not an error of the call.
+ *   out_evals n x 5 words (only with fold_point / fold_vars; 2^fold_vars x elem_dim == width), may be NULL otherwise */
+int lm_verify_openings(lm_ctx* ctx, const uint32_t root[8], uint32_t log_height, const uint64_t* indices, uint32_t n,
+                       const uint32_t* rows, uint32_t width, uint32_t elem_dim, const uint32_t* paths,
+                       const uint32_t* fold_point, uint32_t fold_vars, uint8_t* out_ok, uint32_t* out_evals);
 /* height (rows), full row width in words, stored row width in words, elem_dim */
 int lm_tree_shape(const lm_tree* tree, uint64_t* height, uint32_t* full_width, uint32_t* stored_width,
                   uint32_t* elem_dim);

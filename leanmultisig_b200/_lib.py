@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
             "lm_commit_stacked": [vp, vp, u32, u32, u32, u32, C.POINTER(vp), u32p],
             "lm_access_counts": [vp, C.POINTER(vp), u64p, u32p, u32, u64, u32p],
             "lm_open": [vp, u64p, u32, u32p, u32p],
+            "lm_verify_openings": [vp, u32p, u32, u64p, u32, u32p, u32, u32, u32p, u32p, u32, C.POINTER(C.c_uint8), u32p],
             "lm_tree_shape": [vp, u64p, u32p, u32p, u32p],
             "lm_tree_eval": [vp, u32p, u32p],
             "lm_tree_read_codeword": [vp, u32p],

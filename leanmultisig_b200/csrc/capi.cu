@@ -851,6 +851,53 @@ int lm_open_fold(lm_tree* t, const uint64_t* indices, uint32_t n, const uint32_t
   return open_impl(t, indices, n, out_rows, out_paths, fold_point, fold_vars, out_evals);
 }
 
+int lm_verify_openings(lm_ctx* c, const uint32_t root[8], uint32_t log_height, const uint64_t* indices, uint32_t n,
+                       const uint32_t* rows, uint32_t width, uint32_t elem_dim, const uint32_t* paths, const uint32_t* fold_point,
+                       uint32_t fold_vars, uint8_t* out_ok, uint32_t* out_evals) {
+  if (!c || !root || (n && (!indices || !rows || !out_ok || (log_height && !paths))))
+    return fail(LM_ERR_INVALID, "lm_verify_openings: null argument");
+  if (width < 16 || (width & 7)) return fail(LM_ERR_INVALID, "lm_verify_openings: row width %u is not a multiple of 8 >= 16", width);
+  if (log_height > 40) return fail(LM_ERR_INVALID, "lm_verify_openings: log_height %u", log_height);
+  const bool fold = fold_point || out_evals;
+  if (fold && (!out_evals || (fold_vars && !fold_point) || (elem_dim != 1 && elem_dim != 5) || fold_vars > 12 ||
+               ((uint32_t)1 << fold_vars) * elem_dim != width))
+    return fail(LM_ERR_INVALID, "lm_verify_openings: a leaf of %u words is not 2^%u elements of dimension %u", width, fold_vars, elem_dim);
+  if (n == 0) return LM_OK;
+  CU(cudaSetDevice(c->device));
+  const size_t rows_words = (size_t)n * width, paths_words = (size_t)n * log_height * 8;
+  const size_t evals_words = fold ? (size_t)n * 5 + (size_t)fold_vars * 5 : 0;
+  uint64_t* d_idx = nullptr;
+  uint32_t* d_buf = nullptr;  // rows | paths | root | ok | evals | point
+  CU(c->pool.alloc(&d_idx, n * sizeof(uint64_t)));
+  cudaError_t e = c->pool.alloc(&d_buf, (rows_words + paths_words + 8 + n + evals_words + 1) * sizeof(uint32_t));
+  uint32_t* d_paths = d_buf + rows_words;
+  uint32_t* d_root = d_paths + paths_words;
+  uint32_t* d_ok = d_root + 8;
+  uint32_t* d_ev = d_ok + n;
+  uint32_t* d_pt = d_ev + (size_t)n * 5;
+  std::vector<uint32_t> ok(n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, indices, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_buf, rows, rows_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess && paths_words)
+    e = cudaMemcpyAsync(d_paths, paths, paths_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_root, root, 8 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = lm::merkle_verify_openings(c->stream, d_root, log_height, d_idx, n, d_buf, width, d_paths, d_ok);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ok.data(), d_ok, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (fold) {
+    if (e == cudaSuccess && fold_vars)
+      e = cudaMemcpyAsync(d_pt, fold_point, (size_t)fold_vars * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = lm::rows_mle_eval(c->stream, d_buf, n, elem_dim, fold_vars, d_pt, d_ev);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_evals, d_ev, (size_t)n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream);
+  c->pool.free(d_idx);
+  if (d_buf) c->pool.free(d_buf);
+  if (e != cudaSuccess) return cuda_fail(e, "lm_verify_openings");
+  for (uint32_t q = 0; q < n; q++) out_ok[q] = ok[q] ? 1 : 0;
+  return LM_OK;
+}
+
 int lm_tree_eval(lm_tree* t, const uint32_t* point, uint32_t out[5]) {
   if (!t || !point || !out) return fail(LM_ERR_INVALID, "lm_tree_eval: null argument");
   if (!t->d_evals) return fail(LM_ERR_INVALID, "lm_tree_eval: the polynomial was not retained by this commit");

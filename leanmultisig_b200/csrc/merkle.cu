@@ -498,6 +498,69 @@ cudaError_t merkle_open_gather(cudaStream_t stream, const uint32_t* d_mat, const
   return cudaGetLastError();
 }
 
+// Verifier side: the openings of one STIR round checked against the round's root in one launch.
+// Replaces the per-query loops of crates/whir/src/verify.rs:313-318,333-338 over
+// crates/backend/symetric/src/merkle.rs:92-122 (merkle_verify) and sponge.rs:7-25 (hash_slice).
+// One WARP per opening on the transcript's warp-wide permutation (a STIR round has 20..230 openings: latency, not
+// throughput): lane j & 15 carries word j of the sponge / compression state.  A word that is not a canonical Montgomery
+// residue (>= p) fails the opening instead of entering the arithmetic.
+__global__ void __launch_bounds__(256) verify_openings_kernel(const uint32_t* __restrict__ root, uint32_t log_h,
+                                                              const uint64_t* __restrict__ indices, uint32_t n,
+                                                              const uint32_t* __restrict__ rows, uint32_t width,
+                                                              const uint32_t* __restrict__ paths, uint32_t* __restrict__ ok) {
+  __shared__ uint32_t rc_s[DEVFS_RC_WORDS];
+  for (int t = threadIdx.x; t < DEVFS_RC_WORDS; t += blockDim.x) rc_s[t] = (&d_fs_tables.rc[0][0])[t];
+  __syncthreads();
+  uint32_t mds_h[8];
+  fs_load_mds_half(mds_h);
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n) return;  // whole warps leave together
+  const int lane = threadIdx.x & 31, j = lane & 15;
+  const uint32_t* row = rows + (uint64_t)q * width;
+  bool good = true;
+  // hash_slice: the last 16 words, then one rate chunk at a time towards the front
+  uint32_t x = row[width - 16 + j];
+  good &= x < KB_P;
+  uint32_t y = kb_add(fs_warp_permute(x, rc_s, mds_h), x);
+  for (int64_t c = (int64_t)(width >> 3) - 3; c >= 0; c--) {
+    if (j >= 8) {
+      x = row[c * 8 + (j - 8)];
+      good &= x < KB_P;
+    } else {
+      x = y;
+    }
+    y = kb_add(fs_warp_permute(x, rc_s, mds_h), x);
+  }
+  // the path, leaf level first: (node, sibling) or (sibling, node) by the index bit
+  uint64_t idx = indices[q];
+  const uint32_t* sib = paths + (uint64_t)q * log_h * 8;
+  for (uint32_t l = 0; l < log_h; l++, sib += 8, idx >>= 1) {
+    const uint32_t moved = __shfl_sync(0xffffffffu, y, lane ^ 8);
+    const bool node_left = (idx & 1) == 0;
+    if ((j < 8) == node_left) {
+      x = j < 8 ? y : moved;
+    } else {
+      x = sib[j & 7];
+      good &= x < KB_P;
+    }
+    y = kb_add(fs_warp_permute(x, rc_s, mds_h), x);
+  }
+  good &= idx == 0;  // the index addresses a leaf of this tree
+  if (j < 8) good &= y == root[j];
+  good = __all_sync(0xffffffffu, good);
+  if (lane == 0) ok[q] = good ? 1u : 0u;
+}
+
+cudaError_t merkle_verify_openings(cudaStream_t stream, const uint32_t* d_root, uint32_t log_h, const uint64_t* d_indices,
+                                   uint32_t n, const uint32_t* d_rows, uint32_t width, const uint32_t* d_paths, uint32_t* d_ok) {
+  if (n == 0) return cudaSuccess;
+  if (width < 16 || (width & 7)) return cudaErrorInvalidValue;
+  verify_openings_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_root, log_h, d_indices, n, d_rows, width, d_paths, d_ok);
+  count_launch();
+  return cudaGetLastError();
+}
+
+
 // Batched permutation / compression of explicit states (parity tests, PoW grinding building block).
 __global__ void __launch_bounds__(128) permute_states_kernel(uint32_t* states, uint64_t n, int compress) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -17,6 +17,9 @@ cudaError_t merkle_tree_from_digests(cudaStream_t stream, uint32_t* d_layers, ui
 cudaError_t merkle_open_gather(cudaStream_t stream, const uint32_t* d_mat, const uint32_t* d_layers, uint64_t h,
                                uint32_t stored_w, uint32_t full_w, const uint64_t* d_indices, uint32_t n,
                                uint32_t* d_rows, uint32_t* d_paths);
+// verifier side: ok[q] = 1 iff row q (width words) hashes, through its sibling path (log_h x 8 words, leaf level first), to root
+cudaError_t merkle_verify_openings(cudaStream_t stream, const uint32_t* d_root, uint32_t log_h, const uint64_t* d_indices,
+                                   uint32_t n, const uint32_t* d_rows, uint32_t width, const uint32_t* d_paths, uint32_t* d_ok);
 // n explicit 16-word states: permutation (compress = 0) or permutation + feed-forward (compress = 1)
 cudaError_t poseidon1_states(cudaStream_t stream, uint32_t* d_states, uint64_t n, int compress);
 // smallest w >= start whose PoW check passes for the challenger state `state` (host, 16 words); d_best: device u64

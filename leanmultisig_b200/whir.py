@@ -317,6 +317,24 @@ class Context:
         d.free(), d_layers.free()
         return out
 
+    def verify_openings(self, root, log_height: int, indices, rows, paths, elem_dim: int = 1, fold_point=None):
+        """Verifier side of Tree.open / open_fold (verify.rs:229-345): ok[q] = opening q hashes to `root`; with `fold_point`
+        also the fold of every leaf at the round's folding randomness.  One launch for all openings of a round."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        n = idx.size
+        r = _u32(rows).reshape(n, -1) if n else _u32(rows).reshape(0, 16)
+        pth = _u32(paths).reshape(n, log_height, 8)
+        ok = np.zeros(n, dtype=np.uint8)
+        pt = evals = None
+        if fold_point is not None:
+            pt = _u32(fold_point).reshape(-1, 5)
+            evals = np.empty((n, 5), dtype=np.uint32)
+        check(lib().lm_verify_openings(self.handle, _p(_u32(root)), log_height, idx.ctypes.data_as(u64p), n, _p(r), r.shape[1],
+                                       elem_dim, _p(pth), _p(pt) if pt is not None and pt.size else None,
+                                       pt.shape[0] if pt is not None else 0, ok.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                       _p(evals) if evals is not None else None))
+        return (ok.astype(bool), evals) if fold_point is not None else ok.astype(bool)
+
     def fold_msb(self, evals, r) -> np.ndarray:
         e, r = _u32(evals), _u32(r)
         dim = 5 if (e.ndim == 2 and e.shape[1] == 5) else 1
