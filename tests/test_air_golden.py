@@ -1,7 +1,7 @@
 """AIR constraint ORDER and polynomials pinned by the reference's own source text.
 
-tests/golden/air_constraints.json holds, for the execution table and the extension_op precompile, the value of every
-constraint at a random point, in `assert_zero` call order, obtained by mechanically translating and EXECUTING the
+tests/golden/air_constraints.json (execution table, extension_op precompile) and air_constraints_poseidon16.json (the
+poseidon16 precompile, tools/gen_air_golden_poseidon16.py) hold the value of every constraint at a random point, in `assert_zero` call order, obtained by mechanically translating and EXECUTING the
 reference's `Air::eval` bodies (tools/gen_air_golden.py - no formula retyped).  Constraint k is multiplied by alpha^k in the
 sumcheck (constraint_folder/normal.rs:49-62), so alpha = the k-th unit vector isolates it: the oracle (CPU tier) and the
 CUDA sessions (GPU tier) must reproduce each value, which pins the alpha-power assignment that "all constraints vanish on
@@ -18,7 +18,9 @@ import oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "air_constraints.json")))
-TABLE_ID = {"execution": 0, "extension_op": 1}
+# the poseidon16 table (100 constraints over 109 columns) comes from its own translator, tools/gen_air_golden_poseidon16.py
+GOLDEN["tables"] = GOLDEN["tables"] + json.load(open(os.path.join(ROOT, "tests", "golden", "air_constraints_poseidon16.json")))["tables"]
+TABLE_ID = {"execution": 0, "extension_op": 1, "poseidon16": 2}
 
 
 def _m(x):
@@ -43,6 +45,8 @@ def _expected(c):
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
 def test_golden_file_is_what_the_reference_source_evaluates_to():
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_air_golden.py"), "--check"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_air_golden_poseidon16.py"), "--check"],
+                          stdout=subprocess.DEVNULL)
 
 
 @pytest.mark.parametrize("t", GOLDEN["tables"], ids=lambda t: t["table"])
