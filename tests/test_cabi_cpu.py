@@ -199,3 +199,25 @@ def test_native_prover_state_matches_the_python_transcript():
                 got.append(ps.sample_in_range(op[1], op[2]))
         outs.append((got, list(ps.transcript)))
     assert outs[0] == outs[1] == outs[2]
+
+
+def test_verify_openings_rejects_bad_arguments_without_a_device():
+    """lm_verify_openings validates its arguments before touching the device (include/leanmultisig_b200.h): null handles, a row
+    width that hash_slice cannot take (sponge.rs:7-25 needs a multiple of 8, at least 16) and a fold shape that does not match."""
+    lib = L.lib()
+    u8p = C.POINTER(C.c_uint8)
+    root = np.zeros(8, dtype=np.uint32)
+    idx = np.zeros(2, dtype=np.uint64)
+    rows = np.zeros((2, 16), dtype=np.uint32)
+    paths = np.zeros((2, 3, 8), dtype=np.uint32)
+    ok = np.zeros(2, dtype=np.uint8)
+    p32 = lambda a: a.ctypes.data_as(O.u32p)  # noqa: E731
+    args = lambda ctx, width, fold_vars, evals: (  # noqa: E731
+        ctx, p32(root), 3, idx.ctypes.data_as(C.POINTER(C.c_uint64)), 2, p32(rows), width, 1, p32(paths), None, fold_vars,
+        ok.ctypes.data_as(u8p), evals)
+    assert lib.lm_verify_openings(*args(None, 16, 0, None)) != 0 and b"null" in lib.lm_last_error()
+    fake = C.c_void_p(1)  # never dereferenced: the checks below come first
+    assert lib.lm_verify_openings(*args(fake, 12, 0, None)) != 0 and b"width" in lib.lm_last_error()
+    assert lib.lm_verify_openings(*args(fake, 20, 0, None)) != 0 and b"width" in lib.lm_last_error()
+    ev = np.zeros((2, 5), dtype=np.uint32)
+    assert lib.lm_verify_openings(*args(fake, 16, 3, p32(ev))) != 0 and b"leaf" in lib.lm_last_error()
