@@ -13,5 +13,6 @@ from .logup import GkrQuotientProver, finger_print  # noqa: F401
 from .whir import Context, DeviceBuffer, ProductSumcheck, SparseStatement, Tree, WhirProver, Witness  # noqa: F401
 from .whir_config import WhirConfig  # noqa: F401
 from . import stacked_pcs  # noqa: F401,E402
+from . import verify  # noqa: F401,E402
 
 __all__ = ["Context", "DeviceBuffer", "ProductSumcheck", "Tree", "LmError", "build", "lib", "declared_symbols", "LIB_PATH"]
