@@ -119,3 +119,26 @@ def test_mle_eval_small_cases_and_fold(rng):
         term = O.ef_mul(eq[b], np.array([ev[b], 0, 0, 0, 0], dtype=np.uint32))
         tot = ((tot.astype(np.uint64) + term) % O.P).astype(np.uint32)
     assert np.array_equal(tot, full)
+
+
+def test_next_mle_on_the_boolean_cube():
+    """The reference's own test (crates/backend/poly/src/next_mle.rs:57-82, test_matrix_down_folded): on boolean inputs
+    next_mle(x, y) = [y = x + 1] in big-endian binary, with next_mle(2^n - 1, 2^n - 1) = 1 — for the oracle's folded table
+    (what the prover adds to the weights), the oracle's verifier formula and the product's verifier formula."""
+    from oracle import whir as W
+
+    from leanmultisig_b200 import verify as V
+
+    n = 5
+    one = int(O.to_monty(1))
+
+    def bools(v):  # to_big_endian_in_field
+        return [(1, 0, 0, 0, 0) if (v >> (n - 1 - k)) & 1 else (0, 0, 0, 0, 0) for k in range(n)]
+
+    for x in range(1 << n):
+        table = O.next_mle_folded(W._pts(bools(x)))
+        for y in range(1 << n):
+            expected = 1 if (x + 1 == y or (x == y == (1 << n) - 1)) else 0
+            assert table[y].tolist() == [one * expected, 0, 0, 0, 0], (x, y)
+            assert W._next_mle(bools(x), bools(y)) == (expected, 0, 0, 0, 0)
+            assert V._next_mle(bools(x), bools(y)) == (expected, 0, 0, 0, 0)
