@@ -237,3 +237,30 @@ def test_gpu_logup_larger_instance_verifies(ctx):
     vs = W.VerifierState(ps.transcript, [])
     OL.verify_generic_logup(vs, c, alphas, al_eq, 16, bytecode, {k: v[1] for k, v in traces.items()})
     assert vs.off == len(ps.transcript)
+
+
+def test_mle_of_zeros_then_ones_is_the_evaluation_of_that_slice():
+    """The reference's own test (crates/backend/poly/src/mle/mle_custom.rs:32-44): the closed form used by the Logup verifier
+    for padded tables equals the multilinear evaluation of [0; n_zeros] ++ [1; 2^n - n_zeros], for every split."""
+    from oracle import logup as OL
+    from oracle import whir as W
+
+    rng = np.random.default_rng(0)
+    for n_vars in range(0, 7):
+        for n_zeros in range(0, (1 << n_vars) + 1):
+            point = [tuple(int(x) for x in rng.integers(0, W.P, 5)) for _ in range(n_vars)]
+            values = [W.ZERO] * n_zeros + [W.ONE] * ((1 << n_vars) - n_zeros)
+            assert OL.mle_of_zeros_then_ones(n_zeros, point) == W.mle_eval_small(values, point), (n_vars, n_zeros)
+
+
+def test_mle_of_the_index_column_is_its_evaluation():
+    """mle_of_01234567_etc (crates/backend/poly/src/mle/mle_custom.rs): the closed form of the multilinear extension of
+    (0, 1, 2, ..., 2^n - 1), the implicit index column of the Logup memory / bytecode tables, against the plain evaluation."""
+    from oracle import logup as OL
+    from oracle import whir as W
+
+    rng = np.random.default_rng(1)
+    for n_vars in range(0, 8):
+        point = [tuple(int(x) for x in rng.integers(0, W.P, 5)) for _ in range(n_vars)]
+        values = [(i, 0, 0, 0, 0) for i in range(1 << n_vars)]
+        assert OL.mle_of_01234567_etc(point) == W.mle_eval_small(values, point), n_vars
