@@ -14,10 +14,26 @@ def open_all(mat, full_w, layers, indices):
     return np.stack(rows), np.stack(paths)
 
 
+class _OracleHasher:
+    """the two batched hash services of the product's level-synchronous restore (leanmultisig_b200/verify.py), on the oracle"""
+
+    def hash_leaves(self, rows):
+        return np.stack([O.hash_slice(np.ascontiguousarray(r)) for r in rows])
+
+    def compress_pairs(self, left, right):
+        return O.poseidon1_compress(np.concatenate([left, right], axis=1).astype(np.uint32))[:, :8].copy()
+
+
 def check_roundtrip(indices, rows, paths, root, log_h):
+    from leanmultisig_b200.verify import restore as product_restore
+
     pruned = prune(indices, rows, paths)
     restored = OMP.restore(pruned)
     assert restored is not None and len(restored) == len(indices)
+    again = product_restore(pruned, _OracleHasher())  # same result level by level as path by path
+    assert again is not None and len(again) == len(restored)
+    for (a, b, c), (d, e, f) in zip(again, restored):
+        assert a == d and np.array_equal(b, e) and np.array_equal(c, f)
     for q, (li, row, sibs) in enumerate(restored):
         assert li == indices[q] and np.array_equal(row, rows[q]) and np.array_equal(sibs, paths[q])
         assert O.merkle_verify(root, log_h, li, row, sibs)
@@ -48,11 +64,16 @@ def test_restore_rejects_malformed_hints(rng):
     layers = O.merkle_tree(mat, 16, 16)
     rows, paths = open_all(mat, 16, layers, [1, 6])
     pruned = prune([1, 6], rows, paths)
+    from leanmultisig_b200.verify import restore as product_restore
+
     pruned.paths[0] = (pruned.paths[0][0], pruned.paths[0][1][:-1])   # a digest is missing
-    assert OMP.restore(pruned) is None
+    assert OMP.restore(pruned) is None and product_restore(pruned, _OracleHasher()) is None
     pruned = prune([1, 6], rows, paths)
     pruned.paths[1] = (9, pruned.paths[1][1])                         # leaf index outside the tree
-    assert OMP.restore(pruned) is None
+    assert OMP.restore(pruned) is None and product_restore(pruned, _OracleHasher()) is None
+    pruned = prune([1, 6], rows, paths)
+    pruned.original_order = [0, 2]                                    # a query that points at no kept leaf
+    assert OMP.restore(pruned) is None and product_restore(pruned, _OracleHasher()) is None
     pruned = prune([1, 6], rows, paths)
     pruned.leaf_data[0] = pruned.leaf_data[0].copy()
     pruned.leaf_data[0][0] ^= 1                                       # tampered leaf: restores, but does not verify
