@@ -17,6 +17,7 @@
 //   tree_level_warp_kernel, tree_top_warp_kernel   the narrow levels, one WARP per parent (latency, not throughput)
 //   tree_levels_kernel     one CTA folds 2*T consecutive digests of a layer through up to log2(2T) levels (LM_TREE_TAIL_THREADS=1)
 //   pow_grind_umma_kernel  Fiat-Shamir proof-of-work search, one candidate per thread
+//   verify_openings_kernel  verifier side: one warp per opening hashes the leaf (hash_slice) and walks its sibling path to the root
 // Every intermediate layer is written (all layers are retained for openings).
 #include <cuda_runtime.h>
 #include <cstdint>
