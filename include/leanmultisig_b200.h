@@ -432,6 +432,13 @@ int lm_fs_state(const lm_fs* fs, uint32_t state[16], int* rate_fresh);
 int lm_whir_stir_update(lm_sumcheck* sc, const uint64_t* idx, uint32_t n_q, uint32_t gen, uint32_t num_variables,
                         const uint32_t comb[5], const uint32_t* ood_ys, const uint32_t* ood_answers, uint32_t n_ood,
                         const uint32_t* stir_evals, uint32_t total_io[5]);
+/* The sumcheck phase of a WHIR round in one call (sumcheck_prove_many_rounds, crates/backend/sumcheck/src/prove.rs:86-151, with
+ * the product computation of product_computation.rs:37-125): n_rounds times { device round (the fold by the previous challenge
+ * fused in), c1 from the running sum, absorb (c0, c1, c2) and send (c1, c2), PoW of pow_bits, sample the challenge }, then the
+ * fold by the last challenge.  total_io: the claimed sum, updated; out_challenges: n_rounds x 5.  Same transcript as the
+ * per-round entry points (lm_sc_round / lm_sc_fold_round + lm_fs_*), without the caller's round trips. */
+int lm_whir_sumcheck_rounds(lm_sumcheck* sc, lm_fs* fs, uint32_t n_rounds, uint32_t pow_bits, uint32_t total_io[5],
+                            uint32_t* out_challenges);
 /* Hand-over of the sponge to a caller-owned transcript and back (state 16 words, rate_fresh as in challenger.rs): a Rust
  * ProverState that wants the device-resident challenger of lm_gkr_prove / lm_air_prove_batched exports its Challenger into
  * an lm_fs, runs the phase, and re-imports state + the transcript words the phase appended. */

@@ -163,6 +163,7 @@ def lib() -> C.CDLL:
             "lm_sc_add_strided_eq": [vp, u64, u32, u64, u32p, u32, u32p],
             "lm_open_fold": [vp, u64p, u32, u32p, u32, u32p, u32p, u32p],
             "lm_whir_stir_update": [vp, u64p, u32, u32, u32, u32p, u32p, u32p, u32, u32p, u32p],
+            "lm_whir_sumcheck_rounds": [vp, vp, u32, u32, u32p, u32p],
             "lm_gkr_prove_hostloop": [vp, vp, u32p, u32p, u32p, u32p],
             "lm_fs_set_state": [vp, u32p, i],
             "lm_air_prove_batched": [C.POINTER(vp), u32, u32p, u32p, u32p, vp, u32p, u32p],

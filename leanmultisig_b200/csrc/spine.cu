@@ -315,6 +315,34 @@ int lm_whir_stir_update(lm_sumcheck* sc, const uint64_t* idx, uint32_t n_q, uint
   return LM_OK;
 }
 
+// sumcheck_prove_many_rounds for the product sumcheck of the opening (sumcheck/src/prove.rs:86-151 over
+// product_computation.rs:37-125), the whole phase without returning to the caller between rounds: per round the device pass
+// (first round: lm_sc_round; later: the fold by the previous challenge fused with the round, lm_sc_fold_round), c1 from the
+// running sum, absorb (c0, c1, c2), PoW, sample r, sum <- c0 + r (c1 + r c2); the last challenge is folded at the end.
+int lm_whir_sumcheck_rounds(lm_sumcheck* sc, lm_fs* fs, uint32_t n_rounds, uint32_t pow_bits, uint32_t total_io[5],
+                            uint32_t* out_challenges) {
+  if (!sc || !fs || !total_io || (n_rounds && !out_challenges))
+    return lm_internal_fail(LM_ERR_INVALID, "lm_whir_sumcheck_rounds: null argument");
+  Ef total = ef_load(total_io), pending = EF_ZERO;
+  for (uint32_t i = 0; i < n_rounds; i++) {
+    uint32_t c0w[5], c2w[5];
+    if (int rc = i ? lm_sc_fold_round(sc, pending.c, c0w, c2w) : lm_sc_round(sc, c0w, c2w)) return rc;
+    const Ef c0 = ef_load(c0w), c2 = ef_load(c2w);
+    const Ef c1 = lm::ef_sub(lm::ef_sub(total, lm::ef_add(c0, c0)), c2);  // h(0) + h(1) = sum, h(1) = c0 + c1 + c2
+    fs->add_sumcheck_polynomial({c0, c1, c2}, nullptr);
+    if (int rc = lm_fs_pow_grinding(fs, pow_bits)) return rc;
+    std::vector<Ef> r;
+    if (!fs->sample_ef(1, &r)) return lm_internal_fail(LM_ERR_INVALID, "lm_whir_sumcheck_rounds: stale rate");
+    pending = r[0];
+    total = lm::ef_add(c0, lm::ef_mul(pending, lm::ef_add(c1, lm::ef_mul(pending, c2))));
+    ef_store(out_challenges + 5 * i, pending);
+  }
+  if (n_rounds)
+    if (int rc = lm_sc_fold(sc, pending.c)) return rc;
+  ef_store(total_io, total);
+  return LM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ quotient GKR
 int lm_gkr_prove(lm_gkr* gkr, lm_fs* fs, uint32_t out_quotient[5], uint32_t* out_point, uint32_t out_claim_num[5],
                  uint32_t out_claim_den[5]) {

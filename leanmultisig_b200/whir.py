@@ -11,6 +11,7 @@ All field elements are numpy uint32 in Montgomery form, exactly as the reference
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -505,7 +506,15 @@ class WhirProver:
     @staticmethod
     def _rounds(sc: ProductSumcheck, prover_state, n_rounds: int, pow_bits: int, total):
         from . import field as F
+        from .fiat_shamir import NativeProverState
 
+        if (type(sc) is ProductSumcheck and isinstance(prover_state, NativeProverState) and n_rounds
+                and not os.environ.get("LM_WHIR_PY_ROUNDS")):
+            # the whole phase in the library's C++ spine (lm_whir_sumcheck_rounds): same transcript, no per-round return to Python
+            tot = np.ascontiguousarray(F.to_monty(total), dtype=np.uint32)
+            out = np.empty((n_rounds, 5), dtype=np.uint32)
+            check(lib().lm_whir_sumcheck_rounds(sc.handle, prover_state.handle, n_rounds, pow_bits, _p(tot), _p(out)))
+            return [F.from_monty(r) for r in out], F.from_monty(tot)
         chals, pending = [], None
         for _ in range(n_rounds):
             c0, c2 = sc.round() if pending is None else sc.fold_round(pending)

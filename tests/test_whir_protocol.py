@@ -228,11 +228,13 @@ def test_gpu_pow_grind_smallest_witness(ctx, bits):
         assert np.array_equal(a.challenger.state, b.challenger.state)
 
 
-def gpu_prove(ctx, cfg, poly, stm, actual_len=None):
-    from leanmultisig_b200.fiat_shamir import ProverState
+def gpu_prove(ctx, cfg, poly, stm, actual_len=None, native=False):
+    """native: the C++ transcript of the library (lm_fs) — the sumcheck phases then run in the spine without returning to
+    Python between rounds (lm_whir_sumcheck_rounds)"""
+    from leanmultisig_b200.fiat_shamir import NativeProverState, ProverState
     from leanmultisig_b200.whir import WhirProver
 
-    ps = ProverState(ctx)
+    ps = NativeProverState(ctx) if native else ProverState(ctx)
     prover = WhirProver(ctx, cfg)
     wit = prover.commit(ps, poly, actual_len)
     point = prover.prove(ps, to_product_statements(stm), wit)
@@ -241,9 +243,12 @@ def gpu_prove(ctx, cfg, poly, stm, actual_len=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["small", "small_next", "small_padded", "run_whir"])
+@pytest.mark.parametrize("case", ["small", "small_next", "small_padded", "run_whir", "small_native", "small_next_native",
+                                  "run_whir_native"])
 def test_gpu_prover_transcript_equals_oracle_and_verifies(ctx, case):
     rng = np.random.default_rng(21)
+    native = case.endswith("_native")
+    case = case[:-7] if native else case
     if case == "run_whir":  # the parameters of crates/whir/tests/run_whir.rs:34-56
         nv, kw = 18, dict(security_level=124, pow_bits=18, first_folding=7, subsequent_folding=4,
                           rs_domain_initial_reduction_factor=5, max_num_variables_to_send_coeffs=9, starting_log_inv_rate=2)
@@ -256,7 +261,7 @@ def test_gpu_prover_transcript_equals_oracle_and_verifies(ctx, case):
         live = (1 << nv) * 3 // 8
         poly[live:] = 0
     stm = make_statements(rng, poly, nv, n_sparse=7 if case == "run_whir" else 3, with_next=case == "small_next")
-    ps_g, point_g = gpu_prove(ctx, cfg_p, poly, stm, live)
+    ps_g, point_g = gpu_prove(ctx, cfg_p, poly, stm, live, native=native)
     ps_o, point_o = oracle_prove(cfg_o, poly, stm, live)
     assert ps_g.transcript == ps_o.transcript
     assert point_g == point_o
