@@ -221,3 +221,10 @@ def test_verify_openings_rejects_bad_arguments_without_a_device():
     assert lib.lm_verify_openings(*args(fake, 20, 0, None)) != 0 and b"width" in lib.lm_last_error()
     ev = np.zeros((2, 5), dtype=np.uint32)
     assert lib.lm_verify_openings(*args(fake, 16, 3, p32(ev))) != 0 and b"leaf" in lib.lm_last_error()
+
+
+def test_every_declared_symbol_is_accounted_for_in_the_integration_notes():
+    """INTEGRATION.md either shows the reference-side binding of an entry point or lists it among those a Rust integration does
+    not bind (section 2.7): nothing in the header is undocumented at the boundary."""
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert [s for s in L.declared_symbols() if s not in txt] == []
