@@ -97,3 +97,35 @@ def test_gpu_openings_prune_and_restore(rng):
     assert pruned.n_trailing_zeros == 64 and pruned.n_digests() < len(set(indices)) * tree.log_height
     tree.free()
     ctx.close()
+
+
+@pytest.mark.parametrize("log_h,indices,sorted_kept,kept_lens", [
+    (3, [5, 1, 3], [1, 3, 5], [2, 2, 3]),                                  # test_prune_and_restore_basic (merkle_pruning.rs:253-298)
+    (2, [1, 2], [1, 2], [1, 2]),                                           # two leaves under different parents
+    (2, [0, 1], [0, 1], [1, 1]),                                           # test_prune_adjacent_leaves (:301-325)
+    (3, list(range(8)), list(range(8)), [2, 1, 1, 1, 2, 1, 1, 1]),         # test_prune_all_leaves (:328-367), 10 digests in all
+    (2, [2], [2], [2]),                                                    # test_single_path (:370-382)
+    (3, [5, 1, 3, 1], [1, 3, 5], [2, 2, 3]),                               # test_duplicated_paths_preserved (:385-422)
+])
+def test_prune_keeps_exactly_the_digests_the_reference_counts(rng, log_h, indices, sorted_kept, kept_lens):
+    """the sibling counts the reference's tests assert path by path (the numbers are theirs), on Poseidon1 trees"""
+    h = 1 << log_h
+    mat = O.random_field(rng, (h, 16))
+    layers = O.merkle_tree(mat, 16, 16)
+    rows, paths = open_all(mat, 16, layers, indices)
+    pruned = check_roundtrip(indices, rows, paths, layers[-1], log_h)
+    assert [i for i, _ in pruned.paths] == sorted_kept
+    assert [len(s) for _, s in pruned.paths] == kept_lens
+    if indices == list(range(8)):
+        assert pruned.n_digests() == 10
+
+
+def test_trailing_zeros_stripped(rng):
+    """test_trailing_zeros_stripped (merkle_pruning.rs:425-449): leaves that all end in the same run of zeros are sent without it"""
+    mat = O.random_field(rng, (8, 16))
+    mat[:, 13:] = 0
+    mat[:, 12] = np.maximum(mat[:, 12], 1)
+    layers = O.merkle_tree(mat, 16, 16)
+    rows, paths = open_all(mat, 16, layers, [2, 5, 7])
+    pruned = check_roundtrip([2, 5, 7], rows, paths, layers[-1], 3)
+    assert pruned.n_trailing_zeros == 3 and all(len(d) == 13 for d in pruned.leaf_data)

@@ -142,3 +142,19 @@ def test_next_mle_on_the_boolean_cube():
             assert table[y].tolist() == [one * expected, 0, 0, 0, 0], (x, y)
             assert W._next_mle(bools(x), bools(y)) == (expected, 0, 0, 0, 0)
             assert V._next_mle(bools(x), bools(y)) == (expected, 0, 0, 0, 0)
+
+
+def test_sparse_eq_statement_equals_dense_eq_with_boolean_prefix():
+    """The reference's own test (crates/backend/poly/src/eq_mle.rs:1117-1136, test_compute_sparse_eval) with its values: the
+    eq table of the point (0, 1, 1, 0, 96, 85, 1, 854, 2) scaled by 789 equals the SPARSE form — selector 0b0110 = 6 over
+    the four boolean coordinates, eq over the remaining five — which is how statements with selectors enter the weights."""
+    pt = np.zeros((9, 5), dtype=np.uint32)
+    pt[:, 0] = O.to_monty(np.array([0, 1, 1, 0, 96, 85, 1, 854, 2], dtype=np.uint64))
+    scalar = np.zeros(5, dtype=np.uint32)
+    scalar[0] = int(O.to_monty(789))
+    structured = np.zeros((1 << 9, 5), dtype=np.uint32)
+    unstructured = np.zeros((1 << 9, 5), dtype=np.uint32)
+    O.weights_add_eq(structured, 6, pt[4:], scalar)
+    O.weights_add_eq(unstructured, 0, pt, scalar)
+    assert np.array_equal(structured, unstructured)
+    assert np.count_nonzero(structured[:, 0]) <= 32 and np.array_equal(O.eq_table(pt, scalar), unstructured)
