@@ -63,3 +63,24 @@ def test_golden_file_is_current():
     fresh = g.generate()
     assert fresh["cases"] == GOLD["cases"]
     assert fresh["translated_python"] == GOLD["translated_python"]
+
+
+def test_published_proof_sizes_are_consistent_with_the_schedule():
+    """README.md:35-36 of the reference publishes 338 KiB (rate 1/2) and 228 KiB (rate 1/4) for the same witness (KiB =
+    field elements x 31 bits, rec_aggregation/src/benchmark.rs:425).  The size of the WHIR opening computed from this
+    repository's schedule, leaf widths and path pruning (tools/proof_size_check.py) must leave the same positive remainder for
+    the rest of the proof at both rates for some witness size; it does at 2^24..2^25 and the published difference lies between
+    the two."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    import proof_size_check as psc
+
+    rng = np.random.default_rng(0)
+    kib = {nv: {r: psc.whir_opening_fe(nv, r, 20, rng) * 31 / 8 / 1024 for r in (1, 2)} for nv in (24, 25, 27)}
+    d24, d25 = kib[24][1] - kib[24][2], kib[25][1] - kib[25][2]
+    assert d24 < psc.PUBLISHED[1] - psc.PUBLISHED[2] < d25
+    for nv in (24, 25):
+        rest = [psc.PUBLISHED[r] - kib[nv][r] for r in (1, 2)]
+        assert 25 < rest[0] < 60 and 25 < rest[1] < 60 and abs(rest[0] - rest[1]) < 6
+    assert psc.PUBLISHED[1] - kib[27][1] < 0  # a 2^27 witness would already exceed the published size
