@@ -136,7 +136,9 @@ def run(n_sigs: int = 1550, reps: int = 5, verbose: bool = False) -> dict:
         "assumed_shapes": shapes,
         "proxy": "hot-path time of one proof on synthetic Logup-consistent tables of ASSUMED XMSS-aggregation shape (165 Poseidon "
                  "rows per signature, cycles = 8 x that, memory = 2 x cycles); witness generation / VM execution not included; the "
-                 "real metric needs the Rust caller (SURVEY 8d)",
+                 "real metric needs the Rust caller (SURVEY 8d).  The reference's published proof sizes put the real N = 1550 "
+                 "witness at 2^24 - 2^25 stacked entries (tools/proof_size_check.py): these assumed shapes are 4 - 8 x larger, "
+                 "i.e. conservative",
     }
 
 
