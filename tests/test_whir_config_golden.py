@@ -84,3 +84,8 @@ def test_published_proof_sizes_are_consistent_with_the_schedule():
         rest = [psc.PUBLISHED[r] - kib[nv][r] for r in (1, 2)]
         assert 25 < rest[0] < 60 and 25 < rest[1] < 60 and abs(rest[0] - rest[1]) < 6
     assert psc.PUBLISHED[1] - kib[27][1] < 0  # a 2^27 witness would already exceed the published size
+    # the recursion figures (README.md:53-60): each pair fits one witness size with the same remainder at both rates
+    for name, nv in (("recursion --n 1", 21), ("recursion --n 4", 23)):
+        a, b = psc.PUBLISHED_PAIRS[name]
+        ra, rb = (a - psc.whir_opening_fe(nv, 1, 20, rng) * 31 / 8 / 1024, b - psc.whir_opening_fe(nv, 2, 20, rng) * 31 / 8 / 1024)
+        assert 20 < ra < 40 and 20 < rb < 40 and abs(ra - rb) < 4, (name, ra, rb)

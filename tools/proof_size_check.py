@@ -17,6 +17,9 @@ from leanmultisig_b200.merkle_pruning import lca_level
 from leanmultisig_b200.whir_config import WhirConfig
 
 PUBLISHED = {1: 338, 2: 228}  # KiB, proven regime (Johnson bound), README.md:35-36
+# all pairs (rate 1/2, rate 1/4) the README publishes for the proven regime: xmss (README.md:35-36), recursion n = 1..4 (:53-60)
+PUBLISHED_PAIRS = {"xmss --n-signatures 1550": (338, 228), "recursion --n 1": (278, 188), "recursion --n 2": (293, 194),
+                   "recursion --n 3": (312, 203), "recursion --n 4": (308, 206)}
 
 
 def pruned_digests(idx, h):
@@ -53,9 +56,14 @@ def whir_opening_fe(nv, rate, trials, rng):
 if __name__ == "__main__":
     trials = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.default_rng(0)
-    print("stacked 2^n | opening KiB at rate 1/2, 1/4 | difference (published: %d) | left for the rest of the proof at 1/2, 1/4"
-          % (PUBLISHED[1] - PUBLISHED[2]))
-    for nv in range(22, 29):
-        kib = {r: whir_opening_fe(nv, r, trials, rng) * 31 / 8 / 1024 for r in (1, 2)}
-        print(f"   n = {nv}   |  {kib[1]:6.1f}  {kib[2]:6.1f}         |  {kib[1] - kib[2]:6.1f}                   |"
-              f"  {PUBLISHED[1] - kib[1]:6.1f}  {PUBLISHED[2] - kib[2]:6.1f}")
+    print("stacked 2^n | opening KiB at rate 1/2, 1/4 | difference")
+    kib = {}
+    for nv in range(19, 29):
+        kib[nv] = {r: whir_opening_fe(nv, r, trials, rng) * 31 / 8 / 1024 for r in (1, 2)}
+        print(f"   n = {nv}   |  {kib[nv][1]:6.1f}  {kib[nv][2]:6.1f}         |  {kib[nv][1] - kib[nv][2]:6.1f}")
+    print()
+    print("published pair (KiB at 1/2, 1/4; difference) -> witness sizes that leave the SAME positive remainder at both rates")
+    for name, (a, b) in PUBLISHED_PAIRS.items():
+        fits = [(nv, a - kib[nv][1], b - kib[nv][2]) for nv in kib
+                if a - kib[nv][1] > 0 and b - kib[nv][2] > 0 and abs((a - kib[nv][1]) - (b - kib[nv][2])) < 6]
+        print(f"   {name:26s} {a} {b} ({a - b:3d}) -> " + ", ".join(f"2^{nv}: {x:.1f} / {y:.1f} KiB left" for nv, x, y in fits))
