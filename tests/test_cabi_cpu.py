@@ -228,3 +228,13 @@ def test_every_declared_symbol_is_accounted_for_in_the_integration_notes():
     not bind (section 2.7): nothing in the header is undocumented at the boundary."""
     txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert [s for s in L.declared_symbols() if s not in txt] == []
+
+
+def test_public_header_is_plain_c():
+    """the boundary is a C ABI: include/leanmultisig_b200.h must compile as C11 (what cgo / bindgen / ctypes-style FFI consume)
+    and as C++17, with nothing but <stdint.h> / <stddef.h> types in the signatures"""
+    hdr = os.path.join(ROOT, "include", "leanmultisig_b200.h")
+    assert subprocess.call(["gcc", "-fsyntax-only", "-x", "c", "-std=c11", "-Wall", "-Werror", hdr]) == 0
+    assert subprocess.call(["g++", "-fsyntax-only", "-x", "c++", "-std=c++17", hdr]) == 0
+    txt = open(hdr).read()
+    assert "torch" not in txt and "at::" not in txt and "std::" not in txt
