@@ -236,5 +236,7 @@ def test_public_header_is_plain_c():
     hdr = os.path.join(ROOT, "include", "leanmultisig_b200.h")
     assert subprocess.call(["gcc", "-fsyntax-only", "-x", "c", "-std=c11", "-Wall", "-Werror", hdr]) == 0
     assert subprocess.call(["g++", "-fsyntax-only", "-x", "c++", "-std=c++17", hdr]) == 0
-    txt = open(hdr).read()
-    assert "torch" not in txt and "at::" not in txt and "std::" not in txt
+    import re
+
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)  # declarations only: comments may mention the caller's plumbing
+    assert "torch" not in code and "at::" not in code and "std::" not in code
