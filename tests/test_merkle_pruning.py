@@ -129,3 +129,19 @@ def test_trailing_zeros_stripped(rng):
     rows, paths = open_all(mat, 16, layers, [2, 5, 7])
     pruned = check_roundtrip([2, 5, 7], rows, paths, layers[-1], 3)
     assert pruned.n_trailing_zeros == 3 and all(len(d) == 13 for d in pruned.leaf_data)
+
+
+def test_prune_restore_random_query_sets(rng):
+    """120 random (height, query multiset) cases incl. duplicates, neighbours and full coverage: prune -> oracle restore and
+    prune -> product (level-synchronous) restore both return the original openings in the original order"""
+    for case in range(120):
+        log_h = int(rng.integers(1, 9))
+        h = 1 << log_h
+        n_q = int(rng.integers(1, min(3 * h, 40) + 1))
+        indices = [int(i) for i in rng.integers(0, h, n_q)]
+        if case % 7 == 0:
+            indices = list(range(h))[: max(1, n_q)]
+        mat = O.random_field(rng, (h, 16))
+        layers = O.merkle_tree(mat, 16, 16)
+        rows, paths = open_all(mat, 16, layers, indices)
+        check_roundtrip(indices, rows, paths, layers[-1], log_h)
